@@ -1,0 +1,267 @@
+"""ctypes binding of the Tier A CPU oracle (oracle/c/vslam_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/c/vslam_oracle.h.  Imported by tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs; never by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libvslam_oracle.so")
+
+KP = np.dtype([("x", "<f4"), ("y", "<f4"), ("response", "<f4")])
+FEATURE = np.dtype([("x", "<f4"), ("y", "<f4"), ("row", "<i4"), ("col", "<i4"), ("index", "<i4"),
+                    ("desc", "u1", (32,))])
+MATCH = np.dtype([("index_left", "<i4"), ("index_right", "<i4"), ("xl", "<f4"), ("yl", "<f4"), ("xr", "<f4"),
+                  ("yr", "<f4"), ("distance", "<i4"), ("epipolar_offset", "<i4"), ("cam", "<f8", (3,))])
+TRACKED = np.dtype([("row", "<i4"), ("col", "<i4"), ("has_previous", "<i4"), ("_pad", "<i4"),
+                    ("disparity", "<f8"), ("distance", "<f8")])
+RECT = np.dtype([("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4")])
+
+
+class StereoCamera(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("bx", C.c_double)]
+
+
+class AlignerProblem(C.Structure):
+    _fields_ = [("n", C.c_int), ("moving", C.c_void_p), ("fixed", C.c_void_p), ("omega", C.c_void_p),
+                ("wt", C.c_void_p), ("K", C.c_double * 9), ("baseline", C.c_double * 3), ("rows", C.c_int),
+                ("cols", C.c_int), ("min_depth", C.c_double), ("kernel", C.c_double)]
+
+
+class LinearSystem(C.Structure):
+    _fields_ = [("H", C.c_double * 36), ("b", C.c_double * 6), ("total_error", C.c_double), ("inliers", C.c_int),
+                ("outliers", C.c_int)]
+
+
+def build(force: bool = False) -> str:
+    src = [os.path.join(_HERE, "c", "vslam_oracle.c"), os.path.join(_HERE, "c", "vslam_oracle.h"),
+           os.path.join(_HERE, "data", "orb_pattern_31.inc")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.orc_threshold_proposal.restype = C.c_double
+        _lib.orc_threshold_proposal.argtypes = [C.c_double, C.c_int] + [C.c_double] * 5
+        _lib.orc_triangulation_threshold.restype = C.c_double
+        _lib.orc_triangulation_threshold.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double]
+        _lib.orc_adjust_thresholds.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_double] * 5
+        _lib.orc_stereo_compute.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_one_round.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]
+        _lib.orc_converge.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_triangulate.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _img(a):
+    a = np.asarray(a)
+    assert a.dtype == np.uint8 and a.ndim == 2 and a.strides[1] == 1
+    return a
+
+
+# ------------------------------------------------------------------------------------------------
+def detector_regions(rows, cols, nv, nh):
+    out = np.zeros(nv * nh, RECT)
+    lib().orc_detector_regions(rows, cols, nv, nh, _p(out))
+    return out
+
+
+def bin_grid(rows, cols, bin_size):
+    rb, cb = C.c_int(), C.c_int()
+    lib().orc_bin_grid(rows, cols, bin_size, C.byref(rb), C.byref(cb))
+    return rb.value, cb.value
+
+
+def fast_detect(img, threshold, cap=None):
+    img = _img(img)
+    h, w = img.shape
+    cap = cap or (w * h // 4 + 16)
+    out = np.zeros(cap, KP)
+    n = lib().orc_fast_detect(_p(img), img.strides[0], w, h, int(threshold), _p(out), cap)
+    assert n <= cap
+    return out[:n].copy()
+
+
+def detect_keypoints(img, nv, nh, thresholds, cap=None):
+    """-> (keypoints in reference order, raw count per region)"""
+    img = _img(img)
+    h, w = img.shape
+    cap = cap or (w * h // 4 + 16)
+    out = np.zeros(cap, KP)
+    counts = np.zeros(nv * nh, np.int32)
+    thr = np.ascontiguousarray(thresholds, np.float64)
+    n = lib().orc_detect_keypoints(_p(img), img.strides[0], h, w, nv, nh, _p(thr), _p(out), cap, _p(counts))
+    assert n <= cap
+    return out[:n].copy(), counts
+
+
+def adjust_thresholds(thresholds, counts_l, counts_r, target, tolerance, max_change, thr_min, thr_max):
+    thr = np.ascontiguousarray(thresholds, np.float64).copy()
+    cl = np.ascontiguousarray(counts_l, np.int32)
+    cr = np.ascontiguousarray(counts_r, np.int32)
+    lib().orc_adjust_thresholds(_p(thr), len(thr), _p(cl), _p(cr), float(target), float(tolerance),
+                                float(max_change), float(thr_min), float(thr_max))
+    return thr
+
+
+def gauss7_kernel():
+    k = np.zeros(7, np.float32)
+    lib().orc_gauss7_kernel(_p(k))
+    return k
+
+
+def gauss7_u8(img):
+    img = _img(img)
+    h, w = img.shape
+    out = np.zeros((h, w), np.uint8)
+    lib().orc_gauss7_u8(_p(img), img.strides[0], w, h, _p(out), w)
+    return out
+
+
+def orb_compute(img, kps, blurred=None):
+    """-> (filtered keypoints, descriptors [n,32])"""
+    img = _img(img)
+    h, w = img.shape
+    kps = np.ascontiguousarray(kps, KP).copy()
+    desc = np.zeros((max(len(kps), 1), 32), np.uint8)
+    if blurred is not None:
+        blurred = _img(blurred)
+        n = lib().orc_orb_compute(_p(img), img.strides[0], w, h, _p(blurred), blurred.strides[0], _p(kps), len(kps),
+                                  _p(desc))
+    else:
+        n = lib().orc_orb_compute(_p(img), img.strides[0], w, h, None, 0, _p(kps), len(kps), _p(desc))
+    return kps[:n].copy(), desc[:n].copy()
+
+
+def hamming256(a, b):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_hamming256(_p(a), _p(b))
+
+
+def triangulation_threshold(localizing, n_left, target, max_dist):
+    return lib().orc_triangulation_threshold(int(bool(localizing)), int(n_left), int(target), float(max_dist))
+
+
+def make_features(kps, desc):
+    kps = np.ascontiguousarray(kps, KP)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    out = np.zeros(len(kps), FEATURE)
+    if len(kps):
+        lib().orc_make_features(_p(kps), _p(desc), len(kps), _p(out))
+    return out
+
+
+def triangulate(cam: StereoCamera, xl, yl, xr, yr):
+    out = np.zeros(3)
+    lib().orc_triangulate(C.byref(cam), xl, yl, xr, yr, _p(out))
+    return out
+
+
+def stereo_compute(fl, fr, cam: StereoCamera, max_distance, min_disparity, max_epipolar_offset, enable_binning,
+                   bin_size, rows, cols, tracked=None):
+    """-> dict(matches, winners, remaining_left, remaining_right)"""
+    fl = np.ascontiguousarray(fl, FEATURE).copy()
+    fr = np.ascontiguousarray(fr, FEATURE).copy()
+    nl, nr = C.c_int(len(fl)), C.c_int(len(fr))
+    tracked = np.zeros(0, TRACKED) if tracked is None else np.ascontiguousarray(tracked, TRACKED)
+    matches = np.zeros(max(len(fl), 1), MATCH)
+    winners = np.zeros(max(len(fl), 1) + len(tracked) + 1, np.int32)
+    nw = C.c_int()
+    n = lib().orc_stereo_compute(_p(fl), C.byref(nl), _p(fr), C.byref(nr), C.byref(cam), float(max_distance),
+                                 float(min_disparity), int(max_epipolar_offset), int(bool(enable_binning)),
+                                 int(bin_size), int(rows), int(cols), _p(tracked), len(tracked), _p(matches),
+                                 _p(winners), C.byref(nw))
+    return {"matches": matches[:n].copy(), "winners": winners[:nw.value].copy(),
+            "remaining_left": fl[:nl.value].copy(), "remaining_right": fr[:nr.value].copy()}
+
+
+# ------------------------------------------------------------------------------------------------
+class Aligner:
+    """Holds the SoA inputs of one alignment problem (StereoUVAligner / UVDAligner::initialize output)."""
+
+    def __init__(self, kind, moving, fixed, omega, wt, K, baseline, rows, cols, min_depth, kernel):
+        self.kind = {"stereouv": 0, "uvd": 1}[kind] if isinstance(kind, str) else int(kind)
+        self.moving = np.ascontiguousarray(moving, np.float64)
+        self.fixed = np.ascontiguousarray(fixed, np.float64)
+        self.omega = np.ascontiguousarray(omega, np.float64)
+        self.wt = np.ascontiguousarray(wt, np.float64)
+        n = len(self.moving)
+        assert self.fixed.shape == (n, 4 if self.kind == 0 else 3)
+        assert self.omega.shape == ((n,) if self.kind == 0 else (n, 2))
+        p = AlignerProblem()
+        p.n = n
+        p.moving, p.fixed, p.omega, p.wt = (a.ctypes.data for a in (self.moving, self.fixed, self.omega, self.wt))
+        p.K = (C.c_double * 9)(*np.asarray(K, np.float64).ravel())
+        p.baseline = (C.c_double * 3)(*np.asarray(baseline, np.float64).ravel())
+        p.rows, p.cols, p.min_depth, p.kernel = int(rows), int(cols), float(min_depth), float(kernel)
+        self.p = p
+        self.errors = np.zeros(n, np.float64)
+        self.inliers = np.zeros(n, np.uint8)
+
+    @staticmethod
+    def _sys(s):
+        return {"H": np.array(s.H).reshape(6, 6), "b": np.array(s.b), "total_error": s.total_error,
+                "inliers": s.inliers, "outliers": s.outliers}
+
+    def linearize(self, T, ignore_outliers=False):
+        T = np.ascontiguousarray(T, np.float64).reshape(12)
+        s = LinearSystem()
+        fn = lib().orc_stereouv_linearize if self.kind == 0 else lib().orc_uvd_linearize
+        fn(C.byref(self.p), _p(T), int(bool(ignore_outliers)), C.byref(s), _p(self.errors), _p(self.inliers))
+        return self._sys(s)
+
+    def one_round(self, T, damping, ignore_outliers=False):
+        T = np.ascontiguousarray(T, np.float64).reshape(12).copy()
+        s = LinearSystem()
+        lib().orc_one_round(self.kind, C.byref(self.p), float(damping), _p(T), int(bool(ignore_outliers)),
+                            C.byref(s), _p(self.errors), _p(self.inliers))
+        return T.reshape(3, 4), self._sys(s)
+
+    def converge(self, T0, damping, error_delta, max_iterations, min_inliers):
+        T = np.ascontiguousarray(T0, np.float64).reshape(12).copy()
+        s = LinearSystem()
+        info = np.zeros(36)
+        rounds = C.c_int()
+        ok = lib().orc_converge(self.kind, C.byref(self.p), float(damping), float(error_delta), int(max_iterations),
+                                int(min_inliers), _p(T), C.byref(s), _p(self.errors), _p(self.inliers), _p(info),
+                                C.byref(rounds))
+        out = self._sys(s)
+        out.update(T=T.reshape(3, 4), converged=bool(ok), rounds=rounds.value, information=info.reshape(6, 6))
+        return out
+
+
+def solve6(A, b):
+    A = np.ascontiguousarray(A, np.float64)
+    b = np.ascontiguousarray(b, np.float64)
+    x = np.zeros(6)
+    lib().orc_solve6_fullpiv(_p(A), _p(b), _p(x))
+    return x
+
+
+def v2t(v):
+    v = np.ascontiguousarray(v, np.float64)
+    T = np.zeros(12)
+    lib().orc_v2t(_p(v), _p(T))
+    return T.reshape(3, 4)
