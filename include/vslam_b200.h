@@ -1,0 +1,264 @@
+/*
+ * vslam_b200.h -- C ABI of libvslam_b200.so: the B200-native (sm_100a) replacement of the per-frame hot
+ * path of Ssellu/vslam-pose-estimation-framework (ProSLAM fork):
+ *
+ *   stereo framepoint generation   src/framepoint_generation/{base,stereo}_framepoint_generator.cpp
+ *   projective aligner linearise   src/aligners/{stereouv,uvd}_aligner.cpp
+ *
+ * Every entry point cites the reference interface it replaces (file:line relative to the reference root).
+ * The reference has no FFI: its boundary is two abstract C++ classes injected by raw pointer
+ * (src/position_tracking/pose_tracker_3d.h:36-37, src/system/slam_assembly.cpp:62-76).  The C++14 adapters
+ * in adapters/ derive from those classes and call ONLY the functions below; INTEGRATION.md shows the wiring.
+ *
+ * Conventions: opaque handles; plain pointers and sizes; caller-owned HOST buffers unless a name says
+ * "device"; int status (0 ok, <0 error, message via vslam_last_error()); no exceptions cross the boundary;
+ * one handle = one CUDA device + one stream, not thread-safe per handle; there is NO CPU fallback --
+ * every call that computes fails with VSLAM_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef VSLAM_B200_H
+#define VSLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSLAM_OK 0
+#define VSLAM_ERR_INVALID_ARGUMENT (-1)
+#define VSLAM_ERR_CUDA (-2)
+#define VSLAM_ERR_CAPACITY (-3) /* more keypoints / points than the handle was created for */
+#define VSLAM_ERR_STATE (-4)    /* call order violated (e.g. compute before initialize) */
+
+#define VSLAM_MAX_DETECTOR_REGIONS 64
+#define VSLAM_DESCRIPTOR_BYTES 32 /* SRRG_PROSLAM_DESCRIPTOR_SIZE_BITS = 256, CMakeLists.txt:32 */
+
+/* message of the last failing call on the calling thread */
+const char* vslam_last_error(void);
+/* "vslam_b200 <version> sm_100a" ; number of usable CUDA devices (0 when none: nothing will compute) */
+const char* vslam_version(void);
+int vslam_device_count(void);
+
+/* pinned host memory for the caller-owned buffers of the batched calls (optional; any host pointer works,
+ * pinned ones make the copies asynchronous) */
+int vslam_host_alloc(void** ptr, size_t bytes);
+int vslam_host_free(void* ptr);
+
+/* ===================================================================================================
+ * Stereo framepoint generation
+ * =================================================================================================*/
+
+typedef struct vslam_fpg vslam_fpg;
+
+/* The reference's parameter structs, unchanged in meaning:
+ * BaseFramePointGeneratorParameters / StereoFramePointGeneratorParameters (src/types/parameters.h:161-238),
+ * plus what configure() reads from the cameras (base_framepoint_generator.cpp:169-173,
+ * stereo_framepoint_generator.cpp:26-38). */
+typedef struct {
+  int32_t rows, cols;                                /* _camera_left->numberOfImageRows/Cols */
+  double target_number_of_keypoints_tolerance;
+  int32_t detector_threshold_minimum;
+  int32_t detector_threshold_maximum;
+  double detector_threshold_maximum_change;
+  int32_t number_of_detectors_vertical;
+  int32_t number_of_detectors_horizontal;
+  int32_t enable_keypoint_binning;
+  int32_t bin_size_pixels;
+  double maximum_matching_distance_triangulation;
+  double minimum_disparity_pixels;
+  int32_t maximum_epipolar_search_offset_pixels;
+  double fx, fy, cx, cy;                             /* _camera_right->cameraMatrix() */
+  double bx;                                         /* _camera_right->baselineHomogeneous()(0), < 0 */
+  /* capacities of the device-resident state (not reference parameters) */
+  int32_t max_keypoints_per_image;                   /* descriptor-valid keypoints per image; 0 -> default */
+  int32_t max_batch;                                 /* stereo pairs per batched call; 0 -> 1 */
+} vslam_fpg_config;
+
+/* cv::KeyPoint as the reference sees it after computeDescriptors (size 7, angle -1, octave 0, class_id -1
+ * are implied: cv::FastFeatureDetector defaults) */
+typedef struct {
+  float x, y;      /* pt */
+  float response;  /* FAST corner score */
+} vslam_keypoint;
+
+/* what StereoFramePointGenerator::compute hands to Frame::createFramepoint
+ * (stereo_framepoint_generator.cpp:364-368; src/types/frame_point.cpp:8-24) */
+typedef struct {
+  int32_t index_left, index_right; /* rows of keypointsLeft()/descriptorsLeft() resp. Right (reference order) */
+  float xl, yl, xr, yr;            /* keypoint.pt of both features */
+  int32_t distance;                /* descriptor_distance_triangulation (Hamming) */
+  int32_t epipolar_offset;         /* setEpipolarOffset */
+  double camera[3];                /* getPointInLeftCamera */
+} vslam_framepoint;
+
+/* a point already in frame->points() when compute() starts (stereo_framepoint_generator.cpp:147-155) */
+typedef struct {
+  int32_t row, col;       /* FramePoint::row / col */
+  int32_t has_previous;   /* previous() != nullptr */
+  int32_t reserved;
+  double disparity;       /* disparityPixels() */
+  double distance;        /* descriptorDistanceTriangulation() */
+} vslam_tracked_point;
+
+/* StereoFramePointGenerator ctor + configure(): stereo_framepoint_generator.cpp:7-60,
+ * base_framepoint_generator.cpp:165-329.  Fails like the reference on a non-positive baseline (:29-34). */
+int vslam_fpg_create(const vslam_fpg_config* config, int device, vslam_fpg** out);
+int vslam_fpg_destroy(vslam_fpg* h);
+
+/* derived configuration (base_framepoint_generator.cpp:293-312): regions as x,y,w,h quadruples */
+int vslam_fpg_info(const vslam_fpg* h, int32_t* n_regions, int32_t* regions_xywh, int32_t* rows_bin,
+                   int32_t* cols_bin, int32_t* target_number_of_keypoints);
+
+/* detector thresholds, one per region, row-major (FastDetector::getThreshold/setThreshold, :16-22) */
+int vslam_fpg_get_thresholds(const vslam_fpg* h, double* thresholds);
+int vslam_fpg_set_thresholds(vslam_fpg* h, const double* thresholds);
+
+/* StereoFramePointGenerator::initialize(frame, extract_features=true), :73-133:
+ * detectKeypoints(L), detectKeypoints(R), adjustDetectorThresholds(), computeDescriptors(L/R), triangulation
+ * distance for frame->status() (localizing != 0 <=> Frame::Localizing), setFeatures(L/R).
+ * left/right: rows x cols uint8, `stride` bytes between rows.  Results stay on the device;
+ * n_left/n_right = keypointsLeft()/Right().size() after the call. */
+int vslam_fpg_initialize(vslam_fpg* h, const uint8_t* left, const uint8_t* right, size_t stride, int localizing,
+                         int32_t* n_left, int32_t* n_right);
+
+/* frame->keypointsLeft()/descriptorsLeft() (side 0) or ...Right() (side 1) after initialize, in the
+ * reference's order (detector region by region, row-major inside a region).  descriptors: n x 32 bytes. */
+int vslam_fpg_get_features(vslam_fpg* h, int side, vslam_keypoint* keypoints, uint8_t* descriptors,
+                           int32_t capacity, int32_t* n);
+
+/* raw FAST keypoint count per detector region of the last initialize (what drives the threshold
+ * controller, base_framepoint_generator.cpp:382), and _current_maximum_descriptor_distance_triangulation */
+int vslam_fpg_get_detection_stats(vslam_fpg* h, int32_t* counts_left, int32_t* counts_right,
+                                  double* matching_distance);
+
+/* StereoFramePointGenerator::compute(frame), :135-462 (without the dead use_matches block :168-273).
+ * tracked: the points already in frame->points().  framepoints: the points compute() appends to
+ * frame->points(), in order (bin winners without previous(), row-major over bins; every match in emission
+ * order when binning is off).  n_matches (optional) = number_of_new_points before binning. */
+int vslam_fpg_compute(vslam_fpg* h, const vslam_tracked_point* tracked, int32_t n_tracked,
+                      vslam_framepoint* framepoints, int32_t capacity, int32_t* n_framepoints,
+                      int32_t* n_matches);
+
+/* all new stereo matches of the last compute in emission order (framepoints_new, :163,397) */
+int vslam_fpg_get_matches(vslam_fpg* h, vslam_framepoint* matches, int32_t capacity, int32_t* n);
+
+/* getTimeConsumptionSeconds_{keypoint_detection, descriptor_extraction, point_triangulation}
+ * (base_framepoint_generator.h:232-233, stereo_framepoint_generator.h:81): accumulated DEVICE seconds,
+ * measured with CUDA events when profiling is enabled. */
+int vslam_fpg_set_profiling(vslam_fpg* h, int enabled);
+int vslam_fpg_get_time_consumption(vslam_fpg* h, double* keypoint_detection, double* descriptor_extraction,
+                                   double* point_triangulation);
+
+/* ---- batched form: n_pairs INDEPENDENT stereo pairs (BASELINE.json config 3) -------------------------
+ * Every pair is processed exactly like initialize()+compute() on a fresh generator whose thresholds are
+ * the handle's current ones (they are not updated by batched calls) and with no tracked points.
+ * Images: pair i at left + i*pair_stride (rows x cols, row stride `stride`). */
+int vslam_fpg_batch_upload(vslam_fpg* h, int32_t n_pairs, const uint8_t* left, const uint8_t* right,
+                           size_t stride, size_t pair_stride);
+/* all kernels of the path, device-resident inputs and outputs, asynchronous on the handle's stream */
+int vslam_fpg_batch_run(vslam_fpg* h, int32_t n_pairs, int localizing);
+/* framepoints of pair i at framepoints + i*capacity_per_pair; n_framepoints[i], n_matches[i] (optional),
+ * n_left[i], n_right[i] (optional).  Synchronises the stream. */
+int vslam_fpg_batch_download(vslam_fpg* h, int32_t n_pairs, vslam_framepoint* framepoints,
+                             int32_t capacity_per_pair, int32_t* n_framepoints, int32_t* n_matches,
+                             int32_t* n_left, int32_t* n_right);
+/* upload + run + download with copy/compute overlap: the end-to-end call */
+int vslam_fpg_batch_process(vslam_fpg* h, int32_t n_pairs, const uint8_t* left, const uint8_t* right,
+                            size_t stride, size_t pair_stride, int localizing, vslam_framepoint* framepoints,
+                            int32_t capacity_per_pair, int32_t* n_framepoints);
+/* per-pair features of the last batched run (reference order), for parity checks */
+int vslam_fpg_batch_get_features(vslam_fpg* h, int32_t pair, int side, vslam_keypoint* keypoints,
+                                 uint8_t* descriptors, int32_t capacity, int32_t* n);
+
+/* the handle's cudaStream_t (as void*) and a stream synchronise, for callers that time with CUDA events */
+void* vslam_fpg_stream(vslam_fpg* h);
+int vslam_fpg_synchronize(vslam_fpg* h);
+/* number of kernels the handle has launched so far */
+int64_t vslam_fpg_launch_count(const vslam_fpg* h);
+
+/* debug / parity taps on device intermediates of pair `pair`, image `side`:
+ * FAST keypoint bitmask before the 31 px descriptor border filter (rows x ceil(cols/32) words, bit x%32 of
+ * word x/32), and the 7x7 sigma 2 blurred image (rows x cols) cv::ORB::compute samples. */
+int vslam_fpg_debug_keypoint_mask(vslam_fpg* h, int32_t pair, int side, uint32_t* words);
+int vslam_fpg_debug_blurred(vslam_fpg* h, int32_t pair, int side, uint8_t* image);
+
+/* BaseFramePointGenerator threshold controller for one region (base_framepoint_generator.cpp:377-415),
+ * exposed so hosts that batch independent sequences can run it themselves */
+double vslam_threshold_proposal(double threshold, int32_t n_keypoints, double target_per_detector,
+                                double tolerance, double maximum_change, double threshold_minimum,
+                                double threshold_maximum);
+
+/* ===================================================================================================
+ * Frame aligners (pose optimisation previous -> current)
+ * =================================================================================================*/
+
+typedef struct vslam_aligner vslam_aligner;
+
+#define VSLAM_ALIGNER_STEREO_UV 0 /* src/aligners/stereouv_aligner.cpp */
+#define VSLAM_ALIGNER_UVD 1       /* src/aligners/uvd_aligner.cpp */
+
+/* AlignerParameters (src/types/parameters.h:66-95) + BaseAligner thresholds (base_aligner.h:62-63) */
+typedef struct {
+  double error_delta_for_convergence;
+  double maximum_error_kernel;
+  double damping;
+  int32_t maximum_number_of_iterations;
+  int32_t minimum_number_of_inliers;
+} vslam_aligner_parameters;
+
+typedef struct {
+  double H[36];            /* _H, row-major */
+  double b[6];             /* _b */
+  double total_error;      /* _total_error */
+  int32_t number_of_inliers;
+  int32_t number_of_outliers;
+} vslam_linear_system;
+
+int vslam_aligner_create(int kind, int32_t max_points, int device, vslam_aligner** out);
+int vslam_aligner_destroy(vslam_aligner* h);
+
+/* what StereoUVAligner::initialize (:10-69) / UVDAligner::initialize (:11-74) leave in their buffers:
+ * moving  n x 3  (_moving)
+ * fixed   n x 4  (uL,vL,uR,vR)  StereoUV  |  n x 3 (u,v,depth) UVD            (_fixed)
+ * omega   n      scalar of the scalar*I4 information matrix, StereoUV
+ *         n x 2  (w_uv, w_depth) of diag(w_uv, w_uv, w_depth), UVD              (_information_matrix_vector)
+ * weights_translation n                                                         (_weights_translation)
+ * K 3x3 row-major (_camera_calibration_matrix); baseline[3] (_offset_camera_right, ignored for UVD);
+ * rows/cols (_number_of_rows/cols_image); minimum_depth (_minimum_reliable_depth_meters). */
+int vslam_aligner_upload(vslam_aligner* h, int32_t n, const double* moving, const double* fixed,
+                         const double* omega, const double* weights_translation, const double K[9],
+                         const double baseline[3], int32_t rows, int32_t cols, double minimum_depth);
+
+/* BaseAligner::linearize(ignore_outliers): stereouv_aligner.cpp:72-187 / uvd_aligner.cpp:77-171.
+ * previous_to_current: row-major 3x4 [R|t]. */
+int vslam_aligner_linearize(vslam_aligner* h, const double previous_to_current[12], int ignore_outliers,
+                            double maximum_error_kernel, vslam_linear_system* system);
+/* _errors / _inliers of the last linearize (either may be NULL) */
+int vslam_aligner_download(vslam_aligner* h, double* errors, uint8_t* inliers);
+
+/* BaseAligner::oneRound: :190-207 / :174-191 (linearize, damping, 6x6 full-pivot LU, v2t, re-orthonormalise) */
+int vslam_aligner_one_round(vslam_aligner* h, const vslam_aligner_parameters* parameters, int ignore_outliers,
+                            double previous_to_current[12], vslam_linear_system* system);
+/* BaseAligner::converge: :210-264 / :194-248.  information[36] = _information_matrix (may be NULL). */
+int vslam_aligner_converge(vslam_aligner* h, const vslam_aligner_parameters* parameters,
+                           double previous_to_current[12], vslam_linear_system* system, double* information,
+                           int32_t* has_system_converged, int32_t* number_of_rounds);
+
+/* asynchronous linearize without the host read-back (for callers that time the kernel with CUDA events) */
+int vslam_aligner_linearize_async(vslam_aligner* h, const double previous_to_current[12], int ignore_outliers,
+                                  double maximum_error_kernel);
+int vslam_aligner_read_system(vslam_aligner* h, vslam_linear_system* system);
+
+void* vslam_aligner_stream(vslam_aligner* h);
+int vslam_aligner_synchronize(vslam_aligner* h);
+int64_t vslam_aligner_launch_count(const vslam_aligner* h);
+
+/* host-side 6x6 helpers used by one_round (exposed for tests): complete-pivoting LU solve; srrg_core::v2t */
+void vslam_solve6(const double A[36], const double rhs[6], double x[6]);
+void vslam_v2t(const double v[6], double T[12]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSLAM_B200_H */

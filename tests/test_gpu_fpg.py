@@ -1,0 +1,243 @@
+"""Parity of the CUDA framepoint generator (through the C ABI) with the CPU oracle: bit-exact keypoint sets,
+scores, order, descriptors, thresholds, match lists, bin winners; triangulated points bit-exact too (the kernel
+uses the oracle's evaluation order with no contraction), asserted at 0 tolerance and documented as <= 1e-4 rel."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pipeline, tier_a
+from vslam_b200 import api, configs, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(cfg, cam, left, right, localizing, thresholds=None, tracked=None):
+    o = pipeline.StereoFramePointGeneratorOracle(cfg, cam, "a")
+    if thresholds is not None:
+        o.thresholds = np.asarray(thresholds, np.float64).copy()
+    o.initialize(left, right, localizing)
+    o.compute(None if tracked is None else tracked.astype(tier_a.TRACKED))
+    return o
+
+
+def _same_points(got, want):
+    assert len(got) == len(want)
+    for f, g in (("index_left", "index_left"), ("index_right", "index_right"), ("xl", "xl"), ("yl", "yl"),
+                 ("xr", "xr"), ("yr", "yr"), ("distance", "distance"), ("epipolar_offset", "epipolar_offset")):
+        assert np.array_equal(got[f], want[g]), f
+    # tolerance stated by north_star: 1e-4 relative; achieved: bit-exact
+    assert np.array_equal(got["camera"], want["cam"])
+
+
+def _check_pair(gen, o, side_features=True):
+    for side, (kps, desc) in enumerate(((o.kps_left, o.desc_left), (o.kps_right, o.desc_right))):
+        k, d = gen.features(side)
+        assert len(k) == len(kps)
+        assert np.array_equal(k["x"], kps["x"]) and np.array_equal(k["y"], kps["y"])
+        assert np.array_equal(k["response"], kps["response"])
+        assert np.array_equal(d, desc)
+
+
+@pytest.mark.parametrize("cfgname,seed,localizing", [("kitti", 1, True), ("kitti", 2, False), ("kitti_fast", 4, True),
+                                                     ("euroc", 0, True), ("euroc", 1, False), ("hd", 0, True)])
+def test_initialize_and_compute_match_oracle(cfgname, seed, localizing):
+    cfg = configs.BY_NAME[cfgname]
+    cam = synth.camera(cfg.camera)
+    left, right = synth.band_world_pair(cfg.camera, seed)
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    nl, nr = gen.initialize(left, right, localizing)
+    o = _oracle(cfg, cam, left, right, localizing)
+    assert (nl, nr) == (len(o.kps_left), len(o.kps_right))
+    cl, cr, dist = gen.detection_stats()
+    assert np.array_equal(cl, o.counts_left) and np.array_equal(cr, o.counts_right)
+    assert dist == o.max_distance
+    assert np.array_equal(gen.thresholds, o.thresholds)
+    _check_pair(gen, o)
+    fps = gen.compute()
+    assert gen.number_of_matches == len(o.matches)
+    _same_points(fps, o.framepoints())
+    _same_points(gen.matches(), o.matches)
+    assert len(fps) > 300
+    gen.close()
+
+
+@pytest.mark.parametrize("cfgname", ["kitti", "euroc"])
+def test_raw_fast_mask_and_blur_taps_match_oracle(cfgname):
+    cfg = configs.BY_NAME[cfgname]
+    cam = synth.camera(cfg.camera)
+    left, right = synth.band_world_pair(cfg.camera, 9)
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    thr = gen.thresholds
+    gen.initialize(left, right, True)
+    for side, img in enumerate((left, right)):
+        kps, _ = tier_a.detect_keypoints(img, cfg.number_of_detectors_vertical, cfg.number_of_detectors_horizontal, thr)
+        want = np.zeros((cam.rows, cam.cols), bool)
+        want[kps["y"].astype(int), kps["x"].astype(int)] = True
+        assert np.array_equal(gen.debug_keypoint_mask(side), want)      # every raw FAST keypoint, border included
+        assert np.array_equal(gen.debug_blurred(side), tier_a.gauss7_u8(img))
+    gen.close()
+
+
+def test_sequence_threshold_controller_feedback_matches_oracle():
+    """frames of one sequence: the thresholds of frame t+1 depend on the counts of frame t (L and R)."""
+    cfg, cam = configs.KITTI_FAST, synth.camera("kitti")
+    world = synth.BandWorld(cam.cols, cam.rows, 1, max_frames=8)
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    o = pipeline.StereoFramePointGeneratorOracle(cfg, cam, "a")
+    seen = []
+    for k in range(6):
+        left, right = world.pair(k)
+        gen.initialize(left, right, k == 0)
+        o.initialize(left, right, k == 0)
+        o.compute()
+        assert np.array_equal(gen.thresholds, o.thresholds), k
+        _check_pair(gen, o)
+        _same_points(gen.compute(), o.framepoints())
+        seen.append(float(o.thresholds[0]))
+    assert len(set(seen)) > 2          # the controller really moved
+    gen.close()
+
+
+def test_tracked_points_preload_bins():
+    cfg, cam = configs.KITTI, synth.camera("kitti")
+    left, right = synth.band_world_pair("kitti", 3)
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    gen.initialize(left, right, False)
+    base = gen.compute()
+    # pretend every third winner had been tracked from the previous frame (has_previous), plus two untracked
+    tracked = np.zeros(len(base[::3]) + 2, api.TRACKED)
+    tracked["row"][:-2] = base["yl"][::3].astype(int)
+    tracked["col"][:-2] = base["xl"][::3].astype(int)
+    tracked["has_previous"][:-2] = 1
+    tracked["row"][-2:], tracked["col"][-2:] = (100, 200), (500, 900)
+    tracked["disparity"][-2:], tracked["distance"][-2:] = (1000.0, 0.5), (0.0, 300.0)
+    o = _oracle(cfg, cam, left, right, False, tracked=tracked)
+    fps = gen.compute(tracked)
+    w = o.winners
+    assert len(fps) == len(w) and (w < 0).sum() >= 1
+    new = w >= 0
+    _same_points(fps[new], o.matches[w[new]])
+    assert np.array_equal(fps["index_left"][~new], w[~new])       # surviving pre-loaded point k reported as -(k+1)
+    assert len(fps) < len(base)
+    gen.close()
+
+
+def test_epipolar_offset_three_like_test_stereo_frontend():
+    """executables/test_stereo_frontend.cpp:98-104: pinned threshold, offset 3 (7 passes), distance 35."""
+    import dataclasses
+    cfg = dataclasses.replace(configs.KITTI, detector_threshold_minimum=25, detector_threshold_maximum=25,
+                              maximum_matching_distance_triangulation=35.0, maximum_epipolar_search_offset_pixels=3)
+    cam = synth.camera("kitti")
+    left, right = synth.band_world_pair("kitti", 5)
+    right = np.roll(right, 1, axis=0).copy()      # true matches now sit one row lower in the right image
+    right[:2] = 96
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    gen.initialize(left, right, False)
+    o = _oracle(cfg, cam, left, right, False)
+    fps = gen.compute()
+    _same_points(gen.matches(), o.matches)
+    _same_points(fps, o.framepoints())
+    offs = set(o.matches["epipolar_offset"].tolist())
+    assert -1 in offs and len(offs) >= 3
+    gen.close()
+
+
+def test_binning_disabled_returns_every_match_in_emission_order():
+    import dataclasses
+    cfg = dataclasses.replace(configs.EUROC, enable_keypoint_binning=False)
+    cam = synth.camera("euroc")
+    left, right = synth.band_world_pair("euroc", 2)
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    gen.initialize(left, right, True)
+    o = _oracle(cfg, cam, left, right, True)
+    fps = gen.compute()
+    assert len(fps) == len(o.matches) == gen.number_of_matches
+    _same_points(fps, o.matches)
+    gen.close()
+
+
+@pytest.mark.parametrize("cfgname,n", [("kitti_fast", 7), ("euroc", 5)])
+def test_batched_pairs_equal_independent_first_frames(cfgname, n):
+    cfg = configs.BY_NAME[cfgname]
+    cam = synth.camera(cfg.camera)
+    left, right = synth.band_world_batch(cfg.camera, range(20, 20 + n))
+    os.environ["VSLAM_CHUNK_PAIRS"] = "3"          # force several chunks on both pipeline lanes
+    try:
+        gen = api.StereoFramePointGenerator(cfg, cam, max_batch=n)
+    finally:
+        del os.environ["VSLAM_CHUNK_PAIRS"]
+    out, counts = gen.batch_process(left, right, True)
+    gen.batch_upload(left, right)
+    gen.batch_run(n, True)
+    out2, nf, nm, nl, nr = gen.batch_download(n)
+    assert np.array_equal(counts, nf)
+    for i in range(n):
+        o = _oracle(cfg, cam, left[i], right[i], True)
+        _same_points(out[i, :counts[i]], o.framepoints())
+        _same_points(out2[i, :nf[i]], o.framepoints())
+        assert nm[i] == len(o.matches) and nl[i] == len(o.kps_left) and nr[i] == len(o.kps_right)
+        k, d = gen.features(0, pair=i)
+        assert np.array_equal(d, o.desc_left) and np.array_equal(k["x"], o.kps_left["x"])
+    assert np.array_equal(gen.thresholds, np.full(gen.number_of_detectors, cfg.detector_threshold_minimum))
+    gen.close()
+
+
+@pytest.mark.parametrize("name", ["kitti_crop", "euroc_crop"])
+def test_against_committed_cv2_golden_vectors(golden_dir, name):
+    import dataclasses
+    g = np.load(os.path.join(golden_dir, "fast_orb_%s.npz" % name))
+    img = g["image"]
+    cam = synth.Camera(img.shape[1], img.shape[0], 400.0, 400.0, img.shape[1] / 2, img.shape[0] / 2, -40.0)
+    cfg = dataclasses.replace(configs.KITTI, detector_threshold_minimum=12, detector_threshold_maximum=12)
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    gen.initialize(img, img, True)
+    want = np.zeros(img.shape, bool)
+    want[g["fast12"][:, 1].astype(int), g["fast12"][:, 0].astype(int)] = True
+    assert np.array_equal(gen.debug_keypoint_mask(0), want)
+    k, d = gen.features(0)
+    assert np.array_equal(np.stack([k["x"], k["y"], k["response"]], 1), g["orb_kps"])
+    assert np.array_equal(d, g["orb_desc"])
+    gen.close()
+
+
+def test_edge_cases_blank_tiny_and_capacity():
+    import dataclasses
+    cam = synth.Camera(96, 80, 100.0, 100.0, 48.0, 40.0, -10.0)
+    gen = api.StereoFramePointGenerator(configs.KITTI, cam)
+    blank = np.full((80, 96), 128, np.uint8)
+    assert gen.initialize(blank, blank, True) == (0, 0)
+    assert len(gen.compute()) == 0 and gen.number_of_matches == 0
+    assert gen.thresholds[0] == 20.0            # already at the minimum
+    gen.close()
+    # an image smaller than the 31 px descriptor border on each side: raw corners but no descriptors
+    cam = synth.Camera(40, 40, 100.0, 100.0, 20.0, 20.0, -10.0)
+    rng = np.random.default_rng(0)
+    noise = rng.integers(0, 255, (40, 40), dtype=np.uint8)
+    gen = api.StereoFramePointGenerator(configs.KITTI, cam)
+    assert gen.initialize(noise, noise, True) == (0, 0)
+    cl, _, _ = gen.detection_stats()
+    kps, counts = tier_a.detect_keypoints(noise, 1, 1, [20.0])
+    assert cl[0] == counts[0] > 0
+    gen.close()
+    # capacity overflow is an error, not a truncation
+    kcam = synth.camera("kitti")
+    left, right = synth.band_world_pair("kitti", 1)
+    gen = api.StereoFramePointGenerator(configs.KITTI, kcam, max_keypoints=500)
+    with pytest.raises(api.VslamError) as e:
+        gen.initialize(left, right, True)
+    assert e.value.code == -3
+    gen.close()
+
+
+def test_row_strided_input_views():
+    cfg, cam = configs.EUROC, synth.camera("euroc")
+    left, right = synth.band_world_pair("euroc", 6)
+    big_l = np.zeros((cam.rows, cam.cols + 40), np.uint8)
+    big_r = np.zeros_like(big_l)
+    big_l[:, :cam.cols], big_r[:, :cam.cols] = left, right
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    gen.initialize(big_l[:, :cam.cols], big_r[:, :cam.cols], True)
+    o = _oracle(cfg, cam, left, right, True)
+    _check_pair(gen, o)
+    gen.close()

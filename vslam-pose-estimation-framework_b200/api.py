@@ -1,0 +1,490 @@
+"""ctypes binding of libvslam_b200.so (include/vslam_b200.h) and a thin Python mirror of the reference's plugin
+interface for the hot path, used by the tests and bench.py:
+
+    StereoFramePointGenerator.{configure (ctor), initialize, compute, track: n/a}   <- BaseFramePointGenerator
+        (/root/reference/src/framepoint_generation/base_framepoint_generator.h:110-234,
+         stereo_framepoint_generator.cpp:16-60,73-133,135-462)
+    StereoUVAligner / UVDAligner.{initialize, linearize, oneRound, converge, errors, inliers, ...}  <- BaseFrameAligner
+        (/root/reference/src/aligners/base_aligner.h:7-71, base_frame_aligner.h:8-41)
+
+Nothing here computes: every method is one C-ABI call into the CUDA library.  There is no CPU fallback; importing
+this module without the built library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvslam_b200.so")
+
+KEYPOINT = np.dtype([("x", "<f4"), ("y", "<f4"), ("response", "<f4")])
+FRAMEPOINT = np.dtype([("index_left", "<i4"), ("index_right", "<i4"), ("xl", "<f4"), ("yl", "<f4"), ("xr", "<f4"),
+                       ("yr", "<f4"), ("distance", "<i4"), ("epipolar_offset", "<i4"), ("camera", "<f8", (3,))])
+TRACKED = np.dtype([("row", "<i4"), ("col", "<i4"), ("has_previous", "<i4"), ("reserved", "<i4"),
+                    ("disparity", "<f8"), ("distance", "<f8")])
+assert FRAMEPOINT.itemsize == 56 and TRACKED.itemsize == 32
+
+# every symbol include/vslam_b200.h declares (tests check that the library exports each one)
+EXPORTS = """vslam_last_error vslam_version vslam_device_count vslam_host_alloc vslam_host_free
+vslam_fpg_create vslam_fpg_destroy vslam_fpg_info vslam_fpg_get_thresholds vslam_fpg_set_thresholds
+vslam_fpg_initialize vslam_fpg_get_features vslam_fpg_get_detection_stats vslam_fpg_compute vslam_fpg_get_matches
+vslam_fpg_set_profiling vslam_fpg_get_time_consumption vslam_fpg_batch_upload vslam_fpg_batch_run
+vslam_fpg_batch_download vslam_fpg_batch_process vslam_fpg_batch_get_features vslam_fpg_stream vslam_fpg_synchronize
+vslam_fpg_launch_count vslam_fpg_debug_keypoint_mask vslam_fpg_debug_blurred vslam_threshold_proposal
+vslam_aligner_create vslam_aligner_destroy vslam_aligner_upload vslam_aligner_linearize vslam_aligner_download
+vslam_aligner_one_round vslam_aligner_converge vslam_aligner_linearize_async vslam_aligner_read_system
+vslam_aligner_stream vslam_aligner_synchronize vslam_aligner_launch_count vslam_solve6 vslam_v2t""".split()
+
+
+class FpgConfig(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("cols", C.c_int32),
+                ("target_number_of_keypoints_tolerance", C.c_double),
+                ("detector_threshold_minimum", C.c_int32), ("detector_threshold_maximum", C.c_int32),
+                ("detector_threshold_maximum_change", C.c_double),
+                ("number_of_detectors_vertical", C.c_int32), ("number_of_detectors_horizontal", C.c_int32),
+                ("enable_keypoint_binning", C.c_int32), ("bin_size_pixels", C.c_int32),
+                ("maximum_matching_distance_triangulation", C.c_double), ("minimum_disparity_pixels", C.c_double),
+                ("maximum_epipolar_search_offset_pixels", C.c_int32),
+                ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("bx", C.c_double),
+                ("max_keypoints_per_image", C.c_int32), ("max_batch", C.c_int32)]
+
+
+class AlignerParameters(C.Structure):
+    _fields_ = [("error_delta_for_convergence", C.c_double), ("maximum_error_kernel", C.c_double),
+                ("damping", C.c_double), ("maximum_number_of_iterations", C.c_int32),
+                ("minimum_number_of_inliers", C.c_int32)]
+
+
+class LinearSystem(C.Structure):
+    _fields_ = [("H", C.c_double * 36), ("b", C.c_double * 6), ("total_error", C.c_double),
+                ("number_of_inliers", C.c_int32), ("number_of_outliers", C.c_int32)]
+
+
+class VslamError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("vslam_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C vslam-pose-estimation-framework_b200/csrc); there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.vslam_last_error.restype = C.c_char_p
+        L.vslam_version.restype = C.c_char_p
+        L.vslam_fpg_stream.restype = C.c_void_p
+        L.vslam_aligner_stream.restype = C.c_void_p
+        L.vslam_fpg_launch_count.restype = C.c_int64
+        L.vslam_aligner_launch_count.restype = C.c_int64
+        L.vslam_threshold_proposal.restype = C.c_double
+        L.vslam_threshold_proposal.argtypes = [C.c_double, C.c_int32] + [C.c_double] * 5
+        vp, i32, sz = C.c_void_p, C.c_int32, C.c_size_t
+        L.vslam_host_alloc.argtypes = [vp, sz]
+        L.vslam_host_free.argtypes = [vp]
+        L.vslam_fpg_create.argtypes = [vp, C.c_int, vp]
+        L.vslam_fpg_destroy.argtypes = [vp]
+        L.vslam_fpg_info.argtypes = [vp] * 6
+        L.vslam_fpg_get_thresholds.argtypes = [vp, vp]
+        L.vslam_fpg_set_thresholds.argtypes = [vp, vp]
+        L.vslam_fpg_initialize.argtypes = [vp, vp, vp, sz, C.c_int, vp, vp]
+        L.vslam_fpg_get_features.argtypes = [vp, C.c_int, vp, vp, i32, vp]
+        L.vslam_fpg_get_detection_stats.argtypes = [vp, vp, vp, vp]
+        L.vslam_fpg_compute.argtypes = [vp, vp, i32, vp, i32, vp, vp]
+        L.vslam_fpg_get_matches.argtypes = [vp, vp, i32, vp]
+        L.vslam_fpg_set_profiling.argtypes = [vp, C.c_int]
+        L.vslam_fpg_get_time_consumption.argtypes = [vp, vp, vp, vp]
+        L.vslam_fpg_batch_upload.argtypes = [vp, i32, vp, vp, sz, sz]
+        L.vslam_fpg_batch_run.argtypes = [vp, i32, C.c_int]
+        L.vslam_fpg_batch_download.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp]
+        L.vslam_fpg_batch_process.argtypes = [vp, i32, vp, vp, sz, sz, C.c_int, vp, i32, vp]
+        L.vslam_fpg_batch_get_features.argtypes = [vp, i32, C.c_int, vp, vp, i32, vp]
+        L.vslam_fpg_stream.argtypes = [vp]
+        L.vslam_fpg_synchronize.argtypes = [vp]
+        L.vslam_fpg_launch_count.argtypes = [vp]
+        L.vslam_fpg_debug_keypoint_mask.argtypes = [vp, i32, C.c_int, vp]
+        L.vslam_fpg_debug_blurred.argtypes = [vp, i32, C.c_int, vp]
+        L.vslam_aligner_create.argtypes = [C.c_int, i32, C.c_int, vp]
+        L.vslam_aligner_destroy.argtypes = [vp]
+        L.vslam_aligner_upload.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, C.c_double]
+        L.vslam_aligner_linearize.argtypes = [vp, vp, C.c_int, C.c_double, vp]
+        L.vslam_aligner_download.argtypes = [vp, vp, vp]
+        L.vslam_aligner_one_round.argtypes = [vp, vp, C.c_int, vp, vp]
+        L.vslam_aligner_converge.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.vslam_aligner_linearize_async.argtypes = [vp, vp, C.c_int, C.c_double]
+        L.vslam_aligner_read_system.argtypes = [vp, vp]
+        L.vslam_aligner_stream.argtypes = [vp]
+        L.vslam_aligner_synchronize.argtypes = [vp]
+        L.vslam_aligner_launch_count.argtypes = [vp]
+        L.vslam_solve6.argtypes = [vp, vp, vp]
+        L.vslam_v2t.argtypes = [vp, vp]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise VslamError(rc, lib().vslam_last_error().decode())
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def device_count() -> int:
+    return lib().vslam_device_count()
+
+
+def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
+    """numpy array over page-locked host memory (vslam_host_alloc); freed with the process."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    ptr = C.c_void_p()
+    _check(lib().vslam_host_alloc(C.byref(ptr), n))
+    buf = (C.c_uint8 * n).from_address(ptr.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def make_config(cfg, cam, max_batch=1, max_keypoints=0) -> FpgConfig:
+    c = FpgConfig()
+    c.rows, c.cols = cam.rows, cam.cols
+    c.target_number_of_keypoints_tolerance = cfg.target_number_of_keypoints_tolerance
+    c.detector_threshold_minimum = cfg.detector_threshold_minimum
+    c.detector_threshold_maximum = cfg.detector_threshold_maximum
+    c.detector_threshold_maximum_change = cfg.detector_threshold_maximum_change
+    c.number_of_detectors_vertical = cfg.number_of_detectors_vertical
+    c.number_of_detectors_horizontal = cfg.number_of_detectors_horizontal
+    c.enable_keypoint_binning = int(cfg.enable_keypoint_binning)
+    c.bin_size_pixels = cfg.bin_size_pixels
+    c.maximum_matching_distance_triangulation = cfg.maximum_matching_distance_triangulation
+    c.minimum_disparity_pixels = cfg.minimum_disparity_pixels
+    c.maximum_epipolar_search_offset_pixels = cfg.maximum_epipolar_search_offset_pixels
+    c.fx, c.fy, c.cx, c.cy, c.bx = cam.fx, cam.fy, cam.cx, cam.cy, cam.bx
+    c.max_keypoints_per_image = max_keypoints
+    c.max_batch = max_batch
+    return c
+
+
+class StereoFramePointGenerator:
+    """GPU drop-in for proslam::StereoFramePointGenerator (initialize / compute), single pair and batched."""
+
+    def __init__(self, cfg, cam, device=0, max_batch=1, max_keypoints=0):
+        self.cfg, self.cam = cfg, cam
+        self._h = C.c_void_p()
+        self._c = make_config(cfg, cam, max_batch, max_keypoints)
+        _check(lib().vslam_fpg_create(C.byref(self._c), device, C.byref(self._h)))
+        n = C.c_int32()
+        rb, cb, tg = C.c_int32(), C.c_int32(), C.c_int32()
+        reg = np.zeros((64, 4), np.int32)
+        _check(lib().vslam_fpg_info(self._h, C.byref(n), _p(reg), C.byref(rb), C.byref(cb), C.byref(tg)))
+        self.number_of_detectors = n.value
+        self.detector_regions = reg[:n.value].copy()
+        self.rows_bin, self.cols_bin, self.target_number_of_keypoints = rb.value, cb.value, tg.value
+        self.max_batch = max(1, max_batch)
+        self.capacity = min(65535, max(4096, 4 * tg.value) if max_keypoints <= 0 else max_keypoints)
+        self.out_capacity = tg.value if cfg.enable_keypoint_binning else self.capacity
+        self.number_of_matches = 0
+
+    def close(self):
+        if self._h:
+            lib().vslam_fpg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- thresholds (FastDetector::getThreshold / setThreshold)
+    @property
+    def thresholds(self):
+        t = np.zeros(self.number_of_detectors)
+        _check(lib().vslam_fpg_get_thresholds(self._h, _p(t)))
+        return t
+
+    @thresholds.setter
+    def thresholds(self, v):
+        t = np.ascontiguousarray(v, np.float64)
+        assert t.shape == (self.number_of_detectors,)
+        _check(lib().vslam_fpg_set_thresholds(self._h, _p(t)))
+
+    # -- StereoFramePointGenerator::initialize(frame, true)
+    def initialize(self, left, right, localizing: bool):
+        left, right = _image(left, self.cam), _image(right, self.cam)
+        assert left.strides[0] == right.strides[0]
+        nl, nr = C.c_int32(), C.c_int32()
+        _check(lib().vslam_fpg_initialize(self._h, _p(left), _p(right), left.strides[0], int(bool(localizing)),
+                                          C.byref(nl), C.byref(nr)))
+        return nl.value, nr.value
+
+    def features(self, side: int, pair: int | None = None):
+        """(keypoints, descriptors) of frame->keypointsLeft/Right(), descriptorsLeft/Right() in reference order"""
+        kps = np.zeros(self.capacity, KEYPOINT)
+        desc = np.zeros((self.capacity, 32), np.uint8)
+        n = C.c_int32()
+        if pair is None:
+            _check(lib().vslam_fpg_get_features(self._h, side, _p(kps), _p(desc), self.capacity, C.byref(n)))
+        else:
+            _check(lib().vslam_fpg_batch_get_features(self._h, pair, side, _p(kps), _p(desc), self.capacity, C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def detection_stats(self):
+        cl = np.zeros(self.number_of_detectors, np.int32)
+        cr = np.zeros(self.number_of_detectors, np.int32)
+        d = C.c_double()
+        _check(lib().vslam_fpg_get_detection_stats(self._h, _p(cl), _p(cr), C.byref(d)))
+        return cl, cr, d.value
+
+    # -- StereoFramePointGenerator::compute(frame)
+    def compute(self, tracked=None):
+        tracked = np.zeros(0, TRACKED) if tracked is None else np.ascontiguousarray(tracked, TRACKED)
+        cap = self.out_capacity + len(tracked)
+        out = np.zeros(cap, FRAMEPOINT)
+        n, nm = C.c_int32(), C.c_int32()
+        _check(lib().vslam_fpg_compute(self._h, _p(tracked) if len(tracked) else None, len(tracked), _p(out), cap,
+                                       C.byref(n), C.byref(nm)))
+        self.number_of_matches = nm.value
+        return out[:n.value].copy()
+
+    def matches(self):
+        out = np.zeros(self.capacity, FRAMEPOINT)
+        n = C.c_int32()
+        _check(lib().vslam_fpg_get_matches(self._h, _p(out), self.capacity, C.byref(n)))
+        return out[:n.value].copy()
+
+    # -- chronometers
+    def set_profiling(self, on: bool):
+        _check(lib().vslam_fpg_set_profiling(self._h, int(on)))
+
+    def time_consumption(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _check(lib().vslam_fpg_get_time_consumption(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"keypoint_detection": a.value, "descriptor_extraction": b.value, "point_triangulation": c.value}
+
+    # -- batched
+    def batch_upload(self, left, right):
+        left, right = _batch(left, self.cam), _batch(right, self.cam)
+        assert left.shape == right.shape and left.strides == right.strides
+        _check(lib().vslam_fpg_batch_upload(self._h, left.shape[0], _p(left), _p(right), left.strides[1], left.strides[0]))
+        return left.shape[0]
+
+    def batch_run(self, n_pairs, localizing=True):
+        _check(lib().vslam_fpg_batch_run(self._h, n_pairs, int(bool(localizing))))
+
+    def batch_download(self, n_pairs, out=None):
+        if out is None:
+            out = np.zeros((n_pairs, self.out_capacity), FRAMEPOINT)
+        nf, nm = np.zeros(n_pairs, np.int32), np.zeros(n_pairs, np.int32)
+        nl, nr = np.zeros(n_pairs, np.int32), np.zeros(n_pairs, np.int32)
+        _check(lib().vslam_fpg_batch_download(self._h, n_pairs, _p(out), out.shape[1], _p(nf), _p(nm), _p(nl), _p(nr)))
+        return out, nf, nm, nl, nr
+
+    def batch_process(self, left, right, localizing=True, out=None, counts=None):
+        """end-to-end call: host images in, framepoints out"""
+        left, right = _batch(left, self.cam), _batch(right, self.cam)
+        n = left.shape[0]
+        if out is None:
+            out = np.zeros((n, self.out_capacity), FRAMEPOINT)
+        if counts is None:
+            counts = np.zeros(n, np.int32)
+        _check(lib().vslam_fpg_batch_process(self._h, n, _p(left), _p(right), left.strides[1], left.strides[0],
+                                             int(bool(localizing)), _p(out), out.shape[1], _p(counts)))
+        return out, counts
+
+    def synchronize(self):
+        _check(lib().vslam_fpg_synchronize(self._h))
+
+    @property
+    def stream(self) -> int:
+        return lib().vslam_fpg_stream(self._h) or 0
+
+    @property
+    def launch_count(self) -> int:
+        return lib().vslam_fpg_launch_count(self._h)
+
+    # -- parity taps
+    def debug_keypoint_mask(self, side, pair=0):
+        words = np.zeros((self.cam.rows, (self.cam.cols + 31) // 32), np.uint32)
+        _check(lib().vslam_fpg_debug_keypoint_mask(self._h, pair, side, _p(words)))
+        bits = np.unpackbits(words.view(np.uint8).reshape(self.cam.rows, -1), axis=1, bitorder="little")
+        return bits[:, :self.cam.cols].astype(bool)
+
+    def debug_blurred(self, side, pair=0):
+        img = np.zeros((self.cam.rows, self.cam.cols), np.uint8)
+        _check(lib().vslam_fpg_debug_blurred(self._h, pair, side, _p(img)))
+        return img
+
+
+def _image(a, cam):
+    a = np.asarray(a)
+    if a.dtype != np.uint8 or a.shape != (cam.rows, cam.cols) or a.strides[1] != 1:
+        raise ValueError("expected a uint8 image of shape (%d, %d)" % (cam.rows, cam.cols))
+    return a
+
+
+def _batch(a, cam):
+    a = np.asarray(a)
+    if a.dtype != np.uint8 or a.ndim != 3 or a.shape[1:] != (cam.rows, cam.cols) or a.strides[2] != 1:
+        raise ValueError("expected uint8 images of shape (B, %d, %d)" % (cam.rows, cam.cols))
+    return a
+
+
+class _FrameAligner:
+    """BaseFrameAligner mirror: same method names and meaning as the reference (base_aligner.h:26-48)."""
+    KIND = 0
+
+    def __init__(self, parameters, max_points=1 << 17, device=0):
+        self.parameters = parameters          # configs.AlignerConfig (mutable, like AlignerParameters*)
+        self._h = C.c_void_p()
+        _check(lib().vslam_aligner_create(self.KIND, max_points, device, C.byref(self._h)))
+        self._n = 0
+        self._sys = LinearSystem()
+        self._T = np.hstack([np.eye(3), np.zeros((3, 1))]).reshape(12).copy()
+        self.has_system_converged = False
+        self.number_of_rounds = 0
+        self.information_matrix = np.eye(6)
+
+    def close(self):
+        if self._h:
+            lib().vslam_aligner_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _params(self):
+        p = AlignerParameters()
+        q = self.parameters
+        p.error_delta_for_convergence = q.error_delta_for_convergence
+        p.maximum_error_kernel = q.maximum_error_kernel
+        p.damping = q.damping
+        p.maximum_number_of_iterations = q.maximum_number_of_iterations
+        p.minimum_number_of_inliers = q.minimum_number_of_inliers
+        return p
+
+    def initialize(self, moving, fixed, omega, weights_translation, K, baseline, rows, cols, previous_to_current=None):
+        """the buffers StereoUVAligner/UVDAligner::initialize builds from the two frames (a11 in SURVEY 8a)"""
+        moving = np.ascontiguousarray(moving, np.float64)
+        fixed = np.ascontiguousarray(fixed, np.float64)
+        omega = np.ascontiguousarray(omega, np.float64)
+        wt = np.ascontiguousarray(weights_translation, np.float64)
+        n = len(moving)
+        K = np.ascontiguousarray(K, np.float64)
+        baseline = np.ascontiguousarray(baseline, np.float64)
+        _check(lib().vslam_aligner_upload(self._h, n, _p(moving), _p(fixed), _p(omega), _p(wt), _p(K), _p(baseline),
+                                          int(rows), int(cols), float(self.parameters.minimum_reliable_depth_meters)))
+        self._n = n
+        if previous_to_current is not None:
+            self._T = np.ascontiguousarray(previous_to_current, np.float64).reshape(12).copy()
+
+    def _system(self):
+        s = self._sys
+        return {"H": np.array(s.H).reshape(6, 6), "b": np.array(s.b), "total_error": s.total_error,
+                "inliers": s.number_of_inliers, "outliers": s.number_of_outliers}
+
+    def linearize(self, ignore_outliers=False):
+        _check(lib().vslam_aligner_linearize(self._h, _p(self._T), int(bool(ignore_outliers)),
+                                             float(self.parameters.maximum_error_kernel), C.byref(self._sys)))
+        return self._system()
+
+    def oneRound(self, ignore_outliers=False):
+        p = self._params()
+        _check(lib().vslam_aligner_one_round(self._h, C.byref(p), int(bool(ignore_outliers)), _p(self._T),
+                                             C.byref(self._sys)))
+        return self._system()
+
+    def converge(self):
+        p = self._params()
+        info = np.zeros(36)
+        ok, rounds = C.c_int32(), C.c_int32()
+        _check(lib().vslam_aligner_converge(self._h, C.byref(p), _p(self._T), C.byref(self._sys), _p(info),
+                                            C.byref(ok), C.byref(rounds)))
+        self.has_system_converged = bool(ok.value)
+        self.number_of_rounds = rounds.value
+        if ok.value:
+            self.information_matrix = info.reshape(6, 6)
+        return self._system()
+
+    def linearize_async(self, ignore_outliers=False):
+        _check(lib().vslam_aligner_linearize_async(self._h, _p(self._T), int(bool(ignore_outliers)),
+                                                   float(self.parameters.maximum_error_kernel)))
+
+    def read_system(self):
+        _check(lib().vslam_aligner_read_system(self._h, C.byref(self._sys)))
+        return self._system()
+
+    def synchronize(self):
+        _check(lib().vslam_aligner_synchronize(self._h))
+
+    @property
+    def stream(self) -> int:
+        return lib().vslam_aligner_stream(self._h) or 0
+
+    @property
+    def launch_count(self) -> int:
+        return lib().vslam_aligner_launch_count(self._h)
+
+    # getters of BaseAligner
+    def previousToCurrent(self):
+        return self._T.reshape(3, 4).copy()
+
+    def setPreviousToCurrent(self, T):
+        self._T = np.ascontiguousarray(T, np.float64).reshape(12).copy()
+
+    def errors(self):
+        e = np.zeros(self._n)
+        _check(lib().vslam_aligner_download(self._h, _p(e), None))
+        return e
+
+    def inliers(self):
+        i = np.zeros(self._n, np.uint8)
+        _check(lib().vslam_aligner_download(self._h, None, _p(i)))
+        return i.astype(bool)
+
+    def numberOfInliers(self):
+        return self._sys.number_of_inliers
+
+    def numberOfOutliers(self):
+        return self._sys.number_of_outliers
+
+    def numberOfCorrespondences(self):
+        return self._n
+
+    def totalError(self):
+        return self._sys.total_error
+
+    def averageError(self):
+        return self._sys.total_error / self._n
+
+
+class StereoUVAligner(_FrameAligner):
+    KIND = 0
+
+
+class UVDAligner(_FrameAligner):
+    KIND = 1
+
+
+def solve6(A, b):
+    A, b, x = np.ascontiguousarray(A, np.float64), np.ascontiguousarray(b, np.float64), np.zeros(6)
+    lib().vslam_solve6(_p(A), _p(b), _p(x))
+    return x
+
+
+def v2t(v):
+    v, T = np.ascontiguousarray(v, np.float64), np.zeros(12)
+    lib().vslam_v2t(_p(v), _p(T))
+    return T.reshape(3, 4)

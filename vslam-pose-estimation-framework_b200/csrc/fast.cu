@@ -1,0 +1,278 @@
+// fast.cu -- K1 fast_nms_kernel + K2 compact_kernel.
+//
+// Replaces cv::FastFeatureDetector::detect per detector region as called by
+// BaseFramePointGenerator::detectKeypoints (reference src/framepoint_generation/base_framepoint_generator.cpp:
+// 23-25, 362-367) and the ordering / border filtering that cv::ORB::compute (:434) and
+// IntensityFeatureMatcher::setFeatures + sortFeatureVector (intensity_feature_matcher.cpp:48-79) impose:
+// the device-canonical feature order is ascending (row, col), the order the stereo scan consumes.
+//
+// FAST-9/16 semantics (OpenCV, TYPE_9_16, nonmaxSuppression=true): SURVEY.md Appendix A.1.
+#include "kernels.cuh"
+
+namespace vslam {
+
+namespace {
+
+constexpr int TW = 128;            // output tile width  (image-aligned: 128 B = 4 mask words)
+constexpr int TH = 16;             // output tile height
+constexpr int HX = 16;             // smem halo in x (only 4 needed; 16 keeps uint4 loads aligned)
+constexpr int SW = TW + 2 * HX;    // 160
+constexpr int SH = TH + 8;         // 24 : 3 (ring) + 1 (NMS) on both sides
+constexpr int CW = TW + 2;         // score tile width (NMS halo 1)
+constexpr int CH = TH + 2;
+constexpr int CPITCH = 132;
+
+// true iff the 16-bit circular mask m has >= 9 contiguous set bits
+__device__ __forceinline__ bool arc9(unsigned m) {
+  m |= m << 16;
+  unsigned a = m & (m >> 1);
+  a &= a >> 2;
+  a &= a >> 4;
+  a &= m >> 8;
+  return (a & 0xFFFFu) != 0;
+}
+
+// OpenCV cornerScore<16> for a pixel already known to be a corner:
+// max(max over 9-arcs of min(d), -(min over 9-arcs of max(d))) - 1 with d[k] = v - ring[k]
+__device__ __forceinline__ int corner_score(const int (&d)[16]) {
+  int mn[16], mx[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    mn[i] = min(d[i], d[(i + 1) & 15]);
+    mx[i] = max(d[i], d[(i + 1) & 15]);
+  }
+  int mn4[16], mx4[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    mn4[i] = min(mn[i], mn[(i + 2) & 15]);
+    mx4[i] = max(mx[i], mx[(i + 2) & 15]);
+  }
+  int a = -1000, b = 1000;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int m9 = min(min(mn4[i], mn4[(i + 4) & 15]), d[(i + 8) & 15]);
+    const int x9 = max(max(mx4[i], mx4[(i + 4) & 15]), d[(i + 8) & 15]);
+    a = max(a, m9);
+    b = min(b, x9);
+  }
+  return max(a, -b) - 1;
+}
+
+}  // namespace
+
+// ring offsets (dx, dy), k = 0..15 : (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+#define VSLAM_RING(F) \
+  F(0, 0, 3) F(1, 1, 3) F(2, 2, 2) F(3, 3, 1) F(4, 3, 0) F(5, 3, -1) F(6, 2, -2) F(7, 1, -3) \
+  F(8, 0, -3) F(9, -1, -3) F(10, -2, -2) F(11, -3, -1) F(12, -3, 0) F(13, -3, 1) F(14, -2, 2) F(15, -1, 3)
+
+// FAST score of the pixel at p (row pitch `pitch`); 0 if not a corner at threshold t
+template <typename Ptr>
+__device__ __forceinline__ int fast_score_at(Ptr p, int pitch, int t) {
+  const int v = p[0];
+  int d[16];
+#define F(k, dx, dy) d[k] = v - (int)p[(dy) * pitch + (dx)];
+  VSLAM_RING(F)
+#undef F
+  unsigned dark = 0, bright = 0;   // dark: ring darker than v - t (d > t); bright: d < -t
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    dark |= (unsigned)(d[k] > t) << k;
+    bright |= (unsigned)(d[k] < -t) << k;
+  }
+  if (!(arc9(dark) || arc9(bright))) return 0;
+  return corner_score(d);
+}
+
+__global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable rt, const uint8_t* __restrict__ image,
+                                                       uint32_t* __restrict__ mask, int32_t* __restrict__ raw_count,
+                                                       int single_region) {
+  __shared__ __align__(16) uint8_t s_img[SH][SW];
+  __shared__ uint8_t s_score[CH][CPITCH];
+  __shared__ int s_count;
+
+  const int tid = threadIdx.x;
+  const int img = blockIdx.z / g.n_regions;
+  const int reg = blockIdx.z - img * g.n_regions;
+  const Region R = rt.r[reg];
+  const int t = rt.threshold[reg];
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  // keypoint area of this region, inclusive, image coordinates (FAST skips a 3 px border of its view)
+  const int ax0 = R.x + 3, ax1 = R.x + R.w - 4, ay0 = R.y + 3, ay1 = R.y + R.h - 4;
+  uint32_t* mrow = mask + (size_t)img * g.rows * g.mask_words;
+
+  const bool hit = !(x0 > ax1 || x0 + TW - 1 < ax0 || y0 > ay1 || y0 + TH - 1 < ay0);
+  if (!hit) {
+    if (single_region) {  // the mask is written with plain stores: cover this tile with zeros
+      for (int i = tid; i < TH * 4; i += 256) {
+        const int y = y0 + (i >> 2), wd = (x0 >> 5) + (i & 3);
+        if (y < g.rows && wd < g.mask_words) mrow[(size_t)y * g.mask_words + wd] = 0u;
+      }
+    }
+    return;
+  }
+  if (tid == 0) s_count = 0;
+
+  // ---- stage the tile (+halo) in shared memory: 24 rows x 10 uint4, coalesced 16 B loads
+  const uint8_t* base = image + (size_t)img * g.rows * g.pitch;
+  for (int i = tid; i < SH * (SW / 16); i += 256) {
+    const int r = i / (SW / 16), c = i - r * (SW / 16);
+    const int gy = y0 - 4 + r, gx = x0 - HX + c * 16;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (gy >= 0 && gy < g.rows && gx >= 0 && gx + 16 <= g.pitch)
+      v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)gy * g.pitch + gx));
+    *reinterpret_cast<uint4*>(&s_img[r][c * 16]) = v;
+  }
+  __syncthreads();
+
+  // ---- corner score on the tile + 1 px NMS halo
+  for (int i = tid; i < CH * CW; i += 256) {
+    const int sy = i / CW, sx = i - sy * CW;
+    const int ix = x0 - 1 + sx, iy = y0 - 1 + sy;
+    int s = 0;
+    if (ix >= ax0 && ix <= ax1 && iy >= ay0 && iy <= ay1) s = fast_score_at(&s_img[sy + 3][sx + HX - 1], SW, t);
+    s_score[sy][sx] = (uint8_t)s;
+  }
+  __syncthreads();
+
+  // ---- 3x3 strict non-maximum suppression, one warp per (row, 32-column word)
+  const int warp = tid >> 5, lane = tid & 31;
+  int found = 0;
+  for (int u = warp; u < TH * 4; u += 8) {
+    const int ry = u >> 2, wx = u & 3;
+    const int sx = wx * 32 + lane + 1, sy = ry + 1;
+    const int s = s_score[sy][sx];
+    bool kp = false;
+    if (s > 0) {
+      kp = s > s_score[sy - 1][sx - 1] && s > s_score[sy - 1][sx] && s > s_score[sy - 1][sx + 1] &&
+           s > s_score[sy][sx - 1] && s > s_score[sy][sx + 1] && s > s_score[sy + 1][sx - 1] &&
+           s > s_score[sy + 1][sx] && s > s_score[sy + 1][sx + 1];
+    }
+    const unsigned word = __ballot_sync(0xffffffffu, kp);
+    const int y = y0 + ry, wd = (x0 >> 5) + wx;
+    if (lane == 0 && y < g.rows && wd < g.mask_words) {
+      if (single_region) mrow[(size_t)y * g.mask_words + wd] = word;
+      else if (word) atomicOr(&mrow[(size_t)y * g.mask_words + wd], word);
+      found += __popc(word);
+    }
+  }
+  if (lane == 0 && found) atomicAdd(&s_count, found);
+  __syncthreads();
+  if (tid == 0 && s_count) atomicAdd(&raw_count[img * g.n_regions + reg], s_count);
+}
+
+// K2: one CTA per image.  Applies cv::ORB's 31 px border filter (KeyPointsFilter::runByImageBorder), builds the
+// CSR row pointer and the (row, col)-sorted keypoint list, and recomputes the FAST score of each kept keypoint
+// (for a corner the score does not depend on the threshold).
+__global__ void __launch_bounds__(256) compact_kernel(Geometry g, const uint8_t* __restrict__ image,
+                                                      const uint32_t* __restrict__ mask, int32_t* __restrict__ row_ptr,
+                                                      uint32_t* __restrict__ kp_xy, uint8_t* __restrict__ kp_score,
+                                                      int32_t* __restrict__ n_desc, int32_t* __restrict__ error_flag) {
+  extern __shared__ int s_rows[];   // rows + 1 counts -> exclusive offsets
+  __shared__ int s_warp[8];
+  const int img = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t* m = mask + (size_t)img * g.rows * g.mask_words;
+  const int lo_x = 31, hi_x = g.cols - 31;   // keep lo_x <= x < hi_x
+  const int lo_y = 31, hi_y = g.rows - 31;
+
+  auto valid_word = [&](int y, int wd) -> uint32_t {
+    uint32_t w = m[(size_t)y * g.mask_words + wd];
+    const int bx = wd * 32;
+    if (bx < lo_x) w &= (lo_x - bx >= 32) ? 0u : (0xffffffffu << (lo_x - bx));
+    if (bx + 32 > hi_x) w &= (hi_x - bx <= 0) ? 0u : (0xffffffffu >> (32 - (hi_x - bx)));
+    return w;
+  };
+
+  // per-row counts
+  for (int y = warp; y < g.rows; y += 8) {
+    int c = 0;
+    if (y >= lo_y && y < hi_y)
+      for (int wd = lane; wd < g.mask_words; wd += 32) c += __popc(valid_word(y, wd));
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) s_rows[y] = c;
+  }
+  __syncthreads();
+
+  // block-wide exclusive scan over rows (chunks of 256)
+  int carry = 0;
+  for (int b0 = 0; b0 < g.rows; b0 += 256) {
+    const int y = b0 + tid;
+    const int v = y < g.rows ? s_rows[y] : 0;
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += s_warp[w];
+    int total = 0;
+    for (int w = 0; w < 8; ++w) total += s_warp[w];
+    if (y < g.rows) s_rows[y] = carry + woff + inc - v;
+    carry += total;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    s_rows[g.rows] = carry;
+    n_desc[img] = min(carry, g.cap);
+    if (carry > g.cap) atomicExch(error_flag, 1);
+  }
+  __syncthreads();
+  int32_t* rp = row_ptr + (size_t)img * (g.rows + 1);
+  for (int y = tid; y <= g.rows; y += 256) rp[y] = min(s_rows[y], g.cap);
+
+  // ordered emission
+  const uint8_t* base = image + (size_t)img * g.rows * g.pitch;
+  uint32_t* xy = kp_xy + (size_t)img * g.cap;
+  uint8_t* sc = kp_score + (size_t)img * g.cap;
+  for (int y = lo_y + warp; y < hi_y; y += 8) {
+    if (s_rows[y + 1] == s_rows[y]) continue;
+    int row_base = s_rows[y];
+    for (int w0 = 0; w0 < g.mask_words; w0 += 32) {
+      const int wd = w0 + lane;
+      const uint32_t w = wd < g.mask_words ? valid_word(y, wd) : 0u;
+      const int c = __popc(w);
+      int inc = c;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+      }
+      int idx = row_base + inc - c;
+      uint32_t bits = w;
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int x = wd * 32 + b;
+        if (idx < g.cap) {
+          xy[idx] = (uint32_t)x | ((uint32_t)y << 16);
+          sc[idx] = (uint8_t)fast_score_at(base + (size_t)y * g.pitch + x, g.pitch, 0);
+        }
+        ++idx;
+      }
+      row_base += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+}
+
+void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, int first_image, int n_images,
+                 cudaStream_t stream) {
+  const int single = g.n_regions == 1;
+  const size_t mask_bytes = (size_t)g.rows * g.mask_words * sizeof(uint32_t);
+  if (!single) cudaMemsetAsync(b.mask + (size_t)first_image * g.rows * g.mask_words, 0, mask_bytes * n_images, stream);
+  cudaMemsetAsync(b.raw_count + (size_t)first_image * g.n_regions, 0, sizeof(int32_t) * g.n_regions * n_images, stream);
+  dim3 grid((g.cols + TW - 1) / TW, (g.rows + TH - 1) / TH, n_images * g.n_regions);
+  fast_nms_kernel<<<grid, 256, 0, stream>>>(g, rt, b.image + (size_t)first_image * g.rows * g.pitch,
+                                            b.mask + (size_t)first_image * g.rows * g.mask_words,
+                                            b.raw_count + (size_t)first_image * g.n_regions, single);
+}
+
+void launch_compact(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream) {
+  const size_t smem = sizeof(int) * (g.rows + 1);
+  compact_kernel<<<n_images, 256, smem, stream>>>(
+      g, b.image + (size_t)first_image * g.rows * g.pitch, b.mask + (size_t)first_image * g.rows * g.mask_words,
+      b.row_ptr + (size_t)first_image * (g.rows + 1), b.kp_xy + (size_t)first_image * g.cap,
+      b.kp_score + (size_t)first_image * g.cap, b.n_desc + first_image, b.error_flag);
+}
+
+}  // namespace vslam

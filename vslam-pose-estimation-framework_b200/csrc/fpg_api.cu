@@ -1,0 +1,721 @@
+// fpg_api.cu -- C ABI of the stereo framepoint generator (include/vslam_b200.h): handle lifetime, device buffers,
+// streams, chunked batch pipeline with copy/compute overlap, and the host-side scalar logic of
+// StereoFramePointGenerator::{configure, initialize, compute} (reference
+// src/framepoint_generation/stereo_framepoint_generator.cpp:16-60, 73-133, 135-462).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/vslam_b200.h"
+#include "api_common.h"
+#include "host_math.h"
+#include "kernels.cuh"
+
+using namespace vslam;
+
+static_assert(sizeof(FramePointRecord) == sizeof(vslam_framepoint), "record layout");
+static_assert(sizeof(TrackedPoint) == sizeof(vslam_tracked_point), "tracked layout");
+
+namespace {
+
+constexpr int kLanes = 2;   // chunk pipelines that overlap copies and the small kernels of neighbouring chunks
+
+struct Lane {
+  cudaStream_t stream = nullptr;
+  uint8_t* blurred = nullptr;   // [2*chunk][rows][pitch]
+  uint32_t* mask = nullptr;     // [2*chunk][rows][mask_words]
+};
+
+struct StageClock {
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+}  // namespace
+
+struct vslam_fpg {
+  vslam_fpg_config cfg;
+  int device = 0;
+  int sm_count = 0;
+  Geometry g;
+  int n_passes = 1;
+  int chunk = 1;              // pairs per pipeline chunk
+  int max_batch = 1;
+  int out_cap = 0;            // framepoint records per pair
+  HostRegion regions[kMaxRegions];
+  double thresholds[kMaxRegions];
+  int target_keypoints = 0;
+  int target_per_detector = 0;
+  StereoParams sp;
+  Lane lanes[kLanes];
+  Buffers b;                  // b.blurred / b.mask are per-lane and set per launch
+  FramePointRecord* d_out = nullptr;       // [max_batch][out_cap]
+  FramePointRecord* d_matches = nullptr;   // [cap] (single pair, emission order)
+  int32_t* d_n_matches = nullptr;
+  TrackedPoint* d_tracked = nullptr;
+  int tracked_cap = 0;
+  // pinned staging
+  int32_t* h_counts = nullptr;   // [2*max_batch][n_regions]
+  int32_t* h_n_desc = nullptr;   // [2*max_batch]
+  int32_t* h_n_out = nullptr;    // [max_batch][2]
+  int32_t* h_flag = nullptr;
+  // state of the last single-pair initialize / last batch
+  bool initialized = false;
+  int last_pairs = 0;
+  int localizing = 1;
+  double matching_distance = 0;
+  int64_t launches = 0;
+  bool profiling = false;
+  StageClock clock;
+  double t_detect = 0, t_describe = 0, t_match = 0;
+};
+
+namespace {
+
+void refresh_region_table(const vslam_fpg* h, RegionTable* rt) {
+  for (int i = 0; i < h->g.n_regions; ++i) {
+    rt->r[i] = Region{h->regions[i].x, h->regions[i].y, h->regions[i].w, h->regions[i].h};
+    int t = (int)std::rint(h->thresholds[i]);   // FastDetector::setThreshold -> std::rint (:21); cv::FAST clamps
+    rt->threshold[i] = std::min(std::max(t, 0), 255);
+  }
+}
+
+int check_flag(vslam_fpg* h) {
+  if (*h->h_flag == 1)
+    return fail(VSLAM_ERR_CAPACITY, "more than max_keypoints_per_image=%d descriptor-valid keypoints in an image", h->g.cap);
+  if (*h->h_flag == 2) return fail(VSLAM_ERR_CAPACITY, "framepoint output capacity exceeded");
+  return VSLAM_OK;
+}
+
+// kernels of initialize() for images [2*p0, 2*(p0+n)) on one lane
+void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n) {
+  Buffers b = h->b;
+  // lane-local scratch is indexed from image 0 of the chunk: shift the base so that image index 2*p0 lands on it
+  b.blurred = lane.blurred - (size_t)2 * p0 * h->g.rows * h->g.pitch;
+  b.mask = lane.mask - (size_t)2 * p0 * h->g.rows * h->g.mask_words;
+  RegionTable rt;
+  refresh_region_table(h, &rt);
+  const bool prof = h->profiling;
+  if (prof) cudaEventRecord(h->clock.ev[0], lane.stream);
+  launch_fast(h->g, rt, b, 2 * p0, 2 * n, lane.stream);
+  launch_compact(h->g, b, 2 * p0, 2 * n, lane.stream);
+  if (prof) cudaEventRecord(h->clock.ev[1], lane.stream);
+  launch_blur(h->g, b, 2 * p0, 2 * n, lane.stream);
+  launch_describe(h->g, b, 2 * p0, 2 * n, lane.stream);
+  if (prof) cudaEventRecord(h->clock.ev[2], lane.stream);
+  h->launches += 4;
+}
+
+// kernels of compute() for pairs [p0, p0+n) on one lane
+void run_match_select(vslam_fpg* h, Lane& lane, int p0, int n, const TrackedPoint* tracked, int n_tracked) {
+  const bool prof = h->profiling;
+  if (prof) cudaEventRecord(h->clock.ev[3], lane.stream);
+  for (int pass = 0; pass < h->n_passes; ++pass) {
+    const int offset = pass == 0 ? 0 : ((pass & 1) ? (pass + 1) / 2 : -(pass / 2));
+    launch_match(h->g, h->sp, h->b, p0, n, pass, offset, lane.stream);
+    ++h->launches;
+  }
+  launch_select(h->g, h->sp, h->b, p0, n, h->n_passes, tracked, n_tracked, h->d_out, h->out_cap, lane.stream);
+  ++h->launches;
+  if (prof) cudaEventRecord(h->clock.ev[4], lane.stream);
+}
+
+void collect_clock(vslam_fpg* h, bool detect, bool match) {
+  if (!h->profiling) return;
+  float ms = 0;
+  if (detect) {
+    if (cudaEventElapsedTime(&ms, h->clock.ev[0], h->clock.ev[1]) == cudaSuccess) h->t_detect += ms * 1e-3;
+    if (cudaEventElapsedTime(&ms, h->clock.ev[1], h->clock.ev[2]) == cudaSuccess) h->t_describe += ms * 1e-3;
+  }
+  if (match && cudaEventElapsedTime(&ms, h->clock.ev[3], h->clock.ev[4]) == cudaSuccess) h->t_match += ms * 1e-3;
+}
+
+int upload_images(vslam_fpg* h, Lane& lane, int p0, int n, const uint8_t* left, const uint8_t* right, size_t stride,
+                  size_t pair_stride) {
+  const Geometry& g = h->g;
+  for (int side = 0; side < 2; ++side) {
+    const uint8_t* src = (side == 0 ? left : right) + (size_t)p0 * pair_stride;
+    uint8_t* dst = h->b.image + ((size_t)2 * p0 + side) * g.rows * g.pitch;
+    if (n > 1 && pair_stride % stride == 0 && pair_stride / stride >= (size_t)g.rows) {
+      // one strided 3-D copy: host [pair][row][col] -> device [pair][side][row][col]
+      cudaMemcpy3DParms p;
+      std::memset(&p, 0, sizeof(p));
+      p.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(src), stride, g.cols, pair_stride / stride);
+      p.dstPtr = make_cudaPitchedPtr(dst, g.pitch, g.cols, (size_t)2 * g.rows);
+      p.extent = make_cudaExtent(g.cols, g.rows, n);
+      p.kind = cudaMemcpyHostToDevice;
+      CUDA_TRY(cudaMemcpy3DAsync(&p, lane.stream));
+    } else {
+      for (int i = 0; i < n; ++i)
+        CUDA_TRY(cudaMemcpy2DAsync(dst + (size_t)2 * i * g.rows * g.pitch, g.pitch, src + (size_t)i * pair_stride, stride,
+                                   g.cols, g.rows, cudaMemcpyHostToDevice, lane.stream));
+    }
+  }
+  return VSLAM_OK;
+}
+
+// sorted (row, col) feature order -> the reference's order (region by region, row-major inside a region)
+void reference_order(const vslam_fpg* h, const std::vector<uint32_t>& xy, std::vector<int>& sorted_to_ref,
+                     std::vector<int>& ref_to_sorted) {
+  const int n = (int)xy.size();
+  sorted_to_ref.resize(n);
+  ref_to_sorted.resize(n);
+  if (h->g.n_regions == 1) {
+    for (int i = 0; i < n; ++i) sorted_to_ref[i] = ref_to_sorted[i] = i;
+    return;
+  }
+  std::vector<int> region_of(n, 0);
+  for (int i = 0; i < n; ++i) {
+    const int x = xy[i] & 0xffff, y = xy[i] >> 16;
+    for (int r = 0; r < h->g.n_regions; ++r) {
+      const HostRegion& q = h->regions[r];
+      if (x >= q.x + 3 && x <= q.x + q.w - 4 && y >= q.y + 3 && y <= q.y + q.h - 4) {
+        region_of[i] = r;
+        break;
+      }
+    }
+  }
+  int k = 0;
+  for (int r = 0; r < h->g.n_regions; ++r)
+    for (int i = 0; i < n; ++i)
+      if (region_of[i] == r) {
+        ref_to_sorted[k] = i;
+        sorted_to_ref[i] = k++;
+      }
+}
+
+int fetch_xy(vslam_fpg* h, int image, int n, std::vector<uint32_t>& xy) {
+  xy.resize(n);
+  if (n) CUDA_TRY(cudaMemcpy(xy.data(), h->b.kp_xy + (size_t)image * h->g.cap, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
+}
+
+int remap_records(vslam_fpg* h, int pair, vslam_framepoint* rec, int n) {
+  if (h->g.n_regions == 1 || n == 0) return VSLAM_OK;
+  std::vector<uint32_t> xl, xr;
+  std::vector<int> s2r_l, s2r_r, tmp;
+  int rc;
+  if ((rc = fetch_xy(h, 2 * pair, h->h_n_desc[2 * pair], xl))) return rc;
+  if ((rc = fetch_xy(h, 2 * pair + 1, h->h_n_desc[2 * pair + 1], xr))) return rc;
+  reference_order(h, xl, s2r_l, tmp);
+  reference_order(h, xr, s2r_r, tmp);
+  for (int i = 0; i < n; ++i) {
+    if (rec[i].index_left >= 0) rec[i].index_left = s2r_l[rec[i].index_left];
+    if (rec[i].index_right >= 0) rec[i].index_right = s2r_r[rec[i].index_right];
+  }
+  return VSLAM_OK;
+}
+
+int get_features(vslam_fpg* h, int pair, int side, vslam_keypoint* kps, uint8_t* desc, int32_t capacity, int32_t* n_out) {
+  if (!h->initialized || pair < 0 || pair >= h->last_pairs) return fail(VSLAM_ERR_STATE, "no features for pair %d", pair);
+  if (side != 0 && side != 1) return fail(VSLAM_ERR_INVALID_ARGUMENT, "side must be 0 or 1");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int image = 2 * pair + side;
+  const int n = h->h_n_desc[image];
+  if (n_out) *n_out = n;
+  if (n > capacity) return fail(VSLAM_ERR_CAPACITY, "capacity %d < %d features", capacity, n);
+  std::vector<uint32_t> xy;
+  int rc;
+  if ((rc = fetch_xy(h, image, n, xy))) return rc;
+  std::vector<int> s2r, r2s;
+  reference_order(h, xy, s2r, r2s);
+  if (kps) {
+    std::vector<uint8_t> score(n);
+    if (n) CUDA_TRY(cudaMemcpy(score.data(), h->b.kp_score + (size_t)image * h->g.cap, n, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n; ++k) {
+      const int i = r2s[k];
+      kps[k].x = (float)(xy[i] & 0xffff);
+      kps[k].y = (float)(xy[i] >> 16);
+      kps[k].response = (float)score[i];
+    }
+  }
+  if (desc) {
+    std::vector<uint8_t> d((size_t)n * kDescBytes);
+    if (n) CUDA_TRY(cudaMemcpy(d.data(), h->b.desc + (size_t)image * h->g.cap * kDescBytes, d.size(), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n; ++k) std::memcpy(desc + (size_t)k * kDescBytes, d.data() + (size_t)r2s[k] * kDescBytes, kDescBytes);
+  }
+  return VSLAM_OK;
+}
+
+double host_matching_distance(const vslam_fpg* h, int localizing, int n_left) {   // :109-125
+  if (localizing) return std::min(0.1 * 256, h->cfg.maximum_matching_distance_triangulation);
+  const double ratio = std::min(static_cast<double>(n_left) / h->target_keypoints, 1.0);
+  return std::max(ratio * h->cfg.maximum_matching_distance_triangulation, 0.1 * 256);
+}
+
+}  // namespace
+
+extern "C" {
+
+int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
+  if (!c || !out) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  if (c->rows < 7 || c->cols < 7 || c->cols > 65535 || c->rows > 65535)
+    return fail(VSLAM_ERR_INVALID_ARGUMENT, "unsupported image size %dx%d", c->cols, c->rows);
+  const int nv = c->number_of_detectors_vertical, nh = c->number_of_detectors_horizontal;
+  if (nv < 1 || nh < 1 || nv * nh > kMaxRegions) return fail(VSLAM_ERR_INVALID_ARGUMENT, "unsupported detector grid %dx%d", nv, nh);
+  if (c->bin_size_pixels < 1) return fail(VSLAM_ERR_INVALID_ARGUMENT, "bin_size_pixels must be positive");
+  if (c->maximum_epipolar_search_offset_pixels < 0 || c->maximum_epipolar_search_offset_pixels > 100)
+    return fail(VSLAM_ERR_INVALID_ARGUMENT, "maximum_epipolar_search_offset_pixels out of range");
+  // stereo_framepoint_generator.cpp:26-34
+  const double baseline_meters = -c->bx / c->fx;
+  if (!(baseline_meters > 0))
+    return fail(VSLAM_ERR_INVALID_ARGUMENT, "StereoFramePointGenerator::configure|invalid baseline (m): '%f' verify intrinsic camera parameters", baseline_meters);
+  int rc = require_device(device);
+  if (rc) return rc;
+
+  vslam_fpg* h = new vslam_fpg();
+  h->cfg = *c;
+  h->device = device;
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+  Geometry& g = h->g;
+  g.rows = c->rows;
+  g.cols = c->cols;
+  g.pitch = (c->cols + 127) & ~127;
+  g.mask_words = ((c->cols + 31) / 32 + 3) & ~3;
+  g.n_regions = nv * nh;
+  g.bin_size = c->bin_size_pixels;
+  g.enable_binning = c->enable_keypoint_binning != 0;
+  bin_grid(g.rows, g.cols, g.bin_size, &g.rows_bin, &g.cols_bin);
+  h->target_keypoints = g.rows_bin * g.cols_bin;                    // base :308
+  h->target_per_detector = h->target_keypoints / g.n_regions;       // base :312 (Count)
+  g.cap = c->max_keypoints_per_image > 0 ? c->max_keypoints_per_image : std::max(4096, 4 * h->target_keypoints);
+  if (g.cap > 65535) g.cap = 65535;
+  h->max_batch = std::max(1, c->max_batch);
+  h->n_passes = 1 + 2 * c->maximum_epipolar_search_offset_pixels;   // stereo :45-50
+  detector_regions(g.rows, g.cols, nv, nh, h->regions);
+  for (int i = 0; i < g.n_regions; ++i) {
+    const HostRegion& q = h->regions[i];
+    if (q.x < 0 || q.y < 0 || q.x + q.w > g.cols || q.y + q.h > g.rows || q.w < 7 || q.h < 7) {
+      delete h;
+      return fail(VSLAM_ERR_INVALID_ARGUMENT, "detector region %d out of the image", i);
+    }
+    h->thresholds[i] = std::rint((double)c->detector_threshold_minimum);   // base :244, :13
+  }
+  h->sp.fx = c->fx; h->sp.fy = c->fy; h->sp.cx = c->cx; h->sp.cy = c->cy; h->sp.bx = c->bx;
+  h->sp.max_matching_distance = c->maximum_matching_distance_triangulation;
+  h->sp.min_disparity = c->minimum_disparity_pixels;
+  h->sp.target_keypoints = h->target_keypoints;
+  h->sp.localizing = 1;
+  h->out_cap = g.enable_binning ? h->target_keypoints : g.cap;
+
+  // chunk: keep image + blurred + mask of one chunk well inside the 126 MB L2
+  const size_t per_pair = (size_t)2 * g.rows * (2 * g.pitch + 4 * g.mask_words);
+  int chunk = (int)std::max<size_t>(1, (size_t)(40u << 20) / per_pair);
+  if (const char* e = std::getenv("VSLAM_CHUNK_PAIRS")) chunk = std::max(1, atoi(e));
+  h->chunk = std::min(chunk, h->max_batch);
+
+  const size_t B = h->max_batch, I = 2 * B;
+  const size_t img_bytes = (size_t)g.rows * g.pitch;
+  Buffers& b = h->b;
+  std::memset(&b, 0, sizeof(b));
+  bool ok = true;
+  auto dalloc = [&](void** p, size_t bytes) {
+    if (ok && cudaMalloc(p, bytes ? bytes : 1) != cudaSuccess) ok = false;
+  };
+  dalloc((void**)&b.image, I * img_bytes);
+  dalloc((void**)&b.raw_count, I * g.n_regions * sizeof(int32_t));
+  dalloc((void**)&b.row_ptr, I * (g.rows + 1) * sizeof(int32_t));
+  dalloc((void**)&b.kp_xy, I * g.cap * sizeof(uint32_t));
+  dalloc((void**)&b.kp_score, I * g.cap);
+  dalloc((void**)&b.desc, I * g.cap * kDescBytes);
+  dalloc((void**)&b.n_desc, I * sizeof(int32_t));
+  dalloc((void**)&b.match, B * g.cap * sizeof(int2));
+  dalloc((void**)&b.consumed_r, B * g.cap);
+  dalloc((void**)&b.n_out, B * 2 * sizeof(int32_t));
+  dalloc((void**)&b.error_flag, sizeof(int32_t));
+  dalloc((void**)&h->d_out, B * h->out_cap * sizeof(FramePointRecord));
+  dalloc((void**)&h->d_matches, (size_t)g.cap * sizeof(FramePointRecord));
+  dalloc((void**)&h->d_n_matches, sizeof(int32_t));
+  for (int l = 0; l < kLanes; ++l) {
+    dalloc((void**)&h->lanes[l].blurred, (size_t)2 * h->chunk * img_bytes);
+    dalloc((void**)&h->lanes[l].mask, (size_t)2 * h->chunk * g.rows * g.mask_words * sizeof(uint32_t));
+    if (ok && cudaStreamCreateWithFlags(&h->lanes[l].stream, cudaStreamNonBlocking) != cudaSuccess) ok = false;
+  }
+  auto halloc = [&](void** p, size_t bytes) {
+    if (ok && cudaMallocHost(p, bytes) != cudaSuccess) ok = false;
+  };
+  halloc((void**)&h->h_counts, I * g.n_regions * sizeof(int32_t));
+  halloc((void**)&h->h_n_desc, I * sizeof(int32_t));
+  halloc((void**)&h->h_n_out, B * 2 * sizeof(int32_t));
+  halloc((void**)&h->h_flag, sizeof(int32_t));
+  for (auto& e : h->clock.ev)
+    if (ok && cudaEventCreate(&e) != cudaSuccess) ok = false;
+  if (ok && cudaMemset(b.error_flag, 0, sizeof(int32_t)) != cudaSuccess) ok = false;
+  if (ok && cudaMemset(b.image, 0, I * img_bytes) != cudaSuccess) ok = false;   // row padding is never uninitialised
+  if (!ok) {
+    const cudaError_t e = cudaGetLastError();
+    vslam_fpg_destroy(h);
+    return fail(VSLAM_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
+  }
+  *h->h_flag = 0;
+  *out = h;
+  return VSLAM_OK;
+}
+
+int vslam_fpg_destroy(vslam_fpg* h) {
+  if (!h) return VSLAM_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  Buffers& b = h->b;
+  cudaFree(b.image); cudaFree(b.raw_count); cudaFree(b.row_ptr); cudaFree(b.kp_xy); cudaFree(b.kp_score);
+  cudaFree(b.desc); cudaFree(b.n_desc); cudaFree(b.match); cudaFree(b.consumed_r); cudaFree(b.n_out);
+  cudaFree(b.error_flag); cudaFree(h->d_out); cudaFree(h->d_matches); cudaFree(h->d_n_matches); cudaFree(h->d_tracked);
+  for (auto& l : h->lanes) {
+    cudaFree(l.blurred);
+    cudaFree(l.mask);
+    if (l.stream) cudaStreamDestroy(l.stream);
+  }
+  cudaFreeHost(h->h_counts); cudaFreeHost(h->h_n_desc); cudaFreeHost(h->h_n_out); cudaFreeHost(h->h_flag);
+  for (auto& e : h->clock.ev)
+    if (e) cudaEventDestroy(e);
+  delete h;
+  return VSLAM_OK;
+}
+
+int vslam_fpg_info(const vslam_fpg* h, int32_t* n_regions, int32_t* regions_xywh, int32_t* rows_bin, int32_t* cols_bin,
+                   int32_t* target) {
+  if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null handle");
+  if (n_regions) *n_regions = h->g.n_regions;
+  if (regions_xywh)
+    for (int i = 0; i < h->g.n_regions; ++i) {
+      regions_xywh[4 * i] = h->regions[i].x;
+      regions_xywh[4 * i + 1] = h->regions[i].y;
+      regions_xywh[4 * i + 2] = h->regions[i].w;
+      regions_xywh[4 * i + 3] = h->regions[i].h;
+    }
+  if (rows_bin) *rows_bin = h->g.rows_bin;
+  if (cols_bin) *cols_bin = h->g.cols_bin;
+  if (target) *target = h->target_keypoints;
+  return VSLAM_OK;
+}
+
+int vslam_fpg_get_thresholds(const vslam_fpg* h, double* t) {
+  if (!h || !t) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  for (int i = 0; i < h->g.n_regions; ++i) t[i] = h->thresholds[i];
+  return VSLAM_OK;
+}
+
+int vslam_fpg_set_thresholds(vslam_fpg* h, const double* t) {
+  if (!h || !t) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  for (int i = 0; i < h->g.n_regions; ++i) h->thresholds[i] = std::rint(t[i]);
+  return VSLAM_OK;
+}
+
+int vslam_fpg_initialize(vslam_fpg* h, const uint8_t* left, const uint8_t* right, size_t stride, int localizing,
+                         int32_t* n_left, int32_t* n_right) {
+  if (!h || !left || !right)   // stereo :75-78
+    return fail(VSLAM_ERR_INVALID_ARGUMENT, "StereoFramePointGenerator::initialize|called with empty frame");
+  if (stride < (size_t)h->g.cols) return fail(VSLAM_ERR_INVALID_ARGUMENT, "stride smaller than the image width");
+  CUDA_TRY(cudaSetDevice(h->device));
+  Lane& lane = h->lanes[0];
+  const Geometry& g = h->g;
+  int rc = upload_images(h, lane, 0, 1, left, right, stride, stride * g.rows);
+  if (rc) return rc;
+  run_detect_describe(h, lane, 0, 1);
+  CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->b.raw_count, sizeof(int32_t) * 2 * g.n_regions, cudaMemcpyDeviceToHost, lane.stream));
+  CUDA_TRY(cudaMemcpyAsync(h->h_n_desc, h->b.n_desc, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, lane.stream));
+  CUDA_TRY(cudaMemcpyAsync(h->h_flag, h->b.error_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, lane.stream));
+  CUDA_TRY(cudaStreamSynchronize(lane.stream));
+  CUDA_TRY(cudaGetLastError());
+  collect_clock(h, true, false);
+  if ((rc = check_flag(h))) {
+    cudaMemset(h->b.error_flag, 0, sizeof(int32_t));
+    return rc;
+  }
+  // adjustDetectorThresholds (base :440-459) over the two detections (L, R) of this frame
+  for (int i = 0; i < g.n_regions; ++i) {
+    double acc = 0;
+    for (int side = 0; side < 2; ++side)
+      acc += threshold_proposal(h->thresholds[i], h->h_counts[side * g.n_regions + i], h->target_per_detector,
+                                h->cfg.target_number_of_keypoints_tolerance, h->cfg.detector_threshold_maximum_change,
+                                h->cfg.detector_threshold_minimum, h->cfg.detector_threshold_maximum);
+    h->thresholds[i] = std::rint(acc / 2);
+  }
+  h->localizing = localizing != 0;
+  h->sp.localizing = h->localizing;
+  h->matching_distance = host_matching_distance(h, h->localizing, h->h_n_desc[0]);
+  h->initialized = true;
+  h->last_pairs = 1;
+  if (n_left) *n_left = h->h_n_desc[0];
+  if (n_right) *n_right = h->h_n_desc[1];
+  return VSLAM_OK;
+}
+
+int vslam_fpg_get_features(vslam_fpg* h, int side, vslam_keypoint* kps, uint8_t* desc, int32_t capacity, int32_t* n) {
+  if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null handle");
+  return get_features(h, 0, side, kps, desc, capacity, n);
+}
+
+int vslam_fpg_batch_get_features(vslam_fpg* h, int32_t pair, int side, vslam_keypoint* kps, uint8_t* desc,
+                                 int32_t capacity, int32_t* n) {
+  if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null handle");
+  return get_features(h, pair, side, kps, desc, capacity, n);
+}
+
+int vslam_fpg_get_detection_stats(vslam_fpg* h, int32_t* cl, int32_t* cr, double* matching_distance) {
+  if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null handle");
+  if (!h->initialized) return fail(VSLAM_ERR_STATE, "initialize has not run");
+  for (int i = 0; i < h->g.n_regions; ++i) {
+    if (cl) cl[i] = h->h_counts[i];
+    if (cr) cr[i] = h->h_counts[h->g.n_regions + i];
+  }
+  if (matching_distance) *matching_distance = h->matching_distance;
+  return VSLAM_OK;
+}
+
+int vslam_fpg_compute(vslam_fpg* h, const vslam_tracked_point* tracked, int32_t n_tracked, vslam_framepoint* out,
+                      int32_t capacity, int32_t* n_out, int32_t* n_matches) {
+  if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "StereoFramePointGenerator::compute|called with empty frame");
+  if (!h->initialized || h->last_pairs != 1) return fail(VSLAM_ERR_STATE, "compute without initialize");
+  if (n_tracked < 0 || (n_tracked > 0 && !tracked)) return fail(VSLAM_ERR_INVALID_ARGUMENT, "bad tracked points");
+  CUDA_TRY(cudaSetDevice(h->device));
+  Lane& lane = h->lanes[0];
+  if (n_tracked > h->tracked_cap) {
+    cudaFree(h->d_tracked);
+    h->d_tracked = nullptr;
+    h->tracked_cap = 0;
+    CUDA_TRY(cudaMalloc((void**)&h->d_tracked, sizeof(TrackedPoint) * (size_t)n_tracked * 2));
+    h->tracked_cap = n_tracked * 2;
+  }
+  if (n_tracked)
+    CUDA_TRY(cudaMemcpyAsync(h->d_tracked, tracked, sizeof(TrackedPoint) * n_tracked, cudaMemcpyHostToDevice, lane.stream));
+  run_match_select(h, lane, 0, 1, h->d_tracked, n_tracked);
+  const FramePointRecord* src = h->d_out;
+  if (!h->g.enable_binning) {   // :456-460 : every new point, in emission order
+    launch_emit_matches(h->g, h->sp, h->b, 0, h->n_passes, h->d_matches, h->g.cap, h->d_n_matches, lane.stream);
+    ++h->launches;
+    CUDA_TRY(cudaMemcpyAsync(h->h_n_out, h->d_n_matches, sizeof(int32_t), cudaMemcpyDeviceToHost, lane.stream));
+    CUDA_TRY(cudaMemcpyAsync(h->h_n_out + 1, h->b.n_out + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, lane.stream));
+    src = h->d_matches;
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(h->h_n_out, h->b.n_out, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, lane.stream));
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->h_flag, h->b.error_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, lane.stream));
+  CUDA_TRY(cudaStreamSynchronize(lane.stream));
+  CUDA_TRY(cudaGetLastError());
+  collect_clock(h, false, true);
+  int rc = check_flag(h);
+  if (rc) {
+    cudaMemset(h->b.error_flag, 0, sizeof(int32_t));
+    return rc;
+  }
+  const int n = h->h_n_out[0];
+  if (n_out) *n_out = n;
+  if (n_matches) *n_matches = h->h_n_out[1];
+  if (n > capacity) return fail(VSLAM_ERR_CAPACITY, "capacity %d < %d framepoints", capacity, n);
+  if (n && !out) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null output");
+  if (n) CUDA_TRY(cudaMemcpy(out, src, sizeof(FramePointRecord) * n, cudaMemcpyDeviceToHost));
+  return remap_records(h, 0, out, n);
+}
+
+int vslam_fpg_get_matches(vslam_fpg* h, vslam_framepoint* out, int32_t capacity, int32_t* n_out) {
+  if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null handle");
+  if (!h->initialized || h->last_pairs != 1) return fail(VSLAM_ERR_STATE, "no single-pair compute to read");
+  CUDA_TRY(cudaSetDevice(h->device));
+  Lane& lane = h->lanes[0];
+  launch_emit_matches(h->g, h->sp, h->b, 0, h->n_passes, h->d_matches, h->g.cap, h->d_n_matches, lane.stream);
+  ++h->launches;
+  int32_t n = 0;
+  CUDA_TRY(cudaMemcpyAsync(&n, h->d_n_matches, sizeof(int32_t), cudaMemcpyDeviceToHost, lane.stream));
+  CUDA_TRY(cudaStreamSynchronize(lane.stream));
+  if (n_out) *n_out = n;
+  if (n > capacity) return fail(VSLAM_ERR_CAPACITY, "capacity %d < %d matches", capacity, n);
+  if (n) CUDA_TRY(cudaMemcpy(out, h->d_matches, sizeof(FramePointRecord) * n, cudaMemcpyDeviceToHost));
+  return remap_records(h, 0, out, n);
+}
+
+int vslam_fpg_set_profiling(vslam_fpg* h, int enabled) {
+  if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null handle");
+  h->profiling = enabled != 0;
+  return VSLAM_OK;
+}
+
+int vslam_fpg_get_time_consumption(vslam_fpg* h, double* detect, double* describe, double* match) {
+  if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null handle");
+  if (detect) *detect = h->t_detect;
+  if (describe) *describe = h->t_describe;
+  if (match) *match = h->t_match;
+  return VSLAM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// batched form
+// ---------------------------------------------------------------------------------------------------------------
+
+static int check_batch(vslam_fpg* h, int32_t n_pairs) {
+  if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null handle");
+  if (n_pairs < 1 || n_pairs > h->max_batch) return fail(VSLAM_ERR_INVALID_ARGUMENT, "n_pairs %d outside [1, max_batch=%d]", n_pairs, h->max_batch);
+  return VSLAM_OK;
+}
+
+// lanes alternate over chunks; before a lane is reused its previous work is already ordered on its stream
+static int batch_pipeline(vslam_fpg* h, int32_t n_pairs, const uint8_t* left, const uint8_t* right, size_t stride,
+                          size_t pair_stride, bool upload, bool run, vslam_framepoint* out, int32_t out_capacity) {
+  int li = 0;
+  for (int p0 = 0; p0 < n_pairs; p0 += h->chunk, li = (li + 1) % kLanes) {
+    const int n = std::min(h->chunk, n_pairs - p0);
+    Lane& lane = h->lanes[h->profiling ? 0 : li];
+    if (upload) {
+      int rc = upload_images(h, lane, p0, n, left, right, stride, pair_stride);
+      if (rc) return rc;
+    }
+    if (run) {
+      run_detect_describe(h, lane, p0, n);
+      run_match_select(h, lane, p0, n, nullptr, 0);
+      if (h->profiling) {
+        CUDA_TRY(cudaStreamSynchronize(lane.stream));
+        collect_clock(h, true, true);
+      }
+    }
+    if (out) {
+      if (out_capacity == h->out_cap) {
+        CUDA_TRY(cudaMemcpyAsync(out + (size_t)p0 * out_capacity, h->d_out + (size_t)p0 * h->out_cap,
+                                 sizeof(FramePointRecord) * (size_t)n * h->out_cap, cudaMemcpyDeviceToHost, lane.stream));
+      } else {
+        const size_t w = sizeof(FramePointRecord) * (size_t)std::min(out_capacity, h->out_cap);
+        CUDA_TRY(cudaMemcpy2DAsync(out + (size_t)p0 * out_capacity, sizeof(FramePointRecord) * (size_t)out_capacity,
+                                   h->d_out + (size_t)p0 * h->out_cap, sizeof(FramePointRecord) * (size_t)h->out_cap, w, n,
+                                   cudaMemcpyDeviceToHost, lane.stream));
+      }
+    }
+  }
+  return VSLAM_OK;
+}
+
+static int batch_finish(vslam_fpg* h, int32_t n_pairs) {
+  // counts travel on lane 0 after every lane has finished its kernels
+  for (int l = 1; l < kLanes; ++l) CUDA_TRY(cudaStreamSynchronize(h->lanes[l].stream));
+  cudaStream_t s = h->lanes[0].stream;
+  CUDA_TRY(cudaMemcpyAsync(h->h_n_out, h->b.n_out, sizeof(int32_t) * 2 * n_pairs, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->h_n_desc, h->b.n_desc, sizeof(int32_t) * 2 * n_pairs, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->b.raw_count, sizeof(int32_t) * 2 * n_pairs * h->g.n_regions, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->h_flag, h->b.error_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  int rc = check_flag(h);
+  if (rc) cudaMemset(h->b.error_flag, 0, sizeof(int32_t));
+  return rc;
+}
+
+int vslam_fpg_batch_upload(vslam_fpg* h, int32_t n_pairs, const uint8_t* left, const uint8_t* right, size_t stride,
+                           size_t pair_stride) {
+  int rc = check_batch(h, n_pairs);
+  if (rc) return rc;
+  if (!left || !right || stride < (size_t)h->g.cols) return fail(VSLAM_ERR_INVALID_ARGUMENT, "bad image arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  rc = batch_pipeline(h, n_pairs, left, right, stride, pair_stride, true, false, nullptr, 0);
+  if (rc) return rc;
+  for (auto& l : h->lanes) CUDA_TRY(cudaStreamSynchronize(l.stream));
+  return VSLAM_OK;
+}
+
+int vslam_fpg_batch_run(vslam_fpg* h, int32_t n_pairs, int localizing) {
+  int rc = check_batch(h, n_pairs);
+  if (rc) return rc;
+  if (!h->g.enable_binning) return fail(VSLAM_ERR_INVALID_ARGUMENT, "batched runs require enable_keypoint_binning");
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->localizing = localizing != 0;
+  h->sp.localizing = h->localizing;
+  // lane 1 must see the uploads / previous results ordered on lane 0 and vice versa: callers synchronise
+  // between upload and run (batch_upload does), so plain issue order is enough here
+  rc = batch_pipeline(h, n_pairs, nullptr, nullptr, 0, 0, false, true, nullptr, 0);
+  if (rc) return rc;
+  h->initialized = true;
+  h->last_pairs = n_pairs;
+  return VSLAM_OK;
+}
+
+int vslam_fpg_batch_download(vslam_fpg* h, int32_t n_pairs, vslam_framepoint* out, int32_t capacity_per_pair,
+                             int32_t* n_framepoints, int32_t* n_matches, int32_t* n_left, int32_t* n_right) {
+  int rc = check_batch(h, n_pairs);
+  if (rc) return rc;
+  if (!h->initialized || h->last_pairs < n_pairs) return fail(VSLAM_ERR_STATE, "no batched run to download");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (out) {
+    rc = batch_pipeline(h, n_pairs, nullptr, nullptr, 0, 0, false, false, out, capacity_per_pair);
+    if (rc) return rc;
+  }
+  if ((rc = batch_finish(h, n_pairs))) return rc;
+  for (int i = 0; i < n_pairs; ++i) {
+    if (n_framepoints) n_framepoints[i] = h->h_n_out[2 * i];
+    if (n_matches) n_matches[i] = h->h_n_out[2 * i + 1];
+    if (n_left) n_left[i] = h->h_n_desc[2 * i];
+    if (n_right) n_right[i] = h->h_n_desc[2 * i + 1];
+    if (out && h->h_n_out[2 * i] > capacity_per_pair)
+      return fail(VSLAM_ERR_CAPACITY, "capacity_per_pair %d < %d framepoints of pair %d", capacity_per_pair, h->h_n_out[2 * i], i);
+    if (out && (rc = remap_records(h, i, out + (size_t)i * capacity_per_pair, h->h_n_out[2 * i]))) return rc;
+  }
+  return VSLAM_OK;
+}
+
+int vslam_fpg_batch_process(vslam_fpg* h, int32_t n_pairs, const uint8_t* left, const uint8_t* right, size_t stride,
+                            size_t pair_stride, int localizing, vslam_framepoint* out, int32_t capacity_per_pair,
+                            int32_t* n_framepoints) {
+  int rc = check_batch(h, n_pairs);
+  if (rc) return rc;
+  if (!left || !right || stride < (size_t)h->g.cols) return fail(VSLAM_ERR_INVALID_ARGUMENT, "bad image arguments");
+  if (!h->g.enable_binning) return fail(VSLAM_ERR_INVALID_ARGUMENT, "batched runs require enable_keypoint_binning");
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->localizing = localizing != 0;
+  h->sp.localizing = h->localizing;
+  rc = batch_pipeline(h, n_pairs, left, right, stride, pair_stride, true, true, out, capacity_per_pair);
+  if (rc) return rc;
+  h->initialized = true;
+  h->last_pairs = n_pairs;
+  if ((rc = batch_finish(h, n_pairs))) return rc;
+  for (int i = 0; i < n_pairs; ++i) {
+    if (n_framepoints) n_framepoints[i] = h->h_n_out[2 * i];
+    if (out && h->h_n_out[2 * i] > capacity_per_pair)
+      return fail(VSLAM_ERR_CAPACITY, "capacity_per_pair %d < %d framepoints of pair %d", capacity_per_pair, h->h_n_out[2 * i], i);
+    if (out && (rc = remap_records(h, i, out + (size_t)i * capacity_per_pair, h->h_n_out[2 * i]))) return rc;
+  }
+  return VSLAM_OK;
+}
+
+void* vslam_fpg_stream(vslam_fpg* h) { return h ? (void*)h->lanes[0].stream : nullptr; }
+
+int vslam_fpg_synchronize(vslam_fpg* h) {
+  if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  for (auto& l : h->lanes) CUDA_TRY(cudaStreamSynchronize(l.stream));
+  return VSLAM_OK;
+}
+
+int64_t vslam_fpg_launch_count(const vslam_fpg* h) { return h ? h->launches : 0; }
+
+int vslam_fpg_debug_keypoint_mask(vslam_fpg* h, int32_t pair, int side, uint32_t* words) {
+  if (!h || !words) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  if (!h->initialized || pair < 0 || pair >= h->last_pairs || h->last_pairs > h->chunk)
+    return fail(VSLAM_ERR_STATE, "debug taps need a run of at most chunk=%d pairs", h->chunk);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const Geometry& g = h->g;
+  const int w = (g.cols + 31) / 32;
+  CUDA_TRY(cudaMemcpy2D(words, sizeof(uint32_t) * w, h->lanes[0].mask + ((size_t)2 * pair + side) * g.rows * g.mask_words,
+                        sizeof(uint32_t) * g.mask_words, sizeof(uint32_t) * w, g.rows, cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
+}
+
+int vslam_fpg_debug_blurred(vslam_fpg* h, int32_t pair, int side, uint8_t* image) {
+  if (!h || !image) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  if (!h->initialized || pair < 0 || pair >= h->last_pairs || h->last_pairs > h->chunk)
+    return fail(VSLAM_ERR_STATE, "debug taps need a run of at most chunk=%d pairs", h->chunk);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const Geometry& g = h->g;
+  CUDA_TRY(cudaMemcpy2D(image, g.cols, h->lanes[0].blurred + ((size_t)2 * pair + side) * g.rows * g.pitch, g.pitch, g.cols,
+                        g.rows, cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
+}
+
+double vslam_threshold_proposal(double threshold, int32_t n_keypoints, double target, double tolerance,
+                                double maximum_change, double threshold_minimum, double threshold_maximum) {
+  return threshold_proposal(threshold, n_keypoints, target, tolerance, maximum_change, threshold_minimum, threshold_maximum);
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+// kernels.cuh -- launch interface of the framepoint-generation and aligner kernels (sm_100a).
+#pragma once
+
+#include "common.cuh"
+
+namespace vslam {
+
+struct RegionTable {
+  Region r[kMaxRegions];
+  int threshold[kMaxRegions];   // rint(detector threshold), clamped to [0, 255] like cv::FAST
+};
+
+struct StereoParams {
+  double fx, fy, cx, cy, bx;
+  double max_matching_distance;   // maximum_matching_distance_triangulation
+  double min_disparity;           // minimum_disparity_pixels
+  int target_keypoints;           // _target_number_of_keypoints
+  int localizing;                 // frame->status() == Frame::Localizing
+};
+
+struct TrackedPoint {   // == vslam_tracked_point
+  int32_t row, col, has_previous, reserved;
+  double disparity, distance;
+};
+
+struct FramePointRecord {   // == vslam_framepoint
+  int32_t index_left, index_right;
+  float xl, yl, xr, yr;
+  int32_t distance, epipolar_offset;
+  double camera[3];
+};
+
+// all launches are asynchronous on `stream`; image ranges are [first_image, first_image + n_images)
+void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, int first_image, int n_images,
+                 cudaStream_t stream);
+void launch_compact(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream);
+void launch_blur(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream);
+void launch_describe(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream);
+// one launch per epipolar offset (pass index -> offset 0,+1,-1,+2,...)
+void launch_match(const Geometry& g, const StereoParams& sp, const Buffers& b, int first_pair, int n_pairs, int pass,
+                  int epipolar_offset, cudaStream_t stream);
+void launch_select(const Geometry& g, const StereoParams& sp, const Buffers& b, int first_pair, int n_pairs,
+                   int n_passes, const TrackedPoint* tracked, int n_tracked, FramePointRecord* out,
+                   int out_capacity_per_pair, cudaStream_t stream);
+void launch_emit_matches(const Geometry& g, const StereoParams& sp, const Buffers& b, int pair, int n_passes,
+                         FramePointRecord* out, int out_capacity, int32_t* n_out, cudaStream_t stream);
+int kernels_per_match_pass();
+
+// ---- aligner ----
+struct AlignerBuffers {
+  const double* moving;   // SoA: [3][stride]
+  const double* fixed;    // SoA: [4 or 3][stride]
+  const double* omega;    // SoA: [1 or 2][stride]
+  const double* wt;       // [stride]
+  double* errors;         // [stride]
+  uint8_t* inliers;       // [stride]
+  double* partials;       // [grid][32]
+  double* system;         // [32] : H upper triangle (21), b (6), total error, inliers
+  unsigned int* ticket;   // [1]
+  int stride;
+};
+
+struct AlignerCamera {
+  double K[9];
+  double baseline[3];
+  double rows, cols;
+  double min_depth;
+};
+
+int aligner_grid(int n, int sm_count);
+void launch_linearize(int kind, int n, const AlignerBuffers& b, const AlignerCamera& cam, const double T[12],
+                      int ignore_outliers, double kernel, int grid, cudaStream_t stream);
+
+}  // namespace vslam

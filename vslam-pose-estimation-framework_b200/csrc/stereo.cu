@@ -1,0 +1,303 @@
+// stereo.cu -- K5 match_kernel (epipolar row scan, popc-256 Hamming, warp argmin, monotone cursor),
+//              K6 select_kernel (bin regularisation + triangulation + ordered output), emit_matches_kernel.
+//
+// Replaces the scan loop, the bin rule and getPointInLeftCamera of StereoFramePointGenerator::compute
+// (reference src/framepoint_generation/stereo_framepoint_generator.cpp:278-426, 147-155/371-394/435-455, 871-895)
+// and the adaptive triangulation distance of ::initialize (:109-125).  Semantics: SURVEY.md Appendix A.4/A.5.
+//
+// Parallel decomposition that keeps the reference's sequential semantics:
+//   * within one epipolar pass, image rows are independent (the right cursor never crosses a row except forward
+//     to the row's first right feature) -> one warp per (pair, left row); inside the row the left features are
+//     visited in ascending column and the cursor `index_R = index_best_R + 1` is carried sequentially;
+//   * passes (epipolar offsets 0,+1,-1,...) are separate launches; features matched in an earlier pass are skipped,
+//     which equals the reference's prune() because pruning preserves order;
+//   * the bin rule is order dependent (partial-order dominance): one thread per bin replays that bin's candidates in
+//     emission order (pass, row, col).
+#include "kernels.cuh"
+
+namespace vslam {
+
+namespace {
+
+// stereo_framepoint_generator.cpp:109-125 ; 0.1 * SRRG_PROSLAM_DESCRIPTOR_SIZE_BITS with 256 bits
+__device__ __forceinline__ double triangulation_threshold(const StereoParams& sp, int n_left) {
+  const double tenth = __dmul_rn(0.1, 256.0);
+  if (sp.localizing) return fmin(tenth, sp.max_matching_distance);
+  const double ratio = fmin(__ddiv_rn((double)n_left, (double)sp.target_keypoints), 1.0);
+  return fmax(__dmul_rn(ratio, sp.max_matching_distance), tenth);
+}
+
+__device__ __forceinline__ int popc256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+         __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__global__ void __launch_bounds__(256) match_kernel(Geometry g, StereoParams sp, const int32_t* __restrict__ row_ptr,
+                                                    const uint32_t* __restrict__ kp_xy,
+                                                    const uint8_t* __restrict__ desc,
+                                                    const int32_t* __restrict__ n_desc, int2* __restrict__ match,
+                                                    uint8_t* __restrict__ consumed_r, int pass, int offset) {
+  const int pair = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= g.rows) return;
+  const int rrow = row - offset;   // left.row == right.row + offset
+  if (rrow < 0 || rrow >= g.rows) return;
+  const int il = 2 * pair, ir = 2 * pair + 1;
+  const int32_t* rpl = row_ptr + (size_t)il * (g.rows + 1);
+  const int32_t* rpr = row_ptr + (size_t)ir * (g.rows + 1);
+  const int lb = rpl[row], le = rpl[row + 1];
+  if (lb == le) return;
+  const int rb = rpr[rrow], re = rpr[rrow + 1];
+  if (rb == re) return;
+
+  const double thr = triangulation_threshold(sp, n_desc[il]);
+  const uint32_t* xyl = kp_xy + (size_t)il * g.cap;
+  const uint32_t* xyr = kp_xy + (size_t)ir * g.cap;
+  const uint4* dl = reinterpret_cast<const uint4*>(desc + (size_t)il * g.cap * kDescBytes);
+  const uint4* dr = reinterpret_cast<const uint4*>(desc + (size_t)ir * g.cap * kDescBytes);
+  int2* m = match + (size_t)pair * g.cap;
+  uint8_t* used = consumed_r + (size_t)pair * g.cap;
+
+  int cursor = rb;
+  for (int i = lb; i < le; ++i) {
+    if (pass > 0 && m[i].x >= 0) continue;   // pruned after an earlier pass
+    const int col_l = (int)(xyl[i] & 0xffffu);
+    const uint4 a0 = dl[2 * i], a1 = dl[2 * i + 1];
+    unsigned best = 0xffffffffu;
+    for (int s = cursor + lane; s < re; s += 32) {
+      const int col_r = (int)(xyr[s] & 0xffffu);
+      if (col_l - col_r < 0) break;            // :333 (columns ascend, so the lane's later candidates fail too)
+      if (pass > 0 && used[s]) continue;
+      const int d = popc256(a0, a1, dr[2 * s], dr[2 * s + 1]);
+      const unsigned key = ((unsigned)d << 16) | (unsigned)(s - rb);
+      best = min(best, key);                   // strict '<' of :342 == lowest index among equal distances
+    }
+    best = __reduce_min_sync(0xffffffffu, best);
+    if (best == 0xffffffffu) continue;
+    const int d = (int)(best >> 16);
+    const int s = rb + (int)(best & 0xffffu);
+    if (!((double)d < thr)) continue;                                        // :342/:353
+    const int col_r = (int)(xyr[s] & 0xffffu);
+    if ((double)(col_l - col_r) < sp.min_disparity) continue;                // :358-361, cursor NOT advanced
+    if (lane == 0) {
+      m[i] = make_int2(s, d | (pass << 16));
+      used[s] = 1;
+    }
+    cursor = s + 1;                                                          // :414
+  }
+}
+
+// stereo_framepoint_generator.cpp:871-895 ; x, y are integer-valued floats
+__device__ __forceinline__ void triangulate(const StereoParams& sp, float xl, float yl, float xr, float yr,
+                                            double out[3]) {
+  const double z = __ddiv_rn(sp.bx, (double)__fsub_rn(xr, xl));
+  out[0] = __dmul_rn(__dmul_rn(__ddiv_rn(1.0, sp.fx), __dsub_rn((double)xl, sp.cx)), z);
+  out[1] = __dmul_rn(__dmul_rn(__ddiv_rn(1.0, sp.fy), __dsub_rn(__ddiv_rn((double)__fadd_rn(yl, yr), 2.0), sp.cy)), z);
+  out[2] = z;
+}
+
+__device__ __forceinline__ void write_record(const StereoParams& sp, FramePointRecord* o, int i, int s, int dist,
+                                             int offset, uint32_t ql, uint32_t qr) {
+  FramePointRecord r;
+  r.index_left = i;
+  r.index_right = s;
+  r.xl = (float)(ql & 0xffffu);
+  r.yl = (float)(ql >> 16);
+  r.xr = (float)(qr & 0xffffu);
+  r.yr = (float)(qr >> 16);
+  r.distance = dist;
+  r.epipolar_offset = offset;
+  triangulate(sp, r.xl, r.yl, r.xr, r.yr, r.camera);
+  *o = r;
+}
+
+__device__ __forceinline__ int pass_to_offset(int pass) {   // :45-50 : 0, +1, -1, +2, -2, ...
+  return pass == 0 ? 0 : ((pass & 1) ? (pass + 1) / 2 : -(pass / 2));
+}
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  int woff = 0;
+  total = 0;
+  for (int w = 0; w < 8; ++w) {
+    if (w < warp) woff += s_warp[w];
+    total += s_warp[w];
+  }
+  __syncthreads();
+  return woff + inc - v;
+}
+
+// one CTA per pair; thread per bin replays the bin's candidates in emission order
+__global__ void __launch_bounds__(256) select_kernel(Geometry g, StereoParams sp, const int32_t* __restrict__ row_ptr,
+                                                     const uint32_t* __restrict__ kp_xy,
+                                                     const int32_t* __restrict__ n_desc,
+                                                     const int2* __restrict__ match, int n_passes,
+                                                     const TrackedPoint* __restrict__ tracked, int n_tracked,
+                                                     FramePointRecord* __restrict__ out, int out_cap,
+                                                     int32_t* __restrict__ n_out, int32_t* __restrict__ error_flag) {
+  __shared__ int s_warp[8];
+  const int pair = blockIdx.x;
+  const int il = 2 * pair, ir = 2 * pair + 1;
+  const int32_t* rpl = row_ptr + (size_t)il * (g.rows + 1);
+  const uint32_t* xyl = kp_xy + (size_t)il * g.cap;
+  const uint32_t* xyr = kp_xy + (size_t)ir * g.cap;
+  const int2* m = match + (size_t)pair * g.cap;
+  FramePointRecord* o = out + (size_t)pair * out_cap;
+  const int n_bins = g.rows_bin * g.cols_bin;
+  const double bs = (double)g.bin_size;
+
+  // number_of_new_points (:397-398)
+  {
+    const int nl = n_desc[il];
+    int c = 0;
+    for (int i = threadIdx.x; i < nl; i += 256) c += m[i].x >= 0;
+    int total;
+    block_exclusive_scan(c, s_warp, total);
+    if (threadIdx.x == 0) n_out[2 * pair + 1] = total;
+  }
+
+  int carry = 0;
+  for (int b0 = 0; b0 < n_bins; b0 += 256) {
+    const int bin = b0 + threadIdx.x;
+    int win = INT32_MIN;   // >= 0: sorted left index ; < 0 (not MIN): -(k+1) tracked point k
+    if (bin < n_bins) {
+      const int rbin = bin / g.cols_bin, cbin = bin - rbin * g.cols_bin;
+      bool has_prev = false;
+      double cur_disp = 0, cur_dist = 0;
+      for (int k = 0; k < n_tracked; ++k) {                                   // :147-155
+        const TrackedPoint t = tracked[k];
+        if (__double2int_rn(__ddiv_rn((double)t.row, bs)) == rbin && __double2int_rn(__ddiv_rn((double)t.col, bs)) == cbin) {
+          win = -(k + 1);
+          has_prev = t.has_previous != 0;
+          cur_disp = t.disparity;
+          cur_dist = t.distance;
+        }
+      }
+      const int r_lo = max(0, rbin * g.bin_size - g.bin_size / 2 - 1);
+      const int r_hi = min(g.rows - 1, rbin * g.bin_size + g.bin_size / 2 + 1);
+      for (int pass = 0; pass < n_passes; ++pass) {
+        for (int r = r_lo; r <= r_hi; ++r) {
+          if (__double2int_rn(__ddiv_rn((double)r, bs)) != rbin) continue;
+          for (int i = rpl[r]; i < rpl[r + 1]; ++i) {
+            const int2 mm = m[i];
+            if (mm.x < 0 || (mm.y >> 16) != pass) continue;
+            const int col = (int)(xyl[i] & 0xffffu);
+            if (__double2int_rn(__ddiv_rn((double)col, bs)) != cbin) continue;
+            const double disp = (double)(col - (int)(xyr[mm.x] & 0xffffu));    // frame_point.cpp:19
+            const double dist = (double)(mm.y & 0xffff);
+            if (win != INT32_MIN) {                                           // :378-389
+              if (!has_prev && disp > cur_disp && dist <= cur_dist) {
+                win = i;
+                cur_disp = disp;
+                cur_dist = dist;
+              }
+            } else {                                                          // :390-393
+              win = i;
+              has_prev = false;
+              cur_disp = disp;
+              cur_dist = dist;
+            }
+          }
+        }
+      }
+      if (win != INT32_MIN && has_prev) win = INT32_MIN;                      // :443
+    }
+    int total;
+    const int pos = carry + block_exclusive_scan(win != INT32_MIN, s_warp, total);
+    if (win != INT32_MIN) {
+      if (pos < out_cap) {
+        if (win >= 0) {
+          const int2 mm = m[win];
+          write_record(sp, &o[pos], win, mm.x, mm.y & 0xffff, pass_to_offset(mm.y >> 16), xyl[win], xyr[mm.x]);
+        } else {
+          FramePointRecord r = {};
+          r.index_left = win;
+          r.index_right = -1;
+          o[pos] = r;
+        }
+      } else {
+        atomicExch(error_flag, 2);
+      }
+    }
+    carry += total;
+  }
+  if (threadIdx.x == 0) n_out[2 * pair] = min(carry, out_cap);
+}
+
+// all new matches of one pair in emission order (pass, row, col): framepoints_new of :163,397, and the output
+// of compute() when binning is disabled (:456-460)
+__global__ void __launch_bounds__(256) emit_matches_kernel(Geometry g, StereoParams sp,
+                                                           const uint32_t* __restrict__ kp_xy,
+                                                           const int32_t* __restrict__ n_desc,
+                                                           const int2* __restrict__ match, int n_passes,
+                                                           FramePointRecord* __restrict__ out, int out_cap,
+                                                           int32_t* __restrict__ n_out, int32_t* __restrict__ error_flag) {
+  __shared__ int s_warp[8];
+  const int pair = blockIdx.x;
+  const int il = 2 * pair, ir = 2 * pair + 1;
+  const uint32_t* xyl = kp_xy + (size_t)il * g.cap;
+  const uint32_t* xyr = kp_xy + (size_t)ir * g.cap;
+  const int2* m = match + (size_t)pair * g.cap;
+  FramePointRecord* o = out + (size_t)pair * out_cap;
+  const int nl = n_desc[il];
+  int carry = 0;
+  for (int pass = 0; pass < n_passes; ++pass) {
+    for (int b0 = 0; b0 < nl; b0 += 256) {
+      const int i = b0 + threadIdx.x;
+      int2 mm = make_int2(-1, 0);
+      if (i < nl) mm = m[i];
+      const bool on = mm.x >= 0 && (mm.y >> 16) == pass;
+      int total;
+      const int pos = carry + block_exclusive_scan(on, s_warp, total);
+      if (on) {
+        if (pos < out_cap) write_record(sp, &o[pos], i, mm.x, mm.y & 0xffff, pass_to_offset(pass), xyl[i], xyr[mm.x]);
+        else atomicExch(error_flag, 2);
+      }
+      carry += total;
+    }
+  }
+  if (threadIdx.x == 0) n_out[pair] = min(carry, out_cap);
+}
+
+}  // namespace
+
+void launch_match(const Geometry& g, const StereoParams& sp, const Buffers& b, int first_pair, int n_pairs, int pass,
+                  int epipolar_offset, cudaStream_t stream) {
+  if (pass == 0) {
+    cudaMemsetAsync(b.match + (size_t)first_pair * g.cap, 0xff, sizeof(int2) * (size_t)g.cap * n_pairs, stream);
+    cudaMemsetAsync(b.consumed_r + (size_t)first_pair * g.cap, 0, (size_t)g.cap * n_pairs, stream);
+  }
+  dim3 grid((g.rows + 7) / 8, n_pairs);
+  match_kernel<<<grid, 256, 0, stream>>>(g, sp, b.row_ptr + (size_t)2 * first_pair * (g.rows + 1),
+                                         b.kp_xy + (size_t)2 * first_pair * g.cap,
+                                         b.desc + (size_t)2 * first_pair * g.cap * kDescBytes, b.n_desc + 2 * first_pair,
+                                         b.match + (size_t)first_pair * g.cap, b.consumed_r + (size_t)first_pair * g.cap,
+                                         pass, epipolar_offset);
+}
+
+void launch_select(const Geometry& g, const StereoParams& sp, const Buffers& b, int first_pair, int n_pairs,
+                   int n_passes, const TrackedPoint* tracked, int n_tracked, FramePointRecord* out,
+                   int out_capacity_per_pair, cudaStream_t stream) {
+  select_kernel<<<n_pairs, 256, 0, stream>>>(g, sp, b.row_ptr + (size_t)2 * first_pair * (g.rows + 1),
+                                             b.kp_xy + (size_t)2 * first_pair * g.cap, b.n_desc + 2 * first_pair,
+                                             b.match + (size_t)first_pair * g.cap, n_passes, tracked, n_tracked,
+                                             out + (size_t)first_pair * out_capacity_per_pair, out_capacity_per_pair,
+                                             b.n_out + 2 * first_pair, b.error_flag);
+}
+
+void launch_emit_matches(const Geometry& g, const StereoParams& sp, const Buffers& b, int pair, int n_passes,
+                         FramePointRecord* out, int out_capacity, int32_t* n_out, cudaStream_t stream) {
+  emit_matches_kernel<<<1, 256, 0, stream>>>(g, sp, b.kp_xy + (size_t)2 * pair * g.cap, b.n_desc + 2 * pair,
+                                             b.match + (size_t)pair * g.cap, n_passes, out, out_capacity, n_out,
+                                             b.error_flag);
+}
+
+}  // namespace vslam
