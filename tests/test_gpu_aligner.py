@@ -27,7 +27,10 @@ def _pair(kind, n, acfg, seed=424242, cam=None):
 def _close(got, want):
     scale = np.abs(want["H"]).max()
     np.testing.assert_allclose(got["H"], want["H"], rtol=1e-10, atol=1e-12 * scale)
-    np.testing.assert_allclose(got["b"], want["b"], rtol=1e-10, atol=1e-12 * np.abs(want["b"]).max())
+    # b is a cancelling sum near the optimum: bound the absolute error by the Cauchy-Schwarz norm of its terms,
+    # sum |J_i w e| <= sqrt(H_ii * chi2), at 1e-13 of that norm
+    b_atol = 1e-13 * np.sqrt(np.abs(np.diag(want["H"])) * max(want["total_error"], 0.0))
+    assert np.all(np.abs(got["b"] - want["b"]) <= 1e-10 * np.abs(want["b"]) + b_atol), (got["b"], want["b"])
     np.testing.assert_allclose(got["total_error"], want["total_error"], rtol=1e-12)
     assert got["inliers"] == want["inliers"] and got["outliers"] == want["outliers"]
 
@@ -97,7 +100,8 @@ def test_converge_matches_oracle(kind, acfg):
     ang, dist = _pose_delta(gpu.previousToCurrent(), want["T"])
     assert ang <= 1e-6 and dist <= 1e-5
     assert got["inliers"] == want["inliers"]
-    np.testing.assert_allclose(gpu.information_matrix, want["information"], rtol=1e-8)
+    np.testing.assert_allclose(gpu.information_matrix, want["information"], rtol=1e-8,
+                               atol=1e-12 * np.abs(want["information"]).max())
     assert np.array_equal(gpu.inliers(), cpu.inliers.astype(bool))
     # and it is the right answer
     ang, dist = _pose_delta(gpu.previousToCurrent(), c["T_true"])
