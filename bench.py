@@ -1,0 +1,358 @@
+#!/usr/bin/env python3
+"""bench.py -- stereo frames/s of the hot path (framepoint generation + aligner linearize) on N B200s.
+
+Workload (BASELINE.json configs[2], "configuration_kitti_fast.yaml, 4096 independent KITTI-shape stereo pairs
+batched and sharded across 1/2/4/8 B200"): every rank owns one GPU and a batch of `--pairs` independent 1241x376
+pairs, each processed as a first frame (status Localizing).  One step = one pass over the rank's batch:
+
+    initialize (FAST + NMS, border filter, blur, rBRIEF)  ->  compute (epipolar Hamming scan, bins, triangulation)
+    ->  StereoUVAligner initialize + `--rounds` x linearize per pair over the pair's new framepoints
+
+value   : whole-job frames/s with the images already resident in HBM (CUDA events, max over ranks)
+e2e     : the same through the C-ABI call that takes HOST buffers (H2D of the images and D2H of the framepoint
+          records and normal equations inside the timed region)
+roofline: dominant kernel, algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
+cpu_baseline / --impl reference: the oracle pipeline with OpenCV primitives (tier B) on the host cores.
+
+Launch: python bench.py [--gpus N --steps K --warmup W]; for N > 1 under torch.distributed.run (one rank per GPU).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "stereo frames/s (framepoint gen + aligner linearize)"
+CONFIG_NAME = "kitti_fast"
+KERNEL_OF_INTEREST = "fast_nms"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=4096, help="stereo pairs per rank per step")
+    ap.add_argument("--distinct", type=int, default=256, help="distinct synthetic pairs generated per rank")
+    ap.add_argument("--rounds", type=int, default=10, help="linearize rounds per pair per step (BASELINE config 4)")
+    ap.add_argument("--cpu-sample", type=int, default=192, help="pairs of the single-thread CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU side (oracle; the checker timed as the reference's CPU path -- never on the product path)
+# ------------------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init(left, right, rounds):
+    _CPU.update(left=left, right=right, rounds=rounds)
+
+
+def _cpu_pair(i):
+    """one stereo pair through the reference's CPU path (OpenCV primitives, 1 thread): returns n framepoints"""
+    from oracle import pipeline, tier_a
+    from vslam_b200 import configs, synth
+    cfg, acfg = configs.BY_NAME[CONFIG_NAME], configs.ALIGNER_BY_NAME[CONFIG_NAME]
+    cam = synth.camera(cfg.camera)
+    if "gen" not in _CPU:
+        _CPU["gen"] = pipeline.StereoFramePointGeneratorOracle(cfg, cam, "b")
+        _CPU["T"] = _prior()
+    gen = _CPU["gen"]
+    gen.thresholds[:] = cfg.detector_threshold_minimum       # every pair is a first frame
+    gen.initialize(_CPU["left"][i], _CPU["right"][i], True)
+    gen.compute()
+    fp = gen.framepoints()
+    moving = np.ascontiguousarray(fp["cam"])
+    fixed = np.stack([fp["xl"], fp["yl"], fp["xr"], fp["yr"]], 1).astype(np.float64)
+    wt = np.minimum(acfg.maximum_reliable_depth_meters / moving[:, 2], 1.0) if len(fp) else np.zeros(0)
+    al = tier_a.Aligner("stereouv", moving, fixed, np.ones(len(fp)), wt, cam.K, cam.baseline, cam.rows, cam.cols,
+                        acfg.minimum_reliable_depth_meters, acfg.maximum_error_kernel)
+    for _ in range(_CPU["rounds"]):
+        al.linearize(_CPU["T"], False)
+    return len(fp)
+
+
+def _prior():
+    from vslam_b200 import synth
+    T = synth.true_motion().copy()
+    T[:, 3] *= 0.05
+    return T
+
+
+def cpu_baseline(left, right, rounds, sample):
+    import cv2
+    cv2.setNumThreads(0)
+    n = min(sample, len(left))
+    _cpu_init(left, right, rounds)
+    _cpu_pair(0)                                               # warm-up (imports, first-touch)
+    t0 = time.perf_counter()
+    for i in range(n):
+        _cpu_pair(i)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+            "sample": "%d of the same KITTI-shape pairs, oracle tier B (cv2 %s FAST/ORB with cv2.setNumThreads(0) as "
+                      "executables/app.cpp:96, C -O2 stereo scan/bins/triangulation/linearize x%d), one thread; the "
+                      "reference's dead use_matches FLANN block is not executed" % (n, cv2.__version__, rounds),
+            "seconds": dt}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle tier B) on every host core, one process per core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+
+    import cv2
+    from vslam_b200 import configs, synth
+    cfg = configs.BY_NAME[CONFIG_NAME]
+    cores = len(os.sched_getaffinity(0))
+    per_step = max(cores * 2, 32)
+    distinct = min(args.distinct, per_step)
+    left, right = synth.band_world_batch(cfg.camera, range(distinct), workers=min(cores, 32))
+    idx = [i % distinct for i in range(per_step)]
+    _cpu_init(left, right, args.rounds)
+    with mp.get_context("fork").Pool(cores) as pool:
+        for _ in range(args.warmup):
+            pool.map(_cpu_pair, idx, chunksize=1)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_pair, idx, chunksize=1)
+        dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic",
+            "config": workload_config(args, per_step),
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": "%d pairs per step (%d distinct), one process per core, oracle tier B (cv2 %s)"
+                                       % (per_step, distinct, cv2.__version__)},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, pairs):
+    return {"workload": "configuration_kitti_fast.yaml: independent KITTI-shape 1241x376 stereo pairs as first frames "
+                        "(Localizing), FAST thr 15, bin 25, ORB-256, triangulation distance 25.6; + StereoUV "
+                        "linearize x%d per pair over the pair's framepoints" % args.rounds,
+            "pairs_per_gpu_per_step": pairs, "linearize_rounds": args.rounds, "image": "1241x376 u8",
+            "l2": "inputs larger than L2 (%.0f MB of images per step per GPU)" % (pairs * 2 * 1241 * 376 / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons of one GPU during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.12)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from vslam_b200 import api, configs, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    cfg, acfg = configs.BY_NAME[CONFIG_NAME], configs.ALIGNER_BY_NAME[CONFIG_NAME]
+    cam = synth.camera(cfg.camera)
+    P, R, K, W = args.pairs, args.rounds, args.steps, max(args.warmup, 0)
+    D = min(args.distinct, P)
+
+    # ---- synthetic inputs: D distinct band-world pairs per rank (seeds disjoint across ranks), tiled to P pairs in
+    # pinned host memory (every pair is its own memory and is processed independently)
+    cores = len(os.sched_getaffinity(0))
+    dl, dr = synth.band_world_batch(cfg.camera, range(rank * D, (rank + 1) * D), workers=max(1, min(cores // world, 32)))
+    left = api.pinned_empty((P, cam.rows, cam.cols))
+    right = api.pinned_empty((P, cam.rows, cam.cols))
+    for i in range(0, P, D):
+        n = min(D, P - i)
+        left[i:i + n], right[i:i + n] = dl[:n], dr[:n]
+
+    gen = api.StereoFramePointGenerator(cfg, cam, device=local_rank, max_batch=P)
+    out = api.pinned_empty((P, gen.out_capacity), api.FRAMEPOINT)
+    counts = np.zeros(P, np.int32)
+    T = _prior()
+    stream = torch.cuda.ExternalStream(gen.stream, device=dev)
+
+    def step_resident():
+        gen.batch_run(P, True)
+        gen.batch_linearize(P, T, acfg, False, R)
+
+    def step_e2e():
+        gen.batch_process(left, right, True, out, counts)
+        gen.batch_linearize(P, T, acfg, False, R)
+        return gen.batch_systems(P, raw=True)
+
+    # ---- device-resident throughput
+    gen.batch_upload(left, right)
+    for _ in range(W):
+        step_resident()
+    barrier()
+    launches0 = gen.launch_count
+    with ClockSampler(local_rank) as clk:
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(stream)
+        for _ in range(K):
+            step_resident()
+        end.record(stream)
+        barrier()
+    ms = max_over_ranks(start.elapsed_time(end))
+    launches = gen.launch_count - launches0
+    value = world * P * K / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer API
+    for _ in range(min(W, 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step_e2e()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * P * K / e2e_s
+    h2d = 2 * P * cam.rows * cam.cols
+    d2h = P * gen.out_capacity * api.FRAMEPOINT.itemsize + P * 8 * 4 + P * 32 * 8
+
+    # ---- per-kernel durations (CUDA events inside the library, serialised on one stream) and the roofline
+    _, nf, nm, nl, nr = gen.batch_download(P, out)
+    gen.set_profiling(-1)
+    gen.set_profiling(1)
+    for _ in range(max(1, min(K, 3))):
+        step_resident()
+    gen.synchronize()
+    prof = gen.kernel_profile()
+    gen.set_profiling(0)
+    steps_prof = max(1, min(K, 3))
+    chunks = prof[KERNEL_OF_INTEREST][1] / steps_prof
+    kernel_ms = {k: v[0] / steps_prof for k, v in prof.items()}
+    total_kernel_ms = sum(kernel_ms.values())
+    peak, peak_kind = peaks()
+    # algorithmic bytes of the FAST kernel per step: both images read once (u8) + 8 B per raw keypoint found
+    # (2*W*H + 2*N_kp*8 of the per-frame figure); N_kp from this run's own counts is not kept per image,
+    # the descriptor-valid count (nl + nr) is a lower bound and is what is charged
+    fast_bytes = float(2 * P * cam.rows * cam.cols + 8 * (nl.sum() + nr.sum()))
+    fast_ms_per_launch = kernel_ms[KERNEL_OF_INTEREST] / max(chunks, 1)
+    achieved = fast_bytes / max(chunks, 1) / (fast_ms_per_launch * 1e-3) / 1e9
+    # whole path, per frame: 2WH + 2 N_kp 8 + 2 N_desc 32 + 2 N_desc 40 + N_match 48  (+ 81 B per point per round)
+    n_desc = float(nl.sum() + nr.sum())
+    path_bytes = (2.0 * P * cam.rows * cam.cols + 8 * n_desc + 32 * n_desc + 40 * n_desc + 48.0 * nm.sum()
+                  + 81.0 * nf.sum() * R)
+    roofline = {"bound": "hbm", "kernel": "fast_nms_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_kind + " (of %s)" % peak_kind,
+                "launch_ms": fast_ms_per_launch, "launches_per_step": chunks,
+                "kernel_share_of_step": kernel_ms[KERNEL_OF_INTEREST] / total_kernel_ms,
+                "kernel_ms_per_step": kernel_ms,
+                "path": {"algorithmic_bytes_per_step": path_bytes,
+                         "achieved_gbs": path_bytes / (ms / K * 1e-3) / 1e9,
+                         "frac": path_bytes / (ms / K * 1e-3) / 1e9 / peak}}
+
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8+f64", "data": "synthetic (band-world, %d distinct pairs per GPU tiled to %d)" % (D, P),
+            "config": workload_config(args, P), "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s / K * 1e3},
+            "gpu_launches": int(launches), "roofline": roofline,
+            "counts": {"mean_descriptors_left": float(nl.mean()), "mean_matches": float(nm.mean()),
+                       "mean_framepoints": float(nf.mean())}}
+    if rank == 0 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(dl, dr, R, args.cpu_sample)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    gen.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

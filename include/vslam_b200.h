@@ -45,6 +45,15 @@ int vslam_device_count(void);
 int vslam_host_alloc(void** ptr, size_t bytes);
 int vslam_host_free(void* ptr);
 
+/* the normal equations BaseAligner::linearize leaves behind (AlignerWorkspace<6,D>, base_aligner.h:74-106) */
+typedef struct {
+  double H[36];            /* _H, row-major */
+  double b[6];             /* _b */
+  double total_error;      /* _total_error */
+  int32_t number_of_inliers;
+  int32_t number_of_outliers;
+} vslam_linear_system;
+
 /* ===================================================================================================
  * Stereo framepoint generation
  * =================================================================================================*/
@@ -146,7 +155,12 @@ int vslam_fpg_get_matches(vslam_fpg* h, vslam_framepoint* matches, int32_t capac
 /* getTimeConsumptionSeconds_{keypoint_detection, descriptor_extraction, point_triangulation}
  * (base_framepoint_generator.h:232-233, stereo_framepoint_generator.h:81): accumulated DEVICE seconds,
  * measured with CUDA events when profiling is enabled. */
+/* enabled > 0: on (batched calls then run serialised on one stream); 0: off; < 0: off and reset accumulators */
 int vslam_fpg_set_profiling(vslam_fpg* h, int enabled);
+/* accumulated device milliseconds and launch counts per kernel while profiling was on, in this order:
+ * fast_nms, compact, blur, describe, match, select, linearize_pairs */
+#define VSLAM_FPG_KERNELS 7
+int vslam_fpg_get_kernel_profile(vslam_fpg* h, double* milliseconds, int64_t* launches);
 int vslam_fpg_get_time_consumption(vslam_fpg* h, double* keypoint_detection, double* descriptor_extraction,
                                    double* point_triangulation);
 
@@ -167,6 +181,17 @@ int vslam_fpg_batch_download(vslam_fpg* h, int32_t n_pairs, vslam_framepoint* fr
 int vslam_fpg_batch_process(vslam_fpg* h, int32_t n_pairs, const uint8_t* left, const uint8_t* right,
                             size_t stride, size_t pair_stride, int localizing, vslam_framepoint* framepoints,
                             int32_t capacity_per_pair, int32_t* n_framepoints);
+/* StereoUVAligner::initialize (stereouv_aligner.cpp:10-69) + `rounds` x linearize (:72-187) for every pair of the
+ * last batched run, device-resident, one problem per pair: the pair's new framepoints are aligned against
+ * themselves (what the tracker does when previous and current frame hold the same points and no landmarks):
+ * _moving = cameraCoordinatesLeft, _fixed = (uL,vL,uR,vR), information = I4, w_t = min(max_depth/depth, 1) if
+ * enable_inverse_depth_as_information else 1.  Asynchronous on the handle's stream. */
+int vslam_fpg_batch_linearize(vslam_fpg* h, int32_t n_pairs, const double previous_to_current[12], int ignore_outliers,
+                              double maximum_error_kernel, double minimum_reliable_depth,
+                              double maximum_reliable_depth, int enable_inverse_depth_as_information, int32_t rounds);
+/* systems[n_pairs]; optional per-point _errors / _inliers, pair i at + i*capacity_per_pair.  Synchronises. */
+int vslam_fpg_batch_get_systems(vslam_fpg* h, int32_t n_pairs, vslam_linear_system* systems, double* errors,
+                                uint8_t* inliers, int32_t capacity_per_pair);
 /* per-pair features of the last batched run (reference order), for parity checks */
 int vslam_fpg_batch_get_features(vslam_fpg* h, int32_t pair, int side, vslam_keypoint* keypoints,
                                  uint8_t* descriptors, int32_t capacity, int32_t* n);
@@ -206,14 +231,6 @@ typedef struct {
   int32_t maximum_number_of_iterations;
   int32_t minimum_number_of_inliers;
 } vslam_aligner_parameters;
-
-typedef struct {
-  double H[36];            /* _H, row-major */
-  double b[6];             /* _b */
-  double total_error;      /* _total_error */
-  int32_t number_of_inliers;
-  int32_t number_of_outliers;
-} vslam_linear_system;
 
 int vslam_aligner_create(int kind, int32_t max_points, int device, vslam_aligner** out);
 int vslam_aligner_destroy(vslam_aligner* h);

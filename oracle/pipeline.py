@@ -53,9 +53,11 @@ class StereoFramePointGeneratorOracle:
             kps = det.detect(img[q["y"]:q["y"] + q["h"], q["x"]:q["x"] + q["w"]])
             counts.append(len(kps))
             a = np.zeros(len(kps), tier_a.KP)
-            a["x"] = [k.pt[0] + q["x"] for k in kps]
-            a["y"] = [k.pt[1] + q["y"] for k in kps]
-            a["response"] = [k.response for k in kps]
+            if len(kps):   # bulk conversions: the Python glue must not dominate the timed CPU baseline
+                pts = cv2.KeyPoint_convert(kps)
+                a["x"] = pts[:, 0] + np.float32(q["x"])                                      # :418-419
+                a["y"] = pts[:, 1] + np.float32(q["y"])
+                a["response"] = np.fromiter((k.response for k in kps), np.float32, len(kps))
             out.append(a)
         return np.concatenate(out), np.asarray(counts, np.int32)
 
@@ -64,13 +66,20 @@ class StereoFramePointGeneratorOracle:
         if self.tier == "a":
             return tier_a.orb_compute(img, kps)
         cv2 = _cv2()
-        cvk = [cv2.KeyPoint(float(k["x"]), float(k["y"]), 7.0, -1.0, float(k["response"]), 0, -1) for k in kps]
+        if len(kps) == 0:
+            return kps, np.zeros((0, 32), np.uint8)
+        pts = np.ascontiguousarray(np.stack([kps["x"], kps["y"]], 1))
+        cvk = cv2.KeyPoint_convert(pts, size=7.0)            # angle -1, octave 0, class_id -1 like FAST's own
         cvk, desc = self._orb.compute(img, cvk)
-        a = np.zeros(len(cvk), tier_a.KP)
-        a["x"] = [k.pt[0] for k in cvk]
-        a["y"] = [k.pt[1] for k in cvk]
-        a["response"] = [k.response for k in cvk]
-        return a, (desc if desc is not None else np.zeros((0, 32), np.uint8))
+        if desc is None:
+            return kps[:0], np.zeros((0, 32), np.uint8)
+        kept = cv2.KeyPoint_convert(cvk)
+        # ORB only drops keypoints (31 px border) and keeps the order: carry the responses over by position
+        h, w = img.shape
+        keep = (kps["x"] >= 31) & (kps["x"] < w - 31) & (kps["y"] >= 31) & (kps["y"] < h - 31)
+        a = kps[keep].copy()
+        assert len(a) == len(kept) and np.array_equal(a["x"], kept[:, 0]) and np.array_equal(a["y"], kept[:, 1])
+        return a, desc
 
     # ---- stereo_framepoint_generator.cpp:73-133 ------------------------------------------------
     def initialize(self, left, right, localizing: bool):

@@ -241,3 +241,50 @@ def test_row_strided_input_views():
     o = _oracle(cfg, cam, left, right, True)
     _check_pair(gen, o)
     gen.close()
+
+
+def test_batched_self_alignment_linearize_matches_oracle():
+    """vslam_fpg_batch_linearize: per pair, StereoUVAligner::initialize + linearize over the pair's own framepoints."""
+    cfg, acfg = configs.KITTI_FAST, configs.KITTI_FAST_ALIGNER
+    cam = synth.camera(cfg.camera)
+    n = 4
+    left, right = synth.band_world_batch(cfg.camera, range(40, 40 + n))
+    gen = api.StereoFramePointGenerator(cfg, cam, max_batch=n)
+    out, counts = gen.batch_process(left, right, True)
+    T = synth.true_motion().copy()
+    T[:, 3] *= 0.05                         # a small prior error so that errors, inliers and outliers all occur
+    for ignore in (False, True):
+        gen.batch_linearize(n, T, acfg, ignore_outliers=ignore, rounds=2)
+        systems, errors, inliers = gen.batch_systems(n, with_points=True)
+        for i in range(n):
+            fp = out[i, :counts[i]]
+            moving = fp["camera"]
+            fixed = np.stack([fp["xl"], fp["yl"], fp["xr"], fp["yr"]], 1).astype(np.float64)
+            wt = np.minimum(acfg.maximum_reliable_depth_meters / moving[:, 2], 1.0)
+            ora = tier_a.Aligner("stereouv", moving, fixed, np.ones(len(fp)), wt, cam.K, cam.baseline, cam.rows, cam.cols,
+                                 acfg.minimum_reliable_depth_meters, acfg.maximum_error_kernel)
+            want = ora.linearize(T, ignore)
+            got = systems[i]
+            assert got["inliers"] == want["inliers"] and got["outliers"] == want["outliers"]
+            assert 0 < want["inliers"] < len(fp)
+            np.testing.assert_allclose(got["H"], want["H"], rtol=1e-10, atol=1e-12 * np.abs(want["H"]).max())
+            np.testing.assert_allclose(got["b"], want["b"], rtol=1e-9, atol=1e-12 * np.abs(want["H"]).max())
+            np.testing.assert_allclose(got["total_error"], want["total_error"], rtol=1e-12)
+            assert np.array_equal(errors[i, :counts[i]], ora.errors)
+            assert np.array_equal(inliers[i, :counts[i]], ora.inliers)
+    gen.close()
+
+
+def test_chronometers_and_kernel_profile():
+    cfg, cam = configs.KITTI, synth.camera("kitti")
+    left, right = synth.band_world_pair("kitti", 1)
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    gen.set_profiling(True)
+    gen.initialize(left, right, True)
+    gen.compute()
+    t = gen.time_consumption()
+    assert t["keypoint_detection"] > 0 and t["descriptor_extraction"] > 0 and t["point_triangulation"] > 0
+    prof = gen.kernel_profile()
+    assert all(prof[k][1] == 1 for k in ("fast_nms", "compact", "blur", "describe", "match", "select"))
+    assert gen.launch_count == 6
+    gen.close()

@@ -32,7 +32,8 @@ EXPORTS = """vslam_last_error vslam_version vslam_device_count vslam_host_alloc 
 vslam_fpg_create vslam_fpg_destroy vslam_fpg_info vslam_fpg_get_thresholds vslam_fpg_set_thresholds
 vslam_fpg_initialize vslam_fpg_get_features vslam_fpg_get_detection_stats vslam_fpg_compute vslam_fpg_get_matches
 vslam_fpg_set_profiling vslam_fpg_get_time_consumption vslam_fpg_batch_upload vslam_fpg_batch_run
-vslam_fpg_batch_download vslam_fpg_batch_process vslam_fpg_batch_get_features vslam_fpg_stream vslam_fpg_synchronize
+vslam_fpg_batch_download vslam_fpg_batch_process vslam_fpg_batch_linearize vslam_fpg_batch_get_systems
+vslam_fpg_get_kernel_profile vslam_fpg_batch_get_features vslam_fpg_stream vslam_fpg_synchronize
 vslam_fpg_launch_count vslam_fpg_debug_keypoint_mask vslam_fpg_debug_blurred vslam_threshold_proposal
 vslam_aligner_create vslam_aligner_destroy vslam_aligner_upload vslam_aligner_linearize vslam_aligner_download
 vslam_aligner_one_round vslam_aligner_converge vslam_aligner_linearize_async vslam_aligner_read_system
@@ -108,6 +109,9 @@ def lib():
         L.vslam_fpg_batch_download.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp]
         L.vslam_fpg_batch_process.argtypes = [vp, i32, vp, vp, sz, sz, C.c_int, vp, i32, vp]
         L.vslam_fpg_batch_get_features.argtypes = [vp, i32, C.c_int, vp, vp, i32, vp]
+        L.vslam_fpg_batch_linearize.argtypes = [vp, i32, vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, i32]
+        L.vslam_fpg_batch_get_systems.argtypes = [vp, i32, vp, vp, vp, i32]
+        L.vslam_fpg_get_kernel_profile.argtypes = [vp, vp, vp]
         L.vslam_fpg_stream.argtypes = [vp]
         L.vslam_fpg_synchronize.argtypes = [vp]
         L.vslam_fpg_launch_count.argtypes = [vp]
@@ -300,6 +304,41 @@ class StereoFramePointGenerator:
         _check(lib().vslam_fpg_batch_process(self._h, n, _p(left), _p(right), left.strides[1], left.strides[0],
                                              int(bool(localizing)), _p(out), out.shape[1], _p(counts)))
         return out, counts
+
+    KERNELS = ("fast_nms", "compact", "blur", "describe", "match", "select", "linearize_pairs")
+
+    def kernel_profile(self):
+        """{kernel: (accumulated device ms, launches)} while profiling was on"""
+        ms = np.zeros(len(self.KERNELS))
+        n = np.zeros(len(self.KERNELS), np.int64)
+        _check(lib().vslam_fpg_get_kernel_profile(self._h, _p(ms), _p(n)))
+        return {k: (float(a), int(b)) for k, a, b in zip(self.KERNELS, ms, n)}
+
+    def batch_linearize(self, n_pairs, previous_to_current, aligner_cfg, ignore_outliers=False, rounds=1):
+        """StereoUVAligner::initialize + rounds x linearize per pair, over the pair's own new framepoints"""
+        T = np.ascontiguousarray(previous_to_current, np.float64).reshape(12)
+        _check(lib().vslam_fpg_batch_linearize(self._h, n_pairs, _p(T), int(bool(ignore_outliers)),
+                                               float(aligner_cfg.maximum_error_kernel),
+                                               float(aligner_cfg.minimum_reliable_depth_meters),
+                                               float(aligner_cfg.maximum_reliable_depth_meters),
+                                               int(bool(aligner_cfg.enable_inverse_depth_as_information)), int(rounds)))
+
+    def batch_systems(self, n_pairs, with_points=False, raw=False):
+        if raw:   # no Python-side conversion: the ctypes array of vslam_linear_system
+            if getattr(self, "_sys_buf", None) is None or len(self._sys_buf) != n_pairs:
+                self._sys_buf = (LinearSystem * n_pairs)()
+            _check(lib().vslam_fpg_batch_get_systems(self._h, n_pairs, C.byref(self._sys_buf), None, None, 0))
+            return self._sys_buf
+        sys_ = (LinearSystem * n_pairs)()
+        errors = inliers = None
+        if with_points:
+            errors = np.zeros((n_pairs, self.out_capacity))
+            inliers = np.zeros((n_pairs, self.out_capacity), np.uint8)
+        _check(lib().vslam_fpg_batch_get_systems(self._h, n_pairs, C.byref(sys_), _p(errors), _p(inliers),
+                                                 self.out_capacity))
+        out = [{"H": np.array(s.H).reshape(6, 6), "b": np.array(s.b), "total_error": s.total_error,
+                "inliers": s.number_of_inliers, "outliers": s.number_of_outliers} for s in sys_]
+        return (out, errors, inliers) if with_points else out
 
     def synchronize(self):
         _check(lib().vslam_fpg_synchronize(self._h))

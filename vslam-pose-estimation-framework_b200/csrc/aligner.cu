@@ -25,129 +25,122 @@ __device__ __forceinline__ int tri(int i, int j) {   // upper-triangle index, i 
   return i * 6 - (i * (i - 1)) / 2 + (j - i);
 }
 
+// One correspondence: error, robust kernel, Jacobian, and its contribution to acc[0..28].
+// Returns the error (chi, or -1 when skipped) and the inlier flag exactly as linearize() leaves them in
+// _errors[u] / _inliers[u].  fx[] = fixed measurement, om[] = information scalars (1 for StereoUV, 2 for UVD).
 template <int KIND>
-__global__ void __launch_bounds__(kThreads) linearize_kernel(int n, AlignerBuffers b, AlignerCamera cam, Pose pose,
-                                                             int ignore_outliers, double kernel) {
+__device__ __forceinline__ void accumulate_point(const double m0, const double m1, const double m2, const double* fx,
+                                                 const double* om, const double wt, const double* T,
+                                                 const AlignerCamera& cam, const int ignore_outliers,
+                                                 const double kernel, double (&acc)[kAcc], double& err, uint8_t& inl) {
   constexpr int D = KIND == 0 ? 4 : 3;
-  double acc[kAcc];
-#pragma unroll
-  for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
   const double* K = cam.K;
-  const double* T = pose.T;
-
-  for (int u = blockIdx.x * kThreads + threadIdx.x; u < n; u += gridDim.x * kThreads) {
-    double err = -1.0;      // :82-84 / :88-90
-    uint8_t inl = 0;
-    const double m0 = b.moving[u], m1 = b.moving[b.stride + u], m2 = b.moving[2 * b.stride + u];
-    double pc[3];
+  err = -1.0;      // :82-84 / :88-90
+  inl = 0;
+  double pc[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) pc[i] = T[4 * i] * m0 + T[4 * i + 1] * m1 + T[4 * i + 2] * m2 + T[4 * i + 3];
-    bool use = KIND == 0 ? !(pc[2] < cam.min_depth) : !(pc[2] <= cam.min_depth);   // :88 / :95
-    double e[D], w[D], J[D][6];
-    double abc[3], abr[3];
-    if (use) {
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        abc[i] = K[3 * i] * pc[0] + K[3 * i + 1] * pc[1] + K[3 * i + 2] * pc[2];
-        abr[i] = abc[i] + cam.baseline[i];
-      }
-      const double ul = abc[0] / abc[2], vl = abc[1] / abc[2];
-      if (ul < 0 || ul > cam.cols || vl < 0 || vl > cam.rows) use = false;        // :103-106 / :109-112
-      if (KIND == 0) {
-        const double ur = abr[0] / abr[2], vr = abr[1] / abr[2];
-        if (ur < 0 || ur > cam.cols || vr < 0 || vr > cam.rows) use = false;      // :107-110
-        e[0] = ul - b.fixed[u];
-        e[1] = vl - b.fixed[b.stride + u];
-        e[2] = ur - b.fixed[2 * b.stride + u];
-        e[3] = vr - b.fixed[3 * b.stride + u];
-        const double om = b.omega[u];
-#pragma unroll
-        for (int d = 0; d < D; ++d) w[d] = om;
-      } else {
-        e[0] = ul - b.fixed[u];
-        e[1] = vl - b.fixed[b.stride + u];
-        e[2] = pc[2] - b.fixed[2 * b.stride + u];
-        w[0] = w[1] = b.omega[u];
-        w[2] = b.omega[b.stride + u];
-      }
-    }
-    if (use) {
-      double chi = w[0] * e[0] * e[0];
-#pragma unroll
-      for (int d = 1; d < D; ++d) chi = chi + w[d] * e[d] * e[d];                  // :121 / :120
-      err = chi;
-      if (chi > kernel) {                                                          // :127-137 / :126-135
-        if (ignore_outliers) {
-          use = false;
-        } else {
-          const double s = kernel / chi;
-#pragma unroll
-          for (int d = 0; d < D; ++d) w[d] = w[d] * s;
-        }
-      } else {
-        inl = 1;
-        acc[28] += 1.0;
-      }
-    }
-    b.errors[u] = err;
-    b.inliers[u] = inl;
-    if (!use) continue;
-    acc[27] += err;                                                                // :140 / :138
-
-    // K * [wt*I3 | -2*skew(p)]  (:143-152 / :145-161); zero terms of the dense product are dropped (exact)
-    const double wt = b.wt[u];
-    double kj[3][6];
+  for (int i = 0; i < 3; ++i) pc[i] = T[4 * i] * m0 + T[4 * i + 1] * m1 + T[4 * i + 2] * m2 + T[4 * i + 3];
+  bool use = KIND == 0 ? !(pc[2] < cam.min_depth) : !(pc[2] <= cam.min_depth);   // :88 / :95
+  double e[D], w[D], J[D][6];
+  double abc[3], abr[3];
+  if (use) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      kj[i][0] = K[3 * i] * wt;
-      kj[i][1] = K[3 * i + 1] * wt;
-      kj[i][2] = K[3 * i + 2] * wt;
-      kj[i][3] = K[3 * i + 1] * (-2 * pc[2]) + K[3 * i + 2] * (-2 * -pc[1]);
-      kj[i][4] = K[3 * i] * (-2 * -pc[2]) + K[3 * i + 2] * (-2 * pc[0]);
-      kj[i][5] = K[3 * i] * (-2 * pc[1]) + K[3 * i + 1] * (-2 * -pc[0]);
+      abc[i] = K[3 * i] * pc[0] + K[3 * i + 1] * pc[1] + K[3 * i + 2] * pc[2];
+      abr[i] = abc[i] + cam.baseline[i];
     }
+    const double ul = abc[0] / abc[2], vl = abc[1] / abc[2];
+    if (ul < 0 || ul > cam.cols || vl < 0 || vl > cam.rows) use = false;        // :103-106 / :109-112
     if (KIND == 0) {
-      const double il = 1 / abc[2], ir = 1 / abr[2];                               // :155-158
-      const double il2 = il * il, ir2 = ir * ir;
+      const double ur = abr[0] / abr[2], vr = abr[1] / abr[2];
+      if (ur < 0 || ur > cam.cols || vr < 0 || vr > cam.rows) use = false;      // :107-110
+      e[0] = ul - fx[0];
+      e[1] = vl - fx[1];
+      e[2] = ur - fx[2];
+      e[3] = vr - fx[3];
 #pragma unroll
-      for (int j = 0; j < 6; ++j) {                                                // :161-177
-        J[0][j] = il * kj[0][j] + (-abc[0] * il2) * kj[2][j];
-        J[1][j] = il * kj[1][j] + (-abc[1] * il2) * kj[2][j];
-        J[2][j] = ir * kj[0][j] + (-abr[0] * ir2) * kj[2][j];
-        J[3][j] = ir * kj[1][j] + (-abr[1] * ir2) * kj[2][j];
-      }
+      for (int d = 0; d < D; ++d) w[d] = om[0];
     } else {
-      const double iz = 1 / pc[2], iz2 = iz * iz;                                  // :141-142
-#pragma unroll
-      for (int j = 0; j < 6; ++j) {                                                // :155-161
-        J[0][j] = iz * kj[0][j] + (-abc[0] * iz2) * kj[2][j];
-        J[1][j] = iz * kj[1][j] + (-abc[1] * iz2) * kj[2][j];
-        J[2][j] = kj[2][j];
-      }
-    }
-    // H += J^T W J (upper triangle), b += J^T W e                                  (:183-184 / :167-168)
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      double jw[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) jw[d] = J[d][i] * w[d];
-#pragma unroll
-      for (int j = i; j < 6; ++j) {
-        double a = jw[0] * J[0][j];
-#pragma unroll
-        for (int d = 1; d < D; ++d) a = a + jw[d] * J[d][j];
-        acc[tri(i, j)] += a;
-      }
-      double a = jw[0] * e[0];
-#pragma unroll
-      for (int d = 1; d < D; ++d) a = a + jw[d] * e[d];
-      acc[21 + i] += a;
+      e[0] = ul - fx[0];
+      e[1] = vl - fx[1];
+      e[2] = pc[2] - fx[2];
+      w[0] = w[1] = om[0];
+      w[2] = om[1];
     }
   }
+  if (use) {
+    double chi = w[0] * e[0] * e[0];
+#pragma unroll
+    for (int d = 1; d < D; ++d) chi = chi + w[d] * e[d] * e[d];                  // :121 / :120
+    err = chi;
+    if (chi > kernel) {                                                          // :127-137 / :126-135
+      if (ignore_outliers) {
+        use = false;
+      } else {
+        const double s = kernel / chi;
+#pragma unroll
+        for (int d = 0; d < D; ++d) w[d] = w[d] * s;
+      }
+    } else {
+      inl = 1;
+      acc[28] += 1.0;
+    }
+  }
+  if (!use) return;
+  acc[27] += err;                                                                // :140 / :138
 
-  // ---- warp shuffle tree, then per-block partials
-  __shared__ double s_part[kThreads / 32][kAcc];
-  __shared__ bool s_last;
+  // K * [wt*I3 | -2*skew(p)]  (:143-152 / :145-161); zero terms of the dense product are dropped (exact)
+  double kj[3][6];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    kj[i][0] = K[3 * i] * wt;
+    kj[i][1] = K[3 * i + 1] * wt;
+    kj[i][2] = K[3 * i + 2] * wt;
+    kj[i][3] = K[3 * i + 1] * (-2 * pc[2]) + K[3 * i + 2] * (-2 * -pc[1]);
+    kj[i][4] = K[3 * i] * (-2 * -pc[2]) + K[3 * i + 2] * (-2 * pc[0]);
+    kj[i][5] = K[3 * i] * (-2 * pc[1]) + K[3 * i + 1] * (-2 * -pc[0]);
+  }
+  if (KIND == 0) {
+    const double il = 1 / abc[2], ir = 1 / abr[2];                               // :155-158
+    const double il2 = il * il, ir2 = ir * ir;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {                                                // :161-177
+      J[0][j] = il * kj[0][j] + (-abc[0] * il2) * kj[2][j];
+      J[1][j] = il * kj[1][j] + (-abc[1] * il2) * kj[2][j];
+      J[2][j] = ir * kj[0][j] + (-abr[0] * ir2) * kj[2][j];
+      J[3][j] = ir * kj[1][j] + (-abr[1] * ir2) * kj[2][j];
+    }
+  } else {
+    const double iz = 1 / pc[2], iz2 = iz * iz;                                  // :141-142
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {                                                // :155-161
+      J[0][j] = iz * kj[0][j] + (-abc[0] * iz2) * kj[2][j];
+      J[1][j] = iz * kj[1][j] + (-abc[1] * iz2) * kj[2][j];
+      J[2][j] = kj[2][j];
+    }
+  }
+  // H += J^T W J (upper triangle), b += J^T W e                                  (:183-184 / :167-168)
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double jw[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) jw[d] = J[d][i] * w[d];
+#pragma unroll
+    for (int j = i; j < 6; ++j) {
+      double a = jw[0] * J[0][j];
+#pragma unroll
+      for (int d = 1; d < D; ++d) a = a + jw[d] * J[d][j];
+      acc[tri(i, j)] += a;
+    }
+    double a = jw[0] * e[0];
+#pragma unroll
+    for (int d = 1; d < D; ++d) a = a + jw[d] * e[d];
+    acc[21 + i] += a;
+  }
+}
+
+// warp shuffle tree + cross-warp sum; the block's kAcc totals end up in threads 0..kAcc-1 (return value)
+__device__ __forceinline__ double block_reduce(const double (&acc)[kAcc], double (*s_part)[kAcc]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < kAcc; ++i) {
@@ -156,11 +149,39 @@ __global__ void __launch_bounds__(kThreads) linearize_kernel(int n, AlignerBuffe
     if (lane == 0) s_part[warp][i] = v;
   }
   __syncthreads();
-  if (threadIdx.x < kAcc) {
-    double v = 0;
+  double v = 0;
+  if (threadIdx.x < kAcc)
     for (int w = 0; w < kThreads / 32; ++w) v += s_part[w][threadIdx.x];
-    b.partials[(size_t)blockIdx.x * 32 + threadIdx.x] = v;
+  return v;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads) linearize_kernel(int n, AlignerBuffers b, AlignerCamera cam, Pose pose,
+                                                             int ignore_outliers, double kernel) {
+  constexpr int D = KIND == 0 ? 4 : 3;
+  constexpr int W = KIND == 0 ? 1 : 2;
+  double acc[kAcc];
+#pragma unroll
+  for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
+
+  for (int u = blockIdx.x * kThreads + threadIdx.x; u < n; u += gridDim.x * kThreads) {
+    double fx[D], om[W], err;
+    uint8_t inl;
+#pragma unroll
+    for (int d = 0; d < D; ++d) fx[d] = b.fixed[d * b.stride + u];
+#pragma unroll
+    for (int d = 0; d < W; ++d) om[d] = b.omega[d * b.stride + u];
+    accumulate_point<KIND>(b.moving[u], b.moving[b.stride + u], b.moving[2 * b.stride + u], fx, om, b.wt[u], pose.T, cam,
+                           ignore_outliers, kernel, acc, err, inl);
+    b.errors[u] = err;
+    b.inliers[u] = inl;
   }
+
+  // ---- warp shuffle tree, then per-block partials
+  __shared__ double s_part[kThreads / 32][kAcc];
+  __shared__ bool s_last;
+  const double total = block_reduce(acc, s_part);
+  if (threadIdx.x < kAcc) b.partials[(size_t)blockIdx.x * 32 + threadIdx.x] = total;
   // ---- the one atomic stage: a ticket; the last block to arrive reduces the block partials in block order
   __threadfence();
   __syncthreads();
@@ -187,6 +208,41 @@ __global__ void __launch_bounds__(kThreads) linearize_kernel(int n, AlignerBuffe
   }
 }
 
+// Batched form for independent stereo pairs: one CTA per pair linearises the StereoUV problem that aligns the
+// pair's new framepoints against themselves -- StereoUVAligner::initialize (:10-69) fused in: _moving =
+// cameraCoordinatesLeft, _fixed = (uL, vL, uR, vR), information = I4 (no landmark), w_t = min(max_depth/depth, 1).
+__global__ void __launch_bounds__(kThreads) linearize_pairs_kernel(const FramePointRecord* __restrict__ records,
+                                                                   int record_stride, const int32_t* __restrict__ n_out,
+                                                                   AlignerCamera cam, Pose pose, int ignore_outliers,
+                                                                   double kernel, double max_reliable_depth,
+                                                                   int inverse_depth_weight, double* __restrict__ systems,
+                                                                   double* __restrict__ errors,
+                                                                   uint8_t* __restrict__ inliers) {
+  const int pair = blockIdx.x;
+  const int n = n_out[2 * pair];
+  const FramePointRecord* rec = records + (size_t)pair * record_stride;
+  double acc[kAcc];
+#pragma unroll
+  for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
+  for (int u = threadIdx.x; u < n; u += kThreads) {
+    const FramePointRecord r = rec[u];
+    double err = -1.0;
+    uint8_t inl = 0;
+    if (r.index_left >= 0) {
+      const double fx[4] = {(double)r.xl, (double)r.yl, (double)r.xr, (double)r.yr};
+      const double om[1] = {1.0};
+      const double wt = inverse_depth_weight ? fmin(max_reliable_depth / r.camera[2], 1.0) : 1.0;   // :59-63
+      accumulate_point<0>(r.camera[0], r.camera[1], r.camera[2], fx, om, wt, pose.T, cam, ignore_outliers, kernel, acc,
+                          err, inl);
+    }
+    errors[(size_t)pair * record_stride + u] = err;
+    inliers[(size_t)pair * record_stride + u] = inl;
+  }
+  __shared__ double s_part[kThreads / 32][kAcc];
+  const double total = block_reduce(acc, s_part);
+  if (threadIdx.x < kAcc) systems[(size_t)pair * 32 + threadIdx.x] = total;
+}
+
 }  // namespace
 
 int aligner_grid(int n, int sm_count) {
@@ -201,6 +257,17 @@ void launch_linearize(int kind, int n, const AlignerBuffers& b, const AlignerCam
   for (int i = 0; i < 12; ++i) pose.T[i] = T[i];
   if (kind == 0) linearize_kernel<0><<<grid, kThreads, 0, stream>>>(n, b, cam, pose, ignore_outliers, kernel);
   else linearize_kernel<1><<<grid, kThreads, 0, stream>>>(n, b, cam, pose, ignore_outliers, kernel);
+}
+
+void launch_linearize_pairs(const FramePointRecord* records, int record_stride, const int32_t* n_out, int n_pairs,
+                            const AlignerCamera& cam, const double T[12], int ignore_outliers, double kernel,
+                            double max_reliable_depth, int inverse_depth_weight, double* systems, double* errors,
+                            uint8_t* inliers, cudaStream_t stream) {
+  Pose pose;
+  for (int i = 0; i < 12; ++i) pose.T[i] = T[i];
+  linearize_pairs_kernel<<<n_pairs, kThreads, 0, stream>>>(records, record_stride, n_out, cam, pose, ignore_outliers,
+                                                           kernel, max_reliable_depth, inverse_depth_weight, systems,
+                                                           errors, inliers);
 }
 
 }  // namespace vslam

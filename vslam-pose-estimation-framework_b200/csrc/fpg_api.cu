@@ -33,8 +33,12 @@ struct Lane {
   uint32_t* mask = nullptr;     // [2*chunk][rows][mask_words]
 };
 
+// profiling: events at the kernel boundaries of one chunk (single lane, serialised)
+enum { kEvFast0, kEvFast1, kEvCompact1, kEvBlur1, kEvDescribe1, kEvMatch0, kEvMatch1, kEvSelect1, kEvLin0, kEvLin1, kNumEv };
+enum { kKFast, kKCompact, kKBlur, kKDescribe, kKMatch, kKSelect, kKLinearize, kNumKernels };
+
 struct StageClock {
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[kNumEv] = {};
 };
 
 }  // namespace
@@ -74,6 +78,15 @@ struct vslam_fpg {
   bool profiling = false;
   StageClock clock;
   double t_detect = 0, t_describe = 0, t_match = 0;
+  double k_ms[kNumKernels] = {};
+  int64_t k_n[kNumKernels] = {};
+  cudaEvent_t fork_ev = nullptr;
+  cudaEvent_t join_ev[kLanes] = {};
+  // batched StereoUV linearize over the pairs' own framepoints
+  double* d_systems = nullptr;        // [max_batch][32]
+  double* d_pair_errors = nullptr;    // [max_batch][out_cap]
+  uint8_t* d_pair_inliers = nullptr;  // [max_batch][out_cap]
+  double* h_systems = nullptr;        // pinned [max_batch][32]
 };
 
 namespace {
@@ -93,6 +106,10 @@ int check_flag(vslam_fpg* h) {
   return VSLAM_OK;
 }
 
+inline void mark(vslam_fpg* h, Lane& lane, int ev) {
+  if (h->profiling) cudaEventRecord(h->clock.ev[ev], lane.stream);
+}
+
 // kernels of initialize() for images [2*p0, 2*(p0+n)) on one lane
 void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n) {
   Buffers b = h->b;
@@ -101,39 +118,75 @@ void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n) {
   b.mask = lane.mask - (size_t)2 * p0 * h->g.rows * h->g.mask_words;
   RegionTable rt;
   refresh_region_table(h, &rt);
-  const bool prof = h->profiling;
-  if (prof) cudaEventRecord(h->clock.ev[0], lane.stream);
+  mark(h, lane, kEvFast0);
   launch_fast(h->g, rt, b, 2 * p0, 2 * n, lane.stream);
+  mark(h, lane, kEvFast1);
   launch_compact(h->g, b, 2 * p0, 2 * n, lane.stream);
-  if (prof) cudaEventRecord(h->clock.ev[1], lane.stream);
+  mark(h, lane, kEvCompact1);
   launch_blur(h->g, b, 2 * p0, 2 * n, lane.stream);
+  mark(h, lane, kEvBlur1);
   launch_describe(h->g, b, 2 * p0, 2 * n, lane.stream);
-  if (prof) cudaEventRecord(h->clock.ev[2], lane.stream);
+  mark(h, lane, kEvDescribe1);
   h->launches += 4;
 }
 
 // kernels of compute() for pairs [p0, p0+n) on one lane
 void run_match_select(vslam_fpg* h, Lane& lane, int p0, int n, const TrackedPoint* tracked, int n_tracked) {
-  const bool prof = h->profiling;
-  if (prof) cudaEventRecord(h->clock.ev[3], lane.stream);
+  mark(h, lane, kEvMatch0);
   for (int pass = 0; pass < h->n_passes; ++pass) {
     const int offset = pass == 0 ? 0 : ((pass & 1) ? (pass + 1) / 2 : -(pass / 2));
     launch_match(h->g, h->sp, h->b, p0, n, pass, offset, lane.stream);
     ++h->launches;
   }
+  mark(h, lane, kEvMatch1);
   launch_select(h->g, h->sp, h->b, p0, n, h->n_passes, tracked, n_tracked, h->d_out, h->out_cap, lane.stream);
   ++h->launches;
-  if (prof) cudaEventRecord(h->clock.ev[4], lane.stream);
+  mark(h, lane, kEvSelect1);
+}
+
+void add_interval(vslam_fpg* h, int kernel, int e0, int e1, int launches) {
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, h->clock.ev[e0], h->clock.ev[e1]) == cudaSuccess) {
+    h->k_ms[kernel] += ms;
+    h->k_n[kernel] += launches;
+  } else {
+    cudaGetLastError();
+  }
 }
 
 void collect_clock(vslam_fpg* h, bool detect, bool match) {
   if (!h->profiling) return;
-  float ms = 0;
   if (detect) {
-    if (cudaEventElapsedTime(&ms, h->clock.ev[0], h->clock.ev[1]) == cudaSuccess) h->t_detect += ms * 1e-3;
-    if (cudaEventElapsedTime(&ms, h->clock.ev[1], h->clock.ev[2]) == cudaSuccess) h->t_describe += ms * 1e-3;
+    const double d0 = h->k_ms[kKFast] + h->k_ms[kKCompact], e0 = h->k_ms[kKBlur] + h->k_ms[kKDescribe];
+    add_interval(h, kKFast, kEvFast0, kEvFast1, 1);
+    add_interval(h, kKCompact, kEvFast1, kEvCompact1, 1);
+    add_interval(h, kKBlur, kEvCompact1, kEvBlur1, 1);
+    add_interval(h, kKDescribe, kEvBlur1, kEvDescribe1, 1);
+    h->t_detect += (h->k_ms[kKFast] + h->k_ms[kKCompact] - d0) * 1e-3;
+    h->t_describe += (h->k_ms[kKBlur] + h->k_ms[kKDescribe] - e0) * 1e-3;
   }
-  if (match && cudaEventElapsedTime(&ms, h->clock.ev[3], h->clock.ev[4]) == cudaSuccess) h->t_match += ms * 1e-3;
+  if (match) {
+    const double m0 = h->k_ms[kKMatch] + h->k_ms[kKSelect];
+    add_interval(h, kKMatch, kEvMatch0, kEvMatch1, h->n_passes);
+    add_interval(h, kKSelect, kEvMatch1, kEvSelect1, 1);
+    h->t_match += (h->k_ms[kKMatch] + h->k_ms[kKSelect] - m0) * 1e-3;
+  }
+}
+
+// lanes other than 0 start after everything already ordered on lane 0 (the handle's stream) ...
+int fork_lanes(vslam_fpg* h) {
+  CUDA_TRY(cudaEventRecord(h->fork_ev, h->lanes[0].stream));
+  for (int l = 1; l < kLanes; ++l) CUDA_TRY(cudaStreamWaitEvent(h->lanes[l].stream, h->fork_ev, 0));
+  return VSLAM_OK;
+}
+
+// ... and lane 0 continues only after they are done: work issued by a batched call is ordered on lane 0
+int join_lanes(vslam_fpg* h) {
+  for (int l = 1; l < kLanes; ++l) {
+    CUDA_TRY(cudaEventRecord(h->join_ev[l], h->lanes[l].stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->lanes[0].stream, h->join_ev[l], 0));
+  }
+  return VSLAM_OK;
 }
 
 int upload_images(vslam_fpg* h, Lane& lane, int p0, int n, const uint8_t* left, const uint8_t* right, size_t stride,
@@ -333,6 +386,9 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
   dalloc((void**)&h->d_out, B * h->out_cap * sizeof(FramePointRecord));
   dalloc((void**)&h->d_matches, (size_t)g.cap * sizeof(FramePointRecord));
   dalloc((void**)&h->d_n_matches, sizeof(int32_t));
+  dalloc((void**)&h->d_systems, B * 32 * sizeof(double));
+  dalloc((void**)&h->d_pair_errors, B * h->out_cap * sizeof(double));
+  dalloc((void**)&h->d_pair_inliers, B * h->out_cap);
   for (int l = 0; l < kLanes; ++l) {
     dalloc((void**)&h->lanes[l].blurred, (size_t)2 * h->chunk * img_bytes);
     dalloc((void**)&h->lanes[l].mask, (size_t)2 * h->chunk * g.rows * g.mask_words * sizeof(uint32_t));
@@ -345,8 +401,12 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
   halloc((void**)&h->h_n_desc, I * sizeof(int32_t));
   halloc((void**)&h->h_n_out, B * 2 * sizeof(int32_t));
   halloc((void**)&h->h_flag, sizeof(int32_t));
+  halloc((void**)&h->h_systems, B * 32 * sizeof(double));
   for (auto& e : h->clock.ev)
     if (ok && cudaEventCreate(&e) != cudaSuccess) ok = false;
+  if (ok && cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming) != cudaSuccess) ok = false;
+  for (auto& e : h->join_ev)
+    if (ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) ok = false;
   if (ok && cudaMemset(b.error_flag, 0, sizeof(int32_t)) != cudaSuccess) ok = false;
   if (ok && cudaMemset(b.image, 0, I * img_bytes) != cudaSuccess) ok = false;   // row padding is never uninitialised
   if (!ok) {
@@ -372,8 +432,13 @@ int vslam_fpg_destroy(vslam_fpg* h) {
     cudaFree(l.mask);
     if (l.stream) cudaStreamDestroy(l.stream);
   }
+  cudaFree(h->d_systems); cudaFree(h->d_pair_errors); cudaFree(h->d_pair_inliers);
   cudaFreeHost(h->h_counts); cudaFreeHost(h->h_n_desc); cudaFreeHost(h->h_n_out); cudaFreeHost(h->h_flag);
+  cudaFreeHost(h->h_systems);
   for (auto& e : h->clock.ev)
+    if (e) cudaEventDestroy(e);
+  if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+  for (auto& e : h->join_ev)
     if (e) cudaEventDestroy(e);
   delete h;
   return VSLAM_OK;
@@ -534,6 +599,10 @@ int vslam_fpg_get_matches(vslam_fpg* h, vslam_framepoint* out, int32_t capacity,
 int vslam_fpg_set_profiling(vslam_fpg* h, int enabled) {
   if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null handle");
   h->profiling = enabled != 0;
+  if (enabled < 0) {   // reset the accumulators
+    h->t_detect = h->t_describe = h->t_match = 0;
+    for (int i = 0; i < kNumKernels; ++i) h->k_ms[i] = 0, h->k_n[i] = 0;
+  }
   return VSLAM_OK;
 }
 
@@ -559,6 +628,8 @@ static int check_batch(vslam_fpg* h, int32_t n_pairs) {
 static int batch_pipeline(vslam_fpg* h, int32_t n_pairs, const uint8_t* left, const uint8_t* right, size_t stride,
                           size_t pair_stride, bool upload, bool run, vslam_framepoint* out, int32_t out_capacity) {
   int li = 0;
+  int frc = fork_lanes(h);
+  if (frc) return frc;
   for (int p0 = 0; p0 < n_pairs; p0 += h->chunk, li = (li + 1) % kLanes) {
     const int n = std::min(h->chunk, n_pairs - p0);
     Lane& lane = h->lanes[h->profiling ? 0 : li];
@@ -586,12 +657,11 @@ static int batch_pipeline(vslam_fpg* h, int32_t n_pairs, const uint8_t* left, co
       }
     }
   }
-  return VSLAM_OK;
+  return join_lanes(h);
 }
 
 static int batch_finish(vslam_fpg* h, int32_t n_pairs) {
-  // counts travel on lane 0 after every lane has finished its kernels
-  for (int l = 1; l < kLanes; ++l) CUDA_TRY(cudaStreamSynchronize(h->lanes[l].stream));
+  // counts travel on lane 0, which batch_pipeline ordered after every other lane
   cudaStream_t s = h->lanes[0].stream;
   CUDA_TRY(cudaMemcpyAsync(h->h_n_out, h->b.n_out, sizeof(int32_t) * 2 * n_pairs, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(h->h_n_desc, h->b.n_desc, sizeof(int32_t) * 2 * n_pairs, cudaMemcpyDeviceToHost, s));
@@ -612,7 +682,7 @@ int vslam_fpg_batch_upload(vslam_fpg* h, int32_t n_pairs, const uint8_t* left, c
   CUDA_TRY(cudaSetDevice(h->device));
   rc = batch_pipeline(h, n_pairs, left, right, stride, pair_stride, true, false, nullptr, 0);
   if (rc) return rc;
-  for (auto& l : h->lanes) CUDA_TRY(cudaStreamSynchronize(l.stream));
+  CUDA_TRY(cudaStreamSynchronize(h->lanes[0].stream));   // the host buffers may be reused after this call
   return VSLAM_OK;
 }
 
@@ -623,8 +693,6 @@ int vslam_fpg_batch_run(vslam_fpg* h, int32_t n_pairs, int localizing) {
   CUDA_TRY(cudaSetDevice(h->device));
   h->localizing = localizing != 0;
   h->sp.localizing = h->localizing;
-  // lane 1 must see the uploads / previous results ordered on lane 0 and vice versa: callers synchronise
-  // between upload and run (batch_upload does), so plain issue order is enough here
   rc = batch_pipeline(h, n_pairs, nullptr, nullptr, 0, 0, false, true, nullptr, 0);
   if (rc) return rc;
   h->initialized = true;
@@ -675,6 +743,81 @@ int vslam_fpg_batch_process(vslam_fpg* h, int32_t n_pairs, const uint8_t* left, 
     if (out && h->h_n_out[2 * i] > capacity_per_pair)
       return fail(VSLAM_ERR_CAPACITY, "capacity_per_pair %d < %d framepoints of pair %d", capacity_per_pair, h->h_n_out[2 * i], i);
     if (out && (rc = remap_records(h, i, out + (size_t)i * capacity_per_pair, h->h_n_out[2 * i]))) return rc;
+  }
+  return VSLAM_OK;
+}
+
+int vslam_fpg_batch_linearize(vslam_fpg* h, int32_t n_pairs, const double T[12], int ignore_outliers,
+                              double maximum_error_kernel, double minimum_reliable_depth, double maximum_reliable_depth,
+                              int enable_inverse_depth_as_information, int32_t rounds) {
+  int rc = check_batch(h, n_pairs);
+  if (rc) return rc;
+  if (!T || rounds < 1) return fail(VSLAM_ERR_INVALID_ARGUMENT, "bad pose / rounds");
+  if (!h->initialized || h->last_pairs < n_pairs) return fail(VSLAM_ERR_STATE, "no batched run to align");
+  CUDA_TRY(cudaSetDevice(h->device));
+  AlignerCamera cam;   // StereoUVAligner::initialize :65-68
+  const double K[9] = {h->cfg.fx, 0, h->cfg.cx, 0, h->cfg.fy, h->cfg.cy, 0, 0, 1};
+  for (int i = 0; i < 9; ++i) cam.K[i] = K[i];
+  cam.baseline[0] = h->cfg.bx;
+  cam.baseline[1] = cam.baseline[2] = 0;
+  cam.rows = h->g.rows;
+  cam.cols = h->g.cols;
+  cam.min_depth = minimum_reliable_depth;
+  Lane& lane = h->lanes[0];
+  mark(h, lane, kEvLin0);
+  for (int r = 0; r < rounds; ++r) {
+    launch_linearize_pairs(h->d_out, h->out_cap, h->b.n_out, n_pairs, cam, T, ignore_outliers, maximum_error_kernel,
+                           maximum_reliable_depth, enable_inverse_depth_as_information, h->d_systems, h->d_pair_errors,
+                           h->d_pair_inliers, lane.stream);
+    ++h->launches;
+  }
+  mark(h, lane, kEvLin1);
+  CUDA_TRY(cudaGetLastError());
+  if (h->profiling) {
+    CUDA_TRY(cudaStreamSynchronize(lane.stream));
+    add_interval(h, kKLinearize, kEvLin0, kEvLin1, rounds);
+  }
+  return VSLAM_OK;
+}
+
+int vslam_fpg_batch_get_systems(vslam_fpg* h, int32_t n_pairs, vslam_linear_system* systems, double* errors,
+                                uint8_t* inliers, int32_t capacity_per_pair) {
+  int rc = check_batch(h, n_pairs);
+  if (rc) return rc;
+  if (!systems) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null output");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->lanes[0].stream;
+  CUDA_TRY(cudaMemcpyAsync(h->h_systems, h->d_systems, sizeof(double) * 32 * n_pairs, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->h_n_out, h->b.n_out, sizeof(int32_t) * 2 * n_pairs, cudaMemcpyDeviceToHost, s));
+  if (errors || inliers) {
+    const size_t w = (size_t)std::min(capacity_per_pair, h->out_cap);
+    if (errors)
+      CUDA_TRY(cudaMemcpy2DAsync(errors, sizeof(double) * capacity_per_pair, h->d_pair_errors, sizeof(double) * h->out_cap,
+                                 sizeof(double) * w, n_pairs, cudaMemcpyDeviceToHost, s));
+    if (inliers)
+      CUDA_TRY(cudaMemcpy2DAsync(inliers, capacity_per_pair, h->d_pair_inliers, h->out_cap, w, n_pairs,
+                                 cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  for (int p = 0; p < n_pairs; ++p) {
+    const double* v = h->h_systems + (size_t)p * 32;
+    vslam_linear_system& o = systems[p];
+    int k = 0;
+    for (int i = 0; i < 6; ++i)
+      for (int j = i; j < 6; ++j, ++k) o.H[i * 6 + j] = o.H[j * 6 + i] = v[k];
+    for (int i = 0; i < 6; ++i) o.b[i] = v[21 + i];
+    o.total_error = v[27];
+    o.number_of_inliers = (int32_t)std::llrint(v[28]);
+    o.number_of_outliers = h->h_n_out[2 * p] - o.number_of_inliers;
+  }
+  return VSLAM_OK;
+}
+
+int vslam_fpg_get_kernel_profile(vslam_fpg* h, double* milliseconds, int64_t* launches) {
+  if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null handle");
+  for (int i = 0; i < kNumKernels; ++i) {
+    if (milliseconds) milliseconds[i] = h->k_ms[i];
+    if (launches) launches[i] = h->k_n[i];
   }
   return VSLAM_OK;
 }

@@ -70,5 +70,10 @@ struct AlignerCamera {
 int aligner_grid(int n, int sm_count);
 void launch_linearize(int kind, int n, const AlignerBuffers& b, const AlignerCamera& cam, const double T[12],
                       int ignore_outliers, double kernel, int grid, cudaStream_t stream);
+// one CTA per stereo pair: StereoUV initialize + linearize of the pair's new framepoints against themselves
+void launch_linearize_pairs(const FramePointRecord* records, int record_stride, const int32_t* n_out, int n_pairs,
+                            const AlignerCamera& cam, const double T[12], int ignore_outliers, double kernel,
+                            double max_reliable_depth, int inverse_depth_weight, double* systems, double* errors,
+                            uint8_t* inliers, cudaStream_t stream);
 
 }  // namespace vslam
