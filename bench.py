@@ -85,9 +85,7 @@ def _cpu_pair(i):
 
 def _prior():
     from vslam_b200 import synth
-    T = synth.true_motion().copy()
-    T[:, 3] *= 0.05
-    return T
+    return synth.true_motion(0.15)
 
 
 def cpu_baseline(left, right, rounds, sample):

@@ -20,7 +20,7 @@ constexpr int SW = TW + 2 * HX;    // 160
 constexpr int SH = TH + 8;         // 24 : 3 (ring) + 1 (NMS) on both sides
 constexpr int CW = TW + 2;         // score tile width (NMS halo 1)
 constexpr int CH = TH + 2;
-constexpr int CPITCH = 132;
+constexpr int CPITCH = 144;          // multiple of 16 (the score tile is cleared with uint4 stores)
 
 // true iff the 16-bit circular mask m has >= 9 contiguous set bits
 __device__ __forceinline__ bool arc9(unsigned m) {
@@ -83,14 +83,31 @@ __device__ __forceinline__ int fast_score_at(Ptr p, int pitch, int t) {
   return corner_score(d);
 }
 
+// |d| > t per byte lane (t <= 127): bit 7 of each byte of the result.  VABSDIFF4 is the one native byte-SIMD op.
+__device__ __forceinline__ uint32_t absdiff_gt(uint32_t ring, uint32_t center, uint32_t c127_minus_t) {
+  const uint32_t ad = __vabsdiffu4(ring, center);
+  return (((ad & 0x7f7f7f7fu) + c127_minus_t) | ad) & 0x80808080u;
+}
+
+// K1.  Work-efficient FAST: the 16-pixel ring test and the corner score are only evaluated where a cheap necessary
+// condition holds, with two in-CTA compactions so that every phase runs on dense lists:
+//   phase 1  all pixels, 4 per thread, byte-SIMD: every 9-arc contains two ADJACENT compass points (N,E,S,W), so a
+//            corner needs (|dN|>t or |dS|>t) and (|dE|>t or |dW|>t)            -> candidate list
+//   phase 2  candidates: exact 9-of-16 bright/dark arc test                    -> corner list
+//   phase 3  corners: cornerScore<16>                                           -> score tile (zero elsewhere)
+//   phase 4  corners inside the tile: strict 3x3 non-maximum suppression        -> keypoint bit mask
 __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable rt, const uint8_t* __restrict__ image,
                                                        uint32_t* __restrict__ mask, int32_t* __restrict__ raw_count,
                                                        int single_region) {
+  constexpr int WPR = 34;   // words per pretest row: image x in [x0 - 4, x0 + 132)
   __shared__ __align__(16) uint8_t s_img[SH][SW];
-  __shared__ uint8_t s_score[CH][CPITCH];
-  __shared__ int s_count;
+  __shared__ __align__(16) uint8_t s_score[CH][CPITCH];
+  __shared__ uint16_t s_cand[CH * CW];
+  __shared__ uint16_t s_corner[CH * CW];
+  __shared__ uint32_t s_mask[TH][4];
+  __shared__ int s_ncand, s_ncorner;
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int img = blockIdx.z / g.n_regions;
   const int reg = blockIdx.z - img * g.n_regions;
   const Region R = rt.r[reg];
@@ -110,9 +127,8 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable r
     }
     return;
   }
-  if (tid == 0) s_count = 0;
 
-  // ---- stage the tile (+halo) in shared memory: 24 rows x 10 uint4, coalesced 16 B loads
+  // ---- phase 0: stage the tile (+halo) in shared memory: 24 rows x 10 uint4, coalesced 16 B loads; clear state
   const uint8_t* base = image + (size_t)img * g.rows * g.pitch;
   for (int i = tid; i < SH * (SW / 16); i += 256) {
     const int r = i / (SW / 16), c = i - r * (SW / 16);
@@ -122,42 +138,130 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable r
       v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)gy * g.pitch + gx));
     *reinterpret_cast<uint4*>(&s_img[r][c * 16]) = v;
   }
+  for (int i = tid; i < CH * CPITCH / 16; i += 256) reinterpret_cast<uint4*>(&s_score[0][0])[i] = make_uint4(0, 0, 0, 0);
+  if (tid < TH * 4) (&s_mask[0][0])[tid] = 0u;
+  if (tid == 0) s_ncand = s_ncorner = 0;
   __syncthreads();
 
-  // ---- corner score on the tile + 1 px NMS halo
-  for (int i = tid; i < CH * CW; i += 256) {
-    const int sy = i / CW, sx = i - sy * CW;
-    const int ix = x0 - 1 + sx, iy = y0 - 1 + sy;
-    int s = 0;
-    if (ix >= ax0 && ix <= ax1 && iy >= ay0 && iy <= ay1) s = fast_score_at(&s_img[sy + 3][sx + HX - 1], SW, t);
-    s_score[sy][sx] = (uint8_t)s;
+  // ---- phase 1: compass pre-test on the tile + 1 px NMS halo
+  const int cx_lo = max(ax0, x0 - 1), cx_hi = min(ax1, x0 + TW);   // columns whose score is needed
+  if (t <= 127) {
+    const uint32_t cadd = 0x01010101u * (uint32_t)(127 - t);
+    for (int u0 = 0; u0 < CH * WPR; u0 += 256) {
+      const int u = u0 + tid;
+      uint32_t m = 0;
+      int sy = 0, wi = 0;
+      if (u < CH * WPR) {
+        sy = u / WPR;
+        wi = u - sy * WPR;
+        const int iy = y0 - 1 + sy;
+        if (iy >= ay0 && iy <= ay1) {
+          const uint32_t* rc = reinterpret_cast<const uint32_t*>(&s_img[sy + 3][0]) + 3 + wi;
+          const uint32_t c = rc[0];
+          const uint32_t rn = reinterpret_cast<const uint32_t*>(&s_img[sy][0])[3 + wi];       // y - 3
+          const uint32_t rs = reinterpret_cast<const uint32_t*>(&s_img[sy + 6][0])[3 + wi];   // y + 3
+          const uint32_t re = __funnelshift_r(c, rc[1], 24);                                  // x + 3
+          const uint32_t rw = __funnelshift_r(rc[-1], c, 8);                                  // x - 3
+          m = (absdiff_gt(rn, c, cadd) | absdiff_gt(rs, c, cadd)) & (absdiff_gt(re, c, cadd) | absdiff_gt(rw, c, cadd));
+          // keep the bytes whose column lies in [cx_lo, cx_hi]
+          const int bx = x0 - 4 + 4 * wi;
+          const int lo = cx_lo - bx, hi = cx_hi - bx;
+          uint32_t keep = 0x80808080u;
+          if (lo > 0) keep = lo > 3 ? 0u : keep << (8 * lo);
+          if (hi < 3) keep = hi < 0 ? 0u : keep & (0x80808080u >> (8 * (3 - hi)));
+          m &= keep;
+        }
+      }
+      // warp-level compaction of the up-to-4 candidates per thread
+      const int n = __popc(m);
+      int inc = n;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      int wbase = 0;
+      if (lane == 31 && inc) wbase = atomicAdd(&s_ncand, inc);
+      wbase = __shfl_sync(0xffffffffu, wbase, 31);
+      int pos = wbase + inc - n;
+      while (m) {
+        const int j = (__ffs(m) - 1) >> 3;
+        m &= m - 1;
+        s_cand[pos++] = (uint16_t)(sy * CW + 4 * wi + j - 3);
+      }
+    }
+  } else {   // thresholds above 127 (never produced by the reference's configurations): every pixel is a candidate
+    for (int i = tid; i < CH * CW; i += 256) {
+      const int sy = i / CW, sx = i - sy * CW;
+      const int ix = x0 - 1 + sx, iy = y0 - 1 + sy;
+      if (ix >= cx_lo && ix <= cx_hi && iy >= ay0 && iy <= ay1) s_cand[atomicAdd(&s_ncand, 1)] = (uint16_t)i;
+    }
   }
   __syncthreads();
 
-  // ---- 3x3 strict non-maximum suppression, one warp per (row, 32-column word)
-  const int warp = tid >> 5, lane = tid & 31;
-  int found = 0;
-  for (int u = warp; u < TH * 4; u += 8) {
-    const int ry = u >> 2, wx = u & 3;
-    const int sx = wx * 32 + lane + 1, sy = ry + 1;
+  // ---- phase 2: exact segment test on the candidates
+  const int ncand = s_ncand;
+  for (int c = tid; c < ncand; c += 256) {
+    const int i = s_cand[c];
+    const int sy = i / CW, sx = i - sy * CW;
+    const uint8_t* p = &s_img[sy + 3][sx + HX - 1];
+    const int v = p[0];
+    unsigned dark = 0, bright = 0;
+#define F(k, dx, dy)                                  \
+  {                                                   \
+    const int d = v - (int)p[(dy) * SW + (dx)];       \
+    dark |= (unsigned)(d > t) << k;                   \
+    bright |= (unsigned)(d < -t) << k;                \
+  }
+    VSLAM_RING(F)
+#undef F
+    if (arc9(dark) || arc9(bright)) s_corner[atomicAdd(&s_ncorner, 1)] = (uint16_t)i;
+  }
+  __syncthreads();
+
+  // ---- phase 3: corner scores
+  const int ncorner = s_ncorner;
+  for (int c = tid; c < ncorner; c += 256) {
+    const int i = s_corner[c];
+    const int sy = i / CW, sx = i - sy * CW;
+    const uint8_t* p = &s_img[sy + 3][sx + HX - 1];
+    const int v = p[0];
+    int d[16];
+#define F(k, dx, dy) d[k] = v - (int)p[(dy) * SW + (dx)];
+    VSLAM_RING(F)
+#undef F
+    s_score[sy][sx] = (uint8_t)corner_score(d);
+  }
+  __syncthreads();
+
+  // ---- phase 4: 3x3 strict non-maximum suppression of the corners inside the tile
+  for (int c = tid; c < ncorner; c += 256) {
+    const int i = s_corner[c];
+    const int sy = i / CW, sx = i - sy * CW;
+    if (sy < 1 || sy > TH || sx < 1 || sx > TW) continue;
     const int s = s_score[sy][sx];
-    bool kp = false;
-    if (s > 0) {
-      kp = s > s_score[sy - 1][sx - 1] && s > s_score[sy - 1][sx] && s > s_score[sy - 1][sx + 1] &&
-           s > s_score[sy][sx - 1] && s > s_score[sy][sx + 1] && s > s_score[sy + 1][sx - 1] &&
-           s > s_score[sy + 1][sx] && s > s_score[sy + 1][sx + 1];
-    }
-    const unsigned word = __ballot_sync(0xffffffffu, kp);
+    const bool kp = s > s_score[sy - 1][sx - 1] && s > s_score[sy - 1][sx] && s > s_score[sy - 1][sx + 1] &&
+                    s > s_score[sy][sx - 1] && s > s_score[sy][sx + 1] && s > s_score[sy + 1][sx - 1] &&
+                    s > s_score[sy + 1][sx] && s > s_score[sy + 1][sx + 1];
+    if (kp) atomicOr(&s_mask[sy - 1][(sx - 1) >> 5], 1u << ((sx - 1) & 31));
+  }
+  __syncthreads();
+
+  // ---- phase 5: publish the tile's 16 x 4 mask words and the raw keypoint count
+  if (tid < 64) {
+    const int ry = tid >> 2, wx = tid & 3;
+    const uint32_t word = s_mask[ry][wx];
     const int y = y0 + ry, wd = (x0 >> 5) + wx;
-    if (lane == 0 && y < g.rows && wd < g.mask_words) {
+    int found = 0;
+    if (y < g.rows && wd < g.mask_words) {
       if (single_region) mrow[(size_t)y * g.mask_words + wd] = word;
       else if (word) atomicOr(&mrow[(size_t)y * g.mask_words + wd], word);
-      found += __popc(word);
+      found = __popc(word);
     }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) found += __shfl_xor_sync(0xffffffffu, found, o);
+    if (lane == 0 && found) atomicAdd(&raw_count[img * g.n_regions + reg], found);
   }
-  if (lane == 0 && found) atomicAdd(&s_count, found);
-  __syncthreads();
-  if (tid == 0 && s_count) atomicAdd(&raw_count[img * g.n_regions + reg], s_count);
 }
 
 // K2: one CTA per image.  Applies cv::ORB's 31 px border filter (KeyPointsFilter::runByImageBorder), builds the
@@ -253,6 +357,39 @@ __global__ void __launch_bounds__(256) compact_kernel(Geometry g, const uint8_t*
       row_base += __shfl_sync(0xffffffffu, inc, 31);
     }
   }
+}
+
+// one thread per 4 output bytes: aligned 32-bit store, source assembled from two aligned words (rows of the dense
+// layout start at arbitrary byte offsets, e.g. stride 1241)
+__global__ void __launch_bounds__(256) repitch_kernel(Geometry g, const uint8_t* __restrict__ left,
+                                                      const uint8_t* __restrict__ right, int stride,
+                                                      uint8_t* __restrict__ image) {
+  const int words = g.pitch >> 2;
+  const int row = blockIdx.y;
+  const int img = blockIdx.z;   // 2 * pair + side
+  const uint8_t* src = ((img & 1) ? right : left) + ((size_t)(img >> 1) * g.rows + row) * stride;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(image + ((size_t)img * g.rows + row) * g.pitch);
+  const size_t a0 = reinterpret_cast<size_t>(src);
+  for (int w = blockIdx.x * 256 + threadIdx.x; w < words; w += gridDim.x * 256) {
+    uint32_t v = 0;
+    if (4 * w < g.cols) {
+      const size_t a = a0 + 4 * (size_t)w;
+      const uint32_t* p = reinterpret_cast<const uint32_t*>(a & ~(size_t)3);
+      const unsigned sh = (unsigned)(a & 3) * 8;
+      const uint32_t lo = __ldg(p);
+      const uint32_t hi = sh ? __ldg(p + 1) : 0u;   // within the staging slack when it runs past the last row
+      v = __funnelshift_r(lo, hi, sh);
+      const int left_over = g.cols - 4 * w;         // zero the padding beyond the image width
+      if (left_over < 4) v &= 0xffffffffu >> (8 * (4 - left_over));
+    }
+    dst[w] = v;
+  }
+}
+
+void launch_repitch(const Geometry& g, const uint8_t* left, const uint8_t* right, int stride, uint8_t* image,
+                    int n_pairs, cudaStream_t stream) {
+  dim3 grid(((g.pitch >> 2) + 255) / 256, g.rows, 2 * n_pairs);
+  repitch_kernel<<<grid, 256, 0, stream>>>(g, left, right, stride, image);
 }
 
 void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, int first_image, int n_images,

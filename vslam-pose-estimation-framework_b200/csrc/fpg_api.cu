@@ -31,6 +31,8 @@ struct Lane {
   cudaStream_t stream = nullptr;
   uint8_t* blurred = nullptr;   // [2*chunk][rows][pitch]
   uint32_t* mask = nullptr;     // [2*chunk][rows][mask_words]
+  uint8_t* stage = nullptr;     // [2][chunk * pair_stride] dense landing zone of the H2D copies
+  size_t stage_bytes = 0;       // per side
 };
 
 // profiling: events at the kernel boundaries of one chunk (single lane, serialised)
@@ -192,6 +194,29 @@ int join_lanes(vslam_fpg* h) {
 int upload_images(vslam_fpg* h, Lane& lane, int p0, int n, const uint8_t* left, const uint8_t* right, size_t stride,
                   size_t pair_stride) {
   const Geometry& g = h->g;
+  if (n > 1 && pair_stride == stride * (size_t)g.rows) {
+    // Images are contiguous on the host: ONE linear copy per side at full PCIe rate (strided 2-D/3-D copies of
+    // 1241-byte rows run several times slower), then a device kernel re-pitches rows to the 128 B aligned layout.
+    const size_t bytes = (size_t)n * pair_stride;
+    if (lane.stage_bytes < bytes) {
+      CUDA_TRY(cudaStreamSynchronize(lane.stream));
+      cudaFree(lane.stage);
+      lane.stage = nullptr;
+      lane.stage_bytes = 0;
+      const size_t want = (size_t)h->chunk * pair_stride;
+      CUDA_TRY(cudaMalloc((void**)&lane.stage, 2 * want + 64));
+      lane.stage_bytes = want;
+    }
+    for (int side = 0; side < 2; ++side) {
+      const uint8_t* src = (side == 0 ? left : right) + (size_t)p0 * pair_stride;
+      uint8_t* dst = lane.stage + (size_t)side * lane.stage_bytes;
+      CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, lane.stream));
+    }
+    launch_repitch(g, lane.stage, lane.stage + lane.stage_bytes, (int)stride,
+                   h->b.image + (size_t)2 * p0 * g.rows * g.pitch, n, lane.stream);
+    ++h->launches;
+    return VSLAM_OK;
+  }
   for (int side = 0; side < 2; ++side) {
     const uint8_t* src = (side == 0 ? left : right) + (size_t)p0 * pair_stride;
     uint8_t* dst = h->b.image + ((size_t)2 * p0 + side) * g.rows * g.pitch;
@@ -358,9 +383,11 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
   h->sp.localizing = 1;
   h->out_cap = g.enable_binning ? h->target_keypoints : g.cap;
 
-  // chunk: keep image + blurred + mask of one chunk well inside the 126 MB L2
+  // chunk: pairs per launch.  Large enough that the one-CTA-per-image / per-pair kernels (compact, select) fill the
+  // 148 SMs; the path is instruction-bound, not HBM-bound, so L2 residency of a chunk's intermediates is secondary
+  // (measured: profiles/r1_notes.md)
   const size_t per_pair = (size_t)2 * g.rows * (2 * g.pitch + 4 * g.mask_words);
-  int chunk = (int)std::max<size_t>(1, (size_t)(40u << 20) / per_pair);
+  int chunk = (int)std::min<size_t>(256, std::max<size_t>(1, ((size_t)512u << 20) / per_pair));
   if (const char* e = std::getenv("VSLAM_CHUNK_PAIRS")) chunk = std::max(1, atoi(e));
   h->chunk = std::min(chunk, h->max_batch);
 
@@ -430,6 +457,7 @@ int vslam_fpg_destroy(vslam_fpg* h) {
   for (auto& l : h->lanes) {
     cudaFree(l.blurred);
     cudaFree(l.mask);
+    cudaFree(l.stage);
     if (l.stream) cudaStreamDestroy(l.stream);
   }
   cudaFree(h->d_systems); cudaFree(h->d_pair_errors); cudaFree(h->d_pair_inliers);

@@ -31,6 +31,9 @@ struct FramePointRecord {   // == vslam_framepoint
 };
 
 // all launches are asynchronous on `stream`; image ranges are [first_image, first_image + n_images)
+// dense host-layout images (row stride `stride` bytes, any alignment) -> pitched device images [pair][side][row][pitch]
+void launch_repitch(const Geometry& g, const uint8_t* left, const uint8_t* right, int stride, uint8_t* image,
+                    int n_pairs, cudaStream_t stream);
 void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, int first_image, int n_images,
                  cudaStream_t stream);
 void launch_compact(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream);

@@ -137,10 +137,10 @@ def _rot(rx, ry, rz):
     return Rz @ Ry @ Rx
 
 
-def true_motion() -> np.ndarray:
-    """T* = rot(0.01,-0.02,0.005 rad) . trans(0.05,-0.02,0.8 m) as a 3x4 [R|t]."""
-    R = _rot(0.01, -0.02, 0.005)
-    t = R @ np.array([0.05, -0.02, 0.8])
+def true_motion(scale: float = 1.0) -> np.ndarray:
+    """T* = rot(0.01,-0.02,0.005 rad) . trans(0.05,-0.02,0.8 m) as a 3x4 [R|t]; `scale` shrinks angles and lengths."""
+    R = _rot(0.01 * scale, -0.02 * scale, 0.005 * scale)
+    t = R @ (np.array([0.05, -0.02, 0.8]) * scale)
     return np.hstack([R, t[:, None]])
 
 
