@@ -265,11 +265,9 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable r
 }
 
 // K2: one CTA per image.  Applies cv::ORB's 31 px border filter (KeyPointsFilter::runByImageBorder), builds the
-// CSR row pointer and the (row, col)-sorted keypoint list, and recomputes the FAST score of each kept keypoint
-// (for a corner the score does not depend on the threshold).
-__global__ void __launch_bounds__(256) compact_kernel(Geometry g, const uint8_t* __restrict__ image,
-                                                      const uint32_t* __restrict__ mask, int32_t* __restrict__ row_ptr,
-                                                      uint32_t* __restrict__ kp_xy, uint8_t* __restrict__ kp_score,
+// CSR row pointer and the (row, col)-sorted keypoint list.
+__global__ void __launch_bounds__(256) compact_kernel(Geometry g, const uint32_t* __restrict__ mask,
+                                                      int32_t* __restrict__ row_ptr, uint32_t* __restrict__ kp_xy,
                                                       int32_t* __restrict__ n_desc, int32_t* __restrict__ error_flag) {
   extern __shared__ int s_rows[];   // rows + 1 counts -> exclusive offsets
   __shared__ int s_warp[8];
@@ -327,9 +325,7 @@ __global__ void __launch_bounds__(256) compact_kernel(Geometry g, const uint8_t*
   for (int y = tid; y <= g.rows; y += 256) rp[y] = min(s_rows[y], g.cap);
 
   // ordered emission
-  const uint8_t* base = image + (size_t)img * g.rows * g.pitch;
   uint32_t* xy = kp_xy + (size_t)img * g.cap;
-  uint8_t* sc = kp_score + (size_t)img * g.cap;
   for (int y = lo_y + warp; y < hi_y; y += 8) {
     if (s_rows[y + 1] == s_rows[y]) continue;
     int row_base = s_rows[y];
@@ -348,10 +344,7 @@ __global__ void __launch_bounds__(256) compact_kernel(Geometry g, const uint8_t*
         const int b = __ffs(bits) - 1;
         bits &= bits - 1;
         const int x = wd * 32 + b;
-        if (idx < g.cap) {
-          xy[idx] = (uint32_t)x | ((uint32_t)y << 16);
-          sc[idx] = (uint8_t)fast_score_at(base + (size_t)y * g.pitch + x, g.pitch, 0);
-        }
+        if (idx < g.cap) xy[idx] = (uint32_t)x | ((uint32_t)y << 16);
         ++idx;
       }
       row_base += __shfl_sync(0xffffffffu, inc, 31);
@@ -406,10 +399,28 @@ void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, int
 
 void launch_compact(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream) {
   const size_t smem = sizeof(int) * (g.rows + 1);
-  compact_kernel<<<n_images, 256, smem, stream>>>(
-      g, b.image + (size_t)first_image * g.rows * g.pitch, b.mask + (size_t)first_image * g.rows * g.mask_words,
-      b.row_ptr + (size_t)first_image * (g.rows + 1), b.kp_xy + (size_t)first_image * g.cap,
-      b.kp_score + (size_t)first_image * g.cap, b.n_desc + first_image, b.error_flag);
+  compact_kernel<<<n_images, 256, smem, stream>>>(g, b.mask + (size_t)first_image * g.rows * g.mask_words,
+                                                  b.row_ptr + (size_t)first_image * (g.rows + 1),
+                                                  b.kp_xy + (size_t)first_image * g.cap, b.n_desc + first_image,
+                                                  b.error_flag);
+}
+
+// cv::KeyPoint::response of the kept keypoints (cornerScore<16>): nothing on the path reads it, so it is produced
+// only when a caller asks for keypoints (vslam_fpg_get_features).  For a corner the score does not depend on the
+// detector threshold: max(t, A, -B) - 1 with A > t or -B > t.
+__global__ void __launch_bounds__(256) score_kernel(Geometry g, const uint8_t* __restrict__ image,
+                                                    const uint32_t* __restrict__ kp_xy,
+                                                    const int32_t* __restrict__ n_desc, uint8_t* __restrict__ kp_score) {
+  const int n = n_desc[0];
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const uint32_t q = kp_xy[i];
+    kp_score[i] = (uint8_t)fast_score_at(image + (size_t)(q >> 16) * g.pitch + (q & 0xffffu), g.pitch, 0);
+  }
+}
+
+void launch_score(const Geometry& g, const Buffers& b, int image, cudaStream_t stream) {
+  score_kernel<<<32, 256, 0, stream>>>(g, b.image + (size_t)image * g.rows * g.pitch, b.kp_xy + (size_t)image * g.cap,
+                                       b.n_desc + image, b.kp_score + (size_t)image * g.cap);
 }
 
 }  // namespace vslam

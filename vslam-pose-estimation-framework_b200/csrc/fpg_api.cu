@@ -305,7 +305,13 @@ int get_features(vslam_fpg* h, int pair, int side, vslam_keypoint* kps, uint8_t*
   reference_order(h, xy, s2r, r2s);
   if (kps) {
     std::vector<uint8_t> score(n);
-    if (n) CUDA_TRY(cudaMemcpy(score.data(), h->b.kp_score + (size_t)image * h->g.cap, n, cudaMemcpyDeviceToHost));
+    if (n) {
+      launch_score(h->g, h->b, image, h->lanes[0].stream);
+      ++h->launches;
+      CUDA_TRY(cudaMemcpyAsync(score.data(), h->b.kp_score + (size_t)image * h->g.cap, n, cudaMemcpyDeviceToHost,
+                               h->lanes[0].stream));
+      CUDA_TRY(cudaStreamSynchronize(h->lanes[0].stream));
+    }
     for (int k = 0; k < n; ++k) {
       const int i = r2s[k];
       kps[k].x = (float)(xy[i] & 0xffff);

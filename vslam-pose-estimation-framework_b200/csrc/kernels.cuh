@@ -37,6 +37,8 @@ void launch_repitch(const Geometry& g, const uint8_t* left, const uint8_t* right
 void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, int first_image, int n_images,
                  cudaStream_t stream);
 void launch_compact(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream);
+// FAST response of the kept keypoints of one image -> kp_score (on demand)
+void launch_score(const Geometry& g, const Buffers& b, int image, cudaStream_t stream);
 void launch_blur(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream);
 void launch_describe(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream);
 // one launch per epipolar offset (pass index -> offset 0,+1,-1,+2,...)
