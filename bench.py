@@ -216,7 +216,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from vslam_b200 import api, configs, synth
+    from vslam_b200 import api, configs, sharding, synth
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -233,11 +233,7 @@ def main():
             dist.barrier()
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.max_over_ranks(x, dev)
 
     cfg, acfg = configs.BY_NAME[CONFIG_NAME], configs.ALIGNER_BY_NAME[CONFIG_NAME]
     cam = synth.camera(cfg.camera)
@@ -247,7 +243,7 @@ def main():
     # ---- synthetic inputs: D distinct band-world pairs per rank (seeds disjoint across ranks), tiled to P pairs in
     # pinned host memory (every pair is its own memory and is processed independently)
     cores = len(os.sched_getaffinity(0))
-    dl, dr = synth.band_world_batch(cfg.camera, range(rank * D, (rank + 1) * D), workers=max(1, min(cores // world, 32)))
+    dl, dr = synth.band_world_batch(cfg.camera, sharding.weak_seeds(D, rank), workers=max(1, min(cores // world, 32)))
     left = api.pinned_empty((P, cam.rows, cam.cols))
     right = api.pinned_empty((P, cam.rows, cam.cols))
     for i in range(0, P, D):

@@ -141,6 +141,12 @@ int vslam_fpg_get_features(vslam_fpg* h, int side, vslam_keypoint* keypoints, ui
 int vslam_fpg_get_detection_stats(vslam_fpg* h, int32_t* counts_left, int32_t* counts_right,
                                   double* matching_distance);
 
+/* What track() leaves behind (stereo_framepoint_generator.cpp:646-651, 671-672: matched features are pruned from
+ * _feature_matcher_left/right before compute() scans the rest).  `remaining` = keypoints of the features still in
+ * the matcher's feature_vector for `side` (0 left, 1 right); every other feature of the frame is excluded from the
+ * next compute().  Without this call every feature of initialize() takes part (first frame / Localizing restart). */
+int vslam_fpg_set_remaining_features(vslam_fpg* h, int side, const vslam_keypoint* remaining, int32_t n);
+
 /* StereoFramePointGenerator::compute(frame), :135-462 (without the dead use_matches block :168-273).
  * tracked: the points already in frame->points().  framepoints: the points compute() appends to
  * frame->points(), in order (bin winners without previous(), row-major over bins; every match in emission

@@ -1,0 +1,86 @@
+// host_api_check.cpp -- a C++14 consumer of include/vslam_b200.hpp, shaped like the reference's own
+// executables/test_stereo_frontend.cpp (initialize -> compute on a stereo pair, prints counts) plus an aligner run.
+// Reads raw u8 images and correspondence arrays written by tests/test_gpu_cpp_host.py and prints results as text that
+// the pytest compares with the CPU oracle.
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+
+#include "vslam_b200.hpp"
+
+static std::vector<uint8_t> slurp(const std::string& path) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) throw std::runtime_error("cannot open " + path);
+  return std::vector<uint8_t>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) return 2;
+  const std::string dir = argv[1];
+  try {
+    // ---- framepoint generation, configuration_kitti.yaml values (reference configurations/configuration_kitti.yaml:58-93)
+    vslam_fpg_config c = {};
+    c.rows = 376; c.cols = 1241;
+    c.target_number_of_keypoints_tolerance = 0.1;
+    c.detector_threshold_minimum = 20; c.detector_threshold_maximum = 100; c.detector_threshold_maximum_change = 0.1;
+    c.number_of_detectors_vertical = 1; c.number_of_detectors_horizontal = 1;
+    c.enable_keypoint_binning = 1; c.bin_size_pixels = 15;
+    c.maximum_matching_distance_triangulation = 51.2; c.minimum_disparity_pixels = 1;
+    c.maximum_epipolar_search_offset_pixels = 0;
+    c.fx = c.fy = 718.856; c.cx = 607.1928; c.cy = 185.2157; c.bx = -386.1448;
+    vslam::StereoFramePointGenerator generator(c);
+    const std::vector<uint8_t> left = slurp(dir + "/left.u8"), right = slurp(dir + "/right.u8");
+    vslam::Frame frame;
+    frame.status = vslam::Frame::Localizing;
+    frame.intensity_image_left = left.data();
+    frame.intensity_image_right = right.data();
+    frame.image_step = 1241;
+    generator.initialize(&frame);
+    generator.compute(&frame);
+    std::printf("features %zu %zu\n", frame.keypoints_left.size(), frame.keypoints_right.size());
+    std::printf("points %zu new %d threshold %.1f\n", frame.points.size(), generator.numberOfNewPoints(),
+                generator.meanDetectorThreshold());
+    unsigned long long h = 1469598103934665603ull;   // FNV-1a over the descriptors and the selected points
+    for (uint8_t b : frame.descriptors_left) h = (h ^ b) * 1099511628211ull;
+    for (const vslam_framepoint& p : frame.points) {
+      const int32_t v[4] = {p.index_left, p.index_right, p.distance, p.epipolar_offset};
+      for (int32_t x : v) h = (h ^ (unsigned long long)(uint32_t)x) * 1099511628211ull;
+    }
+    std::printf("hash %llu\n", h);
+    if (!frame.points.empty())
+      std::printf("first %.17g %.17g %.17g\n", frame.points[0].camera[0], frame.points[0].camera[1], frame.points[0].camera[2]);
+
+    // ---- StereoUVAligner::converge on the correspondence set written by the pytest
+    const std::vector<uint8_t> raw = slurp(dir + "/correspondences.f64");
+    const double* d = reinterpret_cast<const double*>(raw.data());
+    const int32_t n = (int32_t)d[0];
+    const double* moving = d + 1;
+    const double* fixed = moving + 3 * (size_t)n;
+    const double* omega = fixed + 4 * (size_t)n;
+    const double* wt = omega + n;
+    vslam_aligner_parameters ap = {1e-3, 16.0, 0.0, 1000, 0};   // configuration_kitti_fast.yaml:109-113
+    vslam::StereoUVAligner aligner(ap, n);
+    const double K[9] = {718.856, 0, 607.1928, 0, 718.856, 185.2157, 0, 0, 1};
+    const double baseline[3] = {-386.1448, 0, 0};
+    aligner.initialize(n, moving, fixed, omega, wt, K, baseline, 376, 1241, 0.1, {{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}});
+    aligner.converge();
+    std::printf("aligner converged %d rounds %d inliers %d outliers %d\n", (int)aligner.hasSystemConverged(),
+                aligner.numberOfRounds(), aligner.numberOfInliers(), aligner.numberOfOutliers());
+    const std::array<double, 12>& T = aligner.previousToCurrent();
+    std::printf("pose");
+    for (double v : T) std::printf(" %.17g", v);
+    std::printf("\n");
+    // error behaviour: exceptions, like the reference
+    try {
+      generator.initialize(nullptr);
+      std::printf("no exception\n");
+    } catch (const std::runtime_error& e) {
+      std::printf("exception %s\n", e.what());
+    }
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "FAILED: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

@@ -1,0 +1,70 @@
+"""The C++14 host layer (include/vslam_b200.hpp) used from a compiled C++ program shaped like the reference's
+executables/test_stereo_frontend.cpp, checked against the CPU oracle."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import pipeline, tier_a
+from vslam_b200 import api, configs, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "host_api_check.cpp")
+LIBDIR = os.path.dirname(api.LIB_PATH)
+
+
+def _build(out):
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), SRC, "-o", out,
+                           "-L", LIBDIR, "-lvslam_b200", "-Wl,-rpath," + LIBDIR])
+
+
+def test_cpp_host_layer_compiles_as_cxx14_and_header_as_c99(tmp_path):
+    _build(str(tmp_path / "host_api_check"))
+    c = tmp_path / "abi.c"
+    c.write_text('#include "vslam_b200.h"\nint main(void) { return vslam_device_count() < 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(c),
+                           "-o", str(tmp_path / "abi"), "-L", LIBDIR, "-lvslam_b200", "-Wl,-rpath," + LIBDIR])
+    subprocess.check_call([str(tmp_path / "abi")])
+
+
+@pytest.mark.gpu
+def test_cpp_frontend_program_matches_oracle(tmp_path):
+    exe = str(tmp_path / "host_api_check")
+    _build(exe)
+    cfg, cam = configs.KITTI, synth.camera("kitti")
+    left, right = synth.band_world_pair("kitti", 12)
+    left.tofile(tmp_path / "left.u8")
+    right.tofile(tmp_path / "right.u8")
+    n = 3000
+    c = synth.correspondences(n, "stereouv", cam, seed=99)
+    np.concatenate([[float(n)], c["moving"].ravel(), c["fixed"].ravel(), c["omega"], c["wt"]]).tofile(
+        tmp_path / "correspondences.f64")
+    out = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    lines = dict(l.split(" ", 1) for l in out.stdout.strip().splitlines())
+
+    o = pipeline.StereoFramePointGeneratorOracle(cfg, cam, "a").initialize(left, right, True)
+    o.compute()
+    fp = o.framepoints()
+    assert lines["features"] == "%d %d" % (len(o.kps_left), len(o.kps_right))
+    assert lines["points"] == "%d new %d threshold %.1f" % (len(fp), len(o.matches), o.thresholds.mean())
+    h = 1469598103934665603
+    for b in o.desc_left.ravel().tolist():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    for p in fp:
+        for x in (p["index_left"], p["index_right"], p["distance"], p["epipolar_offset"]):
+            h = ((h ^ (int(x) & 0xFFFFFFFF)) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    assert lines["hash"] == str(h)
+    assert [float(v) for v in lines["first"].split()] == fp[0]["cam"].tolist()
+
+    al = tier_a.Aligner("stereouv", c["moving"], c["fixed"], c["omega"], c["wt"], cam.K, cam.baseline, cam.rows, cam.cols,
+                        0.1, 16.0)
+    r = al.converge(np.hstack([np.eye(3), np.zeros((3, 1))]), 0.0, 1e-3, 1000, 0)
+    assert lines["aligner"] == "converged %d rounds %d inliers %d outliers %d" % (r["converged"], r["rounds"], r["inliers"],
+                                                                                   r["outliers"])
+    T = np.array([float(v) for v in lines["pose"].split()]).reshape(3, 4)
+    dR = T[:, :3] @ r["T"][:, :3].T
+    assert np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1)) <= 1e-6 and np.linalg.norm(T[:, 3] - r["T"][:, 3]) <= 1e-5
+    assert "called with empty frame" in lines["exception"]

@@ -290,3 +290,31 @@ def test_chronometers_and_kernel_profile():
     assert all(prof[k][1] == 1 for k in ("fast_nms", "compact", "blur", "describe", "match", "select"))
     assert gen.launch_count == 6
     gen.close()
+
+
+def test_features_consumed_by_tracking_are_excluded_from_the_scan():
+    """track() prunes the features it matched before compute() runs (stereo_framepoint_generator.cpp:671-672)."""
+    cfg, cam = configs.KITTI, synth.camera("kitti")
+    left, right = synth.band_world_pair("kitti", 8)
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    gen.initialize(left, right, False)
+    o = pipeline.StereoFramePointGeneratorOracle(cfg, cam, "a").initialize(left, right, False)
+    rng = np.random.default_rng(0)
+    keep_l = rng.random(len(o.kps_left)) > 0.3
+    keep_r = rng.random(len(o.kps_right)) > 0.3
+    gen.set_remaining_features(0, o.kps_left[keep_l])
+    gen.set_remaining_features(1, o.kps_right[keep_r])
+    # oracle: the matcher's feature vectors without the pruned features (indices keep referring to the frame's arrays)
+    fl = o.features_left[keep_l[o.features_left["index"]]]
+    fr = o.features_right[keep_r[o.features_right["index"]]]
+    r = tier_a.stereo_compute(fl, fr, o.stereo_camera, o.max_distance, cfg.minimum_disparity_pixels, 0, True,
+                              cfg.bin_size_pixels, cam.rows, cam.cols)
+    fps = gen.compute()
+    _same_points(gen.matches(), r["matches"])
+    _same_points(fps, r["matches"][r["winners"]])
+    assert 200 < len(r["matches"]) < len(o.kps_left) * 0.6
+    with pytest.raises(api.VslamError):
+        bad = np.zeros(1, api.KEYPOINT)
+        bad["x"], bad["y"] = 5, 5
+        gen.set_remaining_features(0, bad)
+    gen.close()

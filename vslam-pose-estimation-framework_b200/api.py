@@ -30,7 +30,8 @@ assert FRAMEPOINT.itemsize == 56 and TRACKED.itemsize == 32
 # every symbol include/vslam_b200.h declares (tests check that the library exports each one)
 EXPORTS = """vslam_last_error vslam_version vslam_device_count vslam_host_alloc vslam_host_free
 vslam_fpg_create vslam_fpg_destroy vslam_fpg_info vslam_fpg_get_thresholds vslam_fpg_set_thresholds
-vslam_fpg_initialize vslam_fpg_get_features vslam_fpg_get_detection_stats vslam_fpg_compute vslam_fpg_get_matches
+vslam_fpg_initialize vslam_fpg_get_features vslam_fpg_get_detection_stats vslam_fpg_set_remaining_features
+vslam_fpg_compute vslam_fpg_get_matches
 vslam_fpg_set_profiling vslam_fpg_get_time_consumption vslam_fpg_batch_upload vslam_fpg_batch_run
 vslam_fpg_batch_download vslam_fpg_batch_process vslam_fpg_batch_linearize vslam_fpg_batch_get_systems
 vslam_fpg_get_kernel_profile vslam_fpg_batch_get_features vslam_fpg_stream vslam_fpg_synchronize
@@ -101,6 +102,7 @@ def lib():
         L.vslam_fpg_get_features.argtypes = [vp, C.c_int, vp, vp, i32, vp]
         L.vslam_fpg_get_detection_stats.argtypes = [vp, vp, vp, vp]
         L.vslam_fpg_compute.argtypes = [vp, vp, i32, vp, i32, vp, vp]
+        L.vslam_fpg_set_remaining_features.argtypes = [vp, C.c_int, vp, i32]
         L.vslam_fpg_get_matches.argtypes = [vp, vp, i32, vp]
         L.vslam_fpg_set_profiling.argtypes = [vp, C.c_int]
         L.vslam_fpg_get_time_consumption.argtypes = [vp, vp, vp, vp]
@@ -248,6 +250,11 @@ class StereoFramePointGenerator:
         d = C.c_double()
         _check(lib().vslam_fpg_get_detection_stats(self._h, _p(cl), _p(cr), C.byref(d)))
         return cl, cr, d.value
+
+    def set_remaining_features(self, side, keypoints):
+        """the features track() left unmatched in _feature_matcher_left/right (everything else is pruned)"""
+        k = np.ascontiguousarray(keypoints, KEYPOINT)
+        _check(lib().vslam_fpg_set_remaining_features(self._h, side, _p(k) if len(k) else None, len(k)))
 
     # -- StereoFramePointGenerator::compute(frame)
     def compute(self, tracked=None):

@@ -37,7 +37,8 @@ struct Buffers {
   uint8_t* desc;         // [2B][cap][32]            sorted order
   int32_t* n_desc;       // [2B]
   int2* match;           // [B][cap]   per sorted left feature: x = sorted right index or -1, y = dist | pass << 16
-  uint8_t* consumed_r;   // [B][cap]   right features matched in an earlier epipolar pass
+  uint8_t* pruned_l;     // [B][cap]   left features consumed by tracking or matched in an earlier epipolar pass
+  uint8_t* consumed_r;   // [B][cap]   same for the right features
   int32_t* n_out;        // [B][2]     {n_framepoints, n_matches}
   int32_t* error_flag;   // [1]        != 0: capacity exceeded
 };

@@ -120,6 +120,9 @@ void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n) {
   b.mask = lane.mask - (size_t)2 * p0 * h->g.rows * h->g.mask_words;
   RegionTable rt;
   refresh_region_table(h, &rt);
+  // a new frame: no feature is pruned yet (IntensityFeatureMatcher::setFeatures, intensity_feature_matcher.cpp:48-70)
+  cudaMemsetAsync(h->b.pruned_l + (size_t)p0 * h->g.cap, 0, (size_t)n * h->g.cap, lane.stream);
+  cudaMemsetAsync(h->b.consumed_r + (size_t)p0 * h->g.cap, 0, (size_t)n * h->g.cap, lane.stream);
   mark(h, lane, kEvFast0);
   launch_fast(h->g, rt, b, 2 * p0, 2 * n, lane.stream);
   mark(h, lane, kEvFast1);
@@ -413,6 +416,7 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
   dalloc((void**)&b.desc, I * g.cap * kDescBytes);
   dalloc((void**)&b.n_desc, I * sizeof(int32_t));
   dalloc((void**)&b.match, B * g.cap * sizeof(int2));
+  dalloc((void**)&b.pruned_l, B * g.cap);
   dalloc((void**)&b.consumed_r, B * g.cap);
   dalloc((void**)&b.n_out, B * 2 * sizeof(int32_t));
   dalloc((void**)&b.error_flag, sizeof(int32_t));
@@ -458,7 +462,7 @@ int vslam_fpg_destroy(vslam_fpg* h) {
   cudaDeviceSynchronize();
   Buffers& b = h->b;
   cudaFree(b.image); cudaFree(b.raw_count); cudaFree(b.row_ptr); cudaFree(b.kp_xy); cudaFree(b.kp_score);
-  cudaFree(b.desc); cudaFree(b.n_desc); cudaFree(b.match); cudaFree(b.consumed_r); cudaFree(b.n_out);
+  cudaFree(b.desc); cudaFree(b.n_desc); cudaFree(b.match); cudaFree(b.pruned_l); cudaFree(b.consumed_r); cudaFree(b.n_out);
   cudaFree(b.error_flag); cudaFree(h->d_out); cudaFree(h->d_matches); cudaFree(h->d_n_matches); cudaFree(h->d_tracked);
   for (auto& l : h->lanes) {
     cudaFree(l.blurred);
@@ -612,6 +616,28 @@ int vslam_fpg_compute(vslam_fpg* h, const vslam_tracked_point* tracked, int32_t 
   if (n && !out) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null output");
   if (n) CUDA_TRY(cudaMemcpy(out, src, sizeof(FramePointRecord) * n, cudaMemcpyDeviceToHost));
   return remap_records(h, 0, out, n);
+}
+
+int vslam_fpg_set_remaining_features(vslam_fpg* h, int side, const vslam_keypoint* remaining, int32_t n) {
+  if (!h || (n > 0 && !remaining) || n < 0) return fail(VSLAM_ERR_INVALID_ARGUMENT, "bad arguments");
+  if (side != 0 && side != 1) return fail(VSLAM_ERR_INVALID_ARGUMENT, "side must be 0 or 1");
+  if (!h->initialized || h->last_pairs != 1) return fail(VSLAM_ERR_STATE, "set_remaining_features without initialize");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int total = h->h_n_desc[side];
+  std::vector<uint32_t> xy;
+  int rc = fetch_xy(h, side, total, xy);
+  if (rc) return rc;
+  std::vector<uint8_t> flags(std::max(total, 1), 1);   // 1 = pruned
+  for (int i = 0; i < n; ++i) {
+    const uint32_t key = ((uint32_t)(int)remaining[i].y << 16) | (uint32_t)(int)remaining[i].x;   // row/col = trunc(pt)
+    const auto it = std::lower_bound(xy.begin(), xy.end(), key);   // the device order is ascending (row, col)
+    if (it == xy.end() || *it != key)
+      return fail(VSLAM_ERR_INVALID_ARGUMENT, "remaining feature (%g, %g) is not a feature of this frame", remaining[i].x, remaining[i].y);
+    flags[it - xy.begin()] = 0;
+  }
+  uint8_t* dst = side == 0 ? h->b.pruned_l : h->b.consumed_r;
+  if (total) CUDA_TRY(cudaMemcpy(dst, flags.data(), total, cudaMemcpyHostToDevice));
+  return VSLAM_OK;
 }
 
 int vslam_fpg_get_matches(vslam_fpg* h, vslam_framepoint* out, int32_t capacity, int32_t* n_out) {

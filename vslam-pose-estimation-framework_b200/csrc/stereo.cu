@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(256) match_kernel(Geometry g, StereoParams sp,
                                                     const uint32_t* __restrict__ kp_xy,
                                                     const uint8_t* __restrict__ desc,
                                                     const int32_t* __restrict__ n_desc, int2* __restrict__ match,
-                                                    uint8_t* __restrict__ consumed_r, int pass, int offset) {
+                                                    uint8_t* __restrict__ pruned_l, uint8_t* __restrict__ consumed_r,
+                                                    int pass, int offset) {
   const int pair = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -57,18 +58,19 @@ __global__ void __launch_bounds__(256) match_kernel(Geometry g, StereoParams sp,
   const uint4* dl = reinterpret_cast<const uint4*>(desc + (size_t)il * g.cap * kDescBytes);
   const uint4* dr = reinterpret_cast<const uint4*>(desc + (size_t)ir * g.cap * kDescBytes);
   int2* m = match + (size_t)pair * g.cap;
+  uint8_t* gone = pruned_l + (size_t)pair * g.cap;
   uint8_t* used = consumed_r + (size_t)pair * g.cap;
 
   int cursor = rb;
   for (int i = lb; i < le; ++i) {
-    if (pass > 0 && m[i].x >= 0) continue;   // pruned after an earlier pass
+    if (gone[i]) continue;   // pruned: consumed by track() or matched in an earlier pass
     const int col_l = (int)(xyl[i] & 0xffffu);
     const uint4 a0 = dl[2 * i], a1 = dl[2 * i + 1];
     unsigned best = 0xffffffffu;
     for (int s = cursor + lane; s < re; s += 32) {
       const int col_r = (int)(xyr[s] & 0xffffu);
       if (col_l - col_r < 0) break;            // :333 (columns ascend, so the lane's later candidates fail too)
-      if (pass > 0 && used[s]) continue;
+      if (used[s]) continue;
       const int d = popc256(a0, a1, dr[2 * s], dr[2 * s + 1]);
       const unsigned key = ((unsigned)d << 16) | (unsigned)(s - rb);
       best = min(best, key);                   // strict '<' of :342 == lowest index among equal distances
@@ -82,6 +84,7 @@ __global__ void __launch_bounds__(256) match_kernel(Geometry g, StereoParams sp,
     if ((double)(col_l - col_r) < sp.min_disparity) continue;                // :358-361, cursor NOT advanced
     if (lane == 0) {
       m[i] = make_int2(s, d | (pass << 16));
+      gone[i] = 1;
       used[s] = 1;
     }
     cursor = s + 1;                                                          // :414
@@ -271,16 +274,14 @@ __global__ void __launch_bounds__(256) emit_matches_kernel(Geometry g, StereoPar
 
 void launch_match(const Geometry& g, const StereoParams& sp, const Buffers& b, int first_pair, int n_pairs, int pass,
                   int epipolar_offset, cudaStream_t stream) {
-  if (pass == 0) {
+  if (pass == 0)
     cudaMemsetAsync(b.match + (size_t)first_pair * g.cap, 0xff, sizeof(int2) * (size_t)g.cap * n_pairs, stream);
-    cudaMemsetAsync(b.consumed_r + (size_t)first_pair * g.cap, 0, (size_t)g.cap * n_pairs, stream);
-  }
   dim3 grid((g.rows + 7) / 8, n_pairs);
   match_kernel<<<grid, 256, 0, stream>>>(g, sp, b.row_ptr + (size_t)2 * first_pair * (g.rows + 1),
                                          b.kp_xy + (size_t)2 * first_pair * g.cap,
                                          b.desc + (size_t)2 * first_pair * g.cap * kDescBytes, b.n_desc + 2 * first_pair,
-                                         b.match + (size_t)first_pair * g.cap, b.consumed_r + (size_t)first_pair * g.cap,
-                                         pass, epipolar_offset);
+                                         b.match + (size_t)first_pair * g.cap, b.pruned_l + (size_t)first_pair * g.cap,
+                                         b.consumed_r + (size_t)first_pair * g.cap, pass, epipolar_offset);
 }
 
 void launch_select(const Geometry& g, const StereoParams& sp, const Buffers& b, int first_pair, int n_pairs,
