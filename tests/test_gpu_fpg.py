@@ -113,6 +113,9 @@ def test_tracked_points_preload_bins():
     tracked["row"][-2:], tracked["col"][-2:] = (100, 200), (500, 900)
     tracked["disparity"][-2:], tracked["distance"][-2:] = (1000.0, 0.5), (0.0, 300.0)
     o = _oracle(cfg, cam, left, right, False, tracked=tracked)
+    gen.close()
+    gen = api.StereoFramePointGenerator(cfg, cam)     # compute() consumes the matched features, like the reference
+    gen.initialize(left, right, False)
     fps = gen.compute(tracked)
     w = o.winners
     assert len(fps) == len(w) and (w < 0).sum() >= 1
