@@ -14,13 +14,13 @@ namespace vslam {
 namespace {
 
 constexpr int TW = 128;            // output tile width  (image-aligned: 128 B = 4 mask words)
-constexpr int TH = 16;             // output tile height
+constexpr int TH = 30;             // output tile height; TH + 2 = 32 pre-test rows = 4 per warp
 constexpr int HX = 16;             // smem halo in x (only 4 needed; 16 keeps uint4 loads aligned)
 constexpr int SW = TW + 2 * HX;    // 160
-constexpr int SH = TH + 8;         // 24 : 3 (ring) + 1 (NMS) on both sides
+constexpr int SH = TH + 8;         // 38 : 3 (ring) + 1 (NMS) on both sides
 constexpr int CW = TW + 2;         // score tile width (NMS halo 1)
-constexpr int CH = TH + 2;
-constexpr int CPITCH = 144;          // multiple of 16 (the score tile is cleared with uint4 stores)
+constexpr int CH = TH + 2;         // 32
+constexpr int CPITCH = 144;        // multiple of 16 (the score tile is cleared with uint4 stores)
 
 // true iff the 16-bit circular mask m has >= 9 contiguous set bits
 __device__ __forceinline__ bool arc9(unsigned m) {
@@ -83,23 +83,47 @@ __device__ __forceinline__ int fast_score_at(Ptr p, int pitch, int t) {
   return corner_score(d);
 }
 
+// max(A, -B) of cornerScore<16> with packed 16-bit lanes: lane lo carries d = v - ring, lane hi carries -d, so one
+// VIMNMX3.S16x2 chain yields both "max over 9-arcs of min(d)" (lo) and "max over 9-arcs of min(-d)" = -min-max (hi).
+// The pixel is a FAST corner at threshold t iff the result is > t; its OpenCV score is the result - 1.
+__device__ __forceinline__ int arc_strength(const uint8_t* p) {
+  const int v = p[0];
+  unsigned P[16];
+#define F(k, dx, dy)                                            \
+  {                                                             \
+    const int r = p[(dy) * SW + (dx)];                          \
+    P[k] = __byte_perm((unsigned)(v - r), (unsigned)(r - v), 0x5410); \
+  }
+  VSLAM_RING(F)
+#undef F
+  unsigned m3[16], m9[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) m3[i] = __vimin3_s16x2(P[i], P[(i + 1) & 15], P[(i + 2) & 15]);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) m9[i] = __vimin3_s16x2(m3[i], m3[(i + 3) & 15], m3[(i + 6) & 15]);
+  unsigned g[6];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) g[i] = __vimax3_s16x2(m9[3 * i], m9[3 * i + 1], m9[3 * i + 2]);
+  g[5] = m9[15];
+  const unsigned m = __vmaxs2(__vimax3_s16x2(g[0], g[1], g[2]), __vimax3_s16x2(g[3], g[4], g[5]));
+  return max((int)(short)(m & 0xffffu), (int)(short)(m >> 16));
+}
+
 // |d| > t per byte lane (t <= 127): bit 7 of each byte of the result.  VABSDIFF4 is the one native byte-SIMD op.
 __device__ __forceinline__ uint32_t absdiff_gt(uint32_t ring, uint32_t center, uint32_t c127_minus_t) {
   const uint32_t ad = __vabsdiffu4(ring, center);
   return (((ad & 0x7f7f7f7fu) + c127_minus_t) | ad) & 0x80808080u;
 }
 
-// K1.  Work-efficient FAST: the 16-pixel ring test and the corner score are only evaluated where a cheap necessary
-// condition holds, with two in-CTA compactions so that every phase runs on dense lists:
+// K1.  Work-efficient FAST: the 16-pixel ring is only evaluated where a cheap necessary condition holds, with an
+// in-CTA compaction so that the expensive phase runs on a dense list:
 //   phase 1  all pixels, 4 per thread, byte-SIMD: every 9-arc contains two ADJACENT compass points (N,E,S,W), so a
-//            corner needs (|dN|>t or |dS|>t) and (|dE|>t or |dW|>t)            -> candidate list
-//   phase 2  candidates: exact 9-of-16 bright/dark arc test                    -> corner list
-//   phase 3  corners: cornerScore<16>                                           -> score tile (zero elsewhere)
-//   phase 4  corners inside the tile: strict 3x3 non-maximum suppression        -> keypoint bit mask
+//            corner needs (|dN|>t or |dS|>t) and (|dE|>t or |dW|>t)  (~14 % pass) -> ballot-compacted candidate list
+//   phase 2  candidates: packed arc minima -> corner decision AND cornerScore<16> -> score tile + corner list
+//   phase 3  corners inside the tile: strict 3x3 non-maximum suppression          -> keypoint bit mask
 __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable rt, const uint8_t* __restrict__ image,
                                                        uint32_t* __restrict__ mask, int32_t* __restrict__ raw_count,
                                                        int single_region) {
-  constexpr int WPR = 34;   // words per pretest row: image x in [x0 - 4, x0 + 132)
   __shared__ __align__(16) uint8_t s_img[SH][SW];
   __shared__ __align__(16) uint8_t s_score[CH][CPITCH];
   __shared__ uint16_t s_cand[CH * CW];
@@ -107,7 +131,7 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable r
   __shared__ uint32_t s_mask[TH][4];
   __shared__ int s_ncand, s_ncorner;
 
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int img = blockIdx.z / g.n_regions;
   const int reg = blockIdx.z - img * g.n_regions;
   const Region R = rt.r[reg];
@@ -128,7 +152,7 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable r
     return;
   }
 
-  // ---- phase 0: stage the tile (+halo) in shared memory: 24 rows x 10 uint4, coalesced 16 B loads; clear state
+  // ---- phase 0: stage the tile (+halo) in shared memory: 38 rows x 10 uint4, coalesced 16 B loads; clear state
   const uint8_t* base = image + (size_t)img * g.rows * g.pitch;
   for (int i = tid; i < SH * (SW / 16); i += 256) {
     const int r = i / (SW / 16), c = i - r * (SW / 16);
@@ -143,52 +167,58 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable r
   if (tid == 0) s_ncand = s_ncorner = 0;
   __syncthreads();
 
-  // ---- phase 1: compass pre-test on the tile + 1 px NMS halo
+  // ---- phase 1: compass pre-test on the tile + 1 px NMS halo.  Warp w owns pre-test rows w, w+8, w+16, w+24; lane l
+  // owns the aligned word at image x = x0 + 4*l (first pass: x0 .. x0+127) and, second pass, the two halo words
+  // (x0-4.. and x0+128..) of four rows at once.
   const int cx_lo = max(ax0, x0 - 1), cx_hi = min(ax1, x0 + TW);   // columns whose score is needed
   if (t <= 127) {
     const uint32_t cadd = 0x01010101u * (uint32_t)(127 - t);
-    for (int u0 = 0; u0 < CH * WPR; u0 += 256) {
-      const int u = u0 + tid;
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll 1
+    for (int it = 0; it < 5; ++it) {
+      int sy, wi;   // pre-test row, word index in [0, 34): image x = x0 - 4 + 4*wi
+      if (it < 4) {
+        sy = warp + 8 * it;
+        wi = lane + 1;
+      } else {      // halo words: lanes 0..7 -> (row warp + 8*(lane>>1), left/right)
+        sy = warp + 8 * ((lane >> 1) & 3);
+        wi = (lane & 1) ? 33 : 0;
+      }
       uint32_t m = 0;
-      int sy = 0, wi = 0;
-      if (u < CH * WPR) {
-        sy = u / WPR;
-        wi = u - sy * WPR;
-        const int iy = y0 - 1 + sy;
-        if (iy >= ay0 && iy <= ay1) {
-          const uint32_t* rc = reinterpret_cast<const uint32_t*>(&s_img[sy + 3][0]) + 3 + wi;
-          const uint32_t c = rc[0];
-          const uint32_t rn = reinterpret_cast<const uint32_t*>(&s_img[sy][0])[3 + wi];       // y - 3
-          const uint32_t rs = reinterpret_cast<const uint32_t*>(&s_img[sy + 6][0])[3 + wi];   // y + 3
-          const uint32_t re = __funnelshift_r(c, rc[1], 24);                                  // x + 3
-          const uint32_t rw = __funnelshift_r(rc[-1], c, 8);                                  // x - 3
-          m = (absdiff_gt(rn, c, cadd) | absdiff_gt(rs, c, cadd)) & (absdiff_gt(re, c, cadd) | absdiff_gt(rw, c, cadd));
-          // keep the bytes whose column lies in [cx_lo, cx_hi]
-          const int bx = x0 - 4 + 4 * wi;
-          const int lo = cx_lo - bx, hi = cx_hi - bx;
+      const int iy = y0 - 1 + sy;
+      if ((it < 4 || lane < 8) && iy >= ay0 && iy <= ay1) {
+        const uint32_t* rc = reinterpret_cast<const uint32_t*>(&s_img[sy + 3][0]) + 3 + wi;
+        const uint32_t c = rc[0];
+        const uint32_t rn = reinterpret_cast<const uint32_t*>(&s_img[sy][0])[3 + wi];       // y - 3
+        const uint32_t rs = reinterpret_cast<const uint32_t*>(&s_img[sy + 6][0])[3 + wi];   // y + 3
+        const uint32_t re = __funnelshift_r(c, rc[1], 24);                                  // x + 3
+        const uint32_t rw = __funnelshift_r(rc[-1], c, 8);                                  // x - 3
+        m = (absdiff_gt(rn, c, cadd) | absdiff_gt(rs, c, cadd)) & (absdiff_gt(re, c, cadd) | absdiff_gt(rw, c, cadd));
+        // keep the bytes whose column lies in [cx_lo, cx_hi]
+        const int bx = x0 - 4 + 4 * wi;
+        const int lo = cx_lo - bx, hi = cx_hi - bx;
+        if (lo > 0 || hi < 3) {
           uint32_t keep = 0x80808080u;
           if (lo > 0) keep = lo > 3 ? 0u : keep << (8 * lo);
           if (hi < 3) keep = hi < 0 ? 0u : keep & (0x80808080u >> (8 * (3 - hi)));
           m &= keep;
         }
       }
-      // warp-level compaction of the up-to-4 candidates per thread
-      const int n = __popc(m);
-      int inc = n;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
-      }
+      // ballot compaction, bit-plane major (the order of the list is irrelevant)
+      const unsigned b0 = __ballot_sync(0xffffffffu, m & 0x00000080u);
+      const unsigned b1 = __ballot_sync(0xffffffffu, m & 0x00008000u);
+      const unsigned b2 = __ballot_sync(0xffffffffu, m & 0x00800000u);
+      const unsigned b3 = __ballot_sync(0xffffffffu, m & 0x80000000u);
+      if ((b0 | b1 | b2 | b3) == 0u) continue;
+      const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
       int wbase = 0;
-      if (lane == 31 && inc) wbase = atomicAdd(&s_ncand, inc);
-      wbase = __shfl_sync(0xffffffffu, wbase, 31);
-      int pos = wbase + inc - n;
-      while (m) {
-        const int j = (__ffs(m) - 1) >> 3;
-        m &= m - 1;
-        s_cand[pos++] = (uint16_t)(sy * CW + 4 * wi + j - 3);
-      }
+      if (lane == 0) wbase = atomicAdd(&s_ncand, n0 + n1 + n2 + n3);
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      const int code = sy * CW + 4 * wi - 3;
+      if (m & 0x00000080u) s_cand[wbase + __popc(b0 & lt)] = (uint16_t)code;
+      if (m & 0x00008000u) s_cand[wbase + n0 + __popc(b1 & lt)] = (uint16_t)(code + 1);
+      if (m & 0x00800000u) s_cand[wbase + n0 + n1 + __popc(b2 & lt)] = (uint16_t)(code + 2);
+      if (m & 0x80000000u) s_cand[wbase + n0 + n1 + n2 + __popc(b3 & lt)] = (uint16_t)(code + 3);
     }
   } else {   // thresholds above 127 (never produced by the reference's configurations): every pixel is a candidate
     for (int i = tid; i < CH * CW; i += 256) {
@@ -199,42 +229,29 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable r
   }
   __syncthreads();
 
-  // ---- phase 2: exact segment test on the candidates
+  // ---- phase 2: exact segment test + corner score on the candidates
   const int ncand = s_ncand;
-  for (int c = tid; c < ncand; c += 256) {
-    const int i = s_cand[c];
-    const int sy = i / CW, sx = i - sy * CW;
-    const uint8_t* p = &s_img[sy + 3][sx + HX - 1];
-    const int v = p[0];
-    unsigned dark = 0, bright = 0;
-#define F(k, dx, dy)                                  \
-  {                                                   \
-    const int d = v - (int)p[(dy) * SW + (dx)];       \
-    dark |= (unsigned)(d > t) << k;                   \
-    bright |= (unsigned)(d < -t) << k;                \
-  }
-    VSLAM_RING(F)
-#undef F
-    if (arc9(dark) || arc9(bright)) s_corner[atomicAdd(&s_ncorner, 1)] = (uint16_t)i;
+  for (int c0 = 0; c0 < ncand; c0 += 256) {
+    const int c = c0 + tid;
+    int s = 0, i = 0;
+    if (c < ncand) {
+      i = s_cand[c];
+      const int sy = i / CW, sx = i - sy * CW;
+      s = arc_strength(&s_img[sy + 3][sx + HX - 1]);
+      if (s > t) s_score[sy][sx] = (uint8_t)(s - 1);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, s > t);
+    if (bal) {
+      int wbase = 0;
+      if (lane == 0) wbase = atomicAdd(&s_ncorner, __popc(bal));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (s > t) s_corner[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
+    }
   }
   __syncthreads();
 
-  // ---- phase 3: corner scores
+  // ---- phase 3: 3x3 strict non-maximum suppression of the corners inside the tile
   const int ncorner = s_ncorner;
-  for (int c = tid; c < ncorner; c += 256) {
-    const int i = s_corner[c];
-    const int sy = i / CW, sx = i - sy * CW;
-    const uint8_t* p = &s_img[sy + 3][sx + HX - 1];
-    const int v = p[0];
-    int d[16];
-#define F(k, dx, dy) d[k] = v - (int)p[(dy) * SW + (dx)];
-    VSLAM_RING(F)
-#undef F
-    s_score[sy][sx] = (uint8_t)corner_score(d);
-  }
-  __syncthreads();
-
-  // ---- phase 4: 3x3 strict non-maximum suppression of the corners inside the tile
   for (int c = tid; c < ncorner; c += 256) {
     const int i = s_corner[c];
     const int sy = i / CW, sx = i - sy * CW;
@@ -247,16 +264,18 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable r
   }
   __syncthreads();
 
-  // ---- phase 5: publish the tile's 16 x 4 mask words and the raw keypoint count
-  if (tid < 64) {
+  // ---- phase 4: publish the tile's 30 x 4 mask words and the raw keypoint count
+  if (tid < 128) {
     const int ry = tid >> 2, wx = tid & 3;
-    const uint32_t word = s_mask[ry][wx];
-    const int y = y0 + ry, wd = (x0 >> 5) + wx;
     int found = 0;
-    if (y < g.rows && wd < g.mask_words) {
-      if (single_region) mrow[(size_t)y * g.mask_words + wd] = word;
-      else if (word) atomicOr(&mrow[(size_t)y * g.mask_words + wd], word);
-      found = __popc(word);
+    if (ry < TH) {
+      const uint32_t word = s_mask[ry][wx];
+      const int y = y0 + ry, wd = (x0 >> 5) + wx;
+      if (y < g.rows && wd < g.mask_words) {
+        if (single_region) mrow[(size_t)y * g.mask_words + wd] = word;
+        else if (word) atomicOr(&mrow[(size_t)y * g.mask_words + wd], word);
+        found = __popc(word);
+      }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) found += __shfl_xor_sync(0xffffffffu, found, o);

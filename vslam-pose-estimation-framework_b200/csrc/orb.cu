@@ -6,6 +6,8 @@
 // the CPU oracle (oracle/c/vslam_oracle.c, orc_gauss7_u8):
 //   row pass   : acc = k[0]*p[-3]; acc = fma(k[i], p[i-3], acc), i = 1..6
 //   column pass: acc = k[3]*r[0];  acc = fma(k[3+j], r[+j] + r[-j], acc), j = 1..3 ; out = rint(acc)
+#include <utility>
+
 #include "kernels.cuh"
 
 namespace vslam {
@@ -17,10 +19,6 @@ constexpr int TH = 32;
 constexpr int HX = 16;
 constexpr int SW = TW + 2 * HX;   // 160
 constexpr int SH = TH + 6;        // 38
-
-__constant__ int8_t c_pattern[256 * 4] = {
-#include "orb_pattern_31.inc"
-};
 
 struct GaussKernel {
   float k[7];
@@ -121,72 +119,104 @@ __global__ void __launch_bounds__(256) blur_kernel(Geometry g, GaussKernel gk, c
   }
 }
 
-// K4.  One warp per keypoint, lane b produces descriptor byte b (tests 8b..8b+7, LSB first).
-// The 26 x 26 patch the 512 test points fall into (offsets -13..12) is staged in shared memory with coalesced
-// 32-bit loads (8 aligned words per row cover x-13..x+12 at any alignment) and the 16 byte look-ups per lane then
-// hit shared memory instead of scattering over ~26 L1 sectors each; the next keypoint's patch is prefetched into
-// registers while the current one is evaluated.
-constexpr int PR = 26;       // patch rows / columns
-constexpr int PP = 36;       // patch row pitch in shared memory (bytes): 9 words, spreads rows over banks
-constexpr int PW = 8;        // aligned words loaded per patch row
-constexpr int PL = (PR * PW + 31) / 32;   // 7 loads per lane
+// K4.  One LANE per keypoint.  A warp stages the 26-row x 32-byte patches of its 32 keypoints in shared memory
+// (coalesced 32-bit loads from the 4-byte aligned start of each row, 8 words cover x-13..x+12 at any alignment);
+// lane l then evaluates all 256 tests of keypoint l from ITS patch.  All lanes read the same pattern offset at the
+// same time and the patch stride is an odd number of words, so the 512 byte look-ups per lane are bank-conflict free
+// and their offsets are compile-time immediates; each lane stores its 32-byte descriptor as two uint4.
+constexpr int PR = 26;                    // patch rows
+constexpr int PP = 32;                    // patch row pitch (bytes): 8 aligned words
+constexpr int PSTRIDE = PR * PP + 4;      // 836 bytes = 209 words (odd): lane l's patch starts in bank 17*l mod 32
+constexpr int DWARPS = 4;                 // warps per CTA
+constexpr int DSMEM = DWARPS * 32 * PSTRIDE;
 
-__global__ void __launch_bounds__(256) describe_kernel(Geometry g, const uint8_t* __restrict__ blurred,
-                                                       const uint32_t* __restrict__ kp_xy,
-                                                       const int32_t* __restrict__ n_desc, uint8_t* __restrict__ desc) {
-  __shared__ __align__(16) uint8_t s_patch[8][PR * PP];
+struct OrbPattern {
+  int8_t v[1024];
+};
+constexpr OrbPattern kOrb = {{
+#include "orb_pattern_31.inc"
+}};
+
+// test K of the pattern as compile-time patch offsets (the table is only ever read in constant expressions)
+template <int K>
+struct OrbTest {
+  static constexpr int o0 = (kOrb.v[4 * K + 1] + 13) * PP + kOrb.v[4 * K] + 13;
+  static constexpr int o1 = (kOrb.v[4 * K + 3] + 13) * PP + kOrb.v[4 * K + 2] + 13;
+};
+
+template <int W, int... J>   // descriptor word W: tests 32W .. 32W+31, bit j of byte i = test 8i + j (LSB first)
+__device__ __forceinline__ uint32_t brief_word_impl(const uint8_t* c, std::integer_sequence<int, J...>) {
+  return (... | ((uint32_t)(c[OrbTest<32 * W + J>::o0] < c[OrbTest<32 * W + J>::o1]) << J));
+}
+
+template <int W>
+__device__ __forceinline__ uint32_t brief_word(const uint8_t* c) {
+  return brief_word_impl<W>(c, std::make_integer_sequence<int, 32>{});
+}
+
+__global__ void __launch_bounds__(DWARPS * 32) describe_kernel(Geometry g, const uint8_t* __restrict__ blurred,
+                                                                const uint32_t* __restrict__ kp_xy,
+                                                                const int32_t* __restrict__ n_desc,
+                                                                uint8_t* __restrict__ desc) {
+  extern __shared__ __align__(16) uint8_t s_patches[];
   const int img = blockIdx.y;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int warp = blockIdx.x * 8 + wib;
-  const int n_warps = gridDim.x * 8;
   const int n = n_desc[img];
-  if (warp >= n) return;
-  int o0[8], o1[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int8_t* p = &c_pattern[(lane * 8 + k) * 4];
-    o0[k] = (p[1] + 13) * PP + p[0] + 13;
-    o1[k] = (p[3] + 13) * PP + p[2] + 13;
-  }
-  int src_off[PL], dst_off[PL];   // per-lane word slots of the patch
-#pragma unroll
-  for (int t = 0; t < PL; ++t) {
-    const int idx = lane + 32 * t;
-    const int r = idx / PW, w = idx - r * PW;
-    src_off[t] = idx < PR * PW ? r * g.pitch + 4 * w : -1;
-    dst_off[t] = r * PP + 4 * w;
-  }
+  const int warp = blockIdx.x * DWARPS + wib, n_warps = gridDim.x * DWARPS;
   const uint8_t* base = blurred + (size_t)img * g.rows * g.pitch;
   const uint32_t* xy = kp_xy + (size_t)img * g.cap;
-  uint8_t* out = desc + (size_t)img * g.cap * kDescBytes;
-  uint8_t* patch = s_patch[wib];
+  uint4* out = reinterpret_cast<uint4*>(desc + (size_t)img * g.cap * kDescBytes);
+  uint8_t* mine = s_patches + (size_t)(wib * 32 + lane) * PSTRIDE;
+  uint8_t* warp_patches = s_patches + (size_t)(wib * 32) * PSTRIDE;
 
-  uint32_t regs[PL];
-  auto fetch = [&](uint32_t q) {
-    const int x = (int)(q & 0xffffu) - 13, y = (int)(q >> 16) - 13;
-    const uint8_t* p = base + (size_t)y * g.pitch + (x & ~3);
+  // staging slots of this lane inside one patch: 208 words = 6.5 per lane
+  int src_off[7], dst_off[7];
 #pragma unroll
-    for (int t = 0; t < PL; ++t)
-      if (src_off[t] >= 0) regs[t] = __ldg(reinterpret_cast<const uint32_t*>(p + src_off[t]));
-  };
-  uint32_t q = xy[warp];
-  fetch(q);
-  for (int i = warp; i < n; i += n_warps) {
+  for (int t = 0; t < 7; ++t) {
+    const int idx = lane + 32 * t;
+    src_off[t] = (idx >> 3) * g.pitch + 4 * (idx & 7);
+    dst_off[t] = (idx >> 3) * PP + 4 * (idx & 7);
+  }
+
+  for (int i0 = warp * 32; i0 < n; i0 += n_warps * 32) {
+    const int i = i0 + lane;
+    const uint32_t q = i < n ? xy[i] : 0u;
+    const int cnt = min(32, n - i0);
+    for (int j = 0; j < cnt; j += 2) {     // two keypoints per step: 14 independent loads in flight per lane
+      uint32_t r0[7], r1[7];
+      const uint32_t qa = __shfl_sync(0xffffffffu, q, j), qb = __shfl_sync(0xffffffffu, q, min(j + 1, cnt - 1));
+      const uint8_t* pa = base + (size_t)((int)(qa >> 16) - 13) * g.pitch + (((int)(qa & 0xffffu) - 13) & ~3);
+      const uint8_t* pb = base + (size_t)((int)(qb >> 16) - 13) * g.pitch + (((int)(qb & 0xffffu) - 13) & ~3);
 #pragma unroll
-    for (int t = 0; t < PL; ++t)
-      if (src_off[t] >= 0) *reinterpret_cast<uint32_t*>(patch + dst_off[t]) = regs[t];
-    __syncwarp();
-    const int shift = ((int)(q & 0xffffu) - 13) & 3;
-    const int nxt = i + n_warps;
-    if (nxt < n) {
-      q = xy[nxt];
-      fetch(q);
+      for (int t = 0; t < 7; ++t)
+        if (t < 6 || lane < 16) {
+          r0[t] = __ldg(reinterpret_cast<const uint32_t*>(pa + src_off[t]));
+          r1[t] = __ldg(reinterpret_cast<const uint32_t*>(pb + src_off[t]));
+        }
+      uint8_t* da = warp_patches + (size_t)j * PSTRIDE;
+      uint8_t* db = warp_patches + (size_t)min(j + 1, cnt - 1) * PSTRIDE;
+#pragma unroll
+      for (int t = 0; t < 7; ++t)
+        if (t < 6 || lane < 16) {
+          *reinterpret_cast<uint32_t*>(da + dst_off[t]) = r0[t];
+          *reinterpret_cast<uint32_t*>(db + dst_off[t]) = r1[t];
+        }
     }
-    const uint8_t* c = patch + shift;
-    unsigned v = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v |= (unsigned)(c[o0[k]] < c[o1[k]]) << k;
-    out[(size_t)i * kDescBytes + lane] = (uint8_t)v;
+    __syncwarp();
+    if (i < n) {
+      const uint8_t* c = mine + (((int)(q & 0xffffu) - 13) & 3);
+      uint4 lo, hi;
+      lo.x = brief_word<0>(c);
+      lo.y = brief_word<1>(c);
+      lo.z = brief_word<2>(c);
+      lo.w = brief_word<3>(c);
+      hi.x = brief_word<4>(c);
+      hi.y = brief_word<5>(c);
+      hi.z = brief_word<6>(c);
+      hi.w = brief_word<7>(c);
+      out[2 * (size_t)i] = lo;
+      out[2 * (size_t)i + 1] = hi;
+    }
     __syncwarp();
   }
 }
@@ -210,8 +240,13 @@ void launch_blur(const Geometry& g, const Buffers& b, int first_image, int n_ima
 }
 
 void launch_describe(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream) {
-  dim3 grid(n_images <= 8 ? 32 : 8, n_images);
-  describe_kernel<<<grid, 256, 0, stream>>>(g, b.blurred + (size_t)first_image * g.rows * g.pitch,
+  static bool configured = false;   // opt in to > 48 KB dynamic shared memory once per process (per device context)
+  if (!configured) {
+    cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DSMEM);
+    configured = true;
+  }
+  dim3 grid(n_images <= 8 ? 24 : 12, n_images);
+  describe_kernel<<<grid, DWARPS * 32, DSMEM, stream>>>(g, b.blurred + (size_t)first_image * g.rows * g.pitch,
                                             b.kp_xy + (size_t)first_image * g.cap, b.n_desc + first_image,
                                             b.desc + (size_t)first_image * g.cap * kDescBytes);
 }
