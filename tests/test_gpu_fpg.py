@@ -99,7 +99,9 @@ def test_sequence_threshold_controller_feedback_matches_oracle():
     gen.close()
 
 
-def test_tracked_points_preload_bins():
+@pytest.mark.parametrize("exact_in_float", [True, False])
+def test_tracked_points_preload_bins(exact_in_float):
+    """exact_in_float=False sends disparities that do not round-trip through float: the generic select kernel"""
     cfg, cam = configs.KITTI, synth.camera("kitti")
     left, right = synth.band_world_pair("kitti", 3)
     gen = api.StereoFramePointGenerator(cfg, cam)
@@ -112,6 +114,8 @@ def test_tracked_points_preload_bins():
     tracked["has_previous"][:-2] = 1
     tracked["row"][-2:], tracked["col"][-2:] = (100, 200), (500, 900)
     tracked["disparity"][-2:], tracked["distance"][-2:] = (1000.0, 0.5), (0.0, 300.0)
+    if not exact_in_float:
+        tracked["disparity"][:-2] = 0.1
     o = _oracle(cfg, cam, left, right, False, tracked=tracked)
     gen.close()
     gen = api.StereoFramePointGenerator(cfg, cam)     # compute() consumes the matched features, like the reference
@@ -320,4 +324,29 @@ def test_features_consumed_by_tracking_are_excluded_from_the_scan():
         bad = np.zeros(1, api.KEYPOINT)
         bad["x"], bad["y"] = 5, 5
         gen.set_remaining_features(0, bad)
+    gen.close()
+
+
+def test_rows_with_more_than_32_features_take_the_general_scan_path():
+    """dense texture: many image rows hold > 32 features, which leaves the register-resident fast path of match_kernel"""
+    import dataclasses
+    cam = synth.camera("kitti")
+    rng = np.random.default_rng(5)
+    canvas = rng.integers(25, 36, (cam.rows, cam.cols + 64)).astype(np.uint8)
+    for y in range(36, cam.rows - 36, 9):        # isolated bright dots every ~7 px: each one is a FAST keypoint
+        xs = np.arange(20, cam.cols + 44, 7)
+        xs = xs + rng.integers(0, 2, len(xs))
+        canvas[y, xs] = rng.integers(150, 251, len(xs))
+    left = np.ascontiguousarray(canvas[:, 8:8 + cam.cols])
+    right = np.ascontiguousarray(canvas[:, 14:14 + cam.cols])                  # 6 px disparity, ambiguous matches
+    cfg = dataclasses.replace(configs.KITTI, detector_threshold_minimum=30, detector_threshold_maximum=30)
+    gen = api.StereoFramePointGenerator(cfg, cam, max_keypoints=60000)
+    gen.initialize(left, right, True)
+    o = _oracle(cfg, cam, left, right, True)
+    per_row = np.bincount(o.kps_left["y"].astype(int))
+    assert per_row.max() > 100 and len(o.matches) > 5000
+    _check_pair(gen, o)
+    fps = gen.compute()
+    _same_points(gen.matches(), o.matches)
+    _same_points(fps, o.framepoints())
     gen.close()

@@ -208,23 +208,31 @@ __global__ void __launch_bounds__(kThreads) linearize_kernel(int n, AlignerBuffe
   }
 }
 
-// Batched form for independent stereo pairs: one CTA per pair linearises the StereoUV problem that aligns the
+// Batched form for independent stereo pairs: one WARP per pair linearises the StereoUV problem that aligns the
 // pair's new framepoints against themselves -- StereoUVAligner::initialize (:10-69) fused in: _moving =
 // cameraCoordinatesLeft, _fixed = (uL, vL, uR, vR), information = I4 (no landmark), w_t = min(max_depth/depth, 1).
-__global__ void __launch_bounds__(kThreads) linearize_pairs_kernel(const FramePointRecord* __restrict__ records,
-                                                                   int record_stride, const int32_t* __restrict__ n_out,
-                                                                   AlignerCamera cam, Pose pose, int ignore_outliers,
-                                                                   double kernel, double max_reliable_depth,
-                                                                   int inverse_depth_weight, double* __restrict__ systems,
-                                                                   double* __restrict__ errors,
-                                                                   uint8_t* __restrict__ inliers) {
-  const int pair = blockIdx.x;
+// A pair holds a few hundred points: a warp-private shuffle reduction needs no shared memory and no block barrier.
+constexpr int kPairWarps = 4;
+
+__global__ void __launch_bounds__(kPairWarps * 32) linearize_pairs_kernel(const FramePointRecord* __restrict__ records,
+                                                                          int record_stride, int n_pairs,
+                                                                          const int32_t* __restrict__ n_out,
+                                                                          AlignerCamera cam, Pose pose,
+                                                                          int ignore_outliers, double kernel,
+                                                                          double max_reliable_depth,
+                                                                          int inverse_depth_weight,
+                                                                          double* __restrict__ systems,
+                                                                          double* __restrict__ errors,
+                                                                          uint8_t* __restrict__ inliers) {
+  const int lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * kPairWarps + (threadIdx.x >> 5);
+  if (pair >= n_pairs) return;
   const int n = n_out[2 * pair];
   const FramePointRecord* rec = records + (size_t)pair * record_stride;
   double acc[kAcc];
 #pragma unroll
   for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
-  for (int u = threadIdx.x; u < n; u += kThreads) {
+  for (int u = lane; u < n; u += 32) {
     const FramePointRecord r = rec[u];
     double err = -1.0;
     uint8_t inl = 0;
@@ -238,9 +246,14 @@ __global__ void __launch_bounds__(kThreads) linearize_pairs_kernel(const FramePo
     errors[(size_t)pair * record_stride + u] = err;
     inliers[(size_t)pair * record_stride + u] = inl;
   }
-  __shared__ double s_part[kThreads / 32][kAcc];
-  const double total = block_reduce(acc, s_part);
-  if (threadIdx.x < kAcc) systems[(size_t)pair * 32 + threadIdx.x] = total;
+  double mine = 0.0;   // lane i ends up with total i
+#pragma unroll
+  for (int i = 0; i < kAcc; ++i) {
+    double v = acc[i];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == i) mine = v;
+  }
+  if (lane < kAcc) systems[(size_t)pair * 32 + lane] = mine;
 }
 
 }  // namespace
@@ -265,9 +278,9 @@ void launch_linearize_pairs(const FramePointRecord* records, int record_stride, 
                             uint8_t* inliers, cudaStream_t stream) {
   Pose pose;
   for (int i = 0; i < 12; ++i) pose.T[i] = T[i];
-  linearize_pairs_kernel<<<n_pairs, kThreads, 0, stream>>>(records, record_stride, n_out, cam, pose, ignore_outliers,
-                                                           kernel, max_reliable_depth, inverse_depth_weight, systems,
-                                                           errors, inliers);
+  linearize_pairs_kernel<<<(n_pairs + kPairWarps - 1) / kPairWarps, kPairWarps * 32, 0, stream>>>(
+      records, record_stride, n_pairs, n_out, cam, pose, ignore_outliers, kernel, max_reliable_depth,
+      inverse_depth_weight, systems, errors, inliers);
 }
 
 }  // namespace vslam

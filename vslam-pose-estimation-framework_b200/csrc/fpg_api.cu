@@ -136,7 +136,8 @@ void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n) {
 }
 
 // kernels of compute() for pairs [p0, p0+n) on one lane
-void run_match_select(vslam_fpg* h, Lane& lane, int p0, int n, const TrackedPoint* tracked, int n_tracked) {
+void run_match_select(vslam_fpg* h, Lane& lane, int p0, int n, const TrackedPoint* tracked, int n_tracked,
+                      bool generic_select = false) {
   mark(h, lane, kEvMatch0);
   for (int pass = 0; pass < h->n_passes; ++pass) {
     const int offset = pass == 0 ? 0 : ((pass & 1) ? (pass + 1) / 2 : -(pass / 2));
@@ -144,7 +145,8 @@ void run_match_select(vslam_fpg* h, Lane& lane, int p0, int n, const TrackedPoin
     ++h->launches;
   }
   mark(h, lane, kEvMatch1);
-  launch_select(h->g, h->sp, h->b, p0, n, h->n_passes, tracked, n_tracked, h->d_out, h->out_cap, lane.stream);
+  launch_select(h->g, h->sp, h->b, p0, n, h->n_passes, tracked, n_tracked, h->d_out, h->out_cap, generic_select,
+                lane.stream);
   ++h->launches;
   mark(h, lane, kEvSelect1);
 }
@@ -589,7 +591,14 @@ int vslam_fpg_compute(vslam_fpg* h, const vslam_tracked_point* tracked, int32_t 
   }
   if (n_tracked)
     CUDA_TRY(cudaMemcpyAsync(h->d_tracked, tracked, sizeof(TrackedPoint) * n_tracked, cudaMemcpyHostToDevice, lane.stream));
-  run_match_select(h, lane, 0, 1, h->d_tracked, n_tracked);
+  // the strip kernel keeps bin state in float: exact for everything the stereo path produces (disparities are float
+  // differences, distances Hamming counts); other values take the generic double-precision kernel
+  bool generic = false;
+  for (int32_t i = 0; i < n_tracked && !generic; ++i)
+    generic = (double)(float)tracked[i].disparity != tracked[i].disparity ||
+              (double)(float)tracked[i].distance != tracked[i].distance || tracked[i].distance < 0 ||
+              tracked[i].row < 0 || tracked[i].col < 0;
+  run_match_select(h, lane, 0, 1, h->d_tracked, n_tracked, generic);
   const FramePointRecord* src = h->d_out;
   if (!h->g.enable_binning) {   // :456-460 : every new point, in emission order
     launch_emit_matches(h->g, h->sp, h->b, 0, h->n_passes, h->d_matches, h->g.cap, h->d_n_matches, lane.stream);

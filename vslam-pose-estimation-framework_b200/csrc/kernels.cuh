@@ -46,7 +46,7 @@ void launch_match(const Geometry& g, const StereoParams& sp, const Buffers& b, i
                   int epipolar_offset, cudaStream_t stream);
 void launch_select(const Geometry& g, const StereoParams& sp, const Buffers& b, int first_pair, int n_pairs,
                    int n_passes, const TrackedPoint* tracked, int n_tracked, FramePointRecord* out,
-                   int out_capacity_per_pair, cudaStream_t stream);
+                   int out_capacity_per_pair, bool generic, cudaStream_t stream);
 void launch_emit_matches(const Geometry& g, const StereoParams& sp, const Buffers& b, int pair, int n_passes,
                          FramePointRecord* out, int out_capacity, int32_t* n_out, cudaStream_t stream);
 int kernels_per_match_pass();

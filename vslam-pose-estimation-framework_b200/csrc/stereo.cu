@@ -61,6 +61,56 @@ __global__ void __launch_bounds__(256) match_kernel(Geometry g, StereoParams sp,
   uint8_t* gone = pruned_l + (size_t)pair * g.cap;
   uint8_t* used = consumed_r + (size_t)pair * g.cap;
 
+  const int n_l = le - lb, n_r = re - rb;
+  if (n_l <= 32 && n_r <= 32) {
+    // Fast path (a row rarely holds more than 32 features): lane i keeps left feature lb+i, lane s keeps right feature
+    // rb+s -- column, pruned flag and the 256-bit descriptor in registers, loaded once with coalesced accesses.  The
+    // sequential walk over the left features then only shuffles: no dependent global load per feature.
+    int col_mine_l = 0, col_mine_r = 0x7fffffff;
+    bool gone_mine = true, used_mine = true;
+    uint4 l0 = make_uint4(0, 0, 0, 0), l1 = l0, r0 = l0, r1 = l0;
+    if (lane < n_l) {
+      col_mine_l = (int)(xyl[lb + lane] & 0xffffu);
+      gone_mine = gone[lb + lane] != 0;
+      l0 = dl[2 * (lb + lane)];
+      l1 = dl[2 * (lb + lane) + 1];
+    }
+    if (lane < n_r) {
+      col_mine_r = (int)(xyr[rb + lane] & 0xffffu);
+      used_mine = used[rb + lane] != 0;
+      r0 = dr[2 * (rb + lane)];
+      r1 = dr[2 * (rb + lane) + 1];
+    }
+    const unsigned live_l = __ballot_sync(0xffffffffu, !gone_mine);
+    int cursor = 0;
+    for (unsigned todo = live_l; todo;) {
+      const int i = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int col_l = __shfl_sync(0xffffffffu, col_mine_l, i);
+      uint4 a0, a1;
+      a0.x = __shfl_sync(0xffffffffu, l0.x, i); a0.y = __shfl_sync(0xffffffffu, l0.y, i);
+      a0.z = __shfl_sync(0xffffffffu, l0.z, i); a0.w = __shfl_sync(0xffffffffu, l0.w, i);
+      a1.x = __shfl_sync(0xffffffffu, l1.x, i); a1.y = __shfl_sync(0xffffffffu, l1.y, i);
+      a1.z = __shfl_sync(0xffffffffu, l1.z, i); a1.w = __shfl_sync(0xffffffffu, l1.w, i);
+      unsigned best = 0xffffffffu;
+      if (lane >= cursor && !used_mine && col_l - col_mine_r >= 0)             // :330-335 candidates of this scan
+        best = ((unsigned)popc256(a0, a1, r0, r1) << 16) | (unsigned)lane;
+      best = __reduce_min_sync(0xffffffffu, best);                             // first strict minimum (:342)
+      if (best == 0xffffffffu) continue;
+      const int d = (int)(best >> 16), s = (int)(best & 0xffffu);
+      if (!((double)d < thr)) continue;                                        // :353
+      const int col_r = __shfl_sync(0xffffffffu, col_mine_r, s);
+      if ((double)(col_l - col_r) < sp.min_disparity) continue;                // :358-361, cursor NOT advanced
+      if (lane == 0) {
+        m[lb + i] = make_int2(rb + s, d | (pass << 16));
+        gone[lb + i] = 1;
+        used[rb + s] = 1;
+      }
+      cursor = s + 1;                                                          // :414
+    }
+    return;
+  }
+
   int cursor = rb;
   for (int i = lb; i < le; ++i) {
     if (gone[i]) continue;   // pruned: consumed by track() or matched in an earlier pass
@@ -138,7 +188,8 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& tot
   return woff + inc - v;
 }
 
-// one CTA per pair; thread per bin replays the bin's candidates in emission order
+// K6, generic path (any bin count, arbitrary tracked disparities / distances in double): one CTA per pair, one thread
+// per bin replays the bin's candidates in emission order
 __global__ void __launch_bounds__(256) select_kernel(Geometry g, StereoParams sp, const int32_t* __restrict__ row_ptr,
                                                      const uint32_t* __restrict__ kp_xy,
                                                      const int32_t* __restrict__ n_desc,
@@ -235,6 +286,186 @@ __global__ void __launch_bounds__(256) select_kernel(Geometry g, StereoParams sp
   if (threadIdx.x == 0) n_out[2 * pair] = min(carry, out_cap);
 }
 
+// rint(v / bin) for non-negative integers, half to even -- exactly what std::rint(static_cast<real>(v)/bin_size)
+// yields (:149-152, :372-375): a tie needs 2*rem == bin, otherwise the quotient is >= 1/(2*bin) away from .5
+__device__ __forceinline__ int bin_of(int v, int bin) {
+  const int q = v / bin, r2 = 2 * (v - q * bin);
+  return r2 < bin ? q : (r2 > bin ? q + 1 : q + (q & 1));
+}
+
+// K6, fast path.  One CTA (16 warps) per pair, one warp per STRIP of bins (a bin row): the features whose row falls in
+// the strip are a contiguous index range of the (row, col)-sorted arrays, so the warp streams them in chunks of 32
+// with coalesced loads and replays the matched ones IN ORDER (ballot + shuffle broadcast); the lane that owns bin
+// column cb (cb mod 32) updates that bin's state in shared memory.  2.8 k feature visits per pair instead of the
+// 160 k of the thread-per-bin kernel above, and the order-dependent rule is still replayed exactly.
+// State per bin: winner (sorted left index, or -(k+1) for tracked point k, or INT32_MIN), its disparity and distance
+// as float (exact: disparities are differences of integer pixel columns / float-valued inputs, distances Hamming
+// counts; the API routes anything else to the generic kernel); distance -1 marks "occupied by a point with
+// previous()": `dist_new <= dist_cur` (:385-386) can then never hold, which is the !current->previous() test (:383).
+constexpr int kSelectWarps = 16;
+
+__global__ void __launch_bounds__(kSelectWarps * 32) select_strips_kernel(
+    Geometry g, StereoParams sp, const int32_t* __restrict__ row_ptr, const uint32_t* __restrict__ kp_xy,
+    const int32_t* __restrict__ n_desc, const int2* __restrict__ match, int n_passes,
+    const TrackedPoint* __restrict__ tracked, int n_tracked, FramePointRecord* __restrict__ out, int out_cap,
+    int32_t* __restrict__ n_out, int32_t* __restrict__ error_flag) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int n_bins = g.rows_bin * g.cols_bin;
+  int* s_win = reinterpret_cast<int*>(s_raw);
+  float* s_disp = reinterpret_cast<float*>(s_win + n_bins);
+  float* s_dist = s_disp + n_bins;
+  int* s_cnt = reinterpret_cast<int*>(s_dist + n_bins);   // [rows_bin + 1] winners per strip -> exclusive offsets
+  __shared__ int s_matches;
+
+  const int pair = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int il = 2 * pair, ir = 2 * pair + 1;
+  const int32_t* rpl = row_ptr + (size_t)il * (g.rows + 1);
+  const uint32_t* xyl = kp_xy + (size_t)il * g.cap;
+  const uint32_t* xyr = kp_xy + (size_t)ir * g.cap;
+  const int2* m = match + (size_t)pair * g.cap;
+  FramePointRecord* o = out + (size_t)pair * out_cap;
+  const int bs = g.bin_size;
+
+  for (int i = tid; i < n_bins; i += kSelectWarps * 32) s_win[i] = INT32_MIN;
+  if (tid == 0) s_matches = 0;
+  __syncthreads();
+  // :147-155 pre-load, in order (a later tracked point overwrites an earlier one in the same bin)
+  if (warp == 0) {
+    for (int k0 = 0; k0 < n_tracked; k0 += 32) {
+      const int k = k0 + lane;
+      int bin = -1;
+      float disp = 0, dist = 0;
+      if (k < n_tracked) {
+        const TrackedPoint t = tracked[k];
+        const int trb = bin_of(t.row, bs), tcb = bin_of(t.col, bs);
+        if (trb < g.rows_bin && tcb < g.cols_bin) bin = trb * g.cols_bin + tcb;   // (the reference would write out of bounds)
+        disp = (float)t.disparity;
+        dist = t.has_previous ? -1.0f : (float)t.distance;
+      }
+      for (int l = 0; l < 32 && k0 + l < n_tracked; ++l) {
+        const int b = __shfl_sync(0xffffffffu, bin, l);
+        const float dp = __shfl_sync(0xffffffffu, disp, l), dt = __shfl_sync(0xffffffffu, dist, l);
+        if (lane == 0 && b >= 0) {
+          s_win[b] = -(k0 + l + 1);
+          s_disp[b] = dp;
+          s_dist[b] = dt;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  int my_matches = 0;
+  for (int rb = warp; rb < g.rows_bin; rb += kSelectWarps) {
+    // rows of this strip: contiguous, within [rb*bs - bs/2 - 1, rb*bs + bs/2 + 1]
+    int r_lo = max(0, rb * bs - bs / 2 - 1), r_hi = min(g.rows - 1, rb * bs + bs / 2 + 1);
+    while (r_lo <= r_hi && bin_of(r_lo, bs) != rb) ++r_lo;
+    while (r_hi >= r_lo && bin_of(r_hi, bs) != rb) --r_hi;
+    int winners = 0;
+    if (r_lo <= r_hi) {
+      const int f_lo = rpl[r_lo], f_hi = rpl[r_hi + 1];
+      int* win = s_win + rb * g.cols_bin;
+      float* wdisp = s_disp + rb * g.cols_bin;
+      float* wdist = s_dist + rb * g.cols_bin;
+      for (int pass = 0; pass < n_passes; ++pass) {
+        for (int f0 = f_lo; f0 < f_hi; f0 += 32) {
+          const int i = f0 + lane;
+          int cb = 0;
+          float disp = 0, dist = 0;
+          bool cand = false;
+          if (i < f_hi) {
+            const int2 mm = m[i];
+            if (mm.x >= 0 && (mm.y >> 16) == pass) {
+              cand = true;
+              const int col = (int)(xyl[i] & 0xffffu);
+              cb = bin_of(col, bs);
+              disp = (float)(col - (int)(xyr[mm.x] & 0xffffu));   // frame_point.cpp:19
+              dist = (float)(mm.y & 0xffff);
+            }
+          }
+          unsigned todo = __ballot_sync(0xffffffffu, cand);
+          if (pass == 0) my_matches += __popc(todo);
+          while (todo) {                       // replay in emission order (ascending i)
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int b = __shfl_sync(0xffffffffu, cb, l);
+            const float dp = __shfl_sync(0xffffffffu, disp, l), dt = __shfl_sync(0xffffffffu, dist, l);
+            if (lane == (b & 31)) {            // the owner of bin column b
+              const int cur = win[b];
+              if (cur == INT32_MIN || (dp > wdisp[b] && dt <= wdist[b])) {   // :390-393 / :378-389
+                win[b] = f0 + l;
+                wdisp[b] = dp;
+                wdist[b] = dt;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      // :443 only points without previous() are appended; tracked survivors without previous() are reported
+      for (int c0 = 0; c0 < g.cols_bin; c0 += 32) {
+        const int c = c0 + lane;
+        bool on = false;
+        if (c < g.cols_bin) {
+          const int w = win[c];
+          on = w != INT32_MIN && !(w < 0 && wdist[c] < 0.0f);
+          if (!on) win[c] = INT32_MIN;
+        }
+        winners += __popc(__ballot_sync(0xffffffffu, on));
+      }
+    }
+    if (lane == 0) s_cnt[rb] = winners;
+  }
+  if (lane == 0 && my_matches) atomicAdd(&s_matches, my_matches);
+  __syncthreads();
+  if (warp == 0) {   // exclusive scan of the strip counts
+    int carry = 0;
+    for (int r0 = 0; r0 < g.rows_bin; r0 += 32) {
+      const int r = r0 + lane;
+      const int v = r < g.rows_bin ? s_cnt[r] : 0;
+      int inc = v;
+      for (int off = 1; off < 32; off <<= 1) {
+        const int nb = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += nb;
+      }
+      if (r < g.rows_bin) s_cnt[r] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) {
+      s_cnt[g.rows_bin] = carry;
+      n_out[2 * pair] = min(carry, out_cap);
+      n_out[2 * pair + 1] = s_matches;
+      if (carry > out_cap) atomicExch(error_flag, 2);
+    }
+  }
+  __syncthreads();
+  // :435-455 gather the winners row-major over the bin grid
+  for (int rb = warp; rb < g.rows_bin; rb += kSelectWarps) {
+    int pos = s_cnt[rb];
+    const int* win = s_win + rb * g.cols_bin;
+    for (int c0 = 0; c0 < g.cols_bin; c0 += 32) {
+      const int c = c0 + lane;
+      const int w = c < g.cols_bin ? win[c] : INT32_MIN;
+      const bool on = w != INT32_MIN;
+      const unsigned bal = __ballot_sync(0xffffffffu, on);
+      const int p = pos + __popc(bal & ((1u << lane) - 1u));
+      if (on && p < out_cap) {
+        if (w >= 0) {
+          const int2 mm = m[w];
+          write_record(sp, &o[p], w, mm.x, mm.y & 0xffff, pass_to_offset(mm.y >> 16), xyl[w], xyr[mm.x]);
+        } else {
+          FramePointRecord r = {};
+          r.index_left = w;
+          r.index_right = -1;
+          o[p] = r;
+        }
+      }
+      pos += __popc(bal);
+    }
+  }
+}
+
 // all new matches of one pair in emission order (pass, row, col): framepoints_new of :163,397, and the output
 // of compute() when binning is disabled (:456-460)
 __global__ void __launch_bounds__(256) emit_matches_kernel(Geometry g, StereoParams sp,
@@ -286,7 +517,21 @@ void launch_match(const Geometry& g, const StereoParams& sp, const Buffers& b, i
 
 void launch_select(const Geometry& g, const StereoParams& sp, const Buffers& b, int first_pair, int n_pairs,
                    int n_passes, const TrackedPoint* tracked, int n_tracked, FramePointRecord* out,
-                   int out_capacity_per_pair, cudaStream_t stream) {
+                   int out_capacity_per_pair, bool generic, cudaStream_t stream) {
+  // shared state of the strip kernel: 12 B per bin + one counter per bin row
+  const size_t smem = (size_t)g.rows_bin * g.cols_bin * 12 + (size_t)(g.rows_bin + 1) * 4;
+  if (!generic && smem <= 160 * 1024) {
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      cudaFuncSetAttribute(select_strips_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured = smem;
+    }
+    select_strips_kernel<<<n_pairs, kSelectWarps * 32, smem, stream>>>(
+        g, sp, b.row_ptr + (size_t)2 * first_pair * (g.rows + 1), b.kp_xy + (size_t)2 * first_pair * g.cap,
+        b.n_desc + 2 * first_pair, b.match + (size_t)first_pair * g.cap, n_passes, tracked, n_tracked,
+        out + (size_t)first_pair * out_capacity_per_pair, out_capacity_per_pair, b.n_out + 2 * first_pair, b.error_flag);
+    return;
+  }
   select_kernel<<<n_pairs, 256, 0, stream>>>(g, sp, b.row_ptr + (size_t)2 * first_pair * (g.rows + 1),
                                              b.kp_xy + (size_t)2 * first_pair * g.cap, b.n_desc + 2 * first_pair,
                                              b.match + (size_t)first_pair * g.cap, n_passes, tracked, n_tracked,
