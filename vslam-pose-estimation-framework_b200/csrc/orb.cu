@@ -15,10 +15,10 @@ namespace vslam {
 namespace {
 
 constexpr int TW = 128;
-constexpr int TH = 32;
+constexpr int TH = 64;
 constexpr int HX = 16;
 constexpr int SW = TW + 2 * HX;   // 160
-constexpr int SH = TH + 6;        // 38
+constexpr int SH = TH + 6;        // 70
 
 struct GaussKernel {
   float k[7];
@@ -35,8 +35,8 @@ __device__ __forceinline__ float byte_to_float(uint32_t word, int j) {
   return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u | (unsigned)j)) - 8388608.0f;
 }
 
-// K3.  Tile 128 x 32 outputs.  Row pass: one thread per 4 adjacent outputs (10 input bytes converted once, 28 FMA);
-// column pass: one thread per 4 columns x 4 rows (10 float4 shared-memory loads, packed 32-bit stores).
+// K3.  Tile 128 x 64 outputs.  Row pass: one thread per 4 adjacent outputs (10 input bytes converted once, 28 FMA);
+// column pass: one thread per 4 columns x 8 rows (14 float4 shared-memory loads, packed 32-bit stores).
 __global__ void __launch_bounds__(256) blur_kernel(Geometry g, GaussKernel gk, const uint8_t* __restrict__ image,
                                                    uint8_t* __restrict__ blurred) {
   __shared__ __align__(16) uint8_t s_in[SH][SW];
@@ -46,22 +46,32 @@ __global__ void __launch_bounds__(256) blur_kernel(Geometry g, GaussKernel gk, c
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const uint8_t* base = image + (size_t)img * g.rows * g.pitch;
 
+  // ---- stage rows y0-3 .. y0+TH+2 (BORDER_REFLECT_101 in y) with aligned 16 B loads wherever the chunk lies inside
+  // the pitched row; the few columns outside the image are patched afterwards from shared memory itself
   for (int i = tid; i < SH * (SW / 16); i += 256) {
     const int r = i / (SW / 16), c = i - r * (SW / 16);
-    const int gy = reflect101(y0 - 3 + r, g.rows);
+    int gy = y0 - 3 + r;
+    gy = gy < 0 ? -gy : gy;
+    gy = gy >= g.rows ? 2 * g.rows - 2 - gy : gy;
+    gy = min(max(gy, 0), g.rows - 1);            // images shorter than the reflection: value unused by any kept keypoint
     const int gx = x0 - HX + c * 16;
-    const uint8_t* row = base + (size_t)gy * g.pitch;
-    if (gx >= 0 && gx + 16 <= g.cols) {
-      *reinterpret_cast<uint4*>(&s_in[r][c * 16]) = __ldg(reinterpret_cast<const uint4*>(row + gx));
-    } else {
-      for (int j = 0; j < 16; ++j) {
-        const int x = gx + j;
-        // only columns within the 3 px filter support of this tile are ever read
-        s_in[r][c * 16 + j] = (x >= x0 - 3 && x < x0 + TW + 3) ? row[reflect101(x, g.cols)] : 0;
-      }
-    }
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (gx >= 0 && gx + 16 <= g.pitch) v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)gy * g.pitch + gx));
+    *reinterpret_cast<uint4*>(&s_in[r][c * 16]) = v;
   }
   __syncthreads();
+  if (x0 == 0 || x0 + TW + 3 > g.cols) {         // BORDER_REFLECT_101 in x: columns -3..-1 and cols..cols+2
+    for (int i = tid; i < SH * 6; i += 256) {
+      const int r = i / 6, j = i - r * 6;
+      if (j < 3) {
+        if (x0 == 0) s_in[r][HX - 1 - j] = s_in[r][HX + 1 + j];
+      } else {
+        const int x = g.cols + (j - 3), src = g.cols - 2 - (j - 3);
+        if (x >= x0 && x < x0 + TW + 3 && src >= x0 - HX && src >= 0) s_in[r][x - x0 + HX] = s_in[r][src - x0 + HX];
+      }
+    }
+    __syncthreads();
+  }
 
   // ---- row pass: outputs x = xq .. xq+3 need inputs xq-3 .. xq+6, all inside three aligned words
   for (int i = tid; i < SH * (TW / 4); i += 256) {
@@ -90,17 +100,20 @@ __global__ void __launch_bounds__(256) blur_kernel(Geometry g, GaussKernel gk, c
   }
   __syncthreads();
 
-  // ---- column pass + round half-to-even to u8 (adding 1.5 * 2^23 leaves rint(acc) in the low mantissa bits)
+  // ---- column pass + round half-to-even to u8: adding 1.5 * 2^23 leaves rint(acc) in the low mantissa byte.
+  // acc is a convex combination (weights sum to 1 within 1e-7) of values in [0, 255]: it cannot leave [0, 255.0001],
+  // so cv::saturate_cast's clamp is a no-op and is not evaluated.
   uint8_t* outp = blurred + (size_t)img * g.rows * g.pitch;
   {
-    const int xq = (tid & 31) * 4, yb = (tid >> 5) * 4;
-    float4 t[10];
+    constexpr int RPT = TH / 8;   // rows per thread
+    const int xq = (tid & 31) * 4, yb = (tid >> 5) * RPT;
+    float4 t[RPT + 6];
 #pragma unroll
-    for (int r = 0; r < 10; ++r) t[r] = *reinterpret_cast<const float4*>(&s_tmp[yb + r][xq]);
+    for (int r = 0; r < RPT + 6; ++r) t[r] = *reinterpret_cast<const float4*>(&s_tmp[yb + r][xq]);
 #pragma unroll
-    for (int y = 0; y < 4; ++y) {
+    for (int y = 0; y < RPT; ++y) {
       if (y0 + yb + y >= g.rows || x0 + xq >= g.pitch) continue;
-      uint32_t packed = 0;
+      uint32_t b[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float* c = reinterpret_cast<const float*>(&t[y + 3]) + j;
@@ -111,9 +124,9 @@ __global__ void __launch_bounds__(256) blur_kernel(Geometry g, GaussKernel gk, c
           const float dn = reinterpret_cast<const float*>(&t[y + 3 - d])[j];
           acc = __fmaf_rn(gk.k[3 + d], __fadd_rn(up, dn), acc);
         }
-        acc = fminf(fmaxf(acc, 0.0f), 255.0f);
-        packed |= (__float_as_uint(__fadd_rn(acc, 12582912.0f)) & 0xffu) << (8 * j);
+        b[j] = __float_as_uint(__fadd_rn(acc, 12582912.0f));
       }
+      const uint32_t packed = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
       *reinterpret_cast<uint32_t*>(outp + (size_t)(y0 + yb + y) * g.pitch + x0 + xq) = packed;
     }
   }
