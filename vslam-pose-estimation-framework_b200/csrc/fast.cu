@@ -115,21 +115,60 @@ __device__ __forceinline__ uint32_t absdiff_gt(uint32_t ring, uint32_t center, u
   return (((ad & 0x7f7f7f7fu) + c127_minus_t) | ad) & 0x80808080u;
 }
 
-// K1.  Work-efficient FAST: the 16-pixel ring is only evaluated where a cheap necessary condition holds, with an
-// in-CTA compaction so that the expensive phase runs on a dense list:
+// K1.  Work-efficient FAST: the 16-pixel ring is only evaluated where a cheap necessary condition holds.  After the
+// tile is staged, every warp runs a PRIVATE pipeline over its 4 pre-test rows (no atomics, no block barrier between
+// the two expensive phases):
 //   phase 1  all pixels, 4 per thread, byte-SIMD: every 9-arc contains two ADJACENT compass points (N,E,S,W), so a
 //            corner needs (|dN|>t or |dS|>t) and (|dE|>t or |dW|>t)  (~14 % pass) -> ballot-compacted candidate list
-//   phase 2  candidates: packed arc minima -> corner decision AND cornerScore<16> -> score tile + corner list
-//   phase 3  corners inside the tile: strict 3x3 non-maximum suppression          -> keypoint bit mask
+//   phase 2  candidates: packed arc minima -> corner decision AND cornerScore<16> -> score tile; the list is
+//            compacted in place to the corners inside the tile
+//   phase 3  (after one block barrier) strict 3x3 non-maximum suppression of the listed corners -> keypoint bit mask
+constexpr int kListCap = 4 * CW + 8;   // candidates of one warp: 4 rows x 130 columns
+
+template <bool INTERIOR>
+__device__ __forceinline__ uint32_t compass_pretest(const uint8_t (*s_img)[SW], int sy, int wi, uint32_t cadd, int x0,
+                                                    int y0, int ay0, int ay1, int cx_lo, int cx_hi) {
+  const uint32_t* rc = reinterpret_cast<const uint32_t*>(&s_img[sy + 3][0]) + 3 + wi;
+  const uint32_t c = rc[0];
+  const uint32_t rn = rc[-3 * (SW / 4)];                   // y - 3
+  const uint32_t rs = rc[3 * (SW / 4)];                    // y + 3
+  const uint32_t re = __funnelshift_r(c, rc[1], 24);       // x + 3
+  const uint32_t rw = __funnelshift_r(rc[-1], c, 8);       // x - 3
+  uint32_t m = (absdiff_gt(rn, c, cadd) | absdiff_gt(rs, c, cadd)) & (absdiff_gt(re, c, cadd) | absdiff_gt(rw, c, cadd));
+  if (!INTERIOR) {   // tiles touching the border of the region: drop rows / columns outside the keypoint area
+    const int iy = y0 - 1 + sy;
+    if (iy < ay0 || iy > ay1) return 0u;
+    const int bx = x0 - 4 + 4 * wi;
+    const int lo = cx_lo - bx, hi = cx_hi - bx;
+    uint32_t keep = 0x80808080u;
+    if (lo > 0) keep = lo > 3 ? 0u : keep << (8 * lo);
+    if (hi < 3) keep = hi < 0 ? 0u : keep & (0x80808080u >> (8 * (3 - hi)));
+    m &= keep;
+  }
+  return m;
+}
+
+// append the up-to-4 candidates of every lane to the warp's list (bit-plane major; the order is irrelevant)
+__device__ __forceinline__ void append_candidates(uint16_t* list, int& n, uint32_t m, int code, uint32_t lt) {
+  const unsigned b0 = __ballot_sync(0xffffffffu, m & 0x00000080u);
+  const unsigned b1 = __ballot_sync(0xffffffffu, m & 0x00008000u);
+  const unsigned b2 = __ballot_sync(0xffffffffu, m & 0x00800000u);
+  const unsigned b3 = __ballot_sync(0xffffffffu, m & 0x80000000u);
+  const int p1 = n + __popc(b0), p2 = p1 + __popc(b1), p3 = p2 + __popc(b2);
+  if (m & 0x00000080u) list[n + __popc(b0 & lt)] = (uint16_t)code;
+  if (m & 0x00008000u) list[p1 + __popc(b1 & lt)] = (uint16_t)(code + 1);
+  if (m & 0x00800000u) list[p2 + __popc(b2 & lt)] = (uint16_t)(code + 2);
+  if (m & 0x80000000u) list[p3 + __popc(b3 & lt)] = (uint16_t)(code + 3);
+  n = p3 + __popc(b3);
+}
+
 __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable rt, const uint8_t* __restrict__ image,
                                                        uint32_t* __restrict__ mask, int32_t* __restrict__ raw_count,
                                                        int single_region) {
   __shared__ __align__(16) uint8_t s_img[SH][SW];
   __shared__ __align__(16) uint8_t s_score[CH][CPITCH];
-  __shared__ uint16_t s_cand[CH * CW];
-  __shared__ uint16_t s_corner[CH * CW];
+  __shared__ uint16_t s_list[8][kListCap];     // position codes (sy << 8 | sx)
   __shared__ uint32_t s_mask[TH][4];
-  __shared__ int s_ncand, s_ncorner;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int img = blockIdx.z / g.n_regions;
@@ -164,98 +203,79 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable r
   }
   for (int i = tid; i < CH * CPITCH / 16; i += 256) reinterpret_cast<uint4*>(&s_score[0][0])[i] = make_uint4(0, 0, 0, 0);
   if (tid < TH * 4) (&s_mask[0][0])[tid] = 0u;
-  if (tid == 0) s_ncand = s_ncorner = 0;
   __syncthreads();
 
-  // ---- phase 1: compass pre-test on the tile + 1 px NMS halo.  Warp w owns pre-test rows w, w+8, w+16, w+24; lane l
-  // owns the aligned word at image x = x0 + 4*l (first pass: x0 .. x0+127) and, second pass, the two halo words
-  // (x0-4.. and x0+128..) of four rows at once.
+  // ---- phase 1 (warp-private): compass pre-test on the tile + 1 px NMS halo.  Warp w owns pre-test rows w, w+8,
+  // w+16, w+24; lane l owns the aligned word at image x = x0 + 4*l, and lanes 0..7 also the two halo words
+  // (x0-4.. and x0+128..) of the warp's four rows.
   const int cx_lo = max(ax0, x0 - 1), cx_hi = min(ax1, x0 + TW);   // columns whose score is needed
+  const bool interior = cx_lo == x0 - 1 && cx_hi == x0 + TW && y0 - 1 >= ay0 && y0 + TH <= ay1;
+  uint16_t* list = s_list[warp];
+  const uint32_t lt = (1u << lane) - 1u;
+  int ncand = 0;
   if (t <= 127) {
     const uint32_t cadd = 0x01010101u * (uint32_t)(127 - t);
-    const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll 1
-    for (int it = 0; it < 5; ++it) {
-      int sy, wi;   // pre-test row, word index in [0, 34): image x = x0 - 4 + 4*wi
-      if (it < 4) {
-        sy = warp + 8 * it;
-        wi = lane + 1;
-      } else {      // halo words: lanes 0..7 -> (row warp + 8*(lane>>1), left/right)
-        sy = warp + 8 * ((lane >> 1) & 3);
-        wi = (lane & 1) ? 33 : 0;
+    const int hsy = warp + 8 * ((lane >> 1) & 3), hwi = (lane & 1) ? 33 : 0;   // this lane's halo word
+    if (interior) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int sy = warp + 8 * it;
+        const uint32_t m = compass_pretest<true>(s_img, sy, lane + 1, cadd, x0, y0, ay0, ay1, cx_lo, cx_hi);
+        append_candidates(list, ncand, m, (sy << 8) + 4 * lane + 1, lt);
       }
       uint32_t m = 0;
-      const int iy = y0 - 1 + sy;
-      if ((it < 4 || lane < 8) && iy >= ay0 && iy <= ay1) {
-        const uint32_t* rc = reinterpret_cast<const uint32_t*>(&s_img[sy + 3][0]) + 3 + wi;
-        const uint32_t c = rc[0];
-        const uint32_t rn = reinterpret_cast<const uint32_t*>(&s_img[sy][0])[3 + wi];       // y - 3
-        const uint32_t rs = reinterpret_cast<const uint32_t*>(&s_img[sy + 6][0])[3 + wi];   // y + 3
-        const uint32_t re = __funnelshift_r(c, rc[1], 24);                                  // x + 3
-        const uint32_t rw = __funnelshift_r(rc[-1], c, 8);                                  // x - 3
-        m = (absdiff_gt(rn, c, cadd) | absdiff_gt(rs, c, cadd)) & (absdiff_gt(re, c, cadd) | absdiff_gt(rw, c, cadd));
-        // keep the bytes whose column lies in [cx_lo, cx_hi]
-        const int bx = x0 - 4 + 4 * wi;
-        const int lo = cx_lo - bx, hi = cx_hi - bx;
-        if (lo > 0 || hi < 3) {
-          uint32_t keep = 0x80808080u;
-          if (lo > 0) keep = lo > 3 ? 0u : keep << (8 * lo);
-          if (hi < 3) keep = hi < 0 ? 0u : keep & (0x80808080u >> (8 * (3 - hi)));
-          m &= keep;
-        }
+      if (lane < 8)   // of the left halo word only x0-1 (byte 3) is needed, of the right one only x0+128 (byte 0)
+        m = compass_pretest<true>(s_img, hsy, hwi, cadd, x0, y0, ay0, ay1, cx_lo, cx_hi) & (hwi ? 0x00000080u : 0x80000000u);
+      append_candidates(list, ncand, m, (hsy << 8) + 4 * hwi - 3, lt);
+    } else {
+#pragma unroll 1
+      for (int it = 0; it < 4; ++it) {
+        const int sy = warp + 8 * it;
+        const uint32_t m = compass_pretest<false>(s_img, sy, lane + 1, cadd, x0, y0, ay0, ay1, cx_lo, cx_hi);
+        append_candidates(list, ncand, m, (sy << 8) + 4 * lane + 1, lt);
       }
-      // ballot compaction, bit-plane major (the order of the list is irrelevant)
-      const unsigned b0 = __ballot_sync(0xffffffffu, m & 0x00000080u);
-      const unsigned b1 = __ballot_sync(0xffffffffu, m & 0x00008000u);
-      const unsigned b2 = __ballot_sync(0xffffffffu, m & 0x00800000u);
-      const unsigned b3 = __ballot_sync(0xffffffffu, m & 0x80000000u);
-      if ((b0 | b1 | b2 | b3) == 0u) continue;
-      const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
-      int wbase = 0;
-      if (lane == 0) wbase = atomicAdd(&s_ncand, n0 + n1 + n2 + n3);
-      wbase = __shfl_sync(0xffffffffu, wbase, 0);
-      const int code = sy * CW + 4 * wi - 3;
-      if (m & 0x00000080u) s_cand[wbase + __popc(b0 & lt)] = (uint16_t)code;
-      if (m & 0x00008000u) s_cand[wbase + n0 + __popc(b1 & lt)] = (uint16_t)(code + 1);
-      if (m & 0x00800000u) s_cand[wbase + n0 + n1 + __popc(b2 & lt)] = (uint16_t)(code + 2);
-      if (m & 0x80000000u) s_cand[wbase + n0 + n1 + n2 + __popc(b3 & lt)] = (uint16_t)(code + 3);
+      uint32_t m = 0;
+      if (lane < 8) m = compass_pretest<false>(s_img, hsy, hwi, cadd, x0, y0, ay0, ay1, cx_lo, cx_hi);
+      append_candidates(list, ncand, m, (hsy << 8) + 4 * hwi - 3, lt);
     }
   } else {   // thresholds above 127 (never produced by the reference's configurations): every pixel is a candidate
-    for (int i = tid; i < CH * CW; i += 256) {
-      const int sy = i / CW, sx = i - sy * CW;
-      const int ix = x0 - 1 + sx, iy = y0 - 1 + sy;
-      if (ix >= cx_lo && ix <= cx_hi && iy >= ay0 && iy <= ay1) s_cand[atomicAdd(&s_ncand, 1)] = (uint16_t)i;
+    for (int it = 0; it < 4; ++it) {
+      const int sy = warp + 8 * it, iy = y0 - 1 + sy;
+      for (int sx0 = 0; sx0 < CW; sx0 += 32) {
+        const int sx = sx0 + lane, ix = x0 - 1 + sx;
+        const bool on = sx < CW && ix >= cx_lo && ix <= cx_hi && iy >= ay0 && iy <= ay1;
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        if (on) list[ncand + __popc(bal & lt)] = (uint16_t)((sy << 8) + sx);
+        ncand += __popc(bal);
+      }
     }
   }
-  __syncthreads();
+  __syncwarp();
 
-  // ---- phase 2: exact segment test + corner score on the candidates
-  const int ncand = s_ncand;
-  for (int c0 = 0; c0 < ncand; c0 += 256) {
-    const int c = c0 + tid;
-    int s = 0, i = 0;
+  // ---- phase 2 (warp-private): exact segment test + corner score; compact the list in place to in-tile corners
+  int ncorner = 0;
+  for (int c0 = 0; c0 < ncand; c0 += 32) {
+    const int c = c0 + lane;
+    int s = 0, code = 0;
     if (c < ncand) {
-      i = s_cand[c];
-      const int sy = i / CW, sx = i - sy * CW;
+      code = list[c];
+      const int sy = code >> 8, sx = code & 0xff;
       s = arc_strength(&s_img[sy + 3][sx + HX - 1]);
       if (s > t) s_score[sy][sx] = (uint8_t)(s - 1);
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, s > t);
-    if (bal) {
-      int wbase = 0;
-      if (lane == 0) wbase = atomicAdd(&s_ncorner, __popc(bal));
-      wbase = __shfl_sync(0xffffffffu, wbase, 0);
-      if (s > t) s_corner[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
-    }
+    const int sy = code >> 8, sx = code & 0xff;
+    const bool keep = s > t && sy >= 1 && sy <= TH && sx >= 1 && sx <= TW;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();                                   // every lane has read its entry of this chunk
+    if (keep) list[ncorner + __popc(bal & lt)] = (uint16_t)code;
+    ncorner += __popc(bal);
   }
-  __syncthreads();
+  __syncthreads();                                  // the score tile is complete
 
-  // ---- phase 3: 3x3 strict non-maximum suppression of the corners inside the tile
-  const int ncorner = s_ncorner;
-  for (int c = tid; c < ncorner; c += 256) {
-    const int i = s_corner[c];
-    const int sy = i / CW, sx = i - sy * CW;
-    if (sy < 1 || sy > TH || sx < 1 || sx > TW) continue;
+  // ---- phase 3 (warp-private list): 3x3 strict non-maximum suppression of the corners inside the tile
+  for (int c = lane; c < ncorner; c += 32) {
+    const int code = list[c];
+    const int sy = code >> 8, sx = code & 0xff;
     const int s = s_score[sy][sx];
     const bool kp = s > s_score[sy - 1][sx - 1] && s > s_score[sy - 1][sx] && s > s_score[sy - 1][sx + 1] &&
                     s > s_score[sy][sx - 1] && s > s_score[sy][sx + 1] && s > s_score[sy + 1][sx - 1] &&

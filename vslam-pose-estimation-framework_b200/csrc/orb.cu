@@ -157,9 +157,13 @@ struct OrbTest {
   static constexpr int o1 = (kOrb.v[4 * K + 3] + 13) * PP + kOrb.v[4 * K + 2] + 13;
 };
 
-template <int W, int... J>   // descriptor word W: tests 32W .. 32W+31, bit j of byte i = test 8i + j (LSB first)
+// descriptor word W: tests 32W .. 32W+31, bit j of byte i = test 8i + j (LSB first).  The tests are visited from
+// j = 31 down to 0 and the sign bit of t0 - t1 (set iff t0 < t1) is shifted in with one funnel shift per test.
+template <int W, int... J>
 __device__ __forceinline__ uint32_t brief_word_impl(const uint8_t* c, std::integer_sequence<int, J...>) {
-  return (... | ((uint32_t)(c[OrbTest<32 * W + J>::o0] < c[OrbTest<32 * W + J>::o1]) << J));
+  uint32_t w = 0;
+  ((w = __funnelshift_l((uint32_t)((int)c[OrbTest<32 * W + 31 - J>::o0] - (int)c[OrbTest<32 * W + 31 - J>::o1]), w, 1)), ...);
+  return w;
 }
 
 template <int W>
@@ -195,25 +199,29 @@ __global__ void __launch_bounds__(DWARPS * 32) describe_kernel(Geometry g, const
     const int i = i0 + lane;
     const uint32_t q = i < n ? xy[i] : 0u;
     const int cnt = min(32, n - i0);
-    for (int j = 0; j < cnt; j += 2) {     // two keypoints per step: 14 independent loads in flight per lane
-      uint32_t r0[7], r1[7];
-      const uint32_t qa = __shfl_sync(0xffffffffu, q, j), qb = __shfl_sync(0xffffffffu, q, min(j + 1, cnt - 1));
-      const uint8_t* pa = base + (size_t)((int)(qa >> 16) - 13) * g.pitch + (((int)(qa & 0xffffu) - 13) & ~3);
-      const uint8_t* pb = base + (size_t)((int)(qb >> 16) - 13) * g.pitch + (((int)(qb & 0xffffu) - 13) & ~3);
+    for (int j = 0; j < cnt; j += 4) {     // four keypoints per step: 28 independent loads in flight per lane
+      uint32_t r[4][7];
+      const uint8_t* p[4];
+      int slot[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        slot[u] = min(j + u, cnt - 1);     // the tail repeats the last keypoint (same data, same destination)
+        const uint32_t qq = __shfl_sync(0xffffffffu, q, slot[u]);
+        p[u] = base + (size_t)((int)(qq >> 16) - 13) * g.pitch + (((int)(qq & 0xffffu) - 13) & ~3);
+      }
 #pragma unroll
       for (int t = 0; t < 7; ++t)
         if (t < 6 || lane < 16) {
-          r0[t] = __ldg(reinterpret_cast<const uint32_t*>(pa + src_off[t]));
-          r1[t] = __ldg(reinterpret_cast<const uint32_t*>(pb + src_off[t]));
-        }
-      uint8_t* da = warp_patches + (size_t)j * PSTRIDE;
-      uint8_t* db = warp_patches + (size_t)min(j + 1, cnt - 1) * PSTRIDE;
 #pragma unroll
-      for (int t = 0; t < 7; ++t)
-        if (t < 6 || lane < 16) {
-          *reinterpret_cast<uint32_t*>(da + dst_off[t]) = r0[t];
-          *reinterpret_cast<uint32_t*>(db + dst_off[t]) = r1[t];
+          for (int u = 0; u < 4; ++u) r[u][t] = __ldg(reinterpret_cast<const uint32_t*>(p[u] + src_off[t]));
         }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint8_t* d = warp_patches + (size_t)slot[u] * PSTRIDE;
+#pragma unroll
+        for (int t = 0; t < 7; ++t)
+          if (t < 6 || lane < 16) *reinterpret_cast<uint32_t*>(d + dst_off[t]) = r[u][t];
+      }
     }
     __syncwarp();
     if (i < n) {
