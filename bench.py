@@ -151,18 +151,21 @@ def workload_config(args, pairs):
 
 # ------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons of one GPU during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks + throttle reasons of one GPU (B200_PROFILING.md recipe).  Started before the warm-up so that
+    nvidia-smi's start-up latency does not eat the timed region; only samples that arrive between begin() and end()
+    count (if the region is shorter than three sampling periods, every sample under load since start is used)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -172,33 +175,47 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def __exit__(self, *a):
         if self.proc:
-            time.sleep(0.12)
+            time.sleep(0.08)
             self.proc.terminate()
             self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(lines):
+            sm, mx, reasons = [], [], set()
+            for _, ln in lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+        inside = [x for x in self.lines if self.t0 is not None and self.t0 <= x[0] <= (self.t1 or 1e30) + 0.06]
+        window = "timed region"
+        if len(inside) < 3:
+            inside, window = self.lines, "warm-up + timed region (region shorter than 3 sampling periods)"
+        sm, mx, reasons = parse(inside)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def peaks():
@@ -268,17 +285,19 @@ def main():
 
     # ---- device-resident throughput
     gen.batch_upload(left, right)
-    for _ in range(W):
-        step_resident()
-    barrier()
-    launches0 = gen.launch_count
     with ClockSampler(local_rank) as clk:
+        for _ in range(W):
+            step_resident()
+        barrier()
+        launches0 = gen.launch_count
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clk.begin()
         start.record(stream)
         for _ in range(K):
             step_resident()
         end.record(stream)
         barrier()
+        clk.end()
     ms = max_over_ranks(start.elapsed_time(end))
     launches = gen.launch_count - launches0
     value = world * P * K / (ms * 1e-3)
