@@ -127,7 +127,8 @@ void GpuFrameAligner<A, K>::converge() {                                      //
   vslam_linear_system s;
   int32_t converged = 0, rounds = 0;
   const vslam_aligner_parameters q = parameters_for_abi();
-  check(vslam_aligner_converge(_handle, &q, T, &s, information, &converged, &rounds));
+  // the whole Gauss-Newton loop as one persistent device kernel (bit-identical to the round-by-round driver)
+  check(vslam_aligner_converge_fused(_handle, &q, T, &s, information, &converged, &rounds));
   adopt(s);
   array_to_pose(T);
   this->_has_system_converged = converged != 0;

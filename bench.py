@@ -218,6 +218,64 @@ class ClockSampler:
                 "samples": len(sm), "window": window}
 
 
+def aligner_stress(api, configs, synth, torch, dev):
+    """BASELINE.json configs[3]: 100k synthetic 3D-2D correspondences, 10 Gauss-Newton rounds on one GPU, plus the
+    linearize kernel alone on 4M correspondences (81 algorithmic bytes per correspondence per round)."""
+    acfg = configs.KITTI_FAST_ALIGNER
+    cam = synth.camera("kitti")
+    out = {}
+    peak, _ = peaks()
+    for kind, cls in (("stereouv", api.StereoUVAligner), ("uvd", api.UVDAligner)):
+        n = 100000
+        c = synth.correspondences(n, kind, cam)
+        omega = c["omega"] if kind == "stereouv" else np.stack([c["omega_uv"], c["omega_d"]], 1)
+        al = cls(acfg, max_points=4_000_000)
+        T0 = np.hstack([np.eye(3), np.zeros((3, 1))])
+        al.initialize(c["moving"], c["fixed"], omega, c["wt"], cam.K, cam.baseline, cam.rows, cam.cols, T0)
+        stream = torch.cuda.ExternalStream(al.stream, device=dev)
+        for _ in range(3):
+            al.setPreviousToCurrent(T0)
+            for _ in range(10):
+                al.oneRound(False)
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            al.setPreviousToCurrent(T0)
+            for _ in range(10):
+                al.oneRound(False)                      # host-driven: kernel + read-back + 6x6 solve per round
+        stepwise_ms = (time.perf_counter() - t0) / reps * 1e3
+        al.setPreviousToCurrent(T0)
+        al.converge(fused=True)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            al.setPreviousToCurrent(T0)
+            al.converge(fused=True)                     # one persistent kernel for the whole converge()
+        fused_ms = (time.perf_counter() - t0) / reps * 1e3
+        rounds = al.number_of_rounds
+        # the linearize kernel alone at a size that exceeds L2: CUDA events on the library's stream
+        big = 4_000_000
+        reps_n = big // n
+        al.initialize(np.tile(c["moving"], (reps_n, 1)), np.tile(c["fixed"], (reps_n, 1)),
+                      np.tile(omega, (reps_n, 1)) if omega.ndim == 2 else np.tile(omega, reps_n), np.tile(c["wt"], reps_n),
+                      cam.K, cam.baseline, cam.rows, cam.cols, synth.true_motion())
+        for _ in range(3):
+            al.linearize_async(False)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        al.synchronize()
+        e0.record(stream)
+        for _ in range(10):
+            al.linearize_async(False)
+        e1.record(stream)
+        al.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        gbs = 81.0 * big / (ms * 1e-3) / 1e9
+        out[kind] = {"n": n, "ten_rounds_host_driven_ms": stepwise_ms, "converge_fused_ms": fused_ms,
+                     "converge_rounds": rounds, "fused_ms_per_round": fused_ms / max(rounds, 1),
+                     "linearize_4M_ms": ms, "linearize_4M_gbs": gbs, "linearize_4M_frac_of_hbm": gbs / peak}
+        al.close()
+    return out
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -357,6 +415,8 @@ def main():
             "gpu_launches": int(launches), "roofline": roofline,
             "counts": {"mean_descriptors_left": float(nl.mean()), "mean_matches": float(nm.mean()),
                        "mean_framepoints": float(nf.mean())}}
+    if rank == 0:
+        line["aligner_stress"] = aligner_stress(api, configs, synth, torch, dev)
     if rank == 0 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(dl, dr, R, args.cpu_sample)
     if rank == 0:

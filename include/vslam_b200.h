@@ -268,6 +268,13 @@ int vslam_aligner_converge(vslam_aligner* h, const vslam_aligner_parameters* par
                            double previous_to_current[12], vslam_linear_system* system, double* information,
                            int32_t* has_system_converged, int32_t* number_of_rounds);
 
+/* converge() as ONE persistent cooperative kernel (linearize, grid barrier, 6x6 full-pivot LU, v2t update and the
+ * convergence logic on the device): no host round trip per Gauss-Newton round.  Same arguments and results as
+ * vslam_aligner_converge, bit-identical pose and round count. */
+int vslam_aligner_converge_fused(vslam_aligner* h, const vslam_aligner_parameters* parameters,
+                                 double previous_to_current[12], vslam_linear_system* system, double* information,
+                                 int32_t* has_system_converged, int32_t* number_of_rounds);
+
 /* asynchronous linearize without the host read-back (for callers that time the kernel with CUDA events) */
 int vslam_aligner_linearize_async(vslam_aligner* h, const double previous_to_current[12], int ignore_outliers,
                                   double maximum_error_kernel);

@@ -133,7 +133,7 @@ class FrameAligner {
   }
   void converge() {
     int32_t ok = 0, rounds = 0;
-    check(vslam_aligner_converge(_handle, &_parameters, _previous_to_current.data(), &_system, _information_matrix.data(),
+    check(vslam_aligner_converge_fused(_handle, &_parameters, _previous_to_current.data(), &_system, _information_matrix.data(),
                                  &ok, &rounds), "Aligner::converge");
     _has_system_converged = ok != 0;
     _number_of_rounds = rounds;

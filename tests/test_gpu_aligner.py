@@ -140,3 +140,33 @@ def test_capacity_error():
                        cam.rows, cam.cols)
     assert e.value.code == -3
     gpu.close()
+
+
+@pytest.mark.parametrize("kind,acfg,n", [("stereouv", configs.KITTI_FAST_ALIGNER, 20000), ("stereouv", configs.KITTI_ALIGNER, 700),
+                                         ("stereouv", configs.EUROC_ALIGNER, 100000), ("uvd", configs.KITTI_FAST_ALIGNER, 20000),
+                                         ("uvd", configs.KITTI_ALIGNER, 3)])
+def test_fused_gauss_newton_is_bit_identical_to_the_stepwise_driver(kind, acfg, n):
+    """vslam_aligner_converge_fused (one persistent cooperative kernel) vs vslam_aligner_converge (host loop)."""
+    gpu, cpu, c = _pair(kind, n, acfg)
+    a = gpu.converge(fused=False)
+    Ta, ra, ca, ia = gpu.previousToCurrent(), gpu.number_of_rounds, gpu.has_system_converged, gpu.information_matrix.copy()
+    ea, ina = gpu.errors(), gpu.inliers()
+    gpu.setPreviousToCurrent(T0)
+    b = gpu.converge(fused=True)
+    assert gpu.number_of_rounds == ra and gpu.has_system_converged == ca and ra >= 1
+    assert np.array_equal(gpu.previousToCurrent(), Ta)
+    assert np.array_equal(a["H"], b["H"]) and np.array_equal(a["b"], b["b"]) and a["total_error"] == b["total_error"]
+    assert a["inliers"] == b["inliers"] and np.array_equal(gpu.information_matrix, ia)
+    assert np.array_equal(gpu.errors(), ea) and np.array_equal(gpu.inliers(), ina)
+    gpu.close()
+
+
+def test_fused_gauss_newton_iteration_cap():
+    import dataclasses
+    acfg = dataclasses.replace(configs.KITTI_FAST_ALIGNER, maximum_number_of_iterations=3, error_delta_for_convergence=1e-12)
+    gpu, cpu, c = _pair("stereouv", 5000, acfg)
+    gpu.converge(fused=True)
+    want = cpu.converge(T0, acfg.damping, acfg.error_delta_for_convergence, 3, acfg.minimum_number_of_inliers)
+    assert not gpu.has_system_converged and not want["converged"]
+    assert gpu.number_of_rounds == want["rounds"] == 3
+    gpu.close()

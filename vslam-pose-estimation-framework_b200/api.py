@@ -37,7 +37,7 @@ vslam_fpg_batch_download vslam_fpg_batch_process vslam_fpg_batch_linearize vslam
 vslam_fpg_get_kernel_profile vslam_fpg_batch_get_features vslam_fpg_stream vslam_fpg_synchronize
 vslam_fpg_launch_count vslam_fpg_debug_keypoint_mask vslam_fpg_debug_blurred vslam_threshold_proposal
 vslam_aligner_create vslam_aligner_destroy vslam_aligner_upload vslam_aligner_linearize vslam_aligner_download
-vslam_aligner_one_round vslam_aligner_converge vslam_aligner_linearize_async vslam_aligner_read_system
+vslam_aligner_one_round vslam_aligner_converge vslam_aligner_converge_fused vslam_aligner_linearize_async vslam_aligner_read_system
 vslam_aligner_stream vslam_aligner_synchronize vslam_aligner_launch_count vslam_solve6 vslam_v2t""".split()
 
 
@@ -126,6 +126,7 @@ def lib():
         L.vslam_aligner_download.argtypes = [vp, vp, vp]
         L.vslam_aligner_one_round.argtypes = [vp, vp, C.c_int, vp, vp]
         L.vslam_aligner_converge.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.vslam_aligner_converge_fused.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.vslam_aligner_linearize_async.argtypes = [vp, vp, C.c_int, C.c_double]
         L.vslam_aligner_read_system.argtypes = [vp, vp]
         L.vslam_aligner_stream.argtypes = [vp]
@@ -452,12 +453,14 @@ class _FrameAligner:
                                              C.byref(self._sys)))
         return self._system()
 
-    def converge(self):
+    def converge(self, fused=True):
+        """BaseAligner::converge; fused=True runs the whole Gauss-Newton loop as one persistent device kernel,
+        fused=False drives linearize round by round from the host like the reference's loop (same results)"""
         p = self._params()
         info = np.zeros(36)
         ok, rounds = C.c_int32(), C.c_int32()
-        _check(lib().vslam_aligner_converge(self._h, C.byref(p), _p(self._T), C.byref(self._sys), _p(info),
-                                            C.byref(ok), C.byref(rounds)))
+        fn = lib().vslam_aligner_converge_fused if fused else lib().vslam_aligner_converge
+        _check(fn(self._h, C.byref(p), _p(self._T), C.byref(self._sys), _p(info), C.byref(ok), C.byref(rounds)))
         self.has_system_converged = bool(ok.value)
         self.number_of_rounds = rounds.value
         if ok.value:

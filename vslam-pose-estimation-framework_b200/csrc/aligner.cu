@@ -8,9 +8,14 @@
 // CPU oracle (oracle/c/vslam_oracle.c), so errors[] and the inlier classification are bit-identical to it; only
 // the summation order of H/b differs (per-thread partials, warp shuffle tree, per-block partials, and ONE atomic
 // ticket after which the last block adds the block partials in a fixed order -> run-to-run deterministic).
+#include <cooperative_groups.h>
+
+#include "gn_math.h"
 #include "kernels.cuh"
 
 namespace vslam {
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -208,6 +213,114 @@ __global__ void __launch_bounds__(kThreads) linearize_kernel(int n, AlignerBuffe
   }
 }
 
+// Fused Gauss-Newton: BaseAligner::converge (reference stereouv_aligner.cpp:210-264, uvd_aligner.cpp:194-248) as ONE
+// persistent cooperative kernel -- per round: linearize (same per-point code and the same ordered reduction as
+// linearize_kernel, so H and b are bit-identical to the stepwise path), grid barrier, block 0 solves the damped 6x6
+// system, updates the pose (v2t, re-orthonormalisation) and advances the convergence state machine, grid barrier.
+// No host round trip per round; errors[] / inliers[] hold the last round's values as in the reference.
+template <int KIND>
+__global__ void __launch_bounds__(kThreads) converge_kernel(int n, AlignerBuffers b, AlignerCamera cam, GnParams p,
+                                                            GnControl* __restrict__ ctl) {
+  constexpr int D = KIND == 0 ? 4 : 3;
+  constexpr int W = KIND == 0 ? 1 : 2;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double s_part[kThreads / 32][kAcc];
+  __shared__ double s_T[12];
+  __shared__ double s_sys[32];
+  __shared__ int s_ignore;
+
+  for (;;) {
+    if (threadIdx.x < 12) s_T[threadIdx.x] = __ldcg(&ctl->T[threadIdx.x]);
+    if (threadIdx.x == 0) s_ignore = __ldcg(&ctl->ignore);
+    __syncthreads();
+    const int ignore_outliers = s_ignore;
+
+    double acc[kAcc];
+#pragma unroll
+    for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
+    for (int u = blockIdx.x * kThreads + threadIdx.x; u < n; u += gridDim.x * kThreads) {
+      double fx[D], om[W], err;
+      uint8_t inl;
+#pragma unroll
+      for (int d = 0; d < D; ++d) fx[d] = b.fixed[d * b.stride + u];
+#pragma unroll
+      for (int d = 0; d < W; ++d) om[d] = b.omega[d * b.stride + u];
+      accumulate_point<KIND>(b.moving[u], b.moving[b.stride + u], b.moving[2 * b.stride + u], fx, om, b.wt[u], s_T, cam,
+                             ignore_outliers, p.kernel, acc, err, inl);
+      b.errors[u] = err;
+      b.inliers[u] = inl;
+    }
+    const double total = block_reduce(acc, s_part);
+    if (threadIdx.x < kAcc) b.partials[(size_t)blockIdx.x * 32 + threadIdx.x] = total;
+    grid.sync();
+
+    if (blockIdx.x == 0) {
+      {  // the block partials in block order, 8 interleaved slices per value -- as in linearize_kernel
+        const int j = threadIdx.x & 31, part = threadIdx.x >> 5;
+        double v = 0;
+        if (j < kAcc)
+          for (int blk = part; blk < (int)gridDim.x; blk += kThreads / 32) v += __ldcg(&b.partials[(size_t)blk * 32 + j]);
+        __syncthreads();
+        if (j < kAcc) s_part[part][j] = v;
+        __syncthreads();
+        if (threadIdx.x < kAcc) {
+          double s = 0;
+          for (int w = 0; w < kThreads / 32; ++w) s += s_part[w][threadIdx.x];
+          s_sys[threadIdx.x] = s;
+          b.system[threadIdx.x] = s;
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) {
+        // ---- oneRound (:190-207 / :174-191)
+        double H[36], nb[6], dx[6], T[12];
+        int k = 0;
+        for (int i = 0; i < 6; ++i)
+          for (int j = i; j < 6; ++j, ++k) H[i * 6 + j] = H[j * 6 + i] = s_sys[k];
+        for (int i = 0; i < 6; ++i) {
+          H[i * 6 + i] += p.damping * n;
+          nb[i] = -s_sys[21 + i];
+        }
+        for (int i = 0; i < 12; ++i) T[i] = s_T[i];
+        solve6(H, nb, dx);
+        apply_update(dx, T);
+        for (int i = 0; i < 12; ++i) ctl->T[i] = T[i];
+        for (int i = 0; i < 36; ++i) ctl->H[i] = H[i];
+        // ---- converge state machine (:213-247 / :197-233)
+        const double total_error = s_sys[27];
+        const int inliers = (int)llrint(s_sys[28]);
+        const int outliers = n - inliers;
+        const double prev = ctl->total_error_previous;
+        int rounds = ctl->rounds + 1, done = 0, converged = 0, phase = ctl->phase, it = ctl->iteration;
+        if (phase == 0) {
+          if (p.error_delta > fabs(prev - total_error)) {
+            if (inliers > p.inlier_gate && inliers > outliers && p.max_iterations > 0) {
+              phase = 1;      // inlier-only rounds (:224-236)
+              it = 0;
+            } else {
+              done = converged = 1;
+            }
+          } else if (++it >= p.max_iterations) {
+            done = 1;         // "system did not converge" (:250-255)
+          }
+        } else {
+          if (fabs(prev - total_error) < p.error_delta || ++it >= p.max_iterations) done = converged = 1;
+        }
+        ctl->total_error_previous = total_error;
+        ctl->rounds = rounds;
+        ctl->phase = phase;
+        ctl->iteration = it;
+        ctl->ignore = phase;
+        ctl->converged = converged;
+        __threadfence();
+        ctl->done = done;
+      }
+    }
+    grid.sync();
+    if (__ldcg(&ctl->done)) break;
+  }
+}
+
 // Batched form for independent stereo pairs: one WARP per pair linearises the StereoUV problem that aligns the
 // pair's new framepoints against themselves -- StereoUVAligner::initialize (:10-69) fused in: _moving =
 // cameraCoordinatesLeft, _fixed = (uL, vL, uR, vR), information = I4 (no landmark), w_t = min(max_depth/depth, 1).
@@ -258,10 +371,11 @@ __global__ void __launch_bounds__(kPairWarps * 32) linearize_pairs_kernel(const 
 
 }  // namespace
 
-int aligner_grid(int n, int sm_count) {
+// grid of both the stepwise and the fused kernel: every block co-resident (the fused kernel is cooperative), and the
+// SAME grid for both so that their ordered reductions -- hence H, b and the pose sequence -- are bit-identical
+int aligner_grid(int n, int resident_blocks) {
   const int blocks = (n + kThreads - 1) / kThreads;
-  const int cap = sm_count * 4;   // <= 4 resident CTAs per SM at this register budget; grid-stride beyond
-  return blocks < 1 ? 1 : (blocks < cap ? blocks : cap);
+  return blocks < 1 ? 1 : (blocks < resident_blocks ? blocks : resident_blocks);
 }
 
 void launch_linearize(int kind, int n, const AlignerBuffers& b, const AlignerCamera& cam, const double T[12],
@@ -270,6 +384,24 @@ void launch_linearize(int kind, int n, const AlignerBuffers& b, const AlignerCam
   for (int i = 0; i < 12; ++i) pose.T[i] = T[i];
   if (kind == 0) linearize_kernel<0><<<grid, kThreads, 0, stream>>>(n, b, cam, pose, ignore_outliers, kernel);
   else linearize_kernel<1><<<grid, kThreads, 0, stream>>>(n, b, cam, pose, ignore_outliers, kernel);
+}
+
+int converge_max_blocks_per_sm(int kind) {
+  int n = 0;
+  if (kind == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, converge_kernel<0>, kThreads, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, converge_kernel<1>, kThreads, 0);
+  return n;
+}
+
+cudaError_t launch_converge(int kind, int n, const AlignerBuffers& b, const AlignerCamera& cam, const GnParams& p,
+                            GnControl* ctl, int grid, cudaStream_t stream) {
+  int n_arg = n;
+  AlignerBuffers b_arg = b;
+  AlignerCamera cam_arg = cam;
+  GnParams p_arg = p;
+  void* args[] = {&n_arg, &b_arg, &cam_arg, &p_arg, &ctl};
+  const void* fn = kind == 0 ? (const void*)converge_kernel<0> : (const void*)converge_kernel<1>;
+  return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, stream);
 }
 
 void launch_linearize_pairs(const FramePointRecord* records, int record_stride, const int32_t* n_out, int n_pairs,

@@ -3,12 +3,14 @@
 // (reference src/aligners/stereouv_aligner.cpp:190-264, uvd_aligner.cpp:174-248).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
 
 #include "../../include/vslam_b200.h"
 #include "api_common.h"
+#include "gn_math.h"
 #include "host_math.h"
 #include "kernels.cuh"
 
@@ -35,6 +37,9 @@ struct vslam_aligner {
   double* h_system = nullptr;   // pinned [32]
   AlignerCamera cam;
   int max_grid = 0;
+  int resident_blocks = 0;      // co-resident CTAs of the cooperative kernel = grid cap of both linearize paths
+  GnControl* d_ctl = nullptr;
+  GnControl* h_ctl = nullptr;   // pinned
   int64_t launches = 0;
   bool uploaded = false;
 };
@@ -74,7 +79,8 @@ int linearize_async(vslam_aligner* h, const double T[12], int ignore_outliers, d
     CUDA_TRY(cudaMemsetAsync(h->d_system, 0, sizeof(double) * 32, h->stream));
     return VSLAM_OK;
   }
-  launch_linearize(h->kind, h->n, buffers(h), h->cam, T, ignore_outliers, kernel, aligner_grid(h->n, h->sm_count), h->stream);
+  launch_linearize(h->kind, h->n, buffers(h), h->cam, T, ignore_outliers, kernel, aligner_grid(h->n, h->resident_blocks),
+                   h->stream);
   ++h->launches;
   CUDA_TRY(cudaGetLastError());
   return VSLAM_OK;
@@ -117,7 +123,8 @@ int vslam_aligner_create(int kind, int32_t max_points, int device, vslam_aligner
   h->fixed_dim = kind == VSLAM_ALIGNER_STEREO_UV ? 4 : 3;
   h->omega_dim = kind == VSLAM_ALIGNER_STEREO_UV ? 1 : 2;
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
-  h->max_grid = aligner_grid(h->max_points, h->sm_count);
+  h->resident_blocks = std::max(1, converge_max_blocks_per_sm(kind)) * h->sm_count;
+  h->max_grid = aligner_grid(h->max_points, h->resident_blocks);
   const size_t N = h->max_points;
   bool ok = true;
   auto dalloc = [&](void** p, size_t bytes) {
@@ -132,6 +139,8 @@ int vslam_aligner_create(int kind, int32_t max_points, int device, vslam_aligner
   dalloc((void**)&h->d_partials, sizeof(double) * 32 * h->max_grid);
   dalloc((void**)&h->d_system, sizeof(double) * 32);
   dalloc((void**)&h->d_ticket, sizeof(unsigned int));
+  dalloc((void**)&h->d_ctl, sizeof(GnControl));
+  if (ok && cudaMallocHost((void**)&h->h_ctl, sizeof(GnControl)) != cudaSuccess) ok = false;
   if (ok && cudaMallocHost((void**)&h->h_stage, sizeof(double) * (3 + h->fixed_dim + h->omega_dim + 1) * N) != cudaSuccess) ok = false;
   if (ok && cudaMallocHost((void**)&h->h_system, sizeof(double) * 32) != cudaSuccess) ok = false;
   if (ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) ok = false;
@@ -151,7 +160,8 @@ int vslam_aligner_destroy(vslam_aligner* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_moving); cudaFree(h->d_fixed); cudaFree(h->d_omega); cudaFree(h->d_wt); cudaFree(h->d_errors);
   cudaFree(h->d_inliers); cudaFree(h->d_partials); cudaFree(h->d_system); cudaFree(h->d_ticket);
-  cudaFreeHost(h->h_stage); cudaFreeHost(h->h_system);
+  cudaFree(h->d_ctl);
+  cudaFreeHost(h->h_stage); cudaFreeHost(h->h_system); cudaFreeHost(h->h_ctl);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return VSLAM_OK;
@@ -257,6 +267,36 @@ int vslam_aligner_converge(vslam_aligner* h, const vslam_aligner_parameters* p, 
   }
   if (has_converged) *has_converged = converged;
   if (number_of_rounds) *number_of_rounds = rounds;
+  return VSLAM_OK;
+}
+
+int vslam_aligner_converge_fused(vslam_aligner* h, const vslam_aligner_parameters* p, double T[12], vslam_linear_system* s,
+                                 double* information, int32_t* has_converged, int32_t* number_of_rounds) {
+  if (!h || !p || !T || !s) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  if (!h->uploaded) return fail(VSLAM_ERR_STATE, "converge before upload");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (h->n == 0 || p->maximum_number_of_iterations < 1)   // nothing to iterate on the device: the stepwise driver
+    return vslam_aligner_converge(h, p, T, s, information, has_converged, number_of_rounds);
+  GnControl* c = h->h_ctl;
+  std::memset(c, 0, sizeof(*c));
+  for (int i = 0; i < 12; ++i) c->T[i] = T[i];
+  GnParams gp;
+  gp.error_delta = p->error_delta_for_convergence;
+  gp.kernel = p->maximum_error_kernel;
+  gp.damping = p->damping;
+  gp.max_iterations = p->maximum_number_of_iterations;
+  gp.inlier_gate = h->kind == VSLAM_ALIGNER_STEREO_UV ? p->minimum_number_of_inliers : 100;   // :224 / :208
+  CUDA_TRY(cudaMemcpyAsync(h->d_ctl, c, sizeof(GnControl), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(launch_converge(h->kind, h->n, buffers(h), h->cam, gp, h->d_ctl, aligner_grid(h->n, h->resident_blocks), h->stream));
+  ++h->launches;
+  CUDA_TRY(cudaMemcpyAsync(c, h->d_ctl, sizeof(GnControl), cudaMemcpyDeviceToHost, h->stream));
+  int rc = read_system(h, s);   // synchronises
+  if (rc) return rc;
+  for (int i = 0; i < 12; ++i) T[i] = c->T[i];
+  for (int i = 0; i < 6; ++i) s->H[i * 6 + i] += p->damping * h->n;   // _H after oneRound carries the damping (:196)
+  if (information && c->converged) std::memcpy(information, c->H, sizeof(double) * 36);
+  if (has_converged) *has_converged = c->converged;
+  if (number_of_rounds) *number_of_rounds = c->rounds;
   return VSLAM_OK;
 }
 

@@ -72,7 +72,26 @@ struct AlignerCamera {
   double min_depth;
 };
 
-int aligner_grid(int n, int sm_count);
+// parameters and device-resident state of the fused Gauss-Newton kernel
+struct GnParams {
+  double error_delta;   // error_delta_for_convergence
+  double kernel;        // maximum_error_kernel
+  double damping;
+  int max_iterations;   // maximum_number_of_iterations
+  int inlier_gate;      // minimum_number_of_inliers (StereoUV) / 100 (UVD)
+};
+
+struct GnControl {
+  double T[12];                  // previous_to_current, in/out
+  double H[36];                  // damped H of the last round (-> _information_matrix)
+  double total_error_previous;
+  int rounds, phase, iteration, ignore, converged, done;
+};
+
+int aligner_grid(int n, int resident_blocks);
+int converge_max_blocks_per_sm(int kind);
+cudaError_t launch_converge(int kind, int n, const AlignerBuffers& b, const AlignerCamera& cam, const GnParams& p,
+                            GnControl* ctl, int grid, cudaStream_t stream);
 void launch_linearize(int kind, int n, const AlignerBuffers& b, const AlignerCamera& cam, const double T[12],
                       int ignore_outliers, double kernel, int grid, cudaStream_t stream);
 // one CTA per stereo pair: StereoUV initialize + linearize of the pair's new framepoints against themselves
