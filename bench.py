@@ -276,6 +276,37 @@ def aligner_stress(api, configs, synth, torch, dev):
     return out
 
 
+def sequence_latency(api, configs, synth, device):
+    """BASELINE.json configs[0]/[1] shape: ONE sequence, frame by frame through the reference-shaped calls
+    (initialize -> compute, thresholds fed back between frames, host images in, host framepoints out, one host
+    synchronisation per call): single-stream frames/s, i.e. the latency-bound regime of a live tracker."""
+    out = {}
+    for name in ("kitti", "euroc"):
+        cfg = configs.BY_NAME[name]
+        cam = synth.camera(cfg.camera)
+        world = synth.BandWorld(cam.cols, cam.rows, 7, max_frames=40)
+        frames = []
+        for k in range(24):       # page-locked frame buffers (vslam_host_alloc): the H2D copy is one async DMA
+            l, r = world.pair(k)
+            pl, pr = api.pinned_empty(l.shape), api.pinned_empty(r.shape)
+            pl[:], pr[:] = l, r
+            frames.append((pl, pr))
+        gen = api.StereoFramePointGenerator(cfg, cam, device=device)
+        for k in range(4):
+            gen.initialize(frames[k][0], frames[k][1], k == 0)
+            gen.compute()
+        t0 = time.perf_counter()
+        n_fp = 0
+        for k in range(4, 24):
+            gen.initialize(frames[k][0], frames[k][1], False)
+            n_fp += len(gen.compute())
+        dt = time.perf_counter() - t0
+        out[name] = {"frames_per_s": 20 / dt, "ms_per_frame": dt / 20 * 1e3, "mean_framepoints": n_fp / 20,
+                     "image": "%dx%d" % (cam.cols, cam.rows)}
+        gen.close()
+    return out
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -417,6 +448,7 @@ def main():
                        "mean_framepoints": float(nf.mean())}}
     if rank == 0:
         line["aligner_stress"] = aligner_stress(api, configs, synth, torch, dev)
+        line["sequence"] = sequence_latency(api, configs, synth, local_rank)
     if rank == 0 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(dl, dr, R, args.cpu_sample)
     if rank == 0:

@@ -28,6 +28,8 @@ def test_product_does_not_link_or_import_the_oracle():
     import subprocess
     out = subprocess.run(["ldd", api.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out
+    undefined = subprocess.run(["nm", "-D", "-C", "--undefined-only", api.LIB_PATH], capture_output=True, text=True).stdout
+    assert "vslam" not in undefined, undefined       # every kernel launcher the ABI calls is linked in
     pkg = os.path.join(ROOT, "vslam-pose-estimation-framework_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:

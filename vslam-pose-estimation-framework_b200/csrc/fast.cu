@@ -191,18 +191,28 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable r
     return;
   }
 
-  // ---- phase 0: stage the tile (+halo) in shared memory: 38 rows x 10 uint4, coalesced 16 B loads; clear state
-  const uint8_t* base = image + (size_t)img * g.rows * g.pitch;
-  for (int i = tid; i < SH * (SW / 16); i += 256) {
-    const int r = i / (SW / 16), c = i - r * (SW / 16);
-    const int gy = y0 - 4 + r, gx = x0 - HX + c * 16;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (gy >= 0 && gy < g.rows && gx >= 0 && gx + 16 <= g.pitch)
-      v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)gy * g.pitch + gx));
-    *reinterpret_cast<uint4*>(&s_img[r][c * 16]) = v;
+  // ---- phase 0: stage the tile (+halo) in shared memory: 38 rows x 10 uint4, coalesced 16 B loads; clear state.
+  // Thread -> (row r0 + 25*pass, 16-byte chunk c) is fixed, so the address arithmetic is done once per thread.
+  {
+    const uint8_t* base = image + (size_t)img * g.rows * g.pitch;
+    const int c = tid % (SW / 16), r0 = tid / (SW / 16);   // 250 loader threads: 25 rows per pass
+    const int gx = x0 - HX + c * 16;
+    const bool col_ok = tid < 250 && gx >= 0 && gx + 16 <= g.pitch;
+    const uint8_t* src = base + (ptrdiff_t)(y0 - 4 + r0) * g.pitch + gx;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int r = r0 + 25 * pass, gy = y0 - 4 + r;
+      if (tid < 250 && r < SH) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (col_ok && gy >= 0 && gy < g.rows) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(25 * pass) * g.pitch));
+        *reinterpret_cast<uint4*>(&s_img[r][c * 16]) = v;
+      }
+    }
+    uint4* sc = reinterpret_cast<uint4*>(&s_score[0][0]);
+    sc[tid] = make_uint4(0, 0, 0, 0);
+    if (tid < CH * CPITCH / 16 - 256) sc[256 + tid] = make_uint4(0, 0, 0, 0);
+    if (tid < TH * 4) (&s_mask[0][0])[tid] = 0u;
   }
-  for (int i = tid; i < CH * CPITCH / 16; i += 256) reinterpret_cast<uint4*>(&s_score[0][0])[i] = make_uint4(0, 0, 0, 0);
-  if (tid < TH * 4) (&s_mask[0][0])[tid] = 0u;
   __syncthreads();
 
   // ---- phase 1 (warp-private): compass pre-test on the tile + 1 px NMS halo.  Warp w owns pre-test rows w, w+8,
@@ -303,18 +313,24 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable r
   }
 }
 
-// K2: one CTA per image.  Applies cv::ORB's 31 px border filter (KeyPointsFilter::runByImageBorder), builds the
-// CSR row pointer and the (row, col)-sorted keypoint list.
+// K2: gridDim.x CTAs per image, each owning a strip of image rows.  Applies cv::ORB's 31 px border filter
+// (KeyPointsFilter::runByImageBorder), builds the CSR row pointer and the (row, col)-sorted keypoint list.
+// A CTA obtains the offset of its strip by re-counting the (L2-resident, 60 KB) mask rows above it, which is cheaper
+// than a second kernel or a cross-CTA scan; batches use one CTA per image, single frames split the image to cut latency.
 __global__ void __launch_bounds__(256) compact_kernel(Geometry g, const uint32_t* __restrict__ mask,
                                                       int32_t* __restrict__ row_ptr, uint32_t* __restrict__ kp_xy,
                                                       int32_t* __restrict__ n_desc, int32_t* __restrict__ error_flag) {
-  extern __shared__ int s_rows[];   // rows + 1 counts -> exclusive offsets
+  extern __shared__ int s_rows[];   // counts of the strip's rows -> exclusive offsets (+1 entry)
   __shared__ int s_warp[8];
-  const int img = blockIdx.x;
+  __shared__ int s_base;
+  const int img = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t* m = mask + (size_t)img * g.rows * g.mask_words;
   const int lo_x = 31, hi_x = g.cols - 31;   // keep lo_x <= x < hi_x
   const int lo_y = 31, hi_y = g.rows - 31;
+  const int strip = (g.rows + gridDim.x - 1) / gridDim.x;
+  const int y_begin = blockIdx.x * strip, y_end = min(g.rows, y_begin + strip);
+  const bool last = blockIdx.x == gridDim.x - 1;
 
   auto valid_word = [&](int y, int wd) -> uint32_t {
     uint32_t w = m[(size_t)y * g.mask_words + wd];
@@ -324,21 +340,41 @@ __global__ void __launch_bounds__(256) compact_kernel(Geometry g, const uint32_t
     return w;
   };
 
-  // per-row counts
-  for (int y = warp; y < g.rows; y += 8) {
+  // offset of the strip: keypoints in the rows above it
+  {
+    int c = 0;
+    const int r0 = lo_y, r1 = min(y_begin, hi_y);
+    for (int i = tid; i < (r1 - r0) * g.mask_words; i += 256) {
+      const int y = r0 + i / g.mask_words, wd = i - (y - r0) * g.mask_words;
+      c += __popc(valid_word(y, wd));
+    }
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) s_warp[warp] = c;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < 8; ++w) t += s_warp[w];
+      s_base = t;
+    }
+    __syncthreads();
+  }
+
+  // per-row counts of the strip
+  for (int y = y_begin + warp; y < y_end; y += 8) {
     int c = 0;
     if (y >= lo_y && y < hi_y)
       for (int wd = lane; wd < g.mask_words; wd += 32) c += __popc(valid_word(y, wd));
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0) s_rows[y] = c;
+    if (lane == 0) s_rows[y - y_begin] = c;
   }
   __syncthreads();
 
-  // block-wide exclusive scan over rows (chunks of 256)
-  int carry = 0;
-  for (int b0 = 0; b0 < g.rows; b0 += 256) {
-    const int y = b0 + tid;
-    const int v = y < g.rows ? s_rows[y] : 0;
+  // block-wide exclusive scan over the strip's rows (chunks of 256)
+  int carry = s_base;
+  const int n_rows = y_end - y_begin;
+  for (int b0 = 0; b0 < n_rows; b0 += 256) {
+    const int r = b0 + tid;
+    const int v = r < n_rows ? s_rows[r] : 0;
     int inc = v;
     for (int o = 1; o < 32; o <<= 1) {
       const int n = __shfl_up_sync(0xffffffffu, inc, o);
@@ -350,24 +386,26 @@ __global__ void __launch_bounds__(256) compact_kernel(Geometry g, const uint32_t
     for (int w = 0; w < warp; ++w) woff += s_warp[w];
     int total = 0;
     for (int w = 0; w < 8; ++w) total += s_warp[w];
-    if (y < g.rows) s_rows[y] = carry + woff + inc - v;
+    if (r < n_rows) s_rows[r] = carry + woff + inc - v;
     carry += total;
     __syncthreads();
   }
   if (tid == 0) {
-    s_rows[g.rows] = carry;
-    n_desc[img] = min(carry, g.cap);
-    if (carry > g.cap) atomicExch(error_flag, 1);
+    s_rows[n_rows] = carry;
+    if (last) {
+      n_desc[img] = min(carry, g.cap);
+      if (carry > g.cap) atomicExch(error_flag, 1);
+    }
   }
   __syncthreads();
   int32_t* rp = row_ptr + (size_t)img * (g.rows + 1);
-  for (int y = tid; y <= g.rows; y += 256) rp[y] = min(s_rows[y], g.cap);
+  for (int r = tid; r < n_rows + (last ? 1 : 0); r += 256) rp[y_begin + r] = min(s_rows[r], g.cap);
 
   // ordered emission
   uint32_t* xy = kp_xy + (size_t)img * g.cap;
-  for (int y = lo_y + warp; y < hi_y; y += 8) {
-    if (s_rows[y + 1] == s_rows[y]) continue;
-    int row_base = s_rows[y];
+  for (int y = max(lo_y, y_begin) + warp; y < min(hi_y, y_end); y += 8) {
+    if (s_rows[y - y_begin + 1] == s_rows[y - y_begin]) continue;
+    int row_base = s_rows[y - y_begin];
     for (int w0 = 0; w0 < g.mask_words; w0 += 32) {
       const int wd = w0 + lane;
       const uint32_t w = wd < g.mask_words ? valid_word(y, wd) : 0u;
@@ -437,11 +475,11 @@ void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, int
 }
 
 void launch_compact(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream) {
-  const size_t smem = sizeof(int) * (g.rows + 1);
-  compact_kernel<<<n_images, 256, smem, stream>>>(g, b.mask + (size_t)first_image * g.rows * g.mask_words,
-                                                  b.row_ptr + (size_t)first_image * (g.rows + 1),
-                                                  b.kp_xy + (size_t)first_image * g.cap, b.n_desc + first_image,
-                                                  b.error_flag);
+  const int strips = n_images <= 16 ? 8 : 1;   // single frames: split each image over 8 CTAs (latency)
+  const size_t smem = sizeof(int) * ((g.rows + strips - 1) / strips + 2);
+  compact_kernel<<<dim3(strips, n_images), 256, smem, stream>>>(
+      g, b.mask + (size_t)first_image * g.rows * g.mask_words, b.row_ptr + (size_t)first_image * (g.rows + 1),
+      b.kp_xy + (size_t)first_image * g.cap, b.n_desc + first_image, b.error_flag);
 }
 
 // cv::KeyPoint::response of the kept keypoints (cornerScore<16>): nothing on the path reads it, so it is produced
