@@ -447,6 +447,216 @@ int orc_stereo_compute(orc_feature* fl, int* n_l, orc_feature* fr, int* n_r, con
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * tracking (track) and recovery (recoverPoints)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* `const int32_t v = <double expression>;` as x86-64 evaluates it (cvttsd2si): truncation toward zero; NaN and
+ * values outside int32 give INT32_MIN ("integer indefinite"), which every caller below rejects as `< 0`. */
+static int32_t to_i32(double v) {
+  if (!(v > -2147483649.0 && v < 2147483648.0)) return INT32_MIN;
+  return (int32_t)v;
+}
+
+/* intensity_feature_matcher.cpp:81-148 on a lattice of feature positions (-1 = nullptr).  Returns the position
+ * of the chosen feature or -1; *distance_best as the reference leaves descriptor_distance_best_. */
+static int match_in_region(const int32_t* lattice, int cols, const orc_feature* f, int row_reference,
+                           int col_reference, const uint8_t* descriptor_reference, int row_start, int row_end,
+                           int col_start, int col_end, double maximum_distance, int track_by_appearance,
+                           double* distance_best) {
+  *distance_best = maximum_distance;                                           /* :91 */
+  int best = -1;
+  if (track_by_appearance) {                                                   /* :96-112 */
+    for (int row = row_start; row < row_end; ++row)
+      for (int col = col_start; col < col_end; ++col) {
+        const int32_t k = lattice[(size_t)row * cols + col];
+        if (k < 0) continue;
+        const double d = orc_hamming256(descriptor_reference, f[k].desc);
+        if (d < *distance_best) {
+          *distance_best = d;
+          best = k;
+        }
+      }
+  } else {                                                                     /* :115-139 */
+    uint32_t projection_distance_best = 10000;
+    for (int row = row_start; row < row_end; ++row)
+      for (int col = col_start; col < col_end; ++col) {
+        const int32_t k = lattice[(size_t)row * cols + col];
+        if (k < 0) continue;
+        const double d = orc_hamming256(descriptor_reference, f[k].desc);
+        if (d < maximum_distance) {
+          const int32_t dr = row_reference - row, dc = col_reference - col;
+          const uint32_t projection_distance = (uint32_t)(dr * dr + dc * dc);
+          if (projection_distance < projection_distance_best) {
+            projection_distance_best = projection_distance;
+            *distance_best = d;
+            best = k;
+          }
+        }
+      }
+  }
+  return best;                                                                 /* :142-147 */
+}
+
+static int32_t* make_lattice(const orc_feature* f, int n, int rows, int cols) {  /* :48-70 setFeatures */
+  int32_t* lattice = (int32_t*)malloc(sizeof(int32_t) * (size_t)rows * cols);
+  for (size_t i = 0; i < (size_t)rows * cols; ++i) lattice[i] = -1;
+  for (int i = 0; i < n; ++i) lattice[(size_t)f[i].row * cols + f[i].col] = i;
+  return lattice;
+}
+
+static int imax(int a, int b) { return a > b ? a : b; }
+static int imin(int a, int b) { return a < b ? a : b; }
+
+/* stereo_framepoint_generator.cpp:464-681.  Floating-point evaluation order of the two Eigen products is not pinned
+ * by the reference (Eigen is un-vendored): T*p is evaluated row by row, left to right, like transform_point below;
+ * K*p as fx*X + cx*Z, fy*Y + cy*Z, Z (the zero products of the dense 3x3 product add exact zeros). */
+int orc_track(const orc_feature* fl, int n_l, const orc_feature* fr, int n_r, int rows, int cols,
+              const orc_stereo_camera* cam, const orc_previous_point* previous, int n_previous, const double T[12],
+              int track_by_appearance, int tracking_distance_pixels, double max_distance_tracking,
+              double max_distance_triangulation, double min_disparity, orc_track_record* tracks, int32_t* lost,
+              int* n_lost, uint8_t* matched_l, uint8_t* matched_r, int* n_tracked_landmarks,
+              double* accumulated_distance) {
+  int32_t* lattice_l = make_lattice(fl, n_l, rows, cols);
+  int32_t* lattice_r = make_lattice(fr, n_r, rows, cols);
+  memset(matched_l, 0, (size_t)(n_l > 0 ? n_l : 1));
+  memset(matched_r, 0, (size_t)(n_r > 0 ? n_r : 1));
+  int number_of_tracked_points = 0, number_of_points_lost = 0, tracked_landmarks = 0;
+  double accumulated = 0;
+  const int D = tracking_distance_pixels;
+
+  for (int u = 0; u < n_previous; ++u) {                                       /* :494 */
+    const orc_previous_point* pp = &previous[u];
+    double pc[3];
+    for (int i = 0; i < 3; ++i)                                                /* :496-498 */
+      pc[i] = T[4 * i] * pp->cam[0] + T[4 * i + 1] * pp->cam[1] + T[4 * i + 2] * pp->cam[2] + T[4 * i + 3];
+    const double il[3] = {cam->fx * pc[0] + cam->cx * pc[2], cam->fy * pc[1] + cam->cy * pc[2], pc[2]}; /* :501-502 */
+    const int32_t col_l = to_i32(il[0] / il[2]);                               /* :503-506 */
+    const int32_t row_l = to_i32(il[1] / il[2]);
+    if (col_l < 0 || col_l > cols || row_l < 0 || row_l > rows) continue;      /* :509-514 */
+
+    double distance_best = max_distance_tracking;                              /* :517 */
+    int row_start = imax(row_l - D, 0), row_end = imin(row_l + D + 1, rows);   /* :520-529 */
+    int col_start = imax(col_l - D, 0), col_end = imin(col_l + D + 1, cols);
+    const int kl = match_in_region(lattice_l, cols, fl, row_l, col_l, pp->desc_left, row_start, row_end, col_start,
+                                   col_end, max_distance_tracking, track_by_appearance, &distance_best); /* :532-538 */
+    int tracked = 0;
+    if (kl >= 0) {
+      const orc_feature* feature_left = &fl[kl];
+      const float error_x = (float)col_l - feature_left->x;                    /* :543-545 cv::Point2f */
+      const float error_y = (float)row_l - feature_left->y;
+      const double ir[3] = {il[0] + cam->bx, il[1] + 0.0, il[2] + 0.0};        /* :549 _baseline = (b_x, 0, 0) */
+      const int32_t col_r = to_i32(ir[0] / ir[2] - (double)error_x);           /* :550-555 */
+      const int32_t row_r = to_i32(ir[1] / ir[2] - (double)error_y);
+      if (col_r < 0 || col_r > cols || row_r < 0 || row_r > rows) continue;    /* :558-563 */
+      const int32_t e = (int32_t)fabs((double)pp->epipolar_offset);            /* :568-569 */
+      row_start = imax(row_r - e, 0);                                          /* :570-579 */
+      row_end = imin(row_r + e + 1, rows);
+      col_start = imax(col_r - D, 0);
+      col_end = imin(col_r + D + 1, feature_left->col);
+      const int kr = match_in_region(lattice_r, cols, fr, row_r, col_r, feature_left->desc, row_start, row_end,
+                                     col_start, col_end, max_distance_triangulation, 1, &distance_best); /* :584-590 */
+      if (kr >= 0) {
+        const orc_feature* feature_right = &fr[kr];
+        if ((double)(feature_left->col - feature_right->col) < min_disparity) continue;                  /* :597-600 */
+        if ((double)orc_hamming256(feature_right->desc, pp->desc_right) > max_distance_tracking) continue; /* :603-607 */
+        for (int col = feature_right->col + 1; col < feature_left->col; ++col) {                         /* :611-620 */
+          int32_t* cell = &lattice_r[(size_t)feature_right->row * cols + col];
+          if (*cell >= 0) {
+            matched_r[*cell] = 1;
+            *cell = -1;
+          }
+        }
+        orc_track_record* t = &tracks[number_of_tracked_points++];                    /* :623-643 */
+        memset(t, 0, sizeof(*t));
+        t->index_previous = u;
+        t->index_left = feature_left->index;
+        t->index_right = feature_right->index;
+        t->xl = feature_left->x; t->yl = feature_left->y;
+        t->xr = feature_right->x; t->yr = feature_right->y;
+        t->distance = (int32_t)distance_best;
+        t->epipolar_offset = feature_right->row - feature_left->row;
+        t->projection_left[0] = (float)col_l; t->projection_left[1] = (float)row_l;
+        t->projection_right[0] = (float)(ir[0] / ir[2]); t->projection_right[1] = (float)(ir[1] / ir[2]);
+        t->projection_right_corrected[0] = (float)col_r; t->projection_right_corrected[1] = (float)row_r;
+        orc_triangulate(cam, t->xl, t->yl, t->xr, t->yr, t->cam);
+        accumulated += distance_best;                                          /* :627 */
+        matched_l[kl] = 1;                                                     /* :646-651 */
+        matched_r[kr] = 1;
+        lattice_l[(size_t)feature_left->row * cols + feature_left->col] = -1;
+        lattice_r[(size_t)feature_right->row * cols + feature_right->col] = -1;
+        if (pp->has_landmark) ++tracked_landmarks;                             /* :653-655 */
+        tracked = 1;
+      }
+    }
+    if (!tracked) lost[number_of_points_lost++] = u;                           /* :660-663 : !point_previous->next() */
+  }
+  free(lattice_l);
+  free(lattice_r);
+  *n_lost = number_of_points_lost;
+  *n_tracked_landmarks = tracked_landmarks;
+  *accumulated_distance = accumulated;   /* :666-667 divides by number_of_tracked_points (NaN when zero) */
+  return number_of_tracked_points;
+}
+
+/* rBRIEF-256 at an integer pixel of a blurred image (the inner loop of orc_orb_compute) */
+static void brief_at(const uint8_t* blurred, int stride, int x, int y, uint8_t* d) {
+  const uint8_t* c = blurred + (size_t)y * stride + x;
+  for (int b = 0; b < 32; ++b) {
+    unsigned v = 0;
+    for (int k = 0; k < 8; ++k) {
+      const int8_t* p = kOrbPattern + (b * 8 + k) * 4;
+      v |= (unsigned)((int)c[p[1] * stride + p[0]] < (int)c[p[3] * stride + p[2]]) << k;
+    }
+    d[b] = (uint8_t)v;
+  }
+}
+
+/* stereo_framepoint_generator.cpp:683-869 */
+int orc_recover_points(const uint8_t* blurred_l, const uint8_t* blurred_r, int stride, int rows, int cols,
+                       const orc_stereo_camera* cam, const orc_previous_point* lost, int n_lost,
+                       const double W[12], double min_depth, double max_depth, double max_distance_tracking,
+                       double max_distance_triangulation, double min_disparity, orc_recovered* out) {
+  int n = 0;
+  for (int u = 0; u < n_lost; ++u) {                                           /* :702 */
+    const orc_previous_point* pp = &lost[u];
+    if (!pp->has_landmark) continue;                                           /* :704-706 */
+    double pc[3];
+    for (int i = 0; i < 3; ++i)                                                /* :716-717 */
+      pc[i] = W[4 * i] * pp->world[0] + W[4 * i + 1] * pp->world[1] + W[4 * i + 2] * pp->world[2] + W[4 * i + 3];
+    double il[3] = {cam->fx * pc[0] + cam->cx * pc[2], cam->fy * pc[1] + cam->cy * pc[2], pc[2]};        /* :725-726 */
+    double ir[3] = {il[0] + cam->bx, il[1] + 0.0, il[2] + 0.0};                                          /* :727-728 */
+    if (il[2] < min_depth || il[2] > max_depth || ir[2] < min_depth || ir[2] > max_depth) continue;     /* :731-736 */
+    /* :739-740  `v /= v.z()` : Eigen evaluates the scalar first; element-wise division */
+    const double zl = il[2], zr = ir[2];
+    for (int i = 0; i < 3; ++i) { il[i] /= zl; ir[i] /= zr; }
+    const float plx = (float)rint(il[0]), ply = (float)rint(il[1]);            /* :743-746 */
+    const float prx = (float)rint(ir[0]), pry = (float)rint(ir[1]);
+    const float border = 5 * pp->keypoint_size;                                /* :749-750 */
+    if (plx < border + 1 || plx > cols - border - 1 || prx < border + 1 || prx > cols - border - 1 ||
+        ply < border + 1 || ply > rows - border - 1 || pry < border + 1 || pry > rows - border - 1) continue; /* :751-766 */
+    /* :769-795 / :808-822 : cv::ORB::compute on the (2*border+1)^2 region around the projection with the keypoint at
+     * its centre; with border >= 31 the keypoint survives ORB's 31 px border filter and its patch + blur support
+     * are interior, so the descriptor is rBRIEF of the blurred frame at the projection */
+    if (border < 31) continue;                                                 /* descriptor.rows == 0 (:790-792) */
+    orc_recovered r;
+    memset(&r, 0, sizeof(r));
+    brief_at(blurred_l, stride, (int)plx, (int)ply, r.desc_left);
+    if ((double)orc_hamming256(pp->desc_left, r.desc_left) > max_distance_tracking) continue;            /* :798-802 */
+    brief_at(blurred_r, stride, (int)prx, (int)pry, r.desc_right);
+    if ((double)(plx - prx) < min_disparity) continue;                                                   /* :825-828 */
+    if ((double)orc_hamming256(pp->desc_right, r.desc_right) > max_distance_tracking) continue;          /* :831-835 */
+    const int d = orc_hamming256(r.desc_left, r.desc_right);                                             /* :838-843 */
+    if ((double)d > max_distance_triangulation) continue;
+    r.index_lost = u;
+    r.distance = d;
+    r.xl = plx; r.yl = ply; r.xr = prx; r.yr = pry;
+    orc_triangulate(cam, plx, ply, prx, pry, r.cam);                                                     /* :851-855 */
+    out[n++] = r;
+  }
+  return n;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * aligners
  * ---------------------------------------------------------------------------------------------- */
 

@@ -99,7 +99,43 @@ class StereoFramePointGeneratorOracle:
             c.maximum_matching_distance_triangulation)
         self.features_left = tier_a.make_features(self.kps_left, self.desc_left)             # :129-132, :159-160
         self.features_right = tier_a.make_features(self.kps_right, self.desc_right)
+        self.images = (left, right)
+        self._blurred = None
         return self
+
+    # ---- stereo_framepoint_generator.cpp:464-681 -----------------------------------------------
+    def track(self, previous, previous_to_current, track_by_appearance, tracking_distance_pixels,
+              max_distance_tracking):
+        """previous: tier_a.PREVIOUS_POINT records of frame_previous->points().  Prunes the matched features from the
+        candidate pools like :671-672, so that the next compute() only scans the rest."""
+        c = self.cfg
+        r = tier_a.track(self.features_left, self.features_right, self.rows, self.cols, self.stereo_camera, previous,
+                         previous_to_current, track_by_appearance, tracking_distance_pixels, max_distance_tracking,
+                         self.max_distance, c.minimum_disparity_pixels)
+        self.features_left = self.features_left[~r["matched_left"]]
+        self.features_right = self.features_right[~r["matched_right"]]
+        self.tracks = r["tracks"]
+        return r
+
+    @staticmethod
+    def tracked_points(tracks):
+        """the tracked points as compute() finds them in frame->points() (:147-155): FramePoint row/col
+        (frame_point.cpp:8-24), previous() set, disparityPixels, descriptorDistanceTriangulation"""
+        t = np.zeros(len(tracks), tier_a.TRACKED)
+        t["row"], t["col"] = tracks["yl"].astype(np.int32), tracks["xl"].astype(np.int32)
+        t["has_previous"] = 1
+        t["disparity"] = (tracks["xl"] - tracks["xr"]).astype(np.float64)
+        t["distance"] = tracks["distance"]
+        return t
+
+    # ---- stereo_framepoint_generator.cpp:683-869 -----------------------------------------------
+    def recover_points(self, lost, world_to_camera_left, max_distance_tracking, min_depth=0.1, max_depth=1000.0):
+        """lost: tier_a.PREVIOUS_POINT records of the lost points (parameters.h:196-199 depth defaults)"""
+        if self._blurred is None:
+            self._blurred = (tier_a.gauss7_u8(self.images[0]), tier_a.gauss7_u8(self.images[1]))
+        return tier_a.recover_points(self._blurred[0], self._blurred[1], self.stereo_camera, lost,
+                                     world_to_camera_left, min_depth, max_depth, max_distance_tracking,
+                                     self.max_distance, self.cfg.minimum_disparity_pixels)
 
     # ---- stereo_framepoint_generator.cpp:135-462 -----------------------------------------------
     def compute(self, tracked=None):

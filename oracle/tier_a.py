@@ -22,6 +22,16 @@ MATCH = np.dtype([("index_left", "<i4"), ("index_right", "<i4"), ("xl", "<f4"), 
 TRACKED = np.dtype([("row", "<i4"), ("col", "<i4"), ("has_previous", "<i4"), ("_pad", "<i4"),
                     ("disparity", "<f8"), ("distance", "<f8")])
 RECT = np.dtype([("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4")])
+PREVIOUS_POINT = np.dtype([("cam", "<f8", (3,)), ("world", "<f8", (3,)), ("desc_left", "u1", (32,)),
+                           ("desc_right", "u1", (32,)), ("epipolar_offset", "<i4"), ("has_landmark", "<i4"),
+                           ("keypoint_size", "<f4"), ("_reserved", "<i4")])
+TRACK = np.dtype([("index_previous", "<i4"), ("index_left", "<i4"), ("index_right", "<i4"), ("xl", "<f4"),
+                  ("yl", "<f4"), ("xr", "<f4"), ("yr", "<f4"), ("distance", "<i4"), ("epipolar_offset", "<i4"),
+                  ("projection_left", "<f4", (2,)), ("projection_right", "<f4", (2,)),
+                  ("projection_right_corrected", "<f4", (2,)), ("_reserved", "<i4"), ("cam", "<f8", (3,))])
+RECOVERED = np.dtype([("index_lost", "<i4"), ("distance", "<i4"), ("xl", "<f4"), ("yl", "<f4"), ("xr", "<f4"),
+                      ("yr", "<f4"), ("cam", "<f8", (3,)), ("desc_left", "u1", (32,)), ("desc_right", "u1", (32,))])
+assert PREVIOUS_POINT.itemsize == 128 and TRACK.itemsize == 88 and RECOVERED.itemsize == 112
 
 
 class StereoCamera(C.Structure):
@@ -67,6 +77,12 @@ def lib():
         _lib.orc_converge.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_triangulate.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        _lib.orc_track.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_recover_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
+                                            C.c_double, C.c_void_p]
     return _lib
 
 
@@ -195,6 +211,44 @@ def stereo_compute(fl, fr, cam: StereoCamera, max_distance, min_disparity, max_e
                                  _p(winners), C.byref(nw))
     return {"matches": matches[:n].copy(), "winners": winners[:nw.value].copy(),
             "remaining_left": fl[:nl.value].copy(), "remaining_right": fr[:nr.value].copy()}
+
+
+def track(fl, fr, rows, cols, cam: StereoCamera, previous, T, track_by_appearance, tracking_distance_pixels,
+          max_distance_tracking, max_distance_triangulation, min_disparity):
+    """StereoFramePointGenerator::track -> dict(tracks, lost, matched_left, matched_right, tracked_landmarks,
+    accumulated_distance); matched_* are flags over the positions of fl / fr (what prune() removes)"""
+    fl = np.ascontiguousarray(fl, FEATURE)
+    fr = np.ascontiguousarray(fr, FEATURE)
+    previous = np.ascontiguousarray(previous, PREVIOUS_POINT)
+    T = np.ascontiguousarray(T, np.float64).reshape(12)
+    n = len(previous)
+    tracks = np.zeros(max(n, 1), TRACK)
+    lost = np.zeros(max(n, 1), np.int32)
+    ml = np.zeros(max(len(fl), 1), np.uint8)
+    mr = np.zeros(max(len(fr), 1), np.uint8)
+    n_lost, n_lm, acc = C.c_int(), C.c_int(), C.c_double()
+    nt = lib().orc_track(_p(fl), len(fl), _p(fr), len(fr), int(rows), int(cols), C.byref(cam), _p(previous), n, _p(T),
+                         int(bool(track_by_appearance)), int(tracking_distance_pixels), float(max_distance_tracking),
+                         float(max_distance_triangulation), float(min_disparity), _p(tracks), _p(lost),
+                         C.byref(n_lost), _p(ml), _p(mr), C.byref(n_lm), C.byref(acc))
+    return {"tracks": tracks[:nt].copy(), "lost": lost[:n_lost.value].copy(), "matched_left": ml[:len(fl)].astype(bool),
+            "matched_right": mr[:len(fr)].astype(bool), "tracked_landmarks": n_lm.value,
+            "accumulated_distance": acc.value}
+
+
+def recover_points(blurred_left, blurred_right, cam: StereoCamera, lost, world_to_camera_left, min_depth, max_depth,
+                   max_distance_tracking, max_distance_triangulation, min_disparity):
+    """StereoFramePointGenerator::recoverPoints -> RECOVERED records"""
+    bl, br = _img(blurred_left), _img(blurred_right)
+    assert bl.shape == br.shape and bl.strides == br.strides
+    rows, cols = bl.shape
+    lost = np.ascontiguousarray(lost, PREVIOUS_POINT)
+    W = np.ascontiguousarray(world_to_camera_left, np.float64).reshape(12)
+    out = np.zeros(max(len(lost), 1), RECOVERED)
+    n = lib().orc_recover_points(_p(bl), _p(br), bl.strides[0], rows, cols, C.byref(cam), _p(lost), len(lost), _p(W),
+                                 float(min_depth), float(max_depth), float(max_distance_tracking),
+                                 float(max_distance_triangulation), float(min_disparity), _p(out))
+    return out[:n].copy()
 
 
 # ------------------------------------------------------------------------------------------------
