@@ -147,6 +147,68 @@ int vslam_fpg_get_detection_stats(vslam_fpg* h, int32_t* counts_left, int32_t* c
  * next compute().  Without this call every feature of initialize() takes part (first frame / Localizing restart). */
 int vslam_fpg_set_remaining_features(vslam_fpg* h, int side, const vslam_keypoint* remaining, int32_t n);
 
+/* What track() and recoverPoints() read of one FramePoint of the previous frame
+ * (stereo_framepoint_generator.cpp:494-606, 702-835; src/types/frame_point.h) */
+typedef struct {
+  double camera_left[3];        /* cameraCoordinatesLeft()                                   (track) */
+  double world[3];              /* landmark()->coordinates(), world frame                    (recoverPoints) */
+  uint8_t descriptor_left[32];  /* descriptorLeft() */
+  uint8_t descriptor_right[32]; /* descriptorRight() */
+  int32_t epipolar_offset;      /* epipolarOffset() */
+  int32_t has_landmark;         /* landmark() != nullptr */
+  float keypoint_size;          /* keypointLeft().size (7 for cv::FAST keypoints)            (recoverPoints) */
+  int32_t reserved;
+} vslam_previous_point;
+
+/* one tracked and triangulated point: the arguments of Frame::createFramepoint(feature_left, feature_right,
+ * descriptor_distance_best, getPointInLeftCamera(...), point_previous) and the setters behind it (:623-643) */
+typedef struct {
+  int32_t index_previous;          /* position of point_previous in frame_previous->points() */
+  int32_t index_left, index_right; /* rows of keypointsLeft()/descriptorsLeft() resp. Right (reference order) */
+  float xl, yl, xr, yr;            /* keypoint.pt of both features */
+  int32_t distance;                /* descriptor_distance_best (of the right search, :584-590) */
+  int32_t epipolar_offset;         /* setEpipolarOffset(feature_right->row - feature_left->row) */
+  float projection_left[2];        /* setProjectionEstimateLeft */
+  float projection_right[2];       /* setProjectionEstimateRight */
+  float projection_right_corrected[2]; /* setProjectionEstimateRightCorrected */
+  int32_t reserved;
+  double camera[3];                /* getPointInLeftCamera */
+} vslam_track;
+
+/* one recovered point (:840-858): keypoints at the rounded projections, the two new descriptors, their distance */
+typedef struct {
+  int32_t index_lost;              /* position in the lost-point array */
+  int32_t distance;                /* descriptor_distance_triangulation */
+  float xl, yl, xr, yr;
+  double camera[3];
+  uint8_t descriptor_left[32], descriptor_right[32];
+} vslam_recovered_point;
+
+/* StereoFramePointGenerator::track(frame, frame_previous, camera_left_previous_in_current, lost_points,
+ * track_by_appearance), :464-681, after initialize() of the current frame.  projection_tracking_distance_pixels and
+ * maximum_descriptor_distance_tracking are what setProjectionTrackingDistancePixels /
+ * setMaximumDescriptorDistanceTracking (base_framepoint_generator.h:164-165) set before the call.
+ * tracks: frame->points() after the call, in order.  lost: positions (in `previous`) of lost_points_, in order.
+ * average_descriptor_distance: what setAverageDescriptorDistanceTracking receives (NaN without tracks).
+ * The matched features (and the right features in the parallax ranges) are pruned on the device exactly like
+ * :671-672, so the next compute() scans only the rest; no vslam_fpg_set_remaining_features call is needed. */
+int vslam_fpg_track(vslam_fpg* h, const vslam_previous_point* previous, int32_t n_previous,
+                    const double previous_to_current[12], int track_by_appearance,
+                    int32_t projection_tracking_distance_pixels, double maximum_descriptor_distance_tracking,
+                    vslam_track* tracks, int32_t capacity, int32_t* n_tracks, int32_t* lost, int32_t* n_lost,
+                    int32_t* n_tracked_landmarks, double* average_descriptor_distance);
+
+/* StereoFramePointGenerator::recoverPoints(frame, lost_points), :683-869, with the ORB extractor.  recovered: the
+ * points appended to frame->points(), in order.  minimum/maximum_depth_meters: parameters.h:197-198. */
+int vslam_fpg_recover_points(vslam_fpg* h, const vslam_previous_point* lost, int32_t n_lost,
+                             const double world_to_camera_left[12], double minimum_depth_meters,
+                             double maximum_depth_meters, double maximum_descriptor_distance_tracking,
+                             vslam_recovered_point* recovered, int32_t capacity, int32_t* n_recovered);
+
+/* pass as n_tracked (tracked = NULL) to vslam_fpg_compute: the tracked points are those of the last
+ * vslam_fpg_track, already resident on the device (no host round trip of the bin pre-load records) */
+#define VSLAM_TRACKED_FROM_LAST_TRACK (-1)
+
 /* StereoFramePointGenerator::compute(frame), :135-462 (without the dead use_matches block :168-273).
  * tracked: the points already in frame->points().  framepoints: the points compute() appends to
  * frame->points(), in order (bin winners without previous(), row-major over bins; every match in emission

@@ -1,9 +1,9 @@
 """ctypes binding of libvslam_b200.so (include/vslam_b200.h) and a thin Python mirror of the reference's plugin
 interface for the hot path, used by the tests and bench.py:
 
-    StereoFramePointGenerator.{configure (ctor), initialize, compute, track: n/a}   <- BaseFramePointGenerator
+    StereoFramePointGenerator.{configure (ctor), initialize, track, compute, recoverPoints}  <- BaseFramePointGenerator
         (/root/reference/src/framepoint_generation/base_framepoint_generator.h:110-234,
-         stereo_framepoint_generator.cpp:16-60,73-133,135-462)
+         stereo_framepoint_generator.cpp:16-60,73-133,135-462,464-681,683-869)
     StereoUVAligner / UVDAligner.{initialize, linearize, oneRound, converge, errors, inliers, ...}  <- BaseFrameAligner
         (/root/reference/src/aligners/base_aligner.h:7-71, base_frame_aligner.h:8-41)
 
@@ -25,13 +25,25 @@ FRAMEPOINT = np.dtype([("index_left", "<i4"), ("index_right", "<i4"), ("xl", "<f
                        ("yr", "<f4"), ("distance", "<i4"), ("epipolar_offset", "<i4"), ("camera", "<f8", (3,))])
 TRACKED = np.dtype([("row", "<i4"), ("col", "<i4"), ("has_previous", "<i4"), ("reserved", "<i4"),
                     ("disparity", "<f8"), ("distance", "<f8")])
+PREVIOUS_POINT = np.dtype([("camera_left", "<f8", (3,)), ("world", "<f8", (3,)), ("descriptor_left", "u1", (32,)),
+                           ("descriptor_right", "u1", (32,)), ("epipolar_offset", "<i4"), ("has_landmark", "<i4"),
+                           ("keypoint_size", "<f4"), ("reserved", "<i4")])
+TRACK = np.dtype([("index_previous", "<i4"), ("index_left", "<i4"), ("index_right", "<i4"), ("xl", "<f4"),
+                  ("yl", "<f4"), ("xr", "<f4"), ("yr", "<f4"), ("distance", "<i4"), ("epipolar_offset", "<i4"),
+                  ("projection_left", "<f4", (2,)), ("projection_right", "<f4", (2,)),
+                  ("projection_right_corrected", "<f4", (2,)), ("reserved", "<i4"), ("camera", "<f8", (3,))])
+RECOVERED = np.dtype([("index_lost", "<i4"), ("distance", "<i4"), ("xl", "<f4"), ("yl", "<f4"), ("xr", "<f4"),
+                      ("yr", "<f4"), ("camera", "<f8", (3,)), ("descriptor_left", "u1", (32,)),
+                      ("descriptor_right", "u1", (32,))])
 assert FRAMEPOINT.itemsize == 56 and TRACKED.itemsize == 32
+assert PREVIOUS_POINT.itemsize == 128 and TRACK.itemsize == 88 and RECOVERED.itemsize == 112
+TRACKED_FROM_LAST_TRACK = -1
 
 # every symbol include/vslam_b200.h declares (tests check that the library exports each one)
 EXPORTS = """vslam_last_error vslam_version vslam_device_count vslam_host_alloc vslam_host_free
 vslam_fpg_create vslam_fpg_destroy vslam_fpg_info vslam_fpg_get_thresholds vslam_fpg_set_thresholds
 vslam_fpg_initialize vslam_fpg_get_features vslam_fpg_get_detection_stats vslam_fpg_set_remaining_features
-vslam_fpg_compute vslam_fpg_get_matches
+vslam_fpg_compute vslam_fpg_get_matches vslam_fpg_track vslam_fpg_recover_points
 vslam_fpg_set_profiling vslam_fpg_get_time_consumption vslam_fpg_batch_upload vslam_fpg_batch_run
 vslam_fpg_batch_download vslam_fpg_batch_process vslam_fpg_batch_linearize vslam_fpg_batch_get_systems
 vslam_fpg_get_kernel_profile vslam_fpg_batch_get_features vslam_fpg_stream vslam_fpg_synchronize
@@ -104,6 +116,8 @@ def lib():
         L.vslam_fpg_compute.argtypes = [vp, vp, i32, vp, i32, vp, vp]
         L.vslam_fpg_set_remaining_features.argtypes = [vp, C.c_int, vp, i32]
         L.vslam_fpg_get_matches.argtypes = [vp, vp, i32, vp]
+        L.vslam_fpg_track.argtypes = [vp, vp, i32, vp, C.c_int, i32, C.c_double, vp, i32, vp, vp, vp, vp, vp]
+        L.vslam_fpg_recover_points.argtypes = [vp, vp, i32, vp, C.c_double, C.c_double, C.c_double, vp, i32, vp]
         L.vslam_fpg_set_profiling.argtypes = [vp, C.c_int]
         L.vslam_fpg_get_time_consumption.argtypes = [vp, vp, vp, vp]
         L.vslam_fpg_batch_upload.argtypes = [vp, i32, vp, vp, sz, sz]
@@ -257,8 +271,48 @@ class StereoFramePointGenerator:
         k = np.ascontiguousarray(keypoints, KEYPOINT)
         _check(lib().vslam_fpg_set_remaining_features(self._h, side, _p(k) if len(k) else None, len(k)))
 
+    # -- StereoFramePointGenerator::track(frame, frame_previous, previous_to_current, lost_points, by_appearance)
+    def track(self, previous, previous_to_current, track_by_appearance, projection_tracking_distance_pixels,
+              maximum_descriptor_distance_tracking):
+        """-> dict(tracks, lost, tracked_landmarks, average_descriptor_distance); the matched features are pruned on
+        the device, `compute(TRACKED_FROM_LAST_TRACK)` then pre-loads the tracks into the bins without a round trip"""
+        previous = np.ascontiguousarray(previous, PREVIOUS_POINT)
+        T = np.ascontiguousarray(previous_to_current, np.float64).reshape(12)
+        n = len(previous)
+        tracks = np.zeros(max(n, 1), TRACK)
+        lost = np.zeros(max(n, 1), np.int32)
+        nt, nl, nlm, avg = C.c_int32(), C.c_int32(), C.c_int32(), C.c_double()
+        _check(lib().vslam_fpg_track(self._h, _p(previous) if n else None, n, _p(T), int(bool(track_by_appearance)),
+                                     int(projection_tracking_distance_pixels),
+                                     float(maximum_descriptor_distance_tracking), _p(tracks), len(tracks), C.byref(nt),
+                                     _p(lost), C.byref(nl), C.byref(nlm), C.byref(avg)))
+        return {"tracks": tracks[:nt.value].copy(), "lost": lost[:nl.value].copy(), "tracked_landmarks": nlm.value,
+                "average_descriptor_distance": avg.value}
+
+    # -- StereoFramePointGenerator::recoverPoints(frame, lost_points)
+    def recover_points(self, lost, world_to_camera_left, maximum_descriptor_distance_tracking, minimum_depth=0.1,
+                       maximum_depth=1000.0):
+        lost = np.ascontiguousarray(lost, PREVIOUS_POINT)
+        W = np.ascontiguousarray(world_to_camera_left, np.float64).reshape(12)
+        out = np.zeros(max(len(lost), 1), RECOVERED)
+        n = C.c_int32()
+        _check(lib().vslam_fpg_recover_points(self._h, _p(lost) if len(lost) else None, len(lost), _p(W),
+                                              float(minimum_depth), float(maximum_depth),
+                                              float(maximum_descriptor_distance_tracking), _p(out), len(out),
+                                              C.byref(n)))
+        return out[:n.value].copy()
+
     # -- StereoFramePointGenerator::compute(frame)
     def compute(self, tracked=None):
+        """tracked: TRACKED records of the points already in frame->points(), or TRACKED_FROM_LAST_TRACK"""
+        if isinstance(tracked, int) and tracked == TRACKED_FROM_LAST_TRACK:
+            cap = self.out_capacity
+            out = np.zeros(cap, FRAMEPOINT)
+            n, nm = C.c_int32(), C.c_int32()
+            _check(lib().vslam_fpg_compute(self._h, None, TRACKED_FROM_LAST_TRACK, _p(out), cap, C.byref(n),
+                                           C.byref(nm)))
+            self.number_of_matches = nm.value
+            return out[:n.value].copy()
         tracked = np.zeros(0, TRACKED) if tracked is None else np.ascontiguousarray(tracked, TRACKED)
         cap = self.out_capacity + len(tracked)
         out = np.zeros(cap, FRAMEPOINT)

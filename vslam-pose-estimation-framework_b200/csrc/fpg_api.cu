@@ -22,6 +22,9 @@ using namespace vslam;
 
 static_assert(sizeof(FramePointRecord) == sizeof(vslam_framepoint), "record layout");
 static_assert(sizeof(TrackedPoint) == sizeof(vslam_tracked_point), "tracked layout");
+static_assert(sizeof(PreviousPoint) == sizeof(vslam_previous_point) && sizeof(PreviousPoint) == 128, "previous point layout");
+static_assert(sizeof(TrackRecord) == sizeof(vslam_track) && sizeof(TrackRecord) == 88, "track layout");
+static_assert(sizeof(RecoveredRecord) == sizeof(vslam_recovered_point) && sizeof(RecoveredRecord) == 112, "recovered layout");
 
 namespace {
 
@@ -89,6 +92,18 @@ struct vslam_fpg {
   double* d_pair_errors = nullptr;    // [max_batch][out_cap]
   uint8_t* d_pair_inliers = nullptr;  // [max_batch][out_cap]
   double* h_systems = nullptr;        // pinned [max_batch][32]
+  // track() / recoverPoints() (single pair)
+  PreviousPoint* d_previous = nullptr;   // [previous_cap]
+  int previous_cap = 0;
+  TrackScratch track_scratch = {};
+  TrackRecord* d_tracks = nullptr;       // [previous_cap]
+  int32_t* d_lost = nullptr;             // [previous_cap]
+  int32_t* h_track_stats = nullptr;      // pinned [4]
+  int n_device_tracks = -1;              // tracks of the last vslam_fpg_track still valid for compute()
+  uint32_t* d_recover_xy = nullptr;      // [2][previous_cap]
+  uint8_t* d_recover_desc = nullptr;     // [2][previous_cap][32] + [previous_cap] flags
+  RecoveredRecord* d_recovered = nullptr;
+  int32_t* d_recover_n = nullptr;        // {n_xy left, n_xy right, n_recovered}
 };
 
 namespace {
@@ -428,6 +443,10 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
   dalloc((void**)&h->d_systems, B * 32 * sizeof(double));
   dalloc((void**)&h->d_pair_errors, B * h->out_cap * sizeof(double));
   dalloc((void**)&h->d_pair_inliers, B * h->out_cap);
+  dalloc((void**)&h->track_scratch.claim_l, (size_t)g.cap * sizeof(int32_t));
+  dalloc((void**)&h->track_scratch.claim_r, (size_t)g.cap * sizeof(int32_t));
+  dalloc((void**)&h->track_scratch.stats, 4 * sizeof(int32_t));
+  dalloc((void**)&h->d_recover_n, 4 * sizeof(int32_t));
   for (int l = 0; l < kLanes; ++l) {
     dalloc((void**)&h->lanes[l].blurred, (size_t)2 * h->chunk * img_bytes);
     dalloc((void**)&h->lanes[l].mask, (size_t)2 * h->chunk * g.rows * g.mask_words * sizeof(uint32_t));
@@ -441,6 +460,7 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
   halloc((void**)&h->h_n_out, B * 2 * sizeof(int32_t));
   halloc((void**)&h->h_flag, sizeof(int32_t));
   halloc((void**)&h->h_systems, B * 32 * sizeof(double));
+  halloc((void**)&h->h_track_stats, 4 * sizeof(int32_t));
   for (auto& e : h->clock.ev)
     if (ok && cudaEventCreate(&e) != cudaSuccess) ok = false;
   if (ok && cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming) != cudaSuccess) ok = false;
@@ -473,6 +493,10 @@ int vslam_fpg_destroy(vslam_fpg* h) {
     if (l.stream) cudaStreamDestroy(l.stream);
   }
   cudaFree(h->d_systems); cudaFree(h->d_pair_errors); cudaFree(h->d_pair_inliers);
+  cudaFree(h->d_previous); cudaFree(h->track_scratch.tentative); cudaFree(h->track_scratch.claim_l);
+  cudaFree(h->track_scratch.claim_r); cudaFree(h->track_scratch.stats); cudaFree(h->d_tracks); cudaFree(h->d_lost);
+  cudaFree(h->d_recover_xy); cudaFree(h->d_recover_desc); cudaFree(h->d_recovered); cudaFree(h->d_recover_n);
+  cudaFreeHost(h->h_track_stats);
   cudaFreeHost(h->h_counts); cudaFreeHost(h->h_n_desc); cudaFreeHost(h->h_n_out); cudaFreeHost(h->h_flag);
   cudaFreeHost(h->h_systems);
   for (auto& e : h->clock.ev)
@@ -548,6 +572,7 @@ int vslam_fpg_initialize(vslam_fpg* h, const uint8_t* left, const uint8_t* right
   h->matching_distance = host_matching_distance(h, h->localizing, h->h_n_desc[0]);
   h->initialized = true;
   h->last_pairs = 1;
+  h->n_device_tracks = -1;
   if (n_left) *n_left = h->h_n_desc[0];
   if (n_right) *n_right = h->h_n_desc[1];
   return VSLAM_OK;
@@ -579,22 +604,30 @@ int vslam_fpg_compute(vslam_fpg* h, const vslam_tracked_point* tracked, int32_t 
                       int32_t capacity, int32_t* n_out, int32_t* n_matches) {
   if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "StereoFramePointGenerator::compute|called with empty frame");
   if (!h->initialized || h->last_pairs != 1) return fail(VSLAM_ERR_STATE, "compute without initialize");
-  if (n_tracked < 0 || (n_tracked > 0 && !tracked)) return fail(VSLAM_ERR_INVALID_ARGUMENT, "bad tracked points");
+  const bool device_tracks = n_tracked == VSLAM_TRACKED_FROM_LAST_TRACK;
+  if (device_tracks) {
+    if (h->n_device_tracks < 0) return fail(VSLAM_ERR_STATE, "VSLAM_TRACKED_FROM_LAST_TRACK without vslam_fpg_track on this frame");
+    n_tracked = h->n_device_tracks;
+    tracked = nullptr;
+  } else if (n_tracked < 0 || (n_tracked > 0 && !tracked)) {
+    return fail(VSLAM_ERR_INVALID_ARGUMENT, "bad tracked points");
+  }
   CUDA_TRY(cudaSetDevice(h->device));
   Lane& lane = h->lanes[0];
-  if (n_tracked > h->tracked_cap) {
+  if (!device_tracks) h->n_device_tracks = -1;   // d_tracked is about to be overwritten
+  if (!device_tracks && n_tracked > h->tracked_cap) {
     cudaFree(h->d_tracked);
     h->d_tracked = nullptr;
     h->tracked_cap = 0;
     CUDA_TRY(cudaMalloc((void**)&h->d_tracked, sizeof(TrackedPoint) * (size_t)n_tracked * 2));
     h->tracked_cap = n_tracked * 2;
   }
-  if (n_tracked)
+  if (n_tracked && !device_tracks)
     CUDA_TRY(cudaMemcpyAsync(h->d_tracked, tracked, sizeof(TrackedPoint) * n_tracked, cudaMemcpyHostToDevice, lane.stream));
   // the strip kernel keeps bin state in float: exact for everything the stereo path produces (disparities are float
   // differences, distances Hamming counts); other values take the generic double-precision kernel
   bool generic = false;
-  for (int32_t i = 0; i < n_tracked && !generic; ++i)
+  for (int32_t i = 0; i < n_tracked && !generic && !device_tracks; ++i)
     generic = (double)(float)tracked[i].disparity != tracked[i].disparity ||
               (double)(float)tracked[i].distance != tracked[i].distance || tracked[i].distance < 0 ||
               tracked[i].row < 0 || tracked[i].col < 0;
@@ -625,6 +658,118 @@ int vslam_fpg_compute(vslam_fpg* h, const vslam_tracked_point* tracked, int32_t 
   if (n && !out) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null output");
   if (n) CUDA_TRY(cudaMemcpy(out, src, sizeof(FramePointRecord) * n, cudaMemcpyDeviceToHost));
   return remap_records(h, 0, out, n);
+}
+
+// grows the per-previous-point buffers of track() / recoverPoints()
+static int ensure_previous_capacity(vslam_fpg* h, int n) {
+  if (n <= h->previous_cap) return VSLAM_OK;
+  CUDA_TRY(cudaStreamSynchronize(h->lanes[0].stream));
+  const int cap = std::max(2 * n, 1024);
+  cudaFree(h->d_previous); cudaFree(h->track_scratch.tentative); cudaFree(h->d_tracks); cudaFree(h->d_lost);
+  cudaFree(h->d_recover_xy); cudaFree(h->d_recover_desc); cudaFree(h->d_recovered);
+  h->d_previous = nullptr; h->track_scratch.tentative = nullptr; h->d_tracks = nullptr; h->d_lost = nullptr;
+  h->d_recover_xy = nullptr; h->d_recover_desc = nullptr; h->d_recovered = nullptr;
+  h->previous_cap = 0;
+  CUDA_TRY(cudaMalloc((void**)&h->d_previous, sizeof(PreviousPoint) * (size_t)cap));
+  CUDA_TRY(cudaMalloc((void**)&h->track_scratch.tentative, sizeof(int4) * (size_t)cap));
+  CUDA_TRY(cudaMalloc((void**)&h->d_tracks, sizeof(TrackRecord) * (size_t)cap));
+  CUDA_TRY(cudaMalloc((void**)&h->d_lost, sizeof(int32_t) * (size_t)cap));
+  CUDA_TRY(cudaMalloc((void**)&h->d_recover_xy, sizeof(uint32_t) * 2 * (size_t)cap));
+  CUDA_TRY(cudaMalloc((void**)&h->d_recover_desc, (size_t)cap * (2 * kDescBytes + 1)));
+  CUDA_TRY(cudaMalloc((void**)&h->d_recovered, sizeof(RecoveredRecord) * (size_t)cap));
+  h->previous_cap = cap;
+  if (cap > h->tracked_cap) {
+    cudaFree(h->d_tracked);
+    h->d_tracked = nullptr;
+    h->tracked_cap = 0;
+    CUDA_TRY(cudaMalloc((void**)&h->d_tracked, sizeof(TrackedPoint) * (size_t)cap));
+    h->tracked_cap = cap;
+  }
+  return VSLAM_OK;
+}
+
+int vslam_fpg_track(vslam_fpg* h, const vslam_previous_point* previous, int32_t n_previous, const double T[12],
+                    int track_by_appearance, int32_t projection_tracking_distance_pixels,
+                    double maximum_descriptor_distance_tracking, vslam_track* tracks, int32_t capacity,
+                    int32_t* n_tracks, int32_t* lost, int32_t* n_lost, int32_t* n_tracked_landmarks,
+                    double* average_descriptor_distance) {
+  if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "StereoFramePointGenerator::track|called with invalid frames");   // :468-471
+  if (!T || n_previous < 0 || (n_previous > 0 && !previous)) return fail(VSLAM_ERR_INVALID_ARGUMENT, "bad previous points / transform");
+  if (!h->initialized || h->last_pairs != 1) return fail(VSLAM_ERR_STATE, "track without initialize");
+  if (projection_tracking_distance_pixels < 0) return fail(VSLAM_ERR_INVALID_ARGUMENT, "negative tracking distance");
+  CUDA_TRY(cudaSetDevice(h->device));
+  Lane& lane = h->lanes[0];
+  int rc = ensure_previous_capacity(h, n_previous);
+  if (rc) return rc;
+  if (n_previous)
+    CUDA_TRY(cudaMemcpyAsync(h->d_previous, previous, sizeof(PreviousPoint) * (size_t)n_previous, cudaMemcpyHostToDevice, lane.stream));
+  TrackParams tp;
+  for (int i = 0; i < 12; ++i) tp.T[i] = T[i];
+  tp.by_appearance = track_by_appearance != 0;
+  tp.distance_pixels = projection_tracking_distance_pixels;
+  tp.max_distance_tracking = maximum_descriptor_distance_tracking;
+  launch_track(h->g, h->sp, h->b, 0, h->d_previous, n_previous, tp, h->track_scratch, h->d_tracks, h->d_lost,
+               h->d_tracked, lane.stream);
+  h->launches += n_previous > 0 ? 2 : 1;
+  CUDA_TRY(cudaMemcpyAsync(h->h_track_stats, h->track_scratch.stats, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, lane.stream));
+  CUDA_TRY(cudaStreamSynchronize(lane.stream));
+  CUDA_TRY(cudaGetLastError());
+  const int nt = h->h_track_stats[0], nl = h->h_track_stats[1];
+  h->n_device_tracks = nt;
+  if (n_tracks) *n_tracks = nt;
+  if (n_lost) *n_lost = nl;
+  if (n_tracked_landmarks) *n_tracked_landmarks = h->h_track_stats[2];
+  if (average_descriptor_distance)   // :666-667 (0/0 -> NaN like the reference)
+    *average_descriptor_distance = nt ? (double)h->h_track_stats[3] / (double)nt : std::nan("");
+  if (nt > capacity) return fail(VSLAM_ERR_CAPACITY, "capacity %d < %d tracks", capacity, nt);
+  if (nt && !tracks) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null output");
+  if (nt) CUDA_TRY(cudaMemcpy(tracks, h->d_tracks, sizeof(TrackRecord) * (size_t)nt, cudaMemcpyDeviceToHost));
+  if (nl && lost) CUDA_TRY(cudaMemcpy(lost, h->d_lost, sizeof(int32_t) * (size_t)nl, cudaMemcpyDeviceToHost));
+  if (h->g.n_regions > 1 && nt) {   // sorted device order -> the reference's keypoint order
+    std::vector<uint32_t> xl, xr;
+    std::vector<int> s2r_l, s2r_r, tmp;
+    if ((rc = fetch_xy(h, 0, h->h_n_desc[0], xl))) return rc;
+    if ((rc = fetch_xy(h, 1, h->h_n_desc[1], xr))) return rc;
+    reference_order(h, xl, s2r_l, tmp);
+    reference_order(h, xr, s2r_r, tmp);
+    for (int i = 0; i < nt; ++i) {
+      tracks[i].index_left = s2r_l[tracks[i].index_left];
+      tracks[i].index_right = s2r_r[tracks[i].index_right];
+    }
+  }
+  return VSLAM_OK;
+}
+
+int vslam_fpg_recover_points(vslam_fpg* h, const vslam_previous_point* lost, int32_t n_lost, const double W[12],
+                             double minimum_depth_meters, double maximum_depth_meters,
+                             double maximum_descriptor_distance_tracking, vslam_recovered_point* recovered,
+                             int32_t capacity, int32_t* n_recovered) {
+  if (!h || !W || n_lost < 0 || (n_lost > 0 && !lost)) return fail(VSLAM_ERR_INVALID_ARGUMENT, "bad arguments");
+  if (!h->initialized || h->last_pairs != 1) return fail(VSLAM_ERR_STATE, "recoverPoints without initialize");
+  CUDA_TRY(cudaSetDevice(h->device));
+  Lane& lane = h->lanes[0];
+  int rc = ensure_previous_capacity(h, n_lost);
+  if (rc) return rc;
+  if (n_lost)
+    CUDA_TRY(cudaMemcpyAsync(h->d_previous, lost, sizeof(PreviousPoint) * (size_t)n_lost, cudaMemcpyHostToDevice, lane.stream));
+  RecoverParams rp;
+  for (int i = 0; i < 12; ++i) rp.W[i] = W[i];
+  rp.min_depth = minimum_depth_meters;
+  rp.max_depth = maximum_depth_meters;
+  rp.max_distance_tracking = maximum_descriptor_distance_tracking;
+  // the blurred images of the last initialize() are still in lane 0's scratch (pair 0)
+  launch_recover(h->g, h->sp, h->b, 0, lane.blurred, h->d_previous, n_lost, rp, h->d_recover_xy, h->d_recover_n,
+                 h->d_recover_desc, h->d_recovered, h->d_recover_n + 2, lane.stream);
+  h->launches += n_lost > 0 ? 3 : 1;
+  int32_t n = 0;
+  CUDA_TRY(cudaMemcpyAsync(&n, h->d_recover_n + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, lane.stream));
+  CUDA_TRY(cudaStreamSynchronize(lane.stream));
+  CUDA_TRY(cudaGetLastError());
+  if (n_recovered) *n_recovered = n;
+  if (n > capacity) return fail(VSLAM_ERR_CAPACITY, "capacity %d < %d recovered points", capacity, n);
+  if (n && !recovered) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null output");
+  if (n) CUDA_TRY(cudaMemcpy(recovered, h->d_recovered, sizeof(RecoveredRecord) * (size_t)n, cudaMemcpyDeviceToHost));
+  return VSLAM_OK;
 }
 
 int vslam_fpg_set_remaining_features(vslam_fpg* h, int side, const vslam_keypoint* remaining, int32_t n) {

@@ -30,6 +30,51 @@ struct FramePointRecord {   // == vslam_framepoint
   double camera[3];
 };
 
+struct PreviousPoint {   // == vslam_previous_point (128 bytes)
+  double camera[3];
+  double world[3];
+  uint8_t descriptor_left[32], descriptor_right[32];
+  int32_t epipolar_offset, has_landmark;
+  float keypoint_size;
+  int32_t reserved;
+};
+
+struct TrackRecord {   // == vslam_track (88 bytes)
+  int32_t index_previous, index_left, index_right;
+  float xl, yl, xr, yr;
+  int32_t distance, epipolar_offset;
+  float projection_left[2], projection_right[2], projection_right_corrected[2];
+  int32_t reserved;
+  double camera[3];
+};
+
+struct RecoveredRecord {   // == vslam_recovered_point (112 bytes)
+  int32_t index_lost, distance;
+  float xl, yl, xr, yr;
+  double camera[3];
+  uint8_t descriptor_left[32], descriptor_right[32];
+};
+
+struct TrackParams {
+  double T[12];                    // camera_left_previous_in_current, row-major 3x4
+  int by_appearance;               // track_by_appearance_
+  int distance_pixels;             // _projection_tracking_distance_pixels
+  double max_distance_tracking;    // _maximum_descriptor_distance_tracking
+};
+
+struct TrackScratch {
+  int4* tentative;       // [n_previous] {sorted left feature | -1, sorted right feature | -1, distance, status}
+  int32_t* claim_l;      // [cap] lowest previous-point index that consumes the left feature
+  int32_t* claim_r;      // [cap]
+  int32_t* stats;        // [4] {tracks, lost, tracked landmarks, accumulated distance}
+};
+
+struct RecoverParams {
+  double W[12];                    // world_to_camera_left
+  double min_depth, max_depth;     // minimum_depth_meters / maximum_depth_meters
+  double max_distance_tracking;
+};
+
 // all launches are asynchronous on `stream`; image ranges are [first_image, first_image + n_images)
 // dense host-layout images (row stride `stride` bytes, any alignment) -> pitched device images [pair][side][row][pitch]
 void launch_repitch(const Geometry& g, const uint8_t* left, const uint8_t* right, int stride, uint8_t* image,
@@ -50,6 +95,19 @@ void launch_select(const Geometry& g, const StereoParams& sp, const Buffers& b, 
 void launch_emit_matches(const Geometry& g, const StereoParams& sp, const Buffers& b, int pair, int n_passes,
                          FramePointRecord* out, int out_capacity, int32_t* n_out, cudaStream_t stream);
 int kernels_per_match_pass();
+// rBRIEF-256 at arbitrary interior pixels of `n_images` blurred images: image i reads xy[i * stride .. + n[i]) and
+// writes desc[(i * stride + k) * 32]
+void launch_describe_at(const Geometry& g, const uint8_t* blurred, const uint32_t* xy, const int32_t* n, uint8_t* desc,
+                        int stride, int n_images, cudaStream_t stream);
+// StereoFramePointGenerator::track for pair `pair`: two launches (parallel search, ordered resolution).  Marks the
+// consumed features in pruned_l / consumed_r, writes tracks / lost (ordered), the bin pre-load records and stats.
+void launch_track(const Geometry& g, const StereoParams& sp, const Buffers& b, int pair, const PreviousPoint* previous,
+                  int n_previous, const TrackParams& tp, const TrackScratch& scratch, TrackRecord* tracks,
+                  int32_t* lost, TrackedPoint* tracked, cudaStream_t stream);
+// StereoFramePointGenerator::recoverPoints for pair `pair` (blurred images at `blurred`): three launches
+void launch_recover(const Geometry& g, const StereoParams& sp, const Buffers& b, int pair, const uint8_t* blurred,
+                    const PreviousPoint* lost, int n_lost, const RecoverParams& rp, uint32_t* xy, int32_t* n_xy,
+                    uint8_t* desc, RecoveredRecord* out, int32_t* n_out, cudaStream_t stream);
 
 // ---- aligner ----
 struct AlignerBuffers {

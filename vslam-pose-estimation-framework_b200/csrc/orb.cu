@@ -174,15 +174,15 @@ __device__ __forceinline__ uint32_t brief_word(const uint8_t* c) {
 __global__ void __launch_bounds__(DWARPS * 32) describe_kernel(Geometry g, const uint8_t* __restrict__ blurred,
                                                                 const uint32_t* __restrict__ kp_xy,
                                                                 const int32_t* __restrict__ n_desc,
-                                                                uint8_t* __restrict__ desc) {
+                                                                uint8_t* __restrict__ desc, int kp_stride) {
   extern __shared__ __align__(16) uint8_t s_patches[];
   const int img = blockIdx.y;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int n = n_desc[img];
   const int warp = blockIdx.x * DWARPS + wib, n_warps = gridDim.x * DWARPS;
   const uint8_t* base = blurred + (size_t)img * g.rows * g.pitch;
-  const uint32_t* xy = kp_xy + (size_t)img * g.cap;
-  uint4* out = reinterpret_cast<uint4*>(desc + (size_t)img * g.cap * kDescBytes);
+  const uint32_t* xy = kp_xy + (size_t)img * kp_stride;
+  uint4* out = reinterpret_cast<uint4*>(desc + (size_t)img * kp_stride * kDescBytes);
   uint8_t* mine = s_patches + (size_t)(wib * 32 + lane) * PSTRIDE;
   uint8_t* warp_patches = s_patches + (size_t)(wib * 32) * PSTRIDE;
 
@@ -260,16 +260,30 @@ void launch_blur(const Geometry& g, const Buffers& b, int first_image, int n_ima
                                         b.blurred + (size_t)first_image * g.rows * g.pitch);
 }
 
-void launch_describe(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream) {
-  static bool configured = false;   // opt in to > 48 KB dynamic shared memory once per process (per device context)
-  if (!configured) {
+// opt in to > 48 KB dynamic shared memory once per device
+static void configure_describe() {
+  static unsigned long long configured = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 64 || !((configured >> dev) & 1ull)) {
     cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DSMEM);
-    configured = true;
+    if (dev < 64) configured |= 1ull << dev;
   }
+}
+
+void launch_describe(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream) {
+  configure_describe();
   dim3 grid(n_images <= 8 ? 24 : 12, n_images);
   describe_kernel<<<grid, DWARPS * 32, DSMEM, stream>>>(g, b.blurred + (size_t)first_image * g.rows * g.pitch,
                                             b.kp_xy + (size_t)first_image * g.cap, b.n_desc + first_image,
-                                            b.desc + (size_t)first_image * g.cap * kDescBytes);
+                                            b.desc + (size_t)first_image * g.cap * kDescBytes, g.cap);
+}
+
+void launch_describe_at(const Geometry& g, const uint8_t* blurred, const uint32_t* xy, const int32_t* n, uint8_t* desc,
+                        int stride, int n_images, cudaStream_t stream) {
+  configure_describe();
+  dim3 grid(8, n_images);
+  describe_kernel<<<grid, DWARPS * 32, DSMEM, stream>>>(g, blurred, xy, n, desc, stride);
 }
 
 }  // namespace vslam

@@ -14,23 +14,11 @@
 //   * the bin rule is order dependent (partial-order dominance): one thread per bin replays that bin's candidates in
 //     emission order (pass, row, col).
 #include "kernels.cuh"
+#include "stereo_device.cuh"
 
 namespace vslam {
 
 namespace {
-
-// stereo_framepoint_generator.cpp:109-125 ; 0.1 * SRRG_PROSLAM_DESCRIPTOR_SIZE_BITS with 256 bits
-__device__ __forceinline__ double triangulation_threshold(const StereoParams& sp, int n_left) {
-  const double tenth = __dmul_rn(0.1, 256.0);
-  if (sp.localizing) return fmin(tenth, sp.max_matching_distance);
-  const double ratio = fmin(__ddiv_rn((double)n_left, (double)sp.target_keypoints), 1.0);
-  return fmax(__dmul_rn(ratio, sp.max_matching_distance), tenth);
-}
-
-__device__ __forceinline__ int popc256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
-  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
-         __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
-}
 
 __global__ void __launch_bounds__(256) match_kernel(Geometry g, StereoParams sp, const int32_t* __restrict__ row_ptr,
                                                     const uint32_t* __restrict__ kp_xy,
@@ -139,15 +127,6 @@ __global__ void __launch_bounds__(256) match_kernel(Geometry g, StereoParams sp,
     }
     cursor = s + 1;                                                          // :414
   }
-}
-
-// stereo_framepoint_generator.cpp:871-895 ; x, y are integer-valued floats
-__device__ __forceinline__ void triangulate(const StereoParams& sp, float xl, float yl, float xr, float yr,
-                                            double out[3]) {
-  const double z = __ddiv_rn(sp.bx, (double)__fsub_rn(xr, xl));
-  out[0] = __dmul_rn(__dmul_rn(__ddiv_rn(1.0, sp.fx), __dsub_rn((double)xl, sp.cx)), z);
-  out[1] = __dmul_rn(__dmul_rn(__ddiv_rn(1.0, sp.fy), __dsub_rn(__ddiv_rn((double)__fadd_rn(yl, yr), 2.0), sp.cy)), z);
-  out[2] = z;
 }
 
 __device__ __forceinline__ void write_record(const StereoParams& sp, FramePointRecord* o, int i, int s, int dist,

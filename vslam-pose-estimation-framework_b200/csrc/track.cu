@@ -1,0 +1,482 @@
+// track.cu -- StereoFramePointGenerator::track and ::recoverPoints on the device
+// (reference src/framepoint_generation/stereo_framepoint_generator.cpp:464-681, 683-869 and
+// IntensityFeatureMatcher::getMatchingFeatureInRectangularRegion, intensity_feature_matcher.cpp:81-148).
+//
+// track() is sequential over the previous frame's points: a point that is tracked AND triangulated removes its left
+// feature, its right feature and the right features in its parallax range from the lattices, so later points cannot
+// pick them.  Removing a feature changes another point's result only if it was that point's chosen left or right
+// feature (an argmin with first-wins ties does not move when a loser disappears).  Hence:
+//
+//   K9  track_search_kernel   one warp per previous point, all points in parallel against the UNCONSUMED lattices:
+//                             projection, rectangular window search (popc-256, warp argmin), corrected right window.
+//   K10 track_resolve_kernel  one CTA per frame.  Every tentative success claims its features with atomicMin(point
+//                             index).  A point is DIRTY when a lower-indexed point claims one of the (at most two)
+//                             features its result depends on.  The points below the lowest dirty index are exactly
+//                             what the sequential loop produces; they are committed, the dirty point is recomputed by
+//                             one warp against the committed lattices (now exact for it), its new claims are added,
+//                             and the scan continues behind it.  Stale claims only cause a redundant recompute.
+//                             The kernel then emits tracks / lost points in order and the bin pre-load records.
+//
+// The lattice of the reference is replaced by the (row, col)-sorted feature arrays + CSR row pointers: a window's rows
+// are one contiguous index range, scanned in the reference's row-major order (ties resolve to the lowest index).
+#include "kernels.cuh"
+#include "stereo_device.cuh"
+
+namespace vslam {
+
+namespace {
+
+constexpr int kStatusSkipped = 0;   // left the loop body through `continue`: neither tracked nor lost
+constexpr int kStatusLost = 1;      // reached :660-663 without a track
+constexpr int kStatusTracked = 2;
+
+struct TrackView {
+  const int32_t* rpl;
+  const int32_t* rpr;
+  const uint32_t* xyl;
+  const uint32_t* xyr;
+  const uint4* dl;
+  const uint4* dr;
+  const uint8_t* gone_l;   // read with ld.cg: the resolve kernel updates them between recomputes
+  const uint8_t* gone_r;
+  int rows, cols;
+  double fx, fy, cx, cy, bx;
+  double threshold_triangulation;   // _current_maximum_descriptor_distance_triangulation
+  double min_disparity;
+};
+
+struct Projection {
+  int32_t col_l, row_l, col_r, row_r;
+  float right_x, right_y;
+};
+
+// intensity_feature_matcher.cpp:81-148, warp-cooperative.  Returns the sorted index of the chosen feature or -1;
+// *distance = descriptor_distance_best_ of the chosen feature.
+__device__ int search_region(const int32_t* __restrict__ row_ptr, const uint32_t* __restrict__ xy,
+                             const uint4* __restrict__ desc, const uint8_t* gone, int row_reference, int col_reference,
+                             const uint4& q0, const uint4& q1, int row_start, int row_end, int col_start, int col_end,
+                             double maximum_distance, bool by_appearance, int* distance) {
+  const int lane = threadIdx.x & 31;
+  if (row_start >= row_end || col_start >= col_end) return -1;
+  const int f0 = row_ptr[row_start], f1 = row_ptr[row_end];
+  unsigned best = 0xffffffffu;
+  for (int f = f0 + lane; f < f1; f += 32) {
+    const uint32_t q = xy[f];
+    const int col = (int)(q & 0xffffu);
+    if (col < col_start || col >= col_end) continue;
+    if (__ldcg(gone + f)) continue;                                  // feature_lattice[row][col] == nullptr
+    const int d = popc256(q0, q1, desc[2 * f], desc[2 * f + 1]);
+    if (!((double)d < maximum_distance)) continue;                   // :103 / :121 (strict, against the double limit)
+    unsigned key;
+    if (by_appearance) {
+      key = ((unsigned)d << 16) | (unsigned)f;                       // :103-107 first strict minimum in scan order
+    } else {
+      const int dr = row_reference - (int)(q >> 16), dc = col_reference - col;
+      const unsigned pd = (unsigned)(dr * dr + dc * dc);             // :124-126
+      if (pd >= 10000u) continue;                                    // :115, :129
+      key = (pd << 16) | (unsigned)f;
+    }
+    best = min(best, key);
+  }
+  best = __reduce_min_sync(0xffffffffu, best);
+  if (best == 0xffffffffu) return -1;
+  const int f = (int)(best & 0xffffu);
+  *distance = by_appearance ? (int)(best >> 16) : popc256(q0, q1, desc[2 * f], desc[2 * f + 1]);
+  return f;
+}
+
+// one iteration of the loop :494-664 for previous point `pp` against the lattices as `v` shows them.
+// result: {left feature | -1, right feature | -1, descriptor_distance_best, status}
+__device__ int4 track_point(const TrackView& v, const TrackParams& tp, const PreviousPoint* __restrict__ pp,
+                            Projection* proj) {
+  const double X = pp->camera[0], Y = pp->camera[1], Z = pp->camera[2];
+  double pc[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)                                                                    // :496-498
+    pc[i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(tp.T[4 * i], X), __dmul_rn(tp.T[4 * i + 1], Y)),
+                                __dmul_rn(tp.T[4 * i + 2], Z)), tp.T[4 * i + 3]);
+  const double il0 = __dadd_rn(__dmul_rn(v.fx, pc[0]), __dmul_rn(v.cx, pc[2]));                  // :501-502
+  const double il1 = __dadd_rn(__dmul_rn(v.fy, pc[1]), __dmul_rn(v.cy, pc[2]));
+  const double il2 = pc[2];
+  const int32_t col_l = to_i32(__ddiv_rn(il0, il2)), row_l = to_i32(__ddiv_rn(il1, il2));        // :503-506
+  proj->col_l = col_l;
+  proj->row_l = row_l;
+  if (col_l < 0 || col_l > v.cols || row_l < 0 || row_l > v.rows) return make_int4(-1, -1, 0, kStatusSkipped);
+
+  const int D = tp.distance_pixels;
+  const uint4* ql = reinterpret_cast<const uint4*>(pp->descriptor_left);
+  const uint4 q0 = ql[0], q1 = ql[1];
+  int distance = 0;
+  const int fl = search_region(v.rpl, v.xyl, v.dl, v.gone_l, row_l, col_l, q0, q1, max(row_l - D, 0),   // :520-538
+                               min(row_l + D + 1, v.rows), max(col_l - D, 0), min(col_l + D + 1, v.cols),
+                               tp.max_distance_tracking, tp.by_appearance != 0, &distance);
+  if (fl < 0) return make_int4(-1, -1, 0, kStatusLost);
+
+  const uint32_t pl = v.xyl[fl];
+  const int col_fl = (int)(pl & 0xffffu), row_fl = (int)(pl >> 16);
+  const float error_x = __fsub_rn((float)col_l, (float)col_fl);                                  // :543-545
+  const float error_y = __fsub_rn((float)row_l, (float)row_fl);
+  const double ir0 = __dadd_rn(il0, v.bx), ir1 = __dadd_rn(il1, 0.0), ir2 = __dadd_rn(il2, 0.0); // :549
+  const double rx = __ddiv_rn(ir0, ir2), ry = __ddiv_rn(ir1, ir2);
+  const int32_t col_r = to_i32(__dsub_rn(rx, (double)error_x));                                  // :550-555
+  const int32_t row_r = to_i32(__dsub_rn(ry, (double)error_y));
+  proj->col_r = col_r;
+  proj->row_r = row_r;
+  proj->right_x = (float)rx;
+  proj->right_y = (float)ry;
+  if (col_r < 0 || col_r > v.cols || row_r < 0 || row_r > v.rows) return make_int4(fl, -1, 0, kStatusSkipped);
+
+  const int e = (int)fabs((double)pp->epipolar_offset);                                          // :568-569
+  const uint4 l0 = v.dl[2 * fl], l1 = v.dl[2 * fl + 1];
+  const int fr = search_region(v.rpr, v.xyr, v.dr, v.gone_r, row_r, col_r, l0, l1, max(row_r - e, 0),   // :570-590
+                               min(row_r + e + 1, v.rows), max(col_r - D, 0), min(col_r + D + 1, col_fl),
+                               v.threshold_triangulation, true, &distance);
+  if (fr < 0) return make_int4(fl, -1, 0, kStatusLost);
+  const int col_fr = (int)(v.xyr[fr] & 0xffffu);
+  if ((double)(col_fl - col_fr) < v.min_disparity) return make_int4(fl, fr, distance, kStatusSkipped);   // :597-600
+  const uint4* qr = reinterpret_cast<const uint4*>(pp->descriptor_right);
+  if ((double)popc256(v.dr[2 * fr], v.dr[2 * fr + 1], qr[0], qr[1]) > tp.max_distance_tracking)  // :603-607
+    return make_int4(fl, fr, distance, kStatusSkipped);
+  return make_int4(fl, fr, distance, kStatusTracked);
+}
+
+__device__ __forceinline__ TrackView make_view(const Geometry& g, const StereoParams& sp, const int32_t* row_ptr,
+                                               const uint32_t* kp_xy, const uint8_t* desc, const int32_t* n_desc,
+                                               const uint8_t* gone_l, const uint8_t* gone_r) {
+  TrackView v;
+  v.rpl = row_ptr;
+  v.rpr = row_ptr + (g.rows + 1);
+  v.xyl = kp_xy;
+  v.xyr = kp_xy + g.cap;
+  v.dl = reinterpret_cast<const uint4*>(desc);
+  v.dr = reinterpret_cast<const uint4*>(desc + (size_t)g.cap * kDescBytes);
+  v.gone_l = gone_l;
+  v.gone_r = gone_r;
+  v.rows = g.rows;
+  v.cols = g.cols;
+  v.fx = sp.fx; v.fy = sp.fy; v.cx = sp.cx; v.cy = sp.cy; v.bx = sp.bx;
+  v.threshold_triangulation = triangulation_threshold(sp, n_desc[0]);
+  v.min_disparity = sp.min_disparity;
+  return v;
+}
+
+// K9: every previous point against the lattices as initialize() (or the caller) left them
+__global__ void __launch_bounds__(256) track_search_kernel(Geometry g, StereoParams sp, TrackParams tp,
+                                                           const int32_t* row_ptr, const uint32_t* kp_xy,
+                                                           const uint8_t* desc, const int32_t* n_desc,
+                                                           const uint8_t* gone_l, const uint8_t* gone_r,
+                                                           const PreviousPoint* __restrict__ previous, int n_previous,
+                                                           int4* __restrict__ tentative) {
+  const int u = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (u >= n_previous) return;
+  const TrackView v = make_view(g, sp, row_ptr, kp_xy, desc, n_desc, gone_l, gone_r);
+  Projection proj;
+  const int4 r = track_point(v, tp, previous + u, &proj);
+  if ((threadIdx.x & 31) == 0) tentative[u] = r;
+}
+
+// right features a track removes: the match and the parallax range behind it on its row (:611-620, :646-651)
+template <typename F>
+__device__ __forceinline__ void for_each_consumed_right(const TrackView& v, int fl, int fr, F&& f) {
+  const int col_fl = (int)(v.xyl[fl] & 0xffffu);
+  const int row_fr = (int)(v.xyr[fr] >> 16);
+  const int end = v.rpr[row_fr + 1];
+  f(fr);
+  for (int s = fr + 1; s < end && (int)(v.xyr[s] & 0xffffu) < col_fl; ++s) f(s);
+}
+
+constexpr int kResolveThreads = 1024;
+
+__device__ __forceinline__ int block_min(int v, int* s_red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = __reduce_min_sync(0xffffffffu, v);
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  v = s_red[lane];
+  v = __reduce_min_sync(0xffffffffu, v);
+  __syncthreads();
+  return v;
+}
+
+// exclusive scan of a 0/1 flag over the block; total in *total
+__device__ __forceinline__ int block_scan_flag(bool flag, int* s_red, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) s_red[warp] = __popc(bal);
+  __syncthreads();
+  const int mine = s_red[lane];
+  int inc = mine;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  const int warp_offset = __shfl_sync(0xffffffffu, inc - mine, warp);
+  *total = __shfl_sync(0xffffffffu, inc, 31);
+  __syncthreads();
+  return warp_offset + __popc(bal & ((1u << lane) - 1u));
+}
+
+// K10
+__global__ void __launch_bounds__(kResolveThreads) track_resolve_kernel(
+    Geometry g, StereoParams sp, TrackParams tp, const int32_t* row_ptr, const uint32_t* kp_xy, const uint8_t* desc,
+    const int32_t* n_desc, uint8_t* gone_l, uint8_t* gone_r, const PreviousPoint* __restrict__ previous,
+    int n_previous, int4* tentative, int32_t* claim_l, int32_t* claim_r, TrackRecord* __restrict__ tracks,
+    int32_t* __restrict__ lost, TrackedPoint* __restrict__ tracked, int32_t* __restrict__ stats) {
+  __shared__ int s_red[32];
+  __shared__ int s_acc[2];
+  const int tid = threadIdx.x;
+  const TrackView v = make_view(g, sp, row_ptr, kp_xy, desc, n_desc, gone_l, gone_r);
+  const int n_l = n_desc[0], n_r = n_desc[1];
+
+  for (int i = tid; i < n_l; i += kResolveThreads) claim_l[i] = INT32_MAX;
+  for (int i = tid; i < n_r; i += kResolveThreads) claim_r[i] = INT32_MAX;
+  if (tid < 2) s_acc[tid] = 0;
+  __syncthreads();
+  for (int u = tid; u < n_previous; u += kResolveThreads) {
+    const int4 t = tentative[u];
+    if (t.w != kStatusTracked) continue;
+    atomicMin(&claim_l[t.x], u);
+    for_each_consumed_right(v, t.x, t.y, [&](int s) { atomicMin(&claim_r[s], u); });
+  }
+  __syncthreads();
+
+  int frontier = 0;
+  while (frontier < n_previous) {
+    // lowest point at or above the frontier whose result depends on a feature a lower point consumes
+    int dirty = INT32_MAX;
+    for (int u = frontier + tid; u < n_previous; u += kResolveThreads) {
+      const int4 t = __ldcg(tentative + u);
+      const bool d = (t.x >= 0 && __ldcg(claim_l + t.x) < u) || (t.y >= 0 && __ldcg(claim_r + t.y) < u);
+      if (d) {
+        dirty = u;
+        break;
+      }
+    }
+    dirty = block_min(dirty, s_red);
+    const int stop = min(dirty, n_previous);
+    // commit [frontier, stop): these results are what the sequential loop yields
+    for (int u = frontier + tid; u < stop; u += kResolveThreads) {
+      const int4 t = __ldcg(tentative + u);
+      if (t.w != kStatusTracked) continue;
+      gone_l[t.x] = 1;
+      for_each_consumed_right(v, t.x, t.y, [&](int s) { gone_r[s] = 1; });
+    }
+    __syncthreads();
+    if (dirty == INT32_MAX) break;
+    if (tid < 32) {   // the lattices now hold exactly the removals of the points below `dirty`
+      Projection proj;
+      const int4 t = track_point(v, tp, previous + dirty, &proj);
+      if (tid == 0) {
+        tentative[dirty] = t;
+        if (t.w == kStatusTracked) {
+          gone_l[t.x] = 1;
+          atomicMin(&claim_l[t.x], dirty);
+          for_each_consumed_right(v, t.x, t.y, [&](int s) {
+            gone_r[s] = 1;
+            atomicMin(&claim_r[s], dirty);
+          });
+        }
+      }
+    }
+    __syncthreads();
+    frontier = dirty + 1;
+  }
+
+  // ordered output: tracks (:623-643), lost points (:660-663), the tracked points as compute() pre-loads them (:147-155)
+  int n_tracks = 0, n_lost = 0, landmarks = 0, accumulated = 0;
+  for (int u0 = 0; u0 < n_previous; u0 += kResolveThreads) {
+    const int u = u0 + tid;
+    int4 t = make_int4(-1, -1, 0, kStatusSkipped);
+    if (u < n_previous) t = __ldcg(tentative + u);
+    int total_t, total_l;
+    const int pos_t = n_tracks + block_scan_flag(t.w == kStatusTracked, s_red, &total_t);
+    const int pos_l = n_lost + block_scan_flag(t.w == kStatusLost, s_red, &total_l);
+    if (t.w == kStatusLost) lost[pos_l] = u;
+    if (t.w == kStatusTracked) {
+      const PreviousPoint* pp = previous + u;
+      // the projections of this point (visualisation fields :620-626): same arithmetic as track_point
+      double pc[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        pc[i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(tp.T[4 * i], pp->camera[0]), __dmul_rn(tp.T[4 * i + 1], pp->camera[1])),
+                                    __dmul_rn(tp.T[4 * i + 2], pp->camera[2])), tp.T[4 * i + 3]);
+      const double il0 = __dadd_rn(__dmul_rn(v.fx, pc[0]), __dmul_rn(v.cx, pc[2]));
+      const double il1 = __dadd_rn(__dmul_rn(v.fy, pc[1]), __dmul_rn(v.cy, pc[2]));
+      const int32_t col_l = to_i32(__ddiv_rn(il0, pc[2])), row_l = to_i32(__ddiv_rn(il1, pc[2]));
+      const uint32_t pl = v.xyl[t.x], pr = v.xyr[t.y];
+      const float error_x = __fsub_rn((float)col_l, (float)(pl & 0xffffu));
+      const float error_y = __fsub_rn((float)row_l, (float)(pl >> 16));
+      const double rx = __ddiv_rn(__dadd_rn(il0, v.bx), __dadd_rn(pc[2], 0.0));
+      const double ry = __ddiv_rn(__dadd_rn(il1, 0.0), __dadd_rn(pc[2], 0.0));
+      TrackRecord r;
+      r.index_previous = u;
+      r.index_left = t.x;
+      r.index_right = t.y;
+      r.xl = (float)(pl & 0xffffu);
+      r.yl = (float)(pl >> 16);
+      r.xr = (float)(pr & 0xffffu);
+      r.yr = (float)(pr >> 16);
+      r.distance = t.z;
+      r.epipolar_offset = (int)(pr >> 16) - (int)(pl >> 16);                                     // :616
+      r.projection_left[0] = (float)col_l;
+      r.projection_left[1] = (float)row_l;
+      r.projection_right[0] = (float)rx;
+      r.projection_right[1] = (float)ry;
+      r.projection_right_corrected[0] = (float)to_i32(__dsub_rn(rx, (double)error_x));
+      r.projection_right_corrected[1] = (float)to_i32(__dsub_rn(ry, (double)error_y));
+      r.reserved = 0;
+      triangulate(sp, r.xl, r.yl, r.xr, r.yr, r.camera);
+      tracks[pos_t] = r;
+      TrackedPoint q;
+      q.row = (int)(pl >> 16);
+      q.col = (int)(pl & 0xffffu);
+      q.has_previous = 1;
+      q.reserved = 0;
+      q.disparity = (double)__fsub_rn(r.xl, r.xr);                                               // frame_point.cpp:19
+      q.distance = (double)t.z;
+      tracked[pos_t] = q;
+      atomicAdd(&s_acc[0], pp->has_landmark != 0);                                               // :653-655
+      atomicAdd(&s_acc[1], t.z);                                                                 // :627
+    }
+    n_tracks += total_t;
+    n_lost += total_l;
+  }
+  __syncthreads();
+  landmarks = s_acc[0];
+  accumulated = s_acc[1];
+  if (tid == 0) {
+    stats[0] = n_tracks;
+    stats[1] = n_lost;
+    stats[2] = landmarks;
+    stats[3] = accumulated;
+  }
+}
+
+// ---- recoverPoints ---------------------------------------------------------------------------------------------
+
+// R1: projection and geometric gates (:702-766); slot u of xy[0][.] / xy[1][.] receives the rounded projections of
+// lost point u (or a dummy interior pixel when it is rejected; flag in the top bit of the LEFT entry's partner array)
+__global__ void __launch_bounds__(256) recover_project_kernel(Geometry g, StereoParams sp, RecoverParams rp,
+                                                              const PreviousPoint* __restrict__ lost, int n_lost,
+                                                              uint32_t* __restrict__ xy, int stride,
+                                                              uint8_t* __restrict__ valid, int32_t* __restrict__ n_xy) {
+  const int u = blockIdx.x * 256 + threadIdx.x;
+  if (u == 0) n_xy[0] = n_xy[1] = n_lost;
+  if (u >= n_lost) return;
+  const PreviousPoint* pp = lost + u;
+  bool ok = pp->has_landmark != 0;                                                               // :704-706
+  double pc[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)                                                                    // :716-717
+    pc[i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(rp.W[4 * i], pp->world[0]), __dmul_rn(rp.W[4 * i + 1], pp->world[1])),
+                                __dmul_rn(rp.W[4 * i + 2], pp->world[2])), rp.W[4 * i + 3]);
+  const double il0 = __dadd_rn(__dmul_rn(sp.fx, pc[0]), __dmul_rn(sp.cx, pc[2]));                // :725-728
+  const double il1 = __dadd_rn(__dmul_rn(sp.fy, pc[1]), __dmul_rn(sp.cy, pc[2]));
+  const double il2 = pc[2];
+  const double ir0 = __dadd_rn(il0, sp.bx), ir1 = __dadd_rn(il1, 0.0), ir2 = __dadd_rn(il2, 0.0);
+  if (il2 < rp.min_depth || il2 > rp.max_depth || ir2 < rp.min_depth || ir2 > rp.max_depth) ok = false;   // :731-736
+  const float plx = (float)rint(__ddiv_rn(il0, il2)), ply = (float)rint(__ddiv_rn(il1, il2));    // :739-746
+  const float prx = (float)rint(__ddiv_rn(ir0, ir2)), pry = (float)rint(__ddiv_rn(ir1, ir2));
+  const float border = __fmul_rn(5.0f, pp->keypoint_size);                                       // :749-750
+  const float lo = __fadd_rn(border, 1.0f);
+  const float hx = __fsub_rn(__fsub_rn((float)g.cols, border), 1.0f), hy = __fsub_rn(__fsub_rn((float)g.rows, border), 1.0f);
+  if (!(plx >= lo && plx <= hx && prx >= lo && prx <= hx && ply >= lo && ply <= hy && pry >= lo && pry <= hy))
+    ok = false;                                                                                  // :751-766 (NaN fails)
+  if (border < 31.0f) ok = false;   // ORB's 31 px border filter would drop the keypoint: descriptor.rows == 0 (:790-792)
+  uint32_t l = 31u | (31u << 16), r = l;   // any interior pixel: the descriptor of a rejected slot is never read
+  if (ok) {
+    l = (uint32_t)(int)plx | ((uint32_t)(int)ply << 16);
+    r = (uint32_t)(int)prx | ((uint32_t)(int)pry << 16);
+  }
+  xy[u] = l;
+  xy[stride + u] = r;
+  valid[u] = ok;
+}
+
+// R3: the three descriptor gates, disparity gate, triangulation and ordered output (:798-858)
+__global__ void __launch_bounds__(kResolveThreads) recover_finish_kernel(
+    StereoParams sp, RecoverParams rp, const int32_t* n_desc,
+    const PreviousPoint* __restrict__ lost, int n_lost, const uint32_t* __restrict__ xy, int stride,
+    const uint8_t* __restrict__ valid, const uint8_t* __restrict__ desc, RecoveredRecord* __restrict__ out,
+    int32_t* __restrict__ n_out) {
+  __shared__ int s_red[32];
+  const int tid = threadIdx.x;
+  const double thr_tri = triangulation_threshold(sp, n_desc[0]);   // _current_maximum_descriptor_distance_triangulation
+  int n = 0;
+  for (int u0 = 0; u0 < n_lost; u0 += kResolveThreads) {
+    const int u = u0 + tid;
+    bool ok = u < n_lost && valid[u];
+    uint4 l0, l1, r0, r1;
+    int distance = 0;
+    uint32_t pl = 0, pr = 0;
+    if (ok) {
+      const PreviousPoint* pp = lost + u;
+      const uint4* dl = reinterpret_cast<const uint4*>(desc + (size_t)u * kDescBytes);
+      const uint4* dr = reinterpret_cast<const uint4*>(desc + ((size_t)stride + u) * kDescBytes);
+      l0 = dl[0]; l1 = dl[1]; r0 = dr[0]; r1 = dr[1];
+      const uint4* ql = reinterpret_cast<const uint4*>(pp->descriptor_left);
+      const uint4* qr = reinterpret_cast<const uint4*>(pp->descriptor_right);
+      pl = xy[u];
+      pr = xy[stride + u];
+      if ((double)popc256(ql[0], ql[1], l0, l1) > rp.max_distance_tracking) ok = false;          // :798-802
+      if ((double)__fsub_rn((float)(pl & 0xffffu), (float)(pr & 0xffffu)) < sp.min_disparity) ok = false;   // :825-828
+      if ((double)popc256(qr[0], qr[1], r0, r1) > rp.max_distance_tracking) ok = false;          // :831-835
+      distance = popc256(l0, l1, r0, r1);                                                        // :838-843
+      if ((double)distance > thr_tri) ok = false;
+    }
+    int total;
+    const int pos = n + block_scan_flag(ok, s_red, &total);
+    if (ok) {
+      RecoveredRecord r;
+      r.index_lost = u;
+      r.distance = distance;
+      r.xl = (float)(pl & 0xffffu);
+      r.yl = (float)(pl >> 16);
+      r.xr = (float)(pr & 0xffffu);
+      r.yr = (float)(pr >> 16);
+      triangulate(sp, r.xl, r.yl, r.xr, r.yr, r.camera);                                         // :851-855
+      *reinterpret_cast<uint4*>(r.descriptor_left) = l0;
+      *reinterpret_cast<uint4*>(r.descriptor_left + 16) = l1;
+      *reinterpret_cast<uint4*>(r.descriptor_right) = r0;
+      *reinterpret_cast<uint4*>(r.descriptor_right + 16) = r1;
+      out[pos] = r;
+    }
+    n += total;
+  }
+  if (tid == 0) *n_out = n;
+}
+
+}  // namespace
+
+void launch_track(const Geometry& g, const StereoParams& sp, const Buffers& b, int pair, const PreviousPoint* previous,
+                  int n_previous, const TrackParams& tp, const TrackScratch& s, TrackRecord* tracks, int32_t* lost,
+                  TrackedPoint* tracked, cudaStream_t stream) {
+  const int32_t* row_ptr = b.row_ptr + (size_t)2 * pair * (g.rows + 1);
+  const uint32_t* kp_xy = b.kp_xy + (size_t)2 * pair * g.cap;
+  const uint8_t* desc = b.desc + (size_t)2 * pair * g.cap * kDescBytes;
+  const int32_t* n_desc = b.n_desc + 2 * pair;
+  uint8_t* gone_l = b.pruned_l + (size_t)pair * g.cap;
+  uint8_t* gone_r = b.consumed_r + (size_t)pair * g.cap;
+  if (n_previous > 0)
+    track_search_kernel<<<(n_previous + 7) / 8, 256, 0, stream>>>(g, sp, tp, row_ptr, kp_xy, desc, n_desc, gone_l, gone_r,
+                                                                  previous, n_previous, s.tentative);
+  track_resolve_kernel<<<1, kResolveThreads, 0, stream>>>(g, sp, tp, row_ptr, kp_xy, desc, n_desc, gone_l, gone_r,
+                                                          previous, n_previous, s.tentative, s.claim_l, s.claim_r, tracks,
+                                                          lost, tracked, s.stats);
+}
+
+void launch_recover(const Geometry& g, const StereoParams& sp, const Buffers& b, int pair, const uint8_t* blurred,
+                    const PreviousPoint* lost, int n_lost, const RecoverParams& rp, uint32_t* xy, int32_t* n_xy,
+                    uint8_t* desc, RecoveredRecord* out, int32_t* n_out, cudaStream_t stream) {
+  // scratch layout: xy[2][stride] projections, desc[2][stride][32], valid flags behind the descriptors
+  const int stride = n_lost;
+  uint8_t* valid = desc + (size_t)2 * stride * kDescBytes;
+  if (n_lost > 0) {
+    recover_project_kernel<<<(n_lost + 255) / 256, 256, 0, stream>>>(g, sp, rp, lost, n_lost, xy, stride, valid, n_xy);
+    launch_describe_at(g, blurred, xy, n_xy, desc, stride, 2, stream);
+  }
+  recover_finish_kernel<<<1, kResolveThreads, 0, stream>>>(sp, rp, b.n_desc + 2 * pair, lost, n_lost, xy, stride,
+                                                           valid, desc, out, n_out);
+}
+
+}  // namespace vslam
