@@ -2,6 +2,7 @@
 // effect the call reproduces (reference src/framepoint_generation/stereo_framepoint_generator.cpp unless noted).
 #include "gpu_stereo_framepoint_generator.h"
 
+#include <cstring>
 #include <stdexcept>
 
 namespace proslam {
@@ -76,29 +77,117 @@ void GpuStereoFramePointGenerator::initialize(Frame* frame_, const bool& extract
     check(vslam_fpg_get_detection_stats(_handle, nullptr, nullptr, &distance));
     _current_maximum_descriptor_distance_triangulation = distance;                                   // :109-125
   }
-  // :129-132 the lattice + vectors the inherited track() / recoverPoints() work on
-  _feature_matcher_left.setFeatures(frame_->keypointsLeft(), frame_->descriptorsLeft());
-  _feature_matcher_right.setFeatures(frame_->keypointsRight(), frame_->descriptorsRight());
+  // :129-132 setFeatures(): the lattices live on the device (row-sorted feature arrays + pruned flags); the host
+  // matchers of the base classes stay empty
+}
+
+void GpuStereoFramePointGenerator::fillPreviousPoint(const FramePoint* point_, vslam_previous_point& out_) {
+  const PointCoordinates camera_coordinates(point_->cameraCoordinatesLeft());
+  for (int i = 0; i < 3; ++i) out_.camera_left[i] = camera_coordinates(i);
+  const bool has_landmark = point_->landmark() != nullptr;
+  const PointCoordinates world_coordinates(has_landmark ? point_->landmark()->coordinates() : point_->worldCoordinates());
+  for (int i = 0; i < 3; ++i) out_.world[i] = world_coordinates(i);
+  std::memcpy(out_.descriptor_left, point_->descriptorLeft().data, VSLAM_DESCRIPTOR_BYTES);
+  std::memcpy(out_.descriptor_right, point_->descriptorRight().data, VSLAM_DESCRIPTOR_BYTES);
+  out_.epipolar_offset = point_->epipolarOffset();
+  out_.has_landmark = has_landmark;
+  out_.keypoint_size = point_->keypointLeft().size;
+  out_.reserved = 0;
+}
+
+void GpuStereoFramePointGenerator::track(Frame* frame_, Frame* frame_previous_,
+                                         const TransformMatrix3D& camera_left_previous_in_current_,
+                                         FramePointPointerVector& lost_points_, const bool track_by_appearance_) {
+  if (!frame_ || !frame_previous_)                                                                   // :468-471
+    throw std::runtime_error("StereoFramePointGenerator::track|called with invalid frames");
+  FramePointPointerVector& framepoints(frame_->points());
+  FramePointPointerVector& framepoints_previous(frame_previous_->points());
+  const size_t n_previous = framepoints_previous.size();
+
+  _previous_buffer.resize(n_previous);
+  for (size_t i = 0; i < n_previous; ++i) fillPreviousPoint(framepoints_previous[i], _previous_buffer[i]);
+  double T[12];   // row-major 3x4 [R|t]
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) T[4 * r + c] = camera_left_previous_in_current_.matrix()(r, c);
+
+  _track_buffer.resize(n_previous);
+  _lost_buffer.resize(n_previous);
+  int32_t n_tracks = 0, n_lost = 0, n_landmarks = 0;
+  double average_distance = 0;
+  // :494-672 in two kernels; the matched features are pruned on the device (== :671-672)
+  check(vslam_fpg_track(_handle, _previous_buffer.data(), (int32_t)n_previous, T, track_by_appearance_,
+                        _projection_tracking_distance_pixels, _maximum_descriptor_distance_tracking, _track_buffer.data(),
+                        (int32_t)_track_buffer.size(), &n_tracks, _lost_buffer.data(), &n_lost, &n_landmarks,
+                        &average_distance));
+
+  const std::vector<cv::KeyPoint>& kl = frame_->keypointsLeft();
+  const std::vector<cv::KeyPoint>& kr = frame_->keypointsRight();
+  framepoints.resize(n_tracks);                                                                      // :479, :665
+  for (int32_t i = 0; i < n_tracks; ++i) {
+    const vslam_track& t = _track_buffer[i];
+    const IntensityFeature feature_left(kl[t.index_left], frame_->descriptorsLeft().row(t.index_left), t.index_left);
+    const IntensityFeature feature_right(kr[t.index_right], frame_->descriptorsRight().row(t.index_right), t.index_right);
+    FramePoint* framepoint = frame_->createFramepoint(&feature_left, &feature_right, t.distance,                // :623-626
+                                                      PointCoordinates(t.camera[0], t.camera[1], t.camera[2]),
+                                                      framepoints_previous[t.index_previous]);
+    framepoint->setEpipolarOffset(t.epipolar_offset);                                                // :627
+    framepoint->setProjectionEstimateLeft(cv::Point2f(t.projection_left[0], t.projection_left[1]));  // :631-637
+    framepoint->setProjectionEstimateRight(cv::Point2f(t.projection_right[0], t.projection_right[1]));
+    framepoint->setProjectionEstimateRightCorrected(
+        cv::Point2f(t.projection_right_corrected[0], t.projection_right_corrected[1]));
+    framepoints[i] = framepoint;
+  }
+  lost_points_.resize(n_lost);                                                                       // :482, :666
+  for (int32_t i = 0; i < n_lost; ++i) lost_points_[i] = framepoints_previous[_lost_buffer[i]];
+  _number_of_tracked_landmarks = n_landmarks;                                                        // :653-655
+  frame_previous_->setAverageDescriptorDistanceTracking(average_distance);                           // :667-668
+}
+
+void GpuStereoFramePointGenerator::recoverPoints(Frame* current_frame_,
+                                                 const FramePointPointerVector& lost_points_) const {
+  const size_t n_lost = lost_points_.size();
+  _previous_buffer.resize(n_lost);
+  for (size_t i = 0; i < n_lost; ++i) {
+    fillPreviousPoint(lost_points_[i], _previous_buffer[i]);
+    if (lost_points_[i]->landmark()) lost_points_[i]->landmark()->incrementNumberOfRecoveries();     // :712
+  }
+  double W[12];
+  const TransformMatrix3D world_to_camera_left = current_frame_->worldToCameraLeft();                // :686-687
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) W[4 * r + c] = world_to_camera_left.matrix()(r, c);
+  _recovered_buffer.resize(n_lost);
+  int32_t n_recovered = 0;
+  check(vslam_fpg_recover_points(_handle, _previous_buffer.data(), (int32_t)n_lost, W, _parameters->minimum_depth_meters,
+                                 _parameters->maximum_depth_meters, _maximum_descriptor_distance_tracking,
+                                 _recovered_buffer.data(), (int32_t)_recovered_buffer.size(), &n_recovered));
+  FramePointPointerVector& framepoints(current_frame_->points());
+  framepoints.reserve(framepoints.size() + n_recovered);                                             // :698-700, :861
+  for (int32_t i = 0; i < n_recovered; ++i) {
+    const vslam_recovered_point& r = _recovered_buffer[i];
+    FramePoint* point_previous = lost_points_[r.index_lost];
+    cv::KeyPoint keypoint_left(point_previous->keypointLeft()), keypoint_right(point_previous->keypointRight());
+    keypoint_left.pt = cv::Point2f(r.xl, r.yl);                                                      // :795
+    keypoint_right.pt = cv::Point2f(r.xr, r.yr);                                                     // :822
+    // FramePoint keeps cv::Mat headers: the descriptors must own their memory (clone), like the ones ORB returns
+    const cv::Mat descriptor_left = cv::Mat(1, VSLAM_DESCRIPTOR_BYTES, CV_8UC1, (void*)r.descriptor_left).clone();
+    const cv::Mat descriptor_right = cv::Mat(1, VSLAM_DESCRIPTOR_BYTES, CV_8UC1, (void*)r.descriptor_right).clone();
+    const IntensityFeature feature_left(keypoint_left, descriptor_left, 0);                          // :846-849
+    const IntensityFeature feature_right(keypoint_right, descriptor_right, 0);
+    framepoints.push_back(current_frame_->createFramepoint(&feature_left, &feature_right, r.distance,        // :852-856
+                                                           PointCoordinates(r.camera[0], r.camera[1], r.camera[2]),
+                                                           point_previous));
+  }
 }
 
 void GpuStereoFramePointGenerator::compute(Frame* frame_) {
   if (!frame_) throw std::runtime_error("StereoFramePointGenerator::compute|called with empty frame");     // :139-142
   FramePointPointerVector& framepoints(frame_->points());
 
-  // what track() pruned (:646-651, :671-672) must not take part in the scan
-  for (int side = 0; side < 2; ++side) {
-    const IntensityFeaturePointerVector& remaining =
-        side == 0 ? _feature_matcher_left.feature_vector : _feature_matcher_right.feature_vector;
-    _keypoint_buffer.resize(remaining.size());
-    for (size_t i = 0; i < remaining.size(); ++i) {
-      _keypoint_buffer[i].x = remaining[i]->keypoint.pt.x;
-      _keypoint_buffer[i].y = remaining[i]->keypoint.pt.y;
-      _keypoint_buffer[i].response = remaining[i]->keypoint.response;
-    }
-    check(vslam_fpg_set_remaining_features(_handle, side, _keypoint_buffer.data(), (int32_t)remaining.size()));
-  }
+  // what track() pruned (:646-651, :671-672) is already flagged on the device and does not take part in the scan
 
-  // :147-155 points already in the frame (tracked / recovered) pre-load the bin map
+  // :147-155 points already in the frame (tracked / recovered) pre-load the bin map.  PoseTracker3D::compute may have
+  // dropped outliers or appended recovered points since track() (pose_tracker_3d.cpp:437-472, 206): the list is
+  // rebuilt from frame->points() as the reference reads it.
   _tracked_buffer.resize(framepoints.size());
   for (size_t i = 0; i < framepoints.size(); ++i) {
     const FramePoint* point = framepoints[i];

@@ -4,8 +4,9 @@
 // repository's image.  It derives from StereoFramePointGenerator because SLAMAssembly::printReport reaches the
 // generator through dynamic_cast<StereoFramePointGenerator*> (reference src/system/slam_assembly.cpp:690-719).
 //
-// Overridden: configure(), initialize(), compute()      -> CUDA, through include/vslam_b200.h only
-// Inherited : track(), recoverPoints()                   -> the reference's CPU code (SURVEY.md section 8(f) "next")
+// Overridden: configure(), initialize(), track(), compute(), recoverPoints() -> CUDA, through include/vslam_b200.h only.
+// Nothing of the per-frame work runs the inherited CPU code; the host side only materialises the FramePoint objects
+// the rest of the reference (tracker, landmarks, map) works on.
 #pragma once
 #include "framepoint_generation/stereo_framepoint_generator.h"
 #include "vslam_b200.h"
@@ -20,7 +21,10 @@ class GpuStereoFramePointGenerator : public StereoFramePointGenerator {
 
   void configure() override;
   void initialize(Frame* frame_, const bool& extract_features_ = true) override;
+  void track(Frame* frame_, Frame* frame_previous_, const TransformMatrix3D& camera_left_previous_in_current_,
+             FramePointPointerVector& lost_points_, const bool track_by_appearance_ = true) override;
   void compute(Frame* frame_) override;
+  void recoverPoints(Frame* current_frame_, const FramePointPointerVector& lost_points_) const override;
 
   // device seconds, the GPU counterparts of getTimeConsumptionSeconds_{keypoint_detection, ...}
   double deviceSecondsKeypointDetection() const;
@@ -36,6 +40,12 @@ class GpuStereoFramePointGenerator : public StereoFramePointGenerator {
   std::vector<vslam_keypoint> _keypoint_buffer;
   std::vector<vslam_framepoint> _framepoint_buffer;
   std::vector<vslam_tracked_point> _tracked_buffer;
+  mutable std::vector<vslam_previous_point> _previous_buffer;
+  std::vector<vslam_track> _track_buffer;
+  std::vector<int32_t> _lost_buffer;
+  mutable std::vector<vslam_recovered_point> _recovered_buffer;
+
+  static void fillPreviousPoint(const FramePoint* point_, vslam_previous_point& out_);
 };
 
 }  // namespace proslam

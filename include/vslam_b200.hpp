@@ -2,7 +2,7 @@
 // the hot path with plain value types instead of its Eigen / OpenCV / srrg object graph, so that it builds with
 // nothing but a C++14 compiler:
 //
-//   vslam::StereoFramePointGenerator::{configure (ctor), initialize(Frame&), compute(Frame&)}
+//   vslam::StereoFramePointGenerator::{configure (ctor), initialize, track, compute, recoverPoints}
 //        <- proslam::BaseFramePointGenerator / StereoFramePointGenerator
 //           (reference src/framepoint_generation/base_framepoint_generator.h:119-151)
 //   vslam::StereoUVAligner / vslam::UVDAligner::{initialize, linearize, oneRound, converge, errors, inliers, ...}
@@ -39,6 +39,13 @@ struct Frame {
   std::vector<uint8_t> descriptors_left, descriptors_right;   // n x 32
   std::vector<vslam_tracked_point> tracked_points;            // points() before compute()
   std::vector<vslam_framepoint> points;                       // what compute() appends to points()
+  // track() / recoverPoints(): points() of a processed frame as the NEXT frame's track() reads them, and what the two
+  // calls put into points() of the current frame
+  std::vector<vslam_previous_point> previous_points;
+  std::vector<vslam_track> tracks;
+  std::vector<vslam_recovered_point> recovered;
+  double average_descriptor_distance_tracking = 0;            // setAverageDescriptorDistanceTracking (on the previous frame)
+  std::array<double, 12> world_to_camera_left{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}};
 };
 
 class StereoFramePointGenerator {
@@ -65,18 +72,62 @@ class StereoFramePointGenerator {
     fetch(0, nl, frame->keypoints_left, frame->descriptors_left);
     fetch(1, nr, frame->keypoints_right, frame->descriptors_right);
     _number_of_detected_keypoints = nl;
+    _tracks_resident = false;
+  }
+
+  // base_framepoint_generator.h:164-165
+  void setProjectionTrackingDistancePixels(const int32_t& v) { _projection_tracking_distance_pixels = v; }
+  void setMaximumDescriptorDistanceTracking(const double& v) { _maximum_descriptor_distance_tracking = v; }
+
+  // track(frame, frame_previous, camera_left_previous_in_current, lost_points, track_by_appearance):
+  // frame->tracks = points() after the call; lost_points = positions in frame_previous->previous_points
+  void track(Frame* frame, Frame* frame_previous, const std::array<double, 12>& camera_left_previous_in_current,
+             std::vector<int32_t>& lost_points, const bool track_by_appearance = true) {
+    if (!frame || !frame_previous) throw std::runtime_error("StereoFramePointGenerator::track|called with invalid frames");
+    const std::vector<vslam_previous_point>& previous = frame_previous->previous_points;
+    frame->tracks.resize(previous.size());
+    lost_points.resize(previous.size());
+    int32_t n = 0, n_lost = 0, n_landmarks = 0;
+    check(vslam_fpg_track(_handle, previous.data(), (int32_t)previous.size(), camera_left_previous_in_current.data(),
+                          track_by_appearance, _projection_tracking_distance_pixels, _maximum_descriptor_distance_tracking,
+                          frame->tracks.data(), (int32_t)frame->tracks.size(), &n, lost_points.data(), &n_lost,
+                          &n_landmarks, &frame_previous->average_descriptor_distance_tracking),
+          "StereoFramePointGenerator::track");
+    frame->tracks.resize(n);
+    lost_points.resize(n_lost);
+    _number_of_tracked_landmarks = n_landmarks;
+    _tracks_resident = true;
   }
 
   void compute(Frame* frame) {
     if (!frame) throw std::runtime_error("StereoFramePointGenerator::compute|called with empty frame");
+    // the tracks of this frame are still on the device unless the caller supplies its own list of points()
+    const bool resident = _tracks_resident && frame->tracked_points.empty();
     frame->points.resize((size_t)_capacity + frame->tracked_points.size());
     int32_t n = 0, m = 0;
-    check(vslam_fpg_compute(_handle, frame->tracked_points.data(), (int32_t)frame->tracked_points.size(),
+    check(vslam_fpg_compute(_handle, resident ? nullptr : frame->tracked_points.data(),
+                            resident ? VSLAM_TRACKED_FROM_LAST_TRACK : (int32_t)frame->tracked_points.size(),
                             frame->points.data(), (int32_t)frame->points.size(), &n, &m),
           "StereoFramePointGenerator::compute");
     frame->points.resize(n);
     _number_of_new_points = m;
   }
+
+  // recoverPoints(current_frame, lost_points): lost = the lost points (with landmark coordinates in `world`)
+  void recoverPoints(Frame* current_frame, const std::vector<vslam_previous_point>& lost_points,
+                     double minimum_depth_meters = 0.1, double maximum_depth_meters = 1000) const {
+    if (!current_frame) throw std::runtime_error("StereoFramePointGenerator::recoverPoints|called with empty frame");
+    current_frame->recovered.resize(lost_points.size());
+    int32_t n = 0;
+    check(vslam_fpg_recover_points(_handle, lost_points.data(), (int32_t)lost_points.size(),
+                                   current_frame->world_to_camera_left.data(), minimum_depth_meters, maximum_depth_meters,
+                                   _maximum_descriptor_distance_tracking, current_frame->recovered.data(),
+                                   (int32_t)current_frame->recovered.size(), &n),
+          "StereoFramePointGenerator::recoverPoints");
+    current_frame->recovered.resize(n);
+  }
+
+  int numberOfTrackedLandmarks() const { return _number_of_tracked_landmarks; }
 
   int targetNumberOfKeypoints() const { return _target_number_of_keypoints; }
   int numberOfDetectedKeypoints() const { return _number_of_detected_keypoints; }
@@ -100,6 +151,10 @@ class StereoFramePointGenerator {
   vslam_fpg* _handle = nullptr;
   int32_t _rows_bin = 0, _cols_bin = 0, _target_number_of_keypoints = 0;
   int _number_of_detectors = 1, _capacity = 0, _number_of_detected_keypoints = 0, _number_of_new_points = 0;
+  int32_t _projection_tracking_distance_pixels = 0;     // base_framepoint_generator.h:221
+  double _maximum_descriptor_distance_tracking = 0;     // :224
+  int _number_of_tracked_landmarks = 0;                 // :227
+  bool _tracks_resident = false;
 };
 
 // BaseFrameAligner over caller-provided correspondence buffers (what ::initialize leaves behind)

@@ -51,6 +51,55 @@ int main(int argc, char** argv) {
     if (!frame.points.empty())
       std::printf("first %.17g %.17g %.17g\n", frame.points[0].camera[0], frame.points[0].camera[1], frame.points[0].camera[2]);
 
+    // ---- next frame: initialize -> track (against the first frame's points) -> compute -> recoverPoints, the order of
+    // PoseTracker3D::compute (reference src/position_tracking/pose_tracker_3d.cpp:80, 239, 206-210)
+    for (const vslam_framepoint& p : frame.points) {   // frame.points() as the next track() reads them
+      vslam_previous_point q = {};
+      for (int i = 0; i < 3; ++i) q.camera_left[i] = q.world[i] = p.camera[i];
+      for (int i = 0; i < VSLAM_DESCRIPTOR_BYTES; ++i) {
+        q.descriptor_left[i] = frame.descriptors_left[(size_t)p.index_left * VSLAM_DESCRIPTOR_BYTES + i];
+        q.descriptor_right[i] = frame.descriptors_right[(size_t)p.index_right * VSLAM_DESCRIPTOR_BYTES + i];
+      }
+      q.epipolar_offset = p.epipolar_offset;
+      q.has_landmark = 1;
+      q.keypoint_size = 7.f;
+      frame.previous_points.push_back(q);
+    }
+    const std::vector<uint8_t> left1 = slurp(dir + "/left1.u8"), right1 = slurp(dir + "/right1.u8");
+    vslam::Frame next;
+    next.status = vslam::Frame::Tracking;
+    next.intensity_image_left = left1.data();
+    next.intensity_image_right = right1.data();
+    next.image_step = 1241;
+    generator.initialize(&next);
+    const double tx = -(386.1448 / 718.856) / 4;   // the band world moves the camera a quarter baseline per frame
+    const std::array<double, 12> motion{{1, 0, 0, tx, 0, 1, 0, 0, 0, 0, 1, 0}};
+    std::vector<int32_t> lost;
+    generator.setProjectionTrackingDistancePixels(15);
+    generator.setMaximumDescriptorDistanceTracking(25.6);
+    generator.track(&next, &frame, motion, lost, false);
+    generator.compute(&next);
+    unsigned long long ht = 1469598103934665603ull;
+    for (const vslam_track& t : next.tracks) {
+      const int32_t v[5] = {t.index_previous, t.index_left, t.index_right, t.distance, t.epipolar_offset};
+      for (int32_t x : v) ht = (ht ^ (unsigned long long)(uint32_t)x) * 1099511628211ull;
+    }
+    for (int32_t x : lost) ht = (ht ^ (unsigned long long)(uint32_t)x) * 1099511628211ull;
+    for (const vslam_framepoint& p : next.points) ht = (ht ^ (unsigned long long)(uint32_t)p.index_left) * 1099511628211ull;
+    std::printf("tracking %zu lost %zu landmarks %d new %zu average %.17g hash %llu\n", next.tracks.size(), lost.size(),
+                generator.numberOfTrackedLandmarks(), next.points.size(), frame.average_descriptor_distance_tracking, ht);
+    std::vector<vslam_previous_point> lost_points;
+    for (int32_t i : lost) lost_points.push_back(frame.previous_points[i]);
+    next.world_to_camera_left = motion;             // the first frame's camera is the world frame
+    generator.setMaximumDescriptorDistanceTracking(64);
+    generator.recoverPoints(&next, lost_points);
+    unsigned long long hr = 1469598103934665603ull;
+    for (const vslam_recovered_point& r : next.recovered) {
+      hr = (hr ^ (unsigned long long)(uint32_t)r.index_lost) * 1099511628211ull;
+      for (uint8_t b : r.descriptor_left) hr = (hr ^ b) * 1099511628211ull;
+    }
+    std::printf("recovered %zu hash %llu\n", next.recovered.size(), hr);
+
     // ---- StereoUVAligner::converge on the correspondence set written by the pytest
     const std::vector<uint8_t> raw = slurp(dir + "/correspondences.f64");
     const double* d = reinterpret_cast<const double*>(raw.data());

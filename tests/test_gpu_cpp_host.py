@@ -34,9 +34,13 @@ def test_cpp_frontend_program_matches_oracle(tmp_path):
     exe = str(tmp_path / "host_api_check")
     _build(exe)
     cfg, cam = configs.KITTI, synth.camera("kitti")
-    left, right = synth.band_world_pair("kitti", 12)
+    world = synth.BandWorld(cam.cols, cam.rows, 12, max_frames=4)
+    left, right = world.pair(0)
+    left1, right1 = world.pair(1)
     left.tofile(tmp_path / "left.u8")
     right.tofile(tmp_path / "right.u8")
+    left1.tofile(tmp_path / "left1.u8")
+    right1.tofile(tmp_path / "right1.u8")
     n = 3000
     c = synth.correspondences(n, "stereouv", cam, seed=99)
     np.concatenate([[float(n)], c["moving"].ravel(), c["fixed"].ravel(), c["omega"], c["wt"]]).tofile(
@@ -58,6 +62,34 @@ def test_cpp_frontend_program_matches_oracle(tmp_path):
             h = ((h ^ (int(x) & 0xFFFFFFFF)) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
     assert lines["hash"] == str(h)
     assert [float(v) for v in lines["first"].split()] == fp[0]["cam"].tolist()
+
+    # second frame: track -> compute -> recoverPoints
+    from test_oracle_track import previous_points
+    prev = previous_points(o, fp)
+    o.initialize(left1, right1, False)
+    T = np.hstack([np.eye(3), np.zeros((3, 1))])
+    T[0, 3] = -(386.1448 / 718.856) / 4
+    r = o.track(prev, T, False, 15, 25.6)
+    o.compute(o.tracked_points(r["tracks"]))
+    new = o.framepoints()
+    h = 1469598103934665603
+    for t in r["tracks"]:
+        for x in (t["index_previous"], t["index_left"], t["index_right"], t["distance"], t["epipolar_offset"]):
+            h = ((h ^ (int(x) & 0xFFFFFFFF)) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    for x in r["lost"].tolist() + new["index_left"].tolist():
+        h = ((h ^ (int(x) & 0xFFFFFFFF)) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    f = lines["tracking"].split()
+    assert f[:7] == [str(len(r["tracks"])), "lost", str(len(r["lost"])), "landmarks", str(r["tracked_landmarks"]), "new",
+                     str(len(new))]
+    assert float(f[8]) == r["accumulated_distance"] / len(r["tracks"]) and f[10] == str(h)
+    assert len(r["tracks"]) > 300
+    rec = o.recover_points(prev[r["lost"]], T, 64.0)
+    h = 1469598103934665603
+    for q in rec:
+        h = ((h ^ (int(q["index_lost"]) & 0xFFFFFFFF)) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        for b in q["desc_left"].tolist():
+            h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    assert lines["recovered"] == "%d hash %d" % (len(rec), h)
 
     al = tier_a.Aligner("stereouv", c["moving"], c["fixed"], c["omega"], c["wt"], cam.K, cam.baseline, cam.rows, cam.cols,
                         0.1, 16.0)
