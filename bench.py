@@ -303,6 +303,37 @@ def sequence_latency(api, configs, synth, device):
         dt = time.perf_counter() - t0
         out[name] = {"frames_per_s": 20 / dt, "ms_per_frame": dt / 20 * 1e3, "mean_framepoints": n_fp / 20,
                      "image": "%dx%d" % (cam.cols, cam.rows)}
+        # the tracker's per-frame order (pose_tracker_3d.cpp:80, 239, 210): initialize -> track against ALL points of the
+        # previous frame -> compute with the tracks pre-loaded from device memory.  The host part (descriptor download,
+        # assembly of the previous points) is inside the timed region.
+        T = np.hstack([np.eye(3), np.zeros((3, 1))])
+        T[0, 3] = -(-cam.bx / cam.fx) / 4
+        prev, n_tracks, n_prev, n_new = None, 0, 0, 0
+        t_total = 0.0
+        for k in range(24):
+            t0 = time.perf_counter()
+            gen.initialize(frames[k][0], frames[k][1], k == 0)
+            parts = []
+            if prev is not None:
+                r = gen.track(prev, T, False, 15, 25.6)
+                parts.append(r["tracks"])
+                new = gen.compute(api.TRACKED_FROM_LAST_TRACK)
+            else:
+                new = gen.compute()
+            parts.append(new)
+            _, dl = gen.features(0)
+            _, dr = gen.features(1)
+            nxt = api.make_previous_points(parts, dl, dr)
+            t1 = time.perf_counter()
+            if k >= 4:
+                t_total += t1 - t0
+                n_tracks += len(parts[0]) if prev is not None else 0
+                n_prev += len(prev)
+                n_new += len(new)
+            prev = nxt
+        out[name]["tracked"] = {"frames_per_s": 20 / t_total, "ms_per_frame": t_total / 20 * 1e3,
+                                "mean_previous_points": n_prev / 20, "mean_tracks": n_tracks / 20,
+                                "mean_new_points": n_new / 20}
         gen.close()
     return out
 

@@ -426,6 +426,26 @@ class StereoFramePointGenerator:
         return img
 
 
+def make_previous_points(parts, descriptors_left, descriptors_right, has_landmark=1, world=None):
+    """frame->points() of a processed frame (TRACK / FRAMEPOINT record arrays in order, e.g. [tracks, new points]) as
+    the next frame's track() / recoverPoints() read them: camera coordinates, the two descriptors of each point (rows
+    index_left / index_right of descriptorsLeft() / Right()), epipolar offset"""
+    n = sum(len(p) for p in parts)
+    out = np.zeros(n, PREVIOUS_POINT)
+    i = 0
+    for p in parts:
+        s = slice(i, i + len(p))
+        out["camera_left"][s] = p["camera"]
+        out["descriptor_left"][s] = descriptors_left[p["index_left"]]
+        out["descriptor_right"][s] = descriptors_right[p["index_right"]]
+        out["epipolar_offset"][s] = p["epipolar_offset"]
+        i += len(p)
+    out["world"] = out["camera_left"] if world is None else world
+    out["has_landmark"] = has_landmark
+    out["keypoint_size"] = 7.0
+    return out
+
+
 def _image(a, cam):
     a = np.asarray(a)
     if a.dtype != np.uint8 or a.shape != (cam.rows, cam.cols) or a.strides[1] != 1:
