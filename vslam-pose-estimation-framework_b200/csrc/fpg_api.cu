@@ -34,6 +34,7 @@ struct Lane {
   cudaStream_t stream = nullptr;
   uint8_t* blurred = nullptr;   // [2*chunk][rows][pitch]
   uint32_t* mask = nullptr;     // [2*chunk][rows][mask_words]
+  CUtensorMap blurred_map;      // TMA descriptor of `blurred` (box = describe tile)
   uint8_t* stage = nullptr;     // [2][chunk * pair_stride] dense landing zone of the H2D copies
   size_t stage_bytes = 0;       // per side
 };
@@ -145,7 +146,7 @@ void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n) {
   mark(h, lane, kEvCompact1);
   launch_blur(h->g, b, 2 * p0, 2 * n, lane.stream);
   mark(h, lane, kEvBlur1);
-  launch_describe(h->g, b, 2 * p0, 2 * n, lane.stream);
+  launch_describe(h->g, b, lane.blurred_map, 2 * p0, 2 * n, lane.stream);
   mark(h, lane, kEvDescribe1);
   h->launches += 4;
 }
@@ -451,6 +452,10 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
     dalloc((void**)&h->lanes[l].blurred, (size_t)2 * h->chunk * img_bytes);
     dalloc((void**)&h->lanes[l].mask, (size_t)2 * h->chunk * g.rows * g.mask_words * sizeof(uint32_t));
     if (ok && cudaStreamCreateWithFlags(&h->lanes[l].stream, cudaStreamNonBlocking) != cudaSuccess) ok = false;
+    if (ok && !make_blurred_tensor_map(g, h->lanes[l].blurred, 2 * h->chunk, &h->lanes[l].blurred_map)) {
+      vslam_fpg_destroy(h);
+      return fail(VSLAM_ERR_CUDA, "cuTensorMapEncodeTiled failed for the blurred image buffer (TMA is required: no fallback)");
+    }
   }
   auto halloc = [&](void** p, size_t bytes) {
     if (ok && cudaMallocHost(p, bytes) != cudaSuccess) ok = false;

@@ -1,6 +1,8 @@
 // kernels.cuh -- launch interface of the framepoint-generation and aligner kernels (sm_100a).
 #pragma once
 
+#include <cuda.h>   // CUtensorMap (type only; the encoder is resolved through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 
 namespace vslam {
@@ -85,7 +87,11 @@ void launch_compact(const Geometry& g, const Buffers& b, int first_image, int n_
 // FAST response of the kept keypoints of one image -> kp_score (on demand)
 void launch_score(const Geometry& g, const Buffers& b, int image, cudaStream_t stream);
 void launch_blur(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream);
-void launch_describe(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream);
+// TMA descriptor of a blurred scratch buffer [n_images][rows][pitch]; false when the driver cannot encode it
+bool make_blurred_tensor_map(const Geometry& g, const uint8_t* blurred, int n_images, CUtensorMap* out);
+// image 0 of `blurred_map` is image `first_image` of the batch
+void launch_describe(const Geometry& g, const Buffers& b, const CUtensorMap& blurred_map, int first_image, int n_images,
+                     cudaStream_t stream);
 // one launch per epipolar offset (pass index -> offset 0,+1,-1,+2,...)
 void launch_match(const Geometry& g, const StereoParams& sp, const Buffers& b, int first_pair, int n_pairs, int pass,
                   int epipolar_offset, cudaStream_t stream);

@@ -150,25 +150,125 @@ constexpr OrbPattern kOrb = {{
 #include "orb_pattern_31.inc"
 }};
 
-// test K of the pattern as compile-time patch offsets (the table is only ever read in constant expressions)
-template <int K>
+// test K of the pattern as compile-time offsets into a buffer of row pitch PITCH whose origin is the pixel (x-13, y-13)
+// of the keypoint (the table is only ever read in constant expressions)
+template <int K, int PITCH>
 struct OrbTest {
-  static constexpr int o0 = (kOrb.v[4 * K + 1] + 13) * PP + kOrb.v[4 * K] + 13;
-  static constexpr int o1 = (kOrb.v[4 * K + 3] + 13) * PP + kOrb.v[4 * K + 2] + 13;
+  static constexpr int o0 = (kOrb.v[4 * K + 1] + 13) * PITCH + kOrb.v[4 * K] + 13;
+  static constexpr int o1 = (kOrb.v[4 * K + 3] + 13) * PITCH + kOrb.v[4 * K + 2] + 13;
 };
 
 // descriptor word W: tests 32W .. 32W+31, bit j of byte i = test 8i + j (LSB first).  The tests are visited from
 // j = 31 down to 0 and the sign bit of t0 - t1 (set iff t0 < t1) is shifted in with one funnel shift per test.
-template <int W, int... J>
+template <int W, int PITCH, int... J>
 __device__ __forceinline__ uint32_t brief_word_impl(const uint8_t* c, std::integer_sequence<int, J...>) {
   uint32_t w = 0;
-  ((w = __funnelshift_l((uint32_t)((int)c[OrbTest<32 * W + 31 - J>::o0] - (int)c[OrbTest<32 * W + 31 - J>::o1]), w, 1)), ...);
+  ((w = __funnelshift_l((uint32_t)((int)c[OrbTest<32 * W + 31 - J, PITCH>::o0] - (int)c[OrbTest<32 * W + 31 - J, PITCH>::o1]), w, 1)), ...);
   return w;
 }
 
-template <int W>
+template <int W, int PITCH = PP>
 __device__ __forceinline__ uint32_t brief_word(const uint8_t* c) {
-  return brief_word_impl<W>(c, std::make_integer_sequence<int, 32>{});
+  return brief_word_impl<W, PITCH>(c, std::make_integer_sequence<int, 32>{});
+}
+
+// K4, tile form.  The keypoints of one image are (row, col)-sorted with a CSR row pointer, so the keypoints whose centre
+// lies in a 224 x 64 tile are a filtered slice of one contiguous index range.  One CTA per tile: a single TMA box load
+// (cp.async.bulk.tensor.3d, 256 x 90 bytes = the tile + the 13 px pattern radius, out-of-bounds zero-filled) stages the
+// blurred pixels while the threads compact the tile's keypoints into a list; then one lane per keypoint evaluates the
+// 256 tests straight from the shared tile (offsets are compile-time immediates).  Every blurred byte is fetched about
+// 1.7x (halo) instead of once per overlapping 26 x 32 patch (~5x), and no per-keypoint staging instructions remain.
+constexpr int DT_W = 224, DT_H = 64;            // keypoint-centre area of a tile
+constexpr int DT_BW = 256, DT_BH = DT_H + 26;   // TMA box: columns x0-15 .. x0+240, rows y0-13 .. y0+76
+constexpr int DT_X = 15;                        // the box starts 15 px left of the tile: x0 - 15 = 16 (1 + 14 k), and TMA
+                                                // needs every row of the box to start at a 16-byte aligned address
+static_assert(DT_W % 16 == 0 && (31 - DT_X) % 16 == 0 && DT_X >= 13 && DT_W + 12 + DT_X < DT_BW, "tile geometry");
+constexpr int DT_THREADS = 128;
+constexpr int DT_LIST = 512;                    // keypoints compacted per round
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(DT_THREADS) describe_tile_kernel(const __grid_constant__ CUtensorMap blurred_map,
+                                                                   Geometry g, const int32_t* __restrict__ row_ptr,
+                                                                   const uint32_t* __restrict__ kp_xy,
+                                                                   uint8_t* __restrict__ desc) {
+  __shared__ __align__(128) uint8_t s_tile[DT_BH][DT_BW];
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ uint32_t s_q[DT_LIST];
+  __shared__ int s_f[DT_LIST];
+  __shared__ int s_n;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int img = blockIdx.z;
+  const int x0 = 31 + blockIdx.x * DT_W, y0 = 31 + blockIdx.y * DT_H;
+  const int y1 = min(y0 + DT_H, g.rows - 31);   // keypoints live in [31, rows - 31) x [31, cols - 31)
+  if (y0 >= y1) return;
+  const int32_t* rp = row_ptr + (size_t)img * (g.rows + 1);
+  const int f0 = rp[y0], f1 = rp[y1];
+  if (f0 == f1) return;
+  const uint32_t* xy = kp_xy + (size_t)img * g.cap;
+  uint4* out = reinterpret_cast<uint4*>(desc + (size_t)img * g.cap * kDescBytes);
+
+  if (tid == 0) {
+    const uint32_t bar = smem_u32(&s_bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(DT_BW * DT_BH) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(&s_tile[0][0])), "l"(&blurred_map), "r"(bar), "r"(x0 - DT_X), "r"(y0 - 13), "r"(img)
+        : "memory");
+  }
+  bool tile_ready = false;
+  for (int base = f0; base < f1; base += DT_LIST) {
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    const int end = min(f1, base + DT_LIST);
+    for (int f = base + tid; f < ((end - base + 31) & ~31) + base; f += DT_THREADS) {   // whole warps enter the ballot
+      uint32_t q = 0;
+      bool in = false;
+      if (f < end) {
+        q = xy[f];
+        const int x = (int)(q & 0xffffu);
+        in = x >= x0 && x < x0 + DT_W;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, in);
+      int pos = 0;
+      if (lane == 0 && bal) pos = atomicAdd(&s_n, __popc(bal));
+      pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << lane) - 1u));
+      if (in) {
+        s_q[pos] = q;
+        s_f[pos] = f;
+      }
+    }
+    __syncthreads();
+    if (!tile_ready) {   // wait for the TMA box (phase 0 of the barrier)
+      const uint32_t bar = smem_u32(&s_bar);
+      uint32_t done = 0;
+      while (!done)
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+            : "=r"(done) : "r"(bar) : "memory");
+      tile_ready = true;
+    }
+    const int n = s_n;
+    for (int k = tid; k < n; k += DT_THREADS) {
+      const uint32_t q = s_q[k];
+      const uint8_t* c = &s_tile[(int)(q >> 16) - y0][(int)(q & 0xffffu) - x0 + (DT_X - 13)];
+      uint4 lo, hi;
+      lo.x = brief_word<0, DT_BW>(c);
+      lo.y = brief_word<1, DT_BW>(c);
+      lo.z = brief_word<2, DT_BW>(c);
+      lo.w = brief_word<3, DT_BW>(c);
+      hi.x = brief_word<4, DT_BW>(c);
+      hi.y = brief_word<5, DT_BW>(c);
+      hi.z = brief_word<6, DT_BW>(c);
+      hi.w = brief_word<7, DT_BW>(c);
+      const int f = s_f[k];
+      out[2 * (size_t)f] = lo;
+      out[2 * (size_t)f + 1] = hi;
+    }
+    __syncthreads();
+  }
 }
 
 __global__ void __launch_bounds__(DWARPS * 32) describe_kernel(Geometry g, const uint8_t* __restrict__ blurred,
@@ -271,12 +371,38 @@ static void configure_describe() {
   }
 }
 
-void launch_describe(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream) {
-  configure_describe();
-  dim3 grid(n_images <= 8 ? 24 : 12, n_images);
-  describe_kernel<<<grid, DWARPS * 32, DSMEM, stream>>>(g, b.blurred + (size_t)first_image * g.rows * g.pitch,
-                                            b.kp_xy + (size_t)first_image * g.cap, b.n_desc + first_image,
-                                            b.desc + (size_t)first_image * g.cap * kDescBytes, g.cap);
+// tensor map of a lane's blurred scratch [n_images][rows][pitch] u8 with the describe tile as box
+bool make_blurred_tensor_map(const Geometry& g, const uint8_t* blurred, int n_images, CUtensorMap* out) {
+  typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiled encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn ||
+        qr != cudaDriverEntryPointSuccess)
+      return false;
+    encode = reinterpret_cast<EncodeTiled>(fn);
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.rows, (cuuint64_t)n_images};
+  const cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)g.pitch * g.rows};   // bytes, dims 1 and 2
+  const cuuint32_t box[3] = {DT_BW, DT_BH, 1};
+  const cuuint32_t elem[3] = {1, 1, 1};
+  return encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(blurred), dims, strides, box, elem,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// `blurred_map` describes the buffer whose image 0 is image `first_image` of the batch (the lane's scratch)
+void launch_describe(const Geometry& g, const Buffers& b, const CUtensorMap& blurred_map, int first_image, int n_images,
+                     cudaStream_t stream) {
+  const int tiles_x = (g.cols - 62 + DT_W - 1) / DT_W, tiles_y = (g.rows - 62 + DT_H - 1) / DT_H;
+  if (tiles_x <= 0 || tiles_y <= 0) return;   // no pixel is 31 px away from every border: no descriptor-valid keypoint
+  dim3 grid(tiles_x, tiles_y, n_images);
+  describe_tile_kernel<<<grid, DT_THREADS, 0, stream>>>(blurred_map, g, b.row_ptr + (size_t)first_image * (g.rows + 1),
+                                                        b.kp_xy + (size_t)first_image * g.cap,
+                                                        b.desc + (size_t)first_image * g.cap * kDescBytes);
 }
 
 void launch_describe_at(const Geometry& g, const uint8_t* blurred, const uint32_t* xy, const int32_t* n, uint8_t* desc,
