@@ -324,7 +324,9 @@ __global__ void __launch_bounds__(kThreads) converge_kernel(int n, AlignerBuffer
 // Batched form for independent stereo pairs: one WARP per pair linearises the StereoUV problem that aligns the
 // pair's new framepoints against themselves -- StereoUVAligner::initialize (:10-69) fused in: _moving =
 // cameraCoordinatesLeft, _fixed = (uL, vL, uR, vR), information = I4 (no landmark), w_t = min(max_depth/depth, 1).
-// A pair holds a few hundred points: a warp-private shuffle reduction needs no shared memory and no block barrier.
+// A pair holds a few hundred points and every point is a long dependent FP64 chain (three divisions): one CTA per
+// pair with one point per thread and iteration keeps the chain short; the warps' partial sums meet in shared memory
+// and are added in a fixed order (run-to-run deterministic).
 constexpr int kPairWarps = 4;
 
 __global__ void __launch_bounds__(kPairWarps * 32) linearize_pairs_kernel(const FramePointRecord* __restrict__ records,
@@ -337,15 +339,15 @@ __global__ void __launch_bounds__(kPairWarps * 32) linearize_pairs_kernel(const 
                                                                           double* __restrict__ systems,
                                                                           double* __restrict__ errors,
                                                                           uint8_t* __restrict__ inliers) {
-  const int lane = threadIdx.x & 31;
-  const int pair = blockIdx.x * kPairWarps + (threadIdx.x >> 5);
-  if (pair >= n_pairs) return;
+  __shared__ double s_part[kPairWarps][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pair = blockIdx.x;
   const int n = n_out[2 * pair];
   const FramePointRecord* rec = records + (size_t)pair * record_stride;
   double acc[kAcc];
 #pragma unroll
   for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
-  for (int u = lane; u < n; u += 32) {
+  for (int u = threadIdx.x; u < n; u += kPairWarps * 32) {
     const FramePointRecord r = rec[u];
     double err = -1.0;
     uint8_t inl = 0;
@@ -359,14 +361,21 @@ __global__ void __launch_bounds__(kPairWarps * 32) linearize_pairs_kernel(const 
     errors[(size_t)pair * record_stride + u] = err;
     inliers[(size_t)pair * record_stride + u] = inl;
   }
-  double mine = 0.0;   // lane i ends up with total i
+  double mine = 0.0;   // lane i ends up with the warp's total i
 #pragma unroll
   for (int i = 0; i < kAcc; ++i) {
     double v = acc[i];
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == i) mine = v;
   }
-  if (lane < kAcc) systems[(size_t)pair * 32 + lane] = mine;
+  s_part[warp][lane] = mine;
+  __syncthreads();
+  if (warp == 0 && lane < kAcc) {
+    double v = s_part[0][lane];
+#pragma unroll
+    for (int w = 1; w < kPairWarps; ++w) v += s_part[w][lane];
+    systems[(size_t)pair * 32 + lane] = v;
+  }
 }
 
 }  // namespace
@@ -410,7 +419,7 @@ void launch_linearize_pairs(const FramePointRecord* records, int record_stride, 
                             uint8_t* inliers, cudaStream_t stream) {
   Pose pose;
   for (int i = 0; i < 12; ++i) pose.T[i] = T[i];
-  linearize_pairs_kernel<<<(n_pairs + kPairWarps - 1) / kPairWarps, kPairWarps * 32, 0, stream>>>(
+  linearize_pairs_kernel<<<n_pairs, kPairWarps * 32, 0, stream>>>(
       records, record_stride, n_pairs, n_out, cam, pose, ignore_outliers, kernel, max_reliable_depth,
       inverse_depth_weight, systems, errors, inliers);
 }

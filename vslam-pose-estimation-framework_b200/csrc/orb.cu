@@ -37,7 +37,7 @@ __device__ __forceinline__ float byte_to_float(uint32_t word, int j) {
 
 // K3.  Tile 128 x 64 outputs.  Row pass: one thread per 4 adjacent outputs (10 input bytes converted once, 28 FMA);
 // column pass: one thread per 4 columns x 8 rows (14 float4 shared-memory loads, packed 32-bit stores).
-__global__ void __launch_bounds__(256) blur_kernel(Geometry g, GaussKernel gk, const uint8_t* __restrict__ image,
+__global__ void __launch_bounds__(256, 4) blur_kernel(Geometry g, GaussKernel gk, const uint8_t* __restrict__ image,
                                                    uint8_t* __restrict__ blurred) {
   __shared__ __align__(16) uint8_t s_in[SH][SW];
   __shared__ __align__(16) float s_tmp[SH][TW];
@@ -73,36 +73,39 @@ __global__ void __launch_bounds__(256) blur_kernel(Geometry g, GaussKernel gk, c
     __syncthreads();
   }
 
-  // ---- row pass: outputs x = xq .. xq+3 need inputs xq-3 .. xq+6, all inside three aligned words
-  for (int i = tid; i < SH * (TW / 4); i += 256) {
-    const int r = i / (TW / 4), xq = (i - r * (TW / 4)) * 4;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(&s_in[r][xq + HX - 4]);
-    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-    float p[10];
-    p[0] = byte_to_float(w0, 1);
-    p[1] = byte_to_float(w0, 2);
-    p[2] = byte_to_float(w0, 3);
+  // ---- row pass: outputs x = xq .. xq+3 need inputs xq-3 .. xq+6, all inside three aligned words.  A thread takes
+  // the same four columns of TWO rows and evaluates them with packed FFMA2 (one instruction, two IEEE fp32 FMAs: the
+  // per-element result is the scalar one, so the rounding contract with the oracle is unchanged).
+  for (int i = tid; i < (SH / 2) * (TW / 4); i += 256) {
+    const int r = 2 * (i / (TW / 4)), xq = (i % (TW / 4)) * 4;
+    const uint32_t* wa = reinterpret_cast<const uint32_t*>(&s_in[r][xq + HX - 4]);
+    const uint32_t* wb = reinterpret_cast<const uint32_t*>(&s_in[r + 1][xq + HX - 4]);
+    const uint32_t a0 = wa[0], a1 = wa[1], a2 = wa[2], b0 = wb[0], b1 = wb[1], b2 = wb[2];
+    float2 p[10];   // .x: row r, .y: row r + 1
+    p[0] = make_float2(byte_to_float(a0, 1), byte_to_float(b0, 1));
+    p[1] = make_float2(byte_to_float(a0, 2), byte_to_float(b0, 2));
+    p[2] = make_float2(byte_to_float(a0, 3), byte_to_float(b0, 3));
 #pragma unroll
-    for (int j = 0; j < 4; ++j) p[3 + j] = byte_to_float(w1, j);
-    p[7] = byte_to_float(w2, 0);
-    p[8] = byte_to_float(w2, 1);
-    p[9] = byte_to_float(w2, 2);
-    float4 out;
-    float* o = reinterpret_cast<float*>(&out);
+    for (int j = 0; j < 4; ++j) p[3 + j] = make_float2(byte_to_float(a1, j), byte_to_float(b1, j));
+    p[7] = make_float2(byte_to_float(a2, 0), byte_to_float(b2, 0));
+    p[8] = make_float2(byte_to_float(a2, 1), byte_to_float(b2, 1));
+    p[9] = make_float2(byte_to_float(a2, 2), byte_to_float(b2, 2));
+    float2 o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float acc = __fmul_rn(gk.k[0], p[j]);
+      float2 acc = __fmul2_rn(make_float2(gk.k[0], gk.k[0]), p[j]);
 #pragma unroll
-      for (int t = 1; t < 7; ++t) acc = __fmaf_rn(gk.k[t], p[j + t], acc);
+      for (int t = 1; t < 7; ++t) acc = __ffma2_rn(make_float2(gk.k[t], gk.k[t]), p[j + t], acc);
       o[j] = acc;
     }
-    *reinterpret_cast<float4*>(&s_tmp[r][xq]) = out;
+    *reinterpret_cast<float4*>(&s_tmp[r][xq]) = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
+    *reinterpret_cast<float4*>(&s_tmp[r + 1][xq]) = make_float4(o[0].y, o[1].y, o[2].y, o[3].y);
   }
   __syncthreads();
 
   // ---- column pass + round half-to-even to u8: adding 1.5 * 2^23 leaves rint(acc) in the low mantissa byte.
   // acc is a convex combination (weights sum to 1 within 1e-7) of values in [0, 255]: it cannot leave [0, 255.0001],
-  // so cv::saturate_cast's clamp is a no-op and is not evaluated.
+  // so cv::saturate_cast's clamp is a no-op and is not evaluated.  Adjacent columns are packed (FADD2 / FFMA2).
   uint8_t* outp = blurred + (size_t)img * g.rows * g.pitch;
   {
     constexpr int RPT = TH / 8;   // rows per thread
@@ -110,23 +113,23 @@ __global__ void __launch_bounds__(256) blur_kernel(Geometry g, GaussKernel gk, c
     float4 t[RPT + 6];
 #pragma unroll
     for (int r = 0; r < RPT + 6; ++r) t[r] = *reinterpret_cast<const float4*>(&s_tmp[yb + r][xq]);
+    const float2 k3 = make_float2(gk.k[3], gk.k[3]), bias = make_float2(12582912.0f, 12582912.0f);
 #pragma unroll
     for (int y = 0; y < RPT; ++y) {
       if (y0 + yb + y >= g.rows || x0 + xq >= g.pitch) continue;
-      uint32_t b[4];
+      float2 lo = __fmul2_rn(k3, make_float2(t[y + 3].x, t[y + 3].y));
+      float2 hi = __fmul2_rn(k3, make_float2(t[y + 3].z, t[y + 3].w));
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float* c = reinterpret_cast<const float*>(&t[y + 3]) + j;
-        float acc = __fmul_rn(gk.k[3], *c);
-#pragma unroll
-        for (int d = 1; d <= 3; ++d) {
-          const float up = reinterpret_cast<const float*>(&t[y + 3 + d])[j];
-          const float dn = reinterpret_cast<const float*>(&t[y + 3 - d])[j];
-          acc = __fmaf_rn(gk.k[3 + d], __fadd_rn(up, dn), acc);
-        }
-        b[j] = __float_as_uint(__fadd_rn(acc, 12582912.0f));
+      for (int d = 1; d <= 3; ++d) {
+        const float2 kd = make_float2(gk.k[3 + d], gk.k[3 + d]);
+        const float4 up = t[y + 3 + d], dn = t[y + 3 - d];
+        lo = __ffma2_rn(kd, __fadd2_rn(make_float2(up.x, up.y), make_float2(dn.x, dn.y)), lo);
+        hi = __ffma2_rn(kd, __fadd2_rn(make_float2(up.z, up.w), make_float2(dn.z, dn.w)), hi);
       }
-      const uint32_t packed = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
+      lo = __fadd2_rn(lo, bias);
+      hi = __fadd2_rn(hi, bias);
+      const uint32_t packed = __byte_perm(__byte_perm(__float_as_uint(lo.x), __float_as_uint(lo.y), 0x0040),
+                                          __byte_perm(__float_as_uint(hi.x), __float_as_uint(hi.y), 0x0040), 0x5410);
       *reinterpret_cast<uint32_t*>(outp + (size_t)(y0 + yb + y) * g.pitch + x0 + xq) = packed;
     }
   }
