@@ -40,8 +40,9 @@ struct Lane {
 };
 
 // profiling: events at the kernel boundaries of one chunk (single lane, serialised)
-enum { kEvFast0, kEvFast1, kEvCompact1, kEvBlur1, kEvDescribe1, kEvMatch0, kEvMatch1, kEvSelect1, kEvLin0, kEvLin1, kNumEv };
-enum { kKFast, kKCompact, kKBlur, kKDescribe, kKMatch, kKSelect, kKLinearize, kNumKernels };
+enum { kEvFast0, kEvFast1, kEvCompact1, kEvBlur1, kEvDescribe1, kEvMatch0, kEvMatch1, kEvSelect1, kEvLin0, kEvLin1, kEvTrack0, kEvTrack1, kNumEv };
+enum { kKFast, kKCompact, kKBlur, kKDescribe, kKMatch, kKSelect, kKLinearize, kKTrack, kNumKernels };
+static_assert(kNumKernels == VSLAM_FPG_KERNELS, "kernel profile size");
 
 struct StageClock {
   cudaEvent_t ev[kNumEv] = {};
@@ -100,6 +101,8 @@ struct vslam_fpg {
   TrackRecord* d_tracks = nullptr;       // [previous_cap]
   int32_t* d_lost = nullptr;             // [previous_cap]
   int32_t* h_track_stats = nullptr;      // pinned [4]
+  TrackRecord* h_tracks = nullptr;       // pinned [previous_cap]
+  int32_t* h_lost = nullptr;             // pinned [previous_cap]
   int n_device_tracks = -1;              // tracks of the last vslam_fpg_track still valid for compute()
   uint32_t* d_recover_xy = nullptr;      // [2][previous_cap]
   uint8_t* d_recover_desc = nullptr;     // [2][previous_cap][32] + [previous_cap] flags
@@ -501,7 +504,7 @@ int vslam_fpg_destroy(vslam_fpg* h) {
   cudaFree(h->d_previous); cudaFree(h->track_scratch.tentative); cudaFree(h->track_scratch.claim_l);
   cudaFree(h->track_scratch.claim_r); cudaFree(h->track_scratch.stats); cudaFree(h->d_tracks); cudaFree(h->d_lost);
   cudaFree(h->d_recover_xy); cudaFree(h->d_recover_desc); cudaFree(h->d_recovered); cudaFree(h->d_recover_n);
-  cudaFreeHost(h->h_track_stats);
+  cudaFreeHost(h->h_track_stats); cudaFreeHost(h->h_tracks); cudaFreeHost(h->h_lost);
   cudaFreeHost(h->h_counts); cudaFreeHost(h->h_n_desc); cudaFreeHost(h->h_n_out); cudaFreeHost(h->h_flag);
   cudaFreeHost(h->h_systems);
   for (auto& e : h->clock.ev)
@@ -674,6 +677,8 @@ static int ensure_previous_capacity(vslam_fpg* h, int n) {
   cudaFree(h->d_recover_xy); cudaFree(h->d_recover_desc); cudaFree(h->d_recovered);
   h->d_previous = nullptr; h->track_scratch.tentative = nullptr; h->d_tracks = nullptr; h->d_lost = nullptr;
   h->d_recover_xy = nullptr; h->d_recover_desc = nullptr; h->d_recovered = nullptr;
+  cudaFreeHost(h->h_tracks); cudaFreeHost(h->h_lost);
+  h->h_tracks = nullptr; h->h_lost = nullptr;
   h->previous_cap = 0;
   CUDA_TRY(cudaMalloc((void**)&h->d_previous, sizeof(PreviousPoint) * (size_t)cap));
   CUDA_TRY(cudaMalloc((void**)&h->track_scratch.tentative, sizeof(int4) * (size_t)cap));
@@ -682,6 +687,8 @@ static int ensure_previous_capacity(vslam_fpg* h, int n) {
   CUDA_TRY(cudaMalloc((void**)&h->d_recover_xy, sizeof(uint32_t) * 2 * (size_t)cap));
   CUDA_TRY(cudaMalloc((void**)&h->d_recover_desc, (size_t)cap * (2 * kDescBytes + 1)));
   CUDA_TRY(cudaMalloc((void**)&h->d_recovered, sizeof(RecoveredRecord) * (size_t)cap));
+  CUDA_TRY(cudaMallocHost((void**)&h->h_tracks, sizeof(TrackRecord) * (size_t)cap));
+  CUDA_TRY(cudaMallocHost((void**)&h->h_lost, sizeof(int32_t) * (size_t)cap));
   h->previous_cap = cap;
   if (cap > h->tracked_cap) {
     cudaFree(h->d_tracked);
@@ -713,12 +720,20 @@ int vslam_fpg_track(vslam_fpg* h, const vslam_previous_point* previous, int32_t 
   tp.by_appearance = track_by_appearance != 0;
   tp.distance_pixels = projection_tracking_distance_pixels;
   tp.max_distance_tracking = maximum_descriptor_distance_tracking;
+  mark(h, lane, kEvTrack0);
   launch_track(h->g, h->sp, h->b, 0, h->d_previous, n_previous, tp, h->track_scratch, h->d_tracks, h->d_lost,
                h->d_tracked, lane.stream);
+  mark(h, lane, kEvTrack1);
   h->launches += n_previous > 0 ? 2 : 1;
+  // results travel with the counts in ONE round trip: at most n_previous records each (ordered, valid prefix)
   CUDA_TRY(cudaMemcpyAsync(h->h_track_stats, h->track_scratch.stats, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, lane.stream));
+  if (n_previous) {
+    CUDA_TRY(cudaMemcpyAsync(h->h_tracks, h->d_tracks, sizeof(TrackRecord) * (size_t)n_previous, cudaMemcpyDeviceToHost, lane.stream));
+    CUDA_TRY(cudaMemcpyAsync(h->h_lost, h->d_lost, sizeof(int32_t) * (size_t)n_previous, cudaMemcpyDeviceToHost, lane.stream));
+  }
   CUDA_TRY(cudaStreamSynchronize(lane.stream));
   CUDA_TRY(cudaGetLastError());
+  if (h->profiling) add_interval(h, kKTrack, kEvTrack0, kEvTrack1, n_previous > 0 ? 2 : 1);
   const int nt = h->h_track_stats[0], nl = h->h_track_stats[1];
   h->n_device_tracks = nt;
   if (n_tracks) *n_tracks = nt;
@@ -728,8 +743,8 @@ int vslam_fpg_track(vslam_fpg* h, const vslam_previous_point* previous, int32_t 
     *average_descriptor_distance = nt ? (double)h->h_track_stats[3] / (double)nt : std::nan("");
   if (nt > capacity) return fail(VSLAM_ERR_CAPACITY, "capacity %d < %d tracks", capacity, nt);
   if (nt && !tracks) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null output");
-  if (nt) CUDA_TRY(cudaMemcpy(tracks, h->d_tracks, sizeof(TrackRecord) * (size_t)nt, cudaMemcpyDeviceToHost));
-  if (nl && lost) CUDA_TRY(cudaMemcpy(lost, h->d_lost, sizeof(int32_t) * (size_t)nl, cudaMemcpyDeviceToHost));
+  if (nt) std::memcpy(tracks, h->h_tracks, sizeof(TrackRecord) * (size_t)nt);
+  if (nl && lost) std::memcpy(lost, h->h_lost, sizeof(int32_t) * (size_t)nl);
   if (h->g.n_regions > 1 && nt) {   // sorted device order -> the reference's keypoint order
     std::vector<uint32_t> xl, xr;
     std::vector<int> s2r_l, s2r_r, tmp;

@@ -9,13 +9,19 @@
 //
 //   K9  track_search_kernel   one warp per previous point, all points in parallel against the UNCONSUMED lattices:
 //                             projection, rectangular window search (popc-256, warp argmin), corrected right window.
-//   K10 track_resolve_kernel  one CTA per frame.  Every tentative success claims its features with atomicMin(point
-//                             index).  A point is DIRTY when a lower-indexed point claims one of the (at most two)
-//                             features its result depends on.  The points below the lowest dirty index are exactly
-//                             what the sequential loop produces; they are committed, the dirty point is recomputed by
-//                             one warp against the committed lattices (now exact for it), its new claims are added,
-//                             and the scan continues behind it.  Stale claims only cause a redundant recompute.
-//                             The kernel then emits tracks / lost points in order and the bin pre-load records.
+//   K10 track_resolve_kernel  one CTA per frame; ordered fixed-point iteration.  Every tentative success claims the
+//                             features it removes with atomicMin(point index): feature c is gone FOR POINT i iff
+//                             claim[c] < i, which is exactly the lattice the sequential loop shows to point i once the
+//                             results of the points below i are right.  A point is DIRTY when a lower point claims one
+//                             of the (at most two) features its result depends on.  Each round rebuilds the claims from
+//                             the current results and recomputes, one warp per point, every point that has ever been
+//                             dirty against claim[.] < i; the rounds stop when nothing changes.  By induction over the
+//                             point index the fixed point is unique and equals the sequential result (point 0 never
+//                             depends on anyone; point i is right as soon as 0..i-1 are), and it is reached after as
+//                             many rounds as the longest dependency chain -- a handful, because the dominant conflict
+//                             (a track removes the right features in its parallax range, :611-620) stays within one
+//                             image row.  The kernel then emits tracks / lost points in order, the pruned flags and
+//                             the bin pre-load records.
 //
 // The lattice of the reference is replaced by the (row, col)-sorted feature arrays + CSR row pointers: a window's rows
 // are one contiguous index range, scanned in the reference's row-major order (ties resolve to the lowest index).
@@ -37,8 +43,11 @@ struct TrackView {
   const uint32_t* xyr;
   const uint4* dl;
   const uint4* dr;
-  const uint8_t* gone_l;   // read with ld.cg: the resolve kernel updates them between recomputes
+  const uint8_t* gone_l;   // features removed before track() (pruned flags at entry)
   const uint8_t* gone_r;
+  const int32_t* claim_l;  // when non-null: feature f is removed for point `self` iff claim[f] < self
+  const int32_t* claim_r;
+  int self;
   int rows, cols;
   double fx, fy, cx, cy, bx;
   double threshold_triangulation;   // _current_maximum_descriptor_distance_triangulation
@@ -53,7 +62,8 @@ struct Projection {
 // intensity_feature_matcher.cpp:81-148, warp-cooperative.  Returns the sorted index of the chosen feature or -1;
 // *distance = descriptor_distance_best_ of the chosen feature.
 __device__ int search_region(const int32_t* __restrict__ row_ptr, const uint32_t* __restrict__ xy,
-                             const uint4* __restrict__ desc, const uint8_t* gone, int row_reference, int col_reference,
+                             const uint4* __restrict__ desc, const uint8_t* gone, const int32_t* claim, int self,
+                             int row_reference, int col_reference,
                              const uint4& q0, const uint4& q1, int row_start, int row_end, int col_start, int col_end,
                              double maximum_distance, bool by_appearance, int* distance) {
   const int lane = threadIdx.x & 31;
@@ -64,7 +74,7 @@ __device__ int search_region(const int32_t* __restrict__ row_ptr, const uint32_t
     const uint32_t q = xy[f];
     const int col = (int)(q & 0xffffu);
     if (col < col_start || col >= col_end) continue;
-    if (__ldcg(gone + f)) continue;                                  // feature_lattice[row][col] == nullptr
+    if (claim ? __ldcg(claim + f) < self : gone[f] != 0) continue;  // feature_lattice[row][col] == nullptr
     const int d = popc256(q0, q1, desc[2 * f], desc[2 * f + 1]);
     if (!((double)d < maximum_distance)) continue;                   // :103 / :121 (strict, against the double limit)
     unsigned key;
@@ -107,7 +117,7 @@ __device__ int4 track_point(const TrackView& v, const TrackParams& tp, const Pre
   const uint4* ql = reinterpret_cast<const uint4*>(pp->descriptor_left);
   const uint4 q0 = ql[0], q1 = ql[1];
   int distance = 0;
-  const int fl = search_region(v.rpl, v.xyl, v.dl, v.gone_l, row_l, col_l, q0, q1, max(row_l - D, 0),   // :520-538
+  const int fl = search_region(v.rpl, v.xyl, v.dl, v.gone_l, v.claim_l, v.self, row_l, col_l, q0, q1, max(row_l - D, 0),   // :520-538
                                min(row_l + D + 1, v.rows), max(col_l - D, 0), min(col_l + D + 1, v.cols),
                                tp.max_distance_tracking, tp.by_appearance != 0, &distance);
   if (fl < 0) return make_int4(-1, -1, 0, kStatusLost);
@@ -128,7 +138,7 @@ __device__ int4 track_point(const TrackView& v, const TrackParams& tp, const Pre
 
   const int e = (int)fabs((double)pp->epipolar_offset);                                          // :568-569
   const uint4 l0 = v.dl[2 * fl], l1 = v.dl[2 * fl + 1];
-  const int fr = search_region(v.rpr, v.xyr, v.dr, v.gone_r, row_r, col_r, l0, l1, max(row_r - e, 0),   // :570-590
+  const int fr = search_region(v.rpr, v.xyr, v.dr, v.gone_r, v.claim_r, v.self, row_r, col_r, l0, l1, max(row_r - e, 0),   // :570-590
                                min(row_r + e + 1, v.rows), max(col_r - D, 0), min(col_r + D + 1, col_fl),
                                v.threshold_triangulation, true, &distance);
   if (fr < 0) return make_int4(fl, -1, 0, kStatusLost);
@@ -152,6 +162,9 @@ __device__ __forceinline__ TrackView make_view(const Geometry& g, const StereoPa
   v.dr = reinterpret_cast<const uint4*>(desc + (size_t)g.cap * kDescBytes);
   v.gone_l = gone_l;
   v.gone_r = gone_r;
+  v.claim_l = nullptr;
+  v.claim_r = nullptr;
+  v.self = 0;
   v.rows = g.rows;
   v.cols = g.cols;
   v.fx = sp.fx; v.fy = sp.fy; v.cx = sp.cx; v.cy = sp.cy; v.bx = sp.bx;
@@ -228,59 +241,63 @@ __global__ void __launch_bounds__(kResolveThreads) track_resolve_kernel(
   const TrackView v = make_view(g, sp, row_ptr, kp_xy, desc, n_desc, gone_l, gone_r);
   const int n_l = n_desc[0], n_r = n_desc[1];
 
-  for (int i = tid; i < n_l; i += kResolveThreads) claim_l[i] = INT32_MAX;
-  for (int i = tid; i < n_r; i += kResolveThreads) claim_r[i] = INT32_MAX;
+  __shared__ int s_count, s_changed;
+  TrackView vc = v;   // the lattice as point `self` sees it: claims of lower points
+  vc.claim_l = claim_l;
+  vc.claim_r = claim_r;
+  int32_t* worklist = lost;          // scratch until the ordered output below fills it
+  uint8_t* ever_dirty = reinterpret_cast<uint8_t*>(tracked);   // [n_previous] bytes of the (later written) pre-load array
+  for (int u = tid; u < n_previous; u += kResolveThreads) ever_dirty[u] = 0;
   if (tid < 2) s_acc[tid] = 0;
-  __syncthreads();
-  for (int u = tid; u < n_previous; u += kResolveThreads) {
-    const int4 t = tentative[u];
-    if (t.w != kStatusTracked) continue;
-    atomicMin(&claim_l[t.x], u);
-    for_each_consumed_right(v, t.x, t.y, [&](int s) { atomicMin(&claim_r[s], u); });
-  }
-  __syncthreads();
 
-  int frontier = 0;
-  while (frontier < n_previous) {
-    // lowest point at or above the frontier whose result depends on a feature a lower point consumes
-    int dirty = INT32_MAX;
-    for (int u = frontier + tid; u < n_previous; u += kResolveThreads) {
-      const int4 t = __ldcg(tentative + u);
-      const bool d = (t.x >= 0 && __ldcg(claim_l + t.x) < u) || (t.y >= 0 && __ldcg(claim_r + t.y) < u);
-      if (d) {
-        dirty = u;
-        break;
-      }
-    }
-    dirty = block_min(dirty, s_red);
-    const int stop = min(dirty, n_previous);
-    // commit [frontier, stop): these results are what the sequential loop yields
-    for (int u = frontier + tid; u < stop; u += kResolveThreads) {
+  for (int round = 0; round <= n_previous; ++round) {
+    // claims of the current results; a feature that was gone at entry is gone for everybody (claim -1)
+    for (int i = tid; i < n_l; i += kResolveThreads) claim_l[i] = gone_l[i] ? -1 : INT32_MAX;
+    for (int i = tid; i < n_r; i += kResolveThreads) claim_r[i] = gone_r[i] ? -1 : INT32_MAX;
+    if (tid == 0) s_count = 0, s_changed = 0;
+    __syncthreads();
+    for (int u = tid; u < n_previous; u += kResolveThreads) {
       const int4 t = __ldcg(tentative + u);
       if (t.w != kStatusTracked) continue;
-      gone_l[t.x] = 1;
-      for_each_consumed_right(v, t.x, t.y, [&](int s) { gone_r[s] = 1; });
+      atomicMin(&claim_l[t.x], u);
+      for_each_consumed_right(v, t.x, t.y, [&](int s) { atomicMin(&claim_r[s], u); });
     }
     __syncthreads();
-    if (dirty == INT32_MAX) break;
-    if (tid < 32) {   // the lattices now hold exactly the removals of the points below `dirty`
+    // points whose result depends on a feature a lower point removes join the set that is recomputed every round
+    for (int u = tid; u < n_previous; u += kResolveThreads) {
+      const int4 t = __ldcg(tentative + u);
+      bool d = ever_dirty[u] != 0;
+      if (!d && ((t.x >= 0 && __ldcg(claim_l + t.x) < u) || (t.y >= 0 && __ldcg(claim_r + t.y) < u))) {
+        d = true;
+        ever_dirty[u] = 1;
+        s_changed = 1;
+      }
+      if (d) worklist[atomicAdd(&s_count, 1)] = u;
+    }
+    __syncthreads();
+    const int n_work = s_count;
+    if (n_work == 0) break;
+    for (int k = tid >> 5; k < n_work; k += kResolveThreads / 32) {
+      const int u = __ldcg(worklist + k);
+      vc.self = u;
       Projection proj;
-      const int4 t = track_point(v, tp, previous + dirty, &proj);
-      if (tid == 0) {
-        tentative[dirty] = t;
-        if (t.w == kStatusTracked) {
-          gone_l[t.x] = 1;
-          atomicMin(&claim_l[t.x], dirty);
-          for_each_consumed_right(v, t.x, t.y, [&](int s) {
-            gone_r[s] = 1;
-            atomicMin(&claim_r[s], dirty);
-          });
+      const int4 t = track_point(vc, tp, previous + u, &proj);
+      if ((tid & 31) == 0) {
+        const int4 old = __ldcg(tentative + u);
+        if (old.x != t.x || old.y != t.y || old.z != t.z || old.w != t.w) {
+          tentative[u] = t;
+          s_changed = 1;
         }
       }
     }
     __syncthreads();
-    frontier = dirty + 1;
+    if (!s_changed) break;   // every point satisfies its own equation: the sequential result
+    __syncthreads();
   }
+  // the claims of the final results == matched_indices_left / _right of :646-651 (+ the parallax ranges :611-620)
+  for (int i = tid; i < n_l; i += kResolveThreads) gone_l[i] = claim_l[i] != INT32_MAX;
+  for (int i = tid; i < n_r; i += kResolveThreads) gone_r[i] = claim_r[i] != INT32_MAX;
+  __syncthreads();
 
   // ordered output: tracks (:623-643), lost points (:660-663), the tracked points as compute() pre-loads them (:147-155)
   int n_tracks = 0, n_lost = 0, landmarks = 0, accumulated = 0;
