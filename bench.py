@@ -459,8 +459,17 @@ def main():
     n_desc = float(nl.sum() + nr.sum())
     path_bytes = (2.0 * P * cam.rows * cam.cols + 8 * n_desc + 32 * n_desc + 40 * n_desc + 48.0 * nm.sum()
                   + 81.0 * nf.sum() * R)
+    # DRAM traffic of the kernel from the committed ncu --set full capture, scaled to this run's images per launch
+    traffic = None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["fast_nms_kernel"]
+        if t["image"] == "%dx%d u8" % (cam.cols, cam.rows):
+            traffic = t["dram_bytes_per_launch"] / t["images_per_launch"] * (2.0 * P / max(chunks, 1))
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"bound": "hbm", "kernel": "fast_nms_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_kind + " (of %s)" % peak_kind,
+                "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": fast_bytes / max(chunks, 1),
+                "peak_source": peak_kind + " (of %s)" % peak_kind,
                 "launch_ms": fast_ms_per_launch, "launches_per_step": chunks,
                 "kernel_share_of_step": kernel_ms[KERNEL_OF_INTEREST] / total_kernel_ms,
                 "kernel_ms_per_step": kernel_ms,
