@@ -281,7 +281,7 @@ def sequence_latency(api, configs, synth, device):
     (initialize -> compute, thresholds fed back between frames, host images in, host framepoints out, one host
     synchronisation per call): single-stream frames/s, i.e. the latency-bound regime of a live tracker."""
     out = {}
-    for name in ("kitti", "euroc"):
+    for name in ("kitti", "euroc", "hd"):     # hd: BASELINE.json configs[4] shape (1920x1080, 4k bins), one sequence
         cfg = configs.BY_NAME[name]
         cam = synth.camera(cfg.camera)
         world = synth.BandWorld(cam.cols, cam.rows, 7, max_frames=40)

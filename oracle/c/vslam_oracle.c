@@ -263,6 +263,49 @@ int orc_orb_compute(const uint8_t* img, int stride, int w, int h, const uint8_t*
   return n;
 }
 
+/* xfeatures2d/src/brief.cpp (opencv_contrib): smoothedSum() + pixelTests32() + BriefDescriptorExtractorImpl::compute() */
+int orc_brief32_compute(const uint8_t* img, int stride, int w, int h, const int8_t* tests, orc_kp* kps, int n_kps,
+                        uint8_t* desc) {
+  /* cv::integral(image, sum, CV_32S): sum is (h+1) x (w+1), sum(y, x) = sum of img[0..y) x [0..x) */
+  int32_t* sum = (int32_t*)calloc((size_t)(h + 1) * (w + 1), sizeof(int32_t));
+  const int sp = w + 1;
+  for (int y = 0; y < h; ++y) {
+    int32_t run = 0;
+    for (int x = 0; x < w; ++x) {
+      run += img[(size_t)y * stride + x];
+      sum[(size_t)(y + 1) * sp + x + 1] = sum[(size_t)y * sp + x + 1] + run;
+    }
+  }
+  const int HALF_KERNEL = 4, border = 48 / 2 + 9 / 2;   /* PATCH_SIZE = 48, KERNEL_SIZE = 9 */
+  int n = 0;
+  for (int i = 0; i < n_kps; ++i) {
+    const float x = kps[i].x, y = kps[i].y;
+    if (!(x >= border && x < w - border && y >= border && y < h - border)) continue;   /* runByImageBorder */
+    kps[n] = kps[i];
+    const int cy = (int)(y + 0.5f), cx = (int)(x + 0.5f);
+    uint8_t* d = desc + (size_t)n * 32;
+    for (int b = 0; b < 32; ++b) {
+      unsigned v = 0;
+      for (int k = 0; k < 8; ++k) {
+        const int8_t* t = tests + (b * 8 + k) * 4;
+        int s[2];
+        for (int j = 0; j < 2; ++j) {
+          const int iy = cy + t[2 * j], ix = cx + t[2 * j + 1];
+          s[j] = sum[(size_t)(iy + HALF_KERNEL + 1) * sp + ix + HALF_KERNEL + 1] -
+                 sum[(size_t)(iy + HALF_KERNEL + 1) * sp + ix - HALF_KERNEL] -
+                 sum[(size_t)(iy - HALF_KERNEL) * sp + ix + HALF_KERNEL + 1] +
+                 sum[(size_t)(iy - HALF_KERNEL) * sp + ix - HALF_KERNEL];
+        }
+        v |= (unsigned)(s[0] < s[1]) << (7 - k);
+      }
+      d[b] = (uint8_t)v;
+    }
+    ++n;
+  }
+  free(sum);
+  return n;
+}
+
 int orc_hamming256(const uint8_t* a, const uint8_t* b) {
   int d = 0;
   for (int i = 0; i < 32; ++i) d += __builtin_popcount((unsigned)(a[i] ^ b[i]));

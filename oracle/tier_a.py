@@ -170,6 +170,18 @@ def orb_compute(img, kps, blurred=None):
     return kps[:n].copy(), desc[:n].copy()
 
 
+def brief32_compute(img, kps, tests):
+    """BriefDescriptorExtractor(32) with a supplied 256 x 4 (y0, x0, y1, x1) test table -> (filtered kps, desc)"""
+    img = _img(img)
+    h, w = img.shape
+    kps = np.ascontiguousarray(kps, KP).copy()
+    tests = np.ascontiguousarray(tests, np.int8)
+    assert tests.shape == (256, 4) and np.abs(tests.astype(int)).max() <= 24
+    desc = np.zeros((max(len(kps), 1), 32), np.uint8)
+    n = lib().orc_brief32_compute(_p(img), img.strides[0], w, h, _p(tests), _p(kps), len(kps), _p(desc))
+    return kps[:n].copy(), desc[:n].copy()
+
+
 def hamming256(a, b):
     a = np.ascontiguousarray(a, np.uint8)
     b = np.ascontiguousarray(b, np.uint8)
