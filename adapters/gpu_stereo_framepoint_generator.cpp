@@ -37,11 +37,21 @@ void GpuStereoFramePointGenerator::configure() {
   c.minimum_disparity_pixels = p->minimum_disparity_pixels;
   c.maximum_epipolar_search_offset_pixels = p->maximum_epipolar_search_offset_pixels;
   c.fx = _f_x; c.fy = _f_y; c.cx = _c_x; c.cy = _c_y; c.bx = _b_x;           // :26-38
-  // the GPU path implements FAST + ORB-256, which is what every stereo configuration of the reference resolves to
-  // (parameters.cpp:341 never parses detector_type in stereo mode; BRIEF-256 / ORB-256 fall through to ORB,
-  // base_framepoint_generator.cpp:219-224; BRIEF needs opencv_contrib, :185-192)
-  if (p->detector_type != "FAST" || p->descriptor_type != "ORB")
-    throw std::runtime_error("GpuStereoFramePointGenerator::configure|only FAST + ORB-256 run on the GPU");
+  // after the base configure() the parameter holds what the reference really instantiated (base :184-224): "ORB" for
+  // ORB / ORB-256 / BRIEF-256 and for BRIEF without opencv_contrib; "BRIEF" = xfeatures2d::BriefDescriptorExtractor(32)
+  // when SRRG_PROSLAM_HAS_OPENCV_CONTRIB is defined.  parameters.cpp:341 never parses detector_type in stereo mode: FAST.
+  if (p->detector_type != "FAST")
+    throw std::runtime_error("GpuStereoFramePointGenerator::configure|only the FAST detector runs on the GPU");
+  if (p->descriptor_type == "BRIEF") {
+    if (!_brief_tests_set)
+      throw std::runtime_error("GpuStereoFramePointGenerator::configure|descriptor_type BRIEF needs setBriefTests() "
+                               "(the 256 x 4 table of opencv_contrib's generated_32.i, tools/parse_brief_generated.py)");
+    c.descriptor_type = VSLAM_DESCRIPTOR_BRIEF;
+    c.brief_tests = _brief_tests;
+  } else if (p->descriptor_type != "ORB") {
+    throw std::runtime_error("GpuStereoFramePointGenerator::configure|descriptor_type " + p->descriptor_type +
+                             " does not run on the GPU (ORB-256 and BRIEF-32 do)");
+  }
   vslam_fpg_destroy(_handle);
   _handle = nullptr;
   check(vslam_fpg_create(&c, _cuda_device, &_handle));
@@ -225,6 +235,11 @@ void GpuStereoFramePointGenerator::compute(Frame* frame_) {
   // the matched features are gone from the matchers, as after :419-420 (recoverPoints / the next track() rely on it)
   // NOTE: only the features of the SELECTED points are known here; hosts that need the exact post-compute matcher
   // state call vslam_fpg_get_matches() and prune all n_matches pairs.
+}
+
+void GpuStereoFramePointGenerator::setBriefTests(const int8_t tests_[1024]) {
+  std::memcpy(_brief_tests, tests_, sizeof(_brief_tests));
+  _brief_tests_set = true;
 }
 
 double GpuStereoFramePointGenerator::deviceSecondsKeypointDetection() const {

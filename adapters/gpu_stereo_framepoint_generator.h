@@ -26,6 +26,10 @@ class GpuStereoFramePointGenerator : public StereoFramePointGenerator {
   void compute(Frame* frame_) override;
   void recoverPoints(Frame* current_frame_, const FramePointPointerVector& lost_points_) const override;
 
+  // test table of cv::xfeatures2d::BriefDescriptorExtractor(32), needed before configure() when descriptor_type is
+  // BRIEF in a build with opencv_contrib: 256 x (y0, x0, y1, x1) in the order of generated_32.i
+  void setBriefTests(const int8_t tests_[1024]);
+
   // device seconds, the GPU counterparts of getTimeConsumptionSeconds_{keypoint_detection, ...}
   double deviceSecondsKeypointDetection() const;
   double deviceSecondsDescriptorExtraction() const;
@@ -44,6 +48,9 @@ class GpuStereoFramePointGenerator : public StereoFramePointGenerator {
   std::vector<vslam_track> _track_buffer;
   std::vector<int32_t> _lost_buffer;
   mutable std::vector<vslam_recovered_point> _recovered_buffer;
+
+  int8_t _brief_tests[1024] = {};
+  bool _brief_tests_set = false;
 
   static void fillPreviousPoint(const FramePoint* point_, vslam_previous_point& out_);
 };

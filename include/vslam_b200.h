@@ -82,7 +82,18 @@ typedef struct {
   /* capacities of the device-resident state (not reference parameters) */
   int32_t max_keypoints_per_image;                   /* descriptor-valid keypoints per image; 0 -> default */
   int32_t max_batch;                                 /* stereo pairs per batched call; 0 -> 1 */
+  /* descriptor extractor, base_framepoint_generator.cpp:184-224.  VSLAM_DESCRIPTOR_ORB (the default, 0): cv::ORB::create()
+   * -- what "ORB", "ORB-256", "BRIEF-256" and, without opencv_contrib, "BRIEF" resolve to (:187-195, :219-224).
+   * VSLAM_DESCRIPTOR_BRIEF: cv::xfeatures2d::BriefDescriptorExtractor::create(32) (:186, "BRIEF" with opencv_contrib);
+   * brief_tests then points to its 256 x 4 test table (y0, x0, y1, x1 of `SMOOTHED(y0, x0) < SMOOTHED(y1, x1)`, in the
+   * order of opencv_contrib's generated_32.i, offsets within +-24), copied at creation. */
+  int32_t descriptor_type;
+  int32_t reserved;
+  const int8_t* brief_tests;
 } vslam_fpg_config;
+
+#define VSLAM_DESCRIPTOR_ORB 0
+#define VSLAM_DESCRIPTOR_BRIEF 1
 
 /* cv::KeyPoint as the reference sees it after computeDescriptors (size 7, angle -1, octave 0, class_id -1
  * are implied: cv::FastFeatureDetector defaults) */

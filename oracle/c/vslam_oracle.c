@@ -654,11 +654,29 @@ static void brief_at(const uint8_t* blurred, int stride, int x, int y, uint8_t* 
   }
 }
 
-/* stereo_framepoint_generator.cpp:683-869 */
+/* BRIEF-32 at an integer pixel, box sums taken directly from the image (== the integral-image differences) */
+static void brief32_at(const uint8_t* img, int stride, int x, int y, const int8_t* tests, uint8_t* d) {
+  for (int b = 0; b < 32; ++b) {
+    unsigned v = 0;
+    for (int k = 0; k < 8; ++k) {
+      const int8_t* t = tests + (b * 8 + k) * 4;
+      int s[2] = {0, 0};
+      for (int j = 0; j < 2; ++j)
+        for (int dy = -4; dy <= 4; ++dy)
+          for (int dx = -4; dx <= 4; ++dx) s[j] += img[(size_t)(y + t[2 * j] + dy) * stride + x + t[2 * j + 1] + dx];
+      v |= (unsigned)(s[0] < s[1]) << (7 - k);
+    }
+    d[b] = (uint8_t)v;
+  }
+}
+
+/* stereo_framepoint_generator.cpp:683-869.  brief_tests == NULL: ORB extractor, blurred_l / blurred_r are the blurred
+ * frames; otherwise BRIEF-32 with that test table and blurred_l / blurred_r are the RAW frames. */
 int orc_recover_points(const uint8_t* blurred_l, const uint8_t* blurred_r, int stride, int rows, int cols,
                        const orc_stereo_camera* cam, const orc_previous_point* lost, int n_lost,
                        const double W[12], double min_depth, double max_depth, double max_distance_tracking,
-                       double max_distance_triangulation, double min_disparity, orc_recovered* out) {
+                       double max_distance_triangulation, double min_disparity, const int8_t* brief_tests,
+                       orc_recovered* out) {
   int n = 0;
   for (int u = 0; u < n_lost; ++u) {                                           /* :702 */
     const orc_previous_point* pp = &lost[u];
@@ -680,12 +698,14 @@ int orc_recover_points(const uint8_t* blurred_l, const uint8_t* blurred_r, int s
     /* :769-795 / :808-822 : cv::ORB::compute on the (2*border+1)^2 region around the projection with the keypoint at
      * its centre; with border >= 31 the keypoint survives ORB's 31 px border filter and its patch + blur support
      * are interior, so the descriptor is rBRIEF of the blurred frame at the projection */
-    if (border < 31) continue;                                                 /* descriptor.rows == 0 (:790-792) */
+    if (border < (brief_tests ? 28 : 31)) continue;                            /* descriptor.rows == 0 (:790-792) */
     orc_recovered r;
     memset(&r, 0, sizeof(r));
-    brief_at(blurred_l, stride, (int)plx, (int)ply, r.desc_left);
+    if (brief_tests) brief32_at(blurred_l, stride, (int)plx, (int)ply, brief_tests, r.desc_left);
+    else brief_at(blurred_l, stride, (int)plx, (int)ply, r.desc_left);
     if ((double)orc_hamming256(pp->desc_left, r.desc_left) > max_distance_tracking) continue;            /* :798-802 */
-    brief_at(blurred_r, stride, (int)prx, (int)pry, r.desc_right);
+    if (brief_tests) brief32_at(blurred_r, stride, (int)prx, (int)pry, brief_tests, r.desc_right);
+    else brief_at(blurred_r, stride, (int)prx, (int)pry, r.desc_right);
     if ((double)(plx - prx) < min_disparity) continue;                                                   /* :825-828 */
     if ((double)orc_hamming256(pp->desc_right, r.desc_right) > max_distance_tracking) continue;          /* :831-835 */
     const int d = orc_hamming256(r.desc_left, r.desc_right);                                             /* :838-843 */

@@ -63,6 +63,8 @@ class StereoFramePointGeneratorOracle:
 
     def _describe(self, img, kps):
         """computeDescriptors (:431-438) -> (filtered kps, desc)"""
+        if getattr(self.cfg, "descriptor_type", "ORB") == "BRIEF":   # :186 (no cv2 counterpart here: tier A only)
+            return tier_a.brief32_compute(img, kps, self.cfg.brief_tests)
         if self.tier == "a":
             return tier_a.orb_compute(img, kps)
         cv2 = _cv2()
@@ -131,6 +133,10 @@ class StereoFramePointGeneratorOracle:
     # ---- stereo_framepoint_generator.cpp:683-869 -----------------------------------------------
     def recover_points(self, lost, world_to_camera_left, max_distance_tracking, min_depth=0.1, max_depth=1000.0):
         """lost: tier_a.PREVIOUS_POINT records of the lost points (parameters.h:196-199 depth defaults)"""
+        if getattr(self.cfg, "descriptor_type", "ORB") == "BRIEF":
+            return tier_a.recover_points(self.images[0], self.images[1], self.stereo_camera, lost, world_to_camera_left,
+                                         min_depth, max_depth, max_distance_tracking, self.max_distance,
+                                         self.cfg.minimum_disparity_pixels, self.cfg.brief_tests)
         if self._blurred is None:
             self._blurred = (tier_a.gauss7_u8(self.images[0]), tier_a.gauss7_u8(self.images[1]))
         return tier_a.recover_points(self._blurred[0], self._blurred[1], self.stereo_camera, lost,

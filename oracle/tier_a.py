@@ -82,7 +82,7 @@ def lib():
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_recover_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                             C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
-                                            C.c_double, C.c_void_p]
+                                            C.c_double, C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -249,8 +249,10 @@ def track(fl, fr, rows, cols, cam: StereoCamera, previous, T, track_by_appearanc
 
 
 def recover_points(blurred_left, blurred_right, cam: StereoCamera, lost, world_to_camera_left, min_depth, max_depth,
-                   max_distance_tracking, max_distance_triangulation, min_disparity):
-    """StereoFramePointGenerator::recoverPoints -> RECOVERED records"""
+                   max_distance_tracking, max_distance_triangulation, min_disparity, brief_tests=None):
+    """StereoFramePointGenerator::recoverPoints -> RECOVERED records (brief_tests: BRIEF-32 on the RAW frames)"""
+    if brief_tests is not None:
+        brief_tests = np.ascontiguousarray(brief_tests, np.int8)
     bl, br = _img(blurred_left), _img(blurred_right)
     assert bl.shape == br.shape and bl.strides == br.strides
     rows, cols = bl.shape
@@ -259,7 +261,8 @@ def recover_points(blurred_left, blurred_right, cam: StereoCamera, lost, world_t
     out = np.zeros(max(len(lost), 1), RECOVERED)
     n = lib().orc_recover_points(_p(bl), _p(br), bl.strides[0], rows, cols, C.byref(cam), _p(lost), len(lost), _p(W),
                                  float(min_depth), float(max_depth), float(max_distance_tracking),
-                                 float(max_distance_triangulation), float(min_disparity), _p(out))
+                                 float(max_distance_triangulation), float(min_disparity),
+                                 None if brief_tests is None else _p(brief_tests), _p(out))
     return out[:n].copy()
 
 

@@ -63,7 +63,8 @@ class FpgConfig(C.Structure):
                 ("maximum_matching_distance_triangulation", C.c_double), ("minimum_disparity_pixels", C.c_double),
                 ("maximum_epipolar_search_offset_pixels", C.c_int32),
                 ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("bx", C.c_double),
-                ("max_keypoints_per_image", C.c_int32), ("max_batch", C.c_int32)]
+                ("max_keypoints_per_image", C.c_int32), ("max_batch", C.c_int32),
+                ("descriptor_type", C.c_int32), ("reserved", C.c_int32), ("brief_tests", C.c_void_p)]
 
 
 class AlignerParameters(C.Structure):
@@ -192,6 +193,12 @@ def make_config(cfg, cam, max_batch=1, max_keypoints=0) -> FpgConfig:
     c.fx, c.fy, c.cx, c.cy, c.bx = cam.fx, cam.fy, cam.cx, cam.cy, cam.bx
     c.max_keypoints_per_image = max_keypoints
     c.max_batch = max_batch
+    if getattr(cfg, "descriptor_type", "ORB") == "BRIEF":
+        tests = np.ascontiguousarray(cfg.brief_tests, np.int8)
+        assert tests.shape == (256, 4)
+        c.descriptor_type = 1
+        c.brief_tests = tests.ctypes.data
+        c._keep = tests                      # the library copies the table inside vslam_fpg_create
     return c
 
 

@@ -35,6 +35,11 @@ class FramePointGenerationConfig:
     maximum_matching_distance_triangulation: float = 0.2 * 256
     minimum_disparity_pixels: float = 1.0
     maximum_epipolar_search_offset_pixels: int = 0
+    # descriptor extractor (base_framepoint_generator.cpp:184-224): "ORB" = cv::ORB::create() (what every stereo YAML
+    # resolves to without opencv_contrib), "BRIEF" = xfeatures2d::BriefDescriptorExtractor::create(32) (:186), which
+    # needs its 256 x 4 (y0, x0, y1, x1) test table (opencv_contrib's generated_32.i; tools/parse_brief_generated.py)
+    descriptor_type: str = "ORB"
+    brief_tests: object = None
 
 
 @dataclasses.dataclass

@@ -23,12 +23,13 @@ struct Geometry {
   int n_regions;
   int rows_bin, cols_bin, bin_size;
   int enable_binning;
+  int border;       // keypoints closer than this to the image border get no descriptor: 31 (cv::ORB) / 28 (BRIEF-32)
 };
 
 // device-resident state of a batch of stereo pairs; image index = 2*pair + side
 struct Buffers {
   uint8_t* image;        // [2B][rows][pitch]
-  uint8_t* blurred;      // [2B][rows][pitch]
+  uint8_t* blurred;      // [2B][rows][pitch]      ORB: 7x7 Gaussian (u8) | BRIEF-32: 9x9 box sums (u16, 2 bytes per pixel)
   uint32_t* mask;        // [2B][rows][mask_words]   raw FAST keypoints (after NMS)
   int32_t* raw_count;    // [2B][n_regions]
   int32_t* row_ptr;      // [2B][rows+1]             CSR over rows of the descriptor-valid keypoints

@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable r
   }
 }
 
-// K2: gridDim.x CTAs per image, each owning a strip of image rows.  Applies cv::ORB's 31 px border filter
+// K2: gridDim.x CTAs per image, each owning a strip of image rows.  Applies the extractor's border filter (31 px cv::ORB, 28 px BRIEF-32)
 // (KeyPointsFilter::runByImageBorder), builds the CSR row pointer and the (row, col)-sorted keypoint list.
 // A CTA obtains the offset of its strip by re-counting the (L2-resident, 60 KB) mask rows above it, which is cheaper
 // than a second kernel or a cross-CTA scan; batches use one CTA per image, single frames split the image to cut latency.
@@ -326,8 +326,8 @@ __global__ void __launch_bounds__(256) compact_kernel(Geometry g, const uint32_t
   const int img = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t* m = mask + (size_t)img * g.rows * g.mask_words;
-  const int lo_x = 31, hi_x = g.cols - 31;   // keep lo_x <= x < hi_x
-  const int lo_y = 31, hi_y = g.rows - 31;
+  const int lo_x = g.border, hi_x = g.cols - g.border;   // keep lo_x <= x < hi_x (KeyPointsFilter::runByImageBorder)
+  const int lo_y = g.border, hi_y = g.rows - g.border;
   const int strip = (g.rows + gridDim.x - 1) / gridDim.x;
   const int y_begin = blockIdx.x * strip, y_end = min(g.rows, y_begin + strip);
   const bool last = blockIdx.x == gridDim.x - 1;

@@ -108,6 +108,7 @@ struct vslam_fpg {
   uint8_t* d_recover_desc = nullptr;     // [2][previous_cap][32] + [previous_cap] flags
   RecoveredRecord* d_recovered = nullptr;
   int32_t* d_recover_n = nullptr;        // {n_xy left, n_xy right, n_recovered}
+  int8_t* d_brief_tests = nullptr;       // [256][4] when descriptor_type == VSLAM_DESCRIPTOR_BRIEF
 };
 
 namespace {
@@ -147,9 +148,17 @@ void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n) {
   mark(h, lane, kEvFast1);
   launch_compact(h->g, b, 2 * p0, 2 * n, lane.stream);
   mark(h, lane, kEvCompact1);
-  launch_blur(h->g, b, 2 * p0, 2 * n, lane.stream);
-  mark(h, lane, kEvBlur1);
-  launch_describe(h->g, b, lane.blurred_map, 2 * p0, 2 * n, lane.stream);
+  if (h->d_brief_tests) {   // BRIEF-32: 9x9 box sums (u16) take the place of the blurred image
+    uint16_t* boxsum = reinterpret_cast<uint16_t*>(lane.blurred);
+    launch_box9(h->g, h->b.image + (size_t)2 * p0 * h->g.rows * h->g.pitch, boxsum, 2 * n, lane.stream);
+    mark(h, lane, kEvBlur1);
+    launch_describe_brief(h->g, boxsum, h->d_brief_tests, h->b.kp_xy + (size_t)2 * p0 * h->g.cap, h->b.n_desc + 2 * p0,
+                          h->b.desc + (size_t)2 * p0 * h->g.cap * kDescBytes, h->g.cap, 2 * n, lane.stream);
+  } else {
+    launch_blur(h->g, b, 2 * p0, 2 * n, lane.stream);
+    mark(h, lane, kEvBlur1);
+    launch_describe(h->g, b, lane.blurred_map, 2 * p0, 2 * n, lane.stream);
+  }
   mark(h, lane, kEvDescribe1);
   h->launches += 4;
 }
@@ -375,6 +384,14 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
   const double baseline_meters = -c->bx / c->fx;
   if (!(baseline_meters > 0))
     return fail(VSLAM_ERR_INVALID_ARGUMENT, "StereoFramePointGenerator::configure|invalid baseline (m): '%f' verify intrinsic camera parameters", baseline_meters);
+  if (c->descriptor_type != VSLAM_DESCRIPTOR_ORB && c->descriptor_type != VSLAM_DESCRIPTOR_BRIEF)
+    return fail(VSLAM_ERR_INVALID_ARGUMENT, "unknown descriptor_type %d", c->descriptor_type);
+  const bool brief = c->descriptor_type == VSLAM_DESCRIPTOR_BRIEF;
+  if (brief) {
+    if (!c->brief_tests) return fail(VSLAM_ERR_INVALID_ARGUMENT, "VSLAM_DESCRIPTOR_BRIEF needs brief_tests (256 x 4 int8)");
+    for (int i = 0; i < 1024; ++i)   // PATCH_SIZE / 2 of xfeatures2d/src/brief.cpp
+      if (c->brief_tests[i] < -24 || c->brief_tests[i] > 24) return fail(VSLAM_ERR_INVALID_ARGUMENT, "brief_tests[%d] outside +-24", i);
+  }
   int rc = require_device(device);
   if (rc) return rc;
 
@@ -390,6 +407,7 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
   g.n_regions = nv * nh;
   g.bin_size = c->bin_size_pixels;
   g.enable_binning = c->enable_keypoint_binning != 0;
+  g.border = brief ? 28 : 31;   // KeyPointsFilter::runByImageBorder of the extractor: PATCH/2 + KERNEL/2 | edgeThreshold
   bin_grid(g.rows, g.cols, g.bin_size, &g.rows_bin, &g.cols_bin);
   h->target_keypoints = g.rows_bin * g.cols_bin;                    // base :308
   h->target_per_detector = h->target_keypoints / g.n_regions;       // base :312 (Count)
@@ -451,11 +469,16 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
   dalloc((void**)&h->track_scratch.claim_r, (size_t)g.cap * sizeof(int32_t));
   dalloc((void**)&h->track_scratch.stats, 4 * sizeof(int32_t));
   dalloc((void**)&h->d_recover_n, 4 * sizeof(int32_t));
+  if (brief) {
+    dalloc((void**)&h->d_brief_tests, 1024);
+    if (ok && cudaMemcpy(h->d_brief_tests, c->brief_tests, 1024, cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
+  }
+  h->cfg.brief_tests = nullptr;   // the table was copied; the caller's pointer is not kept
   for (int l = 0; l < kLanes; ++l) {
-    dalloc((void**)&h->lanes[l].blurred, (size_t)2 * h->chunk * img_bytes);
+    dalloc((void**)&h->lanes[l].blurred, (size_t)2 * h->chunk * img_bytes * (brief ? 2 : 1));
     dalloc((void**)&h->lanes[l].mask, (size_t)2 * h->chunk * g.rows * g.mask_words * sizeof(uint32_t));
     if (ok && cudaStreamCreateWithFlags(&h->lanes[l].stream, cudaStreamNonBlocking) != cudaSuccess) ok = false;
-    if (ok && !make_blurred_tensor_map(g, h->lanes[l].blurred, 2 * h->chunk, &h->lanes[l].blurred_map)) {
+    if (ok && !brief && !make_blurred_tensor_map(g, h->lanes[l].blurred, 2 * h->chunk, &h->lanes[l].blurred_map)) {
       vslam_fpg_destroy(h);
       return fail(VSLAM_ERR_CUDA, "cuTensorMapEncodeTiled failed for the blurred image buffer (TMA is required: no fallback)");
     }
@@ -504,6 +527,7 @@ int vslam_fpg_destroy(vslam_fpg* h) {
   cudaFree(h->d_previous); cudaFree(h->track_scratch.tentative); cudaFree(h->track_scratch.claim_l);
   cudaFree(h->track_scratch.claim_r); cudaFree(h->track_scratch.stats); cudaFree(h->d_tracks); cudaFree(h->d_lost);
   cudaFree(h->d_recover_xy); cudaFree(h->d_recover_desc); cudaFree(h->d_recovered); cudaFree(h->d_recover_n);
+  cudaFree(h->d_brief_tests);
   cudaFreeHost(h->h_track_stats); cudaFreeHost(h->h_tracks); cudaFreeHost(h->h_lost);
   cudaFreeHost(h->h_counts); cudaFreeHost(h->h_n_desc); cudaFreeHost(h->h_n_out); cudaFreeHost(h->h_flag);
   cudaFreeHost(h->h_systems);
@@ -777,6 +801,7 @@ int vslam_fpg_recover_points(vslam_fpg* h, const vslam_previous_point* lost, int
   rp.min_depth = minimum_depth_meters;
   rp.max_depth = maximum_depth_meters;
   rp.max_distance_tracking = maximum_descriptor_distance_tracking;
+  rp.brief_tests = h->d_brief_tests;
   // the blurred images of the last initialize() are still in lane 0's scratch (pair 0)
   launch_recover(h->g, h->sp, h->b, 0, lane.blurred, h->d_previous, n_lost, rp, h->d_recover_xy, h->d_recover_n,
                  h->d_recover_desc, h->d_recovered, h->d_recover_n + 2, lane.stream);
@@ -1083,6 +1108,7 @@ int vslam_fpg_debug_blurred(vslam_fpg* h, int32_t pair, int side, uint8_t* image
   if (!h || !image) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
   if (!h->initialized || pair < 0 || pair >= h->last_pairs || h->last_pairs > h->chunk)
     return fail(VSLAM_ERR_STATE, "debug taps need a run of at most chunk=%d pairs", h->chunk);
+  if (h->d_brief_tests) return fail(VSLAM_ERR_STATE, "no blurred image with the BRIEF-32 extractor");
   CUDA_TRY(cudaSetDevice(h->device));
   const Geometry& g = h->g;
   CUDA_TRY(cudaMemcpy2D(image, g.cols, h->lanes[0].blurred + ((size_t)2 * pair + side) * g.rows * g.pitch, g.pitch, g.cols,

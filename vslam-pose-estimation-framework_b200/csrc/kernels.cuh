@@ -75,6 +75,7 @@ struct RecoverParams {
   double W[12];                    // world_to_camera_left
   double min_depth, max_depth;     // minimum_depth_meters / maximum_depth_meters
   double max_distance_tracking;
+  const int8_t* brief_tests;       // non-null: BRIEF-32 on the box-sum images instead of rBRIEF on the blurred ones
 };
 
 // all launches are asynchronous on `stream`; image ranges are [first_image, first_image + n_images)
@@ -105,6 +106,12 @@ int kernels_per_match_pass();
 // writes desc[(i * stride + k) * 32]
 void launch_describe_at(const Geometry& g, const uint8_t* blurred, const uint32_t* xy, const int32_t* n, uint8_t* desc,
                         int stride, int n_images, cudaStream_t stream);
+// BRIEF-32 (cv::xfeatures2d::BriefDescriptorExtractor, base_framepoint_generator.cpp:186): 9x9 box sums of the images
+// (u16 [n_images][rows][pitch]) and the 256 box-sum comparisons of a supplied test table (device, 256 x 4 int8:
+// y0, x0, y1, x1) at the keypoints xy[i * stride .. + n[i]) of image i
+void launch_box9(const Geometry& g, const uint8_t* image, uint16_t* boxsum, int n_images, cudaStream_t stream);
+void launch_describe_brief(const Geometry& g, const uint16_t* boxsum, const int8_t* tests, const uint32_t* xy,
+                           const int32_t* n, uint8_t* desc, int stride, int n_images, cudaStream_t stream);
 // StereoFramePointGenerator::track for pair `pair`: two launches (parallel search, ordered resolution).  Marks the
 // consumed features in pruned_l / consumed_r, writes tracks / lost (ordered), the bin pre-load records and stats.
 void launch_track(const Geometry& g, const StereoParams& sp, const Buffers& b, int pair, const PreviousPoint* previous,

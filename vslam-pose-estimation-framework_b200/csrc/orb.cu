@@ -363,6 +363,84 @@ void launch_blur(const Geometry& g, const Buffers& b, int first_image, int n_ima
                                         b.blurred + (size_t)first_image * g.rows * g.pitch);
 }
 
+// ---- BRIEF-32 (cv::xfeatures2d::BriefDescriptorExtractor::create(32), reference base_framepoint_generator.cpp:186;
+// algorithm of opencv_contrib xfeatures2d/src/brief.cpp).  The extractor compares 9 x 9 box sums read from an integral
+// image; the same integers come from a box-sum image (<= 81 * 255 fits u16), computed once per frame.
+
+constexpr int BX_W = 128, BX_H = 32;
+
+__global__ void __launch_bounds__(256) box9_kernel(Geometry g, const uint8_t* __restrict__ image,
+                                                   uint16_t* __restrict__ boxsum) {
+  __shared__ uint8_t s_in[BX_H + 8][BX_W + 16];
+  __shared__ uint16_t s_row[BX_H + 8][BX_W];
+  const int tid = threadIdx.x, img = blockIdx.z;
+  const int x0 = blockIdx.x * BX_W, y0 = blockIdx.y * BX_H;
+  const uint8_t* base = image + (size_t)img * g.rows * g.pitch;
+  for (int i = tid; i < (BX_H + 8) * (BX_W + 8); i += 256) {
+    const int r = i / (BX_W + 8), c = i - r * (BX_W + 8);
+    const int gy = y0 - 4 + r, gx = x0 - 4 + c;
+    s_in[r][c] = (gy >= 0 && gy < g.rows && gx >= 0 && gx < g.cols) ? base[(size_t)gy * g.pitch + gx] : 0;
+  }
+  __syncthreads();
+  for (int i = tid; i < (BX_H + 8) * BX_W; i += 256) {
+    const int r = i / BX_W, c = i - r * BX_W;
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) v += s_in[r][c + k];
+    s_row[r][c] = (uint16_t)v;
+  }
+  __syncthreads();
+  uint16_t* out = boxsum + (size_t)img * g.rows * g.pitch;
+  for (int i = tid; i < BX_H * BX_W; i += 256) {
+    const int r = i / BX_W, c = i - r * BX_W;
+    if (y0 + r >= g.rows || x0 + c >= g.pitch) continue;
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) v += s_row[r + k][c];
+    out[(size_t)(y0 + r) * g.pitch + x0 + c] = (uint16_t)v;
+  }
+}
+
+// one warp per keypoint, lane b -> descriptor byte b: tests 8b .. 8b+7, bit (7 - k) = test 8b + k (generated_32.i)
+__global__ void __launch_bounds__(256) describe_brief_kernel(Geometry g, const uint16_t* __restrict__ boxsum,
+                                                             const int8_t* __restrict__ tests,
+                                                             const uint32_t* __restrict__ kp_xy,
+                                                             const int32_t* __restrict__ n_desc,
+                                                             uint8_t* __restrict__ desc, int kp_stride) {
+  __shared__ int8_t s_tests[1024];
+  const int img = blockIdx.y, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 1024; i += 256) s_tests[i] = tests[i];
+  __syncthreads();
+  const int n = n_desc[img];
+  const uint16_t* S = boxsum + (size_t)img * g.rows * g.pitch;
+  const uint32_t* xy = kp_xy + (size_t)img * kp_stride;
+  uint8_t* out = desc + (size_t)img * kp_stride * kDescBytes;
+  for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) {
+    const uint32_t q = xy[i];
+    const int cx = (int)(q & 0xffffu), cy = (int)(q >> 16);   // (int)(pt + 0.5) of integer-valued coordinates
+    unsigned v = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int8_t* t = s_tests + (lane * 8 + k) * 4;
+      const int a = S[(size_t)(cy + t[0]) * g.pitch + cx + t[1]];
+      const int b = S[(size_t)(cy + t[2]) * g.pitch + cx + t[3]];
+      v |= (unsigned)(a < b) << (7 - k);
+    }
+    out[(size_t)i * kDescBytes + lane] = (uint8_t)v;
+  }
+}
+
+void launch_box9(const Geometry& g, const uint8_t* image, uint16_t* boxsum, int n_images, cudaStream_t stream) {
+  dim3 grid((g.cols + BX_W - 1) / BX_W, (g.rows + BX_H - 1) / BX_H, n_images);
+  box9_kernel<<<grid, 256, 0, stream>>>(g, image, boxsum);
+}
+
+void launch_describe_brief(const Geometry& g, const uint16_t* boxsum, const int8_t* tests, const uint32_t* xy,
+                           const int32_t* n, uint8_t* desc, int stride, int n_images, cudaStream_t stream) {
+  dim3 grid(n_images <= 8 ? 64 : 16, n_images);
+  describe_brief_kernel<<<grid, 256, 0, stream>>>(g, boxsum, tests, xy, n, desc, stride);
+}
+
 // opt in to > 48 KB dynamic shared memory once per device
 static void configure_describe() {
   static unsigned long long configured = 0;

@@ -399,7 +399,8 @@ __global__ void __launch_bounds__(256) recover_project_kernel(Geometry g, Stereo
   const float hx = __fsub_rn(__fsub_rn((float)g.cols, border), 1.0f), hy = __fsub_rn(__fsub_rn((float)g.rows, border), 1.0f);
   if (!(plx >= lo && plx <= hx && prx >= lo && prx <= hx && ply >= lo && ply <= hy && pry >= lo && pry <= hy))
     ok = false;                                                                                  // :751-766 (NaN fails)
-  if (border < 31.0f) ok = false;   // ORB's 31 px border filter would drop the keypoint: descriptor.rows == 0 (:790-792)
+  // the extractor's own border filter on the (2 border + 1)^2 region would drop the keypoint: descriptor.rows == 0 (:790-792)
+  if (border < (float)g.border) ok = false;
   uint32_t l = 31u | (31u << 16), r = l;   // any interior pixel: the descriptor of a rejected slot is never read
   if (ok) {
     l = (uint32_t)(int)plx | ((uint32_t)(int)ply << 16);
@@ -490,7 +491,10 @@ void launch_recover(const Geometry& g, const StereoParams& sp, const Buffers& b,
   uint8_t* valid = desc + (size_t)2 * stride * kDescBytes;
   if (n_lost > 0) {
     recover_project_kernel<<<(n_lost + 255) / 256, 256, 0, stream>>>(g, sp, rp, lost, n_lost, xy, stride, valid, n_xy);
-    launch_describe_at(g, blurred, xy, n_xy, desc, stride, 2, stream);
+    if (rp.brief_tests)
+      launch_describe_brief(g, reinterpret_cast<const uint16_t*>(blurred), rp.brief_tests, xy, n_xy, desc, stride, 2, stream);
+    else
+      launch_describe_at(g, blurred, xy, n_xy, desc, stride, 2, stream);
   }
   recover_finish_kernel<<<1, kResolveThreads, 0, stream>>>(sp, rp, b.n_desc + 2 * pair, lost, n_lost, xy, stride,
                                                            valid, desc, out, n_out);

@@ -125,6 +125,17 @@ def _pair_job(args):
     return band_world_pair(*args)
 
 
+def brief_test_table(seed: int = 32) -> np.ndarray:
+    """A seeded 256 x 4 (y0, x0, y1, x1) BRIEF test table drawn like the original BRIEF sampling (isotropic Gaussian,
+    sigma = patch / 5, clipped to the 48 px patch).  It is NOT opencv_contrib's generated_32.i (absent from this image):
+    it exercises the table-parametric BRIEF-32 path; the reference's table is supplied by the host at run time."""
+    rng = np.random.default_rng(seed)
+    t = np.clip(np.rint(rng.normal(0.0, 48 / 5.0, (256, 4))), -24, 24).astype(np.int8)
+    same = (t[:, 0] == t[:, 2]) & (t[:, 1] == t[:, 3])
+    t[same, 3] = np.where(t[same, 3] < 24, t[same, 3] + 1, t[same, 3] - 1)
+    return t
+
+
 # ---------------------------------------------------------------------------------------------
 # aligner stress set (config 4)
 # ---------------------------------------------------------------------------------------------
