@@ -350,3 +350,35 @@ def test_rows_with_more_than_32_features_take_the_general_scan_path():
     _same_points(gen.matches(), o.matches)
     _same_points(fps, o.framepoints())
     gen.close()
+
+
+@pytest.mark.parametrize("threshold", [0, 1, 2, 5, 127, 128, 200])
+def test_fast_threshold_extremes(threshold):
+    """t = 0 takes the exactly packed arc test, t >= 1 the multiply-add packing with the biased dark lane, t > 127 the
+    path without the byte-SIMD pre-test: all must give cv::FAST's keypoints and scores"""
+    cfg = configs.KITTI
+    cam = synth.camera(cfg.camera)
+    rng = np.random.default_rng(threshold)
+    left, right = synth.band_world_pair(cfg.camera, 3)
+    # low-contrast noise patches (differences of 0, 1, 2 around a flat level) and saturated blocks
+    left = left.copy()
+    left[40:140, 100:400] = 100 + rng.integers(0, 3, (100, 300))
+    left[200:300, 500:900] = np.where(rng.random((100, 400)) < 0.5, 0, 255)
+    gen = api.StereoFramePointGenerator(cfg, cam, max_keypoints=65535)
+    gen.thresholds = [threshold]
+    try:
+        gen.initialize(left, right, True)
+    except api.VslamError as e:          # t = 0 on noise: more keypoints than any handle can hold is a capacity error
+        assert e.code == -3 and threshold == 0
+        gen.close()
+        return
+    kps = tier_a.fast_detect(left, threshold)
+    want = np.zeros((cam.rows, cam.cols), bool)
+    want[kps["y"].astype(int), kps["x"].astype(int)] = True
+    assert np.array_equal(gen.debug_keypoint_mask(0), want)
+    k, _ = gen.features(0)
+    keep = (kps["x"] >= 31) & (kps["x"] < cam.cols - 31) & (kps["y"] >= 31) & (kps["y"] < cam.rows - 31)
+    ref = kps[keep]
+    order = np.lexsort((ref["x"], ref["y"]))
+    assert np.array_equal(k["x"], ref["x"][order]) and np.array_equal(k["response"], ref["response"][order])
+    gen.close()

@@ -86,13 +86,23 @@ __device__ __forceinline__ int fast_score_at(Ptr p, int pitch, int t) {
 // max(A, -B) of cornerScore<16> with packed 16-bit lanes: lane lo carries d = v - ring, lane hi carries -d, so one
 // VIMNMX3.S16x2 chain yields both "max over 9-arcs of min(d)" (lo) and "max over 9-arcs of min(-d)" = -min-max (hi).
 // The pixel is a FAST corner at threshold t iff the result is > t; its OpenCV score is the result - 1.
+//
+// BIASED = true packs with ONE multiply-add per ring pixel: ring * 0xFFFF + v * (1 - 2^16) = d - (d << 16), whose low
+// half is d and whose high half is -d - [d < 0] (the borrow of the low half).  The dark lane is therefore one too
+// small exactly for the elements that can form a dark arc (d < 0): an arc minimum m >= 1 in that lane is the true
+// minimum - 1, and m <= 0 means the true minimum is <= 1.  For thresholds t >= 1 (every threshold the reference's
+// controller can produce; t = 0 takes the exact packing) max(lo, hi + 1) is therefore exact whenever it exceeds t,
+// and never exceeds t otherwise.
+template <bool BIASED>
 __device__ __forceinline__ int arc_strength(const uint8_t* p) {
   const int v = p[0];
   unsigned P[16];
-#define F(k, dx, dy)                                            \
-  {                                                             \
-    const int r = p[(dy) * SW + (dx)];                          \
-    P[k] = __byte_perm((unsigned)(v - r), (unsigned)(r - v), 0x5410); \
+  const unsigned vv = (unsigned)v * 0xFFFF0001u;
+#define F(k, dx, dy)                                                        \
+  {                                                                         \
+    const int r = p[(dy) * SW + (dx)];                                      \
+    if (BIASED) P[k] = (unsigned)r * 0xFFFFu + vv;                          \
+    else P[k] = __byte_perm((unsigned)(v - r), (unsigned)(r - v), 0x5410);  \
   }
   VSLAM_RING(F)
 #undef F
@@ -106,7 +116,7 @@ __device__ __forceinline__ int arc_strength(const uint8_t* p) {
   for (int i = 0; i < 5; ++i) g[i] = __vimax3_s16x2(m9[3 * i], m9[3 * i + 1], m9[3 * i + 2]);
   g[5] = m9[15];
   const unsigned m = __vmaxs2(__vimax3_s16x2(g[0], g[1], g[2]), __vimax3_s16x2(g[3], g[4], g[5]));
-  return max((int)(short)(m & 0xffffu), (int)(short)(m >> 16));
+  return max((int)(short)(m & 0xffffu), (int)(short)(m >> 16) + (BIASED ? 1 : 0));
 }
 
 // |d| > t per byte lane (t <= 127): bit 7 of each byte of the result.  VABSDIFF4 is the one native byte-SIMD op.
@@ -270,7 +280,8 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable r
     if (c < ncand) {
       code = list[c];
       const int sy = code >> 8, sx = code & 0xff;
-      s = arc_strength(&s_img[sy + 3][sx + HX - 1]);
+      const uint8_t* px = &s_img[sy + 3][sx + HX - 1];
+      s = t >= 1 ? arc_strength<true>(px) : arc_strength<false>(px);
       if (s > t) s_score[sy][sx] = (uint8_t)(s - 1);
     }
     const int sy = code >> 8, sx = code & 0xff;
