@@ -324,10 +324,12 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable r
   }
 }
 
-// K2: gridDim.x CTAs per image, each owning a strip of image rows.  Applies the extractor's border filter (31 px cv::ORB, 28 px BRIEF-32)
-// (KeyPointsFilter::runByImageBorder), builds the CSR row pointer and the (row, col)-sorted keypoint list.
-// A CTA obtains the offset of its strip by re-counting the (L2-resident, 60 KB) mask rows above it, which is cheaper
-// than a second kernel or a cross-CTA scan; batches use one CTA per image, single frames split the image to cut latency.
+// K2: gridDim.x CTAs per image, each owning a strip of image rows.  Applies the extractor's border filter (31 px
+// cv::ORB, 28 px BRIEF-32: KeyPointsFilter::runByImageBorder), builds the CSR row pointer and the (row, col)-sorted
+// keypoint list.  One THREAD per image row: a row of the bit mask is a few uint4, all loads of a thread are independent
+// (one memory round trip instead of one per row of a warp-per-row loop), the row counts meet in a block scan and every
+// thread then emits its own row in order.  A CTA obtains the offset of its strip by re-counting the (L2-resident) mask
+// rows above it; batches use one CTA per image, single frames split the image to cut latency.
 __global__ void __launch_bounds__(256) compact_kernel(Geometry g, const uint32_t* __restrict__ mask,
                                                       int32_t* __restrict__ row_ptr, uint32_t* __restrict__ kp_xy,
                                                       int32_t* __restrict__ n_desc, int32_t* __restrict__ error_flag) {
@@ -337,28 +339,37 @@ __global__ void __launch_bounds__(256) compact_kernel(Geometry g, const uint32_t
   const int img = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t* m = mask + (size_t)img * g.rows * g.mask_words;
-  const int lo_x = g.border, hi_x = g.cols - g.border;   // keep lo_x <= x < hi_x (KeyPointsFilter::runByImageBorder)
+  const int lo_x = g.border, hi_x = g.cols - g.border;   // keep lo_x <= x < hi_x
   const int lo_y = g.border, hi_y = g.rows - g.border;
   const int strip = (g.rows + gridDim.x - 1) / gridDim.x;
   const int y_begin = blockIdx.x * strip, y_end = min(g.rows, y_begin + strip);
   const bool last = blockIdx.x == gridDim.x - 1;
+  // words that can hold a kept column, and the masks of the two partial words
+  const int w_lo = lo_x >> 5, w_hi = min(g.mask_words - 1, (hi_x - 1) >> 5);
+  const uint32_t m_lo = 0xffffffffu << (lo_x & 31);
+  const uint32_t m_hi = ((hi_x & 31) == 0) ? 0xffffffffu : (0xffffffffu >> (32 - (hi_x & 31)));
 
-  auto valid_word = [&](int y, int wd) -> uint32_t {
-    uint32_t w = m[(size_t)y * g.mask_words + wd];
-    const int bx = wd * 32;
-    if (bx < lo_x) w &= (lo_x - bx >= 32) ? 0u : (0xffffffffu << (lo_x - bx));
-    if (bx + 32 > hi_x) w &= (hi_x - bx <= 0) ? 0u : (0xffffffffu >> (32 - (hi_x - bx)));
+  auto clip = [&](uint32_t w, int wd) -> uint32_t {
+    if (wd < w_lo || wd > w_hi) return 0u;
+    if (wd == w_lo) w &= m_lo;
+    if (wd == w_hi) w &= m_hi;
     return w;
+  };
+  auto count_row = [&](int y) -> int {
+    if (y < lo_y || y >= hi_y || hi_x <= lo_x) return 0;
+    const uint4* row = reinterpret_cast<const uint4*>(m + (size_t)y * g.mask_words);
+    int c = 0;
+    for (int q = w_lo >> 2; q <= (w_hi >> 2); ++q) {
+      const uint4 v = __ldg(row + q);
+      c += __popc(clip(v.x, 4 * q)) + __popc(clip(v.y, 4 * q + 1)) + __popc(clip(v.z, 4 * q + 2)) + __popc(clip(v.w, 4 * q + 3));
+    }
+    return c;
   };
 
   // offset of the strip: keypoints in the rows above it
   {
     int c = 0;
-    const int r0 = lo_y, r1 = min(y_begin, hi_y);
-    for (int i = tid; i < (r1 - r0) * g.mask_words; i += 256) {
-      const int y = r0 + i / g.mask_words, wd = i - (y - r0) * g.mask_words;
-      c += __popc(valid_word(y, wd));
-    }
+    for (int y = lo_y + tid; y < min(y_begin, hi_y); y += 256) c += count_row(y);
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (lane == 0) s_warp[warp] = c;
     __syncthreads();
@@ -371,18 +382,12 @@ __global__ void __launch_bounds__(256) compact_kernel(Geometry g, const uint32_t
   }
 
   // per-row counts of the strip
-  for (int y = y_begin + warp; y < y_end; y += 8) {
-    int c = 0;
-    if (y >= lo_y && y < hi_y)
-      for (int wd = lane; wd < g.mask_words; wd += 32) c += __popc(valid_word(y, wd));
-    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0) s_rows[y - y_begin] = c;
-  }
+  const int n_rows = y_end - y_begin;
+  for (int r = tid; r < n_rows; r += 256) s_rows[r] = count_row(y_begin + r);
   __syncthreads();
 
   // block-wide exclusive scan over the strip's rows (chunks of 256)
   int carry = s_base;
-  const int n_rows = y_end - y_begin;
   for (int b0 = 0; b0 < n_rows; b0 += 256) {
     const int r = b0 + tid;
     const int v = r < n_rows ? s_rows[r] : 0;
@@ -412,30 +417,26 @@ __global__ void __launch_bounds__(256) compact_kernel(Geometry g, const uint32_t
   int32_t* rp = row_ptr + (size_t)img * (g.rows + 1);
   for (int r = tid; r < n_rows + (last ? 1 : 0); r += 256) rp[y_begin + r] = min(s_rows[r], g.cap);
 
-  // ordered emission
+  // ordered emission: every thread writes the keypoints of its rows, ascending column
   uint32_t* xy = kp_xy + (size_t)img * g.cap;
-  for (int y = max(lo_y, y_begin) + warp; y < min(hi_y, y_end); y += 8) {
-    if (s_rows[y - y_begin + 1] == s_rows[y - y_begin]) continue;
-    int row_base = s_rows[y - y_begin];
-    for (int w0 = 0; w0 < g.mask_words; w0 += 32) {
-      const int wd = w0 + lane;
-      const uint32_t w = wd < g.mask_words ? valid_word(y, wd) : 0u;
-      const int c = __popc(w);
-      int inc = c;
-      for (int o = 1; o < 32; o <<= 1) {
-        const int n = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += n;
+  for (int r = tid; r < n_rows; r += 256) {
+    int idx = s_rows[r];
+    if (s_rows[r + 1] == idx) continue;
+    const int y = y_begin + r;
+    const uint4* row = reinterpret_cast<const uint4*>(m + (size_t)y * g.mask_words);
+    for (int q = w_lo >> 2; q <= (w_hi >> 2); ++q) {
+      const uint4 v = __ldg(row + q);
+      const uint32_t w4[4] = {clip(v.x, 4 * q), clip(v.y, 4 * q + 1), clip(v.z, 4 * q + 2), clip(v.w, 4 * q + 3)};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t bits = w4[j];
+        while (bits) {
+          const int bpos = __ffs(bits) - 1;
+          bits &= bits - 1;
+          if (idx < g.cap) xy[idx] = (uint32_t)((4 * q + j) * 32 + bpos) | ((uint32_t)y << 16);
+          ++idx;
+        }
       }
-      int idx = row_base + inc - c;
-      uint32_t bits = w;
-      while (bits) {
-        const int b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        const int x = wd * 32 + b;
-        if (idx < g.cap) xy[idx] = (uint32_t)x | ((uint32_t)y << 16);
-        ++idx;
-      }
-      row_base += __shfl_sync(0xffffffffu, inc, 31);
     }
   }
 }

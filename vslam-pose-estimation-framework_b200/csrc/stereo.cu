@@ -500,11 +500,9 @@ void launch_select(const Geometry& g, const StereoParams& sp, const Buffers& b, 
   // shared state of the strip kernel: 12 B per bin + one counter per bin row
   const size_t smem = (size_t)g.rows_bin * g.cols_bin * 12 + (size_t)(g.rows_bin + 1) * 4;
   if (!generic && smem <= 160 * 1024) {
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    // opt in to > 48 KB dynamic shared memory; the attribute is per device, so it is simply set whenever it is needed
+    if (smem > 48 * 1024)
       cudaFuncSetAttribute(select_strips_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      configured = smem;
-    }
     select_strips_kernel<<<n_pairs, kSelectWarps * 32, smem, stream>>>(
         g, sp, b.row_ptr + (size_t)2 * first_pair * (g.rows + 1), b.kp_xy + (size_t)2 * first_pair * g.cap,
         b.n_desc + 2 * first_pair, b.match + (size_t)first_pair * g.cap, n_passes, tracked, n_tracked,
