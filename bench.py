@@ -59,8 +59,10 @@ def _cpu_init(left, right, rounds):
     _CPU.update(left=left, right=right, rounds=rounds)
 
 
-def _cpu_pair(i):
-    """one stereo pair through the reference's CPU path (OpenCV primitives, 1 thread): returns n framepoints"""
+def _cpu_pair(i, as_configured=False):
+    """one stereo pair through the reference's CPU path (OpenCV primitives, 1 thread): returns n framepoints.
+    as_configured: also run the FLANN knnMatch + findHomography block that `use_matches: true` executes and whose
+    results the reference never reads (stereo_framepoint_generator.cpp:168-273)"""
     from oracle import pipeline, tier_a
     from vslam_b200 import configs, synth
     cfg, acfg = configs.BY_NAME[CONFIG_NAME], configs.ALIGNER_BY_NAME[CONFIG_NAME]
@@ -71,6 +73,8 @@ def _cpu_pair(i):
     gen = _CPU["gen"]
     gen.thresholds[:] = cfg.detector_threshold_minimum       # every pair is a first frame
     gen.initialize(_CPU["left"][i], _CPU["right"][i], True)
+    if as_configured:
+        gen.dead_use_matches_block()
     gen.compute()
     fp = gen.framepoints()
     moving = np.ascontiguousarray(fp["cam"])
@@ -98,7 +102,16 @@ def cpu_baseline(left, right, rounds, sample):
     for i in range(n):
         _cpu_pair(i)
     dt = time.perf_counter() - t0
+    n2 = min(12, n)          # the as-configured variant is several times slower: a smaller sample
+    t0 = time.perf_counter()
+    for i in range(n2):
+        _cpu_pair(i, as_configured=True)
+    dt2 = time.perf_counter() - t0
     return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+            "as_configured": {"value": n2 / dt2, "unit": "frames/s", "sample": "%d pairs" % n2,
+                              "what": "the same plus the FLANN knnMatch(k=2) + findHomography(RANSAC) block that "
+                                      "use_matches: true (struct default) executes and never reads "
+                                      "(stereo_framepoint_generator.cpp:168-273)"},
             "sample": "%d of the same KITTI-shape pairs, oracle tier B (cv2 %s FAST/ORB with cv2.setNumThreads(0) as "
                       "executables/app.cpp:96, C -O2 stereo scan/bins/triangulation/linearize x%d), one thread; the "
                       "reference's dead use_matches FLANN block is not executed" % (n, cv2.__version__, rounds),

@@ -152,6 +152,26 @@ class StereoFramePointGeneratorOracle:
         self.matches, self.winners = r["matches"], r["winners"]
         return r
 
+    # ---- stereo_framepoint_generator.cpp:168-273 ------------------------------------------------
+    def dead_use_matches_block(self):
+        """The block `use_matches: true` (the struct default, parameters.h:224-237; kitti_fast / euroc YAMLs do not
+        override it) executes at the top of compute(): CV_32F conversion of both descriptor matrices, FLANN knnMatch
+        (k = 2) and cv::findHomography(RANSAC, reproject 1, 1000 iterations, confidence 0.99).  Its results
+        (left_good_points / right_good_points) are never read: it only costs time.  Tier B (cv2) only; used by
+        bench.py to time the reference's CPU path *as configured*."""
+        cv2 = _cv2()
+        if len(self.desc_left) < 4 or len(self.desc_right) < 4:
+            return 0
+        d1, d2 = self.desc_left.astype(np.float32), self.desc_right.astype(np.float32)          # :199-205
+        matcher = cv2.DescriptorMatcher_create(cv2.DescriptorMatcher_FLANNBASED)                 # :175-177
+        knn = matcher.knnMatch(d1, d2, 2)                                                        # :206
+        q = np.fromiter((m[0].queryIdx for m in knn), np.int64, len(knn))                        # :224-238
+        t = np.fromiter((m[0].trainIdx for m in knn), np.int64, len(knn))
+        p1 = np.stack([self.kps_left["x"][q], self.kps_left["y"][q]], 1).astype(np.float64)
+        p2 = np.stack([self.kps_right["x"][t], self.kps_right["y"][t]], 1).astype(np.float64)
+        _, mask = cv2.findHomography(p1, p2, cv2.RANSAC, 1.0, maxIters=1000, confidence=0.99)    # :242-246
+        return 0 if mask is None else int(mask.sum())
+
     def framepoints(self):
         """new framepoints appended to frame->points() (only new matches; pre-loaded ones excluded)"""
         w = self.winners[self.winners >= 0]
