@@ -41,7 +41,7 @@ int main() {
   const cuuint32_t box[3] = {BW, BH, 1}; const cuuint32_t es[3] = {1, 1, 1};
   CUresult r = ((Enc)fn)(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   printf("encode: %d\n", (int)r);
-  const int cases[4][3] = {{0, 0, 0}, {16, 18, 1}, {1136, 338, 1}, {240, 17, 0}};
+  const int cases[6][3] = {{0, 0, 0}, {16, 18, 1}, {1136, 338, 1}, {240, 17, 0}, {-16, -4, 0}, {-16, 360, 1}};
   for (auto& c : cases) {
     probe<<<1, 128>>>(map, c[0], c[1], c[2], o);
     e = cudaDeviceSynchronize();
@@ -50,7 +50,7 @@ int main() {
     int bad = 0;
     for (int yy = 0; yy < BH; ++yy) for (int xx = 0; xx < BW; ++xx) {
       const int gx = c[0] + xx, gy = c[1] + yy;
-      const uint8_t want = (gx < pitch && gy < rows) ? h[((size_t)c[2] * rows + gy) * pitch + gx] : 0;
+      const uint8_t want = (gx >= 0 && gy >= 0 && gx < pitch && gy < rows) ? h[((size_t)c[2] * rows + gy) * pitch + gx] : 0;
       bad += got[yy * BW + xx] != want;
     }
     printf("case (%d,%d,%d): %s, mismatches %d\n", c[0], c[1], c[2], cudaGetErrorString(e), bad);

@@ -129,7 +129,8 @@ __device__ __forceinline__ uint32_t absdiff_gt(uint32_t ring, uint32_t center, u
 // tile is staged, every warp runs a PRIVATE pipeline over its 4 pre-test rows (no atomics, no block barrier between
 // the two expensive phases):
 //   phase 1  all pixels, 4 per thread, byte-SIMD: every 9-arc contains two ADJACENT compass points (N,E,S,W), so a
-//            corner needs (|dN|>t or |dS|>t) and (|dE|>t or |dW|>t)  (~14 % pass) -> ballot-compacted candidate list
+//            corner needs (|dN|>t or |dS|>t) and (|dE|>t or |dW|>t)  (~14 % pass); each lane keeps the flags of its 20
+//            pixels in one register and one warp scan turns them into the warp's candidate list
 //   phase 2  candidates: packed arc minima -> corner decision AND cornerScore<16> -> score tile; the list is
 //            compacted in place to the corners inside the tile
 //   phase 3  (after one block barrier) strict 3x3 non-maximum suppression of the listed corners -> keypoint bit mask
@@ -158,24 +159,13 @@ __device__ __forceinline__ uint32_t compass_pretest(const uint8_t (*s_img)[SW], 
   return m;
 }
 
-// append the up-to-4 candidates of every lane to the warp's list (bit-plane major; the order is irrelevant)
-__device__ __forceinline__ void append_candidates(uint16_t* list, int& n, uint32_t m, int code, uint32_t lt) {
-  const unsigned b0 = __ballot_sync(0xffffffffu, m & 0x00000080u);
-  const unsigned b1 = __ballot_sync(0xffffffffu, m & 0x00008000u);
-  const unsigned b2 = __ballot_sync(0xffffffffu, m & 0x00800000u);
-  const unsigned b3 = __ballot_sync(0xffffffffu, m & 0x80000000u);
-  const int p1 = n + __popc(b0), p2 = p1 + __popc(b1), p3 = p2 + __popc(b2);
-  if (m & 0x00000080u) list[n + __popc(b0 & lt)] = (uint16_t)code;
-  if (m & 0x00008000u) list[p1 + __popc(b1 & lt)] = (uint16_t)(code + 1);
-  if (m & 0x00800000u) list[p2 + __popc(b2 & lt)] = (uint16_t)(code + 2);
-  if (m & 0x80000000u) list[p3 + __popc(b3 & lt)] = (uint16_t)(code + 3);
-  n = p3 + __popc(b3);
-}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable rt, const uint8_t* __restrict__ image,
-                                                       uint32_t* __restrict__ mask, int32_t* __restrict__ raw_count,
-                                                       int single_region) {
-  __shared__ __align__(16) uint8_t s_img[SH][SW];
+__global__ void __launch_bounds__(256) fast_nms_kernel(const __grid_constant__ CUtensorMap image_map, Geometry g,
+                                                       RegionTable rt, int first_image, uint32_t* __restrict__ mask,
+                                                       int32_t* __restrict__ raw_count, int single_region) {
+  __shared__ __align__(128) uint8_t s_img[SH][SW];
+  __shared__ __align__(8) unsigned long long s_bar;
   __shared__ __align__(16) uint8_t s_score[CH][CPITCH];
   __shared__ uint16_t s_list[8][kListCap];     // position codes (sy << 8 | sx)
   __shared__ uint32_t s_mask[TH][4];
@@ -201,29 +191,32 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable r
     return;
   }
 
-  // ---- phase 0: stage the tile (+halo) in shared memory: 38 rows x 10 uint4, coalesced 16 B loads; clear state.
-  // Thread -> (row r0 + 25*pass, 16-byte chunk c) is fixed, so the address arithmetic is done once per thread.
+  // ---- phase 0: ONE TMA box load (cp.async.bulk.tensor.3d, 160 x 38 bytes: the tile + 16 / 4 px halo, zero fill
+  // outside the image; x0 - 16 is a multiple of 16 as TMA requires) stages the tile while the threads clear the state
+  if (tid == 0) {
+    const uint32_t bar = smem_u32(&s_bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(SW * SH) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(&s_img[0][0])), "l"(&image_map), "r"(bar), "r"(x0 - HX), "r"(y0 - 4), "r"(first_image + img)
+        : "memory");
+  }
   {
-    const uint8_t* base = image + (size_t)img * g.rows * g.pitch;
-    const int c = tid % (SW / 16), r0 = tid / (SW / 16);   // 250 loader threads: 25 rows per pass
-    const int gx = x0 - HX + c * 16;
-    const bool col_ok = tid < 250 && gx >= 0 && gx + 16 <= g.pitch;
-    const uint8_t* src = base + (ptrdiff_t)(y0 - 4 + r0) * g.pitch + gx;
-#pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-      const int r = r0 + 25 * pass, gy = y0 - 4 + r;
-      if (tid < 250 && r < SH) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (col_ok && gy >= 0 && gy < g.rows) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(25 * pass) * g.pitch));
-        *reinterpret_cast<uint4*>(&s_img[r][c * 16]) = v;
-      }
-    }
     uint4* sc = reinterpret_cast<uint4*>(&s_score[0][0]);
     sc[tid] = make_uint4(0, 0, 0, 0);
     if (tid < CH * CPITCH / 16 - 256) sc[256 + tid] = make_uint4(0, 0, 0, 0);
     if (tid < TH * 4) (&s_mask[0][0])[tid] = 0u;
   }
   __syncthreads();
+  {
+    const uint32_t bar = smem_u32(&s_bar);
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(bar) : "memory");
+  }
 
   // ---- phase 1 (warp-private): compass pre-test on the tile + 1 px NMS halo.  Warp w owns pre-test rows w, w+8,
   // w+16, w+24; lane l owns the aligned word at image x = x0 + 4*l, and lanes 0..7 also the two halo words
@@ -236,27 +229,46 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(Geometry g, RegionTable r
   if (t <= 127) {
     const uint32_t cadd = 0x01010101u * (uint32_t)(127 - t);
     const int hsy = warp + 8 * ((lane >> 1) & 3), hwi = (lane & 1) ? 33 : 0;   // this lane's halo word
+    // every lane first collects the flags of ITS 20 pixels (4 rows x 4 bytes + halo word) in one register: nibble `it`
+    // = the four pixels of pre-test row it, nibble 4 = the halo word ...
+    uint32_t flags = 0;
     if (interior) {
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        const int sy = warp + 8 * it;
-        const uint32_t m = compass_pretest<true>(s_img, sy, lane + 1, cadd, x0, y0, ay0, ay1, cx_lo, cx_hi);
-        append_candidates(list, ncand, m, (sy << 8) + 4 * lane + 1, lt);
+        const uint32_t m = compass_pretest<true>(s_img, warp + 8 * it, lane + 1, cadd, x0, y0, ay0, ay1, cx_lo, cx_hi);
+        flags |= ((((m >> 7) & 0x01010101u) * 0x01020408u) >> 24) << (4 * it);
       }
       uint32_t m = 0;
       if (lane < 8)   // of the left halo word only x0-1 (byte 3) is needed, of the right one only x0+128 (byte 0)
         m = compass_pretest<true>(s_img, hsy, hwi, cadd, x0, y0, ay0, ay1, cx_lo, cx_hi) & (hwi ? 0x00000080u : 0x80000000u);
-      append_candidates(list, ncand, m, (hsy << 8) + 4 * hwi - 3, lt);
+      flags |= ((((m >> 7) & 0x01010101u) * 0x01020408u) >> 24) << 16;
     } else {
 #pragma unroll 1
       for (int it = 0; it < 4; ++it) {
-        const int sy = warp + 8 * it;
-        const uint32_t m = compass_pretest<false>(s_img, sy, lane + 1, cadd, x0, y0, ay0, ay1, cx_lo, cx_hi);
-        append_candidates(list, ncand, m, (sy << 8) + 4 * lane + 1, lt);
+        const uint32_t m = compass_pretest<false>(s_img, warp + 8 * it, lane + 1, cadd, x0, y0, ay0, ay1, cx_lo, cx_hi);
+        flags |= ((((m >> 7) & 0x01010101u) * 0x01020408u) >> 24) << (4 * it);
       }
       uint32_t m = 0;
       if (lane < 8) m = compass_pretest<false>(s_img, hsy, hwi, cadd, x0, y0, ay0, ay1, cx_lo, cx_hi);
-      append_candidates(list, ncand, m, (hsy << 8) + 4 * hwi - 3, lt);
+      flags |= ((((m >> 7) & 0x01010101u) * 0x01020408u) >> 24) << 16;
+    }
+    // ... then ONE warp scan places the lanes' candidates in the list (the order is irrelevant), instead of four
+    // ballots and four predicated stores per pre-test row
+    const int mine = __popc(flags);
+    int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    ncand = __shfl_sync(0xffffffffu, inc, 31);
+    int pos = inc - mine;
+    while (flags) {
+      const int bit = __ffs(flags) - 1;
+      flags &= flags - 1;
+      const int it = bit >> 2, byte = bit & 3;
+      const int code = it < 4 ? ((warp + 8 * it) << 8) + 4 * lane + 1 + byte : (hsy << 8) + 4 * hwi - 3 + byte;
+      list[pos++] = (uint16_t)code;
     }
   } else {   // thresholds above 127 (never produced by the reference's configurations): every pixel is a candidate
     for (int it = 0; it < 4; ++it) {
@@ -474,14 +486,18 @@ void launch_repitch(const Geometry& g, const uint8_t* left, const uint8_t* right
   repitch_kernel<<<grid, 256, 0, stream>>>(g, left, right, stride, image);
 }
 
-void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, int first_image, int n_images,
-                 cudaStream_t stream) {
+bool make_fast_tensor_map(const Geometry& g, const uint8_t* images, int n_images, CUtensorMap* out) {
+  return make_image_tensor_map(g, images, n_images, SW, SH, out);
+}
+
+void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, const CUtensorMap& image_map, int first_image,
+                 int n_images, cudaStream_t stream) {
   const int single = g.n_regions == 1;
   const size_t mask_bytes = (size_t)g.rows * g.mask_words * sizeof(uint32_t);
   if (!single) cudaMemsetAsync(b.mask + (size_t)first_image * g.rows * g.mask_words, 0, mask_bytes * n_images, stream);
   cudaMemsetAsync(b.raw_count + (size_t)first_image * g.n_regions, 0, sizeof(int32_t) * g.n_regions * n_images, stream);
   dim3 grid((g.cols + TW - 1) / TW, (g.rows + TH - 1) / TH, n_images * g.n_regions);
-  fast_nms_kernel<<<grid, 256, 0, stream>>>(g, rt, b.image + (size_t)first_image * g.rows * g.pitch,
+  fast_nms_kernel<<<grid, 256, 0, stream>>>(image_map, g, rt, first_image,
                                             b.mask + (size_t)first_image * g.rows * g.mask_words,
                                             b.raw_count + (size_t)first_image * g.n_regions, single);
 }

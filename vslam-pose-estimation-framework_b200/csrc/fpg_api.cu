@@ -66,6 +66,7 @@ struct vslam_fpg {
   StereoParams sp;
   Lane lanes[kLanes];
   Buffers b;                  // b.blurred / b.mask are per-lane and set per launch
+  CUtensorMap image_map;      // TMA descriptor of b.image with the FAST tile as box
   FramePointRecord* d_out = nullptr;       // [max_batch][out_cap]
   FramePointRecord* d_matches = nullptr;   // [cap] (single pair, emission order)
   int32_t* d_n_matches = nullptr;
@@ -144,7 +145,7 @@ void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n) {
   cudaMemsetAsync(h->b.pruned_l + (size_t)p0 * h->g.cap, 0, (size_t)n * h->g.cap, lane.stream);
   cudaMemsetAsync(h->b.consumed_r + (size_t)p0 * h->g.cap, 0, (size_t)n * h->g.cap, lane.stream);
   mark(h, lane, kEvFast0);
-  launch_fast(h->g, rt, b, 2 * p0, 2 * n, lane.stream);
+  launch_fast(h->g, rt, b, h->image_map, 2 * p0, 2 * n, lane.stream);
   mark(h, lane, kEvFast1);
   launch_compact(h->g, b, 2 * p0, 2 * n, lane.stream);
   mark(h, lane, kEvCompact1);
@@ -474,6 +475,10 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
     if (ok && cudaMemcpy(h->d_brief_tests, c->brief_tests, 1024, cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
   }
   h->cfg.brief_tests = nullptr;   // the table was copied; the caller's pointer is not kept
+  if (ok && !make_fast_tensor_map(g, b.image, (int)I, &h->image_map)) {
+    vslam_fpg_destroy(h);
+    return fail(VSLAM_ERR_CUDA, "cuTensorMapEncodeTiled failed for the image buffer (TMA is required: no fallback)");
+  }
   for (int l = 0; l < kLanes; ++l) {
     dalloc((void**)&h->lanes[l].blurred, (size_t)2 * h->chunk * img_bytes * (brief ? 2 : 1));
     dalloc((void**)&h->lanes[l].mask, (size_t)2 * h->chunk * g.rows * g.mask_words * sizeof(uint32_t));

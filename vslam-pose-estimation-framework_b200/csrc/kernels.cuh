@@ -82,8 +82,11 @@ struct RecoverParams {
 // dense host-layout images (row stride `stride` bytes, any alignment) -> pitched device images [pair][side][row][pitch]
 void launch_repitch(const Geometry& g, const uint8_t* left, const uint8_t* right, int stride, uint8_t* image,
                     int n_pairs, cudaStream_t stream);
-void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, int first_image, int n_images,
-                 cudaStream_t stream);
+// `image_map`: TMA descriptor of b.image (all images of the handle) with the FAST tile as box
+bool make_fast_tensor_map(const Geometry& g, const uint8_t* images, int n_images, CUtensorMap* out);
+bool make_image_tensor_map(const Geometry& g, const uint8_t* images, int n_images, int box_w, int box_h, CUtensorMap* out);
+void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, const CUtensorMap& image_map, int first_image,
+                 int n_images, cudaStream_t stream);
 void launch_compact(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream);
 // FAST response of the kept keypoints of one image -> kp_score (on demand)
 void launch_score(const Geometry& g, const Buffers& b, int image, cudaStream_t stream);

@@ -452,8 +452,8 @@ static void configure_describe() {
   }
 }
 
-// tensor map of a lane's blurred scratch [n_images][rows][pitch] u8 with the describe tile as box
-bool make_blurred_tensor_map(const Geometry& g, const uint8_t* blurred, int n_images, CUtensorMap* out) {
+// tensor map of an image stack [n_images][rows][pitch] u8 with a box of box_w x box_h x 1 bytes
+bool make_image_tensor_map(const Geometry& g, const uint8_t* images, int n_images, int box_w, int box_h, CUtensorMap* out) {
   typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -468,11 +468,16 @@ bool make_blurred_tensor_map(const Geometry& g, const uint8_t* blurred, int n_im
   }
   const cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.rows, (cuuint64_t)n_images};
   const cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)g.pitch * g.rows};   // bytes, dims 1 and 2
-  const cuuint32_t box[3] = {DT_BW, DT_BH, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   const cuuint32_t elem[3] = {1, 1, 1};
-  return encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(blurred), dims, strides, box, elem,
+  return encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(images), dims, strides, box, elem,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// tensor map of a lane's blurred scratch with the describe tile as box
+bool make_blurred_tensor_map(const Geometry& g, const uint8_t* blurred, int n_images, CUtensorMap* out) {
+  return make_image_tensor_map(g, blurred, n_images, DT_BW, DT_BH, out);
 }
 
 // `blurred_map` describes the buffer whose image 0 is image `first_image` of the batch (the lane's scratch)
