@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(const __grid_constant__ C
   __shared__ uint32_t s_mask[TH][4];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int img = blockIdx.z / g.n_regions;
+  const int img = single_region ? blockIdx.z : blockIdx.z / g.n_regions;   // (no integer division on the common path)
   const int reg = blockIdx.z - img * g.n_regions;
   const Region R = rt.r[reg];
   const int t = rt.threshold[reg];
@@ -262,13 +262,20 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(const __grid_constant__ C
       if (lane >= o) inc += n;
     }
     ncand = __shfl_sync(0xffffffffu, inc, 31);
-    int pos = inc - mine;
-    while (flags) {
-      const int bit = __ffs(flags) - 1;
-      flags &= flags - 1;
-      const int it = bit >> 2, byte = bit & 3;
-      const int code = it < 4 ? ((warp + 8 * it) << 8) + 4 * lane + 1 + byte : (hsy << 8) + 4 * hwi - 3 + byte;
-      list[pos++] = (uint16_t)code;
+    uint16_t* dst = list + (inc - mine);
+    // bit b of the low half = pre-test row b >> 2, byte b & 3: code = (warp + 8 (b >> 2)) << 8 | 4 lane + 1 + (b & 3)
+    const uint32_t code0 = (uint32_t)((warp << 8) + 4 * lane + 1);
+    uint32_t rows4 = flags & 0xffffu;
+    while (rows4) {
+      const uint32_t bit = (uint32_t)__ffs((int)rows4) - 1u;
+      rows4 &= rows4 - 1u;
+      *dst++ = (uint16_t)(code0 + ((bit & 12u) << 9) + (bit & 3u));
+    }
+    uint32_t halo = flags >> 16;   // lanes 0..7 only, and rarely set
+    while (halo) {
+      const uint32_t bit = (uint32_t)__ffs((int)halo) - 1u;
+      halo &= halo - 1u;
+      *dst++ = (uint16_t)((hsy << 8) + 4 * hwi - 3 + (int)bit);
     }
   } else {   // thresholds above 127 (never produced by the reference's configurations): every pixel is a candidate
     for (int it = 0; it < 4; ++it) {
