@@ -382,3 +382,35 @@ def test_fast_threshold_extremes(threshold):
     order = np.lexsort((ref["x"], ref["y"]))
     assert np.array_equal(k["x"], ref["x"][order]) and np.array_equal(k["response"], ref["response"][order])
     gen.close()
+
+
+def test_full_size_batch_is_replication_invariant():
+    """BASELINE configs[2] at its full size (4096 independent KITTI-shape pairs, kitti_fast): the oracle cannot run
+    4096 pairs in seconds, so the size-independent property is checked instead -- a pair's result does not depend on
+    its position in the batch, on the chunk or on the pipeline lane that processed it.  The batch tiles 8 distinct
+    pairs 512 times; every replica must equal, byte for byte, the first occurrence, whose 8 results are compared with
+    the oracle; the descriptors of the last replica (last chunk) are compared as well."""
+    cfg = configs.BY_NAME["kitti_fast"]
+    cam = synth.camera(cfg.camera)
+    distinct, total = 8, 4096
+    left, right = synth.band_world_batch(cfg.camera, range(300, 300 + distinct))
+    idx = np.arange(total) % distinct
+    big_l, big_r = np.ascontiguousarray(left[idx]), np.ascontiguousarray(right[idx])
+    gen = api.StereoFramePointGenerator(cfg, cam, max_batch=total)
+    out, counts = gen.batch_process(big_l, big_r, True)
+    out2, nf, nm, nl, nr = gen.batch_download(total)
+    assert np.array_equal(counts, nf)
+    for i in range(distinct):
+        o = _oracle(cfg, cam, left[i], right[i], True)
+        _same_points(out[i, :counts[i]], o.framepoints())
+        assert nm[i] == len(o.matches) and nl[i] == len(o.kps_left) and nr[i] == len(o.kps_right)
+        k, d = gen.features(0, pair=total - distinct + i)
+        assert np.array_equal(d, o.desc_left) and np.array_equal(k["x"], o.kps_left["x"])
+    view = out.reshape(total // distinct, distinct, -1)
+    for name, a in (("counts", counts), ("matches", nm), ("left", nl), ("right", nr)):
+        assert np.array_equal(a.reshape(-1, distinct), np.broadcast_to(a[:distinct], (total // distinct, distinct))), name
+    for i in range(distinct):
+        ref = view[0, i, :counts[i]].tobytes()
+        for r in range(1, total // distinct):
+            assert view[r, i, :counts[i]].tobytes() == ref, (r, i)
+    gen.close()

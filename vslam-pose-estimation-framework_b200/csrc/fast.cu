@@ -316,7 +316,8 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(const __grid_constant__ C
   for (int c = lane; c < ncorner; c += 32) {
     const int code = list[c];
     const int sy = code >> 8, sx = code & 0xff;
-    const int s = s_score[sy][sx];
+    const int s = s_score[sy][sx];   // (short-circuit on purpose: most corners lose to their first neighbours; a
+                                     // branch-free maximum of all 8 measured slower, it is bound by the byte loads)
     const bool kp = s > s_score[sy - 1][sx - 1] && s > s_score[sy - 1][sx] && s > s_score[sy - 1][sx + 1] &&
                     s > s_score[sy][sx - 1] && s > s_score[sy][sx + 1] && s > s_score[sy + 1][sx - 1] &&
                     s > s_score[sy + 1][sx] && s > s_score[sy + 1][sx + 1];
