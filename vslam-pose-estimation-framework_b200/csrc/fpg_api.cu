@@ -67,6 +67,7 @@ struct vslam_fpg {
   Lane lanes[kLanes];
   Buffers b;                  // b.blurred / b.mask are per-lane and set per launch
   CUtensorMap image_map;      // TMA descriptor of b.image with the FAST tile as box
+  CUtensorMap blur_map;       // ... with the blur tile as box
   FramePointRecord* d_out = nullptr;       // [max_batch][out_cap]
   FramePointRecord* d_matches = nullptr;   // [cap] (single pair, emission order)
   int32_t* d_n_matches = nullptr;
@@ -156,7 +157,7 @@ void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n) {
     launch_describe_brief(h->g, boxsum, h->d_brief_tests, h->b.kp_xy + (size_t)2 * p0 * h->g.cap, h->b.n_desc + 2 * p0,
                           h->b.desc + (size_t)2 * p0 * h->g.cap * kDescBytes, h->g.cap, 2 * n, lane.stream);
   } else {
-    launch_blur(h->g, b, 2 * p0, 2 * n, lane.stream);
+    launch_blur(h->g, b, h->blur_map, 2 * p0, 2 * n, lane.stream);
     mark(h, lane, kEvBlur1);
     launch_describe(h->g, b, lane.blurred_map, 2 * p0, 2 * n, lane.stream);
   }
@@ -475,7 +476,7 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
     if (ok && cudaMemcpy(h->d_brief_tests, c->brief_tests, 1024, cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
   }
   h->cfg.brief_tests = nullptr;   // the table was copied; the caller's pointer is not kept
-  if (ok && !make_fast_tensor_map(g, b.image, (int)I, &h->image_map)) {
+  if (ok && !(make_fast_tensor_map(g, b.image, (int)I, &h->image_map) && make_blur_tensor_map(g, b.image, (int)I, &h->blur_map))) {
     vslam_fpg_destroy(h);
     return fail(VSLAM_ERR_CUDA, "cuTensorMapEncodeTiled failed for the image buffer (TMA is required: no fallback)");
   }

@@ -90,7 +90,10 @@ void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, con
 void launch_compact(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream);
 // FAST response of the kept keypoints of one image -> kp_score (on demand)
 void launch_score(const Geometry& g, const Buffers& b, int image, cudaStream_t stream);
-void launch_blur(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream);
+// `image_map`: TMA descriptor of b.image (all images of the handle) with the blur tile as box
+bool make_blur_tensor_map(const Geometry& g, const uint8_t* images, int n_images, CUtensorMap* out);
+void launch_blur(const Geometry& g, const Buffers& b, const CUtensorMap& image_map, int first_image, int n_images,
+                 cudaStream_t stream);
 // TMA descriptor of a blurred scratch buffer [n_images][rows][pitch]; false when the driver cannot encode it
 bool make_blurred_tensor_map(const Geometry& g, const uint8_t* blurred, int n_images, CUtensorMap* out);
 // image 0 of `blurred_map` is image `first_image` of the batch

@@ -14,12 +14,6 @@ namespace vslam {
 
 namespace {
 
-constexpr int TW = 128;
-constexpr int TH = 64;
-constexpr int HX = 16;
-constexpr int SW = TW + 2 * HX;   // 160
-constexpr int SH = TH + 6;        // 70
-
 struct GaussKernel {
   float k[7];
 };
@@ -30,118 +24,146 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   return i;
 }
 
-// exact u8 -> float without the (quarter-rate) I2F unit: place the byte in the mantissa of 2^23 and subtract 2^23
-__device__ __forceinline__ float byte_to_float(uint32_t word, int j) {
-  return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u | (unsigned)j)) - 8388608.0f;
-}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// the same byte of two words -> (float, float): two PRMTs and ONE packed FADD2 (per-element IEEE, exact)
+// the same byte of two words -> (float, float), exact and without the (quarter-rate) I2F unit: PRMT places each byte
+// in the mantissa of 2^23, ONE packed FADD2 subtracts 2^23 from both
 __device__ __forceinline__ float2 bytes_to_float2(uint32_t wa, uint32_t wb, int j) {
   return __fadd2_rn(make_float2(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7650u | (unsigned)j)),
                                 __uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7650u | (unsigned)j))),
                     make_float2(-8388608.0f, -8388608.0f));
 }
 
-// K3.  Tile 128 x 64 outputs.  Row pass: one thread per 4 adjacent outputs (10 input bytes converted once, 28 FMA);
-// column pass: one thread per 4 columns x 8 rows (14 float4 shared-memory loads, packed 32-bit stores).
-__global__ void __launch_bounds__(256, 4) blur_kernel(Geometry g, GaussKernel gk, const uint8_t* __restrict__ image,
-                                                   uint8_t* __restrict__ blurred) {
-  __shared__ __align__(16) uint8_t s_in[SH][SW];
-  __shared__ __align__(16) float s_tmp[SH][TW];
-  const int tid = threadIdx.x;
+// K3.  One WARP per 128 x 48 output tile, no block barrier and no intermediate in shared memory.  Lane 0 stages the
+// tile + halo (160 x 54 bytes, zero fill outside the image) with one TMA box load; BORDER_REFLECT_101 is then patched
+// into the out-of-image rows / columns of the staged tile.  Every lane owns 4 columns and walks down the tile two rows
+// per step with the 7-row window of the column pass in registers:
+//   row pass    : rows (2i, 2i+1) together, packed FFMA2 (.x = row 2i, .y = row 2i+1)          -> E_i = (t[2i], t[2i+1])
+//   O_i         : (t[2i+1], t[2i+2]) = (E_i.y, E_{i+1}.x), the pairs of the other parity
+//   column pass : outputs centred on (t[2j+1], t[2j+2]) = O_j:  k3 O_j + k4 (E_{j+1} + E_j) + k5 (O_{j+1} + O_{j-1})
+//                 + k6 (E_{j+2} + E_{j-1}), all packed FADD2 / FFMA2, in the oracle's order
+// Packed ops are two IEEE fp32 operations per instruction: every result equals the scalar evaluation bit for bit.
+constexpr int BL_W = 128;               // columns of a warp tile (4 per lane)
+constexpr int BL_H = 50;                // output rows of a warp tile: 56 staged rows = 7 loop trips x 4 row pairs
+constexpr int BL_SW = BL_W + 32;        // staged columns x0-16 .. x0+143 (TMA rows are multiples of 16 bytes)
+constexpr int BL_SH = BL_H + 6;         // staged rows y0-3 .. y0+52
+static_assert(BL_SH % 8 == 0, "the walk is unrolled over 4 row pairs (the period of the register rings)");
+constexpr int BL_WARPS = 4;             // independent warp tiles per CTA (stacked in y)
+constexpr int BL_TILE = (BL_SW * BL_SH + 127) / 128 * 128;   // TMA destinations are 128-byte aligned
+
+__global__ void __launch_bounds__(BL_WARPS * 32, 4) blur_kernel(const __grid_constant__ CUtensorMap image_map, Geometry g,
+                                                                GaussKernel gk, int first_image,
+                                                                uint8_t* __restrict__ blurred) {
+  __shared__ __align__(128) uint8_t s_in[BL_WARPS][BL_TILE];
+  __shared__ __align__(8) unsigned long long s_bar[BL_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int img = blockIdx.z;
-  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-  const uint8_t* base = image + (size_t)img * g.rows * g.pitch;
+  const int x0 = blockIdx.x * BL_W, y0 = (blockIdx.y * BL_WARPS + warp) * BL_H;
+  if (y0 >= g.rows) return;             // warps are independent: no block-wide barrier below
+  uint8_t* tile = s_in[warp];
+  const int tx0 = x0 - 16, ty0 = y0 - 3;   // image coordinates of the staged tile's origin
 
-  // ---- stage rows y0-3 .. y0+TH+2 (BORDER_REFLECT_101 in y) with aligned 16 B loads wherever the chunk lies inside
-  // the pitched row; the few columns outside the image are patched afterwards from shared memory itself
-  for (int i = tid; i < SH * (SW / 16); i += 256) {
-    const int r = i / (SW / 16), c = i - r * (SW / 16);
-    int gy = y0 - 3 + r;
-    gy = gy < 0 ? -gy : gy;
-    gy = gy >= g.rows ? 2 * g.rows - 2 - gy : gy;
-    gy = min(max(gy, 0), g.rows - 1);            // images shorter than the reflection: value unused by any kept keypoint
-    const int gx = x0 - HX + c * 16;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (gx >= 0 && gx + 16 <= g.pitch) v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)gy * g.pitch + gx));
-    *reinterpret_cast<uint4*>(&s_in[r][c * 16]) = v;
+  const uint32_t bar = smem_u32(&s_bar[warp]);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(BL_SW * BL_SH) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(tile)), "l"(&image_map), "r"(bar), "r"(tx0), "r"(ty0), "r"(first_image + img)
+        : "memory");
   }
-  __syncthreads();
-  if (x0 == 0 || x0 + TW + 3 > g.cols) {         // BORDER_REFLECT_101 in x: columns -3..-1 and cols..cols+2
-    for (int i = tid; i < SH * 6; i += 256) {
-      const int r = i / 6, j = i - r * 6;
-      if (j < 3) {
-        if (x0 == 0) s_in[r][HX - 1 - j] = s_in[r][HX + 1 + j];
-      } else {
-        const int x = g.cols + (j - 3), src = g.cols - 2 - (j - 3);
-        if (x >= x0 && x < x0 + TW + 3 && src >= x0 - HX && src >= 0) s_in[r][x - x0 + HX] = s_in[r][src - x0 + HX];
-      }
-    }
-    __syncthreads();
-  }
-
-  // ---- row pass: outputs x = xq .. xq+3 need inputs xq-3 .. xq+6, all inside three aligned words.  A thread takes
-  // the same four columns of TWO rows and evaluates them with packed FFMA2 (one instruction, two IEEE fp32 FMAs: the
-  // per-element result is the scalar one, so the rounding contract with the oracle is unchanged).
-  for (int i = tid; i < (SH / 2) * (TW / 4); i += 256) {
-    const int r = 2 * (i / (TW / 4)), xq = (i % (TW / 4)) * 4;
-    const uint32_t* wa = reinterpret_cast<const uint32_t*>(&s_in[r][xq + HX - 4]);
-    const uint32_t* wb = reinterpret_cast<const uint32_t*>(&s_in[r + 1][xq + HX - 4]);
-    const uint32_t a0 = wa[0], a1 = wa[1], a2 = wa[2], b0 = wb[0], b1 = wb[1], b2 = wb[2];
-    float2 p[10];   // .x: row r, .y: row r + 1
-    p[0] = bytes_to_float2(a0, b0, 1);
-    p[1] = bytes_to_float2(a0, b0, 2);
-    p[2] = bytes_to_float2(a0, b0, 3);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) p[3 + j] = bytes_to_float2(a1, b1, j);
-    p[7] = bytes_to_float2(a2, b2, 0);
-    p[8] = bytes_to_float2(a2, b2, 1);
-    p[9] = bytes_to_float2(a2, b2, 2);
-    float2 o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float2 acc = __fmul2_rn(make_float2(gk.k[0], gk.k[0]), p[j]);
-#pragma unroll
-      for (int t = 1; t < 7; ++t) acc = __ffma2_rn(make_float2(gk.k[t], gk.k[t]), p[j + t], acc);
-      o[j] = acc;
-    }
-    *reinterpret_cast<float4*>(&s_tmp[r][xq]) = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
-    *reinterpret_cast<float4*>(&s_tmp[r + 1][xq]) = make_float4(o[0].y, o[1].y, o[2].y, o[3].y);
-  }
-  __syncthreads();
-
-  // ---- column pass + round half-to-even to u8: adding 1.5 * 2^23 leaves rint(acc) in the low mantissa byte.
-  // acc is a convex combination (weights sum to 1 within 1e-7) of values in [0, 255]: it cannot leave [0, 255.0001],
-  // so cv::saturate_cast's clamp is a no-op and is not evaluated.  Adjacent columns are packed (FADD2 / FFMA2).
-  uint8_t* outp = blurred + (size_t)img * g.rows * g.pitch;
+  __syncwarp();
   {
-    constexpr int RPT = TH / 8;   // rows per thread
-    const int xq = (tid & 31) * 4, yb = (tid >> 5) * RPT;
-    float4 t[RPT + 6];
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(bar) : "memory");
+  }
+
+  // ---- BORDER_REFLECT_101: rows first (whole staged rows), then the three columns on either side of the image
+  if (ty0 < 0 || ty0 + BL_SH > g.rows) {
+    uint32_t* t32 = reinterpret_cast<uint32_t*>(tile);
+    for (int r = 0; r < BL_SH; ++r) {
+      const int gy = ty0 + r;
+      if (gy >= 0 && gy < g.rows) continue;
+      const int src = reflect101(gy, g.rows) - ty0;
+      if (src < 0 || src >= BL_SH) continue;       // a row no stored output reads
+      for (int w = lane; w < BL_SW / 4; w += 32) t32[r * (BL_SW / 4) + w] = t32[src * (BL_SW / 4) + w];
+    }
+    __syncwarp();
+  }
+  if (x0 == 0 || x0 + BL_W + 3 > g.cols) {
+    for (int i = lane; i < BL_SH * 6; i += 32) {
+      const int r = i / 6, j = i - r * 6;
+      const int x = j < 3 ? -1 - j : g.cols + (j - 3);
+      const int dst = x - tx0, src = reflect101(x, g.cols) - tx0;
+      if (dst >= 0 && dst < BL_SW && src >= 0 && src < BL_SW) tile[r * BL_SW + dst] = tile[r * BL_SW + src];
+    }
+    __syncwarp();
+  }
+
+  // ---- the walk.  Lane l owns columns x0 + 4l .. +3: inputs x0 + 4l - 3 .. + 6 lie in the three words from staged
+  // column 12 + 4l (word 3 + l: consecutive lanes, consecutive banks).
+  const uint32_t* w0 = reinterpret_cast<const uint32_t*>(tile) + 3 + lane;
+  float2 kk[7];
 #pragma unroll
-    for (int r = 0; r < RPT + 6; ++r) t[r] = *reinterpret_cast<const float4*>(&s_tmp[yb + r][xq]);
-    const float2 k3 = make_float2(gk.k[3], gk.k[3]), bias = make_float2(12582912.0f, 12582912.0f);
-    // rows of this thread that exist (0 when the thread's columns lie beyond the pitch); one running output pointer
-    const int n_y = x0 + xq < g.pitch ? min(RPT, g.rows - (y0 + yb)) : 0;
-    uint8_t* o = outp + (size_t)(y0 + yb) * g.pitch + x0 + xq;
+  for (int t = 0; t < 7; ++t) kk[t] = make_float2(gk.k[t], gk.k[t]);
+  const float2 bias = make_float2(12582912.0f, 12582912.0f);   // 1.5 * 2^23: rint(acc) lands in the low mantissa byte
+  uint8_t* o = blurred + ((size_t)img * g.rows + y0) * g.pitch + x0 + 4 * lane;
+  const int n_y = g.rows - y0;            // output rows of this tile that exist
+  // rings of the last four E and O pairs, indexed by compile-time constants only (registers).  The loop is unrolled
+  // over ONE ring period (4 steps): a fully unrolled walk (3.9 k instructions) ran out of the instruction cache
+  // (39 % of the warp stalls were "no instruction").
+  float2 E[4][4], O[4][4];
+#pragma unroll 1
+  for (int i4 = 0; i4 < BL_SH / 2; i4 += 4) {
 #pragma unroll
-    for (int y = 0; y < RPT; ++y) {
-      if (y >= n_y) break;
-      float2 lo = __fmul2_rn(k3, make_float2(t[y + 3].x, t[y + 3].y));
-      float2 hi = __fmul2_rn(k3, make_float2(t[y + 3].z, t[y + 3].w));
+    for (int s4 = 0; s4 < 4; ++s4) {
+      const int i = i4 + s4;
+      const uint32_t* wa = w0 + (2 * i) * (BL_SW / 4);
+      const uint32_t* wb = wa + BL_SW / 4;
+      const uint32_t a0 = wa[0], a1 = wa[1], a2 = wa[2], b0 = wb[0], b1 = wb[1], b2 = wb[2];
+      float2 p[10];   // .x: staged row 2i, .y: staged row 2i + 1; p[j] = input column 4l - 3 + j
+      p[0] = bytes_to_float2(a0, b0, 1);
+      p[1] = bytes_to_float2(a0, b0, 2);
+      p[2] = bytes_to_float2(a0, b0, 3);
 #pragma unroll
-      for (int d = 1; d <= 3; ++d) {
-        const float2 kd = make_float2(gk.k[3 + d], gk.k[3 + d]);
-        const float4 up = t[y + 3 + d], dn = t[y + 3 - d];
-        lo = __ffma2_rn(kd, __fadd2_rn(make_float2(up.x, up.y), make_float2(dn.x, dn.y)), lo);
-        hi = __ffma2_rn(kd, __fadd2_rn(make_float2(up.z, up.w), make_float2(dn.z, dn.w)), hi);
+      for (int j = 0; j < 4; ++j) p[3 + j] = bytes_to_float2(a1, b1, j);
+      p[7] = bytes_to_float2(a2, b2, 0);
+      p[8] = bytes_to_float2(a2, b2, 1);
+      p[9] = bytes_to_float2(a2, b2, 2);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float2 acc = __fmul2_rn(kk[0], p[c]);
+#pragma unroll
+        for (int t = 1; t < 7; ++t) acc = __ffma2_rn(kk[t], p[c + t], acc);
+        O[(s4 + 3) & 3][c] = make_float2(E[(s4 + 3) & 3][c].y, acc.x);   // O_{i-1} (garbage at i = 0, never read)
+        E[s4][c] = acc;                                                   // E_i
       }
-      lo = __fadd2_rn(lo, bias);
-      hi = __fadd2_rn(hi, bias);
-      const uint32_t packed = __byte_perm(__byte_perm(__float_as_uint(lo.x), __float_as_uint(lo.y), 0x0040),
-                                          __byte_perm(__float_as_uint(hi.x), __float_as_uint(hi.y), 0x0040), 0x5410);
-      *reinterpret_cast<uint32_t*>(o) = packed;
-      o += g.pitch;
+      if (i >= 3) {   // outputs centred on O_j, j = i - 2: image rows y0 + 2 (j - 1) and + 1
+        float2 r[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float2 acc = __fmul2_rn(kk[3], O[(s4 + 2) & 3][c]);                                             // O_j
+          acc = __ffma2_rn(kk[4], __fadd2_rn(E[(s4 + 3) & 3][c], E[(s4 + 2) & 3][c]), acc);              // E_{j+1} + E_j
+          acc = __ffma2_rn(kk[5], __fadd2_rn(O[(s4 + 3) & 3][c], O[(s4 + 1) & 3][c]), acc);              // O_{j+1} + O_{j-1}
+          acc = __ffma2_rn(kk[6], __fadd2_rn(E[s4][c], E[(s4 + 1) & 3][c]), acc);                         // E_{j+2} + E_{j-1}
+          // acc is a convex combination (weights sum to 1 within 1e-7) of values in [0, 255]: it cannot leave
+          // [0, 255.0001], so cv::saturate_cast's clamp is a no-op and is not evaluated
+          r[c] = __fadd2_rn(acc, bias);
+        }
+        const int k = 2 * (i - 3);
+        if (k < n_y)
+          *reinterpret_cast<uint32_t*>(o) =
+              __byte_perm(__byte_perm(__float_as_uint(r[0].x), __float_as_uint(r[1].x), 0x0040),
+                          __byte_perm(__float_as_uint(r[2].x), __float_as_uint(r[3].x), 0x0040), 0x5410);
+        if (k + 1 < n_y)
+          *reinterpret_cast<uint32_t*>(o + g.pitch) =
+              __byte_perm(__byte_perm(__float_as_uint(r[0].y), __float_as_uint(r[1].y), 0x0040),
+                          __byte_perm(__float_as_uint(r[2].y), __float_as_uint(r[3].y), 0x0040), 0x5410);
+        o += 2 * (size_t)g.pitch;
+      }
     }
   }
 }
@@ -202,8 +224,6 @@ constexpr int DT_LIST = 512;                    // keypoints compacted per round
 constexpr int DT_BINS = 128;                    // sort key of a keypoint: byte column of its patch origin mod 128 =
                                                 // (shared-memory bank, byte in word)
 static_assert(DT_BINS == DT_THREADS, "one bin per thread");
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __global__ void __launch_bounds__(DT_THREADS) describe_tile_kernel(const __grid_constant__ CUtensorMap blurred_map,
                                                                    Geometry g, const int32_t* __restrict__ row_ptr,
@@ -389,7 +409,13 @@ __global__ void __launch_bounds__(DWARPS * 32) describe_kernel(Geometry g, const
 
 }  // namespace
 
-void launch_blur(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream) {
+bool make_blur_tensor_map(const Geometry& g, const uint8_t* images, int n_images, CUtensorMap* out) {
+  return make_image_tensor_map(g, images, n_images, BL_SW, BL_SH, out);
+}
+
+// `image_map`: TMA descriptor of b.image (all images of the handle) with the blur tile as box
+void launch_blur(const Geometry& g, const Buffers& b, const CUtensorMap& image_map, int first_image, int n_images,
+                 cudaStream_t stream) {
   GaussKernel gk;
   {  // cv::getGaussianKernel(7, 2.0, CV_32F)
     double t[7], sum = 0;
@@ -400,9 +426,11 @@ void launch_blur(const Geometry& g, const Buffers& b, int first_image, int n_ima
     }
     for (int i = 0; i < 7; ++i) gk.k[i] = (float)(t[i] / sum);
   }
-  dim3 grid((g.cols + TW - 1) / TW, (g.rows + TH - 1) / TH, n_images);
-  blur_kernel<<<grid, 256, 0, stream>>>(g, gk, b.image + (size_t)first_image * g.rows * g.pitch,
-                                        b.blurred + (size_t)first_image * g.rows * g.pitch);
+  const int strips = (g.rows + BL_H - 1) / BL_H;
+  dim3 grid((g.cols + BL_W - 1) / BL_W, (strips + BL_WARPS - 1) / BL_WARPS, n_images);
+  // (5 or 6 resident CTAs per SM instead of 4 measured the same: the packed-FP pipe, not latency, bounds the walk)
+  blur_kernel<<<grid, BL_WARPS * 32, 0, stream>>>(image_map, g, gk, first_image,
+                                                   b.blurred + (size_t)first_image * g.rows * g.pitch);
 }
 
 // ---- BRIEF-32 (cv::xfeatures2d::BriefDescriptorExtractor::create(32), reference base_framepoint_generator.cpp:186;
