@@ -2,6 +2,8 @@
 // effect the call reproduces (reference src/framepoint_generation/stereo_framepoint_generator.cpp unless noted).
 #include "gpu_stereo_framepoint_generator.h"
 
+#include "types/landmark.h"
+
 #include <cstring>
 #include <stdexcept>
 
@@ -167,8 +169,8 @@ void GpuStereoFramePointGenerator::recoverPoints(Frame* current_frame_,
     for (int c = 0; c < 4; ++c) W[4 * r + c] = world_to_camera_left.matrix()(r, c);
   _recovered_buffer.resize(n_lost);
   int32_t n_recovered = 0;
-  check(vslam_fpg_recover_points(_handle, _previous_buffer.data(), (int32_t)n_lost, W, _parameters->minimum_depth_meters,
-                                 _parameters->maximum_depth_meters, _maximum_descriptor_distance_tracking,
+  check(vslam_fpg_recover_points(_handle, _previous_buffer.data(), (int32_t)n_lost, W, _stereo_parameters->minimum_depth_meters,
+                                 _stereo_parameters->maximum_depth_meters, _maximum_descriptor_distance_tracking,
                                  _recovered_buffer.data(), (int32_t)_recovered_buffer.size(), &n_recovered));
   FramePointPointerVector& framepoints(current_frame_->points());
   framepoints.reserve(framepoints.size() + n_recovered);                                             // :698-700, :861

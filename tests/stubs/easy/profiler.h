@@ -1,0 +1,9 @@
+// Shape-only stand-in for easy_profiler (tests/stubs/README.md): the macros expand to nothing.
+#pragma once
+#define EASY_BLOCK(...)
+#define EASY_END_BLOCK
+#define EASY_FUNCTION(...)
+#define EASY_PROFILER_ENABLE
+#define EASY_PROFILER_DISABLE
+#define EASY_MAIN_THREAD
+namespace profiler { namespace colors { enum { Red, Green, Blue, Yellow, Orange, Magenta, Cyan, Brown, Black, White, Grey, Purple, Pink, Lime, Amber, Teal, Indigo, Navy, Gold, Coral, Olive, DeepOrange, LightBlue, LightGreen, DarkBlue, DarkGreen, DarkRed, DarkTeal, BlueGrey, RichRed, RichGreen, RichBlue, RichYellow, Mint, Skin }; } inline unsigned dumpBlocksToFile(const char*) { return 0; } }
