@@ -473,11 +473,12 @@ def main():
     path_bytes = (2.0 * P * cam.rows * cam.cols + 8 * n_desc + 32 * n_desc + 40 * n_desc + 48.0 * nm.sum()
                   + 81.0 * nf.sum() * R)
     # DRAM traffic of the kernel from the committed ncu --set full capture, scaled to this run's images per launch
-    traffic = None
+    traffic, limiters = None, None
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["fast_nms_kernel"]
         if t["image"] == "%dx%d u8" % (cam.cols, cam.rows):
             traffic = t["dram_bytes_per_launch"] / t["images_per_launch"] * (2.0 * P / max(chunks, 1))
+        limiters = t.get("limiters_pct_of_peak")     # from the same committed capture: what really bounds the kernel
     except (OSError, KeyError, ValueError):
         pass
     roofline = {"bound": "hbm", "kernel": "fast_nms_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -485,7 +486,7 @@ def main():
                 "peak_source": peak_kind + " (of %s)" % peak_kind,
                 "launch_ms": fast_ms_per_launch, "launches_per_step": chunks,
                 "kernel_share_of_step": kernel_ms[KERNEL_OF_INTEREST] / total_kernel_ms,
-                "kernel_ms_per_step": kernel_ms,
+                "kernel_ms_per_step": kernel_ms, "ncu_limiters_pct_of_peak": limiters,
                 "path": {"algorithmic_bytes_per_step": path_bytes,
                          "achieved_gbs": path_bytes / (ms / K * 1e-3) / 1e9,
                          "frac": path_bytes / (ms / K * 1e-3) / 1e9 / peak}}
