@@ -357,6 +357,59 @@ void* vslam_aligner_stream(vslam_aligner* h);
 int vslam_aligner_synchronize(vslam_aligner* h);
 int64_t vslam_aligner_launch_count(const vslam_aligner* h);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * what follows the aligner in PoseTracker3D::compute -- the landmark refinement -- and the
+ * trajectory wire formats.  Neither sits behind the two plugin classes: PoseTracker3D::_updatePoints
+ * (src/position_tracking/pose_tracker_3d.cpp:475-549) calls Landmark::update per point, so a host replaces that LOOP
+ * (gather the histories, one call, write the results back), see INTEGRATION.md section 6.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct vslam_landmark_optimizer vslam_landmark_optimizer;
+
+/* Landmark::Measurement (src/types/landmark.h:19-33): frame = index into the pose tables of the call */
+typedef struct {
+  int32_t frame;
+  int32_t reserved;
+  double camera_coordinates[3];   /* FramePoint::cameraCoordinatesLeft() */
+  double inverse_depth_meters;    /* 1 / camera_coordinates.z */
+} vslam_landmark_measurement;
+
+#define VSLAM_LANDMARK_NOT_CONVERGED 0 /* iteration cap reached: state untouched (landmark.cpp:91) */
+#define VSLAM_LANDMARK_ADOPTED 1       /* estimate and number of updates replaced (:143-147) */
+#define VSLAM_LANDMARK_RESET 2         /* fewer inliers than outliers: average of the measurements (:150-160) */
+#define VSLAM_LANDMARK_KEPT 3          /* converged, neither branch taken */
+
+int vslam_landmark_optimizer_create(int32_t max_landmarks, int32_t max_measurements, int32_t max_frames, int device,
+                                    vslam_landmark_optimizer** out);
+int vslam_landmark_optimizer_destroy(vslam_landmark_optimizer* h);
+/* Landmark::update (src/types/landmark.cpp:82-167) for n_landmarks independent landmarks, one warp each.
+ * measurement_offsets[n_landmarks + 1]: CSR over `measurements`, the new measurement already appended (:78-79).
+ * world_to_camera_left / camera_left_to_world: [n_frames][12] row-major 3x4 (Frame::worldToCameraLeft /
+ * cameraLeftToWorld).  world_coordinates[n][3] and number_of_updates[n] are _world_coordinates / _number_of_updates,
+ * updated in place exactly where the reference updates them; outcome[n] (VSLAM_LANDMARK_*) and iterations[n] may be
+ * NULL.  Parameters: LandmarkParameters::maximum_number_of_iterations / maximum_error_squared_meters
+ * (src/types/parameters.h:111-114). */
+int vslam_landmark_optimizer_update(vslam_landmark_optimizer* h, int32_t n_landmarks, const int32_t* measurement_offsets,
+                                    const vslam_landmark_measurement* measurements, int32_t n_frames,
+                                    const double* world_to_camera_left, const double* camera_left_to_world,
+                                    uint32_t maximum_number_of_iterations, double maximum_error_squared_meters,
+                                    double* world_coordinates, uint32_t* number_of_updates, uint8_t* outcome,
+                                    int32_t* iterations);
+int64_t vslam_landmark_optimizer_launch_count(const vslam_landmark_optimizer* h);
+
+/* WorldMap::writeTrajectoryKITTI (src/types/world_map.cpp:183-216) / writeTrajectoryTUM (:218-252): one text line per
+ * frame, std::fixed with 9 decimals, every value followed by a blank.  KITTI: the 12 values of robot_to_world row by
+ * row.  TUM: timestamp, translation, orientation quaternion x y z w.  The format_ calls return the line length
+ * (snprintf semantics); write_trajectory overwrites `filename`. */
+#define VSLAM_TRAJECTORY_KITTI 0
+#define VSLAM_TRAJECTORY_TUM 1
+int32_t vslam_format_trajectory_kitti(const double robot_to_world[12], char* line, int32_t capacity);
+int32_t vslam_format_trajectory_tum(double timestamp_seconds, const double robot_to_world[12], char* line, int32_t capacity);
+int vslam_write_trajectory(const char* filename, int format, int32_t n_frames, const double* robot_to_world,
+                           const double* timestamps_seconds);
+
+/* the 3x3 complete-pivoting LU solve of Landmark::update (exposed for tests) */
+void vslam_solve3(const double A[9], const double rhs[3], double x[3]);
+
 /* host-side 6x6 helpers used by one_round (exposed for tests): complete-pivoting LU solve; srrg_core::v2t */
 void vslam_solve6(const double A[36], const double rhs[6], double x[6]);
 void vslam_v2t(const double v[6], double T[12]);

@@ -228,4 +228,57 @@ class FrameAligner {
 typedef FrameAligner<VSLAM_ALIGNER_STEREO_UV> StereoUVAligner;
 typedef FrameAligner<VSLAM_ALIGNER_UVD> UVDAligner;
 
+// The landmark loop of PoseTracker3D::_updatePoints (reference src/position_tracking/pose_tracker_3d.cpp:475-549) as ONE
+// call: Landmark::update (src/types/landmark.cpp:66-152) for every landmark of the frame, one warp each.
+class LandmarkOptimizer {
+ public:
+  LandmarkOptimizer(int32_t max_landmarks, int32_t max_measurements, int32_t max_frames, int device = 0) {
+    check(vslam_landmark_optimizer_create(max_landmarks, max_measurements, max_frames, device, &_handle),
+          "LandmarkOptimizer::LandmarkOptimizer");
+  }
+  ~LandmarkOptimizer() { vslam_landmark_optimizer_destroy(_handle); }
+  LandmarkOptimizer(const LandmarkOptimizer&) = delete;
+  LandmarkOptimizer& operator=(const LandmarkOptimizer&) = delete;
+
+  // LandmarkParameters (src/types/parameters.h:111-114)
+  uint32_t maximum_number_of_iterations = 100;
+  double maximum_error_squared_meters = 5 * 5;
+
+  // offsets: CSR over `measurements` (size n + 1); poses: [n_frames][12] row-major 3x4; world / number_of_updates in place
+  void update(const std::vector<int32_t>& offsets, const std::vector<vslam_landmark_measurement>& measurements,
+              const std::vector<double>& world_to_camera_left, const std::vector<double>& camera_left_to_world,
+              std::vector<double>& world_coordinates, std::vector<uint32_t>& number_of_updates,
+              std::vector<uint8_t>* outcome = nullptr) {
+    const int32_t n = static_cast<int32_t>(offsets.size()) - 1;
+    if (n < 0 || world_coordinates.size() != 3 * static_cast<size_t>(n) || number_of_updates.size() != static_cast<size_t>(n) ||
+        world_to_camera_left.size() != camera_left_to_world.size() || world_to_camera_left.size() % 12 != 0)
+      throw std::runtime_error("LandmarkOptimizer::update|inconsistent buffer sizes");
+    if (outcome) outcome->resize(n);
+    check(vslam_landmark_optimizer_update(_handle, n, offsets.data(), measurements.data(),
+                                          static_cast<int32_t>(world_to_camera_left.size() / 12), world_to_camera_left.data(),
+                                          camera_left_to_world.data(), maximum_number_of_iterations,
+                                          maximum_error_squared_meters, world_coordinates.data(), number_of_updates.data(),
+                                          outcome ? outcome->data() : nullptr, nullptr),
+          "LandmarkOptimizer::update");
+  }
+
+ private:
+  vslam_landmark_optimizer* _handle = nullptr;
+};
+
+// WorldMap::writeTrajectoryKITTI / writeTrajectoryTUM (reference src/types/world_map.cpp:183-252); poses: [n][12] row-major
+inline void writeTrajectoryKITTI(const std::string& filename, const std::vector<double>& robot_to_world) {
+  if (vslam_write_trajectory(filename.c_str(), VSLAM_TRAJECTORY_KITTI, static_cast<int32_t>(robot_to_world.size() / 12),
+                             robot_to_world.data(), nullptr) != VSLAM_OK)
+    throw std::runtime_error(std::string("writeTrajectoryKITTI|") + vslam_last_error());
+}
+inline void writeTrajectoryTUM(const std::string& filename, const std::vector<double>& timestamps_seconds,
+                               const std::vector<double>& robot_to_world) {
+  if (timestamps_seconds.size() * 12 != robot_to_world.size())
+    throw std::runtime_error("writeTrajectoryTUM|one timestamp per pose expected");
+  if (vslam_write_trajectory(filename.c_str(), VSLAM_TRAJECTORY_TUM, static_cast<int32_t>(timestamps_seconds.size()),
+                             robot_to_world.data(), timestamps_seconds.data()) != VSLAM_OK)
+    throw std::runtime_error(std::string("writeTrajectoryTUM|") + vslam_last_error());
+}
+
 }  // namespace vslam

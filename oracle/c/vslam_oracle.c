@@ -10,6 +10,7 @@
  */
 #include "vslam_oracle.h"
 
+#include <stdio.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1004,4 +1005,169 @@ int orc_converge(int kind, const orc_aligner_problem* p, double damping, double 
   }
   if (rounds) *rounds = n_rounds;
   return converged;
+}
+
+/* ================================================================================================================
+ * Landmark::update (src/types/landmark.cpp:66-152) and the trajectory wire formats
+ * (src/types/world_map.cpp:183-252).  Eigen is un-vendored: the evaluation order of its fixed-size products is not
+ * pinned by the reference; the order below (left to right, no contraction) is the contract shared with the kernel.
+ * ================================================================================================================ */
+void orc_solve3_fullpiv(const double A_in[9], const double rhs[3], double x[3]) {
+  double A[9], b[3];
+  int colperm[3] = {0, 1, 2};
+  memcpy(A, A_in, sizeof(A));
+  memcpy(b, rhs, sizeof(b));
+  int rank = 3;
+  for (int k = 0; k < 3; ++k) {
+    int pr = k, pc = k;
+    double best = -1;
+    for (int i = k; i < 3; ++i)
+      for (int j = k; j < 3; ++j)
+        if (fabs(A[i * 3 + j]) > best) {
+          best = fabs(A[i * 3 + j]);
+          pr = i;
+          pc = j;
+        }
+    if (best == 0) {
+      rank = k;
+      break;
+    }
+    if (pr != k) {
+      for (int j = 0; j < 3; ++j) {
+        const double t = A[k * 3 + j];
+        A[k * 3 + j] = A[pr * 3 + j];
+        A[pr * 3 + j] = t;
+      }
+      const double t = b[k];
+      b[k] = b[pr];
+      b[pr] = t;
+    }
+    if (pc != k) {
+      for (int i = 0; i < 3; ++i) {
+        const double t = A[i * 3 + k];
+        A[i * 3 + k] = A[i * 3 + pc];
+        A[i * 3 + pc] = t;
+      }
+      const int t = colperm[k];
+      colperm[k] = colperm[pc];
+      colperm[pc] = t;
+    }
+    for (int i = k + 1; i < 3; ++i) {
+      const double f = A[i * 3 + k] / A[k * 3 + k];
+      A[i * 3 + k] = f;
+      for (int j = k + 1; j < 3; ++j) A[i * 3 + j] -= f * A[k * 3 + j];
+      b[i] -= f * b[k];
+    }
+  }
+  double y[3] = {0, 0, 0};
+  for (int i = rank - 1; i >= 0; --i) {
+    double s = b[i];
+    for (int j = i + 1; j < rank; ++j) s -= A[i * 3 + j] * y[j];
+    y[i] = s / A[i * 3 + i];
+  }
+  for (int i = 0; i < 3; ++i) x[colperm[i]] = y[i];
+}
+
+int orc_landmark_update(const orc_landmark_measurement* ms, int n, const double* w2c, const double* c2w,
+                        uint32_t max_iterations, double max_err2, double world[3], uint32_t* number_of_updates,
+                        int* iterations) {
+  double x[3] = {world[0], world[1], world[2]};                                  /* :82 */
+  double total_previous = 0;                                                     /* :88 */
+  int outcome = 0;
+  uint32_t it = 0;
+  for (; it < max_iterations; ++it) {                                            /* :91 */
+    double H[9] = {0}, b[3] = {0}, total = 0;                                    /* :92-94 */
+    uint32_t outliers = 0;
+    for (int m = 0; m < n; ++m) {                                                /* :98 */
+      const double* W = w2c + 12 * (size_t)ms[m].frame;
+      double p[3], e[3];
+      for (int r = 0; r < 3; ++r)                                                /* :102 worldToCameraLeft * x */
+        p[r] = ((W[4 * r] * x[0] + W[4 * r + 1] * x[1]) + W[4 * r + 2] * x[2]) + W[4 * r + 3];
+      if (p[2] <= 0) {                                                           /* :103-106 */
+        ++outliers;
+        continue;
+      }
+      for (int r = 0; r < 3; ++r) e[r] = p[r] - ms[m].camera_coordinates[r];      /* :109 */
+      double w = ms[m].inverse_depth_meters;                                     /* :112 omega = I * inverse depth */
+      const double err2 = ((e[0] * w) * e[0] + (e[1] * w) * e[1]) + (e[2] * w) * e[2];   /* :115 */
+      total += err2;                                                             /* :116 */
+      if (err2 > max_err2) {                                                     /* :119-122 */
+        w *= max_err2 / err2;
+        ++outliers;
+      }
+      /* :125-132  J = R;  H += J^T (w I) J;  b += J^T (w I) e */
+      for (int i = 0; i < 3; ++i) {
+        const double jw0 = W[i] * w, jw1 = W[4 + i] * w, jw2 = W[8 + i] * w;       /* row i of J^T * omega */
+        for (int j = 0; j < 3; ++j) H[3 * i + j] += (jw0 * W[j] + jw1 * W[4 + j]) + jw2 * W[8 + j];
+        b[i] += (jw0 * e[0] + jw1 * e[1]) + jw2 * e[2];
+      }
+    }
+    double nb[3] = {-b[0], -b[1], -b[2]}, dx[3];
+    orc_solve3_fullpiv(H, nb, dx);                                               /* :136 */
+    for (int i = 0; i < 3; ++i) x[i] += dx[i];
+    if (fabs(total - total_previous) < 1e-5 || it == 999) {                      /* :139 */
+      const uint32_t inliers = (uint32_t)n - outliers;                           /* :140 (unsigned, as the reference) */
+      outcome = 3;
+      if (inliers > *number_of_updates) {                                        /* :143-147 */
+        world[0] = x[0];
+        world[1] = x[1];
+        world[2] = x[2];
+        *number_of_updates = inliers;
+        outcome = 1;
+      } else if (inliers < outliers) {                                           /* :150-160 */
+        double acc[3] = {0, 0, 0};
+        for (int m = 0; m < n; ++m) {
+          const double* C = c2w + 12 * (size_t)ms[m].frame;
+          const double* c = ms[m].camera_coordinates;
+          for (int r = 0; r < 3; ++r) acc[r] += ((C[4 * r] * c[0] + C[4 * r + 1] * c[1]) + C[4 * r + 2] * c[2]) + C[4 * r + 3];
+        }
+        for (int r = 0; r < 3; ++r) world[r] = acc[r] / n;
+        outcome = 2;
+      }
+      ++it;
+      break;
+    }
+    total_previous = total;                                                      /* :166 */
+  }
+  if (iterations) *iterations = (int)it;
+  return outcome;
+}
+
+void orc_rotation_to_quaternion(const double R[9], double q[4]) {   /* Eigen 3.3 quaternionbase_assign_impl<Matrix3> */
+  double t = R[0] + R[4] + R[8];
+  if (t > 0) {
+    t = sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (R[7] - R[5]) * t;
+    q[1] = (R[2] - R[6]) * t;
+    q[2] = (R[3] - R[1]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[3] = (R[3 * k + j] - R[3 * j + k]) * t;
+    q[j] = (R[3 * j + i] + R[3 * i + j]) * t;
+    q[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+  }
+}
+
+int orc_format_trajectory_kitti(const double T[12], char* line, int capacity) {
+  int n = 0;
+  for (int u = 0; u < 3; ++u)
+    for (int v = 0; v < 4; ++v) n += snprintf(line + n, n < capacity ? (size_t)(capacity - n) : 0, "%.9f ", T[4 * u + v]);
+  n += snprintf(line + n, n < capacity ? (size_t)(capacity - n) : 0, "\n");
+  return n;
+}
+
+int orc_format_trajectory_tum(double ts, const double T[12], char* line, int capacity) {
+  const double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+  double q[4];
+  orc_rotation_to_quaternion(R, q);
+  return snprintf(line, (size_t)capacity, "%.9f %.9f %.9f %.9f %.9f %.9f %.9f %.9f \n", ts, T[3], T[7], T[11], q[0], q[1],
+                  q[2], q[3]);
 }

@@ -321,6 +321,54 @@ class Aligner:
         return out
 
 
+LANDMARK_MEASUREMENT = np.dtype([("frame", np.int32), ("reserved", np.int32), ("camera_coordinates", np.float64, 3),
+                                 ("inverse_depth_meters", np.float64)])
+
+
+def landmark_update(measurements, world_to_camera, camera_to_world, world, number_of_updates, max_iterations=100,
+                    maximum_error_squared_meters=25.0):
+    """Landmark::update (landmark.cpp:66-152) -> (world[3], number_of_updates, outcome, iterations)"""
+    ms = np.ascontiguousarray(measurements, LANDMARK_MEASUREMENT)
+    w2c = np.ascontiguousarray(world_to_camera, np.float64)
+    c2w = np.ascontiguousarray(camera_to_world, np.float64)
+    x = np.ascontiguousarray(world, np.float64).copy()
+    n_up = C.c_uint32(int(number_of_updates))
+    it = C.c_int()
+    fn = lib().orc_landmark_update
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    outcome = fn(_p(ms), len(ms), _p(w2c), _p(c2w), int(max_iterations), float(maximum_error_squared_meters), _p(x),
+                 C.byref(n_up), C.byref(it))
+    return x, n_up.value, outcome, it.value
+
+
+def solve3(A, b):
+    A = np.ascontiguousarray(A, np.float64)
+    b = np.ascontiguousarray(b, np.float64)
+    x = np.zeros(3)
+    lib().orc_solve3_fullpiv(_p(A), _p(b), _p(x))
+    return x
+
+
+def rotation_to_quaternion(R):
+    R = np.ascontiguousarray(R, np.float64)
+    q = np.zeros(4)
+    lib().orc_rotation_to_quaternion(_p(R), _p(q))
+    return q
+
+
+def format_trajectory(robot_to_world, timestamp=None):
+    """one line of writeTrajectoryKITTI (timestamp None) / writeTrajectoryTUM (world_map.cpp:183-252)"""
+    T = np.ascontiguousarray(robot_to_world, np.float64).reshape(12)
+    buf = C.create_string_buffer(512)
+    if timestamp is None:
+        n = lib().orc_format_trajectory_kitti(_p(T), buf, 512)
+    else:
+        fn = lib().orc_format_trajectory_tum
+        fn.argtypes = [C.c_double, C.c_void_p, C.c_char_p, C.c_int]
+        n = fn(float(timestamp), _p(T), buf, 512)
+    return buf.raw[:n].decode()
+
+
 def solve6(A, b):
     A = np.ascontiguousarray(A, np.float64)
     b = np.ascontiguousarray(b, np.float64)

@@ -37,6 +37,8 @@ RECOVERED = np.dtype([("index_lost", "<i4"), ("distance", "<i4"), ("xl", "<f4"),
                       ("descriptor_right", "u1", (32,))])
 assert FRAMEPOINT.itemsize == 56 and TRACKED.itemsize == 32
 assert PREVIOUS_POINT.itemsize == 128 and TRACK.itemsize == 88 and RECOVERED.itemsize == 112
+LANDMARK_MEASUREMENT = np.dtype([("frame", "<i4"), ("reserved", "<i4"), ("camera_coordinates", "<f8", (3,)),
+                                 ("inverse_depth_meters", "<f8")])
 TRACKED_FROM_LAST_TRACK = -1
 
 # every symbol include/vslam_b200.h declares (tests check that the library exports each one)
@@ -50,7 +52,10 @@ vslam_fpg_get_kernel_profile vslam_fpg_batch_get_features vslam_fpg_stream vslam
 vslam_fpg_launch_count vslam_fpg_debug_keypoint_mask vslam_fpg_debug_blurred vslam_threshold_proposal
 vslam_aligner_create vslam_aligner_destroy vslam_aligner_upload vslam_aligner_linearize vslam_aligner_download
 vslam_aligner_one_round vslam_aligner_converge vslam_aligner_converge_fused vslam_aligner_linearize_async vslam_aligner_read_system
-vslam_aligner_stream vslam_aligner_synchronize vslam_aligner_launch_count vslam_solve6 vslam_v2t""".split()
+vslam_aligner_stream vslam_aligner_synchronize vslam_aligner_launch_count vslam_solve6 vslam_v2t
+vslam_landmark_optimizer_create vslam_landmark_optimizer_destroy vslam_landmark_optimizer_update
+vslam_landmark_optimizer_launch_count vslam_format_trajectory_kitti vslam_format_trajectory_tum vslam_write_trajectory
+vslam_solve3""".split()
 
 
 class FpgConfig(C.Structure):
@@ -606,6 +611,74 @@ class StereoUVAligner(_FrameAligner):
 
 class UVDAligner(_FrameAligner):
     KIND = 1
+
+
+class LandmarkOptimizer:
+    """batched Landmark::update (reference src/types/landmark.cpp:66-152) through the C ABI"""
+
+    def __init__(self, max_landmarks, max_measurements, max_frames, device=0):
+        self._h = C.c_void_p()
+        _check(lib().vslam_landmark_optimizer_create(int(max_landmarks), int(max_measurements), int(max_frames), device,
+                                                     C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().vslam_landmark_optimizer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def update(self, offsets, measurements, world_to_camera, camera_to_world, world, number_of_updates,
+               maximum_number_of_iterations=100, maximum_error_squared_meters=25.0):
+        """-> (world[n,3], number_of_updates[n], outcome[n], iterations[n]); the inputs are not modified"""
+        off = np.ascontiguousarray(offsets, np.int32)
+        ms = np.ascontiguousarray(measurements, LANDMARK_MEASUREMENT)
+        w2c = np.ascontiguousarray(world_to_camera, np.float64).reshape(-1, 12)
+        c2w = np.ascontiguousarray(camera_to_world, np.float64).reshape(-1, 12)
+        x = np.ascontiguousarray(world, np.float64).reshape(-1, 3).copy()
+        nu = np.ascontiguousarray(number_of_updates, np.uint32).copy()
+        n = len(off) - 1
+        outcome, iterations = np.zeros(n, np.uint8), np.zeros(n, np.int32)
+        fn = lib().vslam_landmark_optimizer_update
+        fn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32,
+                       C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _check(fn(self._h, n, _p(off), _p(ms), len(w2c), _p(w2c), _p(c2w), int(maximum_number_of_iterations),
+                  float(maximum_error_squared_meters), _p(x), _p(nu), _p(outcome), _p(iterations)))
+        return x, nu, outcome, iterations
+
+    @property
+    def launch_count(self) -> int:
+        lib().vslam_landmark_optimizer_launch_count.restype = C.c_int64
+        return int(lib().vslam_landmark_optimizer_launch_count(self._h))
+
+
+def format_trajectory(robot_to_world, timestamp=None) -> str:
+    """one line of WorldMap::writeTrajectoryKITTI (timestamp None) / writeTrajectoryTUM"""
+    T = np.ascontiguousarray(robot_to_world, np.float64).reshape(12)
+    buf = C.create_string_buffer(512)
+    if timestamp is None:
+        n = lib().vslam_format_trajectory_kitti(_p(T), buf, 512)
+    else:
+        fn = lib().vslam_format_trajectory_tum
+        fn.argtypes = [C.c_double, C.c_void_p, C.c_char_p, C.c_int32]
+        n = fn(float(timestamp), _p(T), buf, 512)
+    return buf.raw[:n].decode()
+
+
+def write_trajectory(filename, robot_to_world, timestamps=None):
+    T = np.ascontiguousarray(robot_to_world, np.float64).reshape(-1, 12)
+    ts = None if timestamps is None else np.ascontiguousarray(timestamps, np.float64)
+    _check(lib().vslam_write_trajectory(str(filename).encode(), 0 if ts is None else 1, len(T), _p(T), _p(ts)))
+
+
+def solve3(A, b):
+    A, b, x = np.ascontiguousarray(A, np.float64), np.ascontiguousarray(b, np.float64), np.zeros(3)
+    lib().vslam_solve3(_p(A), _p(b), _p(x))
+    return x
 
 
 def solve6(A, b):

@@ -68,6 +68,52 @@ VSLAM_HD inline void solve6(const double A_in[36], const double rhs[6], double x
   for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
 }
 
+// Eigen::FullPivLU<Matrix3>::solve as used by Landmark::update (reference src/types/landmark.cpp:136): the same
+// complete-pivoting elimination as solve6, on 3 x 3
+VSLAM_HD inline void solve3(const double A_in[9], const double rhs[3], double x[3]) {
+  double A[9], b[3];
+  int perm[3] = {0, 1, 2};
+  for (int i = 0; i < 9; ++i) A[i] = A_in[i];
+  for (int i = 0; i < 3; ++i) b[i] = rhs[i];
+  int rank = 3;
+  for (int k = 0; k < 3; ++k) {
+    int pr = k, pc = k;
+    double biggest = -1;
+    for (int i = k; i < 3; ++i)
+      for (int j = k; j < 3; ++j)
+        if (fabs(A[i * 3 + j]) > biggest) {
+          biggest = fabs(A[i * 3 + j]);
+          pr = i;
+          pc = j;
+        }
+    if (biggest == 0) {
+      rank = k;
+      break;
+    }
+    if (pr != k) {
+      for (int j = 0; j < 3; ++j) swap_values(A[k * 3 + j], A[pr * 3 + j]);
+      swap_values(b[k], b[pr]);
+    }
+    if (pc != k) {
+      for (int i = 0; i < 3; ++i) swap_values(A[i * 3 + k], A[i * 3 + pc]);
+      swap_values(perm[k], perm[pc]);
+    }
+    for (int i = k + 1; i < 3; ++i) {
+      const double f = A[i * 3 + k] / A[k * 3 + k];
+      A[i * 3 + k] = f;
+      for (int j = k + 1; j < 3; ++j) A[i * 3 + j] -= f * A[k * 3 + j];
+      b[i] -= f * b[k];
+    }
+  }
+  double y[3] = {0, 0, 0};
+  for (int i = rank - 1; i >= 0; --i) {
+    double s = b[i];
+    for (int j = i + 1; j < rank; ++j) s -= A[i * 3 + j] * y[j];
+    y[i] = s / A[i * 3 + i];
+  }
+  for (int i = 0; i < 3; ++i) x[perm[i]] = y[i];
+}
+
 VSLAM_HD inline void v2t(const double v[6], double T[12]) {
   double qx = v[3], qy = v[4], qz = v[5], qw;
   const double n2 = qx * qx + qy * qy + qz * qz;

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <utility>
 
@@ -57,6 +58,48 @@ double threshold_proposal(double threshold, int n_keypoints, double target, doub
     if (threshold > threshold_maximum) threshold = threshold_maximum;
   }
   return threshold;
+}
+
+// Eigen::Quaternion<double>(Matrix3) as WorldMap::writeTrajectoryTUM uses it (world_map.cpp:235); Eigen is un-vendored:
+// restated from Eigen 3.3's rotation-matrix assignment (largest of trace / diagonal element decides the branch)
+void rotation_to_quaternion(const double R[9], double q[4]) {
+  double t = R[0] + R[4] + R[8];
+  if (t > 0) {
+    t = std::sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (R[7] - R[5]) * t;
+    q[1] = (R[2] - R[6]) * t;
+    q[2] = (R[3] - R[1]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[3] = (R[3 * k + j] - R[3 * j + k]) * t;
+    q[j] = (R[3 * j + i] + R[3 * i + j]) * t;
+    q[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+  }
+}
+
+// world_map.cpp:196-214: outfile << std::fixed << std::setprecision(9); twelve values row by row, each followed by " "
+int format_trajectory_kitti(const double T[12], char* line, int capacity) {
+  int n = 0;
+  for (int i = 0; i < 12; ++i) n += std::snprintf(line + (n < capacity ? n : 0), n < capacity ? (size_t)(capacity - n) : 0, "%.9f ", T[i]);
+  n += std::snprintf(line + (n < capacity ? n : 0), n < capacity ? (size_t)(capacity - n) : 0, "\n");
+  return n;
+}
+
+// world_map.cpp:230-248: timestamp, translation x y z, orientation x y z w
+int format_trajectory_tum(double timestamp_seconds, const double T[12], char* line, int capacity) {
+  const double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+  double q[4];
+  rotation_to_quaternion(R, q);
+  return std::snprintf(line, capacity > 0 ? (size_t)capacity : 0, "%.9f %.9f %.9f %.9f %.9f %.9f %.9f %.9f \n",
+                       timestamp_seconds, T[3], T[7], T[11], q[0], q[1], q[2], q[3]);
 }
 
 }  // namespace vslam

@@ -177,4 +177,17 @@ void launch_linearize_pairs(const FramePointRecord* records, int record_stride, 
                             double max_reliable_depth, int inverse_depth_weight, double* systems, double* errors,
                             uint8_t* inliers, cudaStream_t stream);
 
+// Landmark::Measurement (reference src/types/landmark.h:19-33) as the device reads it; == vslam_landmark_measurement
+struct LandmarkMeasurement {
+  int32_t frame;                   // index into the pose tables
+  int32_t reserved;
+  double camera_coordinates[3];
+  double inverse_depth_meters;
+};
+// one warp per landmark: Landmark::update's Gauss-Newton (landmark.cpp:82-167); poses are row-major 3x4 per frame
+void launch_landmark_update(int n_landmarks, const int32_t* offsets, const LandmarkMeasurement* measurements,
+                            const double* world_to_camera, const double* camera_to_world, uint32_t max_iterations,
+                            double max_err2, double* world, uint32_t* number_of_updates, uint8_t* outcome,
+                            int32_t* iterations, cudaStream_t stream);
+
 }  // namespace vslam

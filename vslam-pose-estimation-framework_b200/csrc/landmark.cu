@@ -1,0 +1,150 @@
+// landmark.cu -- K13 landmark_update_kernel: Landmark::update (reference src/types/landmark.cpp:66-152), the per-landmark
+// 3 x 3 Gauss-Newton refinement that PoseTracker3D::_updatePoints (src/position_tracking/pose_tracker_3d.cpp:475-549)
+// runs for every tracked landmark of a frame.  Landmarks are independent: one WARP per landmark.
+//
+// The lanes evaluate the measurements of a chunk in parallel (transform, error, robust weight, the 9 + 3 + 1 terms of
+// J^T W J, J^T W e and chi^2); the terms then meet in shared memory and lanes 0..12 add them IN MEASUREMENT ORDER, which
+// is the reference's loop order: with -fmad=false and the oracle's expression order (oracle/c/vslam_oracle.c,
+// orc_landmark_update) the refined positions are bit-identical to the CPU restatement, not merely close.
+#include "gn_math.h"
+#include "kernels.cuh"
+
+namespace vslam {
+
+namespace {
+
+constexpr int kLmWarps = 4;      // landmarks per CTA
+constexpr int kLmTerms = 13;     // H (9, the reference accumulates the full matrix), b (3), total error
+
+// ordered sum of the lanes' terms: lane c < n_terms adds s[c][0 .. count-1] to its running sum
+__device__ __forceinline__ void ordered_add(double (*s)[33], const double* terms, int n_terms, int count, int lane,
+                                            double& running) {
+  for (int c = 0; c < n_terms; ++c) s[c][lane] = terms[c];
+  __syncwarp();
+  if (lane < n_terms)
+    for (int l = 0; l < count; ++l) running = running + s[lane][l];
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kLmWarps * 32) landmark_update_kernel(
+    int n_landmarks, const int32_t* __restrict__ offsets, const LandmarkMeasurement* __restrict__ measurements,
+    const double* __restrict__ world_to_camera, const double* __restrict__ camera_to_world, uint32_t max_iterations,
+    double max_err2, double* __restrict__ world, uint32_t* __restrict__ number_of_updates,
+    uint8_t* __restrict__ outcome, int32_t* __restrict__ iterations) {
+  __shared__ double s_terms[kLmWarps][kLmTerms][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lm = blockIdx.x * kLmWarps + warp;
+  if (lm >= n_landmarks) return;                       // warps are independent (no block barrier)
+  double (*s)[33] = s_terms[warp];
+  const int begin = offsets[lm], n = offsets[lm + 1] - begin;
+  const LandmarkMeasurement* ms = measurements + begin;
+  double x[3] = {world[3 * (size_t)lm], world[3 * (size_t)lm + 1], world[3 * (size_t)lm + 2]};   // :82
+  const uint32_t updates_so_far = number_of_updates[lm];
+  double total_previous = 0;                                                                      // :88
+  int result = 0;
+  uint32_t it = 0;
+  for (; it < max_iterations; ++it) {                                                             // :91
+    double running = 0;                                 // lane c: H[c] (c < 9), b[c - 9] (c < 12), total (c == 12)
+    uint32_t outliers = 0;
+    for (int c0 = 0; c0 < n; c0 += 32) {                                                          // :98
+      const int m = c0 + lane;
+      double terms[kLmTerms];
+#pragma unroll
+      for (int c = 0; c < kLmTerms; ++c) terms[c] = 0.0;   // +0.0 is neutral for sums that start at +0.0
+      bool outlier = false;
+      if (m < n) {
+        const LandmarkMeasurement q = ms[m];
+        const double* W = world_to_camera + 12 * (size_t)q.frame;
+        double w_[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) w_[i] = __ldg(W + i);
+        double p[3], e[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)                                                               // :102
+          p[r] = ((w_[4 * r] * x[0] + w_[4 * r + 1] * x[1]) + w_[4 * r + 2] * x[2]) + w_[4 * r + 3];
+        if (p[2] <= 0) {                                                                          // :103-106
+          outlier = true;
+        } else {
+#pragma unroll
+          for (int r = 0; r < 3; ++r) e[r] = p[r] - q.camera_coordinates[r];                      // :109
+          double w = q.inverse_depth_meters;                                                      // :112
+          const double err2 = ((e[0] * w) * e[0] + (e[1] * w) * e[1]) + (e[2] * w) * e[2];        // :115
+          terms[12] = err2;                                                                       // :116
+          if (err2 > max_err2) {                                                                  // :119-122
+            w = w * (max_err2 / err2);
+            outlier = true;
+          }
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {                                                           // :125-132
+            const double jw0 = w_[i] * w, jw1 = w_[4 + i] * w, jw2 = w_[8 + i] * w;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) terms[3 * i + j] = (jw0 * w_[j] + jw1 * w_[4 + j]) + jw2 * w_[8 + j];
+            terms[9 + i] = (jw0 * e[0] + jw1 * e[1]) + jw2 * e[2];
+          }
+        }
+      }
+      outliers += __popc(__ballot_sync(0xffffffffu, outlier));
+      ordered_add(s, terms, kLmTerms, min(32, n - c0), lane, running);
+    }
+    double H[9], nb[3], dx[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) H[i] = __shfl_sync(0xffffffffu, running, i);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) nb[i] = -__shfl_sync(0xffffffffu, running, 9 + i);
+    const double total = __shfl_sync(0xffffffffu, running, 12);
+    solve3(H, nb, dx);                                                                            // :136 (every lane)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) x[i] = x[i] + dx[i];
+    if (fabs(total - total_previous) < 1e-5 || it == 999) {                                       // :139
+      const uint32_t inliers = (uint32_t)n - outliers;                                            // :140
+      result = 3;
+      if (inliers > updates_so_far) {                                                      // :143-147
+        if (lane == 0) {
+          world[3 * (size_t)lm] = x[0];
+          world[3 * (size_t)lm + 1] = x[1];
+          world[3 * (size_t)lm + 2] = x[2];
+          number_of_updates[lm] = inliers;
+        }
+        result = 1;
+      } else if (inliers < outliers) {                                                            // :150-160
+        double acc = 0;
+        for (int c0 = 0; c0 < n; c0 += 32) {
+          const int m = c0 + lane;
+          double terms[3] = {0.0, 0.0, 0.0};
+          if (m < n) {
+            const LandmarkMeasurement q = ms[m];
+            const double* C = camera_to_world + 12 * (size_t)q.frame;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+              terms[r] = ((__ldg(C + 4 * r) * q.camera_coordinates[0] + __ldg(C + 4 * r + 1) * q.camera_coordinates[1]) +
+                          __ldg(C + 4 * r + 2) * q.camera_coordinates[2]) + __ldg(C + 4 * r + 3);
+          }
+          ordered_add(s, terms, 3, min(32, n - c0), lane, acc);
+        }
+        if (lane < 3) world[3 * (size_t)lm + lane] = acc / n;
+        result = 2;
+      }
+      ++it;
+      break;
+    }
+    total_previous = total;                                                                       // :166
+  }
+  if (lane == 0) {
+    if (outcome) outcome[lm] = (uint8_t)result;
+    if (iterations) iterations[lm] = (int32_t)it;
+  }
+}
+
+}  // namespace
+
+void launch_landmark_update(int n_landmarks, const int32_t* offsets, const LandmarkMeasurement* measurements,
+                            const double* world_to_camera, const double* camera_to_world, uint32_t max_iterations,
+                            double max_err2, double* world, uint32_t* number_of_updates, uint8_t* outcome,
+                            int32_t* iterations, cudaStream_t stream) {
+  if (n_landmarks <= 0) return;
+  landmark_update_kernel<<<(n_landmarks + kLmWarps - 1) / kLmWarps, kLmWarps * 32, 0, stream>>>(
+      n_landmarks, offsets, measurements, world_to_camera, camera_to_world, max_iterations, max_err2, world,
+      number_of_updates, outcome, iterations);
+}
+
+}  // namespace vslam

@@ -196,3 +196,55 @@ def correspondences(n: int, kind: str = "stereouv", cam: Camera | None = None, s
     else:
         raise ValueError(kind)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# landmark histories (Landmark::update)
+# ---------------------------------------------------------------------------------------------
+
+LANDMARK_MEASUREMENT = np.dtype([("frame", "<i4"), ("reserved", "<i4"), ("camera_coordinates", "<f8", (3,)),
+                                 ("inverse_depth_meters", "<f8")])   # == vslam_landmark_measurement
+
+
+def landmark_histories(n_landmarks: int, n_frames: int = 40, seed: int = 7, noise: float = 0.02,
+                       outlier_fraction: float = 0.05, behind_fraction: float = 0.0):
+    """A camera moving forward along z with a small yaw observes `n_landmarks` world points; landmark i has been seen in
+    a contiguous run of frames ending at the last one (track lengths 2 .. n_frames, as a track grows in the reference).
+    Returns world_to_camera[n_frames, 12], camera_to_world[n_frames, 12] (row-major 3x4), offsets[n+1] (CSR),
+    measurements (frame, camera coordinates with N(0, noise * z) error, inverse depth), the initial estimates
+    world[n, 3] (the "rude average" of landmark.cpp:21-31), number_of_updates[n] and the true points."""
+    rng = np.random.default_rng(seed)
+    w2c, c2w = np.zeros((n_frames, 12)), np.zeros((n_frames, 12))
+    for f in range(n_frames):
+        R = _rot(0.002 * f, 0.01 * f, -0.001 * f)
+        t_wc = np.array([0.03 * f, -0.01 * f, 0.7 * f])          # camera position in the world
+        c2w[f] = np.hstack([R, t_wc[:, None]]).reshape(12)
+        w2c[f] = np.hstack([R.T, (-R.T @ t_wc)[:, None]]).reshape(12)
+    last = c2w[-1].reshape(3, 4)
+    z = rng.uniform(3.0, 40.0, n_landmarks)
+    p_cam = np.stack([rng.uniform(-0.8, 0.8, n_landmarks) * z, rng.uniform(-0.3, 0.3, n_landmarks) * z, z], 1)
+    truth = p_cam @ last[:, :3].T + last[:, 3]
+    lengths = rng.integers(2, n_frames + 1, n_landmarks)
+    offsets = np.zeros(n_landmarks + 1, np.int32)
+    offsets[1:] = np.cumsum(lengths)
+    ms = np.zeros(int(offsets[-1]), LANDMARK_MEASUREMENT)
+    world = np.zeros((n_landmarks, 3))
+    for i in range(n_landmarks):
+        frames = np.arange(n_frames - lengths[i], n_frames)
+        W = w2c[frames].reshape(-1, 3, 4)
+        c = np.einsum("fij,j->fi", W[:, :, :3], truth[i]) + W[:, :, 3]
+        c = c + rng.normal(0.0, noise, c.shape) * np.abs(c[:, 2:3])
+        gross = rng.random(len(frames)) < outlier_fraction
+        c[gross] += rng.normal(0.0, 8.0, (int(gross.sum()), 3))
+        behind = rng.random(len(frames)) < behind_fraction
+        sl = slice(offsets[i], offsets[i + 1])
+        ms["frame"][sl] = frames
+        ms["camera_coordinates"][sl] = c
+        ms["inverse_depth_meters"][sl] = 1.0 / c[:, 2]
+        Cw = c2w[frames].reshape(-1, 3, 4)
+        world[i] = (np.einsum("fij,fj->fi", Cw[:, :, :3], c) + Cw[:, :, 3]).mean(0)
+        if behind.any():                                          # an estimate far behind the first cameras
+            world[i] = world[i] - np.array([0.0, 0.0, 200.0])
+    n_updates = np.maximum(lengths - rng.integers(1, 4, n_landmarks), 0).astype(np.uint32)
+    return {"world_to_camera": w2c, "camera_to_world": c2w, "offsets": offsets, "measurements": ms, "world": world,
+            "number_of_updates": n_updates, "truth": truth}
