@@ -150,7 +150,7 @@ def run_reference(args):
                              "sample": "%d pairs per step (%d distinct), one process per core, oracle tier B (cv2 %s)"
                                        % (per_step, distinct, cv2.__version__)},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT, flush=True)
     return 0
 
 
@@ -358,8 +358,22 @@ def peaks():
     return 6650.0, "fallback"
 
 
+_RESULT = sys.stdout
+
+
+def _claim_stdout():
+    """stdout carries ONE JSON line: keep a private handle on the real stdout for it and point file descriptor 1 at
+    stderr, so that nothing a library prints (NCCL's version banner under torchrun, for one) can land beside it"""
+    global _RESULT
+    sys.stdout.flush()
+    _RESULT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+
+
 def main():
     args = parse()
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -373,7 +387,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL_DEBUG=VERSION prints a banner on stdout; stdout carries ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # (and file descriptor 1 is stderr by now, _claim_stdout)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -506,7 +520,7 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(dl, dr, R, args.cpu_sample)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_RESULT, flush=True)
     gen.close()
     if world > 1:
         dist.barrier()
