@@ -162,6 +162,28 @@ def workload_config(args, pairs):
             "l2": "inputs larger than L2 (%.0f MB of images per step per GPU)" % (pairs * 2 * 1241 * 376 / 1e6)}
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Best effort: run this rank (and hence first-touch its pinned host buffers) on the CPU cores NVML reports as local to
+    its GPU, so that the H2D stream of `e2e` does not cross the socket interconnect when 4 or 8 ranks share the host.
+    Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+        handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        n_cpus = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpus + 63) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = local & allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return "bound to %d of %d cores local to the GPU" % (len(cpus), len(allowed))
+        return "all %d allowed cores are local to the GPU" % len(allowed)
+    except Exception as e:   # no NVML, no permission: the run is still valid, only possibly slower end to end
+        return "not bound (%s)" % type(e).__name__
+
+
 # ------------------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons of one GPU (B200_PROFILING.md recipe).  Started before the warm-up so that
@@ -391,6 +413,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else "single rank: not bound"
 
     def barrier():
         torch.cuda.synchronize()
@@ -510,7 +533,7 @@ def main():
             "dtype": "u8+f64", "data": "synthetic (band-world, %d distinct pairs per GPU tiled to %d)" % (D, P),
             "config": workload_config(args, P), "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s / K * 1e3},
+                    "ms_per_step": e2e_s / K * 1e3, "host_placement": numa},
             "gpu_launches": int(launches), "roofline": roofline,
             "counts": {"mean_descriptors_left": float(nl.mean()), "mean_matches": float(nm.mean()),
                        "mean_framepoints": float(nf.mean())}}
