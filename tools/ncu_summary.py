@@ -63,6 +63,17 @@ def launches(path):
     print("%-28s %6s %12s %10s %7s" % ("kernel", "n", "total_us", "avg_us", "share"))
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print("%-28s %6d %12.1f %10.1f %7.3f" % (k, v[0], v[1], v[1] / v[0], v[1] / tot))
+    # the kernels of ONE bench step (the other launches belong to bench.py's aligner_stress / sequence sections and to
+    # the e2e repitch): their shares are what roofline.kernel_share_of_step must agree with
+    step = ("fast_nms_kernel", "compact_kernel", "blur_kernel", "describe_tile_kernel", "match_kernel",
+            "select_strips_kernel", "linearize_pairs_kernel")
+    stot = sum(agg[k][1] for k in step if k in agg)
+    if stot:
+        print()
+        print("kernels of the bench step only:")
+        for k in step:
+            if k in agg:
+                print("%-28s %6d %12.1f %10.1f %7.3f" % (k, agg[k][0], agg[k][1], agg[k][1] / agg[k][0], agg[k][1] / stot))
 
 
 if __name__ == "__main__":
