@@ -414,3 +414,54 @@ def test_full_size_batch_is_replication_invariant():
         for r in range(1, total // distinct):
             assert view[r, i, :counts[i]].tobytes() == ref, (r, i)
     gen.close()
+
+
+def _stress_images(kind, rows, cols, seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:rows, 0:cols]
+    if kind == "noise":                       # almost every pixel passes the pre-test; dense corners
+        img = rng.integers(0, 256, (rows, cols))
+    elif kind == "squares":                   # isolated bright 7 x 7 squares on black: L-corners on a lattice, almost equal
+        img = (((yy % 13) < 7) & ((xx % 13) < 7)) * 249 + rng.integers(0, 7, (rows, cols))   # near-ties in the 3x3 NMS
+    elif kind == "saturated_rectangles":      # overlapping flat 0 / 255 / mid-grey rectangles
+        img = np.full((rows, cols), 128)
+        for _ in range(rows * cols // 400):
+            y, x, h, w = rng.integers(0, rows), rng.integers(0, cols), rng.integers(4, 30), rng.integers(4, 30)
+            img[y:y + h, x:x + w] = rng.choice([0, 255, 64, 200])
+    elif kind == "gradient_texture":          # smooth ramp + mid-frequency texture + sparse salt
+        img = (xx * 255.0 / cols + 40 * np.sin(yy / 3.0) * np.sin(xx / 4.0)).astype(np.int64)
+        salt = rng.random((rows, cols)) < 0.01
+        img = np.where(salt, rng.integers(0, 256, (rows, cols)), img)
+    else:
+        raise ValueError(kind)
+    left = np.clip(img, 0, 255).astype(np.uint8)
+    right = np.roll(left, -6, axis=1)         # a constant 6 px disparity: plenty of true matches
+    return np.ascontiguousarray(left), np.ascontiguousarray(right)
+
+
+@pytest.mark.parametrize("kind", ["noise", "squares", "saturated_rectangles", "gradient_texture"])
+@pytest.mark.parametrize("rows,cols,grid", [(217, 333, (1, 1)), (250, 515, (2, 2)), (131, 129, (1, 3))])
+def test_stress_patterns_at_odd_sizes_match_oracle(kind, rows, cols, grid):
+    """image statistics and shapes the band world does not produce: dense noise (every candidate list full), saturated
+    lattices (blur rounding ties, equal scores in the 3x3 NMS), widths that are no multiple of 4 / 32 / 128, tiles cut
+    by the image border in both directions, 1x3 and 2x2 detector grids.  Everything stays bit-exact."""
+    import dataclasses
+    cfg = dataclasses.replace(configs.EUROC, number_of_detectors_vertical=grid[0], number_of_detectors_horizontal=grid[1],
+                              detector_threshold_minimum=7, detector_threshold_maximum=60)
+    cam = synth.Camera(cols, rows, 300.0, 300.0, cols / 2.0, rows / 2.0, -30.0)
+    left, right = _stress_images(kind, rows, cols, rows + cols)
+    gen = api.StereoFramePointGenerator(cfg, cam, max_keypoints=40000)
+    o = pipeline.StereoFramePointGeneratorOracle(cfg, cam, "a")
+    for frame in range(2):                    # the second frame runs at the thresholds the controller proposed
+        nl, nr = gen.initialize(left, right, frame == 0)
+        o.initialize(left, right, frame == 0)
+        assert (nl, nr) == (len(o.kps_left), len(o.kps_right))
+        _check_pair(gen, o)
+        assert np.array_equal(gen.debug_blurred(0), tier_a.gauss7_u8(left))
+        fps = gen.compute()
+        o.compute(None)
+        assert gen.number_of_matches == len(o.matches)
+        _same_points(fps, o.framepoints())
+        assert np.array_equal(gen.thresholds, o.thresholds)
+        left, right = np.ascontiguousarray(left[:, ::-1]), np.ascontiguousarray(right[:, ::-1])   # new content next frame
+    gen.close()
