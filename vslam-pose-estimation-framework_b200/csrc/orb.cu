@@ -44,12 +44,20 @@ __device__ __forceinline__ float2 bytes_to_float2(uint32_t wa, uint32_t wb, int 
 //                 + k6 (E_{j+2} + E_{j-1}), all packed FADD2 / FFMA2, in the oracle's order
 // Packed ops are two IEEE fp32 operations per instruction: every result equals the scalar evaluation bit for bit.
 constexpr int BL_W = 128;               // columns of a warp tile (4 per lane)
-constexpr int BL_H = 50;                // output rows of a warp tile: 56 staged rows = 7 loop trips x 4 row pairs
+#ifndef VSLAM_BL_H
+#define VSLAM_BL_H 47
+#endif
+constexpr int BL_H = VSLAM_BL_H;        // output rows of a warp tile (376 = 8 x 47: no KITTI tile row is wasted)
 constexpr int BL_SW = BL_W + 32;        // staged columns x0-16 .. x0+143 (TMA rows are multiples of 16 bytes)
 constexpr int BL_SH = BL_H + 6;         // staged rows y0-3 .. y0+52
-static_assert(BL_SH % 8 == 0, "the walk is unrolled over 4 row pairs (the period of the register rings)");
-constexpr int BL_WARPS = 4;             // independent warp tiles per CTA (stacked in y)
-constexpr int BL_TILE = (BL_SW * BL_SH + 127) / 128 * 128;   // TMA destinations are 128-byte aligned
+constexpr int BL_WALK = (BL_SH + 7) / 8 * 8;   // the walk is unrolled over 4 row pairs (the period of the register rings):
+                                               // it may run up to 7 rows past the staged ones; what it computes from
+                                               // them lands in output rows >= BL_H, which are never stored
+#ifndef VSLAM_BL_WARPS
+#define VSLAM_BL_WARPS 4
+#endif
+constexpr int BL_WARPS = VSLAM_BL_WARPS;       // independent warp tiles per CTA (stacked in y)
+constexpr int BL_TILE = (BL_SW * BL_WALK + 127) / 128 * 128;   // TMA destinations are 128-byte aligned
 
 __global__ void __launch_bounds__(BL_WARPS * 32, 4) blur_kernel(const __grid_constant__ CUtensorMap image_map, Geometry g,
                                                                 GaussKernel gk, int first_image,
@@ -111,13 +119,13 @@ __global__ void __launch_bounds__(BL_WARPS * 32, 4) blur_kernel(const __grid_con
   for (int t = 0; t < 7; ++t) kk[t] = make_float2(gk.k[t], gk.k[t]);
   const float2 bias = make_float2(12582912.0f, 12582912.0f);   // 1.5 * 2^23: rint(acc) lands in the low mantissa byte
   uint8_t* o = blurred + ((size_t)img * g.rows + y0) * g.pitch + x0 + 4 * lane;
-  const int n_y = g.rows - y0;            // output rows of this tile that exist
+  const int n_y = min(BL_H, g.rows - y0);   // output rows of this tile that exist
   // rings of the last four E and O pairs, indexed by compile-time constants only (registers).  The loop is unrolled
   // over ONE ring period (4 steps): a fully unrolled walk (3.9 k instructions) ran out of the instruction cache
   // (39 % of the warp stalls were "no instruction").
   float2 E[4][4], O[4][4];
 #pragma unroll 1
-  for (int i4 = 0; i4 < BL_SH / 2; i4 += 4) {
+  for (int i4 = 0; i4 < BL_WALK / 2; i4 += 4) {
 #pragma unroll
     for (int s4 = 0; s4 < 4; ++s4) {
       const int i = i4 + s4;
