@@ -21,7 +21,11 @@ constexpr int TH = 54;             // output tile height; TH + 2 = 56 pre-test r
 constexpr int RPW = (TH + 2) / 8;  // pre-test rows per warp
 static_assert((TH + 2) % 8 == 0 && 4 * RPW + 4 <= 32, "one flag register per lane: 4 bits per row + 4 for the halo word");
 constexpr int HX = 16;             // smem halo in x (only 4 needed; 16 keeps uint4 loads aligned)
-constexpr int SW = TW + 2 * HX;    // 160
+constexpr int SW = TW + 2 * HX + 16;   // 176 bytes = 44 words: consecutive rows are 12 banks apart, so the RPW = 7 consecutive
+                                       // rows of a warp start in 7 DIFFERENT banks (0, 12, 24, 4, 16, 28, 8).  With 160-byte
+                                       // rows 8 apart, all candidates of a lane shared one bank in the 17 ring look-ups of
+                                       // phase 2; the kernel is bound by shared-memory wavefronts (92 % of peak, ncu r1h).
+                                       // TMA box rows are multiples of 16 bytes; the 16 extra columns are not read.
 constexpr int SH = TH + 8;         // 3 (ring) + 1 (NMS) on both sides
 constexpr int CW = TW + 2;         // score tile width (NMS halo 1)
 constexpr int CH = TH + 2;
@@ -223,9 +227,9 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(const __grid_constant__ C
                    : "=r"(done) : "r"(bar) : "memory");
   }
 
-  // ---- phase 1 (warp-private): compass pre-test on the tile + 1 px NMS halo.  Warp w owns pre-test rows w, w+8,
-  // w+16, w+24; lane l owns the aligned word at image x = x0 + 4*l, and lanes 0..7 also the two halo words
-  // (x0-4.. and x0+128..) of the warp's four rows.
+  // ---- phase 1 (warp-private): compass pre-test on the tile + 1 px NMS halo.  Warp w owns the RPW consecutive
+  // pre-test rows from RPW * w; lane l owns the aligned word at image x = x0 + 4*l, and lanes < 2 RPW also the two
+  // halo words (x0-4.. and x0+128..) of the warp's rows.
   const int cx_lo = max(ax0, x0 - 1), cx_hi = min(ax1, x0 + TW);   // columns whose score is needed
   const bool interior = cx_lo == x0 - 1 && cx_hi == x0 + TW && y0 - 1 >= ay0 && y0 + TH <= ay1;
   uint16_t* list = s_list[warp];
@@ -233,14 +237,14 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(const __grid_constant__ C
   int ncand = 0;
   if (t <= 127) {
     const uint32_t cadd = 0x01010101u * (uint32_t)(127 - t);
-    const int hsy = warp + 8 * min(lane >> 1, RPW - 1), hwi = (lane & 1) ? 33 : 0;   // halo word of lanes < 2 RPW
+    const int hsy = RPW * warp + min(lane >> 1, RPW - 1), hwi = (lane & 1) ? 33 : 0;   // halo word of lanes < 2 RPW
     // every lane first collects the flags of ITS pixels (RPW rows x 4 bytes + halo word) in one register: nibble `it`
     // = the four pixels of pre-test row it, nibble RPW = the halo word ...
     uint32_t flags = 0;
     if (interior) {
 #pragma unroll
       for (int it = 0; it < RPW; ++it) {
-        const uint32_t m = compass_pretest<true>(s_img, warp + 8 * it, lane + 1, cadd, x0, y0, ay0, ay1, cx_lo, cx_hi);
+        const uint32_t m = compass_pretest<true>(s_img, RPW * warp + it, lane + 1, cadd, x0, y0, ay0, ay1, cx_lo, cx_hi);
         flags |= ((((m >> 7) & 0x01010101u) * 0x01020408u) >> 24) << (4 * it);
       }
       uint32_t m = 0;
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(const __grid_constant__ C
     } else {
 #pragma unroll 1
       for (int it = 0; it < RPW; ++it) {
-        const uint32_t m = compass_pretest<false>(s_img, warp + 8 * it, lane + 1, cadd, x0, y0, ay0, ay1, cx_lo, cx_hi);
+        const uint32_t m = compass_pretest<false>(s_img, RPW * warp + it, lane + 1, cadd, x0, y0, ay0, ay1, cx_lo, cx_hi);
         flags |= ((((m >> 7) & 0x01010101u) * 0x01020408u) >> 24) << (4 * it);
       }
       uint32_t m = 0;
@@ -268,13 +272,13 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(const __grid_constant__ C
     }
     ncand = __shfl_sync(0xffffffffu, inc, 31);
     uint16_t* dst = list + (inc - mine);
-    // bit b of the low half = pre-test row b >> 2, byte b & 3: code = (warp + 8 (b >> 2)) << 8 | 4 lane + 1 + (b & 3)
-    const uint32_t code0 = (uint32_t)((warp << 8) + 4 * lane + 1);
+    // bit b = pre-test row b >> 2 of this warp, byte b & 3: code = (RPW warp + (b >> 2)) << 8 | 4 lane + 1 + (b & 3)
+    const uint32_t code0 = (uint32_t)(((RPW * warp) << 8) + 4 * lane + 1);
     uint32_t rows4 = flags & ((1u << (4 * RPW)) - 1u);
     while (rows4) {
       const uint32_t bit = (uint32_t)__ffs((int)rows4) - 1u;
       rows4 &= rows4 - 1u;
-      *dst++ = (uint16_t)(code0 + ((bit & ~3u) << 9) + (bit & 3u));
+      *dst++ = (uint16_t)(code0 + ((bit & ~3u) << 6) + (bit & 3u));
     }
     uint32_t halo = flags >> (4 * RPW);   // lanes < 2 RPW only, and rarely set
     while (halo) {
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(const __grid_constant__ C
     }
   } else {   // thresholds above 127 (never produced by the reference's configurations): every pixel is a candidate
     for (int it = 0; it < RPW; ++it) {
-      const int sy = warp + 8 * it, iy = y0 - 1 + sy;
+      const int sy = RPW * warp + it, iy = y0 - 1 + sy;
       for (int sx0 = 0; sx0 < CW; sx0 += 32) {
         const int sx = sx0 + lane, ix = x0 - 1 + sx;
         const bool on = sx < CW && ix >= cx_lo && ix <= cx_hi && iy >= ay0 && iy <= ay1;
