@@ -290,9 +290,9 @@ def aligner_stress(api, configs, synth, torch, dev):
         # the linearize kernel alone at a size that exceeds L2: CUDA events on the library's stream
         big = 4_000_000
         reps_n = big // n
-        al.initialize(np.tile(c["moving"], (reps_n, 1)), np.tile(c["fixed"], (reps_n, 1)),
-                      np.tile(omega, (reps_n, 1)) if omega.ndim == 2 else np.tile(omega, reps_n), np.tile(c["wt"], reps_n),
-                      cam.K, cam.baseline, cam.rows, cam.cols, synth.true_motion())
+        big_set = (np.tile(c["moving"], (reps_n, 1)), np.tile(c["fixed"], (reps_n, 1)),
+                   np.tile(omega, (reps_n, 1)) if omega.ndim == 2 else np.tile(omega, reps_n), np.tile(c["wt"], reps_n))
+        al.initialize(*big_set, cam.K, cam.baseline, cam.rows, cam.cols, synth.true_motion())
         for _ in range(3):
             al.linearize_async(False)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -304,9 +304,24 @@ def aligner_stress(api, configs, synth, torch, dev):
         al.synchronize()
         ms = e0.elapsed_time(e1) / 10
         gbs = 81.0 * big / (ms * 1e-3) / 1e9
+        # size sweep of the linearize kernel alone (show the asymptote), uploads outside the timed launches
+        sweep = []
+        for m in (10_000, 100_000, 1_000_000, 4_000_000):
+            al.initialize(*(a[:m] for a in big_set), cam.K, cam.baseline, cam.rows, cam.cols, synth.true_motion())
+            for _ in range(3):
+                al.linearize_async(False)
+            al.synchronize()
+            e0.record(stream)
+            for _ in range(10):
+                al.linearize_async(False)
+            e1.record(stream)
+            al.synchronize()
+            ms_m = e0.elapsed_time(e1) / 10
+            sweep.append({"n": m, "us": ms_m * 1e3, "gbs": 81.0 * m / (ms_m * 1e-3) / 1e9})
         out[kind] = {"n": n, "ten_rounds_host_driven_ms": stepwise_ms, "converge_fused_ms": fused_ms,
                      "converge_rounds": rounds, "fused_ms_per_round": fused_ms / max(rounds, 1),
-                     "linearize_4M_ms": ms, "linearize_4M_gbs": gbs, "linearize_4M_frac_of_hbm": gbs / peak}
+                     "linearize_4M_ms": ms, "linearize_4M_gbs": gbs, "linearize_4M_frac_of_hbm": gbs / peak,
+                     "linearize_sweep": sweep}
         al.close()
     return out
 
