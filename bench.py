@@ -383,9 +383,49 @@ def sequence_latency(api, configs, synth, device):
             prev = nxt
         out[name]["tracked"] = {"frames_per_s": 20 / t_total, "ms_per_frame": t_total / 20 * 1e3,
                                 "mean_previous_points": n_prev / 20, "mean_tracks": n_tracks / 20,
-                                "mean_new_points": n_new / 20}
+                                "mean_new_points": n_new / 20, "host": "python harness"}
         gen.close()
+        # the same loop from C++14 (tools/sequence_runner.cpp over include/vslam_b200.hpp): what a native host pays
+        out[name]["tracked_native"] = native_sequence(cfg, cam, frames)
     return out
+
+
+_RUNNER = {}
+
+
+def native_sequence(cfg, cam, frames, warmup=4):
+    """builds tools/sequence_runner.cpp once (g++, C++14) and runs the tracked sequence through it; None when the
+    compiler is missing or anything fails -- the number is informative, the run stays valid without it"""
+    import tempfile
+    try:
+        if "exe" not in _RUNNER:
+            d = tempfile.mkdtemp(prefix="vslam_runner_")
+            exe = os.path.join(d, "sequence_runner")
+            pkg = os.path.join(ROOT, "vslam-pose-estimation-framework_b200")
+            subprocess.check_call(["g++", "-std=c++14", "-O2", "-I", os.path.join(ROOT, "include"),
+                                   os.path.join(ROOT, "tools", "sequence_runner.cpp"), "-o", exe, "-L", pkg, "-lvslam_b200",
+                                   "-Wl,-rpath," + pkg], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            _RUNNER["exe"], _RUNNER["dir"] = exe, d
+        path = os.path.join(_RUNNER["dir"], "frames_%s.u8" % cfg.name)
+        with open(path, "wb") as f:
+            for l, r in frames:
+                f.write(np.ascontiguousarray(l).tobytes())
+                f.write(np.ascontiguousarray(r).tobytes())
+        args = [cam.rows, cam.cols, cfg.target_number_of_keypoints_tolerance, cfg.detector_threshold_minimum,
+                cfg.detector_threshold_maximum, cfg.detector_threshold_maximum_change, cfg.number_of_detectors_vertical,
+                cfg.number_of_detectors_horizontal, int(cfg.enable_keypoint_binning), cfg.bin_size_pixels,
+                cfg.maximum_matching_distance_triangulation, cfg.minimum_disparity_pixels,
+                cfg.maximum_epipolar_search_offset_pixels, cam.fx, cam.fy, cam.cx, cam.cy, cam.bx, 15]
+        res = subprocess.run([_RUNNER["exe"], path, str(len(frames)), str(warmup)] + [repr(a) for a in args],
+                             capture_output=True, text=True, timeout=120)
+        os.remove(path)
+        if res.returncode != 0:
+            return None
+        r = json.loads(res.stdout.strip().splitlines()[-1])
+        r["host"] = "C++14 (tools/sequence_runner.cpp)"
+        return r
+    except Exception:
+        return None
 
 
 def peaks():

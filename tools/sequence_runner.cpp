@@ -1,0 +1,108 @@
+// sequence_runner.cpp -- the tracker's per-frame order (reference src/position_tracking/pose_tracker_3d.cpp:80, 239,
+// 210: initialize -> track against ALL points of the previous frame -> compute with the tracks pre-loaded) driven
+// from C++14 through include/vslam_b200.hpp, i.e. what the adapters do per frame minus the reference's object graph.
+// bench.py builds and runs it to report the single-sequence latency without the Python harness in the loop.
+//
+//   sequence_runner <frames.u8> <n_frames> <warmup> <23 configuration numbers, see below>
+// frames.u8: [n_frames][2][rows][cols] u8.  Prints one JSON object.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+
+#include "vslam_b200.hpp"
+
+int main(int argc, char** argv) {
+  if (argc != 4 + 19) {
+    std::fprintf(stderr, "usage: sequence_runner frames.u8 n_frames warmup rows cols tolerance thr_min thr_max max_change "
+                         "detectors_v detectors_h binning bin_size max_distance min_disparity max_offset fx fy cx cy bx "
+                         "projection_tracking_distance descriptor_distance_tracking\n");
+    return 2;
+  }
+  try {
+    const int n_frames = std::atoi(argv[2]), warmup = std::atoi(argv[3]);
+    char** a = argv + 4;
+    vslam_fpg_config c = {};
+    c.rows = std::atoi(a[0]); c.cols = std::atoi(a[1]);
+    c.target_number_of_keypoints_tolerance = std::atof(a[2]);
+    c.detector_threshold_minimum = std::atoi(a[3]); c.detector_threshold_maximum = std::atoi(a[4]);
+    c.detector_threshold_maximum_change = std::atof(a[5]);
+    c.number_of_detectors_vertical = std::atoi(a[6]); c.number_of_detectors_horizontal = std::atoi(a[7]);
+    c.enable_keypoint_binning = std::atoi(a[8]); c.bin_size_pixels = std::atoi(a[9]);
+    c.maximum_matching_distance_triangulation = std::atof(a[10]); c.minimum_disparity_pixels = std::atof(a[11]);
+    c.maximum_epipolar_search_offset_pixels = std::atoi(a[12]);
+    c.fx = std::atof(a[13]); c.fy = std::atof(a[14]); c.cx = std::atof(a[15]); c.cy = std::atof(a[16]); c.bx = std::atof(a[17]);
+    const int tracking_distance = std::atoi(a[18]);
+    const double descriptor_distance = 25.6;
+    const size_t image_bytes = (size_t)c.rows * c.cols;
+
+    // page-locked frame buffers (vslam_host_alloc): the H2D copy of initialize() is one asynchronous DMA
+    uint8_t* frames = nullptr;
+    if (vslam_host_alloc(reinterpret_cast<void**>(&frames), 2 * image_bytes * n_frames) != VSLAM_OK)
+      throw std::runtime_error(vslam_last_error());
+    {
+      std::ifstream f(argv[1], std::ios::binary);
+      if (!f.read(reinterpret_cast<char*>(frames), (std::streamsize)(2 * image_bytes * n_frames)))
+        throw std::runtime_error("short frames file");
+    }
+    vslam::StereoFramePointGenerator generator(c);
+    generator.setProjectionTrackingDistancePixels(tracking_distance);
+    generator.setMaximumDescriptorDistanceTracking(descriptor_distance);
+    // the band world moves the camera a quarter baseline per frame along x (tests/cpp/host_api_check.cpp)
+    const double tx = -(-c.bx / c.fx) / 4;
+    const std::array<double, 12> motion{{1, 0, 0, tx, 0, 1, 0, 0, 0, 0, 1, 0}};
+
+    vslam::Frame previous, current;
+    bool have_previous = false;
+    double seconds = 0;
+    long n_previous = 0, n_tracks = 0, n_new = 0;
+    std::vector<int32_t> lost;
+    for (int k = 0; k < n_frames; ++k) {
+      const auto t0 = std::chrono::steady_clock::now();
+      current.status = k == 0 ? vslam::Frame::Localizing : vslam::Frame::Tracking;
+      current.intensity_image_left = frames + (size_t)(2 * k) * image_bytes;
+      current.intensity_image_right = frames + (size_t)(2 * k + 1) * image_bytes;
+      current.image_step = (size_t)c.cols;
+      current.tracks.clear();
+      generator.initialize(&current);
+      if (have_previous) generator.track(&current, &previous, motion, lost, false);
+      generator.compute(&current);
+      // points() of this frame as the next frame's track() reads them: the tracks, then the new points
+      // (what GpuStereoFramePointGenerator::fillPreviousPoint does per FramePoint)
+      current.previous_points.resize(current.tracks.size() + current.points.size());
+      size_t i = 0;
+      auto fill = [&](const double camera[3], int32_t index_left, int32_t index_right, int32_t epipolar_offset) {
+        vslam_previous_point& q = current.previous_points[i++];
+        for (int d = 0; d < 3; ++d) q.camera_left[d] = q.world[d] = camera[d];
+        std::memcpy(q.descriptor_left, &current.descriptors_left[(size_t)index_left * VSLAM_DESCRIPTOR_BYTES], VSLAM_DESCRIPTOR_BYTES);
+        std::memcpy(q.descriptor_right, &current.descriptors_right[(size_t)index_right * VSLAM_DESCRIPTOR_BYTES], VSLAM_DESCRIPTOR_BYTES);
+        q.epipolar_offset = epipolar_offset;
+        q.has_landmark = 1;
+        q.keypoint_size = 7.f;
+        q.reserved = 0;
+      };
+      for (const vslam_track& t : current.tracks) fill(t.camera, t.index_left, t.index_right, t.epipolar_offset);
+      for (const vslam_framepoint& p : current.points) fill(p.camera, p.index_left, p.index_right, p.epipolar_offset);
+      const auto t1 = std::chrono::steady_clock::now();
+      if (k >= warmup) {
+        seconds += std::chrono::duration<double>(t1 - t0).count();
+        n_previous += have_previous ? (long)previous.previous_points.size() : 0;
+        n_tracks += (long)current.tracks.size();
+        n_new += (long)current.points.size();
+      }
+      std::swap(previous, current);
+      have_previous = true;
+    }
+    const int timed = n_frames - warmup;
+    std::printf("{\"frames_per_s\": %.3f, \"ms_per_frame\": %.6f, \"mean_previous_points\": %.2f, \"mean_tracks\": %.2f, "
+                "\"mean_new_points\": %.2f, \"frames\": %d}\n",
+                timed / seconds, seconds / timed * 1e3, (double)n_previous / timed, (double)n_tracks / timed,
+                (double)n_new / timed, timed);
+    vslam_host_free(frames);
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "FAILED: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}
