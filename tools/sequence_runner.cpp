@@ -55,8 +55,11 @@ int main(int argc, char** argv) {
 
     vslam::Frame previous, current;
     bool have_previous = false;
-    double seconds = 0;
+    double seconds = 0, s_initialize = 0, s_track = 0, s_compute = 0, s_assemble = 0;
     long n_previous = 0, n_tracks = 0, n_new = 0;
+    auto since = [](std::chrono::steady_clock::time_point t) {
+      return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count();
+    };
     std::vector<int32_t> lost;
     for (int k = 0; k < n_frames; ++k) {
       const auto t0 = std::chrono::steady_clock::now();
@@ -66,8 +69,14 @@ int main(int argc, char** argv) {
       current.image_step = (size_t)c.cols;
       current.tracks.clear();
       generator.initialize(&current);
+      const double d_initialize = since(t0);
+      const auto t_track = std::chrono::steady_clock::now();
       if (have_previous) generator.track(&current, &previous, motion, lost, false);
+      const double d_track = since(t_track);
+      const auto t_compute = std::chrono::steady_clock::now();
       generator.compute(&current);
+      const double d_compute = since(t_compute);
+      const auto t_assemble = std::chrono::steady_clock::now();
       // points() of this frame as the next frame's track() reads them: the tracks, then the new points
       // (what GpuStereoFramePointGenerator::fillPreviousPoint does per FramePoint)
       current.previous_points.resize(current.tracks.size() + current.points.size());
@@ -87,6 +96,10 @@ int main(int argc, char** argv) {
       const auto t1 = std::chrono::steady_clock::now();
       if (k >= warmup) {
         seconds += std::chrono::duration<double>(t1 - t0).count();
+        s_initialize += d_initialize;
+        s_track += d_track;
+        s_compute += d_compute;
+        s_assemble += since(t_assemble);
         n_previous += have_previous ? (long)previous.previous_points.size() : 0;
         n_tracks += (long)current.tracks.size();
         n_new += (long)current.points.size();
@@ -96,9 +109,11 @@ int main(int argc, char** argv) {
     }
     const int timed = n_frames - warmup;
     std::printf("{\"frames_per_s\": %.3f, \"ms_per_frame\": %.6f, \"mean_previous_points\": %.2f, \"mean_tracks\": %.2f, "
-                "\"mean_new_points\": %.2f, \"frames\": %d}\n",
+                "\"mean_new_points\": %.2f, \"frames\": %d, \"us_initialize_with_feature_download\": %.1f, \"us_track\": %.1f, "
+                "\"us_compute\": %.1f, \"us_assemble_previous_points\": %.1f}\n",
                 timed / seconds, seconds / timed * 1e3, (double)n_previous / timed, (double)n_tracks / timed,
-                (double)n_new / timed, timed);
+                (double)n_new / timed, timed, s_initialize / timed * 1e6, s_track / timed * 1e6, s_compute / timed * 1e6,
+                s_assemble / timed * 1e6);
     vslam_host_free(frames);
   } catch (const std::exception& e) {
     std::fprintf(stderr, "FAILED: %s\n", e.what());

@@ -81,6 +81,11 @@ struct vslam_fpg {
   // state of the last single-pair initialize / last batch
   bool initialized = false;
   int last_pairs = 0;
+  // features of the single-pair initialize(), downloaded behind its back on lane 1's stream (prefetch_features):
+  // per side [cap] u32 xy | [cap] u8 FAST response | [cap][32] descriptor, pinned
+  uint8_t* h_feat = nullptr;
+  cudaEvent_t feat_ev = nullptr;
+  bool feat_valid = false;
   int localizing = 1;
   double matching_distance = 0;
   int64_t launches = 0;
@@ -303,8 +308,42 @@ void reference_order(const vslam_fpg* h, const std::vector<uint32_t>& xy, std::v
       }
 }
 
+size_t feat_side_bytes(const vslam_fpg* h) { return (size_t)h->g.cap * (sizeof(uint32_t) + 1 + kDescBytes); }
+const uint32_t* feat_xy(const vslam_fpg* h, int side) { return reinterpret_cast<const uint32_t*>(h->h_feat + side * feat_side_bytes(h)); }
+const uint8_t* feat_score(const vslam_fpg* h, int side) { return h->h_feat + side * feat_side_bytes(h) + (size_t)h->g.cap * sizeof(uint32_t); }
+const uint8_t* feat_desc(const vslam_fpg* h, int side) { return feat_score(h, side) + h->g.cap; }
+
+// Every host of the single-pair path asks for the features right after initialize() (frame->keypointsLeft/Right(),
+// descriptorsLeft/Right(): reference frame.h:64-67).  Their download -- positions, FAST responses (computed lazily by
+// score_kernel), descriptors, both sides -- is therefore started at the end of initialize() on lane 1's stream, where
+// it neither delays the kernels of track() / compute() on lane 0 nor costs the caller a round trip per array and side.
+int prefetch_features(vslam_fpg* h) {
+  cudaStream_t s = h->lanes[1].stream;
+  for (int side = 0; side < 2; ++side) {
+    const int n = h->h_n_desc[side];
+    if (!n) continue;
+    launch_score(h->g, h->b, side, s);
+    ++h->launches;
+    uint8_t* base = h->h_feat + side * feat_side_bytes(h);
+    CUDA_TRY(cudaMemcpyAsync(base, h->b.kp_xy + (size_t)side * h->g.cap, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(base + (size_t)h->g.cap * sizeof(uint32_t), h->b.kp_score + (size_t)side * h->g.cap, n,
+                             cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(base + (size_t)h->g.cap * (sizeof(uint32_t) + 1), h->b.desc + (size_t)side * h->g.cap * kDescBytes,
+                             (size_t)n * kDescBytes, cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(cudaEventRecord(h->feat_ev, s));
+  CUDA_TRY(cudaGetLastError());
+  h->feat_valid = true;
+  return VSLAM_OK;
+}
+
 int fetch_xy(vslam_fpg* h, int image, int n, std::vector<uint32_t>& xy) {
   xy.resize(n);
+  if (h->feat_valid && image < 2) {
+    CUDA_TRY(cudaEventSynchronize(h->feat_ev));
+    std::memcpy(xy.data(), feat_xy(h, image), sizeof(uint32_t) * n);
+    return VSLAM_OK;
+  }
   if (n) CUDA_TRY(cudaMemcpy(xy.data(), h->b.kp_xy + (size_t)image * h->g.cap, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
   return VSLAM_OK;
 }
@@ -338,7 +377,16 @@ int get_features(vslam_fpg* h, int pair, int side, vslam_keypoint* kps, uint8_t*
   if ((rc = fetch_xy(h, image, n, xy))) return rc;
   std::vector<int> s2r, r2s;
   reference_order(h, xy, s2r, r2s);
-  if (kps) {
+  const bool staged = h->feat_valid && pair == 0;   // fetch_xy has waited for the prefetch
+  if (kps && staged) {
+    const uint8_t* score = feat_score(h, side);
+    for (int k = 0; k < n; ++k) {
+      const int i = r2s[k];
+      kps[k].x = (float)(xy[i] & 0xffff);
+      kps[k].y = (float)(xy[i] >> 16);
+      kps[k].response = (float)score[i];
+    }
+  } else if (kps) {
     std::vector<uint8_t> score(n);
     if (n) {
       launch_score(h->g, h->b, image, h->lanes[0].stream);
@@ -354,7 +402,12 @@ int get_features(vslam_fpg* h, int pair, int side, vslam_keypoint* kps, uint8_t*
       kps[k].response = (float)score[i];
     }
   }
-  if (desc) {
+  if (desc && staged) {
+    const uint8_t* d = feat_desc(h, side);
+    if (h->g.n_regions == 1) std::memcpy(desc, d, (size_t)n * kDescBytes);   // reference order == device order
+    else
+      for (int k = 0; k < n; ++k) std::memcpy(desc + (size_t)k * kDescBytes, d + (size_t)r2s[k] * kDescBytes, kDescBytes);
+  } else if (desc) {
     std::vector<uint8_t> d((size_t)n * kDescBytes);
     if (n) CUDA_TRY(cudaMemcpy(d.data(), h->b.desc + (size_t)image * h->g.cap * kDescBytes, d.size(), cudaMemcpyDeviceToHost));
     for (int k = 0; k < n; ++k) std::memcpy(desc + (size_t)k * kDescBytes, d.data() + (size_t)r2s[k] * kDescBytes, kDescBytes);
@@ -496,6 +549,8 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
   halloc((void**)&h->h_n_desc, I * sizeof(int32_t));
   halloc((void**)&h->h_n_out, B * 2 * sizeof(int32_t));
   halloc((void**)&h->h_flag, sizeof(int32_t));
+  halloc((void**)&h->h_feat, 2 * feat_side_bytes(h));
+  if (ok && cudaEventCreateWithFlags(&h->feat_ev, cudaEventDisableTiming) != cudaSuccess) ok = false;
   halloc((void**)&h->h_systems, B * 32 * sizeof(double));
   halloc((void**)&h->h_track_stats, 4 * sizeof(int32_t));
   for (auto& e : h->clock.ev)
@@ -535,6 +590,8 @@ int vslam_fpg_destroy(vslam_fpg* h) {
   cudaFree(h->d_recover_xy); cudaFree(h->d_recover_desc); cudaFree(h->d_recovered); cudaFree(h->d_recover_n);
   cudaFree(h->d_brief_tests);
   cudaFreeHost(h->h_track_stats); cudaFreeHost(h->h_tracks); cudaFreeHost(h->h_lost);
+  cudaFreeHost(h->h_feat);
+  if (h->feat_ev) cudaEventDestroy(h->feat_ev);
   cudaFreeHost(h->h_counts); cudaFreeHost(h->h_n_desc); cudaFreeHost(h->h_n_out); cudaFreeHost(h->h_flag);
   cudaFreeHost(h->h_systems);
   for (auto& e : h->clock.ev)
@@ -583,6 +640,7 @@ int vslam_fpg_initialize(vslam_fpg* h, const uint8_t* left, const uint8_t* right
   CUDA_TRY(cudaSetDevice(h->device));
   Lane& lane = h->lanes[0];
   const Geometry& g = h->g;
+  h->feat_valid = false;
   int rc = upload_images(h, lane, 0, 1, left, right, stride, stride * g.rows);
   if (rc) return rc;
   run_detect_describe(h, lane, 0, 1);
@@ -613,7 +671,7 @@ int vslam_fpg_initialize(vslam_fpg* h, const uint8_t* left, const uint8_t* right
   h->n_device_tracks = -1;
   if (n_left) *n_left = h->h_n_desc[0];
   if (n_right) *n_right = h->h_n_desc[1];
-  return VSLAM_OK;
+  return prefetch_features(h);
 }
 
 int vslam_fpg_get_features(vslam_fpg* h, int side, vslam_keypoint* kps, uint8_t* desc, int32_t capacity, int32_t* n) {
@@ -961,6 +1019,7 @@ int vslam_fpg_batch_run(vslam_fpg* h, int32_t n_pairs, int localizing) {
   rc = batch_pipeline(h, n_pairs, nullptr, nullptr, 0, 0, false, true, nullptr, 0);
   if (rc) return rc;
   h->initialized = true;
+  h->feat_valid = false;
   h->last_pairs = n_pairs;
   return VSLAM_OK;
 }
@@ -1001,6 +1060,7 @@ int vslam_fpg_batch_process(vslam_fpg* h, int32_t n_pairs, const uint8_t* left, 
   rc = batch_pipeline(h, n_pairs, left, right, stride, pair_stride, true, true, out, capacity_per_pair);
   if (rc) return rc;
   h->initialized = true;
+  h->feat_valid = false;
   h->last_pairs = n_pairs;
   if ((rc = batch_finish(h, n_pairs))) return rc;
   for (int i = 0; i < n_pairs; ++i) {
