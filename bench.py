@@ -80,10 +80,12 @@ def _cpu_pair(i, as_configured=False):
     moving = np.ascontiguousarray(fp["cam"])
     fixed = np.stack([fp["xl"], fp["yl"], fp["xr"], fp["yr"]], 1).astype(np.float64)
     wt = np.minimum(acfg.maximum_reliable_depth_meters / moving[:, 2], 1.0) if len(fp) else np.zeros(0)
+    t0 = time.perf_counter()
     al = tier_a.Aligner("stereouv", moving, fixed, np.ones(len(fp)), wt, cam.K, cam.baseline, cam.rows, cam.cols,
                         acfg.minimum_reliable_depth_meters, acfg.maximum_error_kernel)
     for _ in range(_CPU["rounds"]):
         al.linearize(_CPU["T"], False)
+    _CPU["pose_optimization"] = _CPU.get("pose_optimization", 0.0) + time.perf_counter() - t0   # pose_tracker_3d.h:123-127
     return len(fp)
 
 
@@ -98,16 +100,20 @@ def cpu_baseline(left, right, rounds, sample):
     n = min(sample, len(left))
     _cpu_init(left, right, rounds)
     _cpu_pair(0)                                               # warm-up (imports, first-touch)
+    _CPU["gen"].seconds = {k: 0.0 for k in _CPU["gen"].seconds}
+    _CPU["pose_optimization"] = 0.0
     t0 = time.perf_counter()
     for i in range(n):
         _cpu_pair(i)
     dt = time.perf_counter() - t0
+    stages = {k: v / n * 1e3 for k, v in _CPU["gen"].seconds.items()}      # the reference's chronometer names
+    stages["pose_optimization"] = _CPU["pose_optimization"] / n * 1e3
     n2 = min(12, n)          # the as-configured variant is several times slower: a smaller sample
     t0 = time.perf_counter()
     for i in range(n2):
         _cpu_pair(i, as_configured=True)
     dt2 = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+    return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": "port", "stages_ms_per_frame": stages,
             "as_configured": {"value": n2 / dt2, "unit": "frames/s", "sample": "%d pairs" % n2,
                               "what": "the same plus the FLANN knnMatch(k=2) + findHomography(RANSAC) block that "
                                       "use_matches: true (struct default) executes and never reads "

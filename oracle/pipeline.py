@@ -8,6 +8,8 @@ BaseFramePointGenerator::{configure, detectKeypoints, computeDescriptors, adjust
 """
 from __future__ import annotations
 
+import time
+
 import numpy as np
 
 from . import tier_a
@@ -22,6 +24,9 @@ def _cv2():
 class StereoFramePointGeneratorOracle:
     def __init__(self, cfg, cam, tier: str = "a"):
         self.cfg, self.cam, self.tier = cfg, cam, tier
+        # accumulated wall time per stage, named like the reference's chronometers (base_framepoint_generator.h:232-233,
+        # stereo_framepoint_generator.h:81)
+        self.seconds = {"keypoint_detection": 0.0, "descriptor_extraction": 0.0, "point_triangulation": 0.0}
         self.configure()
 
     # base_framepoint_generator.cpp:165-329 + stereo_framepoint_generator.cpp:16-60
@@ -87,13 +92,18 @@ class StereoFramePointGeneratorOracle:
     def initialize(self, left, right, localizing: bool):
         c = self.cfg
         self.thresholds_used = self.thresholds.copy()
+        t0 = time.perf_counter()             # CHRONOMETER keypoint_detection (base_framepoint_generator.h:232-233)
         kl, cl = self._detect(left)
         kr, cr = self._detect(right)
         self.thresholds = tier_a.adjust_thresholds(                                          # :94
             self.thresholds, cl, cr, self.target_per_detector, c.target_number_of_keypoints_tolerance,
             c.detector_threshold_maximum_change, c.detector_threshold_minimum, c.detector_threshold_maximum)
+        t1 = time.perf_counter()             # CHRONOMETER descriptor_extraction
         self.kps_left, self.desc_left = self._describe(left, kl)                             # :97-100
         self.kps_right, self.desc_right = self._describe(right, kr)
+        t2 = time.perf_counter()
+        self.seconds["keypoint_detection"] += t1 - t0
+        self.seconds["descriptor_extraction"] += t2 - t1
         self.counts_left, self.counts_right = cl, cr
         self.number_of_detected_keypoints = len(self.kps_left)                               # :101
         self.max_distance = tier_a.triangulation_threshold(                                  # :109-125
@@ -146,9 +156,11 @@ class StereoFramePointGeneratorOracle:
     # ---- stereo_framepoint_generator.cpp:135-462 -----------------------------------------------
     def compute(self, tracked=None):
         c = self.cfg
+        t0 = time.perf_counter()             # CHRONOMETER point_triangulation (stereo_framepoint_generator.h:81)
         r = tier_a.stereo_compute(self.features_left, self.features_right, self.stereo_camera, self.max_distance,
                                   c.minimum_disparity_pixels, c.maximum_epipolar_search_offset_pixels,
                                   c.enable_keypoint_binning, c.bin_size_pixels, self.rows, self.cols, tracked)
+        self.seconds["point_triangulation"] += time.perf_counter() - t0
         self.matches, self.winners = r["matches"], r["winners"]
         return r
 
