@@ -77,6 +77,7 @@ struct vslam_fpg {
   int32_t* h_counts = nullptr;   // [2*max_batch][n_regions]
   int32_t* h_n_desc = nullptr;   // [2*max_batch]
   int32_t* h_n_out = nullptr;    // [max_batch][2]
+  FramePointRecord* h_out_stage = nullptr;   // pinned, [out_cap]: the records of the single-pair compute(), copied with the counts
   int32_t* h_flag = nullptr;
   // state of the last single-pair initialize / last batch
   bool initialized = false;
@@ -548,6 +549,7 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
   halloc((void**)&h->h_counts, I * g.n_regions * sizeof(int32_t));
   halloc((void**)&h->h_n_desc, I * sizeof(int32_t));
   halloc((void**)&h->h_n_out, B * 2 * sizeof(int32_t));
+  halloc((void**)&h->h_out_stage, (size_t)h->out_cap * sizeof(FramePointRecord));
   halloc((void**)&h->h_flag, sizeof(int32_t));
   halloc((void**)&h->h_feat, 2 * feat_side_bytes(h));
   if (ok && cudaEventCreateWithFlags(&h->feat_ev, cudaEventDisableTiming) != cudaSuccess) ok = false;
@@ -591,6 +593,7 @@ int vslam_fpg_destroy(vslam_fpg* h) {
   cudaFree(h->d_brief_tests);
   cudaFreeHost(h->h_track_stats); cudaFreeHost(h->h_tracks); cudaFreeHost(h->h_lost);
   cudaFreeHost(h->h_feat);
+  cudaFreeHost(h->h_out_stage);
   if (h->feat_ev) cudaEventDestroy(h->feat_ev);
   cudaFreeHost(h->h_counts); cudaFreeHost(h->h_n_desc); cudaFreeHost(h->h_n_out); cudaFreeHost(h->h_flag);
   cudaFreeHost(h->h_systems);
@@ -739,6 +742,10 @@ int vslam_fpg_compute(vslam_fpg* h, const vslam_tracked_point* tracked, int32_t 
     CUDA_TRY(cudaMemcpyAsync(h->h_n_out, h->b.n_out, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, lane.stream));
   }
   CUDA_TRY(cudaMemcpyAsync(h->h_flag, h->b.error_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, lane.stream));
+  // the records travel with the counts (one round trip instead of two): the whole bin-sized buffer when it is small
+  const bool staged_records = h->g.enable_binning && (size_t)h->out_cap * sizeof(FramePointRecord) <= (256u << 10);
+  if (staged_records)
+    CUDA_TRY(cudaMemcpyAsync(h->h_out_stage, src, sizeof(FramePointRecord) * (size_t)h->out_cap, cudaMemcpyDeviceToHost, lane.stream));
   CUDA_TRY(cudaStreamSynchronize(lane.stream));
   CUDA_TRY(cudaGetLastError());
   collect_clock(h, false, true);
@@ -752,7 +759,8 @@ int vslam_fpg_compute(vslam_fpg* h, const vslam_tracked_point* tracked, int32_t 
   if (n_matches) *n_matches = h->h_n_out[1];
   if (n > capacity) return fail(VSLAM_ERR_CAPACITY, "capacity %d < %d framepoints", capacity, n);
   if (n && !out) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null output");
-  if (n) CUDA_TRY(cudaMemcpy(out, src, sizeof(FramePointRecord) * n, cudaMemcpyDeviceToHost));
+  if (n && staged_records) std::memcpy(out, h->h_out_stage, sizeof(FramePointRecord) * n);
+  else if (n) CUDA_TRY(cudaMemcpy(out, src, sizeof(FramePointRecord) * n, cudaMemcpyDeviceToHost));
   return remap_records(h, 0, out, n);
 }
 
