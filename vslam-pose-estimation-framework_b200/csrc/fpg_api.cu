@@ -235,9 +235,11 @@ int join_lanes(vslam_fpg* h) {
 int upload_images(vslam_fpg* h, Lane& lane, int p0, int n, const uint8_t* left, const uint8_t* right, size_t stride,
                   size_t pair_stride) {
   const Geometry& g = h->g;
-  if (n > 1 && pair_stride == stride * (size_t)g.rows) {
+  if (pair_stride == stride * (size_t)g.rows && (n > 1 || stride <= (size_t)g.cols + (size_t)g.cols / 4)) {
     // Images are contiguous on the host: ONE linear copy per side at full PCIe rate (strided 2-D/3-D copies of
-    // 1241-byte rows run several times slower), then a device kernel re-pitches rows to the 128 B aligned layout.
+    // 1241-byte rows run several times slower: 47 us instead of ~15 us for one KITTI image), then a device kernel
+    // re-pitches rows to the 128 B aligned layout.  A single frame takes this path too unless its rows are so widely
+    // strided (a view into a much larger image) that the linear copy would move mostly padding.
     const size_t bytes = (size_t)n * pair_stride;
     if (lane.stage_bytes < bytes) {
       CUDA_TRY(cudaStreamSynchronize(lane.stream));
