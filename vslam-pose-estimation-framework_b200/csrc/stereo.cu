@@ -309,29 +309,34 @@ __global__ void __launch_bounds__(kSelectWarps * 32) select_strips_kernel(
   for (int i = tid; i < n_bins; i += kSelectWarps * 32) s_win[i] = INT32_MIN;
   if (tid == 0) s_matches = 0;
   __syncthreads();
-  // :147-155 pre-load, in order (a later tracked point overwrites an earlier one in the same bin)
-  if (warp == 0) {
-    for (int k0 = 0; k0 < n_tracked; k0 += 32) {
-      const int k = k0 + lane;
-      int bin = -1;
-      float disp = 0, dist = 0;
-      if (k < n_tracked) {
-        const TrackedPoint t = tracked[k];
-        const int trb = bin_of(t.row, bs), tcb = bin_of(t.col, bs);
-        if (trb < g.rows_bin && tcb < g.cols_bin) bin = trb * g.cols_bin + tcb;   // (the reference would write out of bounds)
-        disp = (float)t.disparity;
-        dist = t.has_previous ? -1.0f : (float)t.distance;
-      }
-      for (int l = 0; l < 32 && k0 + l < n_tracked; ++l) {
-        const int b = __shfl_sync(0xffffffffu, bin, l);
-        const float dp = __shfl_sync(0xffffffffu, disp, l), dt = __shfl_sync(0xffffffffu, dist, l);
-        if (lane == 0 && b >= 0) {
-          s_win[b] = -(k0 + l + 1);
-          s_disp[b] = dp;
-          s_dist[b] = dt;
-        }
+  // :147-155 pre-load, in order: a later tracked point overwrites an earlier one in the same bin, i.e. the LAST point
+  // of a bin wins.  Two parallel passes: atomicMax of the point index per bin (indices are stored as -(k+1) < 0, so the
+  // last point is the MINIMUM of the stored values; INT32_MIN = empty is kept apart by the first pass writing through
+  // a separate slot), then the winner of each bin writes its disparity / distance.
+  for (int k = tid; k < n_tracked; k += kSelectWarps * 32) {
+    const TrackedPoint t = tracked[k];
+    const int trb = bin_of(t.row, bs), tcb = bin_of(t.col, bs);
+    if (trb < g.rows_bin && tcb < g.cols_bin)   // (the reference would write out of bounds)
+      atomicMax(reinterpret_cast<unsigned int*>(&s_win[trb * g.cols_bin + tcb]), (unsigned int)(k + 1) | 0x80000000u);
+  }
+  __syncthreads();
+  // s_win now holds 0x80000000 | (k_last + 1) for pre-loaded bins (as unsigned: larger k wins) and INT32_MIN =
+  // 0x80000000 for empty ones: decode to -(k_last + 1)
+  for (int k = tid; k < n_tracked; k += kSelectWarps * 32) {
+    const TrackedPoint t = tracked[k];
+    const int trb = bin_of(t.row, bs), tcb = bin_of(t.col, bs);
+    if (trb < g.rows_bin && tcb < g.cols_bin) {
+      const int b = trb * g.cols_bin + tcb;
+      if (((unsigned int)s_win[b] & 0x7fffffffu) == (unsigned int)(k + 1)) {
+        s_disp[b] = (float)t.disparity;
+        s_dist[b] = t.has_previous ? -1.0f : (float)t.distance;
       }
     }
+  }
+  __syncthreads();
+  for (int i = tid; i < n_bins; i += kSelectWarps * 32) {
+    const unsigned int v = (unsigned int)s_win[i];
+    if (v != 0x80000000u) s_win[i] = -(int)(v & 0x7fffffffu);
   }
   __syncthreads();
 
@@ -348,38 +353,53 @@ __global__ void __launch_bounds__(kSelectWarps * 32) select_strips_kernel(
       float* wdisp = s_disp + rb * g.cols_bin;
       float* wdist = s_dist + rb * g.cols_bin;
       for (int pass = 0; pass < n_passes; ++pass) {
-        for (int f0 = f_lo; f0 < f_hi; f0 += 32) {
-          const int i = f0 + lane;
-          int cb = 0;
-          float disp = 0, dist = 0;
-          bool cand = false;
-          if (i < f_hi) {
-            const int2 mm = m[i];
-            if (mm.x >= 0 && (mm.y >> 16) == pass) {
-              cand = true;
-              const int col = (int)(xyl[i] & 0xffffu);
-              cb = bin_of(col, bs);
-              disp = (float)(col - (int)(xyr[mm.x] & 0xffffu));   // frame_point.cpp:19
-              dist = (float)(mm.y & 0xffff);
+        // four chunks of 32 features per trip: their (independent) loads are issued together, so a strip pays the
+        // global-memory latency of m -> xy_right once per 128 features instead of once per 32
+        for (int F0 = f_lo; F0 < f_hi; F0 += 128) {
+          int2 mm[4];
+          uint32_t ql[4], qr[4];
+          bool cand4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = F0 + 32 * u + lane;
+            mm[u] = make_int2(-1, 0);
+            ql[u] = 0;
+            if (i < f_hi) {
+              mm[u] = m[i];
+              ql[u] = xyl[i];
             }
           }
-          unsigned todo = __ballot_sync(0xffffffffu, cand);
-          if (pass == 0) my_matches += __popc(todo);
-          while (todo) {                       // replay in emission order (ascending i)
-            const int l = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int b = __shfl_sync(0xffffffffu, cb, l);
-            const float dp = __shfl_sync(0xffffffffu, disp, l), dt = __shfl_sync(0xffffffffu, dist, l);
-            if (lane == (b & 31)) {            // the owner of bin column b
-              const int cur = win[b];
-              if (cur == INT32_MIN || (dp > wdisp[b] && dt <= wdist[b])) {   // :390-393 / :378-389
-                win[b] = f0 + l;
-                wdisp[b] = dp;
-                wdist[b] = dt;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            cand4[u] = mm[u].x >= 0 && (mm[u].y >> 16) == pass;
+            qr[u] = cand4[u] ? xyr[mm[u].x] : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int f0 = F0 + 32 * u;
+            const bool cand = cand4[u];          // (all false for chunks past the strip: the replay below is skipped)
+            const int col = (int)(ql[u] & 0xffffu);
+            const int cb = bin_of(col, bs);
+            const float disp = (float)(col - (int)(qr[u] & 0xffffu));   // frame_point.cpp:19
+            const float dist = (float)(mm[u].y & 0xffff);
+            unsigned todo = __ballot_sync(0xffffffffu, cand);
+            if (pass == 0) my_matches += __popc(todo);
+            while (todo) {                       // replay in emission order (ascending i)
+              const int l = __ffs(todo) - 1;
+              todo &= todo - 1;
+              const int b = __shfl_sync(0xffffffffu, cb, l);
+              const float dp = __shfl_sync(0xffffffffu, disp, l), dt = __shfl_sync(0xffffffffu, dist, l);
+              if (lane == (b & 31)) {            // the owner of bin column b
+                const int cur = win[b];
+                if (cur == INT32_MIN || (dp > wdisp[b] && dt <= wdist[b])) {   // :390-393 / :378-389
+                  win[b] = f0 + l;
+                  wdisp[b] = dp;
+                  wdist[b] = dt;
+                }
               }
             }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
       // :443 only points without previous() are appended; tracked survivors without previous() are reported
@@ -419,28 +439,45 @@ __global__ void __launch_bounds__(kSelectWarps * 32) select_strips_kernel(
     }
   }
   __syncthreads();
-  // :435-455 gather the winners row-major over the bin grid
+  // :435-455 gather the winners row-major over the bin grid; four chunks of 32 bins per trip so that the dependent
+  // loads of their winners (match -> xy_right) overlap
   for (int rb = warp; rb < g.rows_bin; rb += kSelectWarps) {
     int pos = s_cnt[rb];
     const int* win = s_win + rb * g.cols_bin;
-    for (int c0 = 0; c0 < g.cols_bin; c0 += 32) {
-      const int c = c0 + lane;
-      const int w = c < g.cols_bin ? win[c] : INT32_MIN;
-      const bool on = w != INT32_MIN;
-      const unsigned bal = __ballot_sync(0xffffffffu, on);
-      const int p = pos + __popc(bal & ((1u << lane) - 1u));
-      if (on && p < out_cap) {
-        if (w >= 0) {
-          const int2 mm = m[w];
-          write_record(sp, &o[p], w, mm.x, mm.y & 0xffff, pass_to_offset(mm.y >> 16), xyl[w], xyr[mm.x]);
-        } else {
-          FramePointRecord r = {};
-          r.index_left = w;
-          r.index_right = -1;
-          o[p] = r;
+    for (int C0 = 0; C0 < g.cols_bin; C0 += 128) {
+      int w4[4], p4[4];
+      int2 mm[4];
+      uint32_t ql[4], qr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = C0 + 32 * u + lane;
+        w4[u] = c < g.cols_bin ? win[c] : INT32_MIN;
+        const unsigned bal = __ballot_sync(0xffffffffu, w4[u] != INT32_MIN);
+        p4[u] = pos + __popc(bal & ((1u << lane) - 1u));
+        pos += __popc(bal);
+        mm[u] = make_int2(0, 0);
+        ql[u] = 0;
+        if (w4[u] >= 0) {
+          mm[u] = m[w4[u]];
+          ql[u] = xyl[w4[u]];
         }
       }
-      pos += __popc(bal);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) qr[u] = w4[u] >= 0 ? xyr[mm[u].x] : 0u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int w = w4[u], p = p4[u];
+        if (w != INT32_MIN && p < out_cap) {
+          if (w >= 0) {
+            write_record(sp, &o[p], w, mm[u].x, mm[u].y & 0xffff, pass_to_offset(mm[u].y >> 16), ql[u], qr[u]);
+          } else {
+            FramePointRecord r = {};
+            r.index_left = w;
+            r.index_right = -1;
+            o[p] = r;
+          }
+        }
+      }
     }
   }
 }
