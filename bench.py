@@ -405,7 +405,10 @@ def native_sequence(cfg, cam, frames, warmup=4):
     import tempfile
     try:
         if "exe" not in _RUNNER:
+            import atexit
+            import shutil
             d = tempfile.mkdtemp(prefix="vslam_runner_")
+            atexit.register(shutil.rmtree, d, True)
             exe = os.path.join(d, "sequence_runner")
             pkg = os.path.join(ROOT, "vslam-pose-estimation-framework_b200")
             subprocess.check_call(["g++", "-std=c++14", "-O2", "-I", os.path.join(ROOT, "include"),
