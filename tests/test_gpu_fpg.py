@@ -295,7 +295,7 @@ def test_chronometers_and_kernel_profile():
     assert t["keypoint_detection"] > 0 and t["descriptor_extraction"] > 0 and t["point_triangulation"] > 0
     prof = gen.kernel_profile()
     assert all(prof[k][1] == 1 for k in ("fast_nms", "compact", "blur", "describe", "match", "select"))
-    assert gen.launch_count == 9      # + repitch, + the two score kernels of the feature prefetch of initialize()
+    assert gen.launch_count == 8      # + repitch, + the pack kernel of the feature prefetch that initialize() starts
     gen.close()
 
 

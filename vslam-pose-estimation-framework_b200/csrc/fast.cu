@@ -540,6 +540,35 @@ __global__ void __launch_bounds__(256) score_kernel(Geometry g, const uint8_t* _
   }
 }
 
+// The features of one stereo pair packed for ONE device-to-host copy (the prefetch that vslam_fpg_initialize starts):
+// per side s, at byte offset feature_pack_offset(s): [n] u32 positions | [n] u8 FAST responses, padded to 16 | [n][32]
+// descriptors, n = n_desc[s].  gridDim.y = side.
+__global__ void __launch_bounds__(256) pack_features_kernel(Geometry g, const uint8_t* __restrict__ image,
+                                                            const uint32_t* __restrict__ kp_xy,
+                                                            const uint8_t* __restrict__ desc,
+                                                            const int32_t* __restrict__ n_desc, uint8_t* __restrict__ out) {
+  const int side = blockIdx.y;
+  const int n = n_desc[side];
+  const size_t base = side == 0 ? 0 : feature_pack_bytes(n_desc[0]);
+  uint32_t* o_xy = reinterpret_cast<uint32_t*>(out + base);
+  uint8_t* o_score = out + base + sizeof(uint32_t) * (size_t)n;
+  uint4* o_desc = reinterpret_cast<uint4*>(out + base + feature_pack_desc_offset(n));
+  const uint8_t* img = image + (size_t)side * g.rows * g.pitch;
+  const uint32_t* xy = kp_xy + (size_t)side * g.cap;
+  const uint4* d = reinterpret_cast<const uint4*>(desc + (size_t)side * g.cap * kDescBytes);
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const uint32_t q = xy[i];
+    o_xy[i] = q;
+    o_score[i] = (uint8_t)fast_score_at(img + (size_t)(q >> 16) * g.pitch + (q & 0xffffu), g.pitch, 0);
+    o_desc[2 * i] = d[2 * i];
+    o_desc[2 * i + 1] = d[2 * i + 1];
+  }
+}
+
+void launch_pack_features(const Geometry& g, const Buffers& b, uint8_t* out, cudaStream_t stream) {
+  pack_features_kernel<<<dim3(32, 2), 256, 0, stream>>>(g, b.image, b.kp_xy, b.desc, b.n_desc, out);
+}
+
 void launch_score(const Geometry& g, const Buffers& b, int image, cudaStream_t stream) {
   score_kernel<<<32, 256, 0, stream>>>(g, b.image + (size_t)image * g.rows * g.pitch, b.kp_xy + (size_t)image * g.cap,
                                        b.n_desc + image, b.kp_score + (size_t)image * g.cap);

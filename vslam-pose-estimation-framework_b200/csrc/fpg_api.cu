@@ -83,8 +83,9 @@ struct vslam_fpg {
   bool initialized = false;
   int last_pairs = 0;
   // features of the single-pair initialize(), downloaded behind its back on lane 1's stream (prefetch_features):
-  // per side [cap] u32 xy | [cap] u8 FAST response | [cap][32] descriptor, pinned
+  // packed by pack_features_kernel (layout: feature_pack_bytes in kernels.cuh), device buffer + pinned host copy
   uint8_t* h_feat = nullptr;
+  uint8_t* d_feat = nullptr;
   cudaEvent_t feat_ev = nullptr;
   bool feat_valid = false;
   int localizing = 1;
@@ -311,28 +312,24 @@ void reference_order(const vslam_fpg* h, const std::vector<uint32_t>& xy, std::v
       }
 }
 
-size_t feat_side_bytes(const vslam_fpg* h) { return (size_t)h->g.cap * (sizeof(uint32_t) + 1 + kDescBytes); }
-const uint32_t* feat_xy(const vslam_fpg* h, int side) { return reinterpret_cast<const uint32_t*>(h->h_feat + side * feat_side_bytes(h)); }
-const uint8_t* feat_score(const vslam_fpg* h, int side) { return h->h_feat + side * feat_side_bytes(h) + (size_t)h->g.cap * sizeof(uint32_t); }
-const uint8_t* feat_desc(const vslam_fpg* h, int side) { return feat_score(h, side) + h->g.cap; }
+size_t feat_capacity_bytes(const vslam_fpg* h) { return 2 * feature_pack_bytes(h->g.cap); }
+const uint8_t* feat_side(const vslam_fpg* h, int side) { return h->h_feat + (side ? feature_pack_bytes(h->h_n_desc[0]) : 0); }
+const uint32_t* feat_xy(const vslam_fpg* h, int side) { return reinterpret_cast<const uint32_t*>(feat_side(h, side)); }
+const uint8_t* feat_score(const vslam_fpg* h, int side) { return feat_side(h, side) + sizeof(uint32_t) * (size_t)h->h_n_desc[side]; }
+const uint8_t* feat_desc(const vslam_fpg* h, int side) { return feat_side(h, side) + feature_pack_desc_offset(h->h_n_desc[side]); }
 
 // Every host of the single-pair path asks for the features right after initialize() (frame->keypointsLeft/Right(),
-// descriptorsLeft/Right(): reference frame.h:64-67).  Their download -- positions, FAST responses (computed lazily by
-// score_kernel), descriptors, both sides -- is therefore started at the end of initialize() on lane 1's stream, where
-// it neither delays the kernels of track() / compute() on lane 0 nor costs the caller a round trip per array and side.
+// descriptorsLeft/Right(): reference frame.h:64-67).  Their download -- positions, FAST responses (computed here, not
+// on the path), descriptors, both sides -- is therefore started at the end of initialize() on lane 1's stream, where it
+// neither delays the kernels of track() / compute() on lane 0 nor costs the caller a round trip per array and side:
+// ONE kernel packs everything (pack_features_kernel), ONE copy brings it to pinned host memory.
 int prefetch_features(vslam_fpg* h) {
   cudaStream_t s = h->lanes[1].stream;
-  for (int side = 0; side < 2; ++side) {
-    const int n = h->h_n_desc[side];
-    if (!n) continue;
-    launch_score(h->g, h->b, side, s);
+  const size_t bytes = feature_pack_bytes(h->h_n_desc[0]) + feature_pack_bytes(h->h_n_desc[1]);
+  if (bytes) {
+    launch_pack_features(h->g, h->b, h->d_feat, s);
     ++h->launches;
-    uint8_t* base = h->h_feat + side * feat_side_bytes(h);
-    CUDA_TRY(cudaMemcpyAsync(base, h->b.kp_xy + (size_t)side * h->g.cap, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(base + (size_t)h->g.cap * sizeof(uint32_t), h->b.kp_score + (size_t)side * h->g.cap, n,
-                             cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(base + (size_t)h->g.cap * (sizeof(uint32_t) + 1), h->b.desc + (size_t)side * h->g.cap * kDescBytes,
-                             (size_t)n * kDescBytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h->h_feat, h->d_feat, bytes, cudaMemcpyDeviceToHost, s));
   }
   CUDA_TRY(cudaEventRecord(h->feat_ev, s));
   CUDA_TRY(cudaGetLastError());
@@ -553,7 +550,8 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
   halloc((void**)&h->h_n_out, B * 2 * sizeof(int32_t));
   halloc((void**)&h->h_out_stage, (size_t)h->out_cap * sizeof(FramePointRecord));
   halloc((void**)&h->h_flag, sizeof(int32_t));
-  halloc((void**)&h->h_feat, 2 * feat_side_bytes(h));
+  halloc((void**)&h->h_feat, feat_capacity_bytes(h));
+  dalloc((void**)&h->d_feat, feat_capacity_bytes(h));
   if (ok && cudaEventCreateWithFlags(&h->feat_ev, cudaEventDisableTiming) != cudaSuccess) ok = false;
   halloc((void**)&h->h_systems, B * 32 * sizeof(double));
   halloc((void**)&h->h_track_stats, 4 * sizeof(int32_t));
@@ -595,6 +593,7 @@ int vslam_fpg_destroy(vslam_fpg* h) {
   cudaFree(h->d_brief_tests);
   cudaFreeHost(h->h_track_stats); cudaFreeHost(h->h_tracks); cudaFreeHost(h->h_lost);
   cudaFreeHost(h->h_feat);
+  cudaFree(h->d_feat);
   cudaFreeHost(h->h_out_stage);
   if (h->feat_ev) cudaEventDestroy(h->feat_ev);
   cudaFreeHost(h->h_counts); cudaFreeHost(h->h_n_desc); cudaFreeHost(h->h_n_out); cudaFreeHost(h->h_flag);

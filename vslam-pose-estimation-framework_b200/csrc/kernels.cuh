@@ -88,6 +88,11 @@ bool make_image_tensor_map(const Geometry& g, const uint8_t* images, int n_image
 void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, const CUtensorMap& image_map, int first_image,
                  int n_images, cudaStream_t stream);
 void launch_compact(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream);
+// layout of the packed features of pair 0 (pack_features_kernel): per side [n] u32 | [n] u8 padded to 16 | [n][32]
+__host__ __device__ inline size_t feature_pack_desc_offset(int n) { return (5 * (size_t)n + 15) / 16 * 16; }
+__host__ __device__ inline size_t feature_pack_bytes(int n) { return feature_pack_desc_offset(n) + 32 * (size_t)n; }
+// positions, FAST responses and descriptors of both sides of pair 0, packed for one device-to-host copy
+void launch_pack_features(const Geometry& g, const Buffers& b, uint8_t* out, cudaStream_t stream);
 // FAST response of the kept keypoints of one image -> kp_score (on demand)
 void launch_score(const Geometry& g, const Buffers& b, int image, cudaStream_t stream);
 // `image_map`: TMA descriptor of b.image (all images of the handle) with the blur tile as box
