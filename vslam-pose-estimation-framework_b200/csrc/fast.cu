@@ -361,12 +361,20 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(const __grid_constant__ C
 // rows above it; batches use one CTA per image, single frames split the image to cut latency.
 __global__ void __launch_bounds__(256) compact_kernel(Geometry g, const uint32_t* __restrict__ mask,
                                                       int32_t* __restrict__ row_ptr, uint32_t* __restrict__ kp_xy,
-                                                      int32_t* __restrict__ n_desc, int32_t* __restrict__ error_flag) {
+                                                      int32_t* __restrict__ n_desc, int32_t* __restrict__ error_flag,
+                                                      uint8_t* __restrict__ pruned_l, uint8_t* __restrict__ consumed_r) {
   extern __shared__ int s_rows[];   // counts of the strip's rows -> exclusive offsets (+1 entry)
   __shared__ int s_warp[8];
   __shared__ int s_base;
   const int img = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  {   // a new frame: no feature is pruned yet (IntensityFeatureMatcher::setFeatures, intensity_feature_matcher.cpp:48-70).
+      // The flags of this image (left: pruned, right: consumed) are cleared here instead of by two memsets per chunk.
+    uint8_t* flags = ((img & 1) ? consumed_r : pruned_l) + (size_t)(img >> 1) * g.cap;
+    const int seg = (g.cap + gridDim.x - 1) / gridDim.x;
+    const int end = min(g.cap, (int)(blockIdx.x + 1) * seg);
+    for (int i = blockIdx.x * seg + tid; i < end; i += 256) flags[i] = 0;
+  }
   const uint32_t* m = mask + (size_t)img * g.rows * g.mask_words;
   const int lo_x = g.border, hi_x = g.cols - g.border;   // keep lo_x <= x < hi_x
   const int lo_y = g.border, hi_y = g.rows - g.border;
@@ -524,7 +532,8 @@ void launch_compact(const Geometry& g, const Buffers& b, int first_image, int n_
   const size_t smem = sizeof(int) * ((g.rows + strips - 1) / strips + 2);
   compact_kernel<<<dim3(strips, n_images), 256, smem, stream>>>(
       g, b.mask + (size_t)first_image * g.rows * g.mask_words, b.row_ptr + (size_t)first_image * (g.rows + 1),
-      b.kp_xy + (size_t)first_image * g.cap, b.n_desc + first_image, b.error_flag);
+      b.kp_xy + (size_t)first_image * g.cap, b.n_desc + first_image, b.error_flag,
+      b.pruned_l + (size_t)(first_image >> 1) * g.cap, b.consumed_r + (size_t)(first_image >> 1) * g.cap);
 }
 
 // cv::KeyPoint::response of the kept keypoints (cornerScore<16>): nothing on the path reads it, so it is produced

@@ -79,6 +79,8 @@ struct vslam_fpg {
   int32_t* h_n_out = nullptr;    // [max_batch][2]
   FramePointRecord* h_out_stage = nullptr;   // pinned, [out_cap]: the records of the single-pair compute(), copied with the counts
   int32_t* h_flag = nullptr;
+  int32_t* d_status = nullptr;   // [error_flag, pad | n_desc 2B | raw_count 2B x regions]; b.error_flag / n_desc / raw_count point into it
+  int32_t* h_status = nullptr;   // pinned mirror; h_flag / h_n_desc / h_counts point into it
   // state of the last single-pair initialize / last batch
   bool initialized = false;
   int last_pairs = 0;
@@ -149,9 +151,7 @@ void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n) {
   b.mask = lane.mask - (size_t)2 * p0 * h->g.rows * h->g.mask_words;
   RegionTable rt;
   refresh_region_table(h, &rt);
-  // a new frame: no feature is pruned yet (IntensityFeatureMatcher::setFeatures, intensity_feature_matcher.cpp:48-70)
-  cudaMemsetAsync(h->b.pruned_l + (size_t)p0 * h->g.cap, 0, (size_t)n * h->g.cap, lane.stream);
-  cudaMemsetAsync(h->b.consumed_r + (size_t)p0 * h->g.cap, 0, (size_t)n * h->g.cap, lane.stream);
+  // (the pruned / consumed flags of the new frame are cleared by compact_kernel)
   mark(h, lane, kEvFast0);
   launch_fast(h->g, rt, b, h->image_map, 2 * p0, 2 * n, lane.stream);
   mark(h, lane, kEvFast1);
@@ -503,17 +503,22 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
     if (ok && cudaMalloc(p, bytes ? bytes : 1) != cudaSuccess) ok = false;
   };
   dalloc((void**)&b.image, I * img_bytes);
-  dalloc((void**)&b.raw_count, I * g.n_regions * sizeof(int32_t));
+  // error flag, descriptor counts and raw keypoint counts share ONE allocation (and one pinned mirror): the single-pair
+  // initialize() of a max_batch == 1 handle reads all three with one copy
+  dalloc((void**)&h->d_status, (2 + I + I * g.n_regions) * sizeof(int32_t));
+  if (ok) {
+    b.error_flag = h->d_status;
+    b.n_desc = h->d_status + 2;
+    b.raw_count = h->d_status + 2 + I;
+  }
   dalloc((void**)&b.row_ptr, I * (g.rows + 1) * sizeof(int32_t));
   dalloc((void**)&b.kp_xy, I * g.cap * sizeof(uint32_t));
   dalloc((void**)&b.kp_score, I * g.cap);
   dalloc((void**)&b.desc, I * g.cap * kDescBytes);
-  dalloc((void**)&b.n_desc, I * sizeof(int32_t));
   dalloc((void**)&b.match, B * g.cap * sizeof(int2));
   dalloc((void**)&b.pruned_l, B * g.cap);
   dalloc((void**)&b.consumed_r, B * g.cap);
   dalloc((void**)&b.n_out, B * 2 * sizeof(int32_t));
-  dalloc((void**)&b.error_flag, sizeof(int32_t));
   dalloc((void**)&h->d_out, B * h->out_cap * sizeof(FramePointRecord));
   dalloc((void**)&h->d_matches, (size_t)g.cap * sizeof(FramePointRecord));
   dalloc((void**)&h->d_n_matches, sizeof(int32_t));
@@ -545,11 +550,14 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
   auto halloc = [&](void** p, size_t bytes) {
     if (ok && cudaMallocHost(p, bytes) != cudaSuccess) ok = false;
   };
-  halloc((void**)&h->h_counts, I * g.n_regions * sizeof(int32_t));
-  halloc((void**)&h->h_n_desc, I * sizeof(int32_t));
+  halloc((void**)&h->h_status, (2 + I + I * g.n_regions) * sizeof(int32_t));
+  if (ok) {
+    h->h_flag = h->h_status;
+    h->h_n_desc = h->h_status + 2;
+    h->h_counts = h->h_status + 2 + I;
+  }
   halloc((void**)&h->h_n_out, B * 2 * sizeof(int32_t));
   halloc((void**)&h->h_out_stage, (size_t)h->out_cap * sizeof(FramePointRecord));
-  halloc((void**)&h->h_flag, sizeof(int32_t));
   halloc((void**)&h->h_feat, feat_capacity_bytes(h));
   dalloc((void**)&h->d_feat, feat_capacity_bytes(h));
   if (ok && cudaEventCreateWithFlags(&h->feat_ev, cudaEventDisableTiming) != cudaSuccess) ok = false;
@@ -577,9 +585,9 @@ int vslam_fpg_destroy(vslam_fpg* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   Buffers& b = h->b;
-  cudaFree(b.image); cudaFree(b.raw_count); cudaFree(b.row_ptr); cudaFree(b.kp_xy); cudaFree(b.kp_score);
-  cudaFree(b.desc); cudaFree(b.n_desc); cudaFree(b.match); cudaFree(b.pruned_l); cudaFree(b.consumed_r); cudaFree(b.n_out);
-  cudaFree(b.error_flag); cudaFree(h->d_out); cudaFree(h->d_matches); cudaFree(h->d_n_matches); cudaFree(h->d_tracked);
+  cudaFree(b.image); cudaFree(h->d_status); cudaFree(b.row_ptr); cudaFree(b.kp_xy); cudaFree(b.kp_score);
+  cudaFree(b.desc); cudaFree(b.match); cudaFree(b.pruned_l); cudaFree(b.consumed_r); cudaFree(b.n_out);
+  cudaFree(h->d_out); cudaFree(h->d_matches); cudaFree(h->d_n_matches); cudaFree(h->d_tracked);
   for (auto& l : h->lanes) {
     cudaFree(l.blurred);
     cudaFree(l.mask);
@@ -596,7 +604,7 @@ int vslam_fpg_destroy(vslam_fpg* h) {
   cudaFree(h->d_feat);
   cudaFreeHost(h->h_out_stage);
   if (h->feat_ev) cudaEventDestroy(h->feat_ev);
-  cudaFreeHost(h->h_counts); cudaFreeHost(h->h_n_desc); cudaFreeHost(h->h_n_out); cudaFreeHost(h->h_flag);
+  cudaFreeHost(h->h_status); cudaFreeHost(h->h_n_out);
   cudaFreeHost(h->h_systems);
   for (auto& e : h->clock.ev)
     if (e) cudaEventDestroy(e);
@@ -648,9 +656,12 @@ int vslam_fpg_initialize(vslam_fpg* h, const uint8_t* left, const uint8_t* right
   int rc = upload_images(h, lane, 0, 1, left, right, stride, stride * g.rows);
   if (rc) return rc;
   run_detect_describe(h, lane, 0, 1);
-  CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->b.raw_count, sizeof(int32_t) * 2 * g.n_regions, cudaMemcpyDeviceToHost, lane.stream));
-  CUDA_TRY(cudaMemcpyAsync(h->h_n_desc, h->b.n_desc, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, lane.stream));
-  CUDA_TRY(cudaMemcpyAsync(h->h_flag, h->b.error_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, lane.stream));
+  if (h->max_batch == 1) {   // the three are contiguous: one copy
+    CUDA_TRY(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int32_t) * (2 + 2 + 2 * g.n_regions), cudaMemcpyDeviceToHost, lane.stream));
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->b.raw_count, sizeof(int32_t) * 2 * g.n_regions, cudaMemcpyDeviceToHost, lane.stream));
+    CUDA_TRY(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, lane.stream));   // flag + n_desc[0..1]
+  }
   CUDA_TRY(cudaStreamSynchronize(lane.stream));
   CUDA_TRY(cudaGetLastError());
   collect_clock(h, true, false);
