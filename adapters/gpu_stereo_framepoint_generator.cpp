@@ -91,6 +91,7 @@ void GpuStereoFramePointGenerator::initialize(Frame* frame_, const bool& extract
   }
   // :129-132 setFeatures(): the lattices live on the device (row-sorted feature arrays + pruned flags); the host
   // matchers of the base classes stay empty
+  refreshChronometers();
 }
 
 void GpuStereoFramePointGenerator::fillPreviousPoint(const FramePoint* point_, vslam_previous_point& out_) {
@@ -237,6 +238,18 @@ void GpuStereoFramePointGenerator::compute(Frame* frame_) {
   // the matched features are gone from the matchers, as after :419-420 (recoverPoints / the next track() rely on it)
   // NOTE: only the features of the SELECTED points are known here; hosts that need the exact post-compute matcher
   // state call vslam_fpg_get_matches() and prune all n_matches pairs.
+  refreshChronometers();
+}
+
+// SLAMAssembly::printReport reads the (non-virtual) getTimeConsumptionSeconds_keypoint_detection / _descriptor_extraction /
+// _point_triangulation of the base classes (slam_assembly.cpp:690-719; CREATE_CHRONOMETER, definitions.h:144-148): their
+// protected counters are kept equal to the device seconds of the corresponding kernels
+void GpuStereoFramePointGenerator::refreshChronometers() {
+  double detection = 0, extraction = 0, triangulation = 0;
+  if (vslam_fpg_get_time_consumption(_handle, &detection, &extraction, &triangulation) != VSLAM_OK) return;
+  _time_consumption_seconds_keypoint_detection = detection;
+  _time_consumption_seconds_descriptor_extraction = extraction;
+  _time_consumption_seconds_point_triangulation = triangulation;
 }
 
 void GpuStereoFramePointGenerator::setBriefTests(const int8_t tests_[1024]) {

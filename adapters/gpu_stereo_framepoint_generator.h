@@ -36,6 +36,7 @@ class GpuStereoFramePointGenerator : public StereoFramePointGenerator {
   double deviceSecondsPointTriangulation() const;
 
  private:
+  void refreshChronometers();
   void check(int status_) const;   // rethrows C-ABI errors as std::runtime_error (caught in executables/app.cpp:128)
 
   StereoFramePointGeneratorParameters* _stereo_parameters = nullptr;
