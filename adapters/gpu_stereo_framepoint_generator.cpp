@@ -90,7 +90,10 @@ void GpuStereoFramePointGenerator::initialize(Frame* frame_, const bool& extract
     _current_maximum_descriptor_distance_triangulation = distance;                                   // :109-125
   }
   // :129-132 setFeatures(): the lattices live on the device (row-sorted feature arrays + pruned flags); the host
-  // matchers of the base classes stay empty
+  // matchers of the base classes stay empty.  Without a new extraction (the tracker's retry, pose_tracker_3d.cpp:320,
+  // 402) setFeatures() makes every feature of the frame available again: the device forgets the pruning of the
+  // abandoned track() attempt.
+  if (!extract_features_) check(vslam_fpg_reset_features(_handle));
   refreshChronometers();
 }
 

@@ -158,6 +158,12 @@ int vslam_fpg_get_detection_stats(vslam_fpg* h, int32_t* counts_left, int32_t* c
  * next compute().  Without this call every feature of initialize() takes part (first frame / Localizing restart). */
 int vslam_fpg_set_remaining_features(vslam_fpg* h, int side, const vslam_keypoint* remaining, int32_t n);
 
+/* StereoFramePointGenerator::initialize(frame, extract_features = false) (stereo_framepoint_generator.cpp:73-84,
+ * 126-133): no new detection; both feature matchers are set up again from the frame's keypoints and descriptors, i.e.
+ * every feature of the last vslam_fpg_initialize is available again and what a track() attempt pruned is forgotten.
+ * PoseTracker3D retries a failed track() this way (pose_tracker_3d.cpp:320, 402). */
+int vslam_fpg_reset_features(vslam_fpg* h);
+
 /* What track() and recoverPoints() read of one FramePoint of the previous frame
  * (stereo_framepoint_generator.cpp:494-606, 702-835; src/types/frame_point.h) */
 typedef struct {

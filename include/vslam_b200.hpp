@@ -65,7 +65,11 @@ class StereoFramePointGenerator {
 
   void initialize(Frame* frame, const bool& extract_features = true) {
     if (!frame) throw std::runtime_error("StereoFramePointGenerator::initialize|called with empty frame");
-    if (!extract_features) return;
+    if (!extract_features) {   // :126-133 only: both matchers are set up again, a track() attempt's pruning is forgotten
+      check(vslam_fpg_reset_features(_handle), "StereoFramePointGenerator::initialize");
+      _tracks_resident = false;
+      return;
+    }
     int32_t nl = 0, nr = 0;
     check(vslam_fpg_initialize(_handle, frame->intensity_image_left, frame->intensity_image_right, frame->image_step,
                                frame->status == Frame::Localizing, &nl, &nr), "StereoFramePointGenerator::initialize");

@@ -224,3 +224,29 @@ def test_recover_points_match_oracle(cfg_name):
     assert len(ora.recover_points(lost, W, 38.4)) > 100
     assert len(gen.recover_points(_as_api(lost[:0]), W, 38.4)) == 0
     gen.close()
+
+
+def test_initialize_without_extraction_forgets_the_abandoned_track():
+    """PoseTracker3D retries a failed track() after initialize(frame, extract_features=false)
+    (pose_tracker_3d.cpp:320, 402; stereo_framepoint_generator.cpp:126-133): both matchers are set up again from the
+    frame's features, so the second track() sees every feature -- its result must equal a track() on a freshly
+    initialized frame, whatever the abandoned attempt pruned; and a compute() after the reset scans all features."""
+    cfg = configs.BY_NAME["kitti"]
+    cam, world, ora, gen, prev = _setup(cfg, seed=11)
+    T_bad = _motion(cam, 3, 0.0, seed=5)            # a poor prior: few tracks, but they prune features
+    T_good = _motion(cam, 1, 0.0, seed=5)
+    first = gen.track(_as_api(prev), T_bad, False, 15, 38.4)
+    gen.reset_features()                             # initialize(current_frame_, false)
+    second = gen.track(_as_api(prev), T_good, True, 50, 38.4)
+    want = ora.track(prev, T_good, True, 50, 38.4)   # the oracle's frame was never tracked with the bad prior
+    assert len(want["tracks"]) > 100 and len(first["tracks"]) != len(second["tracks"])
+    _same_tracks(second, want)
+    ora.compute(ora.tracked_points(want["tracks"]))
+    fps = gen.compute(api.TRACKED_FROM_LAST_TRACK)
+    assert gen.number_of_matches == len(ora.matches)
+    _same_points(fps, ora.framepoints())
+    # after a reset the tracks of the abandoned attempt cannot pre-load compute()
+    gen.reset_features()
+    with pytest.raises(api.VslamError):
+        gen.compute(api.TRACKED_FROM_LAST_TRACK)
+    gen.close()

@@ -923,6 +923,17 @@ int vslam_fpg_set_remaining_features(vslam_fpg* h, int side, const vslam_keypoin
   return VSLAM_OK;
 }
 
+int vslam_fpg_reset_features(vslam_fpg* h) {
+  if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "StereoFramePointGenerator::initialize|called with empty frame");
+  if (!h->initialized || h->last_pairs != 1) return fail(VSLAM_ERR_STATE, "reset_features without initialize");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->lanes[0].stream;
+  CUDA_TRY(cudaMemsetAsync(h->b.pruned_l, 0, h->g.cap, s));
+  CUDA_TRY(cudaMemsetAsync(h->b.consumed_r, 0, h->g.cap, s));
+  h->n_device_tracks = -1;   // the tracks of the abandoned attempt must not pre-load the next compute()
+  return VSLAM_OK;
+}
+
 int vslam_fpg_get_matches(vslam_fpg* h, vslam_framepoint* out, int32_t capacity, int32_t* n_out) {
   if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null handle");
   if (!h->initialized || h->last_pairs != 1) return fail(VSLAM_ERR_STATE, "no single-pair compute to read");
