@@ -153,8 +153,15 @@ void GpuStereoFramePointGenerator::track(Frame* frame_, Frame* frame_previous_,
         cv::Point2f(t.projection_right_corrected[0], t.projection_right_corrected[1]));
     framepoints[i] = framepoint;
   }
-  lost_points_.resize(n_lost);                                                                       // :482, :666
-  for (int32_t i = 0; i < n_lost; ++i) lost_points_[i] = framepoints_previous[_lost_buffer[i]];
+  // :660-663 a point is lost iff it reached the end of the loop body with !point_previous->next().  next() is set by
+  // createFramepoint -- also by an ABANDONED attempt on this frame (the tracker's retry, pose_tracker_3d.cpp:320, 402):
+  // the reference then does not report the point as lost, and neither does this
+  lost_points_.clear();                                                                              // :482, :666
+  lost_points_.reserve(n_lost);
+  for (int32_t i = 0; i < n_lost; ++i) {
+    FramePoint* point_previous = framepoints_previous[_lost_buffer[i]];
+    if (!point_previous->next()) lost_points_.push_back(point_previous);
+  }
   _number_of_tracked_landmarks = n_landmarks;                                                        // :653-655
   frame_previous_->setAverageDescriptorDistanceTracking(average_distance);                           // :667-668
 }
