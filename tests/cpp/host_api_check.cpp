@@ -4,6 +4,7 @@
 // the pytest compares with the CPU oracle.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 
@@ -120,6 +121,38 @@ int main(int argc, char** argv) {
     std::printf("pose");
     for (double v : T) std::printf(" %.17g", v);
     std::printf("\n");
+    // ---- SURVEY 8f row 4 through the same header: the landmark loop of PoseTracker3D::_updatePoints as one call, and
+    // the KITTI / TUM trajectory files of WorldMap (world_map.cpp:183-252)
+    {
+      const std::vector<uint8_t> lm = slurp(dir + "/landmarks.bin");
+      const uint8_t* q = lm.data();
+      int32_t n_landmarks, n_measurements, n_frames;
+      std::memcpy(&n_landmarks, q, 4); std::memcpy(&n_measurements, q + 4, 4); std::memcpy(&n_frames, q + 8, 4);
+      q += 16;
+      std::vector<int32_t> offsets(n_landmarks + 1);
+      std::memcpy(offsets.data(), q, 4 * offsets.size()); q += 4 * offsets.size() + (offsets.size() % 2 ? 4 : 0);
+      std::vector<vslam_landmark_measurement> ms(n_measurements);
+      std::memcpy(ms.data(), q, sizeof(vslam_landmark_measurement) * ms.size()); q += sizeof(vslam_landmark_measurement) * ms.size();
+      std::vector<double> w2c(12 * (size_t)n_frames), c2w(12 * (size_t)n_frames), world(3 * (size_t)n_landmarks);
+      std::memcpy(w2c.data(), q, 8 * w2c.size()); q += 8 * w2c.size();
+      std::memcpy(c2w.data(), q, 8 * c2w.size()); q += 8 * c2w.size();
+      std::memcpy(world.data(), q, 8 * world.size()); q += 8 * world.size();
+      std::vector<uint32_t> updates(n_landmarks);
+      std::memcpy(updates.data(), q, 4 * updates.size());
+      vslam::LandmarkOptimizer optimizer(n_landmarks, n_measurements, n_frames);
+      std::vector<uint8_t> outcome;
+      optimizer.update(offsets, ms, w2c, c2w, world, updates, &outcome);
+      unsigned long long hl = 1469598103934665603ull;
+      for (double v : world) { unsigned long long bits; std::memcpy(&bits, &v, 8); hl = (hl ^ bits) * 1099511628211ull; }
+      for (uint32_t u : updates) hl = (hl ^ u) * 1099511628211ull;
+      for (uint8_t o : outcome) hl = (hl ^ o) * 1099511628211ull;
+      std::printf("landmarks %d hash %llu\n", n_landmarks, hl);
+      std::vector<double> timestamps(n_frames);
+      for (int i = 0; i < n_frames; ++i) timestamps[i] = 1403636579.763555527 + 0.05 * i;
+      vslam::writeTrajectoryKITTI(dir + "/trajectory_kitti.txt", c2w);
+      vslam::writeTrajectoryTUM(dir + "/trajectory_tum.txt", timestamps, c2w);
+      std::printf("trajectories %d\n", n_frames);
+    }
     // error behaviour: exceptions, like the reference
     try {
       generator.initialize(nullptr);

@@ -45,6 +45,18 @@ def test_cpp_frontend_program_matches_oracle(tmp_path):
     c = synth.correspondences(n, "stereouv", cam, seed=99)
     np.concatenate([[float(n)], c["moving"].ravel(), c["fixed"].ravel(), c["omega"], c["wt"]]).tofile(
         tmp_path / "correspondences.f64")
+    hist = synth.landmark_histories(200, n_frames=30, seed=17, outlier_fraction=0.05)
+    with open(tmp_path / "landmarks.bin", "wb") as f:
+        nl, nm, nf = 200, int(hist["offsets"][-1]), 30
+        f.write(np.array([nl, nm, nf, 0], np.int32).tobytes())
+        f.write(hist["offsets"].astype(np.int32).tobytes())
+        if (nl + 1) % 2:
+            f.write(b"\0" * 4)                      # keep the 8-byte fields aligned
+        f.write(hist["measurements"].tobytes())
+        f.write(hist["world_to_camera"].tobytes())
+        f.write(hist["camera_to_world"].tobytes())
+        f.write(hist["world"].tobytes())
+        f.write(hist["number_of_updates"].astype(np.uint32).tobytes())
     out = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     lines = dict(l.split(" ", 1) for l in out.stdout.strip().splitlines())
@@ -100,3 +112,22 @@ def test_cpp_frontend_program_matches_oracle(tmp_path):
     dR = T[:, :3] @ r["T"][:, :3].T
     assert np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1)) <= 1e-6 and np.linalg.norm(T[:, 3] - r["T"][:, 3]) <= 1e-5
     assert "called with empty frame" in lines["exception"]
+
+    # landmark refinement and trajectory files through the C++ classes
+    h = 1469598103934665603
+    world, updates, outcomes = hist["world"].copy(), hist["number_of_updates"].copy(), []
+    for i in range(200):
+        ms = hist["measurements"][hist["offsets"][i]:hist["offsets"][i + 1]]
+        world[i], updates[i], oc, _ = tier_a.landmark_update(ms, hist["world_to_camera"], hist["camera_to_world"],
+                                                             hist["world"][i], hist["number_of_updates"][i])
+        outcomes.append(oc)
+    for bits in world.ravel().view(np.uint64).tolist():
+        h = ((h ^ bits) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    for x in updates.tolist() + outcomes:
+        h = ((h ^ int(x)) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    assert lines["landmarks"] == "200 hash %d" % h
+    assert lines["trajectories"] == "30"
+    ts = 1403636579.763555527 + 0.05 * np.arange(30)
+    assert (tmp_path / "trajectory_kitti.txt").read_text() == "".join(tier_a.format_trajectory(t) for t in hist["camera_to_world"])
+    assert (tmp_path / "trajectory_tum.txt").read_text() == "".join(
+        tier_a.format_trajectory(t, s) for t, s in zip(hist["camera_to_world"], ts))
