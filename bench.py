@@ -332,6 +332,25 @@ def aligner_stress(api, configs, synth, torch, dev):
     return out
 
 
+def landmark_refinement(api, synth, device):
+    """SURVEY 8f row 4: Landmark::update for all tracked landmarks of a frame as one call (host buffers in and out,
+    copies inside the timed region); 40 algorithmic bytes per measurement per Gauss-Newton iteration"""
+    out = []
+    for n, frames in ((1000, 60), (20000, 100)):
+        h = synth.landmark_histories(n, n_frames=frames, seed=5, outlier_fraction=0.05)
+        opt = api.LandmarkOptimizer(n, int(h["offsets"][-1]), frames, device=device)
+        a = (h["offsets"], h["measurements"], h["world_to_camera"], h["camera_to_world"], h["world"], h["number_of_updates"])
+        r = opt.update(*a)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            r = opt.update(*a)
+        ms = (time.perf_counter() - t0) / 10 * 1e3
+        out.append({"landmarks": n, "measurements": int(h["offsets"][-1]), "ms_per_call": ms,
+                    "mean_iterations": float(r[3].mean()), "adopted_fraction": float((r[2] == 1).mean())})
+        opt.close()
+    return out
+
+
 def sequence_latency(api, configs, synth, device):
     """BASELINE.json configs[0]/[1] shape: ONE sequence, frame by frame through the reference-shaped calls
     (initialize -> compute, thresholds fed back between frames, host images in, host framepoints out, one host
@@ -604,6 +623,7 @@ def main():
     if rank == 0:
         line["aligner_stress"] = aligner_stress(api, configs, synth, torch, dev)
         line["sequence"] = sequence_latency(api, configs, synth, local_rank)
+        line["landmark_refinement"] = landmark_refinement(api, synth, local_rank)
     if rank == 0 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(dl, dr, R, args.cpu_sample)
     if rank == 0:
