@@ -1,0 +1,35 @@
+"""The driver-facing contract of bench.py that can be checked without a GPU: `--impl reference` (the reference's CPU
+path on the host cores) prints exactly ONE JSON line on stdout with the keys the driver reads, and ranks other than 0
+of a torchrun launch print nothing."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(env_extra=None):
+    env = dict(os.environ)
+    env.update(env_extra or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                           "--distinct", "4"], capture_output=True, text=True, env=env, timeout=600)
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    r = _run()
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("stereo frames/s") and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["steps"] == 1 and d["warmup"] == 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_other_ranks_of_the_reference_arm_stay_silent():
+    r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
