@@ -164,7 +164,7 @@ def test_binning_disabled_returns_every_match_in_emission_order():
     gen.close()
 
 
-@pytest.mark.parametrize("cfgname,n", [("kitti_fast", 7), ("euroc", 5)])
+@pytest.mark.parametrize("cfgname,n", [("kitti_fast", 7), ("euroc", 5), ("hd", 3)])
 def test_batched_pairs_equal_independent_first_frames(cfgname, n):
     cfg = configs.BY_NAME[cfgname]
     cam = synth.camera(cfg.camera)
@@ -237,11 +237,14 @@ def test_edge_cases_blank_tiny_and_capacity():
     gen.close()
 
 
-def test_row_strided_input_views():
+@pytest.mark.parametrize("extra_columns", [40, 1000])
+def test_row_strided_input_views(extra_columns):
+    """images that are views into wider buffers: a moderate row stride is uploaded by one linear copy + repitch (the
+    padding travels too), a wide one by a strided 2-D copy"""
     cfg, cam = configs.EUROC, synth.camera("euroc")
     left, right = synth.band_world_pair("euroc", 6)
-    big_l = np.zeros((cam.rows, cam.cols + 40), np.uint8)
-    big_r = np.zeros_like(big_l)
+    big_l = np.full((cam.rows, cam.cols + extra_columns), 77, np.uint8)
+    big_r = np.full_like(big_l, 201)
     big_l[:, :cam.cols], big_r[:, :cam.cols] = left, right
     gen = api.StereoFramePointGenerator(cfg, cam)
     gen.initialize(big_l[:, :cam.cols], big_r[:, :cam.cols], True)
