@@ -287,6 +287,32 @@ def test_batched_self_alignment_linearize_matches_oracle():
     gen.close()
 
 
+def test_single_pair_initialize_runs_as_a_cuda_graph():
+    """without profiling the device side of initialize() is one CUDA-graph launch per frame (captured once, re-captured
+    when the row stride changes); with profiling the same kernels are launched one by one -- results are identical"""
+    cfg, cam = configs.KITTI, synth.camera("kitti")
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    ref = api.StereoFramePointGenerator(cfg, cam)
+    ref.set_profiling(True)
+    for k in range(3):
+        left, right = synth.band_world_pair("kitti", 30 + k)
+        assert gen.initialize(left, right, k == 0) == ref.initialize(left, right, k == 0)
+        for side in (0, 1):
+            (ka, da), (kb, db) = gen.features(side), ref.features(side)
+            assert np.array_equal(ka, kb) and np.array_equal(da, db)
+        assert np.array_equal(gen.compute(), ref.compute())
+        assert np.array_equal(gen.thresholds, ref.thresholds)
+    assert gen.graph_launch_count == 3 and ref.graph_launch_count == 0
+    wide_l = np.zeros((cam.rows, cam.cols + 24), np.uint8)                  # another row stride: captured again
+    wide_r = np.zeros_like(wide_l)
+    wide_l[:, :cam.cols], wide_r[:, :cam.cols] = left, right
+    assert gen.initialize(wide_l[:, :cam.cols], wide_r[:, :cam.cols], False) == ref.initialize(left, right, False)
+    assert gen.graph_launch_count == 4 and ref.graph_launch_count == 0
+    assert np.array_equal(gen.features(0)[1], ref.features(0)[1])
+    gen.close()
+    ref.close()
+
+
 def test_chronometers_and_kernel_profile():
     cfg, cam = configs.KITTI, synth.camera("kitti")
     left, right = synth.band_world_pair("kitti", 1)

@@ -45,7 +45,7 @@ TRACKED_FROM_LAST_TRACK = -1
 EXPORTS = """vslam_last_error vslam_version vslam_device_count vslam_host_alloc vslam_host_free
 vslam_fpg_create vslam_fpg_destroy vslam_fpg_info vslam_fpg_get_thresholds vslam_fpg_set_thresholds
 vslam_fpg_initialize vslam_fpg_get_features vslam_fpg_get_detection_stats vslam_fpg_set_remaining_features
-vslam_fpg_reset_features
+vslam_fpg_reset_features vslam_fpg_graph_launch_count
 vslam_fpg_compute vslam_fpg_get_matches vslam_fpg_track vslam_fpg_recover_points
 vslam_fpg_set_profiling vslam_fpg_get_time_consumption vslam_fpg_batch_upload vslam_fpg_batch_run
 vslam_fpg_batch_download vslam_fpg_batch_process vslam_fpg_batch_linearize vslam_fpg_batch_get_systems
@@ -278,6 +278,11 @@ class StereoFramePointGenerator:
         d = C.c_double()
         _check(lib().vslam_fpg_get_detection_stats(self._h, _p(cl), _p(cr), C.byref(d)))
         return cl, cr, d.value
+
+    @property
+    def graph_launch_count(self) -> int:
+        lib().vslam_fpg_graph_launch_count.restype = C.c_int64
+        return int(lib().vslam_fpg_graph_launch_count(self._h))
 
     def reset_features(self):
         """initialize(frame, extract_features=False): every feature of the frame takes part again"""

@@ -172,7 +172,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __global__ void __launch_bounds__(256) fast_nms_kernel(const __grid_constant__ CUtensorMap image_map, Geometry g,
                                                        RegionTable rt, int first_image, uint32_t* __restrict__ mask,
-                                                       int32_t* __restrict__ raw_count, int single_region) {
+                                                       int32_t* __restrict__ raw_count, int single_region,
+                                                       const int32_t* __restrict__ thresholds) {
   __shared__ __align__(128) uint8_t s_img[SH][SW];
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ __align__(16) uint8_t s_score[CH][CPITCH];
@@ -183,7 +184,8 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(const __grid_constant__ C
   const int img = single_region ? blockIdx.z : blockIdx.z / g.n_regions;   // (no integer division on the common path)
   const int reg = blockIdx.z - img * g.n_regions;
   const Region R = rt.r[reg];
-  const int t = rt.threshold[reg];
+  // (a captured CUDA graph re-launches this kernel with the same arguments: its thresholds then live in device memory)
+  const int t = thresholds ? thresholds[reg] : rt.threshold[reg];
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   // keypoint area of this region, inclusive, image coordinates (FAST skips a 3 px border of its view)
   const int ax0 = R.x + 3, ax1 = R.x + R.w - 4, ay0 = R.y + 3, ay1 = R.y + R.h - 4;
@@ -516,7 +518,7 @@ bool make_fast_tensor_map(const Geometry& g, const uint8_t* images, int n_images
 }
 
 void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, const CUtensorMap& image_map, int first_image,
-                 int n_images, cudaStream_t stream) {
+                 int n_images, cudaStream_t stream, const int32_t* device_thresholds) {
   const int single = g.n_regions == 1;
   const size_t mask_bytes = (size_t)g.rows * g.mask_words * sizeof(uint32_t);
   if (!single) cudaMemsetAsync(b.mask + (size_t)first_image * g.rows * g.mask_words, 0, mask_bytes * n_images, stream);
@@ -524,7 +526,7 @@ void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, con
   dim3 grid((g.cols + TW - 1) / TW, (g.rows + TH - 1) / TH, n_images * g.n_regions);
   fast_nms_kernel<<<grid, 256, 0, stream>>>(image_map, g, rt, first_image,
                                             b.mask + (size_t)first_image * g.rows * g.mask_words,
-                                            b.raw_count + (size_t)first_image * g.n_regions, single);
+                                            b.raw_count + (size_t)first_image * g.n_regions, single, device_thresholds);
 }
 
 void launch_compact(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream) {

@@ -86,6 +86,18 @@ struct vslam_fpg {
   int last_pairs = 0;
   // features of the single-pair initialize(), downloaded behind its back on lane 1's stream (prefetch_features):
   // packed by pack_features_kernel (layout: feature_pack_bytes in kernels.cuh), device buffer + pinned host copy
+  // The device side of the single-pair initialize() -- threshold upload, repitch, FAST, compact, blur / box sums,
+  // descriptors, status download: ~10 stream operations of a few microseconds each -- is captured ONCE into a CUDA graph
+  // and re-launched per frame.  Nothing in it changes from frame to frame: the thresholds travel through a pinned
+  // buffer that a copy node of the graph reads, the images are copied into the staging buffer before the launch.
+  cudaGraphExec_t init_graph = nullptr;
+  const uint8_t* init_graph_stage = nullptr;   // the graph is valid for this staging buffer ...
+  size_t init_graph_stride = 0;                // ... and this row stride
+  int init_graph_kernels = 0;
+  int64_t graph_launches = 0;
+  bool init_graph_ok = true;                   // false after a failed capture: the direct launches are used
+  int32_t* h_thr = nullptr;                    // pinned [kMaxRegions]
+  int32_t* d_thr = nullptr;
   uint8_t* h_feat = nullptr;
   uint8_t* d_feat = nullptr;
   cudaEvent_t feat_ev = nullptr;
@@ -144,7 +156,7 @@ inline void mark(vslam_fpg* h, Lane& lane, int ev) {
 }
 
 // kernels of initialize() for images [2*p0, 2*(p0+n)) on one lane
-void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n) {
+void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n, const int32_t* device_thresholds = nullptr) {
   Buffers b = h->b;
   // lane-local scratch is indexed from image 0 of the chunk: shift the base so that image index 2*p0 lands on it
   b.blurred = lane.blurred - (size_t)2 * p0 * h->g.rows * h->g.pitch;
@@ -153,7 +165,7 @@ void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n) {
   refresh_region_table(h, &rt);
   // (the pruned / consumed flags of the new frame are cleared by compact_kernel)
   mark(h, lane, kEvFast0);
-  launch_fast(h->g, rt, b, h->image_map, 2 * p0, 2 * n, lane.stream);
+  launch_fast(h->g, rt, b, h->image_map, 2 * p0, 2 * n, lane.stream, device_thresholds);
   mark(h, lane, kEvFast1);
   launch_compact(h->g, b, 2 * p0, 2 * n, lane.stream);
   mark(h, lane, kEvCompact1);
@@ -233,24 +245,33 @@ int join_lanes(vslam_fpg* h) {
   return VSLAM_OK;
 }
 
+bool linear_upload(const Geometry& g, int n, size_t stride, size_t pair_stride) {
+  return pair_stride == stride * (size_t)g.rows && (n > 1 || stride <= (size_t)g.cols + (size_t)g.cols / 4);
+}
+
+int ensure_stage(vslam_fpg* h, Lane& lane, size_t bytes, size_t pair_stride) {
+  if (lane.stage_bytes >= bytes) return VSLAM_OK;
+  CUDA_TRY(cudaStreamSynchronize(lane.stream));
+  cudaFree(lane.stage);
+  lane.stage = nullptr;
+  lane.stage_bytes = 0;
+  const size_t want = (size_t)h->chunk * pair_stride;
+  CUDA_TRY(cudaMalloc((void**)&lane.stage, 2 * want + 64));
+  lane.stage_bytes = want;
+  return VSLAM_OK;
+}
+
 int upload_images(vslam_fpg* h, Lane& lane, int p0, int n, const uint8_t* left, const uint8_t* right, size_t stride,
                   size_t pair_stride) {
   const Geometry& g = h->g;
-  if (pair_stride == stride * (size_t)g.rows && (n > 1 || stride <= (size_t)g.cols + (size_t)g.cols / 4)) {
+  if (linear_upload(g, n, stride, pair_stride)) {
     // Images are contiguous on the host: ONE linear copy per side at full PCIe rate (strided 2-D/3-D copies of
     // 1241-byte rows run several times slower: 47 us instead of ~15 us for one KITTI image), then a device kernel
     // re-pitches rows to the 128 B aligned layout.  A single frame takes this path too unless its rows are so widely
     // strided (a view into a much larger image) that the linear copy would move mostly padding.
     const size_t bytes = (size_t)n * pair_stride;
-    if (lane.stage_bytes < bytes) {
-      CUDA_TRY(cudaStreamSynchronize(lane.stream));
-      cudaFree(lane.stage);
-      lane.stage = nullptr;
-      lane.stage_bytes = 0;
-      const size_t want = (size_t)h->chunk * pair_stride;
-      CUDA_TRY(cudaMalloc((void**)&lane.stage, 2 * want + 64));
-      lane.stage_bytes = want;
-    }
+    int rc = ensure_stage(h, lane, bytes, pair_stride);
+    if (rc) return rc;
     for (int side = 0; side < 2; ++side) {
       const uint8_t* src = (side == 0 ? left : right) + (size_t)p0 * pair_stride;
       uint8_t* dst = lane.stage + (size_t)side * lane.stage_bytes;
@@ -415,6 +436,18 @@ int get_features(vslam_fpg* h, int pair, int side, vslam_keypoint* kps, uint8_t*
   return VSLAM_OK;
 }
 
+// error flag, descriptor counts and raw counts of pair 0 -> pinned host mirror
+int status_download(vslam_fpg* h, Lane& lane) {
+  const Geometry& g = h->g;
+  if (h->max_batch == 1) {   // the three are contiguous: one copy
+    CUDA_TRY(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int32_t) * (2 + 2 + 2 * g.n_regions), cudaMemcpyDeviceToHost, lane.stream));
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->b.raw_count, sizeof(int32_t) * 2 * g.n_regions, cudaMemcpyDeviceToHost, lane.stream));
+    CUDA_TRY(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, lane.stream));   // flag + n_desc[0..1]
+  }
+  return VSLAM_OK;
+}
+
 double host_matching_distance(const vslam_fpg* h, int localizing, int n_left) {   // :109-125
   if (localizing) return std::min(0.1 * 256, h->cfg.maximum_matching_distance_triangulation);
   const double ratio = std::min(static_cast<double>(n_left) / h->target_keypoints, 1.0);
@@ -558,6 +591,8 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
   }
   halloc((void**)&h->h_n_out, B * 2 * sizeof(int32_t));
   halloc((void**)&h->h_out_stage, (size_t)h->out_cap * sizeof(FramePointRecord));
+  halloc((void**)&h->h_thr, kMaxRegions * sizeof(int32_t));
+  dalloc((void**)&h->d_thr, kMaxRegions * sizeof(int32_t));
   halloc((void**)&h->h_feat, feat_capacity_bytes(h));
   dalloc((void**)&h->d_feat, feat_capacity_bytes(h));
   if (ok && cudaEventCreateWithFlags(&h->feat_ev, cudaEventDisableTiming) != cudaSuccess) ok = false;
@@ -600,6 +635,9 @@ int vslam_fpg_destroy(vslam_fpg* h) {
   cudaFree(h->d_recover_xy); cudaFree(h->d_recover_desc); cudaFree(h->d_recovered); cudaFree(h->d_recover_n);
   cudaFree(h->d_brief_tests);
   cudaFreeHost(h->h_track_stats); cudaFreeHost(h->h_tracks); cudaFreeHost(h->h_lost);
+  if (h->init_graph) cudaGraphExecDestroy(h->init_graph);
+  cudaFreeHost(h->h_thr);
+  cudaFree(h->d_thr);
   cudaFreeHost(h->h_feat);
   cudaFree(h->d_feat);
   cudaFreeHost(h->h_out_stage);
@@ -653,14 +691,57 @@ int vslam_fpg_initialize(vslam_fpg* h, const uint8_t* left, const uint8_t* right
   Lane& lane = h->lanes[0];
   const Geometry& g = h->g;
   h->feat_valid = false;
-  int rc = upload_images(h, lane, 0, 1, left, right, stride, stride * g.rows);
-  if (rc) return rc;
-  run_detect_describe(h, lane, 0, 1);
-  if (h->max_batch == 1) {   // the three are contiguous: one copy
-    CUDA_TRY(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int32_t) * (2 + 2 + 2 * g.n_regions), cudaMemcpyDeviceToHost, lane.stream));
-  } else {
-    CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->b.raw_count, sizeof(int32_t) * 2 * g.n_regions, cudaMemcpyDeviceToHost, lane.stream));
-    CUDA_TRY(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, lane.stream));   // flag + n_desc[0..1]
+  int rc = VSLAM_OK;
+  const size_t image_bytes = stride * (size_t)g.rows;
+  bool launched = false;
+  if (h->init_graph_ok && !h->profiling && linear_upload(g, 1, stride, image_bytes)) {
+    if ((rc = ensure_stage(h, lane, image_bytes, image_bytes))) return rc;
+    if (h->init_graph && (h->init_graph_stage != lane.stage || h->init_graph_stride != stride)) {
+      cudaGraphExecDestroy(h->init_graph);
+      h->init_graph = nullptr;
+    }
+    if (!h->init_graph) {   // capture the device side of this call once
+      const int64_t launches_before = h->launches;
+      cudaGraph_t graph = nullptr;
+      bool ok = cudaStreamBeginCapture(lane.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        cudaMemcpyAsync(h->d_thr, h->h_thr, sizeof(int32_t) * g.n_regions, cudaMemcpyHostToDevice, lane.stream);
+        launch_repitch(g, lane.stage, lane.stage + lane.stage_bytes, (int)stride, h->b.image, 1, lane.stream);
+        ++h->launches;
+        run_detect_describe(h, lane, 0, 1, h->d_thr);
+        status_download(h, lane);
+        ok = cudaStreamEndCapture(lane.stream, &graph) == cudaSuccess && graph != nullptr;
+      }
+      if (ok) ok = cudaGraphInstantiate(&h->init_graph, graph, 0) == cudaSuccess;
+      if (graph) cudaGraphDestroy(graph);
+      h->init_graph_kernels = (int)(h->launches - launches_before);
+      h->launches = launches_before;
+      if (!ok) {            // no graph on this system / for this configuration: the plain launches below do the same work
+        cudaGetLastError();
+        h->init_graph = nullptr;
+        h->init_graph_ok = false;
+      } else {
+        h->init_graph_stage = lane.stage;
+        h->init_graph_stride = stride;
+      }
+    }
+    if (h->init_graph) {
+      for (int i = 0; i < g.n_regions; ++i) {   // FastDetector::setThreshold -> std::rint (:21); cv::FAST clamps
+        const int t = (int)std::rint(h->thresholds[i]);
+        h->h_thr[i] = std::min(std::max(t, 0), 255);
+      }
+      CUDA_TRY(cudaMemcpyAsync(lane.stage, left, image_bytes, cudaMemcpyHostToDevice, lane.stream));
+      CUDA_TRY(cudaMemcpyAsync(lane.stage + lane.stage_bytes, right, image_bytes, cudaMemcpyHostToDevice, lane.stream));
+      CUDA_TRY(cudaGraphLaunch(h->init_graph, lane.stream));
+      h->launches += h->init_graph_kernels;
+      ++h->graph_launches;
+      launched = true;
+    }
+  }
+  if (!launched) {
+    if ((rc = upload_images(h, lane, 0, 1, left, right, stride, image_bytes))) return rc;
+    run_detect_describe(h, lane, 0, 1);
+    if ((rc = status_download(h, lane))) return rc;
   }
   CUDA_TRY(cudaStreamSynchronize(lane.stream));
   CUDA_TRY(cudaGetLastError());
@@ -688,6 +769,8 @@ int vslam_fpg_initialize(vslam_fpg* h, const uint8_t* left, const uint8_t* right
   if (n_right) *n_right = h->h_n_desc[1];
   return prefetch_features(h);
 }
+
+int64_t vslam_fpg_graph_launch_count(const vslam_fpg* h) { return h ? h->graph_launches : 0; }
 
 int vslam_fpg_get_features(vslam_fpg* h, int side, vslam_keypoint* kps, uint8_t* desc, int32_t capacity, int32_t* n) {
   if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null handle");
