@@ -145,8 +145,8 @@ int vslam_fpg_initialize(vslam_fpg* h, const uint8_t* left, const uint8_t* right
 /* frame->keypointsLeft()/descriptorsLeft() (side 0) or ...Right() (side 1) after initialize, in the
  * reference's order (detector region by region, row-major inside a region).  descriptors: n x 32 bytes. */
 /* how many vslam_fpg_initialize calls ran their device side as ONE CUDA-graph launch (threshold upload, repitch, FAST,
- * compact, blur, descriptors, status download captured once per handle; used when profiling is off and the images are
- * uploaded linearly).  Identical kernels and results either way. */
+ * compact, blur, descriptors, status download captured once per handle and profiling mode; used when the images are
+ * uploaded linearly, i.e. unless their rows are very widely strided).  Identical kernels and results either way. */
 int64_t vslam_fpg_graph_launch_count(const vslam_fpg* h);
 
 int vslam_fpg_get_features(vslam_fpg* h, int side, vslam_keypoint* keypoints, uint8_t* descriptors,

@@ -96,6 +96,8 @@ struct vslam_fpg {
   int init_graph_kernels = 0;
   int64_t graph_launches = 0;
   bool init_graph_ok = true;                   // false after a failed capture: the direct launches are used
+  bool init_graph_profiling = false;           // the graph was captured with / without the timing events
+  bool capturing = false;
   int32_t* h_thr = nullptr;                    // pinned [kMaxRegions]
   int32_t* d_thr = nullptr;
   uint8_t* h_feat = nullptr;
@@ -152,7 +154,10 @@ int check_flag(vslam_fpg* h) {
 }
 
 inline void mark(vslam_fpg* h, Lane& lane, int ev) {
-  if (h->profiling) cudaEventRecord(h->clock.ev[ev], lane.stream);
+  if (!h->profiling) return;
+  // inside a stream capture the timing events become external event-record nodes of the graph
+  if (h->capturing) cudaEventRecordWithFlags(h->clock.ev[ev], lane.stream, cudaEventRecordExternal);
+  else cudaEventRecord(h->clock.ev[ev], lane.stream);
 }
 
 // kernels of initialize() for images [2*p0, 2*(p0+n)) on one lane
@@ -694,9 +699,10 @@ int vslam_fpg_initialize(vslam_fpg* h, const uint8_t* left, const uint8_t* right
   int rc = VSLAM_OK;
   const size_t image_bytes = stride * (size_t)g.rows;
   bool launched = false;
-  if (h->init_graph_ok && !h->profiling && linear_upload(g, 1, stride, image_bytes)) {
+  if (h->init_graph_ok && linear_upload(g, 1, stride, image_bytes)) {
     if ((rc = ensure_stage(h, lane, image_bytes, image_bytes))) return rc;
-    if (h->init_graph && (h->init_graph_stage != lane.stage || h->init_graph_stride != stride)) {
+    if (h->init_graph && (h->init_graph_stage != lane.stage || h->init_graph_stride != stride ||
+                          h->init_graph_profiling != h->profiling)) {
       cudaGraphExecDestroy(h->init_graph);
       h->init_graph = nullptr;
     }
@@ -705,11 +711,13 @@ int vslam_fpg_initialize(vslam_fpg* h, const uint8_t* left, const uint8_t* right
       cudaGraph_t graph = nullptr;
       bool ok = cudaStreamBeginCapture(lane.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
       if (ok) {
+        h->capturing = true;
         cudaMemcpyAsync(h->d_thr, h->h_thr, sizeof(int32_t) * g.n_regions, cudaMemcpyHostToDevice, lane.stream);
         launch_repitch(g, lane.stage, lane.stage + lane.stage_bytes, (int)stride, h->b.image, 1, lane.stream);
         ++h->launches;
         run_detect_describe(h, lane, 0, 1, h->d_thr);
         status_download(h, lane);
+        h->capturing = false;
         ok = cudaStreamEndCapture(lane.stream, &graph) == cudaSuccess && graph != nullptr;
       }
       if (ok) ok = cudaGraphInstantiate(&h->init_graph, graph, 0) == cudaSuccess;
@@ -723,6 +731,7 @@ int vslam_fpg_initialize(vslam_fpg* h, const uint8_t* left, const uint8_t* right
       } else {
         h->init_graph_stage = lane.stage;
         h->init_graph_stride = stride;
+        h->init_graph_profiling = h->profiling;
       }
     }
     if (h->init_graph) {
