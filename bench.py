@@ -94,6 +94,16 @@ def _prior():
     return synth.true_motion(0.15)
 
 
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_baseline(left, right, rounds, sample):
     import cv2
     cv2.setNumThreads(0)
@@ -114,6 +124,7 @@ def cpu_baseline(left, right, rounds, sample):
         _cpu_pair(i, as_configured=True)
     dt2 = time.perf_counter() - t0
     return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": "port", "stages_ms_per_frame": stages,
+            "host": {"cpu_model": _cpu_model(), "nproc": len(os.sched_getaffinity(0))},
             "as_configured": {"value": n2 / dt2, "unit": "frames/s", "sample": "%d pairs" % n2,
                               "what": "the same plus the FLANN knnMatch(k=2) + findHomography(RANSAC) block that "
                                       "use_matches: true (struct default) executes and never reads "
@@ -153,6 +164,7 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic",
             "config": workload_config(args, per_step),
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "host": {"cpu_model": _cpu_model(), "nproc": cores},
                              "sample": "%d pairs per step (%d distinct), one process per core, oracle tier B (cv2 %s)"
                                        % (per_step, distinct, cv2.__version__)},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
