@@ -866,6 +866,7 @@ void orc_solve6_fullpiv(const double A_in[36], const double rhs[6], double x[6])
   memcpy(b, rhs, sizeof(b));
   for (int i = 0; i < 6; ++i) colperm[i] = i;
   int rank = 6;
+  double maxpivot = 0;
   for (int k = 0; k < 6; ++k) {
     int pr = k, pc = k;
     double best = -1;
@@ -880,6 +881,8 @@ void orc_solve6_fullpiv(const double A_in[36], const double rhs[6], double x[6])
       rank = k;
       break;
     }
+    if (best > maxpivot) maxpivot = best;
+    if (best > maxpivot) maxpivot = best;
     if (pr != k) {
       for (int j = 0; j < 6; ++j) {
         const double t = A[k * 6 + j];
@@ -906,6 +909,11 @@ void orc_solve6_fullpiv(const double A_in[36], const double rhs[6], double x[6])
       for (int j = k + 1; j < 6; ++j) A[i * 6 + j] -= f * A[k * 6 + j];
       b[i] -= f * b[k];
     }
+  }
+  {  /* Eigen::FullPivLU::rank(): only pivots above |largest pivot| * epsilon * size are used by solve() */
+    int r = 0;
+    for (int i = 0; i < rank; ++i) r += fabs(A[i * 6 + i]) > maxpivot * (2.220446049250313e-16 * 6);
+    rank = r;
   }
   double y[6] = {0, 0, 0, 0, 0, 0};
   for (int i = rank - 1; i >= 0; --i) {
@@ -1018,6 +1026,7 @@ void orc_solve3_fullpiv(const double A_in[9], const double rhs[3], double x[3]) 
   memcpy(A, A_in, sizeof(A));
   memcpy(b, rhs, sizeof(b));
   int rank = 3;
+  double maxpivot = 0;
   for (int k = 0; k < 3; ++k) {
     int pr = k, pc = k;
     double best = -1;
@@ -1032,6 +1041,8 @@ void orc_solve3_fullpiv(const double A_in[9], const double rhs[3], double x[3]) 
       rank = k;
       break;
     }
+    if (best > maxpivot) maxpivot = best;
+    if (best > maxpivot) maxpivot = best;
     if (pr != k) {
       for (int j = 0; j < 3; ++j) {
         const double t = A[k * 3 + j];
@@ -1058,6 +1069,11 @@ void orc_solve3_fullpiv(const double A_in[9], const double rhs[3], double x[3]) 
       for (int j = k + 1; j < 3; ++j) A[i * 3 + j] -= f * A[k * 3 + j];
       b[i] -= f * b[k];
     }
+  }
+  {  /* Eigen::FullPivLU::rank(): only pivots above |largest pivot| * epsilon * size are used by solve() */
+    int r = 0;
+    for (int i = 0; i < rank; ++i) r += fabs(A[i * 3 + i]) > maxpivot * (2.220446049250313e-16 * 3);
+    rank = r;
   }
   double y[3] = {0, 0, 0};
   for (int i = rank - 1; i >= 0; --i) {

@@ -143,6 +143,7 @@ def test_epipolar_offset_three_like_test_stereo_frontend():
     gen.initialize(left, right, False)
     o = _oracle(cfg, cam, left, right, False)
     fps = gen.compute()
+    assert gen.number_of_matches == len(o.matches)      # matches of EVERY epipolar pass are counted (:397-398)
     _same_points(gen.matches(), o.matches)
     _same_points(fps, o.framepoints())
     offs = set(o.matches["epipolar_offset"].tolist())
@@ -187,6 +188,29 @@ def test_batched_pairs_equal_independent_first_frames(cfgname, n):
         k, d = gen.features(0, pair=i)
         assert np.array_equal(d, o.desc_left) and np.array_equal(k["x"], o.kps_left["x"])
     assert np.array_equal(gen.thresholds, np.full(gen.number_of_detectors, cfg.detector_threshold_minimum))
+    gen.close()
+
+
+def test_batched_pairs_with_epipolar_offsets_count_every_pass():
+    """maximum_epipolar_search_offset_pixels > 0 in the batched (strip-select) path: number_of_new_points sums the
+    matches of every pass (stereo_framepoint_generator.cpp:278, :397-398)."""
+    import dataclasses
+    cfg = dataclasses.replace(configs.KITTI_FAST, maximum_epipolar_search_offset_pixels=2)
+    cam = synth.camera(cfg.camera)
+    n = 3
+    left, right = synth.band_world_batch(cfg.camera, range(60, 60 + n))
+    right = np.roll(right, 1, axis=1).copy()       # true matches sit one row lower in the right images
+    right[:, :2] = 96
+    gen = api.StereoFramePointGenerator(cfg, cam, max_batch=n)
+    out, counts = gen.batch_process(left, right, True)
+    _, nf, nm, _, _ = gen.batch_download(n)
+    later = 0
+    for i in range(n):
+        o = _oracle(cfg, cam, left[i], right[i], True)
+        assert nm[i] == len(o.matches) and nf[i] == counts[i]
+        _same_points(out[i, :counts[i]], o.framepoints())
+        later += int((o.matches["epipolar_offset"] != 0).sum())
+    assert later > 100
     gen.close()
 
 

@@ -236,6 +236,8 @@ void collect_clock(vslam_fpg* h, bool detect, bool match) {
 
 // lanes other than 0 start after everything already ordered on lane 0 (the handle's stream) ...
 int fork_lanes(vslam_fpg* h) {
+  // an outstanding single-pair feature prefetch on lane 1 still reads the buffers a batched call overwrites
+  if (h->feat_valid) CUDA_TRY(cudaStreamWaitEvent(h->lanes[0].stream, h->feat_ev, 0));
   CUDA_TRY(cudaEventRecord(h->fork_ev, h->lanes[0].stream));
   for (int l = 1; l < kLanes; ++l) CUDA_TRY(cudaStreamWaitEvent(h->lanes[l].stream, h->fork_ev, 0));
   return VSLAM_OK;
@@ -260,6 +262,12 @@ int ensure_stage(vslam_fpg* h, Lane& lane, size_t bytes, size_t pair_stride) {
   cudaFree(lane.stage);
   lane.stage = nullptr;
   lane.stage_bytes = 0;
+  // the captured initialize() graph bakes `stage + stage_bytes` as the right image's source: a reallocation (even one
+  // that returns the same address) invalidates it
+  if (&lane == &h->lanes[0] && h->init_graph) {
+    cudaGraphExecDestroy(h->init_graph);
+    h->init_graph = nullptr;
+  }
   const size_t want = (size_t)h->chunk * pair_stride;
   CUDA_TRY(cudaMalloc((void**)&lane.stage, 2 * want + 64));
   lane.stage_bytes = want;
@@ -526,7 +534,7 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
 
   // chunk: pairs per launch.  Large enough that the one-CTA-per-image / per-pair kernels (compact, select) fill the
   // 148 SMs; the path is instruction-bound, not HBM-bound, so L2 residency of a chunk's intermediates is secondary
-  // (measured: profiles/r1_notes.md)
+  // (measured: DESIGN.md section 3, `blurred` row; profiles/prof_r1j_summary.txt)
   const size_t per_pair = (size_t)2 * g.rows * (2 * g.pitch + 4 * g.mask_words);
   int chunk = (int)std::min<size_t>(256, std::max<size_t>(1, ((size_t)512u << 20) / per_pair));
   if (const char* e = std::getenv("VSLAM_CHUNK_PAIRS")) chunk = std::max(1, atoi(e));
@@ -695,6 +703,9 @@ int vslam_fpg_initialize(vslam_fpg* h, const uint8_t* left, const uint8_t* right
   CUDA_TRY(cudaSetDevice(h->device));
   Lane& lane = h->lanes[0];
   const Geometry& g = h->g;
+  // an outstanding feature prefetch (lane 1) still reads image / kp_xy / desc of the previous frame: order this
+  // frame's writes (lane 0) behind it
+  if (h->feat_valid) CUDA_TRY(cudaStreamWaitEvent(lane.stream, h->feat_ev, 0));
   h->feat_valid = false;
   int rc = VSLAM_OK;
   const size_t image_bytes = stride * (size_t)g.rows;

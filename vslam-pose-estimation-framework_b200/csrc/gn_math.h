@@ -30,6 +30,7 @@ VSLAM_HD inline void solve6(const double A_in[36], const double rhs[6], double x
   for (int i = 0; i < 6; ++i) b[i] = rhs[i];
   for (int i = 0; i < 6; ++i) perm[i] = i;
   int rank = 6;
+  double maxpivot = 0;
   for (int k = 0; k < 6; ++k) {
     int pr = k, pc = k;
     double biggest = -1;
@@ -44,6 +45,8 @@ VSLAM_HD inline void solve6(const double A_in[36], const double rhs[6], double x
       rank = k;
       break;
     }
+    if (biggest > maxpivot) maxpivot = biggest;
+    if (biggest > maxpivot) maxpivot = biggest;
     if (pr != k) {
       for (int j = 0; j < 6; ++j) swap_values(A[k * 6 + j], A[pr * 6 + j]);
       swap_values(b[k], b[pr]);
@@ -58,6 +61,11 @@ VSLAM_HD inline void solve6(const double A_in[36], const double rhs[6], double x
       for (int j = k + 1; j < 6; ++j) A[i * 6 + j] -= f * A[k * 6 + j];
       b[i] -= f * b[k];
     }
+  }
+  {  /* Eigen::FullPivLU::rank(): only pivots above |largest pivot| * epsilon * size are used by solve() */
+    int r = 0;
+    for (int i = 0; i < rank; ++i) r += fabs(A[i * 6 + i]) > maxpivot * (2.220446049250313e-16 * 6);
+    rank = r;
   }
   double y[6] = {0, 0, 0, 0, 0, 0};
   for (int i = rank - 1; i >= 0; --i) {
@@ -76,6 +84,7 @@ VSLAM_HD inline void solve3(const double A_in[9], const double rhs[3], double x[
   for (int i = 0; i < 9; ++i) A[i] = A_in[i];
   for (int i = 0; i < 3; ++i) b[i] = rhs[i];
   int rank = 3;
+  double maxpivot = 0;
   for (int k = 0; k < 3; ++k) {
     int pr = k, pc = k;
     double biggest = -1;
@@ -90,6 +99,8 @@ VSLAM_HD inline void solve3(const double A_in[9], const double rhs[3], double x[
       rank = k;
       break;
     }
+    if (biggest > maxpivot) maxpivot = biggest;
+    if (biggest > maxpivot) maxpivot = biggest;
     if (pr != k) {
       for (int j = 0; j < 3; ++j) swap_values(A[k * 3 + j], A[pr * 3 + j]);
       swap_values(b[k], b[pr]);
@@ -104,6 +115,11 @@ VSLAM_HD inline void solve3(const double A_in[9], const double rhs[3], double x[
       for (int j = k + 1; j < 3; ++j) A[i * 3 + j] -= f * A[k * 3 + j];
       b[i] -= f * b[k];
     }
+  }
+  {  /* Eigen::FullPivLU::rank(): only pivots above |largest pivot| * epsilon * size are used by solve() */
+    int r = 0;
+    for (int i = 0; i < rank; ++i) r += fabs(A[i * 3 + i]) > maxpivot * (2.220446049250313e-16 * 3);
+    rank = r;
   }
   double y[3] = {0, 0, 0};
   for (int i = rank - 1; i >= 0; --i) {

@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(kSelectWarps * 32) select_strips_kernel(
             const float disp = (float)(col - (int)(qr[u] & 0xffffu));   // frame_point.cpp:19
             const float dist = (float)(mm[u].y & 0xffff);
             unsigned todo = __ballot_sync(0xffffffffu, cand);
-            if (pass == 0) my_matches += __popc(todo);
+            my_matches += __popc(todo);   // cand holds this pass only: the passes sum to every match once
             while (todo) {                       // replay in emission order (ascending i)
               const int l = __ffs(todo) - 1;
               todo &= todo - 1;
