@@ -430,7 +430,7 @@ extern "C" int ref_fpg_track(ref_session* s, const double T[12], int by_appearan
   if (lost)
     for (size_t i = 0; i < s->lost.size(); ++i) lost[i] = position.at(s->lost[i]);
   if (number_of_tracked_landmarks) *number_of_tracked_landmarks = (int)s->generator->numberOfTrackedLandmarks();
-  if (average_descriptor_distance) *average_descriptor_distance = current->averageDescriptorDistanceTracking();
+  if (average_descriptor_distance) *average_descriptor_distance = previous->averageDescriptorDistanceTracking();   // set on the PREVIOUS frame (:664)
   return (int)current->points().size();
   REF_CATCH(-1)
 }
