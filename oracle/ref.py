@@ -14,8 +14,10 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "libvslam_ref.so")
+_SO_GPU = os.path.join(_HERE, "_ref", "libvslam_ref_gpu.so")      # + adapters/ + libvslam_b200.so (make _ref_gpu)
 REFERENCE_ROOT = "/root/reference"
 _lib = None
+_lib_gpu = None
 
 
 class Parameters(C.Structure):
@@ -65,6 +67,14 @@ def build(force: bool = False) -> str | None:
     return _SO
 
 
+def build_gpu() -> str | None:
+    """make -C oracle _ref_gpu: the reference + adapters/ linked against the product library (must be built first)"""
+    if not os.path.isdir(REFERENCE_ROOT):
+        return _SO_GPU if os.path.exists(_SO_GPU) else None
+    subprocess.check_call(["make", "-C", _HERE, "-j8", "_ref_gpu"], stdout=subprocess.DEVNULL)
+    return _SO_GPU
+
+
 def available() -> bool:
     try:
         return build() is not None
@@ -72,13 +82,32 @@ def available() -> bool:
         return False
 
 
-def lib():
-    global _lib
+def gpu_available() -> bool:
+    try:
+        return build_gpu() is not None
+    except Exception:
+        return False
+
+
+def lib(gpu: bool = False):
+    global _lib, _lib_gpu
+    if gpu:
+        if _lib_gpu is None:
+            path = build_gpu()
+            if path is None:
+                raise RuntimeError("oracle/_ref/libvslam_ref_gpu.so is not built and /root/reference is absent")
+            _lib_gpu = _declare(C.CDLL(path))
+        return _lib_gpu
     if _lib is None:
         path = build()
         if path is None:
             raise RuntimeError("oracle/_ref is not built and /root/reference is absent")
-        L = C.CDLL(path)
+        _lib = _declare(C.CDLL(path))
+    return _lib
+
+
+def _declare(L):
+    if True:
         L.ref_last_error.restype = C.c_char_p
         L.ref_open.restype = C.c_void_p
         L.ref_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_double]
@@ -91,8 +120,7 @@ def lib():
         L.ref_close.argtypes = [C.c_void_p]
         L.ref_close.restype = None
         assert C.sizeof(Parameters) > 0 and POINT.itemsize == 248, POINT.itemsize
-        _lib = L
-    return _lib
+    return L
 
 
 def _p(a):
@@ -106,12 +134,52 @@ def _t12(T):
     return np.ascontiguousarray(T.reshape(12))
 
 
+def effective_values(name):
+    """ParameterCollection::parseFromFile(configurations/configuration_<name>.yaml), as ref_get_parameters reports it
+    in this repository's container (committed so that the GPU box needs no YAML file)"""
+    common = dict(maximum_number_of_iterations=1000, minimum_inlier_ratio=0.0, enable_inverse_depth_as_information=1,
+                  maximum_number_of_landmark_recoveries=10, enable_landmark_recovery=1, motion_model=1,
+                  minimum_delta_angular_for_movement=0.001, minimum_delta_translational_for_movement=0.01,
+                  minimum_number_of_landmarks_to_track=5, target_number_of_keypoints_tolerance=0.1,
+                  enable_keypoint_binning=1, minimum_disparity_pixels=1.0, maximum_epipolar_search_offset_pixels=0,
+                  maximum_projection_tracking_distance_pixels=50, minimum_depth_meters=0.1, error_delta_for_convergence=1e-3)
+    per = {
+        "kitti": dict(descriptor_type="BRIEF", detector_threshold_minimum=20, detector_threshold_maximum=100,
+                      detector_threshold_maximum_change=0.1, number_of_detectors_vertical=1,
+                      number_of_detectors_horizontal=1, minimum_projection_tracking_distance_pixels=15,
+                      minimum_descriptor_distance_tracking=25.6, maximum_descriptor_distance_tracking=51.2,
+                      maximum_reliable_depth_meters=15.0, maximum_depth_meters=1000.0, bin_size_pixels=15,
+                      maximum_matching_distance_triangulation=51.2, maximum_error_kernel=4.0, damping=5.0,
+                      minimum_number_of_inliers=100, minimum_track_length_for_landmark_creation=1,
+                      tunnel_vision_ratio=0.5, good_tracking_ratio=0.2, maximum_error_squared_meters=100.0),
+        "kitti_fast": dict(descriptor_type="BRIEF-256", detector_threshold_minimum=15, detector_threshold_maximum=100,
+                           detector_threshold_maximum_change=0.5, number_of_detectors_vertical=1,
+                           number_of_detectors_horizontal=1, minimum_projection_tracking_distance_pixels=10,
+                           minimum_descriptor_distance_tracking=25.0, maximum_descriptor_distance_tracking=50.0,
+                           maximum_reliable_depth_meters=15.0, maximum_depth_meters=1000.0, bin_size_pixels=25,
+                           maximum_matching_distance_triangulation=60.0, maximum_error_kernel=16.0, damping=0.0,
+                           minimum_number_of_inliers=0, minimum_track_length_for_landmark_creation=2,
+                           tunnel_vision_ratio=0.75, good_tracking_ratio=0.2, maximum_error_squared_meters=25.0),
+        "euroc": dict(descriptor_type="ORB-256", detector_threshold_minimum=10, detector_threshold_maximum=30,
+                      detector_threshold_maximum_change=1.0, number_of_detectors_vertical=2,
+                      number_of_detectors_horizontal=2, minimum_projection_tracking_distance_pixels=15,
+                      minimum_descriptor_distance_tracking=25.0, maximum_descriptor_distance_tracking=50.0,
+                      maximum_reliable_depth_meters=5.0, maximum_depth_meters=100.0, bin_size_pixels=20,
+                      maximum_matching_distance_triangulation=50.0, maximum_error_kernel=4.0, damping=0.0,
+                      minimum_number_of_inliers=100, minimum_track_length_for_landmark_creation=2,
+                      tunnel_vision_ratio=0.5, good_tracking_ratio=0.25, maximum_error_squared_meters=9.0)}
+    return {**common, **per[name]}
+
+
 class Session:
     """One ParameterCollection + cameras + StereoFramePointGenerator + StereoUVAligner / UVDAligner + WorldMap +
     PoseTracker3D of the reference, built as SLAMAssembly builds them."""
 
-    def __init__(self, cam, yaml: str | None = None, **overrides):
-        self.L = lib()
+    def __init__(self, cam, yaml: str | None = None, gpu: bool = False, **overrides):
+        """gpu=True: adapters/ GpuStereoFramePointGenerator + GpuStereoUVAligner take the place of the CPU classes under
+        the reference's unmodified tracker (needs a B200 at configure())"""
+        self.gpu = gpu
+        self.L = lib(gpu)
         self.cam = cam
         K = np.array([[cam.fx, 0, cam.cx], [0, cam.fy, cam.cy], [0, 0, 1]], np.float64)
         self.rows, self.cols = cam.rows, cam.cols
@@ -153,7 +221,7 @@ class Session:
         return p
 
     def configure(self):
-        self._ck(self.L.ref_configure(self.h))
+        self._ck(self.L.ref_configure_gpu(self.h) if self.gpu else self.L.ref_configure(self.h))
         self.configured = True
         return self
 

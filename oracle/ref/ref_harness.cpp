@@ -16,6 +16,11 @@
 #include "position_tracking/pose_tracker_3d.h"
 #include "types/landmark.h"
 #include "types/world_map.h"
+#ifdef VSLAM_REF_WITH_GPU_ADAPTERS
+// the drop-in classes of adapters/ (backed by libvslam_b200.so) take the place of the reference's CPU classes
+#include "gpu_frame_aligners.h"
+#include "gpu_stereo_framepoint_generator.h"
+#endif
 
 using namespace proslam;
 
@@ -66,6 +71,14 @@ struct UV : AlignerAccess<StereoUVAligner, 4> {
   using StereoUVAligner::_offset_camera_right;
 };
 typedef AlignerAccess<UVDAligner, 3> UVD;
+#ifdef VSLAM_REF_WITH_GPU_ADAPTERS
+struct GpuUV : AlignerAccess<GpuStereoUVAligner, 4> {
+  using AlignerAccess<GpuStereoUVAligner, 4>::AlignerAccess;
+  using StereoUVAligner::_offset_camera_right;
+};
+#else
+struct GpuUV;
+#endif
 
 struct Tracker : PoseTracker3D {
   using PoseTracker3D::PoseTracker3D;
@@ -93,8 +106,12 @@ struct ref_session {
   Camera* camera_right = nullptr;
   WorldMap* world = nullptr;
   Tracker* tracker = nullptr;         // owns generator and uv (pose_tracker_3d.cpp:27-28)
-  Generator* generator = nullptr;
-  UV* uv = nullptr;
+  Generator* generator = nullptr;     // CPU mode only (nullptr when the GPU adapters are in place)
+  StereoFramePointGenerator* base_generator = nullptr;   // either mode
+  BaseFrameAligner* base_uv = nullptr;
+  bool gpu = false;
+  GpuUV* gpu_uv = nullptr;            // GPU mode: the tracker's aligner
+  UV* uv = nullptr;                   // CPU mode: the tracker's aligner
   UVD* uvd = nullptr;
   AlignerParameters* uvd_parameters = nullptr;
   FramePointPointerVector lost;
@@ -268,9 +285,10 @@ extern "C" int ref_set_parameters(ref_session* s, const ref_parameters* i) {
   REF_CATCH(-1)
 }
 
-extern "C" int ref_configure(ref_session* s) {
+static int configure(ref_session* s, bool gpu) {
   REF_TRY
   if (s->tracker) throw std::runtime_error("ref_configure called twice");
+  s->gpu = gpu;
   // counters are process-wide statics (slam_assembly.cpp:28-32)
   Frame::reset();
   FramePoint::reset();
@@ -299,16 +317,29 @@ extern "C" int ref_configure(ref_session* s) {
   // SLAMAssembly::_createStereoTracker (slam_assembly.cpp:48-76)
   s->camera_left->setCameraMatrix(s->camera_left->projectionMatrix().block<3, 3>(0, 0));
   s->camera_right->setCameraMatrix(s->camera_left->cameraMatrix());
-  s->generator = new Generator(s->parameters->stereo_framepoint_generator_parameters);
-  s->generator->setCameraLeft(s->camera_left);
-  s->generator->setCameraRight(s->camera_right);
-  s->generator->configure();
-  s->uv = new UV(s->parameters->tracker_parameters->aligner);
-  s->uv->setMaximumReliableDepthMeters(s->parameters->stereo_framepoint_generator_parameters->maximum_reliable_depth_meters);
-  s->uv->setMinimumReliableDepthMeters(s->parameters->stereo_framepoint_generator_parameters->minimum_depth_meters);
-  s->uv->configure();
-  s->tracker->setFramePointGenerator(s->generator);
-  s->tracker->setAligner(s->uv);
+  if (!gpu) {
+    s->generator = new Generator(s->parameters->stereo_framepoint_generator_parameters);
+    s->base_generator = s->generator;
+    s->uv = new UV(s->parameters->tracker_parameters->aligner);
+    s->base_uv = s->uv;
+  } else {
+#ifdef VSLAM_REF_WITH_GPU_ADAPTERS
+    // the two `new` expressions of slam_assembly.cpp:62, :68 name the GPU classes instead
+    s->base_generator = new GpuStereoFramePointGenerator(s->parameters->stereo_framepoint_generator_parameters);
+    s->gpu_uv = new GpuUV(s->parameters->tracker_parameters->aligner);
+    s->base_uv = s->gpu_uv;
+#else
+    throw std::runtime_error("this build of oracle/_ref has no GPU adapters (make _ref_gpu)");
+#endif
+  }
+  s->base_generator->setCameraLeft(s->camera_left);
+  s->base_generator->setCameraRight(s->camera_right);
+  s->base_generator->configure();
+  s->base_uv->setMaximumReliableDepthMeters(s->parameters->stereo_framepoint_generator_parameters->maximum_reliable_depth_meters);
+  s->base_uv->setMinimumReliableDepthMeters(s->parameters->stereo_framepoint_generator_parameters->minimum_depth_meters);
+  s->base_uv->configure();
+  s->tracker->setFramePointGenerator(s->base_generator);
+  s->tracker->setAligner(s->base_uv);
   s->tracker->configure();
 
   // the depth aligner (slam_assembly.cpp:88-92), on a copy of the same AlignerParameters
@@ -319,6 +350,21 @@ extern "C" int ref_configure(ref_session* s) {
   s->uvd->configure();
   return 0;
   REF_CATCH(-1)
+}
+
+extern "C" int ref_configure(ref_session* s) { return configure(s, false); }
+extern "C" int ref_configure_gpu(ref_session* s) { return configure(s, true); }
+extern "C" int ref_has_gpu_adapters(void) {
+#ifdef VSLAM_REF_WITH_GPU_ADAPTERS
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+static Generator* cpu_generator(ref_session* s) {
+  if (!s->generator) throw std::runtime_error("this call reads the CPU generator's internals (not available with the GPU adapters)");
+  return s->generator;
 }
 
 // ---- generator ---------------------------------------------------------------------------------------------------
@@ -337,7 +383,7 @@ extern "C" int ref_fpg_initialize(ref_session* s, const uint8_t* left, const uin
   frame->setCameraRight(s->camera_right);
   frame->setIntensityImageRight(copy_image(right, s->rows, s->cols, stride));
   frame->setStatus(status ? Frame::Tracking : Frame::Localizing);
-  s->generator->initialize(frame);
+  s->base_generator->initialize(frame);
   s->lost.clear();
   return 0;
   REF_CATCH(-1)
@@ -345,7 +391,7 @@ extern "C" int ref_fpg_initialize(ref_session* s, const uint8_t* left, const uin
 
 extern "C" int ref_fpg_reinitialize(ref_session* s) {
   REF_TRY
-  s->generator->initialize(s->world->currentFrame(), false);
+  s->base_generator->initialize(s->world->currentFrame(), false);
   return 0;
   REF_CATCH(-1)
 }
@@ -373,7 +419,7 @@ extern "C" int ref_fpg_features(ref_session* s, int side, float* xyr, uint8_t* d
 extern "C" int ref_fpg_remaining(ref_session* s, int side, float* xy, int capacity) {
   REF_TRY
   const IntensityFeaturePointerVector& v =
-      side ? s->generator->_feature_matcher_right.feature_vector : s->generator->_feature_matcher_left.feature_vector;
+      side ? cpu_generator(s)->_feature_matcher_right.feature_vector : cpu_generator(s)->_feature_matcher_left.feature_vector;
   const int n = (int)v.size();
   if (n > capacity) throw std::runtime_error("ref_fpg_remaining: capacity");
   for (int i = 0; i < n; ++i) {
@@ -391,20 +437,20 @@ extern "C" int ref_fpg_thresholds(ref_session* s, double* out, int capacity) {
   if (n > capacity) throw std::runtime_error("ref_fpg_thresholds: capacity");
   for (uint32_t r = 0; r < g->number_of_detectors_vertical; ++r)
     for (uint32_t c = 0; c < g->number_of_detectors_horizontal; ++c)
-      out[r * g->number_of_detectors_horizontal + c] = s->generator->_detectors[r][c]->getThreshold();
+      out[r * g->number_of_detectors_horizontal + c] = cpu_generator(s)->_detectors[r][c]->getThreshold();
   return n;
   REF_CATCH(-1)
 }
 
 extern "C" double ref_fpg_triangulation_distance(ref_session* s) {
-  return s->generator->_current_maximum_descriptor_distance_triangulation;
+  return s->generator ? s->generator->_current_maximum_descriptor_distance_triangulation : -1.0;
 }
-extern "C" int ref_fpg_target_number_of_keypoints(ref_session* s) { return (int)s->generator->targetNumberOfKeypoints(); }
+extern "C" int ref_fpg_target_number_of_keypoints(ref_session* s) { return (int)s->base_generator->targetNumberOfKeypoints(); }
 
 extern "C" int ref_fpg_set_tracking(ref_session* s, int distance_pixels, double maximum_descriptor_distance) {
   REF_TRY
-  s->generator->setProjectionTrackingDistancePixels(distance_pixels);
-  s->generator->setMaximumDescriptorDistanceTracking(maximum_descriptor_distance);
+  s->base_generator->setProjectionTrackingDistancePixels(distance_pixels);
+  s->base_generator->setMaximumDescriptorDistanceTracking(maximum_descriptor_distance);
   return 0;
   REF_CATCH(-1)
 }
@@ -425,11 +471,11 @@ extern "C" int ref_fpg_track(ref_session* s, const double T[12], int by_appearan
   std::map<const FramePoint*, int> position;
   for (size_t i = 0; i < previous->points().size(); ++i) position[previous->points()[i]] = (int)i;
   s->lost.clear();
-  s->generator->track(current, previous, to_transform(T), s->lost, by_appearance != 0);
+  s->base_generator->track(current, previous, to_transform(T), s->lost, by_appearance != 0);
   if (n_lost) *n_lost = (int)s->lost.size();
   if (lost)
     for (size_t i = 0; i < s->lost.size(); ++i) lost[i] = position.at(s->lost[i]);
-  if (number_of_tracked_landmarks) *number_of_tracked_landmarks = (int)s->generator->numberOfTrackedLandmarks();
+  if (number_of_tracked_landmarks) *number_of_tracked_landmarks = (int)s->base_generator->numberOfTrackedLandmarks();
   if (average_descriptor_distance) *average_descriptor_distance = previous->averageDescriptorDistanceTracking();   // set on the PREVIOUS frame (:664)
   return (int)current->points().size();
   REF_CATCH(-1)
@@ -439,14 +485,14 @@ extern "C" int ref_fpg_recover(ref_session* s) {
   REF_TRY
   Frame* current = s->world->currentFrame();
   const size_t before = current->points().size();
-  s->generator->recoverPoints(current, s->lost);
+  s->base_generator->recoverPoints(current, s->lost);
   return (int)(current->points().size() - before);
   REF_CATCH(-1)
 }
 
 extern "C" int ref_fpg_compute(ref_session* s) {
   REF_TRY
-  s->generator->compute(s->world->currentFrame());
+  s->base_generator->compute(s->world->currentFrame());
   return (int)s->world->currentFrame()->points().size();
   REF_CATCH(-1)
 }
@@ -528,9 +574,9 @@ extern "C" int ref_frame_make_landmarks(ref_session* s, int every_nth) {
 
 extern "C" double ref_fpg_seconds(ref_session* s, int which) {
   switch (which) {
-    case 0: return s->generator->getTimeConsumptionSeconds_keypoint_detection();
-    case 1: return s->generator->getTimeConsumptionSeconds_descriptor_extraction();
-    default: return s->generator->getTimeConsumptionSeconds_point_triangulation();
+    case 0: return s->base_generator->getTimeConsumptionSeconds_keypoint_detection();
+    case 1: return s->base_generator->getTimeConsumptionSeconds_descriptor_extraction();
+    default: return s->base_generator->getTimeConsumptionSeconds_point_triangulation();
   }
 }
 
@@ -571,6 +617,8 @@ static void load_common(ref_session* s, A* a, int n, const double* moving, const
 extern "C" int ref_aligner_load(ref_session* s, int kind, int n, const double* moving, const double* fixed,
                                 const double* omega, const double* wt, const double baseline[3], double min_depth) {
   REF_TRY
+  if (kind == 0 && s->gpu)
+    throw std::runtime_error("ref_aligner_load: explicit correspondences go through the C ABI in GPU mode (tests/test_gpu_aligner.py)");
   if (kind == 0) {
     load_common(s, s->uv, n, moving, wt, min_depth);
     for (int u = 0; u < n; ++u) {
@@ -593,8 +641,19 @@ extern "C" int ref_aligner_load(ref_session* s, int kind, int n, const double* m
   REF_CATCH(-1)
 }
 
+#ifdef VSLAM_REF_WITH_GPU_ADAPTERS
+#define WITH_GPU_ALIGNER(stmt)    \
+  {                               \
+    GpuUV* a = s->gpu_uv;         \
+    stmt;                         \
+  }
+#else
+#define WITH_GPU_ALIGNER(stmt) throw std::runtime_error("no GPU adapters in this build");
+#endif
 #define WITH_ALIGNER(stmt)        \
-  if (kind == 0) {                \
+  if (kind == 0 && s->gpu) {      \
+    WITH_GPU_ALIGNER(stmt)        \
+  } else if (kind == 0) {         \
     UV* a = s->uv;                \
     stmt;                         \
   } else {                        \
@@ -667,17 +726,21 @@ extern "C" int ref_aligner_initialize_frames(ref_session* s, int kind, const dou
   REF_CATCH(-1)
 }
 
+template <class A>
+static int packed_uv(A* a, double* moving, double* fixed, double* omega, double* wt) {
+  for (size_t u = 0; u < a->_number_of_measurements; ++u) {
+    for (int k = 0; k < 3; ++k) moving[3 * u + k] = a->_moving[u](k);
+    for (int k = 0; k < 4; ++k) fixed[4 * u + k] = a->_fixed[u](k);
+    omega[u] = a->_information_matrix_vector[u](0, 0);
+    wt[u] = a->_weights_translation[u];
+  }
+  return (int)a->_number_of_measurements;
+}
+
 extern "C" int ref_aligner_packed(ref_session* s, int kind, double* moving, double* fixed, double* omega, double* wt) {
   REF_TRY
   if (kind == 0) {
-    UV* a = s->uv;
-    for (size_t u = 0; u < a->_number_of_measurements; ++u) {
-      for (int k = 0; k < 3; ++k) moving[3 * u + k] = a->_moving[u](k);
-      for (int k = 0; k < 4; ++k) fixed[4 * u + k] = a->_fixed[u](k);
-      omega[u] = a->_information_matrix_vector[u](0, 0);
-      wt[u] = a->_weights_translation[u];
-    }
-    return (int)a->_number_of_measurements;
+    WITH_ALIGNER(return packed_uv(a, moving, fixed, omega, wt))
   }
   UVD* a = s->uvd;
   for (size_t u = 0; u < a->_number_of_measurements; ++u) {
@@ -703,7 +766,7 @@ extern "C" int ref_tracker_process(ref_session* s, const uint8_t* left, const ui
   // SLAMAssembly::process (slam_assembly.cpp:554-575, stereo branch, without relocalisation / map optimisation)
   s->tracker->setIntensityImageLeft(copy_image(left, s->rows, s->cols, stride));
   s->tracker->setImageSecondary(copy_image(right, s->rows, s->cols, stride));
-  s->uv->rounds = 0;
+  if (s->uv) s->uv->rounds = 0;
   s->tracker->compute();
   return (int)s->world->currentFrame()->points().size();
   REF_CATCH(-1)

@@ -86,6 +86,10 @@ int ref_get_parameters(ref_session*, ref_parameters* out);
 int ref_set_parameters(ref_session*, const ref_parameters* in);
 /* builds generator, aligners, world map and tracker exactly as SLAMAssembly::_createStereoTracker does */
 int ref_configure(ref_session*);
+/* the same wiring with adapters/ GpuStereoFramePointGenerator + GpuStereoUVAligner (libvslam_b200.so) in place of the CPU
+ * classes -- only in oracle/_ref/libvslam_ref_gpu.so (make _ref_gpu); calls that read CPU internals then fail */
+int ref_configure_gpu(ref_session*);
+int ref_has_gpu_adapters(void);
 
 /* ---- generator, stage by stage ------------------------------------------------------------------------------ */
 /* WorldMap::createFrame + setStatus(status: 0 Localizing, 1 Tracking) + StereoFramePointGenerator::initialize */

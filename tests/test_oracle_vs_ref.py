@@ -79,6 +79,18 @@ def test_effective_parameters_of_the_references_own_parser(name):
     s.close()
 
 
+@pytest.mark.skipif(not HAVE_YAML, reason="configurations/*.yaml live in /root/reference")
+@pytest.mark.parametrize("name", ["kitti", "kitti_fast", "euroc"])
+def test_committed_effective_values_are_what_the_yaml_parses_to(name):
+    cam = synth.camera(configs.BY_NAME[name].camera)
+    s = ref.Session(cam, YAML[name])
+    p = s.parameters()
+    for key, value in ref.effective_values(name).items():
+        got = getattr(p, key)
+        assert (got.decode() if isinstance(got, bytes) else got) == value, key
+    s.close()
+
+
 # ---- first frames: initialize() + compute() ------------------------------------------------------------------------------
 def _assert_features(s, o):
     for side, (kps, desc) in enumerate(((o.kps_left, o.desc_left), (o.kps_right, o.desc_right))):
