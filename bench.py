@@ -42,10 +42,15 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=4096, help="stereo pairs per rank per step")
-    ap.add_argument("--distinct", type=int, default=256, help="distinct synthetic pairs generated per rank")
+    ap.add_argument("--distinct", type=int, default=0,
+                    help="distinct synthetic pairs generated per rank (0: 256 for weak scaling, every pair for strong)")
     ap.add_argument("--rounds", type=int, default=10, help="linearize rounds per pair per step (BASELINE config 4)")
     ap.add_argument("--cpu-sample", type=int, default=192, help="pairs of the single-thread CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --pairs per GPU; strong: --pairs in total, block-partitioned over the ranks "
+                         "(BASELINE.json configs[2]: 4096 pairs sharded across 1/2/4/8)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the aligner / sequence / landmark side measurements")
     return ap.parse_args()
 
 
@@ -59,14 +64,32 @@ def _cpu_init(left, right, rounds):
     _CPU.update(left=left, right=right, rounds=rounds)
 
 
+def _cpu_kind():
+    """"reference": oracle/_ref -- the reference's own unmodified translation units (stereo_framepoint_generator.cpp,
+    stereouv_aligner.cpp, ...) with OpenCV's own FAST / ORB (python cv2) behind its cv:: calls; "port": the tier-B
+    restatement, when the prebuilt library did not travel"""
+    if "kind" not in _CPU:
+        from oracle import ref
+        _CPU["kind"] = "reference" if ref.available() else "port"
+    return _CPU["kind"]
+
+
 def _cpu_pair(i, as_configured=False):
     """one stereo pair through the reference's CPU path (OpenCV primitives, 1 thread): returns n framepoints.
     as_configured: also run the FLANN knnMatch + findHomography block that `use_matches: true` executes and whose
-    results the reference never reads (stereo_framepoint_generator.cpp:168-273)"""
+    results the reference never reads (stereo_framepoint_generator.cpp:168-273) -- tier B only"""
     from oracle import pipeline, tier_a
     from vslam_b200 import configs, synth
     cfg, acfg = configs.BY_NAME[CONFIG_NAME], configs.ALIGNER_BY_NAME[CONFIG_NAME]
     cam = synth.camera(cfg.camera)
+    if _cpu_kind() == "reference" and not as_configured:
+        from oracle import ref
+        if "session" not in _CPU or _CPU.get("pid") != os.getpid():
+            _CPU["cv2"] = ref.install_cv2_backend()
+            _CPU["session"] = ref.Session(cam, None, **ref.effective_values(CONFIG_NAME)).configure()
+            _CPU["pid"] = os.getpid()
+            _CPU["T"] = _prior()
+        return _CPU["session"].first_frame(_CPU["left"][i], _CPU["right"][i], _CPU["rounds"], _CPU["T"])
     if "gen" not in _CPU:
         _CPU["gen"] = pipeline.StereoFramePointGeneratorOracle(cfg, cam, "b")
         _CPU["T"] = _prior()
@@ -104,55 +127,133 @@ def _cpu_model():
     return "unknown"
 
 
-def cpu_baseline(left, right, rounds, sample):
+def _cpu_what(rounds):
+    import cv2
+    if _cpu_kind() == "reference":
+        return ("oracle/_ref: the reference's own unmodified StereoFramePointGenerator::initialize + compute and "
+                "StereoUVAligner::linearize x%d (compiled from /root/reference against the stand-ins of oracle/shims), "
+                "cv::FastFeatureDetector / cv::ORB answered by OpenCV %s (python cv2, cv2.setNumThreads(0) as "
+                "executables/app.cpp:96); the dead use_matches FLANN block (stereo_framepoint_generator.cpp:168-273) "
+                "returns empty results" % (rounds, cv2.__version__))
+    return ("oracle tier B (cv2 %s FAST/ORB with cv2.setNumThreads(0) as executables/app.cpp:96, C -O2 stereo scan / bins / "
+            "triangulation / linearize x%d); the reference's dead use_matches FLANN block is not executed"
+            % (cv2.__version__, rounds))
+
+
+def cpu_baseline(left, right, rounds, sample, budget_s=14.0):
     import cv2
     cv2.setNumThreads(0)
-    n = min(sample, len(left))
     _cpu_init(left, right, rounds)
     _cpu_pair(0)                                               # warm-up (imports, first-touch)
-    _CPU["gen"].seconds = {k: 0.0 for k in _CPU["gen"].seconds}
-    _CPU["pose_optimization"] = 0.0
+    kind = _cpu_kind()
+    if kind == "reference":
+        s = _CPU["session"]
+        g0, p0 = s.generator_seconds(), s.seconds_pose_optimization
+    else:
+        _CPU["gen"].seconds = {k: 0.0 for k in _CPU["gen"].seconds}
+        _CPU["pose_optimization"] = 0.0
     t0 = time.perf_counter()
-    for i in range(n):
-        _cpu_pair(i)
+    n = 0
+    while n < sample and time.perf_counter() - t0 < budget_s:     # a bounded sample: `sample` pairs or `budget_s` seconds
+        _cpu_pair(n % len(left))
+        n += 1
     dt = time.perf_counter() - t0
-    stages = {k: v / n * 1e3 for k, v in _CPU["gen"].seconds.items()}      # the reference's chronometer names
-    stages["pose_optimization"] = _CPU["pose_optimization"] / n * 1e3
-    n2 = min(12, n)          # the as-configured variant is several times slower: a smaller sample
+    if kind == "reference":                                     # the reference's own chronometers (definitions.h:147-151)
+        stages = {k: (v - g0[k]) / n * 1e3 for k, v in s.generator_seconds().items()}
+        stages["pose_optimization"] = (s.seconds_pose_optimization - p0) / n * 1e3
+    else:
+        stages = {k: v / n * 1e3 for k, v in _CPU["gen"].seconds.items()}
+        stages["pose_optimization"] = _CPU["pose_optimization"] / n * 1e3
+    n2 = min(12, len(left))    # the as-configured variant (tier B + FLANN block) is several times slower: a smaller sample
     t0 = time.perf_counter()
     for i in range(n2):
         _cpu_pair(i, as_configured=True)
     dt2 = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": "port", "stages_ms_per_frame": stages,
+    return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": kind, "stages_ms_per_frame": stages,
             "host": {"cpu_model": _cpu_model(), "nproc": len(os.sched_getaffinity(0))},
-            "as_configured": {"value": n2 / dt2, "unit": "frames/s", "sample": "%d pairs" % n2,
-                              "what": "the same plus the FLANN knnMatch(k=2) + findHomography(RANSAC) block that "
+            "as_configured": {"value": n2 / dt2, "unit": "frames/s", "sample": "%d pairs" % n2, "kind": "port",
+                              "what": "oracle tier B plus the FLANN knnMatch(k=2) + findHomography(RANSAC) block that "
                                       "use_matches: true (struct default) executes and never reads "
                                       "(stereo_framepoint_generator.cpp:168-273)"},
-            "sample": "%d of the same KITTI-shape pairs, oracle tier B (cv2 %s FAST/ORB with cv2.setNumThreads(0) as "
-                      "executables/app.cpp:96, C -O2 stereo scan/bins/triangulation/linearize x%d), one thread; the "
-                      "reference's dead use_matches FLANN block is not executed" % (n, cv2.__version__, rounds),
+            "sample": "%d of the same KITTI-shape first-frame pairs, one thread: %s" % (n, _cpu_what(rounds)),
             "seconds": dt}
 
 
+def cpu_sequence_baseline(frames, name="kitti"):
+    """BASELINE.json configs[0]: configuration_kitti.yaml, one synthetic 1241x376 stereo sequence through the tracker
+    that executables/app runs per frame, on the CPU reference path: the reference's own PoseTracker3D::compute
+    (initialize -> track -> StereoUVAligner -> prune -> recoverPoints -> landmark updates -> compute) from oracle/_ref,
+    OpenCV's FAST / ORB behind it, one thread.  None when oracle/_ref did not travel."""
+    from oracle import ref
+    from vslam_b200 import configs, synth
+    if not ref.available():
+        return None
+    version = ref.install_cv2_backend()
+    cam = synth.camera(configs.BY_NAME[name].camera)
+    s = ref.Session(cam, None, **ref.effective_values(name)).configure()
+    t0 = time.perf_counter()
+    for left, right in frames:
+        s.process(left, right)
+    dt = time.perf_counter() - t0
+    stages = {k: v / len(frames) * 1e3 for k, v in {**s.generator_seconds(), **s.tracker_seconds()}.items()}
+    pose = s.pose()
+    out = {"value": len(frames) / dt, "unit": "frames/s", "cores": 1, "kind": "reference", "frames": len(frames),
+           "stages_ms_per_frame": stages, "final_x_m": float(pose[0, 3]),
+           "true_final_x_m": (len(frames) - 1) * (-cam.bx / cam.fx) / 4,
+           "what": "oracle/_ref: the reference's unmodified PoseTracker3D::compute per frame (configuration_%s.yaml values), "
+                   "cv::FastFeatureDetector / cv::ORB answered by OpenCV %s, one thread" % (name, version)}
+    s.close()
+    return out
+
+
+def gpu_sequence_through_the_reference_tracker(frames, name="kitti"):
+    """the same sequence through the same unmodified PoseTracker3D with adapters/ GpuStereoFramePointGenerator +
+    GpuStereoUVAligner in place of the CPU classes (oracle/_ref/libvslam_ref_gpu.so, tests/test_gpu_dropin.py): what a
+    user of the reference gets per frame after the two-line change of INTEGRATION.md, object graph and landmark
+    bookkeeping of the reference included"""
+    from oracle import ref
+    from vslam_b200 import configs, synth
+    if not ref.gpu_available():
+        return None
+    cam = synth.camera(configs.BY_NAME[name].camera)
+    warm = ref.Session(cam, None, gpu=True, **ref.effective_values(name)).configure()
+    for left, right in frames[:4]:      # module load, first allocations
+        warm.process(left, right)
+    warm.close()
+    s = ref.Session(cam, None, gpu=True, **ref.effective_values(name)).configure()
+    t0 = time.perf_counter()
+    for left, right in frames:
+        s.process(left, right)
+    dt = time.perf_counter() - t0
+    pose = s.pose()
+    stages = {k: v / len(frames) * 1e3 for k, v in s.tracker_seconds().items()}
+    out = {"value": len(frames) / dt, "unit": "frames/s", "frames": len(frames), "final_x_m": float(pose[0, 3]),
+           "tracker_stages_ms_per_frame": stages,
+           "what": "PoseTracker3D::compute of the reference (unmodified, oracle/_ref) driving adapters/ on the GPU"}
+    s.close()
+    return out
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle tier B) on every host core, one process per core."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref; the tier-B port only where the
+    prebuilt library is missing) on every host core, one process per core, on OUR arm's config: each step is a bounded
+    sample of that workload (4 pairs per core instead of --pairs), frames/s being independent of the batch size on a CPU."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import multiprocessing as mp
 
-    import cv2
     from vslam_b200 import configs, synth
     cfg = configs.BY_NAME[CONFIG_NAME]
     cores = len(os.sched_getaffinity(0))
-    per_step = max(cores * 2, 32)
-    distinct = min(args.distinct, per_step)
+    per_step = max(cores * 4, 32)
+    distinct = min(args.distinct or 64, per_step)
     left, right = synth.band_world_batch(cfg.camera, range(distinct), workers=min(cores, 32))
     idx = [i % distinct for i in range(per_step)]
     _cpu_init(left, right, args.rounds)
+    kind = _cpu_kind()
     with mp.get_context("fork").Pool(cores) as pool:
-        for _ in range(args.warmup):
+        for _ in range(max(args.warmup, 1)):
             pool.map(_cpu_pair, idx, chunksize=1)
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -161,23 +262,30 @@ def run_reference(args):
     value = per_step * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic",
-            "config": workload_config(args, per_step),
-            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic",
+            "config": workload_config(args, args.pairs),
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
                              "host": {"cpu_model": _cpu_model(), "nproc": cores},
-                             "sample": "%d pairs per step (%d distinct), one process per core, oracle tier B (cv2 %s)"
-                                       % (per_step, distinct, cv2.__version__)},
+                             "sample": "%d pairs per step (%d distinct) of the %d-pair workload, one process per core (%d): %s"
+                                       % (per_step, distinct, args.pairs, cores, _cpu_what(args.rounds))},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=_RESULT, flush=True)
     return 0
 
 
 def workload_config(args, pairs):
-    return {"workload": "configuration_kitti_fast.yaml: independent KITTI-shape 1241x376 stereo pairs as first frames "
-                        "(Localizing), FAST thr 15, bin 25, ORB-256, triangulation distance 25.6; + StereoUV "
-                        "linearize x%d per pair over the pair's framepoints" % args.rounds,
-            "pairs_per_gpu_per_step": pairs, "linearize_rounds": args.rounds, "image": "1241x376 u8",
-            "l2": "inputs larger than L2 (%.0f MB of images per step per GPU)" % (pairs * 2 * 1241 * 376 / 1e6)}
+    c = {"workload": "configuration_kitti_fast.yaml: independent KITTI-shape 1241x376 stereo pairs as first frames "
+                     "(Localizing), FAST thr 15, bin 25, ORB-256, triangulation distance 25.6; + StereoUV "
+                     "linearize x%d per pair over the pair's framepoints" % args.rounds,
+         "linearize_rounds": args.rounds, "image": "1241x376 u8"}
+    if args.scaling == "strong":
+        c["pairs_total_per_step"] = pairs
+        c["partition"] = "contiguous blocks of the %d pairs over the ranks (sharding.block_partition)" % pairs
+        c["l2"] = "inputs larger than L2 (%.0f MB of images per step in total)" % (pairs * 2 * 1241 * 376 / 1e6)
+    else:
+        c["pairs_per_gpu_per_step"] = pairs
+        c["l2"] = "inputs larger than L2 (%.0f MB of images per step per GPU)" % (pairs * 2 * 1241 * 376 / 1e6)
+    return c
 
 
 def bind_to_gpu_numa_node(torch, local_rank):
@@ -427,10 +535,42 @@ def sequence_latency(api, configs, synth, device):
     return out
 
 
+def sequence_multi(configs, synth, rank, world, device, barrier, dist, torch, dev, frames_n=100, passes=5):
+    """BASELINE.json configs[4]: 8 independent 1920x1080 sequences (seeds 8000 + rank, 100 frames, 84 x 47 = 3948 bins),
+    one per GPU: every rank drives its own sequence through initialize -> track -> StereoUVAligner initialize + converge
+    -> errors / inliers -> compute from C++14 (tools/sequence_runner.cpp).  Rank 0 first runs ALONE, then all ranks run
+    at once: efficiency = mean concurrent frames/s / rank 0's frames/s alone."""
+    cfg = configs.BY_NAME["hd"]
+    cam = synth.camera(cfg.camera)
+    bw = synth.BandWorld(cam.cols, cam.rows, 8000 + rank, max_frames=frames_n)
+    frames = [bw.pair(k) for k in range(frames_n)]
+    alone = native_sequence(cfg, cam, frames, passes=passes, device=device) if rank == 0 else None
+    barrier()
+    mine = native_sequence(cfg, cam, frames, passes=passes, device=device)
+    barrier()
+    fps = float(mine["frames_per_s"]) if mine else 0.0
+    if dist is not None:
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = fps
+        dist.all_reduce(t)
+        per_rank = [float(x) for x in t.tolist()]
+    else:
+        per_rank = [fps]
+    if rank != 0:
+        return None
+    out = {"workload": "%d-frame 1920x1080 band-world sequence per GPU (seeds 8000 + rank), bin 23, FAST thr 20..100; "
+                       "per frame initialize + track + StereoUVAligner converge + compute; sequence replayed %d times"
+                       % (frames_n, passes),
+           "per_rank_frames_per_s": per_rank, "aggregate_frames_per_s": sum(per_rank),
+           "rank0_alone": alone, "rank0_concurrent": mine,
+           "efficiency": (sum(per_rank) / len(per_rank)) / alone["frames_per_s"] if alone else None}
+    return out
+
+
 _RUNNER = {}
 
 
-def native_sequence(cfg, cam, frames, warmup=4):
+def native_sequence(cfg, cam, frames, warmup=4, acfg=None, passes=1, device=0):
     """builds tools/sequence_runner.cpp once (g++, C++14) and runs the tracked sequence through it; None when the
     compiler is missing or anything fails -- the number is informative, the run stays valid without it"""
     import tempfile
@@ -456,8 +596,18 @@ def native_sequence(cfg, cam, frames, warmup=4):
                 cfg.number_of_detectors_horizontal, int(cfg.enable_keypoint_binning), cfg.bin_size_pixels,
                 cfg.maximum_matching_distance_triangulation, cfg.minimum_disparity_pixels,
                 cfg.maximum_epipolar_search_offset_pixels, cam.fx, cam.fy, cam.cx, cam.cy, cam.bx, 15]
-        res = subprocess.run([_RUNNER["exe"], path, str(len(frames)), str(warmup)] + [repr(a) for a in args],
-                             capture_output=True, text=True, timeout=120)
+        if acfg is None:
+            from vslam_b200 import configs as _c
+            acfg = _c.ALIGNER_BY_NAME[cfg.name]
+        args += [acfg.error_delta_for_convergence, acfg.maximum_error_kernel, acfg.damping,
+                 acfg.minimum_number_of_inliers, acfg.maximum_reliable_depth_meters]
+        env = dict(os.environ)
+        if device:      # the runner uses device 0 of what it sees: show it this rank's GPU only
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            ids = visible.split(",") if visible else [str(i) for i in range(64)]
+            env["CUDA_VISIBLE_DEVICES"] = ids[device]
+        res = subprocess.run([_RUNNER["exe"], path, str(len(frames)), str(warmup)] + [repr(a) for a in args]
+                             + [str(passes)], capture_output=True, text=True, timeout=300, env=env)
         os.remove(path)
         if res.returncode != 0:
             return None
@@ -520,13 +670,25 @@ def main():
 
     cfg, acfg = configs.BY_NAME[CONFIG_NAME], configs.ALIGNER_BY_NAME[CONFIG_NAME]
     cam = synth.camera(cfg.camera)
-    P, R, K, W = args.pairs, args.rounds, args.steps, max(args.warmup, 0)
-    D = min(args.distinct, P)
+    R, K, W = args.rounds, args.steps, max(args.warmup, 0)
+    cores = len(os.sched_getaffinity(0))
+    if args.scaling == "strong":
+        # BASELINE.json configs[2] as written: args.pairs pairs in TOTAL, pair i (seed i) on rank floor(i * G / B)
+        part = sharding.block_partition(args.pairs, world, rank)
+        lo, hi = part.start, part.stop
+        P = hi - lo
+        D = min(args.distinct or P, P)
+        seeds = range(lo, lo + D)
+        P_total = args.pairs
+    else:
+        P = args.pairs
+        D = min(args.distinct or 256, P)
+        seeds = sharding.weak_seeds(D, rank)
+        P_total = world * P
 
     # ---- synthetic inputs: D distinct band-world pairs per rank (seeds disjoint across ranks), tiled to P pairs in
     # pinned host memory (every pair is its own memory and is processed independently)
-    cores = len(os.sched_getaffinity(0))
-    dl, dr = synth.band_world_batch(cfg.camera, sharding.weak_seeds(D, rank), workers=max(1, min(cores // world, 32)))
+    dl, dr = synth.band_world_batch(cfg.camera, seeds, workers=max(1, min(cores // world, 32)))
     left = api.pinned_empty((P, cam.rows, cam.cols))
     right = api.pinned_empty((P, cam.rows, cam.cols))
     for i in range(0, P, D):
@@ -565,7 +727,7 @@ def main():
         clk.end()
     ms = max_over_ranks(start.elapsed_time(end))
     launches = gen.launch_count - launches0
-    value = world * P * K / (ms * 1e-3)
+    value = P_total * K / (ms * 1e-3)
 
     # ---- end to end through the host-buffer API
     for _ in range(min(W, 2)):
@@ -576,7 +738,16 @@ def main():
         step_e2e()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * P * K / e2e_s
+    e2e_value = P_total * K / e2e_s
+    # copy-only control: the same pinned buffers through the same chunked pipeline with the kernels left out (only the
+    # re-pitch kernel runs) -- if this is as slow as e2e, the host -> device path is the limit, not the pipeline
+    gen.batch_upload(left, right)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        gen.batch_upload(left, right)
+    barrier()
+    h2d_s = max_over_ranks(time.perf_counter() - t0)
     h2d = 2 * P * cam.rows * cam.cols
     d2h = P * gen.out_capacity * api.FRAMEPOINT.itemsize + P * 8 * 4 + P * 32 * 8
 
@@ -624,20 +795,44 @@ def main():
                          "frac": path_bytes / (ms / K * 1e-3) / 1e9 / peak}}
 
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u8+f64", "data": "synthetic (band-world, %d distinct pairs per GPU tiled to %d)" % (D, P),
-            "config": workload_config(args, P), "clocks": clk.summary(),
+            "config": workload_config(args, args.pairs), "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s / K * 1e3, "host_placement": numa},
+                    "ms_per_step": e2e_s / K * 1e3, "host_placement": numa,
+                    "h2d_gbs_per_gpu": h2d * K / e2e_s / 1e9,
+                    "copy_only_control": {"ms_per_step": h2d_s / K * 1e3, "h2d_only_gbs_per_gpu": h2d * K / h2d_s / 1e9,
+                                          "h2d_only_gbs_all_gpus": world * h2d * K / h2d_s / 1e9,
+                                          "frames_per_s_if_copy_bound": P_total * K / h2d_s,
+                                          "e2e_over_copy_only": h2d_s / e2e_s,
+                                          "what": "vslam_fpg_batch_upload of the same pinned buffers, same chunks and "
+                                                  "lanes, no kernels but the row re-pitch; max over ranks"}},
             "gpu_launches": int(launches), "roofline": roofline,
             "counts": {"mean_descriptors_left": float(nl.mean()), "mean_matches": float(nm.mean()),
                        "mean_framepoints": float(nf.mean())}}
-    if rank == 0:
+    if not args.no_extras:
+        # BASELINE.json configs[4]: one independent 1920x1080 sequence per GPU, every rank runs its own
+        multi = sequence_multi(configs, synth, rank, world, local_rank, barrier, dist if world > 1 else None, torch, dev)
+        if rank == 0:
+            line["sequence_multi"] = multi
+    if rank == 0 and not args.no_extras:
         line["aligner_stress"] = aligner_stress(api, configs, synth, torch, dev)
         line["sequence"] = sequence_latency(api, configs, synth, local_rank)
         line["landmark_refinement"] = landmark_refinement(api, synth, local_rank)
     if rank == 0 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(dl, dr, R, args.cpu_sample)
+        if not args.no_extras:
+            # BASELINE.json configs[0]: the 200-frame KITTI sequence through the reference's tracker, CPU classes and
+            # GPU adapters side by side (same unmodified PoseTracker3D, same frames)
+            cam0 = synth.camera("kitti")
+            world0 = synth.BandWorld(cam0.cols, cam0.rows, 1, max_frames=200)
+            frames0 = [world0.pair(k) for k in range(200)]
+            seq_cpu = cpu_sequence_baseline(frames0)
+            line["cpu_baseline"]["sequence"] = seq_cpu
+            seq_gpu = gpu_sequence_through_the_reference_tracker(frames0)
+            line.setdefault("sequence", {})["reference_tracker_kitti_200"] = {
+                "gpu_adapters": seq_gpu, "cpu_reference": seq_cpu,
+                "speedup": (seq_gpu["value"] / seq_cpu["value"]) if seq_gpu and seq_cpu else None}
     if rank == 0:
         print(json.dumps(line), file=_RESULT, flush=True)
     gen.close()

@@ -225,6 +225,20 @@ class Session:
         self.configured = True
         return self
 
+    def reset(self):
+        self._ck(self.L.ref_reset(self.h))
+
+    def first_frame(self, left, right, rounds: int, T) -> int:
+        """bench.py's per-pair workload on the reference's classes; accumulates self.seconds_pose_optimization"""
+        if not hasattr(self, "_pose_seconds"):
+            self._pose_seconds = C.c_double(0)
+        return self._ck(self.L.ref_first_frame(self.h, _p(left), _p(right), left.strides[0], int(rounds), _p(_t12(T)),
+                                               C.byref(self._pose_seconds)))
+
+    @property
+    def seconds_pose_optimization(self) -> float:
+        return getattr(self, "_pose_seconds", C.c_double(0)).value
+
     # ---- generator ---------------------------------------------------------------------------------------------
     def initialize(self, left, right, tracking: bool = False):
         left, right = np.ascontiguousarray(left), np.ascontiguousarray(right)
@@ -381,3 +395,65 @@ class Session:
         nu = C.c_uint32(0)
         self._ck(self.L.ref_landmark_run(self.h, len(fi), _p(fi), _p(cc), len(poses), _p(poses), _p(world), C.byref(nu)))
         return world, nu.value
+
+
+# ---- OpenCV's own FAST / ORB behind the reference's cv:: calls (timing runs: the reference delegates these to OpenCV) ----
+_FAST_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int)
+_DESC_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_uint8))
+_backend_keepalive = []
+
+
+def install_cv2_backend(gpu: bool = False):
+    """cv::FastFeatureDetector::detect and cv::ORB::compute of the stand-in answer with python cv2 (single-threaded,
+    executables/app.cpp:96) instead of tier A: the speed of OpenCV's own SIMD code, the results identical bit for bit
+    (tests/test_oracle_vs_cv2.py).  Returns the cv2 version."""
+    import cv2
+    cv2.setNumThreads(0)
+    detectors, orb = {}, cv2.ORB_create()
+
+    def view(ptr, stride, cols, rows):
+        buf = (C.c_uint8 * (stride * (rows - 1) + cols)).from_address(ptr)
+        return np.lib.stride_tricks.as_strided(np.frombuffer(buf, np.uint8), (rows, cols), (stride, 1))
+
+    def fast(ptr, stride, cols, rows, threshold, xyr, capacity):
+        det = detectors.get(threshold)
+        if det is None:
+            det = detectors[threshold] = cv2.FastFeatureDetector_create(int(threshold))
+        kps = det.detect(view(ptr, stride, cols, rows))
+        n = len(kps)
+        if n > capacity:
+            return -1
+        if n:
+            out = np.ctypeslib.as_array(xyr, (n, 3))
+            out[:, :2] = cv2.KeyPoint_convert(kps)
+            out[:, 2] = np.fromiter((k.response for k in kps), np.float32, n)
+        return n
+
+    def describe(ptr, stride, cols, rows, xyr, n, desc):
+        if n == 0:
+            return 0
+        a = np.ctypeslib.as_array(xyr, (n, 3))
+        img = view(ptr, stride, cols, rows)
+        kps = cv2.KeyPoint_convert(np.ascontiguousarray(a[:, :2]), size=7.0)
+        kps, d = orb.compute(img, kps)
+        if d is None:
+            return 0
+        keep = (a[:, 0] >= 31) & (a[:, 0] < cols - 31) & (a[:, 1] >= 31) & (a[:, 1] < rows - 31)   # ORB's border filter
+        kept = a[keep]
+        assert len(kept) == len(d)
+        a[:len(kept)] = kept
+        np.ctypeslib.as_array(desc, (len(d), 32))[:] = d
+        return len(d)
+
+    f, o = _FAST_FN(fast), _DESC_FN(describe)
+    _backend_keepalive.extend([f, o])
+    L = lib(gpu)
+    L.vslam_shim_set_backend.argtypes = [_FAST_FN, _DESC_FN, C.c_void_p]
+    L.vslam_shim_set_backend(f, o, None)
+    return cv2.__version__
+
+
+def restore_default_backend(gpu: bool = False):
+    L = lib(gpu)
+    L.vslam_shim_set_backend.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.vslam_shim_set_backend(None, None, None)

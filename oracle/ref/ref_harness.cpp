@@ -760,6 +760,68 @@ extern "C" int ref_aligner_rounds(ref_session* s, int kind) {
   WITH_ALIGNER(return a->rounds)
 }
 
+// ---- the batched first-frame workload of bench.py (BASELINE configs[2]) on the reference's classes ------------------------
+extern "C" int ref_reset(ref_session* s) {
+  REF_TRY
+  // a fresh sequence: no frames, no landmarks, detector thresholds back at their configured minimum
+  // (base_framepoint_generator.cpp:244-251), tracker state as constructed
+  s->world->clear();
+  s->world->setCurrentFrame(nullptr);
+  s->world->setPreviousFrame(nullptr);
+  s->lost.clear();
+  if (s->generator) {
+    const StereoFramePointGeneratorParameters* g = s->parameters->stereo_framepoint_generator_parameters;
+    for (uint32_t r = 0; r < g->number_of_detectors_vertical; ++r)
+      for (uint32_t c = 0; c < g->number_of_detectors_horizontal; ++c)
+        s->generator->_detectors[r][c]->setThreshold(g->detector_threshold_minimum);
+  }
+  return 0;
+  REF_CATCH(-1)
+}
+
+extern "C" int ref_first_frame(ref_session* s, const uint8_t* left, const uint8_t* right, int stride, int rounds,
+                               const double T[12], double* seconds_pose_optimization) {
+  REF_TRY
+  if (ref_reset(s) < 0 || ref_fpg_initialize(s, left, right, stride, 0) < 0) return -1;
+  s->base_generator->compute(s->world->currentFrame());
+  // StereoUVAligner over the frame's own new points at a small prior error (previous frame == current frame, no
+  // landmarks: the first-frame analogue of pose_tracker_3d.cpp:124-126), `rounds` x linearize
+  const FramePointPointerVector& points = s->world->currentFrame()->points();
+  const int n = (int)points.size();
+  const double t0 = srrg_core::getTime();
+  if (n && !s->gpu) {
+    UV* a = s->uv;
+    const double max_depth = s->parameters->stereo_framepoint_generator_parameters->maximum_reliable_depth_meters;
+    a->_frame_previous = nullptr;
+    a->_frame_current = s->world->currentFrame();
+    a->_number_of_measurements = n;
+    a->_errors.resize(n);
+    a->_inliers.resize(n);
+    a->_information_matrix_vector.resize(n);
+    a->_weights_translation.resize(n);
+    a->_moving.resize(n);
+    a->_fixed.resize(n);
+    for (int u = 0; u < n; ++u) {                                   // stereouv_aligner.cpp:26-64
+      const FramePoint* p = points[u];
+      a->_information_matrix_vector[u].setIdentity();
+      a->_fixed[u] = Vector4(p->imageCoordinatesLeft().x(), p->imageCoordinatesLeft().y(), p->imageCoordinatesRight().x(),
+                             p->imageCoordinatesRight().y());
+      a->_moving[u] = p->cameraCoordinatesLeft();
+      a->_weights_translation[u] = std::min(max_depth / p->depthMeters(), 1.0);
+    }
+    a->_camera_calibration_matrix = s->camera_left->cameraMatrix();
+    a->_offset_camera_right = s->camera_right->baselineHomogeneous();
+    a->_number_of_rows_image = s->rows;
+    a->_number_of_cols_image = s->cols;
+    a->_minimum_reliable_depth_meters = s->parameters->stereo_framepoint_generator_parameters->minimum_depth_meters;
+    a->_previous_to_current = to_transform(T);
+    for (int r = 0; r < rounds; ++r) a->linearize(false);
+  }
+  if (seconds_pose_optimization) *seconds_pose_optimization += srrg_core::getTime() - t0;
+  return n;
+  REF_CATCH(-1)
+}
+
 // ---- tracker -------------------------------------------------------------------------------------------------------
 extern "C" int ref_tracker_process(ref_session* s, const uint8_t* left, const uint8_t* right, int stride) {
   REF_TRY

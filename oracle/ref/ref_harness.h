@@ -131,6 +131,12 @@ int ref_aligner_packed(ref_session*, int kind, double* moving, double* fixed, do
 int ref_aligner_count(ref_session*, int kind);
 int ref_aligner_rounds(ref_session*, int kind);         /* oneRound calls since the last load / initialize */
 
+/* ---- bench.py's batched first-frame workload (BASELINE configs[2]) on the reference's classes ---------------------- */
+int ref_reset(ref_session*);    /* a fresh sequence: world cleared, detector thresholds back at their minimum */
+/* reset -> initialize(Localizing) -> compute -> StereoUVAligner packed from the frame's points, `rounds` x linearize at T */
+int ref_first_frame(ref_session*, const uint8_t* left, const uint8_t* right, int stride, int rounds, const double T[12],
+                    double* seconds_pose_optimization);
+
 /* ---- the whole tracker (BASELINE configs[0]: executables/app's per-frame call) ------------------------------- */
 int ref_tracker_process(ref_session*, const uint8_t* left, const uint8_t* right, int stride);
 int ref_tracker_pose(ref_session*, double robot_to_world[12]);

@@ -224,7 +224,10 @@ Ptr<ORB> ORB::create(int, float, int, int edgeThreshold, int, int, int, int, int
 }
 void ORB::compute(InputArray image, std::vector<KeyPoint>& keypoints, OutputArray descriptors) {
   if (_edge_threshold != 31) unavailable("ORB with an edge threshold other than 31");
-  describe(g_orb, image, keypoints, descriptors, "ORB::compute");
+  // single-keypoint calls on a small region of interest (recoverPoints, stereo_framepoint_generator.cpp:769-795) stay on the
+  // built-in backend: an installed callback (python cv2) would add more call overhead than the work itself
+  const bool small = (long)image.rows * image.cols <= 128L * 128L;
+  describe(small ? default_orb : g_orb, image, keypoints, descriptors, "ORB::compute");
 }
 
 Ptr<BRISK> BRISK::create(int, int, float) { return makePtr<BRISK>(); }

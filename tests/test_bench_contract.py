@@ -25,9 +25,11 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True
     assert d["metric"].startswith("stereo frames/s") and d["value"] > 0 and d["n_gpus"] == 1
     assert d["steps"] == 1 and d["warmup"] == 0 and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    # the same config description as our own arm prints for the same flags (the driver's same_config check)
+    assert d["config"]["pairs_per_gpu_per_step"] == 4096 and d["scaling"] == "weak"
 
 
 def test_other_ranks_of_the_reference_arm_stay_silent():

@@ -1,11 +1,15 @@
 // sequence_runner.cpp -- the tracker's per-frame order (reference src/position_tracking/pose_tracker_3d.cpp:80, 239,
-// 210: initialize -> track against ALL points of the previous frame -> compute with the tracks pre-loaded) driven
-// from C++14 through include/vslam_b200.hpp, i.e. what the adapters do per frame minus the reference's object graph.
-// bench.py builds and runs it to report the single-sequence latency without the Python harness in the loop.
+// 124-126 / 355-357, 437-472, 210: initialize -> track against ALL points of the previous frame -> StereoUVAligner
+// initialize + converge over the tracks -> read errors / inliers as _prunePoints does -> compute with the tracks
+// pre-loaded) driven from C++14 through include/vslam_b200.hpp, i.e. what the adapters do per frame minus the reference's
+// object graph.  bench.py builds and runs it to report the single-sequence latency without the Python harness in the loop.
 //
-//   sequence_runner <frames.u8> <n_frames> <warmup> <23 configuration numbers, see below>
+//   sequence_runner <frames.u8> <n_frames> <warmup> <24 configuration numbers, see below> [passes]
+// passes > 1 replays the sequence from its first frame (fresh tracker state) so that a short sequence gives a timed
+// region long enough to overlap with the other GPUs' runs (BASELINE configs[4]: one sequence per GPU).
 // frames.u8: [n_frames][2][rows][cols] u8.  Prints one JSON object.
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -14,10 +18,11 @@
 #include "vslam_b200.hpp"
 
 int main(int argc, char** argv) {
-  if (argc != 4 + 19) {
+  if (argc != 4 + 24 && argc != 4 + 25) {
     std::fprintf(stderr, "usage: sequence_runner frames.u8 n_frames warmup rows cols tolerance thr_min thr_max max_change "
                          "detectors_v detectors_h binning bin_size max_distance min_disparity max_offset fx fy cx cy bx "
-                         "projection_tracking_distance descriptor_distance_tracking\n");
+                         "projection_tracking_distance error_delta_for_convergence maximum_error_kernel damping "
+                         "minimum_number_of_inliers maximum_reliable_depth_meters\n");
     return 2;
   }
   try {
@@ -35,6 +40,14 @@ int main(int argc, char** argv) {
     c.fx = std::atof(a[13]); c.fy = std::atof(a[14]); c.cx = std::atof(a[15]); c.cy = std::atof(a[16]); c.bx = std::atof(a[17]);
     const int tracking_distance = std::atoi(a[18]);
     const double descriptor_distance = 25.6;
+    vslam_aligner_parameters ap = {};
+    ap.error_delta_for_convergence = std::atof(a[19]);
+    ap.maximum_error_kernel = std::atof(a[20]);
+    ap.damping = std::atof(a[21]);
+    ap.maximum_number_of_iterations = 1000;
+    ap.minimum_number_of_inliers = std::atoi(a[22]);
+    const double maximum_reliable_depth = std::atof(a[23]);
+    const int passes = argc == 4 + 25 ? std::atoi(a[24]) : 1;
     const size_t image_bytes = (size_t)c.rows * c.cols;
 
     // page-locked frame buffers (vslam_host_alloc): the H2D copy of initialize() is one asynchronous DMA
@@ -53,6 +66,15 @@ int main(int argc, char** argv) {
     const double tx = -(-c.bx / c.fx) / 4;
     const std::array<double, 12> motion{{1, 0, 0, tx, 0, 1, 0, 0, 0, 0, 1, 0}};
 
+    // StereoUVAligner wired as slam_assembly.cpp:68-71: minimum reliable depth = the generator's minimum_depth_meters
+    vslam::StereoUVAligner aligner(ap, 1 << 16);
+    const double K[9] = {c.fx, 0, c.cx, 0, c.fy, c.cy, 0, 0, 1};
+    const double baseline[3] = {c.bx, 0, 0};
+    std::vector<double> moving, fixed, omega, weights;
+    double s_align = 0;
+    long n_rounds = 0, n_inliers = 0;
+    double worst_translation_error = 0;
+
     vslam::Frame previous, current;
     bool have_previous = false;
     double seconds = 0, s_initialize = 0, s_track = 0, s_compute = 0, s_assemble = 0;
@@ -61,6 +83,8 @@ int main(int argc, char** argv) {
       return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count();
     };
     std::vector<int32_t> lost;
+    for (int pass = 0; pass < passes; ++pass) {
+    have_previous = false;
     for (int k = 0; k < n_frames; ++k) {
       const auto t0 = std::chrono::steady_clock::now();
       current.status = k == 0 ? vslam::Frame::Localizing : vslam::Frame::Tracking;
@@ -73,6 +97,33 @@ int main(int argc, char** argv) {
       const auto t_track = std::chrono::steady_clock::now();
       if (have_previous) generator.track(&current, &previous, motion, lost, false);
       const double d_track = since(t_track);
+      // pose optimisation over the tracks (pose_tracker_3d.cpp:355-357): StereoUVAligner::initialize packs per point
+      // (stereouv_aligner.cpp:26-64), converge() runs fused on the device, then errors / inliers as _prunePoints reads them
+      const auto t_align = std::chrono::steady_clock::now();
+      int rounds = 0, inliers = 0;
+      if (have_previous && !current.tracks.empty()) {
+        const size_t n = current.tracks.size();
+        moving.resize(3 * n); fixed.resize(4 * n); omega.assign(n, 1.0); weights.resize(n);
+        for (size_t u = 0; u < n; ++u) {
+          const vslam_track& t = current.tracks[u];
+          const vslam_previous_point& q = previous.previous_points[t.index_previous];
+          for (int d = 0; d < 3; ++d) moving[3 * u + d] = q.camera_left[d];
+          fixed[4 * u] = t.xl; fixed[4 * u + 1] = t.yl; fixed[4 * u + 2] = t.xr; fixed[4 * u + 3] = t.yr;
+          const double w = maximum_reliable_depth / t.camera[2];
+          weights[u] = w < 1.0 ? w : 1.0;
+        }
+        aligner.initialize((int32_t)n, moving.data(), fixed.data(), omega.data(), weights.data(), K, baseline, c.rows,
+                           c.cols, 0.1, motion);
+        aligner.converge();
+        const std::vector<bool> flags = aligner.inliers();
+        const std::vector<double> errors = aligner.errors();
+        (void)flags; (void)errors;
+        rounds = aligner.numberOfRounds();
+        inliers = aligner.numberOfInliers();
+        const double e = std::fabs(aligner.previousToCurrent()[3] - tx);
+        if ((k >= warmup || pass > 0) && e > worst_translation_error) worst_translation_error = e;
+      }
+      const double d_align = since(t_align);
       const auto t_compute = std::chrono::steady_clock::now();
       generator.compute(&current);
       const double d_compute = since(t_compute);
@@ -94,10 +145,13 @@ int main(int argc, char** argv) {
       for (const vslam_track& t : current.tracks) fill(t.camera, t.index_left, t.index_right, t.epipolar_offset);
       for (const vslam_framepoint& p : current.points) fill(p.camera, p.index_left, p.index_right, p.epipolar_offset);
       const auto t1 = std::chrono::steady_clock::now();
-      if (k >= warmup) {
+      if (k >= warmup || pass > 0) {
         seconds += std::chrono::duration<double>(t1 - t0).count();
         s_initialize += d_initialize;
         s_track += d_track;
+        s_align += d_align;
+        n_rounds += rounds;
+        n_inliers += inliers;
         s_compute += d_compute;
         s_assemble += since(t_assemble);
         n_previous += have_previous ? (long)previous.previous_points.size() : 0;
@@ -107,13 +161,16 @@ int main(int argc, char** argv) {
       std::swap(previous, current);
       have_previous = true;
     }
-    const int timed = n_frames - warmup;
+    }
+    const int timed = n_frames * passes - warmup;
     std::printf("{\"frames_per_s\": %.3f, \"ms_per_frame\": %.6f, \"mean_previous_points\": %.2f, \"mean_tracks\": %.2f, "
                 "\"mean_new_points\": %.2f, \"frames\": %d, \"us_initialize_with_feature_download\": %.1f, \"us_track\": %.1f, "
-                "\"us_compute\": %.1f, \"us_assemble_previous_points\": %.1f}\n",
+                "\"us_align\": %.1f, \"us_compute\": %.1f, \"us_assemble_previous_points\": %.1f, \"mean_aligner_rounds\": %.2f, "
+                "\"mean_aligner_inliers\": %.1f, \"worst_translation_error_m\": %.3g}\n",
                 timed / seconds, seconds / timed * 1e3, (double)n_previous / timed, (double)n_tracks / timed,
-                (double)n_new / timed, timed, s_initialize / timed * 1e6, s_track / timed * 1e6, s_compute / timed * 1e6,
-                s_assemble / timed * 1e6);
+                (double)n_new / timed, timed, s_initialize / timed * 1e6, s_track / timed * 1e6, s_align / timed * 1e6,
+                s_compute / timed * 1e6, s_assemble / timed * 1e6, (double)n_rounds / timed, (double)n_inliers / timed,
+                worst_translation_error);
     vslam_host_free(frames);
   } catch (const std::exception& e) {
     std::fprintf(stderr, "FAILED: %s\n", e.what());
