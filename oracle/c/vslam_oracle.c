@@ -1,6 +1,6 @@
 /*
  * vslam_oracle.c -- CPU restatement ("Tier A" oracle) of the reference hot path.  See vslam_oracle.h for
- * the status header (TEST INFRASTRUCTURE ONLY; "parity unpinned" against a reference build).
+ * the status header (TEST INFRASTRUCTURE ONLY; pinned against oracle/_ref, the reference's own translation units).
  *
  * Compile with -ffp-contract=off: every fused multiply-add below is an explicit fmaf()/none, so that the
  * float blur and the double triangulation have ONE defined evaluation order (the CUDA kernels use the

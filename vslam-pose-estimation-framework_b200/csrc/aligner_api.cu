@@ -24,45 +24,75 @@ struct vslam_aligner {
   int n = 0;
   int fixed_dim = 4, omega_dim = 1;
   cudaStream_t stream = nullptr;
-  double* d_moving = nullptr;
-  double* d_fixed = nullptr;
-  double* d_omega = nullptr;
-  double* d_wt = nullptr;
-  double* d_errors = nullptr;
-  uint8_t* d_inliers = nullptr;
+  // ONE device block and its pinned mirror, laid out so that a frame costs one H2D copy, one kernel and one D2H copy:
+  //   [ errors (stride f64) | inliers (stride u8, padded) ]  <- ends at kHeader; the OUT region of the last upload
+  //   [ GnControl (512 B) | system (32 f64) ]                <- header at a fixed offset
+  //   [ moving 3 | fixed 4|3 | omega 1|2 | wt 1 ] x stride   <- the IN region: SoA planes with stride = n rounded to 32
+  // H2D = header + IN (contiguous), D2H = OUT + header (contiguous).  `stride` follows the problem size: a frame with
+  // 700 tracks moves 50 KB, not planes of max_points entries.
+  uint8_t* d_io = nullptr;
+  uint8_t* h_io = nullptr;      // pinned
+  size_t header_offset = 0;     // = out_bytes(max_points)
+  int stride = 32;
+  bool in_dirty = false;        // the pinned IN region is newer than the device's
+  bool host_out_valid = false;  // the pinned OUT region holds errors / inliers of the last device run
   double* d_partials = nullptr;
-  double* d_system = nullptr;
   unsigned int* d_ticket = nullptr;
-  double* h_stage = nullptr;    // pinned SoA staging, (3 + fixed_dim + omega_dim + 1) * max_points
-  double* h_system = nullptr;   // pinned [32]
   AlignerCamera cam;
   int max_grid = 0;
   int resident_blocks = 0;      // co-resident CTAs of the cooperative kernel = grid cap of both linearize paths
-  GnControl* d_ctl = nullptr;
-  GnControl* h_ctl = nullptr;   // pinned
   int64_t launches = 0;
   bool uploaded = false;
 };
 
 namespace {
+constexpr size_t kCtlBytes = 512, kHeaderBytes = 768;
+static_assert(sizeof(GnControl) <= kCtlBytes, "GnControl fits its slot");
+size_t out_bytes(int stride) { return (size_t)stride * 8 + (((size_t)stride + 7) & ~(size_t)7); }
+size_t in_bytes(const vslam_aligner* h, int stride) { return (size_t)stride * 8 * (3 + h->fixed_dim + h->omega_dim + 1); }
+template <class T> T* at(uint8_t* base, size_t off) { return reinterpret_cast<T*>(base + off); }
+GnControl* ctl_of(uint8_t* base, const vslam_aligner* h) { return at<GnControl>(base, h->header_offset); }
+double* system_of(uint8_t* base, const vslam_aligner* h) { return at<double>(base, h->header_offset + kCtlBytes); }
+double* errors_of(uint8_t* base, const vslam_aligner* h) { return at<double>(base, h->header_offset - out_bytes(h->stride)); }
+uint8_t* inliers_of(uint8_t* base, const vslam_aligner* h) {
+  return base + h->header_offset - out_bytes(h->stride) + (size_t)h->stride * 8;
+}
+double* planes_of(uint8_t* base, const vslam_aligner* h) { return at<double>(base, h->header_offset + kHeaderBytes); }
+}  // namespace
+
+namespace {
 
 AlignerBuffers buffers(const vslam_aligner* h) {
   AlignerBuffers b;
-  b.moving = h->d_moving;
-  b.fixed = h->d_fixed;
-  b.omega = h->d_omega;
-  b.wt = h->d_wt;
-  b.errors = h->d_errors;
-  b.inliers = h->d_inliers;
+  const size_t S = h->stride;
+  double* planes = planes_of(h->d_io, h);
+  b.moving = planes;
+  b.fixed = planes + 3 * S;
+  b.omega = planes + (3 + h->fixed_dim) * S;
+  b.wt = planes + (3 + h->fixed_dim + h->omega_dim) * S;
+  b.errors = errors_of(h->d_io, h);
+  b.inliers = inliers_of(h->d_io, h);
   b.partials = h->d_partials;
-  b.system = h->d_system;
+  b.system = system_of(h->d_io, h);
   b.ticket = h->d_ticket;
-  b.stride = h->max_points;
+  b.stride = h->stride;
   return b;
 }
 
+// header (+ correspondences when they changed) host -> device: ONE copy
+int push_inputs(vslam_aligner* h, bool with_header) {
+  if (h->in_dirty) {
+    CUDA_TRY(cudaMemcpyAsync(h->d_io + h->header_offset, h->h_io + h->header_offset, kHeaderBytes + in_bytes(h, h->stride),
+                             cudaMemcpyHostToDevice, h->stream));
+    h->in_dirty = false;
+  } else if (with_header) {
+    CUDA_TRY(cudaMemcpyAsync(h->d_io + h->header_offset, h->h_io + h->header_offset, kCtlBytes, cudaMemcpyHostToDevice, h->stream));
+  }
+  return VSLAM_OK;
+}
+
 void unpack_system(const vslam_aligner* h, vslam_linear_system* s) {
-  const double* v = h->h_system;
+  const double* v = system_of(h->h_io, h);
   int k = 0;
   for (int i = 0; i < 6; ++i)
     for (int j = i; j < 6; ++j, ++k) s->H[i * 6 + j] = s->H[j * 6 + i] = v[k];
@@ -75,10 +105,13 @@ void unpack_system(const vslam_aligner* h, vslam_linear_system* s) {
 int linearize_async(vslam_aligner* h, const double T[12], int ignore_outliers, double kernel) {
   if (!h->uploaded) return fail(VSLAM_ERR_STATE, "linearize before upload");
   CUDA_TRY(cudaSetDevice(h->device));
+  h->host_out_valid = false;
   if (h->n == 0) {
-    CUDA_TRY(cudaMemsetAsync(h->d_system, 0, sizeof(double) * 32, h->stream));
+    CUDA_TRY(cudaMemsetAsync(system_of(h->d_io, h), 0, sizeof(double) * 32, h->stream));
     return VSLAM_OK;
   }
+  int rc = push_inputs(h, false);
+  if (rc) return rc;
   launch_linearize(h->kind, h->n, buffers(h), h->cam, T, ignore_outliers, kernel, aligner_grid(h->n, h->resident_blocks),
                    h->stream);
   ++h->launches;
@@ -87,7 +120,7 @@ int linearize_async(vslam_aligner* h, const double T[12], int ignore_outliers, d
 }
 
 int read_system(vslam_aligner* h, vslam_linear_system* s) {
-  CUDA_TRY(cudaMemcpyAsync(h->h_system, h->d_system, sizeof(double) * 32, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(system_of(h->h_io, h), system_of(h->d_io, h), sizeof(double) * 32, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   if (s) unpack_system(h, s);
   return VSLAM_OK;
@@ -130,19 +163,13 @@ int vslam_aligner_create(int kind, int32_t max_points, int device, vslam_aligner
   auto dalloc = [&](void** p, size_t bytes) {
     if (ok && cudaMalloc(p, bytes) != cudaSuccess) ok = false;
   };
-  dalloc((void**)&h->d_moving, sizeof(double) * 3 * N);
-  dalloc((void**)&h->d_fixed, sizeof(double) * h->fixed_dim * N);
-  dalloc((void**)&h->d_omega, sizeof(double) * h->omega_dim * N);
-  dalloc((void**)&h->d_wt, sizeof(double) * N);
-  dalloc((void**)&h->d_errors, sizeof(double) * N);
-  dalloc((void**)&h->d_inliers, N);
+  h->header_offset = (out_bytes((int)N) + 255) & ~(size_t)255;
+  const size_t io_bytes = h->header_offset + kHeaderBytes + in_bytes(h, (int)N);
+  dalloc((void**)&h->d_io, io_bytes);
   dalloc((void**)&h->d_partials, sizeof(double) * 32 * h->max_grid);
-  dalloc((void**)&h->d_system, sizeof(double) * 32);
   dalloc((void**)&h->d_ticket, sizeof(unsigned int));
-  dalloc((void**)&h->d_ctl, sizeof(GnControl));
-  if (ok && cudaMallocHost((void**)&h->h_ctl, sizeof(GnControl)) != cudaSuccess) ok = false;
-  if (ok && cudaMallocHost((void**)&h->h_stage, sizeof(double) * (3 + h->fixed_dim + h->omega_dim + 1) * N) != cudaSuccess) ok = false;
-  if (ok && cudaMallocHost((void**)&h->h_system, sizeof(double) * 32) != cudaSuccess) ok = false;
+  if (ok && cudaMallocHost((void**)&h->h_io, io_bytes) != cudaSuccess) ok = false;
+  if (ok) std::memset(h->h_io + h->header_offset, 0, kHeaderBytes);
   if (ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) ok = false;
   if (ok && cudaMemset(h->d_ticket, 0, sizeof(unsigned int)) != cudaSuccess) ok = false;
   if (!ok) {
@@ -158,10 +185,8 @@ int vslam_aligner_destroy(vslam_aligner* h) {
   if (!h) return VSLAM_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  cudaFree(h->d_moving); cudaFree(h->d_fixed); cudaFree(h->d_omega); cudaFree(h->d_wt); cudaFree(h->d_errors);
-  cudaFree(h->d_inliers); cudaFree(h->d_partials); cudaFree(h->d_system); cudaFree(h->d_ticket);
-  cudaFree(h->d_ctl);
-  cudaFreeHost(h->h_stage); cudaFreeHost(h->h_system); cudaFreeHost(h->h_ctl);
+  cudaFree(h->d_io); cudaFree(h->d_partials); cudaFree(h->d_ticket);
+  cudaFreeHost(h->h_io);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return VSLAM_OK;
@@ -170,16 +195,18 @@ int vslam_aligner_destroy(vslam_aligner* h) {
 int vslam_aligner_upload(vslam_aligner* h, int32_t n, const double* moving, const double* fixed, const double* omega,
                          const double* wt, const double K[9], const double baseline[3], int32_t rows, int32_t cols,
                          double minimum_depth) {
+  VSLAM_NVTX("vslam_aligner_upload [StereoUVAligner::initialize]");
   if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null handle");
   if (n < 0 || n > h->max_points) return fail(VSLAM_ERR_CAPACITY, "n=%d outside [0, max_points=%d]", n, h->max_points);
   if (n && (!moving || !fixed || !omega || !wt)) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null correspondence array");
   if (!K) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null camera matrix");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaStreamSynchronize(h->stream));   // the staging buffer may still feed a previous copy
-  const size_t N = h->max_points;
-  // AoS (the reference's std::vector<Vector3>, ...) -> SoA planes, so that the kernel's loads coalesce
-  double* s = h->h_stage;
-  double* sm = s;
+  // AoS (the reference's std::vector<Vector3>, ...) -> SoA planes with stride = n rounded up to 32, so that the kernel's
+  // loads coalesce and the copy moves the problem, not the capacity.  The copy itself travels with the next launch.
+  h->stride = std::max(32, (n + 31) & ~31);
+  const size_t N = h->stride;
+  double* sm = planes_of(h->h_io, h);
   double* sf = sm + 3 * N;
   double* so = sf + h->fixed_dim * N;
   double* sw = so + h->omega_dim * N;
@@ -189,12 +216,8 @@ int vslam_aligner_upload(vslam_aligner* h, int32_t n, const double* moving, cons
     for (int k = 0; k < h->omega_dim; ++k) so[k * N + u] = omega[h->omega_dim * u + k];
     sw[u] = wt[u];
   }
-  if (n) {
-    CUDA_TRY(cudaMemcpyAsync(h->d_moving, sm, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(h->d_fixed, sf, sizeof(double) * h->fixed_dim * N, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(h->d_omega, so, sizeof(double) * h->omega_dim * N, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(h->d_wt, sw, sizeof(double) * N, cudaMemcpyHostToDevice, h->stream));
-  }
+  h->in_dirty = n > 0;
+  h->host_out_valid = false;
   for (int i = 0; i < 9; ++i) h->cam.K[i] = K[i];
   for (int i = 0; i < 3; ++i) h->cam.baseline[i] = baseline ? baseline[i] : 0.0;
   h->cam.rows = rows;
@@ -206,6 +229,7 @@ int vslam_aligner_upload(vslam_aligner* h, int32_t n, const double* moving, cons
 }
 
 int vslam_aligner_linearize(vslam_aligner* h, const double T[12], int ignore_outliers, double kernel, vslam_linear_system* s) {
+  VSLAM_NVTX("vslam_aligner_linearize");
   if (!h || !T || !s) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
   int rc = linearize_async(h, T, ignore_outliers, kernel);
   if (rc) return rc;
@@ -224,22 +248,30 @@ int vslam_aligner_read_system(vslam_aligner* h, vslam_linear_system* s) {
 }
 
 int vslam_aligner_download(vslam_aligner* h, double* errors, uint8_t* inliers) {
+  VSLAM_NVTX("vslam_aligner_download [errors / inliers]");
   if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null handle");
   CUDA_TRY(cudaSetDevice(h->device));
-  if (errors && h->n) CUDA_TRY(cudaMemcpyAsync(errors, h->d_errors, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
-  if (inliers && h->n) CUDA_TRY(cudaMemcpyAsync(inliers, h->d_inliers, h->n, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->n == 0) return VSLAM_OK;
+  if (!h->host_out_valid) {   // (the fused converge brings errors / inliers back with its own result copy)
+    CUDA_TRY(cudaMemcpyAsync(errors_of(h->h_io, h), errors_of(h->d_io, h), out_bytes(h->stride), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->host_out_valid = true;
+  }
+  if (errors) std::memcpy(errors, errors_of(h->h_io, h), sizeof(double) * h->n);
+  if (inliers) std::memcpy(inliers, inliers_of(h->h_io, h), h->n);
   return VSLAM_OK;
 }
 
 int vslam_aligner_one_round(vslam_aligner* h, const vslam_aligner_parameters* p, int ignore_outliers, double T[12],
                             vslam_linear_system* s) {
+  VSLAM_NVTX("vslam_aligner_one_round");
   if (!h || !p || !T || !s) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
   return one_round(h, p, ignore_outliers, T, s);
 }
 
 int vslam_aligner_converge(vslam_aligner* h, const vslam_aligner_parameters* p, double T[12], vslam_linear_system* s,
                            double* information, int32_t* has_converged, int32_t* number_of_rounds) {
+  VSLAM_NVTX("vslam_aligner_converge [PoseTracker3D::compute->pose_optim]");
   if (!h || !p || !T || !s) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
   double total_error_previous = 0;                                            // :213 / :197
   int converged = 0, rounds = 0, rc;
@@ -272,12 +304,13 @@ int vslam_aligner_converge(vslam_aligner* h, const vslam_aligner_parameters* p, 
 
 int vslam_aligner_converge_fused(vslam_aligner* h, const vslam_aligner_parameters* p, double T[12], vslam_linear_system* s,
                                  double* information, int32_t* has_converged, int32_t* number_of_rounds) {
+  VSLAM_NVTX("vslam_aligner_converge_fused [PoseTracker3D::compute->pose_optim]");
   if (!h || !p || !T || !s) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
   if (!h->uploaded) return fail(VSLAM_ERR_STATE, "converge before upload");
   CUDA_TRY(cudaSetDevice(h->device));
   if (h->n == 0 || p->maximum_number_of_iterations < 1)   // nothing to iterate on the device: the stepwise driver
     return vslam_aligner_converge(h, p, T, s, information, has_converged, number_of_rounds);
-  GnControl* c = h->h_ctl;
+  GnControl* c = ctl_of(h->h_io, h);
   std::memset(c, 0, sizeof(*c));
   for (int i = 0; i < 12; ++i) c->T[i] = T[i];
   GnParams gp;
@@ -286,12 +319,17 @@ int vslam_aligner_converge_fused(vslam_aligner* h, const vslam_aligner_parameter
   gp.damping = p->damping;
   gp.max_iterations = p->maximum_number_of_iterations;
   gp.inlier_gate = h->kind == VSLAM_ALIGNER_STEREO_UV ? p->minimum_number_of_inliers : 100;   // :224 / :208
-  CUDA_TRY(cudaMemcpyAsync(h->d_ctl, c, sizeof(GnControl), cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(launch_converge(h->kind, h->n, buffers(h), h->cam, gp, h->d_ctl, aligner_grid(h->n, h->resident_blocks), h->stream));
-  ++h->launches;
-  CUDA_TRY(cudaMemcpyAsync(c, h->d_ctl, sizeof(GnControl), cudaMemcpyDeviceToHost, h->stream));
-  int rc = read_system(h, s);   // synchronises
+  // one copy in (control block + the correspondences if they are new), one kernel, one copy out (errors, inliers, control
+  // block, system) and one synchronisation
+  int rc = push_inputs(h, true);
   if (rc) return rc;
+  CUDA_TRY(launch_converge(h->kind, h->n, buffers(h), h->cam, gp, ctl_of(h->d_io, h), aligner_grid(h->n, h->resident_blocks), h->stream));
+  ++h->launches;
+  CUDA_TRY(cudaMemcpyAsync(errors_of(h->h_io, h), errors_of(h->d_io, h), out_bytes(h->stride) + kHeaderBytes,
+                           cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->host_out_valid = true;
+  unpack_system(h, s);
   for (int i = 0; i < 12; ++i) T[i] = c->T[i];
   for (int i = 0; i < 6; ++i) s->H[i * 6 + i] += p->damping * h->n;   // _H after oneRound carries the damping (:196)
   if (information && c->converged) std::memcpy(information, c->H, sizeof(double) * 36);

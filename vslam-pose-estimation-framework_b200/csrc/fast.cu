@@ -7,6 +7,8 @@
 // the device-canonical feature order is ascending (row, col), the order the stereo scan consumes.
 //
 // FAST-9/16 semantics (OpenCV, TYPE_9_16, nonmaxSuppression=true): SURVEY.md Appendix A.1.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace vslam {
@@ -145,27 +147,25 @@ __device__ __forceinline__ uint32_t absdiff_gt(uint32_t ring, uint32_t center, u
 //   phase 3  (after one block barrier) strict 3x3 non-maximum suppression of the listed corners -> keypoint bit mask
 constexpr int kListCap = RPW * CW + 8;   // candidates of one warp: RPW rows x 130 columns
 
-template <bool INTERIOR>
-__device__ __forceinline__ uint32_t compass_pretest(const uint8_t (*s_img)[SW], int sy, int wi, uint32_t cadd, int x0,
-                                                    int y0, int ay0, int ay1, int cx_lo, int cx_hi) {
+// compass pre-test of the four pixels of word `wi` in pre-test row `sy`: bit 7 of byte b = pixel b passes
+__device__ __forceinline__ uint32_t compass_pretest(const uint8_t (*s_img)[SW], int sy, int wi, uint32_t cadd) {
   const uint32_t* rc = reinterpret_cast<const uint32_t*>(&s_img[sy + 3][0]) + 3 + wi;
   const uint32_t c = rc[0];
   const uint32_t rn = rc[-3 * (SW / 4)];                   // y - 3
   const uint32_t rs = rc[3 * (SW / 4)];                    // y + 3
   const uint32_t re = __funnelshift_r(c, rc[1], 24);       // x + 3
   const uint32_t rw = __funnelshift_r(rc[-1], c, 8);       // x - 3
-  uint32_t m = (absdiff_gt(rn, c, cadd) | absdiff_gt(rs, c, cadd)) & (absdiff_gt(re, c, cadd) | absdiff_gt(rw, c, cadd));
-  if (!INTERIOR) {   // tiles touching the border of the region: drop rows / columns outside the keypoint area
-    const int iy = y0 - 1 + sy;
-    if (iy < ay0 || iy > ay1) return 0u;
-    const int bx = x0 - 4 + 4 * wi;
-    const int lo = cx_lo - bx, hi = cx_hi - bx;
-    uint32_t keep = 0x80808080u;
-    if (lo > 0) keep = lo > 3 ? 0u : keep << (8 * lo);
-    if (hi < 3) keep = hi < 0 ? 0u : keep & (0x80808080u >> (8 * (3 - hi)));
-    m &= keep;
-  }
-  return m;
+  return (absdiff_gt(rn, c, cadd) | absdiff_gt(rs, c, cadd)) & (absdiff_gt(re, c, cadd) | absdiff_gt(rw, c, cadd));
+}
+
+// tiles touching the border of the region: the columns of word `wi` inside [cx_lo, cx_hi] (constant over the rows of a tile)
+__device__ __forceinline__ uint32_t keep_columns(int x0, int wi, int cx_lo, int cx_hi) {
+  const int bx = x0 - 4 + 4 * wi;
+  const int lo = cx_lo - bx, hi = cx_hi - bx;
+  uint32_t keep = 0x80808080u;
+  if (lo > 0) keep = lo > 3 ? 0u : keep << (8 * lo);
+  if (hi < 3) keep = hi < 0 ? 0u : keep & (0x80808080u >> (8 * (3 - hi)));
+  return keep;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -246,21 +246,28 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(const __grid_constant__ C
     if (interior) {
 #pragma unroll
       for (int it = 0; it < RPW; ++it) {
-        const uint32_t m = compass_pretest<true>(s_img, RPW * warp + it, lane + 1, cadd, x0, y0, ay0, ay1, cx_lo, cx_hi);
+        const uint32_t m = compass_pretest(s_img, RPW * warp + it, lane + 1, cadd);
         flags |= ((((m >> 7) & 0x01010101u) * 0x01020408u) >> 24) << (4 * it);
       }
       uint32_t m = 0;
       if (lane < 2 * RPW)   // of the left halo word only x0-1 (byte 3) is needed, of the right one only x0+128 (byte 0)
-        m = compass_pretest<true>(s_img, hsy, hwi, cadd, x0, y0, ay0, ay1, cx_lo, cx_hi) & (hwi ? 0x00000080u : 0x80000000u);
+        m = compass_pretest(s_img, hsy, hwi, cadd) & (hwi ? 0x00000080u : 0x80000000u);
       flags |= ((((m >> 7) & 0x01010101u) * 0x01020408u) >> 24) << (4 * RPW);
     } else {
-#pragma unroll 1
+      // tiles on the border of the region (30 of the 70 tiles of a KITTI image): the border only masks columns (the same
+      // for every row of the tile) and whole rows -- both hoisted out of the loop, which unrolls like the interior one
+      const uint32_t keep = keep_columns(x0, lane + 1, cx_lo, cx_hi);
+      const uint32_t keep_halo = keep_columns(x0, hwi, cx_lo, cx_hi);
+      const int sy_lo = ay0 - (y0 - 1), sy_hi = ay1 - (y0 - 1);
+#pragma unroll
       for (int it = 0; it < RPW; ++it) {
-        const uint32_t m = compass_pretest<false>(s_img, RPW * warp + it, lane + 1, cadd, x0, y0, ay0, ay1, cx_lo, cx_hi);
+        const int sy = RPW * warp + it;
+        uint32_t m = compass_pretest(s_img, sy, lane + 1, cadd) & keep;
+        if (sy < sy_lo || sy > sy_hi) m = 0u;
         flags |= ((((m >> 7) & 0x01010101u) * 0x01020408u) >> 24) << (4 * it);
       }
       uint32_t m = 0;
-      if (lane < 2 * RPW) m = compass_pretest<false>(s_img, hsy, hwi, cadd, x0, y0, ay0, ay1, cx_lo, cx_hi);
+      if (lane < 2 * RPW && hsy >= sy_lo && hsy <= sy_hi) m = compass_pretest(s_img, hsy, hwi, cadd) & keep_halo;
       flags |= ((((m >> 7) & 0x01010101u) * 0x01020408u) >> 24) << (4 * RPW);
     }
     // ... then ONE warp scan places the lanes' candidates in the list (the order is irrelevant), instead of four

@@ -32,6 +32,7 @@ constexpr int kLanes = 2;   // chunk pipelines that overlap copies and the small
 
 struct Lane {
   cudaStream_t stream = nullptr;
+
   uint8_t* blurred = nullptr;   // [2*chunk][rows][pitch]
   uint32_t* mask = nullptr;     // [2*chunk][rows][mask_words]
   CUtensorMap blurred_map;      // TMA descriptor of `blurred` (box = describe tile)
@@ -57,6 +58,7 @@ struct vslam_fpg {
   Geometry g;
   int n_passes = 1;
   int chunk = 1;              // pairs per pipeline chunk
+  int describe_sub_chunk = 64;   // pairs per blur -> rBRIEF launch pair (L2 residency of the blurred scratch)
   int max_batch = 1;
   int out_cap = 0;            // framepoint records per pair
   HostRegion regions[kMaxRegions];
@@ -181,9 +183,20 @@ void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n, const int32_t*
     launch_describe_brief(h->g, boxsum, h->d_brief_tests, h->b.kp_xy + (size_t)2 * p0 * h->g.cap, h->b.n_desc + 2 * p0,
                           h->b.desc + (size_t)2 * p0 * h->g.cap * kDescBytes, h->g.cap, 2 * n, lane.stream);
   } else {
-    launch_blur(h->g, b, h->blur_map, 2 * p0, 2 * n, lane.stream);
-    mark(h, lane, kEvBlur1);
-    launch_describe(h->g, b, lane.blurred_map, 2 * p0, 2 * n, lane.stream);
+    // blur -> rBRIEF in sub-chunks that all use the FIRST images of the lane's blurred scratch: 64 pairs are 61 MB, which
+    // stay in the 126 MB L2 between the two kernels and are overwritten there by the next sub-chunk, so the blurred
+    // pixels (246 MB per 256-pair chunk, 100 % non-algorithmic) mostly never travel to DRAM.  (The timing events of the
+    // profiling mode want the two kernels back to back: one sub-chunk then.)
+    const int sub = h->profiling || h->capturing ? n : std::max(1, std::min(n, h->describe_sub_chunk));
+    for (int q0 = 0; q0 < n; q0 += sub) {
+      const int qn = std::min(sub, n - q0);
+      Buffers bq = b;
+      bq.blurred = lane.blurred - (size_t)2 * (p0 + q0) * h->g.rows * h->g.pitch;   // image 2 (p0 + q0) -> scratch image 0
+      launch_blur(h->g, bq, h->blur_map, 2 * (p0 + q0), 2 * qn, lane.stream);
+      if (q0 == 0) mark(h, lane, kEvBlur1);
+      launch_describe(h->g, bq, lane.blurred_map, 2 * (p0 + q0), 2 * qn, lane.stream, 0);
+      h->launches += q0 ? 2 : 0;
+    }
   }
   mark(h, lane, kEvDescribe1);
   h->launches += 4;
@@ -538,6 +551,7 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
   const size_t per_pair = (size_t)2 * g.rows * (2 * g.pitch + 4 * g.mask_words);
   int chunk = (int)std::min<size_t>(256, std::max<size_t>(1, ((size_t)512u << 20) / per_pair));
   if (const char* e = std::getenv("VSLAM_CHUNK_PAIRS")) chunk = std::max(1, atoi(e));
+  if (const char* e = std::getenv("VSLAM_DESCRIBE_SUB_CHUNK")) h->describe_sub_chunk = std::max(1, atoi(e));
   h->chunk = std::min(chunk, h->max_batch);
 
   const size_t B = h->max_batch, I = 2 * B;
@@ -697,6 +711,7 @@ int vslam_fpg_set_thresholds(vslam_fpg* h, const double* t) {
 
 int vslam_fpg_initialize(vslam_fpg* h, const uint8_t* left, const uint8_t* right, size_t stride, int localizing,
                          int32_t* n_left, int32_t* n_right) {
+  VSLAM_NVTX("vslam_fpg_initialize [KeypointDetection + DescriptorExtraction]");
   if (!h || !left || !right)   // stereo :75-78
     return fail(VSLAM_ERR_INVALID_ARGUMENT, "StereoFramePointGenerator::initialize|called with empty frame");
   if (stride < (size_t)h->g.cols) return fail(VSLAM_ERR_INVALID_ARGUMENT, "stride smaller than the image width");
@@ -816,6 +831,7 @@ int vslam_fpg_get_detection_stats(vslam_fpg* h, int32_t* cl, int32_t* cr, double
 
 int vslam_fpg_compute(vslam_fpg* h, const vslam_tracked_point* tracked, int32_t n_tracked, vslam_framepoint* out,
                       int32_t capacity, int32_t* n_out, int32_t* n_matches) {
+  VSLAM_NVTX("vslam_fpg_compute [StereoMatching]");
   if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "StereoFramePointGenerator::compute|called with empty frame");
   if (!h->initialized || h->last_pairs != 1) return fail(VSLAM_ERR_STATE, "compute without initialize");
   const bool device_tracks = n_tracked == VSLAM_TRACKED_FROM_LAST_TRACK;
@@ -916,6 +932,7 @@ int vslam_fpg_track(vslam_fpg* h, const vslam_previous_point* previous, int32_t 
                     double maximum_descriptor_distance_tracking, vslam_track* tracks, int32_t capacity,
                     int32_t* n_tracks, int32_t* lost, int32_t* n_lost, int32_t* n_tracked_landmarks,
                     double* average_descriptor_distance) {
+  VSLAM_NVTX("vslam_fpg_track [PoseTracker3D::compute->track]");
   if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "StereoFramePointGenerator::track|called with invalid frames");   // :468-471
   if (!T || n_previous < 0 || (n_previous > 0 && !previous)) return fail(VSLAM_ERR_INVALID_ARGUMENT, "bad previous points / transform");
   if (!h->initialized || h->last_pairs != 1) return fail(VSLAM_ERR_STATE, "track without initialize");
@@ -975,6 +992,7 @@ int vslam_fpg_recover_points(vslam_fpg* h, const vslam_previous_point* lost, int
                              double minimum_depth_meters, double maximum_depth_meters,
                              double maximum_descriptor_distance_tracking, vslam_recovered_point* recovered,
                              int32_t capacity, int32_t* n_recovered) {
+  VSLAM_NVTX("vslam_fpg_recover_points [PoseTracker3D::compute->framepoint_generator->recoverPoints]");
   if (!h || !W || n_lost < 0 || (n_lost > 0 && !lost)) return fail(VSLAM_ERR_INVALID_ARGUMENT, "bad arguments");
   if (!h->initialized || h->last_pairs != 1) return fail(VSLAM_ERR_STATE, "recoverPoints without initialize");
   CUDA_TRY(cudaSetDevice(h->device));
@@ -1133,6 +1151,7 @@ static int batch_finish(vslam_fpg* h, int32_t n_pairs) {
 
 int vslam_fpg_batch_upload(vslam_fpg* h, int32_t n_pairs, const uint8_t* left, const uint8_t* right, size_t stride,
                            size_t pair_stride) {
+  VSLAM_NVTX("vslam_fpg_batch_upload");
   int rc = check_batch(h, n_pairs);
   if (rc) return rc;
   if (!left || !right || stride < (size_t)h->g.cols) return fail(VSLAM_ERR_INVALID_ARGUMENT, "bad image arguments");
@@ -1144,6 +1163,7 @@ int vslam_fpg_batch_upload(vslam_fpg* h, int32_t n_pairs, const uint8_t* left, c
 }
 
 int vslam_fpg_batch_run(vslam_fpg* h, int32_t n_pairs, int localizing) {
+  VSLAM_NVTX("vslam_fpg_batch_run [KeypointDetection + DescriptorExtraction + StereoMatching]");
   int rc = check_batch(h, n_pairs);
   if (rc) return rc;
   if (!h->g.enable_binning) return fail(VSLAM_ERR_INVALID_ARGUMENT, "batched runs require enable_keypoint_binning");
@@ -1160,6 +1180,7 @@ int vslam_fpg_batch_run(vslam_fpg* h, int32_t n_pairs, int localizing) {
 
 int vslam_fpg_batch_download(vslam_fpg* h, int32_t n_pairs, vslam_framepoint* out, int32_t capacity_per_pair,
                              int32_t* n_framepoints, int32_t* n_matches, int32_t* n_left, int32_t* n_right) {
+  VSLAM_NVTX("vslam_fpg_batch_download");
   int rc = check_batch(h, n_pairs);
   if (rc) return rc;
   if (!h->initialized || h->last_pairs < n_pairs) return fail(VSLAM_ERR_STATE, "no batched run to download");
@@ -1184,6 +1205,7 @@ int vslam_fpg_batch_download(vslam_fpg* h, int32_t n_pairs, vslam_framepoint* ou
 int vslam_fpg_batch_process(vslam_fpg* h, int32_t n_pairs, const uint8_t* left, const uint8_t* right, size_t stride,
                             size_t pair_stride, int localizing, vslam_framepoint* out, int32_t capacity_per_pair,
                             int32_t* n_framepoints) {
+  VSLAM_NVTX("vslam_fpg_batch_process [host images -> framepoints]");
   int rc = check_batch(h, n_pairs);
   if (rc) return rc;
   if (!left || !right || stride < (size_t)h->g.cols) return fail(VSLAM_ERR_INVALID_ARGUMENT, "bad image arguments");
@@ -1209,6 +1231,7 @@ int vslam_fpg_batch_process(vslam_fpg* h, int32_t n_pairs, const uint8_t* left, 
 int vslam_fpg_batch_linearize(vslam_fpg* h, int32_t n_pairs, const double T[12], int ignore_outliers,
                               double maximum_error_kernel, double minimum_reliable_depth, double maximum_reliable_depth,
                               int enable_inverse_depth_as_information, int32_t rounds) {
+  VSLAM_NVTX("vslam_fpg_batch_linearize [PoseTracker3D::compute->pose_optim]");
   int rc = check_batch(h, n_pairs);
   if (rc) return rc;
   if (!T || rounds < 1) return fail(VSLAM_ERR_INVALID_ARGUMENT, "bad pose / rounds");
@@ -1306,8 +1329,8 @@ int vslam_fpg_debug_keypoint_mask(vslam_fpg* h, int32_t pair, int side, uint32_t
 
 int vslam_fpg_debug_blurred(vslam_fpg* h, int32_t pair, int side, uint8_t* image) {
   if (!h || !image) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
-  if (!h->initialized || pair < 0 || pair >= h->last_pairs || h->last_pairs > h->chunk)
-    return fail(VSLAM_ERR_STATE, "debug taps need a run of at most chunk=%d pairs", h->chunk);
+  if (!h->initialized || pair < 0 || pair >= h->last_pairs || h->last_pairs > std::min(h->chunk, h->describe_sub_chunk))
+    return fail(VSLAM_ERR_STATE, "the blurred-image tap needs a run of at most %d pairs", std::min(h->chunk, h->describe_sub_chunk));
   if (h->d_brief_tests) return fail(VSLAM_ERR_STATE, "no blurred image with the BRIEF-32 extractor");
   CUDA_TRY(cudaSetDevice(h->device));
   const Geometry& g = h->g;

@@ -102,9 +102,9 @@ void launch_blur(const Geometry& g, const Buffers& b, const CUtensorMap& image_m
                  cudaStream_t stream);
 // TMA descriptor of a blurred scratch buffer [n_images][rows][pitch]; false when the driver cannot encode it
 bool make_blurred_tensor_map(const Geometry& g, const uint8_t* blurred, int n_images, CUtensorMap* out);
-// image 0 of `blurred_map` is image `first_image` of the batch
+// image `scratch_first` of `blurred_map` (the lane's blurred scratch) is image `first_image` of the batch
 void launch_describe(const Geometry& g, const Buffers& b, const CUtensorMap& blurred_map, int first_image, int n_images,
-                     cudaStream_t stream);
+                     cudaStream_t stream, int scratch_first = 0);
 // one launch per epipolar offset (pass index -> offset 0,+1,-1,+2,...)
 void launch_match(const Geometry& g, const StereoParams& sp, const Buffers& b, int first_pair, int n_pairs, int pass,
                   int epipolar_offset, cudaStream_t stream);

@@ -87,6 +87,7 @@ int vslam_landmark_optimizer_update(vslam_landmark_optimizer* h, int32_t n_landm
                                     uint32_t maximum_number_of_iterations, double maximum_error_squared_meters,
                                     double* world_coordinates, uint32_t* number_of_updates, uint8_t* outcome,
                                     int32_t* iterations) {
+  VSLAM_NVTX("vslam_landmark_optimizer_update [PoseTracker3D::_updatePoints]");
   if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null handle");
   if (n_landmarks < 0 || n_landmarks > h->max_landmarks)
     return fail(VSLAM_ERR_CAPACITY, "%d landmarks exceed the capacity %d", n_landmarks, h->max_landmarks);

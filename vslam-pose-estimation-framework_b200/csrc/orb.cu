@@ -236,7 +236,7 @@ static_assert(DT_BINS == DT_THREADS, "one bin per thread");
 __global__ void __launch_bounds__(DT_THREADS) describe_tile_kernel(const __grid_constant__ CUtensorMap blurred_map,
                                                                    Geometry g, const int32_t* __restrict__ row_ptr,
                                                                    const uint32_t* __restrict__ kp_xy,
-                                                                   uint8_t* __restrict__ desc) {
+                                                                   uint8_t* __restrict__ desc, int scratch_first) {
   __shared__ __align__(128) uint8_t s_tile[DT_BH][DT_BW];
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ uint32_t s_q[DT_LIST];
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(DT_THREADS) describe_tile_kernel(const __grid_
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(DT_BW * DT_BH) : "memory");
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(&s_tile[0][0])), "l"(&blurred_map), "r"(bar), "r"(x0 - DT_X), "r"(y0 - 13), "r"(img)
+        ::"r"(smem_u32(&s_tile[0][0])), "l"(&blurred_map), "r"(bar), "r"(x0 - DT_X), "r"(y0 - 13), "r"(scratch_first + img)
         : "memory");
   }
   // The 375 byte look-ups of a lane go to the bank of its keypoint's tile column (the tile pitch is 2 x 32 banks, so
@@ -560,13 +560,13 @@ bool make_blurred_tensor_map(const Geometry& g, const uint8_t* blurred, int n_im
 
 // `blurred_map` describes the buffer whose image 0 is image `first_image` of the batch (the lane's scratch)
 void launch_describe(const Geometry& g, const Buffers& b, const CUtensorMap& blurred_map, int first_image, int n_images,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int scratch_first) {
   const int tiles_x = (g.cols - 62 + DT_W - 1) / DT_W, tiles_y = (g.rows - 62 + DT_H - 1) / DT_H;
   if (tiles_x <= 0 || tiles_y <= 0) return;   // no pixel is 31 px away from every border: no descriptor-valid keypoint
   dim3 grid(tiles_x, tiles_y, n_images);
   describe_tile_kernel<<<grid, DT_THREADS, 0, stream>>>(blurred_map, g, b.row_ptr + (size_t)first_image * (g.rows + 1),
                                                         b.kp_xy + (size_t)first_image * g.cap,
-                                                        b.desc + (size_t)first_image * g.cap * kDescBytes);
+                                                        b.desc + (size_t)first_image * g.cap * kDescBytes, scratch_first);
 }
 
 void launch_describe_at(const Geometry& g, const uint8_t* blurred, const uint32_t* xy, const int32_t* n, uint8_t* desc,
