@@ -21,6 +21,7 @@ constexpr int TH = 54;             // output tile height; TH + 2 = 56 pre-test r
                                    // arithmetic, clears, scan, publish) is paid 1.8x less often and 376 = 7 x 54 - 2 rows
                                    // waste 0.5 % of the tile rows (3.7 % with 30); 7 rows is what one flag register holds
 constexpr int RPW = (TH + 2) / 8;  // pre-test rows per warp
+constexpr int kSkew = 5;            // word of lane l in pre-test row it: (l + kSkew it) mod 32 (see phase 1)
 static_assert((TH + 2) % 8 == 0 && 4 * RPW + 4 <= 32, "one flag register per lane: 4 bits per row + 4 for the halo word");
 constexpr int HX = 16;             // smem halo in x (only 4 needed; 16 keeps uint4 loads aligned)
 constexpr int SW = TW + 2 * HX + 16;   // 176 bytes = 44 words: consecutive rows are 12 banks apart, so the RPW = 7 consecutive
@@ -158,16 +159,6 @@ __device__ __forceinline__ uint32_t compass_pretest(const uint8_t (*s_img)[SW], 
   return (absdiff_gt(rn, c, cadd) | absdiff_gt(rs, c, cadd)) & (absdiff_gt(re, c, cadd) | absdiff_gt(rw, c, cadd));
 }
 
-// tiles touching the border of the region: the columns of word `wi` inside [cx_lo, cx_hi] (constant over the rows of a tile)
-__device__ __forceinline__ uint32_t keep_columns(int x0, int wi, int cx_lo, int cx_hi) {
-  const int bx = x0 - 4 + 4 * wi;
-  const int lo = cx_lo - bx, hi = cx_hi - bx;
-  uint32_t keep = 0x80808080u;
-  if (lo > 0) keep = lo > 3 ? 0u : keep << (8 * lo);
-  if (hi < 3) keep = hi < 0 ? 0u : keep & (0x80808080u >> (8 * (3 - hi)));
-  return keep;
-}
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __global__ void __launch_bounds__(256) fast_nms_kernel(const __grid_constant__ CUtensorMap image_map, Geometry g,
@@ -230,46 +221,32 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(const __grid_constant__ C
   }
 
   // ---- phase 1 (warp-private): compass pre-test on the tile + 1 px NMS halo.  Warp w owns the RPW consecutive
-  // pre-test rows from RPW * w; lane l owns the aligned word at image x = x0 + 4*l, and lanes < 2 RPW also the two
-  // halo words (x0-4.. and x0+128..) of the warp's rows.
+  // pre-test rows from RPW * w.  In row `it` lane l tests the aligned word (l + kSkew it) mod 32 of the tile (image x =
+  // x0 + 4 word): SKEWED, because corners cluster along edges -- with one word column per lane a vertical edge put all
+  // its candidates into one or two lanes and the per-lane enumeration below ran with 6 of 32 lanes (ncu r2i: 22 % of
+  // the kernel's instructions); skewed, a vertical edge is spread over RPW lanes and a horizontal one over all 32, and
+  // every row is still read as 32 consecutive words (no bank conflict).  Lanes < 2 RPW also test the two halo words
+  // (x0-4.. and x0+128..) of the warp's rows.
   const int cx_lo = max(ax0, x0 - 1), cx_hi = min(ax1, x0 + TW);   // columns whose score is needed
-  const bool interior = cx_lo == x0 - 1 && cx_hi == x0 + TW && y0 - 1 >= ay0 && y0 + TH <= ay1;
+  // the same bounds in tile coordinates (sx = column - (x0 - 1), sy = row - (y0 - 1)); candidates outside them -- they
+  // exist only in tiles on the border of a region -- are dropped in phase 2, where every lane is busy, instead of being
+  // masked word by word here
+  const int sx_lo = cx_lo - (x0 - 1), sx_hi = cx_hi - (x0 - 1);
+  const int sy_lo = max(ay0 - (y0 - 1), 0), sy_hi = min(ay1 - (y0 - 1), CH - 1);
   uint16_t* list = s_list[warp];
   const uint32_t lt = (1u << lane) - 1u;
   int ncand = 0;
   if (t <= 127) {
     const uint32_t cadd = 0x01010101u * (uint32_t)(127 - t);
     const int hsy = RPW * warp + min(lane >> 1, RPW - 1), hwi = (lane & 1) ? 33 : 0;   // halo word of lanes < 2 RPW
-    // every lane first collects the flags of ITS pixels (RPW rows x 4 bytes + halo word) in one register: nibble `it`
-    // = the four pixels of pre-test row it, nibble RPW = the halo word ...
+    // every lane first collects the flags of ITS pixels in one register: bit 8 b + it = byte b of its word in pre-test
+    // row it (the pre-test leaves bit 7 of every byte: one shift and one OR per row), bit 8 b + 7 = its halo word ...
     uint32_t flags = 0;
-    if (interior) {
 #pragma unroll
-      for (int it = 0; it < RPW; ++it) {
-        const uint32_t m = compass_pretest(s_img, RPW * warp + it, lane + 1, cadd);
-        flags |= ((((m >> 7) & 0x01010101u) * 0x01020408u) >> 24) << (4 * it);
-      }
-      uint32_t m = 0;
-      if (lane < 2 * RPW)   // of the left halo word only x0-1 (byte 3) is needed, of the right one only x0+128 (byte 0)
-        m = compass_pretest(s_img, hsy, hwi, cadd) & (hwi ? 0x00000080u : 0x80000000u);
-      flags |= ((((m >> 7) & 0x01010101u) * 0x01020408u) >> 24) << (4 * RPW);
-    } else {
-      // tiles on the border of the region (30 of the 70 tiles of a KITTI image): the border only masks columns (the same
-      // for every row of the tile) and whole rows -- both hoisted out of the loop, which unrolls like the interior one
-      const uint32_t keep = keep_columns(x0, lane + 1, cx_lo, cx_hi);
-      const uint32_t keep_halo = keep_columns(x0, hwi, cx_lo, cx_hi);
-      const int sy_lo = ay0 - (y0 - 1), sy_hi = ay1 - (y0 - 1);
-#pragma unroll
-      for (int it = 0; it < RPW; ++it) {
-        const int sy = RPW * warp + it;
-        uint32_t m = compass_pretest(s_img, sy, lane + 1, cadd) & keep;
-        if (sy < sy_lo || sy > sy_hi) m = 0u;
-        flags |= ((((m >> 7) & 0x01010101u) * 0x01020408u) >> 24) << (4 * it);
-      }
-      uint32_t m = 0;
-      if (lane < 2 * RPW && hsy >= sy_lo && hsy <= sy_hi) m = compass_pretest(s_img, hsy, hwi, cadd) & keep_halo;
-      flags |= ((((m >> 7) & 0x01010101u) * 0x01020408u) >> 24) << (4 * RPW);
-    }
+    for (int it = 0; it < RPW; ++it)
+      flags |= compass_pretest(s_img, RPW * warp + it, ((lane + kSkew * it) & 31) + 1, cadd) >> (7 - it);
+    if (lane < 2 * RPW)   // of the left halo word only x0-1 (byte 3) is needed, of the right one only x0+128 (byte 0)
+      flags |= compass_pretest(s_img, hsy, hwi, cadd) & (hwi ? 0x00000080u : 0x80000000u);
     // ... then ONE warp scan places the lanes' candidates in the list (the order is irrelevant), instead of four
     // ballots and four predicated stores per pre-test row
     const int mine = __popc(flags);
@@ -281,19 +258,14 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(const __grid_constant__ C
     }
     ncand = __shfl_sync(0xffffffffu, inc, 31);
     uint16_t* dst = list + (inc - mine);
-    // bit b = pre-test row b >> 2 of this warp, byte b & 3: code = (RPW warp + (b >> 2)) << 8 | 4 lane + 1 + (b & 3)
-    const uint32_t code0 = (uint32_t)(((RPW * warp) << 8) + 4 * lane + 1);
-    uint32_t rows4 = flags & ((1u << (4 * RPW)) - 1u);
-    while (rows4) {
-      const uint32_t bit = (uint32_t)__ffs((int)rows4) - 1u;
-      rows4 &= rows4 - 1u;
-      *dst++ = (uint16_t)(code0 + ((bit & ~3u) << 6) + (bit & 3u));
-    }
-    uint32_t halo = flags >> (4 * RPW);   // lanes < 2 RPW only, and rarely set
-    while (halo) {
-      const uint32_t bit = (uint32_t)__ffs((int)halo) - 1u;
-      halo &= halo - 1u;
-      *dst++ = (uint16_t)((hsy << 8) + 4 * hwi - 3 + (int)bit);
+    // entry = lane << 5 | bit of `flags`: the enumeration runs with the few lanes that still hold candidates, so it only
+    // stores; phase 2 decodes the entries with all 32 lanes busy
+    const uint32_t entry0 = (uint32_t)lane << 5;
+    uint32_t left = flags;
+    while (left) {
+      const uint32_t bit = (uint32_t)__ffs((int)left) - 1u;
+      left &= left - 1u;
+      *dst++ = (uint16_t)(entry0 + bit);
     }
   } else {   // thresholds above 127 (never produced by the reference's configurations): every pixel is a candidate
     for (int it = 0; it < RPW; ++it) {
@@ -316,10 +288,23 @@ __global__ void __launch_bounds__(256) fast_nms_kernel(const __grid_constant__ C
     int s = 0, code = 0;
     if (c < ncand) {
       code = list[c];
+      if (t <= 127) {   // decode lane << 5 | (8 byte + it) -> position code (sy << 8 | sx)
+        // entry >> 3 = 4 lane + byte; the tested word was (lane + kSkew it) mod 32, i.e. tile column
+        // (4 lane + byte + 4 kSkew it) mod 128, and sx counts from the halo column: + 1
+        const int it = code & 7, x4 = code >> 3;
+        if (it < RPW) {
+          code = ((RPW * warp + it) << 8) + ((x4 + 4 * kSkew * it) & 127) + 1;
+        } else {       // halo word of lane (x4 >> 2): left (byte 3 = column x0 - 1) or right (byte 0 = column x0 + 128)
+          const int src = x4 >> 2;
+          code = ((RPW * warp + min(src >> 1, RPW - 1)) << 8) + ((src & 1) ? CW - 1 : 0);
+        }
+      }
       const int sy = code >> 8, sx = code & 0xff;
-      const uint8_t* px = &s_img[sy + 3][sx + HX - 1];
-      s = t >= 1 ? arc_strength<true>(px) : arc_strength<false>(px);
-      if (s > t) s_score[sy][sx] = (uint8_t)(s - 1);
+      if (sx >= sx_lo && sx <= sx_hi && sy >= sy_lo && sy <= sy_hi) {   // inside the keypoint area of the region
+        const uint8_t* px = &s_img[sy + 3][sx + HX - 1];
+        s = t >= 1 ? arc_strength<true>(px) : arc_strength<false>(px);
+        if (s > t) s_score[sy][sx] = (uint8_t)(s - 1);
+      }
     }
     const int sy = code >> 8, sx = code & 0xff;
     const bool keep = s > t && sy >= 1 && sy <= TH && sx >= 1 && sx <= TW;
