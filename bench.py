@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --pairs per GPU; strong: --pairs in total, block-partitioned over the ranks "
                          "(BASELINE.json configs[2]: 4096 pairs sharded across 1/2/4/8)")
+    ap.add_argument("--wc-images", action="store_true", help="image upload buffers in write-combined pinned memory")
     ap.add_argument("--no-extras", action="store_true", help="skip the aligner / sequence / landmark side measurements")
     return ap.parse_args()
 
@@ -468,6 +469,33 @@ def landmark_refinement(api, synth, device):
         out.append({"landmarks": n, "measurements": int(h["offsets"][-1]), "ms_per_call": ms,
                     "mean_iterations": float(r[3].mean()), "adopted_fraction": float((r[2] == 1).mean())})
         opt.close()
+    # the device-resident map (vslam_landmark_map): histories stay in HBM, a frame appends one measurement per tracked
+    # landmark and refines it -- what a tracker pays per frame for 1000 tracked landmarks with ~30-measurement histories
+    n, frames = 1000, 60
+    h = synth.landmark_histories(n, n_frames=frames, seed=5, outlier_fraction=0.05)
+    lengths = np.diff(h["offsets"])
+    lmap = api.LandmarkMap(n, 8 * n, frames + 64, device=device)
+    for f in range(frames):     # poses of the history frames
+        lmap.set_frame_pose(f, h["world_to_camera"][f], h["camera_to_world"][f])
+    # every landmark is born with its history minus the last measurement (newest first), then updated once per "frame"
+    born = [h["measurements"][h["offsets"][i]:h["offsets"][i + 1] - 1][::-1] for i in range(n)]
+    born = [bm if len(bm) else h["measurements"][h["offsets"][i]:h["offsets"][i + 1]] for i, bm in enumerate(born)]
+    offs = np.concatenate([[0], np.cumsum([len(bm) for bm in born])]).astype(np.int32)
+    last = frames - 1
+    r0 = lmap.update_frame(last, h["world_to_camera"][last], h["camera_to_world"][last], [], [], offs, np.concatenate(born), h["world"])
+    ids = r0["new_ids"]
+    cam = np.array([h["measurements"][h["offsets"][i + 1] - 1]["camera_coordinates"] for i in range(n)])
+    lmap.update_frame(last, h["world_to_camera"][last], h["camera_to_world"][last], ids, cam)
+    t0 = time.perf_counter()
+    reps = 20
+    for _ in range(reps):       # each call appends one more measurement per landmark (histories grow by 20)
+        r = lmap.update_frame(last, h["world_to_camera"][last], h["camera_to_world"][last], ids, cam)
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    out.append({"landmarks": n, "measurements": int(lengths.sum()) + n * (reps // 2), "ms_per_call": ms, "resident": True,
+                "what": "vslam_landmark_map_update_frame: ids + camera coordinates in (28 KB), world / updates / outcome "
+                        "out (29 KB), histories resident in HBM; python harness",
+                "mean_iterations": float(r["iterations"].mean()), "adopted_fraction": float((r["outcome"] == 1).mean())})
+    lmap.close()
     return out
 
 
@@ -689,8 +717,11 @@ def main():
     # ---- synthetic inputs: D distinct band-world pairs per rank (seeds disjoint across ranks), tiled to P pairs in
     # pinned host memory (every pair is its own memory and is processed independently)
     dl, dr = synth.band_world_batch(cfg.camera, seeds, workers=max(1, min(cores // world, 32)))
+    if args.wc_images:      # write-combined upload sources (the host only writes them): DMA reads skip the cache snoop
+        os.environ["VSLAM_HOST_ALLOC_WC"] = "1"
     left = api.pinned_empty((P, cam.rows, cam.cols))
     right = api.pinned_empty((P, cam.rows, cam.cols))
+    os.environ.pop("VSLAM_HOST_ALLOC_WC", None)
     for i in range(0, P, D):
         n = min(D, P - i)
         left[i:i + n], right[i:i + n] = dl[:n], dr[:n]
@@ -741,11 +772,15 @@ def main():
     e2e_value = P_total * K / e2e_s
     # copy-only control: the same pinned buffers through the same chunked pipeline with the kernels left out (only the
     # re-pitch kernel runs) -- if this is as slow as e2e, the host -> device path is the limit, not the pipeline
-    gen.batch_upload(left, right)
+    def step_copies_only():
+        gen.batch_upload(left, right)          # host -> device: the images
+        gen.batch_download(P, out)             # device -> host: the framepoint records (of the last run) ...
+        return gen.batch_systems(P, raw=True)  # ... and the normal equations
+    step_copies_only()
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
-        gen.batch_upload(left, right)
+        step_copies_only()
     barrier()
     h2d_s = max_over_ranks(time.perf_counter() - t0)
     h2d = 2 * P * cam.rows * cam.cols
@@ -800,13 +835,16 @@ def main():
             "config": workload_config(args, args.pairs), "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s / K * 1e3, "host_placement": numa,
+                    "image_buffers": "write-combined pinned" if args.wc_images else "pinned",
                     "h2d_gbs_per_gpu": h2d * K / e2e_s / 1e9,
                     "copy_only_control": {"ms_per_step": h2d_s / K * 1e3, "h2d_only_gbs_per_gpu": h2d * K / h2d_s / 1e9,
                                           "h2d_only_gbs_all_gpus": world * h2d * K / h2d_s / 1e9,
                                           "frames_per_s_if_copy_bound": P_total * K / h2d_s,
                                           "e2e_over_copy_only": h2d_s / e2e_s,
-                                          "what": "vslam_fpg_batch_upload of the same pinned buffers, same chunks and "
-                                                  "lanes, no kernels but the row re-pitch; max over ranks"}},
+                                          "what": "the step's copies without its kernels: vslam_fpg_batch_upload of the "
+                                                  "same pinned image buffers (same chunks and lanes; only the row re-pitch "
+                                                  "kernel runs), then the download of the framepoint records and of the "
+                                                  "normal equations into the same host buffers; max over ranks"}},
             "gpu_launches": int(launches), "roofline": roofline,
             "counts": {"mean_descriptors_left": float(nl.mean()), "mean_matches": float(nm.mean()),
                        "mean_framepoints": float(nf.mean())}}

@@ -220,6 +220,16 @@ int vslam_fpg_track(vslam_fpg* h, const vslam_previous_point* previous, int32_t 
                     vslam_track* tracks, int32_t capacity, int32_t* n_tracks, int32_t* lost, int32_t* n_lost,
                     int32_t* n_tracked_landmarks, double* average_descriptor_distance);
 
+/* PoseTracker3D::_prunePoints (src/position_tracking/pose_tracker_3d.cpp:437-472) for the device-resident tracks: after
+ * the aligner has converged on the tracks of the last vslam_fpg_track (correspondence k = track k), the tracks it rejects
+ * are dropped from the records that pre-load the bins of vslam_fpg_compute(VSLAM_TRACKED_FROM_LAST_TRACK) -- on the
+ * device, in order, without the tracked points travelling host -> device again.  Rule: average error < kernel ? inliers
+ * only : errors != -1 and < 100 kernel.  n_kept / kept[n_tracks] (either may be NULL) tell the host which of its own
+ * track records to keep (frame->points().resize, :471).  Declared here, after both handle types. */
+typedef struct vslam_aligner vslam_aligner;
+int vslam_fpg_prune_tracks(vslam_fpg* h, vslam_aligner* aligner, double maximum_error_kernel, int32_t* n_kept,
+                           uint8_t* kept);
+
 /* StereoFramePointGenerator::recoverPoints(frame, lost_points), :683-869, with the ORB extractor.  recovered: the
  * points appended to frame->points(), in order.  minimum/maximum_depth_meters: parameters.h:197-198. */
 int vslam_fpg_recover_points(vslam_fpg* h, const vslam_previous_point* lost, int32_t n_lost,
@@ -308,7 +318,7 @@ double vslam_threshold_proposal(double threshold, int32_t n_keypoints, double ta
  * Frame aligners (pose optimisation previous -> current)
  * =================================================================================================*/
 
-typedef struct vslam_aligner vslam_aligner;
+/* (vslam_aligner is declared above, with vslam_fpg_prune_tracks) */
 
 #define VSLAM_ALIGNER_STEREO_UV 0 /* src/aligners/stereouv_aligner.cpp */
 #define VSLAM_ALIGNER_UVD 1       /* src/aligners/uvd_aligner.cpp */
@@ -406,6 +416,45 @@ int vslam_landmark_optimizer_update(vslam_landmark_optimizer* h, int32_t n_landm
                                     double* world_coordinates, uint32_t* number_of_updates, uint8_t* outcome,
                                     int32_t* iterations);
 int64_t vslam_landmark_optimizer_launch_count(const vslam_landmark_optimizer* h);
+
+/* The same refinement over a DEVICE-RESIDENT landmark map: the measurement histories (Landmark::_measurements,
+ * src/types/landmark.h:117), world coordinates and update counts stay in HBM, a frame appends ONE measurement per
+ * tracked landmark -- what Landmark::update does first (landmark.cpp:71-79) -- and refines it; nothing is re-uploaded.
+ * Landmarks are named by the ids vslam_landmark_map_update_frame hands out (0, 1, 2, ... in creation order, like
+ * Landmark::_identifier, landmark.cpp:8).  Frames are named by a slot < max_frames chosen by the host (the frame's
+ * identifier modulo max_frames while older frames are still referenced by measurements). */
+typedef struct vslam_landmark_map vslam_landmark_map;
+/* max_measurement_blocks: pool of 32-measurement blocks shared by all landmarks (40 B per measurement);
+ * a landmark holds at most 32 * 64 = 2048 measurements */
+int vslam_landmark_map_create(int32_t max_landmarks, int32_t max_measurement_blocks, int32_t max_frames, int device,
+                              vslam_landmark_map** out);
+int vslam_landmark_map_destroy(vslam_landmark_map* h);
+/* Frame::setRobotToWorld for an already registered frame (pose graph optimisation moves old frames,
+ * src/types/frame.cpp:43-56): later refinements evaluate that frame's measurements with the new poses */
+int vslam_landmark_map_set_frame_pose(vslam_landmark_map* h, int32_t frame, const double world_to_camera_left[12],
+                                      const double camera_left_to_world[12]);
+/* PoseTracker3D::_updatePoints (src/position_tracking/pose_tracker_3d.cpp:475-521) for one frame, as ONE call:
+ *  - the frame's poses are stored in slot `frame`;
+ *  - n_new landmarks are created (WorldMap::createLandmark -> Landmark::Landmark, landmark.cpp:8-33): landmark i takes the
+ *    measurements new_tracks[new_track_offsets[i] .. new_track_offsets[i + 1]) -- its track of framepoints, NEWEST FIRST
+ *    as the constructor walks it -- and the average world position new_world[i] the host formed from the framepoints;
+ *    new_ids[i] receives its id;
+ *  - n_updates existing landmarks (ids unique within the call) receive the measurement
+ *    (frame, camera_coordinates[i], 1 / z) and are refined (Landmark::update).  world_out[i][3], updates_out[i],
+ *    outcome[i] (VSLAM_LANDMARK_*; may be NULL) and iterations[i] (may be NULL) describe landmark ids[i] after the call.
+ * One host -> device copy, two kernels, one device -> host copy. */
+int vslam_landmark_map_update_frame(vslam_landmark_map* h, int32_t frame, const double world_to_camera_left[12],
+                                    const double camera_left_to_world[12], int32_t n_updates, const int32_t* ids,
+                                    const double* camera_coordinates, int32_t n_new, const int32_t* new_track_offsets,
+                                    const vslam_landmark_measurement* new_tracks, const double* new_world,
+                                    uint32_t maximum_number_of_iterations, double maximum_error_squared_meters,
+                                    double* world_out, uint32_t* updates_out, uint8_t* outcome, int32_t* iterations,
+                                    int32_t* new_ids);
+/* state of any landmarks (e.g. before writing the map): world[n][3], number_of_updates[n], n_measurements[n]; NULLs skipped */
+int vslam_landmark_map_get(vslam_landmark_map* h, int32_t n, const int32_t* ids, double* world, uint32_t* number_of_updates,
+                           int32_t* n_measurements);
+int32_t vslam_landmark_map_size(const vslam_landmark_map* h);
+int64_t vslam_landmark_map_launch_count(const vslam_landmark_map* h);
 
 /* WorldMap::writeTrajectoryKITTI (src/types/world_map.cpp:183-216) / writeTrajectoryTUM (:218-252): one text line per
  * frame, std::fixed with 9 decimals, every value followed by a blank.  KITTI: the 12 values of robot_to_world row by

@@ -131,6 +131,19 @@ class StereoFramePointGenerator {
     current_frame->recovered.resize(n);
   }
 
+  // PoseTracker3D::_prunePoints (pose_tracker_3d.cpp:437-472) after the aligner converged on frame->tracks: the rejected
+  // tracks leave frame->tracks AND the device records that pre-load the bins of the next compute(), without an upload
+  void pruneTracks(Frame* frame, vslam_aligner* aligner, double maximum_error_kernel) {
+    if (!frame) throw std::runtime_error("StereoFramePointGenerator::pruneTracks|called with empty frame");
+    std::vector<uint8_t> kept(frame->tracks.size() + 1);
+    int32_t n = 0;
+    check(vslam_fpg_prune_tracks(_handle, aligner, maximum_error_kernel, &n, kept.data()), "StereoFramePointGenerator::pruneTracks");
+    size_t w = 0;
+    for (size_t k = 0; k < frame->tracks.size(); ++k)
+      if (kept[k]) frame->tracks[w++] = frame->tracks[k];
+    frame->tracks.resize(w);
+  }
+
   int numberOfTrackedLandmarks() const { return _number_of_tracked_landmarks; }
 
   int targetNumberOfKeypoints() const { return _target_number_of_keypoints; }
@@ -207,6 +220,7 @@ class FrameAligner {
     check(vslam_aligner_download(_handle, nullptr, b.data()), "Aligner::inliers");
     return std::vector<bool>(b.begin(), b.end());
   }
+  vslam_aligner* handle() { return _handle; }
   int numberOfInliers() const { return _system.number_of_inliers; }
   int numberOfOutliers() const { return _system.number_of_outliers; }
   int numberOfCorrespondences() const { return _number_of_measurements; }

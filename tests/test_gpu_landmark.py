@@ -93,3 +93,87 @@ def test_argument_errors():
     assert e.value.code == -3
     opt.close()
     small.close()
+
+
+# ---- the device-resident landmark map (vslam_landmark_map): PoseTracker3D::_updatePoints frame by frame ------------------
+def _stream_histories(h, n_frames):
+    """landmark i of synth.landmark_histories was seen in the frames [n_frames - len_i, n_frames): it is born with its second
+    framepoint (minimum_track_length_for_landmark_creation = 2, pose_tracker_3d.cpp:492; the constructor walks the track
+    backwards, landmark.cpp:20-33) and updated by every later one"""
+    births, updates = {}, {}
+    for i in range(len(h["offsets"]) - 1):
+        m = h["measurements"][h["offsets"][i]:h["offsets"][i + 1]]
+        if len(m) < 2:
+            continue
+        births.setdefault(int(m["frame"][1]), []).append((i, m[[1, 0]]))
+        for k in range(2, len(m)):
+            updates.setdefault(int(m["frame"][k]), []).append((i, m[k]))
+    return births, updates
+
+
+@pytest.mark.parametrize("n,frames,seed,outliers", [(60, 12, 5, 0.05), (40, 80, 6, 0.2)])
+def test_resident_landmark_map_matches_oracle_frame_by_frame(n, frames, seed, outliers):
+    h = synth.landmark_histories(n, n_frames=frames, seed=seed, outlier_fraction=outliers)
+    births, updates = _stream_histories(h, frames)
+    w2c, c2w = h["world_to_camera"], h["camera_to_world"]
+    lmap = api.LandmarkMap(n, 4 * n + 16, frames)
+    ident = {}                                   # landmark of the synthetic set -> id in the map
+    state = {}                                   # the oracle's (world, number_of_updates, measurements so far)
+    longest = 0
+    for f in range(frames):
+        ups = updates.get(f, [])
+        new = births.get(f, [])
+        # oracle first: Landmark::update per landmark with the history grown by one measurement
+        want = []
+        for i, q in ups:
+            world, nu, ms = state[i]
+            ms = np.concatenate([ms, np.array([q], ms.dtype)])
+            world, nu, outcome, its = tier_a.landmark_update(ms, w2c, c2w, world, nu)
+            state[i] = (world, nu, ms)
+            longest = max(longest, len(ms))
+            want.append((world, nu, outcome, its))
+        new_world = []
+        for i, track in new:
+            C = c2w[track["frame"]].reshape(-1, 3, 4)
+            pts = np.einsum("fij,fj->fi", C[:, :, :3], track["camera_coordinates"]) + C[:, :, 3]
+            wd = np.zeros(3)
+            for p in pts:                        # `_world_coordinates += worldCoordinates()` in track order, then / size
+                wd = wd + p
+            wd = wd / len(pts)
+            new_world.append(wd)
+            state[i] = (wd, len(track), track.copy())
+        offs = np.arange(0, 2 * len(new) + 1, 2, dtype=np.int32)
+        tracks = np.concatenate([t for _, t in new]) if new else None
+        r = lmap.update_frame(f, w2c[f], c2w[f], [ident[i] for i, _ in ups],
+                              np.array([q["camera_coordinates"] for _, q in ups]).reshape(-1, 3),
+                              offs if new else None, tracks, np.array(new_world) if new else None)
+        for k, (world, nu, outcome, its) in enumerate(want):
+            assert np.array_equal(r["world"][k], world) and r["number_of_updates"][k] == nu      # bit-exact
+            assert r["outcome"][k] == outcome and r["iterations"][k] == its
+        for (i, _), lid in zip(new, r["new_ids"]):
+            ident[i] = int(lid)
+    assert longest > 32 or frames < 40           # the 80-frame case crosses block boundaries (33+ measurements)
+    ids = np.array(sorted(ident.values()), np.int32)
+    assert len(lmap) == len(ids) and np.array_equal(ids, np.arange(len(ids)))
+    back = {v: k for k, v in ident.items()}
+    world, nu, cnt = lmap.get(ids)
+    for k, lid in enumerate(ids):
+        w, u, ms = state[back[int(lid)]]
+        assert np.array_equal(world[k], w) and nu[k] == u and cnt[k] == len(ms)
+    assert lmap.launch_count <= 2 * frames
+    lmap.close()
+
+
+def test_resident_landmark_map_capacity_and_arguments():
+    h = synth.landmark_histories(8, n_frames=6, seed=9)
+    lmap = api.LandmarkMap(4, 2, 6)              # 4 landmarks, 2 blocks in the pool
+    track = h["measurements"][:2][::-1].copy()
+    I = np.hstack([np.eye(3), np.zeros((3, 1))])
+    with pytest.raises(api.VslamError):          # unknown id
+        lmap.update_frame(0, I, I, [0], np.ones((1, 3)))
+    offs = np.array([0, 2, 4, 6], np.int32)
+    with pytest.raises(api.VslamError):          # three landmarks need three blocks
+        lmap.update_frame(0, I, I, [], [], offs, np.concatenate([track] * 3), np.ones((3, 3)))
+    with pytest.raises(api.VslamError):          # capacity of the map itself
+        lmap.update_frame(0, I, I, [], [], np.arange(0, 11, 2, dtype=np.int32), np.concatenate([track] * 5), np.ones((5, 3)))
+    lmap.close()

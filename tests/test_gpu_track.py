@@ -250,3 +250,52 @@ def test_initialize_without_extraction_forgets_the_abandoned_track():
     with pytest.raises(api.VslamError):
         gen.compute(api.TRACKED_FROM_LAST_TRACK)
     gen.close()
+
+
+def test_prune_tracks_on_the_device_equals_prune_on_the_host():
+    """PoseTracker3D::_prunePoints (pose_tracker_3d.cpp:437-472): compute() after vslam_fpg_prune_tracks must give what
+    compute() gives when the host prunes the tracks itself and uploads the survivors as tracked points -- both branches
+    of the rule (inliers only / error cap), against the oracle's bin rule"""
+    cfg, acfg = configs.KITTI, configs.KITTI_ALIGNER
+    cam = synth.camera(cfg.camera)
+    world = synth.BandWorld(cam.cols, cam.rows, 23, max_frames=4)
+    for kernel, expect_inliers_only in ((acfg.maximum_error_kernel, False), (1e6, True)):
+        gen = api.StereoFramePointGenerator(cfg, cam)
+        ora = pipeline.StereoFramePointGeneratorOracle(cfg, cam, "a")
+        gen.initialize(*world.pair(0), True)
+        ora.initialize(*world.pair(0), True)
+        first = gen.compute()
+        ora.compute()
+        _, dl = gen.features(0)
+        _, dr = gen.features(1)
+        prev = api.make_previous_points([first], dl, dr)
+        gen.initialize(*world.pair(1), False)
+        ora.initialize(*world.pair(1), False)
+        T = np.hstack([np.eye(3), np.zeros((3, 1))])
+        T[0, 3] = -(-cam.bx / cam.fx) / 4 + 0.05            # a poor prior: the aligner rejects a good share of the tracks
+        got = gen.track(prev, T, False, 25, 40.0)
+        ora.track(prev.view(tier_a.PREVIOUS_POINT), T, False, 25, 40.0)
+        tr = got["tracks"]
+        assert len(tr) > 200
+        # a deliberately wrong pose and ONE linearisation: many outliers, errors spread around the cap
+        import dataclasses
+        al = api.StereoUVAligner(dataclasses.replace(acfg, maximum_error_kernel=kernel), max_points=4096)
+        moving = np.ascontiguousarray(prev["camera_left"][tr["index_previous"]])
+        fixed = np.stack([tr["xl"], tr["yl"], tr["xr"], tr["yr"]], 1).astype(np.float64)
+        al.initialize(moving, fixed, np.ones(len(tr)), np.ones(len(tr)), cam.K, cam.baseline, cam.rows, cam.cols, T)
+        sys_ = al.linearize(False)
+        errors, inliers = al.errors(), al.inliers()
+        average = sys_["total_error"] / len(tr)
+        assert (average < kernel) == expect_inliers_only
+        want_keep = inliers if average < kernel else (errors != -1) & (errors < 100 * kernel)
+        keep = gen.prune_tracks(al, kernel)
+        assert np.array_equal(keep, want_keep) and 0 < keep.sum()
+        if not expect_inliers_only:
+            assert keep.sum() < len(tr)
+        new_device = gen.compute(api.TRACKED_FROM_LAST_TRACK)
+        ora.compute(ora.tracked_points(ora.tracks[want_keep]))
+        want = ora.framepoints()
+        assert len(new_device) == len(want) and np.array_equal(new_device["index_left"], want["index_left"])
+        assert np.array_equal(new_device["camera"], want["cam"])
+        gen.close()
+        al.close()

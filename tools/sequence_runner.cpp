@@ -1,6 +1,6 @@
 // sequence_runner.cpp -- the tracker's per-frame order (reference src/position_tracking/pose_tracker_3d.cpp:80, 239,
 // 124-126 / 355-357, 437-472, 210: initialize -> track against ALL points of the previous frame -> StereoUVAligner
-// initialize + converge over the tracks -> read errors / inliers as _prunePoints does -> compute with the tracks
+// initialize + converge over the tracks -> _prunePoints on the device records -> compute with the surviving tracks
 // pre-loaded) driven from C++14 through include/vslam_b200.hpp, i.e. what the adapters do per frame minus the reference's
 // object graph.  bench.py builds and runs it to report the single-sequence latency without the Python harness in the loop.
 //
@@ -115,9 +115,8 @@ int main(int argc, char** argv) {
         aligner.initialize((int32_t)n, moving.data(), fixed.data(), omega.data(), weights.data(), K, baseline, c.rows,
                            c.cols, 0.1, motion);
         aligner.converge();
-        const std::vector<bool> flags = aligner.inliers();
-        const std::vector<double> errors = aligner.errors();
-        (void)flags; (void)errors;
+        // _prunePoints (:437-472): rejected tracks leave the frame and, on the device, the bin pre-load of compute()
+        generator.pruneTracks(&current, aligner.handle(), ap.maximum_error_kernel);
         rounds = aligner.numberOfRounds();
         inliers = aligner.numberOfInliers();
         const double e = std::fabs(aligner.previousToCurrent()[3] - tx);

@@ -46,7 +46,7 @@ EXPORTS = """vslam_last_error vslam_version vslam_device_count vslam_host_alloc 
 vslam_fpg_create vslam_fpg_destroy vslam_fpg_info vslam_fpg_get_thresholds vslam_fpg_set_thresholds
 vslam_fpg_initialize vslam_fpg_get_features vslam_fpg_get_detection_stats vslam_fpg_set_remaining_features
 vslam_fpg_reset_features vslam_fpg_graph_launch_count
-vslam_fpg_compute vslam_fpg_get_matches vslam_fpg_track vslam_fpg_recover_points
+vslam_fpg_compute vslam_fpg_get_matches vslam_fpg_track vslam_fpg_recover_points vslam_fpg_prune_tracks
 vslam_fpg_set_profiling vslam_fpg_get_time_consumption vslam_fpg_batch_upload vslam_fpg_batch_run
 vslam_fpg_batch_download vslam_fpg_batch_process vslam_fpg_batch_linearize vslam_fpg_batch_get_systems
 vslam_fpg_get_kernel_profile vslam_fpg_batch_get_features vslam_fpg_stream vslam_fpg_synchronize
@@ -55,6 +55,8 @@ vslam_aligner_create vslam_aligner_destroy vslam_aligner_upload vslam_aligner_li
 vslam_aligner_one_round vslam_aligner_converge vslam_aligner_converge_fused vslam_aligner_linearize_async vslam_aligner_read_system
 vslam_aligner_stream vslam_aligner_synchronize vslam_aligner_launch_count vslam_solve6 vslam_v2t
 vslam_landmark_optimizer_create vslam_landmark_optimizer_destroy vslam_landmark_optimizer_update
+vslam_landmark_map_create vslam_landmark_map_destroy vslam_landmark_map_set_frame_pose vslam_landmark_map_update_frame
+vslam_landmark_map_get vslam_landmark_map_size vslam_landmark_map_launch_count
 vslam_landmark_optimizer_launch_count vslam_format_trajectory_kitti vslam_format_trajectory_tum vslam_write_trajectory
 vslam_solve3""".split()
 
@@ -308,6 +310,7 @@ class StereoFramePointGenerator:
                                      int(projection_tracking_distance_pixels),
                                      float(maximum_descriptor_distance_tracking), _p(tracks), len(tracks), C.byref(nt),
                                      _p(lost), C.byref(nl), C.byref(nlm), C.byref(avg)))
+        self._last_n_tracks = nt.value
         return {"tracks": tracks[:nt.value].copy(), "lost": lost[:nl.value].copy(), "tracked_landmarks": nlm.value,
                 "average_descriptor_distance": avg.value}
 
@@ -325,6 +328,17 @@ class StereoFramePointGenerator:
         return out[:n.value].copy()
 
     # -- StereoFramePointGenerator::compute(frame)
+    def prune_tracks(self, aligner, maximum_error_kernel):
+        """PoseTracker3D::_prunePoints for the device-resident tracks of the last track(): -> keep flags [n_tracks] (bool)"""
+        n = C.c_int32(0)
+        kept = np.zeros(max(self._last_n_tracks, 1), np.uint8)
+        fn = lib().vslam_fpg_prune_tracks
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+        _check(fn(self._h, aligner._h, float(maximum_error_kernel), C.byref(n), _p(kept)))
+        out = kept[:self._last_n_tracks].astype(bool)
+        assert int(out.sum()) == n.value
+        return out
+
     def compute(self, tracked=None):
         """tracked: TRACKED records of the points already in frame->points(), or TRACKED_FROM_LAST_TRACK"""
         if isinstance(tracked, int) and tracked == TRACKED_FROM_LAST_TRACK:
@@ -664,6 +678,72 @@ class LandmarkOptimizer:
     def launch_count(self) -> int:
         lib().vslam_landmark_optimizer_launch_count.restype = C.c_int64
         return int(lib().vslam_landmark_optimizer_launch_count(self._h))
+
+
+class LandmarkMap:
+    """device-resident landmark histories (vslam_landmark_map): PoseTracker3D::_updatePoints of one frame per call"""
+
+    def __init__(self, max_landmarks, max_measurement_blocks, max_frames, device=0):
+        self._h = C.c_void_p()
+        _check(lib().vslam_landmark_map_create(int(max_landmarks), int(max_measurement_blocks), int(max_frames), device,
+                                               C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().vslam_landmark_map_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_frame_pose(self, frame, world_to_camera, camera_to_world):
+        w = np.ascontiguousarray(world_to_camera, np.float64).reshape(12)
+        c = np.ascontiguousarray(camera_to_world, np.float64).reshape(12)
+        _check(lib().vslam_landmark_map_set_frame_pose(self._h, int(frame), _p(w), _p(c)))
+
+    def update_frame(self, frame, world_to_camera, camera_to_world, ids=(), camera_coordinates=(), new_track_offsets=None,
+                     new_tracks=None, new_world=None, maximum_number_of_iterations=100, maximum_error_squared_meters=25.0):
+        """-> dict(world[n,3], number_of_updates[n], outcome[n], iterations[n], new_ids[n_new])"""
+        w = np.ascontiguousarray(world_to_camera, np.float64).reshape(12)
+        c = np.ascontiguousarray(camera_to_world, np.float64).reshape(12)
+        ids = np.ascontiguousarray(ids, np.int32)
+        cam = np.ascontiguousarray(camera_coordinates, np.float64).reshape(-1, 3)
+        n = len(ids)
+        assert len(cam) == n
+        n_new = 0 if new_track_offsets is None else len(new_track_offsets) - 1
+        off = np.ascontiguousarray(new_track_offsets if n_new else [0], np.int32)
+        trk = np.ascontiguousarray(new_tracks if n_new else np.zeros(0, LANDMARK_MEASUREMENT), LANDMARK_MEASUREMENT)
+        nw = np.ascontiguousarray(new_world if n_new else np.zeros((0, 3)), np.float64).reshape(-1, 3)
+        world, upd = np.zeros((max(n, 1), 3)), np.zeros(max(n, 1), np.uint32)
+        outcome, its = np.zeros(max(n, 1), np.uint8), np.zeros(max(n, 1), np.int32)
+        new_ids = np.zeros(max(n_new, 1), np.int32)
+        fn = lib().vslam_landmark_map_update_frame
+        fn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                       C.c_void_p, C.c_void_p]
+        _check(fn(self._h, int(frame), _p(w), _p(c), n, _p(ids), _p(cam), n_new, _p(off), _p(trk), _p(nw),
+                  int(maximum_number_of_iterations), float(maximum_error_squared_meters), _p(world), _p(upd), _p(outcome),
+                  _p(its), _p(new_ids)))
+        return {"world": world[:n], "number_of_updates": upd[:n], "outcome": outcome[:n], "iterations": its[:n],
+                "new_ids": new_ids[:n_new]}
+
+    def get(self, ids):
+        ids = np.ascontiguousarray(ids, np.int32)
+        n = len(ids)
+        world, upd, cnt = np.zeros((max(n, 1), 3)), np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.int32)
+        _check(lib().vslam_landmark_map_get(self._h, n, _p(ids), _p(world), _p(upd), _p(cnt)))
+        return world[:n], upd[:n], cnt[:n]
+
+    def __len__(self):
+        return int(lib().vslam_landmark_map_size(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        lib().vslam_landmark_map_launch_count.restype = C.c_int64
+        return int(lib().vslam_landmark_map_launch_count(self._h))
 
 
 def format_trajectory(robot_to_world, timestamp=None) -> str:

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/vslam_b200.h"
+#include "aligner_internal.h"
 #include "api_common.h"
 #include "gn_math.h"
 #include "host_math.h"
@@ -43,6 +44,7 @@ struct vslam_aligner {
   int resident_blocks = 0;      // co-resident CTAs of the cooperative kernel = grid cap of both linearize paths
   int64_t launches = 0;
   bool uploaded = false;
+  double last_total_error = 0;
 };
 
 namespace {
@@ -98,6 +100,7 @@ void unpack_system(const vslam_aligner* h, vslam_linear_system* s) {
     for (int j = i; j < 6; ++j, ++k) s->H[i * 6 + j] = s->H[j * 6 + i] = v[k];
   for (int i = 0; i < 6; ++i) s->b[i] = v[21 + i];
   s->total_error = v[27];
+  const_cast<vslam_aligner*>(h)->last_total_error = v[27];
   s->number_of_inliers = (int32_t)std::llrint(v[28]);
   s->number_of_outliers = h->n - s->number_of_inliers;   // stereouv :186 / uvd :170
 }
@@ -139,6 +142,27 @@ int one_round(vslam_aligner* h, const vslam_aligner_parameters* p, int ignore_ou
 }
 
 }  // namespace
+
+namespace vslam {
+int fetch_aligner_results(vslam_aligner* h, AlignerResults* out) {
+  if (!h || !out) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  if (!h->uploaded) return fail(VSLAM_ERR_STATE, "the aligner holds no correspondences");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (h->n && !h->host_out_valid) {
+    CUDA_TRY(cudaMemcpyAsync(errors_of(h->h_io, h), errors_of(h->d_io, h), out_bytes(h->stride), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->host_out_valid = true;
+  }
+  out->n = h->n;
+  out->device = h->device;
+  out->d_errors = errors_of(h->d_io, h);
+  out->d_inliers = inliers_of(h->d_io, h);
+  out->h_errors = errors_of(h->h_io, h);
+  out->h_inliers = inliers_of(h->h_io, h);
+  out->total_error = h->last_total_error;
+  return VSLAM_OK;
+}
+}  // namespace vslam
 
 extern "C" {
 

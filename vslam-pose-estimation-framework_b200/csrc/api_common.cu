@@ -52,7 +52,11 @@ int vslam_device_count(void) {
 
 int vslam_host_alloc(void** ptr, size_t bytes) {
   if (!ptr) return vslam::fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
-  CUDA_TRY(cudaMallocHost(ptr, bytes ? bytes : 1));
+  // VSLAM_HOST_ALLOC_WC=1: write-combined pinned memory for buffers the host only WRITES (image upload sources): the
+  // DMA engine reads it without snooping the CPU caches (measurement switch; CPU reads of such memory are slow)
+  const char* e = std::getenv("VSLAM_HOST_ALLOC_WC");   // read per call: a host sets it around its upload buffers only
+  const bool wc = e && atoi(e) != 0;
+  CUDA_TRY(cudaHostAlloc(ptr, bytes ? bytes : 1, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
   return VSLAM_OK;
 }
 

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/vslam_b200.h"
+#include "aligner_internal.h"
 #include "api_common.h"
 #include "host_math.h"
 #include "kernels.cuh"
@@ -985,6 +986,37 @@ int vslam_fpg_track(vslam_fpg* h, const vslam_previous_point* previous, int32_t 
       tracks[i].index_right = s2r_r[tracks[i].index_right];
     }
   }
+  return VSLAM_OK;
+}
+
+int vslam_fpg_prune_tracks(vslam_fpg* h, vslam_aligner* aligner, double maximum_error_kernel, int32_t* n_kept,
+                           uint8_t* kept) {
+  VSLAM_NVTX("vslam_fpg_prune_tracks [PoseTracker3D::_prunePoints]");
+  if (!h || !aligner) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null handle");
+  if (h->n_device_tracks < 0) return fail(VSLAM_ERR_STATE, "no tracks of vslam_fpg_track on the device");
+  AlignerResults r;
+  int rc = fetch_aligner_results(aligner, &r);
+  if (rc) return rc;
+  if (r.device != h->device) return fail(VSLAM_ERR_INVALID_ARGUMENT, "generator and aligner live on different devices");
+  const int n = h->n_device_tracks;
+  if (r.n != n) return fail(VSLAM_ERR_STATE, "the aligner holds %d correspondences, the last track() produced %d", r.n, n);
+  if (n > 8192) return fail(VSLAM_ERR_CAPACITY, "at most 8192 tracks can be pruned on the device");
+  // the branch of pose_tracker_3d.cpp:441 on the host (averageError = total error / correspondences, base_aligner.h:46),
+  // the per-point test and the ordered compaction on the device; the count comes from the host copy of the same flags
+  const bool inliers_only = n > 0 && r.total_error / n < maximum_error_kernel;
+  const double cap = 100 * maximum_error_kernel;
+  int count = 0;
+  for (int k = 0; k < n; ++k) {
+    const bool keep = inliers_only ? r.h_inliers[k] != 0 : (r.h_errors[k] != -1.0 && r.h_errors[k] < cap);
+    if (kept) kept[k] = keep;
+    count += keep;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  launch_prune_tracked(h->d_tracked, n, r.d_errors, r.d_inliers, inliers_only, cap, h->lanes[0].stream);
+  ++h->launches;
+  CUDA_TRY(cudaGetLastError());
+  h->n_device_tracks = count;
+  if (n_kept) *n_kept = count;
   return VSLAM_OK;
 }
 

@@ -190,6 +190,28 @@ struct LandmarkMeasurement {
   double camera_coordinates[3];
   double inverse_depth_meters;
 };
+// PoseTracker3D::_prunePoints on the bin pre-load records of the last track() (at most 8192), ordered, in place
+void launch_prune_tracked(TrackedPoint* tracked, int n, const double* errors, const uint8_t* inliers, int inliers_only,
+                          double error_cap, cudaStream_t stream);
+// device-resident landmark map (vslam_landmark_map): per landmark a chain of 32-measurement blocks, its world
+// coordinates and update count; per frame slot the two poses every measurement of that frame is evaluated with
+struct LandmarkMapBuffers {
+  int32_t* count;                  // [max_landmarks] measurements held
+  int32_t* table;                  // [max_landmarks][blocks_per_landmark] block ids
+  LandmarkMeasurement* blocks;     // [max_blocks][32]
+  int32_t* next_block;             // pool cursor
+  int32_t* error;                  // set when the pool or a landmark's table is exhausted
+  double* world;                   // [max_landmarks][3]
+  uint32_t* updates;               // [max_landmarks]
+  const double* world_to_camera;   // [max_frames][12]
+  const double* camera_to_world;   // [max_frames][12]
+  int blocks_per_landmark, max_blocks;
+};
+void launch_landmark_create(const LandmarkMapBuffers& b, int n_new, int first_id, const int32_t* track_offsets,
+                            const LandmarkMeasurement* tracks, const double* world_init, cudaStream_t stream);
+void launch_landmark_map_update(const LandmarkMapBuffers& b, int n, const int32_t* ids, const double* camera_coordinates,
+                                int frame, uint32_t max_iterations, double max_err2, uint8_t* outcome, int32_t* iterations,
+                                double* world_out, uint32_t* updates_out, cudaStream_t stream);
 // one warp per landmark: Landmark::update's Gauss-Newton (landmark.cpp:82-167); poses are row-major 3x4 per frame
 void launch_landmark_update(int n_landmarks, const int32_t* offsets, const LandmarkMeasurement* measurements,
                             const double* world_to_camera, const double* camera_to_world, uint32_t max_iterations,

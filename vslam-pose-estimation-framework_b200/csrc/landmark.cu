@@ -21,23 +21,51 @@ __device__ __forceinline__ void ordered_add(double (*s)[33], const double* terms
                                             double& running) {
   for (int c = 0; c < n_terms; ++c) s[c][lane] = terms[c];
   __syncwarp();
-  if (lane < n_terms)
-    for (int l = 0; l < count; ++l) running = running + s[lane][l];
+  if (lane < n_terms) {
+    // the additions are a dependent chain (measurement order is the parity contract), the loads are not: eight at a time
+    // are issued ahead of the chain instead of one shared-memory round trip per addition
+    const double* row = s[lane];
+    int l = 0;
+    for (; l + 8 <= count; l += 8) {
+      const double v0 = row[l], v1 = row[l + 1], v2 = row[l + 2], v3 = row[l + 3];
+      const double v4 = row[l + 4], v5 = row[l + 5], v6 = row[l + 6], v7 = row[l + 7];
+      running = running + v0;
+      running = running + v1;
+      running = running + v2;
+      running = running + v3;
+      running = running + v4;
+      running = running + v5;
+      running = running + v6;
+      running = running + v7;
+    }
+    for (; l < count; ++l) running = running + row[l];
+  }
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kLmWarps * 32) landmark_update_kernel(
-    int n_landmarks, const int32_t* __restrict__ offsets, const LandmarkMeasurement* __restrict__ measurements,
-    const double* __restrict__ world_to_camera, const double* __restrict__ camera_to_world, uint32_t max_iterations,
-    double max_err2, double* __restrict__ world, uint32_t* __restrict__ number_of_updates,
-    uint8_t* __restrict__ outcome, int32_t* __restrict__ iterations) {
-  __shared__ double s_terms[kLmWarps][kLmTerms][33];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lm = blockIdx.x * kLmWarps + warp;
-  if (lm >= n_landmarks) return;                       // warps are independent (no block barrier)
-  double (*s)[33] = s_terms[warp];
-  const int begin = offsets[lm], n = offsets[lm + 1] - begin;
-  const LandmarkMeasurement* ms = measurements + begin;
+// where the measurement history of a landmark lives: one CSR segment of a caller-provided array (vslam_landmark_optimizer)
+// or the chained 32-entry blocks of the device-resident map (vslam_landmark_map)
+struct CsrHistory {
+  const LandmarkMeasurement* ms;
+  __device__ __forceinline__ LandmarkMeasurement at(int m) const { return ms[m]; }
+};
+struct BlockHistory {
+  const int32_t* table;                 // block ids of this landmark
+  const LandmarkMeasurement* blocks;    // [n_blocks][32]
+  __device__ __forceinline__ LandmarkMeasurement at(int m) const { return blocks[(size_t)table[m >> 5] * 32 + (m & 31)]; }
+};
+
+// Landmark::update for landmark `lm` (state in world / number_of_updates), history `ms` of n measurements; results of
+// the call are also written at position `slot` of outcome / iterations (and of the compact copies when given)
+template <class History>
+__device__ __forceinline__ void landmark_update_warp(const History ms, int n, int lm, int slot, double (*s)[33],
+                                                     const double* __restrict__ world_to_camera,
+                                                     const double* __restrict__ camera_to_world, uint32_t max_iterations,
+                                                     double max_err2, double* __restrict__ world,
+                                                     uint32_t* __restrict__ number_of_updates, uint8_t* __restrict__ outcome,
+                                                     int32_t* __restrict__ iterations, double* __restrict__ world_out,
+                                                     uint32_t* __restrict__ updates_out) {
+  const int lane = threadIdx.x & 31;
   double x[3] = {world[3 * (size_t)lm], world[3 * (size_t)lm + 1], world[3 * (size_t)lm + 2]};   // :82
   const uint32_t updates_so_far = number_of_updates[lm];
   double total_previous = 0;                                                                      // :88
@@ -53,7 +81,7 @@ __global__ void __launch_bounds__(kLmWarps * 32) landmark_update_kernel(
       for (int c = 0; c < kLmTerms; ++c) terms[c] = 0.0;   // +0.0 is neutral for sums that start at +0.0
       bool outlier = false;
       if (m < n) {
-        const LandmarkMeasurement q = ms[m];
+        const LandmarkMeasurement q = ms.at(m);
         const double* W = world_to_camera + 12 * (size_t)q.frame;
         double w_[12];
 #pragma unroll
@@ -112,7 +140,7 @@ __global__ void __launch_bounds__(kLmWarps * 32) landmark_update_kernel(
           const int m = c0 + lane;
           double terms[3] = {0.0, 0.0, 0.0};
           if (m < n) {
-            const LandmarkMeasurement q = ms[m];
+            const LandmarkMeasurement q = ms.at(m);
             const double* C = camera_to_world + 12 * (size_t)q.frame;
 #pragma unroll
             for (int r = 0; r < 3; ++r)
@@ -130,12 +158,110 @@ __global__ void __launch_bounds__(kLmWarps * 32) landmark_update_kernel(
     total_previous = total;                                                                       // :166
   }
   if (lane == 0) {
-    if (outcome) outcome[lm] = (uint8_t)result;
-    if (iterations) iterations[lm] = (int32_t)it;
+    if (outcome) outcome[slot] = (uint8_t)result;
+    if (iterations) iterations[slot] = (int32_t)it;
+  }
+  if (world_out) {     // the state of the landmark after the call, compact (one device -> host copy for the frame)
+    __syncwarp();
+    if (lane < 3) world_out[3 * (size_t)slot + lane] = world[3 * (size_t)lm + lane];
+    if (lane == 0) updates_out[slot] = number_of_updates[lm];
   }
 }
 
+__global__ void __launch_bounds__(kLmWarps * 32) landmark_update_kernel(
+    int n_landmarks, const int32_t* __restrict__ offsets, const LandmarkMeasurement* __restrict__ measurements,
+    const double* __restrict__ world_to_camera, const double* __restrict__ camera_to_world, uint32_t max_iterations,
+    double max_err2, double* __restrict__ world, uint32_t* __restrict__ number_of_updates,
+    uint8_t* __restrict__ outcome, int32_t* __restrict__ iterations) {
+  __shared__ double s_terms[kLmWarps][kLmTerms][33];
+  const int warp = threadIdx.x >> 5;
+  const int lm = blockIdx.x * kLmWarps + warp;
+  if (lm >= n_landmarks) return;                       // warps are independent (no block barrier)
+  const int begin = offsets[lm], n = offsets[lm + 1] - begin;
+  landmark_update_warp(CsrHistory{measurements + begin}, n, lm, lm, s_terms[warp], world_to_camera, camera_to_world,
+                       max_iterations, max_err2, world, number_of_updates, outcome, iterations, nullptr, nullptr);
+}
+
+// ---- the device-resident landmark map (vslam_landmark_map): histories stay in HBM as chains of 32-measurement blocks;
+// a frame appends ONE measurement per tracked landmark and refines it, nothing is re-uploaded.
+// append: measurement number m of landmark lm goes to block table[lm][m / 32] (a new block is taken from the pool when
+// m is a multiple of 32), slot m % 32.  Returns false when the pool or the table is exhausted.
+__device__ __forceinline__ bool append_measurement(const LandmarkMapBuffers& b, int lm, const LandmarkMeasurement& q) {
+  const int m = b.count[lm];
+  int32_t* table = b.table + (size_t)lm * b.blocks_per_landmark;
+  if ((m & 31) == 0) {
+    if ((m >> 5) >= b.blocks_per_landmark) return false;
+    const int blk = atomicAdd(b.next_block, 1);
+    if (blk >= b.max_blocks) return false;
+    table[m >> 5] = blk;
+  }
+  b.blocks[(size_t)table[m >> 5] * 32 + (m & 31)] = q;
+  b.count[lm] = m + 1;
+  return true;
+}
+
+// Landmark::Landmark (landmark.cpp:8-33) for n_new landmarks: the track of framepoints that gives birth to the landmark
+// becomes its first measurements (newest first, as the constructor walks the track), _number_of_updates their number,
+// _world_coordinates the average the host computed from the framepoints' world coordinates.  One thread per landmark.
+__global__ void __launch_bounds__(128) landmark_create_kernel(LandmarkMapBuffers b, int n_new, int first_id,
+                                                              const int32_t* __restrict__ track_offsets,
+                                                              const LandmarkMeasurement* __restrict__ tracks,
+                                                              const double* __restrict__ world_init) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_new) return;
+  const int lm = first_id + i;
+  b.count[lm] = 0;
+  for (int k = track_offsets[i]; k < track_offsets[i + 1]; ++k)
+    if (!append_measurement(b, lm, tracks[k])) atomicExch(b.error, 1);
+  for (int d = 0; d < 3; ++d) b.world[3 * (size_t)lm + d] = world_init[3 * (size_t)i + d];
+  b.updates[lm] = (uint32_t)(track_offsets[i + 1] - track_offsets[i]);
+}
+
+// PoseTracker3D::_updatePoints for the landmarks a frame tracked (pose_tracker_3d.cpp:486-519): Landmark::update =
+// append the framepoint's measurement (landmark.cpp:71-79), then the Gauss-Newton refinement over the whole history.
+__global__ void __launch_bounds__(kLmWarps * 32) landmark_map_update_kernel(
+    LandmarkMapBuffers b, int n, const int32_t* __restrict__ ids, const double* __restrict__ camera_coordinates, int frame,
+    uint32_t max_iterations, double max_err2, uint8_t* __restrict__ outcome, int32_t* __restrict__ iterations,
+    double* __restrict__ world_out, uint32_t* __restrict__ updates_out) {
+  __shared__ double s_terms[kLmWarps][kLmTerms][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * kLmWarps + warp;
+  if (i >= n) return;
+  const int lm = ids[i];
+  int ok = 1;
+  if (lane == 0) {
+    LandmarkMeasurement q;                                       // Landmark::Measurement(framepoint), landmark.h:21-23
+    q.frame = frame;
+    q.reserved = 0;
+    for (int d = 0; d < 3; ++d) q.camera_coordinates[d] = camera_coordinates[3 * (size_t)i + d];
+    q.inverse_depth_meters = 1 / q.camera_coordinates[2];
+    ok = append_measurement(b, lm, q) ? 1 : 0;
+    if (!ok) atomicExch(b.error, 1);
+    __threadfence_block();
+  }
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  if (!ok) return;
+  const int count = b.count[lm];
+  landmark_update_warp(BlockHistory{b.table + (size_t)lm * b.blocks_per_landmark, b.blocks}, count, lm, i, s_terms[warp],
+                       b.world_to_camera, b.camera_to_world, max_iterations, max_err2, b.world, b.updates, outcome,
+                       iterations, world_out, updates_out);
+}
+
 }  // namespace
+
+void launch_landmark_create(const LandmarkMapBuffers& b, int n_new, int first_id, const int32_t* track_offsets,
+                            const LandmarkMeasurement* tracks, const double* world_init, cudaStream_t stream) {
+  if (n_new <= 0) return;
+  landmark_create_kernel<<<(n_new + 127) / 128, 128, 0, stream>>>(b, n_new, first_id, track_offsets, tracks, world_init);
+}
+
+void launch_landmark_map_update(const LandmarkMapBuffers& b, int n, const int32_t* ids, const double* camera_coordinates,
+                                int frame, uint32_t max_iterations, double max_err2, uint8_t* outcome, int32_t* iterations,
+                                double* world_out, uint32_t* updates_out, cudaStream_t stream) {
+  if (n <= 0) return;
+  landmark_map_update_kernel<<<(n + kLmWarps - 1) / kLmWarps, kLmWarps * 32, 0, stream>>>(
+      b, n, ids, camera_coordinates, frame, max_iterations, max_err2, outcome, iterations, world_out, updates_out);
+}
 
 void launch_landmark_update(int n_landmarks, const int32_t* offsets, const LandmarkMeasurement* measurements,
                             const double* world_to_camera, const double* camera_to_world, uint32_t max_iterations,

@@ -500,4 +500,49 @@ void launch_recover(const Geometry& g, const StereoParams& sp, const Buffers& b,
                                                            valid, desc, out, n_out);
 }
 
+// PoseTracker3D::_prunePoints (reference src/position_tracking/pose_tracker_3d.cpp:437-472) on the bin pre-load records of
+// the last track(): record k belongs to correspondence k of the aligner; the kept records are compacted in order (their
+// position is what compute() reports for a pre-loaded point), in place -- every thread reads its contiguous share
+// before anyone writes.  keep = inlier (average error below the kernel) or error != -1 && error < 100 kernel.
+namespace {
+constexpr int kPruneThreads = 1024;
+__global__ void __launch_bounds__(kPruneThreads) prune_tracked_kernel(TrackedPoint* __restrict__ tracked, int n,
+                                                                      const double* __restrict__ errors,
+                                                                      const uint8_t* __restrict__ inliers,
+                                                                      int inliers_only, double error_cap) {
+  __shared__ int s_warp[kPruneThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kPer = 8;                       // up to 8192 tracks
+  const int begin = tid * kPer;
+  TrackedPoint mine[kPer];
+  int kept = 0;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int k = begin + j;
+    if (k < n) {
+      const bool keep = inliers_only ? inliers[k] != 0 : (errors[k] != -1.0 && errors[k] < error_cap);
+      if (keep) mine[kept++] = tracked[k];
+    }
+  }
+  int inc = kept;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();                              // (also: every record has been read)
+  int base = 0;
+  for (int w = 0; w < warp; ++w) base += s_warp[w];
+  const int first = base + inc - kept;
+  for (int j = 0; j < kept; ++j) tracked[first + j] = mine[j];
+}
+}  // namespace
+
+void launch_prune_tracked(TrackedPoint* tracked, int n, const double* errors, const uint8_t* inliers, int inliers_only,
+                          double error_cap, cudaStream_t stream) {
+  if (n <= 0) return;
+  prune_tracked_kernel<<<1, kPruneThreads, 0, stream>>>(tracked, n, errors, inliers, inliers_only, error_cap);
+}
+
 }  // namespace vslam
