@@ -222,7 +222,10 @@ __device__ __forceinline__ uint32_t brief_word(const uint8_t* c) {
 // blurred pixels while the threads compact the tile's keypoints into a list; then one lane per keypoint evaluates the
 // 256 tests straight from the shared tile (offsets are compile-time immediates).  Every blurred byte is fetched about
 // 1.7x (halo) instead of once per overlapping 26 x 32 patch (~5x), and no per-keypoint staging instructions remain.
-constexpr int DT_W = 224, DT_H = 64;            // keypoint-centre area of a tile
+#ifndef VSLAM_DT_H
+#define VSLAM_DT_H 64
+#endif
+constexpr int DT_W = 224, DT_H = VSLAM_DT_H;    // keypoint-centre area of a tile
 constexpr int DT_BW = 256, DT_BH = DT_H + 26;   // TMA box: columns x0-15 .. x0+240, rows y0-13 .. y0+76
 constexpr int DT_X = 15;                        // the box starts 15 px left of the tile: x0 - 15 = 16 (1 + 14 k), and TMA
                                                 // needs every row of the box to start at a 16-byte aligned address
