@@ -10,6 +10,8 @@
 // ticket after which the last block adds the block partials in a fixed order -> run-to-run deterministic).
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "gn_math.h"
 #include "kernels.cuh"
 
@@ -219,6 +221,182 @@ __global__ void __launch_bounds__(kThreads) linearize_kernel(int n, AlignerBuffe
   }
 }
 
+// solve6 of gn_math.h (Eigen::FullPivLU<Matrix6>::solve) by ONE WARP, bit-identical to the single-thread form: lane j < 6
+// holds column j of the matrix, lane 6 the right-hand side as a seventh column (row swaps and eliminations act on it
+// exactly as on the others).  The single-thread form indexes its arrays with the run-time pivot position, i.e. lives in
+// local memory, and costs ~8 us per Gauss-Newton round; here every index is a compile-time constant or a select.
+// Every lane of the warp must call; every lane receives x[6].
+__device__ __forceinline__ void solve6_warp(const double* H /* 36, row-major */, const double* rhs, double x[6]) {
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  double a[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) a[r] = lane < 6 ? H[r * 6 + lane] : (lane == 6 ? rhs[r] : 0.0);
+  int perm = lane;                 // lane j < 6: perm[j]
+  int rank = 6;
+  double maxpivot = 0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    if (k < rank) {               // (uniform: after a zero pivot the remaining steps are skipped, as the break does)
+      // ---- complete pivoting: the first element in row-major order that attains the maximum of |A[i][j]|, i, j >= k
+      double best = -1;
+      int bi = k;
+      if (lane >= k && lane < 6) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+          if (r >= k && fabs(a[r]) > best) {
+            best = fabs(a[r]);
+            bi = r;
+          }
+      }
+      int bj = lane;
+#pragma unroll
+      for (int o = 4; o; o >>= 1) {
+        const double ov = __shfl_xor_sync(full, best, o);
+        const int oi = __shfl_xor_sync(full, bi, o), oj = __shfl_xor_sync(full, bj, o);
+        if (ov > best || (ov == best && (oi < bi || (oi == bi && oj < bj)))) {
+          best = ov;
+          bi = oi;
+          bj = oj;
+        }
+      }
+      // lanes 0..7 now agree; everyone takes lane 0's
+      const double biggest = __shfl_sync(full, best, 0);
+      const int pr = __shfl_sync(full, bi, 0), pc = __shfl_sync(full, bj, 0);
+      if (biggest == 0) {
+        rank = k;
+      } else {
+        if (biggest > maxpivot) maxpivot = biggest;
+        if (pr != k) {            // row swap (the right-hand side in lane 6 follows)
+          const double vk = a[k];
+          double vp = vk;
+#pragma unroll
+          for (int r = 0; r < 6; ++r)
+            if (r == pr) vp = a[r];
+#pragma unroll
+          for (int r = 0; r < 6; ++r)
+            if (r == pr) a[r] = vk;
+          a[k] = vp;
+        }
+        {                          // column swap: lanes k and pc exchange their columns and their perm entry
+          const int partner = pc != k ? (lane == k ? pc : (lane == pc ? k : lane)) : lane;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) a[r] = __shfl_sync(full, a[r], partner);
+          perm = __shfl_sync(full, perm, partner);
+        }
+        // ---- elimination: f_i = A[i][k] / A[k][k] from column k (lane k), then A[i][j] -= f_i A[k][j] in every column
+        double f[6];
+        const double pivot = __shfl_sync(full, a[k], k);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) f[r] = r > k ? __shfl_sync(full, a[r], k) / pivot : 0.0;
+        if (lane == k) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r)
+            if (r > k) a[r] = f[r];
+        } else if (lane > k && lane <= 6) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r)
+            if (r > k) a[r] = a[r] - f[r] * a[k];
+        }
+      }
+    }
+  }
+  // Eigen::FullPivLU::rank(): only pivots above |largest pivot| * epsilon * size are used by solve()
+  {
+    double diag = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+      if (r == lane) diag = a[r];
+    const bool used = lane < rank && fabs(diag) > maxpivot * (2.220446049250313e-16 * 6);
+    rank = __popc(__ballot_sync(full, used));
+  }
+  // ---- back substitution, every lane redundantly on a gathered copy of U and the transformed right-hand side
+  double U[6][6], bb[6], y[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    bb[i] = __shfl_sync(full, a[i], 6);
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      U[i][j] = j >= i ? __shfl_sync(full, a[i], j) : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) y[i] = 0;
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    if (i < rank) {
+      double sum = bb[i];
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        if (j > i && j < rank) sum = sum - U[i][j] * y[j];
+      y[i] = sum / U[i][i];
+    }
+  }
+  // x[perm[i]] = y[i]
+#pragma unroll
+  for (int t = 0; t < 6; ++t) x[t] = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int pi = __shfl_sync(full, perm, i);
+#pragma unroll
+    for (int t = 0; t < 6; ++t)
+      if (t == pi) x[t] = y[i];
+  }
+}
+
+// oneRound (:190-207 / :174-191) + the converge state machine (:213-247 / :197-233) for one finished linearisation:
+// damped system, full-pivot solve, pose update, bookkeeping in *ctl (global memory in the grid kernel, shared memory in
+// the cluster kernel).  Called by the WHOLE first warp of the block (the solve is warp-cooperative); lane 0 writes.
+// `s_H` is a 36-double scratch in shared memory.
+__device__ __forceinline__ void gn_step(GnControl* ctl, const double* s_sys, const double* s_T, double* s_H, int n,
+                                        const GnParams& p) {
+  const int lane = threadIdx.x & 31;
+  {   // H as the single-thread form builds it: both triangles from the packed upper one, then the damping on the diagonal
+    int k = 0;
+    for (int i = 0; i < 6; ++i)
+      for (int j = i; j < 6; ++j, ++k)
+        if (lane == 0) s_H[i * 6 + j] = s_H[j * 6 + i] = s_sys[k];
+    __syncwarp();
+    if (lane < 6) s_H[lane * 6 + lane] += p.damping * n;
+    __syncwarp();
+  }
+  double nb[6], dx[6];
+  for (int i = 0; i < 6; ++i) nb[i] = -s_sys[21 + i];
+  solve6_warp(s_H, nb, dx);
+  if (lane != 0) return;
+  double T[12];
+  for (int i = 0; i < 12; ++i) T[i] = s_T[i];
+  apply_update(dx, T);
+  for (int i = 0; i < 12; ++i) ctl->T[i] = T[i];
+  for (int i = 0; i < 36; ++i) ctl->H[i] = s_H[i];
+  const double total_error = s_sys[27];
+  const int inliers = (int)llrint(s_sys[28]);
+  const int outliers = n - inliers;
+  const double prev = ctl->total_error_previous;
+  int rounds = ctl->rounds + 1, done = 0, converged = 0, phase = ctl->phase, it = ctl->iteration;
+  if (phase == 0) {
+    if (p.error_delta > fabs(prev - total_error)) {
+      if (inliers > p.inlier_gate && inliers > outliers && p.max_iterations > 0) {
+        phase = 1;      // inlier-only rounds (:224-236)
+        it = 0;
+      } else {
+        done = converged = 1;
+      }
+    } else if (++it >= p.max_iterations) {
+      done = 1;         // "system did not converge" (:250-255)
+    }
+  } else {
+    if (fabs(prev - total_error) < p.error_delta || ++it >= p.max_iterations) done = converged = 1;
+  }
+  ctl->total_error_previous = total_error;
+  ctl->rounds = rounds;
+  ctl->phase = phase;
+  ctl->iteration = it;
+  ctl->ignore = phase;
+  ctl->converged = converged;
+  __threadfence();
+  ctl->done = done;
+}
+
 // Fused Gauss-Newton: BaseAligner::converge (reference stereouv_aligner.cpp:210-264, uvd_aligner.cpp:194-248) as ONE
 // persistent cooperative kernel -- per round: linearize (same per-point code and the same ordered reduction as
 // linearize_kernel, so H and b are bit-identical to the stepwise path), grid barrier, block 0 solves the damped 6x6
@@ -233,6 +411,7 @@ __global__ void __launch_bounds__(kThreads) converge_kernel(int n, AlignerBuffer
   __shared__ double s_part[kThreads / 32][kAcc];
   __shared__ double s_T[12];
   __shared__ double s_sys[32];
+  __shared__ double s_H[36];
   __shared__ int s_ignore;
 
   for (;;) {
@@ -277,54 +456,121 @@ __global__ void __launch_bounds__(kThreads) converge_kernel(int n, AlignerBuffer
         }
         __syncthreads();
       }
-      if (threadIdx.x == 0) {
-        // ---- oneRound (:190-207 / :174-191)
-        double H[36], nb[6], dx[6], T[12];
-        int k = 0;
-        for (int i = 0; i < 6; ++i)
-          for (int j = i; j < 6; ++j, ++k) H[i * 6 + j] = H[j * 6 + i] = s_sys[k];
-        for (int i = 0; i < 6; ++i) {
-          H[i * 6 + i] += p.damping * n;
-          nb[i] = -s_sys[21 + i];
-        }
-        for (int i = 0; i < 12; ++i) T[i] = s_T[i];
-        solve6(H, nb, dx);
-        apply_update(dx, T);
-        for (int i = 0; i < 12; ++i) ctl->T[i] = T[i];
-        for (int i = 0; i < 36; ++i) ctl->H[i] = H[i];
-        // ---- converge state machine (:213-247 / :197-233)
-        const double total_error = s_sys[27];
-        const int inliers = (int)llrint(s_sys[28]);
-        const int outliers = n - inliers;
-        const double prev = ctl->total_error_previous;
-        int rounds = ctl->rounds + 1, done = 0, converged = 0, phase = ctl->phase, it = ctl->iteration;
-        if (phase == 0) {
-          if (p.error_delta > fabs(prev - total_error)) {
-            if (inliers > p.inlier_gate && inliers > outliers && p.max_iterations > 0) {
-              phase = 1;      // inlier-only rounds (:224-236)
-              it = 0;
-            } else {
-              done = converged = 1;
-            }
-          } else if (++it >= p.max_iterations) {
-            done = 1;         // "system did not converge" (:250-255)
-          }
-        } else {
-          if (fabs(prev - total_error) < p.error_delta || ++it >= p.max_iterations) done = converged = 1;
-        }
-        ctl->total_error_previous = total_error;
-        ctl->rounds = rounds;
-        ctl->phase = phase;
-        ctl->iteration = it;
-        ctl->ignore = phase;
-        ctl->converged = converged;
-        __threadfence();
-        ctl->done = done;
-      }
+      if (threadIdx.x < 32) gn_step(ctl, s_sys, s_T, s_H, n, p);
     }
     grid.sync();
     if (__ldcg(&ctl->done)) break;
   }
+}
+
+// The same loop for the problem sizes of a tracked frame (n <= 8 x 256 correspondences): ONE thread-block cluster
+// instead of a cooperative grid.  The CTAs of the cluster are the blocks of the grid version -- same per-point code, same
+// per-block partials, same order of the final sum, so pose and round count stay bit-identical -- but the two barriers of
+// a round are cluster barriers (hardware, no round trip through global memory), the block partials and the control
+// block live in shared memory and are read through distributed shared memory, and every thread keeps its ONE
+// correspondence in registers across the rounds.  Launched as a plain kernel with a cluster dimension.
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 1) converge_cluster_kernel(int n, AlignerBuffers b, AlignerCamera cam, GnParams p,
+                                                                    GnControl* __restrict__ ctl) {
+  constexpr int D = KIND == 0 ? 4 : 3;
+  constexpr int W = KIND == 0 ? 1 : 2;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank(), n_blocks = (int)cluster.num_blocks();
+  __shared__ double s_part[kThreads / 32][kAcc];
+  __shared__ double s_total[32];        // this block's partial sums, read by block 0
+  __shared__ double s_T[12];
+  __shared__ double s_sys[32];
+  __shared__ double s_H[36];
+  __shared__ GnControl s_ctl;           // authoritative copy in block 0
+  GnControl* ctl0 = cluster.map_shared_rank(&s_ctl, 0);
+
+  if (rank == 0) {
+    if (threadIdx.x < 12) s_ctl.T[threadIdx.x] = ctl->T[threadIdx.x];
+    if (threadIdx.x == 0) {
+      s_ctl.total_error_previous = ctl->total_error_previous;
+      s_ctl.rounds = ctl->rounds;
+      s_ctl.phase = ctl->phase;
+      s_ctl.iteration = ctl->iteration;
+      s_ctl.ignore = ctl->ignore;
+      s_ctl.converged = ctl->converged;
+      s_ctl.done = ctl->done;
+    }
+  }
+  // this thread's correspondence (the grid version's block `rank`, thread threadIdx.x, first and only iteration)
+  const int u = rank * kThreads + threadIdx.x;
+  const bool mine = u < n;
+  double m[3] = {0, 0, 0}, fx[D], om[W], wt = 0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) fx[d] = 0;
+#pragma unroll
+  for (int d = 0; d < W; ++d) om[d] = 0;
+  if (mine) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) m[d] = b.moving[d * b.stride + u];
+#pragma unroll
+    for (int d = 0; d < D; ++d) fx[d] = b.fixed[d * b.stride + u];
+#pragma unroll
+    for (int d = 0; d < W; ++d) om[d] = b.omega[d * b.stride + u];
+    wt = b.wt[u];
+  }
+  cluster.sync();
+
+  double err = -1.0;
+  uint8_t inl = 0;
+  for (;;) {
+    if (threadIdx.x < 12) s_T[threadIdx.x] = ctl0->T[threadIdx.x];
+    const int ignore_outliers = ctl0->ignore;
+    __syncthreads();
+    double acc[kAcc];
+#pragma unroll
+    for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
+    if (mine) accumulate_point<KIND>(m[0], m[1], m[2], fx, om, wt, s_T, cam, ignore_outliers, p.kernel, acc, err, inl);
+    const double total = block_reduce(acc, s_part);
+    if (threadIdx.x < kAcc) s_total[threadIdx.x] = total;
+    cluster.sync();                     // every block's partial is in its shared memory
+
+    if (rank == 0) {
+      {  // the block partials in block order, 8 interleaved slices per value -- as in linearize_kernel (n_blocks <= 8:
+         // slice `part` holds block `part`)
+        const int j = threadIdx.x & 31, part = threadIdx.x >> 5;
+        double v = 0;
+        if (j < kAcc && part < n_blocks) v += cluster.map_shared_rank(s_total, part)[j];
+        __syncthreads();
+        if (j < kAcc) s_part[part][j] = v;
+        __syncthreads();
+        if (threadIdx.x < kAcc) {
+          double s = 0;
+          for (int w = 0; w < kThreads / 32; ++w) s += s_part[w][threadIdx.x];
+          s_sys[threadIdx.x] = s;
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x < 32) gn_step(&s_ctl, s_sys, s_T, s_H, n, p);
+    }
+    cluster.sync();                     // block 0's control block is final for this round
+    if (ctl0->done) break;
+  }
+  // errors[] / inliers[] hold the last round's values as in the reference; the system and the control block go to
+  // global memory once
+  if (mine) {
+    b.errors[u] = err;
+    b.inliers[u] = inl;
+  }
+  if (rank == 0) {
+    if (threadIdx.x < kAcc) b.system[threadIdx.x] = s_sys[threadIdx.x];
+    if (threadIdx.x < 12) ctl->T[threadIdx.x] = s_ctl.T[threadIdx.x];
+    if (threadIdx.x < 36) ctl->H[threadIdx.x] = s_ctl.H[threadIdx.x];
+    if (threadIdx.x == 0) {
+      ctl->total_error_previous = s_ctl.total_error_previous;
+      ctl->rounds = s_ctl.rounds;
+      ctl->phase = s_ctl.phase;
+      ctl->iteration = s_ctl.iteration;
+      ctl->ignore = s_ctl.ignore;
+      ctl->converged = s_ctl.converged;
+      ctl->done = s_ctl.done;
+    }
+  }
+  cluster.sync();                       // no block may exit while block 0 still reads its shared memory
 }
 
 // Batched form for independent stereo pairs: one WARP per pair linearises the StereoUV problem that aligns the
@@ -415,6 +661,26 @@ cudaError_t launch_converge(int kind, int n, const AlignerBuffers& b, const Alig
   AlignerCamera cam_arg = cam;
   GnParams p_arg = p;
   void* args[] = {&n_arg, &b_arg, &cam_arg, &p_arg, &ctl};
+  // the sizes of a tracked frame: one thread-block cluster (the same blocks, cheaper barriers); anything larger, or a
+  // cluster size the device refuses: the cooperative grid
+  static bool cluster_ok = std::getenv("VSLAM_NO_CLUSTER_CONVERGE") == nullptr;
+  if (cluster_ok && grid <= 8 && n <= grid * kThreads) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = grid;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = kind == 0 ? cudaLaunchKernelEx(&cfg, converge_cluster_kernel<0>, n_arg, b_arg, cam_arg, p_arg, ctl)
+                                    : cudaLaunchKernelEx(&cfg, converge_cluster_kernel<1>, n_arg, b_arg, cam_arg, p_arg, ctl);
+    if (e == cudaSuccess) return e;
+    cudaGetLastError();                 // e.g. a cluster size this device does not schedule: use the grid kernel
+  }
   const void* fn = kind == 0 ? (const void*)converge_kernel<0> : (const void*)converge_kernel<1>;
   return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, stream);
 }
