@@ -45,7 +45,8 @@ def parse():
     ap.add_argument("--distinct", type=int, default=0,
                     help="distinct synthetic pairs generated per rank (0: 256 for weak scaling, every pair for strong)")
     ap.add_argument("--rounds", type=int, default=10, help="linearize rounds per pair per step (BASELINE config 4)")
-    ap.add_argument("--cpu-sample", type=int, default=192, help="pairs of the single-thread CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=1024,
+                    help="pairs of the single-thread CPU baseline sample (at most; the sample also ends after ~14 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --pairs per GPU; strong: --pairs in total, block-partitioned over the ranks "

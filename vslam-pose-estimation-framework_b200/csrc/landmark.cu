@@ -43,6 +43,92 @@ __device__ __forceinline__ void ordered_add(double (*s)[33], const double* terms
   __syncwarp();
 }
 
+// solve3 of gn_math.h (Eigen::FullPivLU<Matrix3>::solve, landmark.cpp:136) with every index a compile-time constant:
+// the run-time pivot position only drives predicated swaps, so the 3 x 3 system stays in registers (the generic form
+// indexes its arrays with the pivot position and lives in local memory: 160 bytes of stack per thread).  Same
+// operations in the same order: bit-identical.
+__device__ __forceinline__ void solve3_registers(const double* H, const double* rhs, double* x) {
+  double a[3][3], b[3];
+  int perm[3] = {0, 1, 2};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    b[i] = rhs[i];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) a[i][j] = H[i * 3 + j];
+  }
+  int rank = 3;
+  double maxpivot = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (k < rank) {
+      int pr = k, pc = k;
+      double biggest = -1;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          if (i >= k && j >= k && fabs(a[i][j]) > biggest) {
+            biggest = fabs(a[i][j]);
+            pr = i;
+            pc = j;
+          }
+      if (biggest == 0) {
+        rank = k;
+      } else {
+        if (biggest > maxpivot) maxpivot = biggest;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+          if (r > k && r == pr) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) swap_values(a[k][j], a[r][j]);
+            swap_values(b[k], b[r]);
+          }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (c > k && c == pc) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) swap_values(a[i][k], a[i][c]);
+            swap_values(perm[k], perm[c]);
+          }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          if (i > k) {
+            const double f = a[i][k] / a[k][k];
+            a[i][k] = f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              if (j > k) a[i][j] -= f * a[k][j];
+            b[i] -= f * b[k];
+          }
+      }
+    }
+  }
+  {
+    int r = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if (i < rank) r += fabs(a[i][i]) > maxpivot * (2.220446049250313e-16 * 3);
+    rank = r;
+  }
+  double y[3] = {0, 0, 0};
+#pragma unroll
+  for (int i = 2; i >= 0; --i)
+    if (i < rank) {
+      double sum = b[i];
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (j > i && j < rank) sum -= a[i][j] * y[j];
+      y[i] = sum / a[i][i];
+    }
+#pragma unroll
+  for (int t = 0; t < 3; ++t) x[t] = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+      if (t == perm[i]) x[t] = y[i];
+}
+
 // where the measurement history of a landmark lives: one CSR segment of a caller-provided array (vslam_landmark_optimizer)
 // or the chained 32-entry blocks of the device-resident map (vslam_landmark_map)
 struct CsrHistory {
@@ -120,7 +206,7 @@ __device__ __forceinline__ void landmark_update_warp(const History ms, int n, in
 #pragma unroll
     for (int i = 0; i < 3; ++i) nb[i] = -__shfl_sync(0xffffffffu, running, 9 + i);
     const double total = __shfl_sync(0xffffffffu, running, 12);
-    solve3(H, nb, dx);                                                                            // :136 (every lane)
+    solve3_registers(H, nb, dx);                                                                  // :136 (every lane)
 #pragma unroll
     for (int i = 0; i < 3; ++i) x[i] = x[i] + dx[i];
     if (fabs(total - total_previous) < 1e-5 || it == 999) {                                       // :139
