@@ -561,6 +561,8 @@ def sequence_latency(api, configs, synth, device):
         gen.close()
         # the same loop from C++14 (tools/sequence_runner.cpp over include/vslam_b200.hpp): what a native host pays
         out[name]["tracked_native"] = native_sequence(cfg, cam, frames)
+        # ... and the frame as one device pass (vslam_fpg_frame_step)
+        out[name]["tracked_fused"] = native_sequence(cfg, cam, frames, fused=True)
     return out
 
 
@@ -574,17 +576,23 @@ def sequence_multi(configs, synth, rank, world, device, barrier, dist, torch, de
     bw = synth.BandWorld(cam.cols, cam.rows, 8000 + rank, max_frames=frames_n)
     frames = [bw.pair(k) for k in range(frames_n)]
     alone = native_sequence(cfg, cam, frames, passes=passes, device=device) if rank == 0 else None
+    alone_fused = native_sequence(cfg, cam, frames, passes=passes, device=device, fused=True) if rank == 0 else None
     barrier()
     mine = native_sequence(cfg, cam, frames, passes=passes, device=device)
     barrier()
+    mine_fused = native_sequence(cfg, cam, frames, passes=passes, device=device, fused=True)
+    barrier()
     fps = float(mine["frames_per_s"]) if mine else 0.0
+    fps_fused = float(mine_fused["frames_per_s"]) if mine_fused else 0.0
     if dist is not None:
-        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t = torch.zeros(2 * world, dtype=torch.float64, device=dev)
         t[rank] = fps
+        t[world + rank] = fps_fused
         dist.all_reduce(t)
-        per_rank = [float(x) for x in t.tolist()]
+        per_rank = [float(x) for x in t.tolist()[:world]]
+        per_rank_fused = [float(x) for x in t.tolist()[world:]]
     else:
-        per_rank = [fps]
+        per_rank, per_rank_fused = [fps], [fps_fused]
     if rank != 0:
         return None
     out = {"workload": "%d-frame 1920x1080 band-world sequence per GPU (seeds 8000 + rank), bin 23, FAST thr 20..100; "
@@ -592,14 +600,18 @@ def sequence_multi(configs, synth, rank, world, device, barrier, dist, torch, de
                        % (frames_n, passes),
            "per_rank_frames_per_s": per_rank, "aggregate_frames_per_s": sum(per_rank),
            "rank0_alone": alone, "rank0_concurrent": mine,
-           "efficiency": (sum(per_rank) / len(per_rank)) / alone["frames_per_s"] if alone else None}
+           "efficiency": (sum(per_rank) / len(per_rank)) / alone["frames_per_s"] if alone else None,
+           "fused": {"per_rank_frames_per_s": per_rank_fused, "aggregate_frames_per_s": sum(per_rank_fused),
+                     "rank0_alone": alone_fused, "rank0_concurrent": mine_fused,
+                     "efficiency": (sum(per_rank_fused) / len(per_rank_fused)) / alone_fused["frames_per_s"]
+                     if alone_fused else None}}
     return out
 
 
 _RUNNER = {}
 
 
-def native_sequence(cfg, cam, frames, warmup=4, acfg=None, passes=1, device=0):
+def native_sequence(cfg, cam, frames, warmup=4, acfg=None, passes=1, device=0, fused=False):
     """builds tools/sequence_runner.cpp once (g++, C++14) and runs the tracked sequence through it; None when the
     compiler is missing or anything fails -- the number is informative, the run stays valid without it"""
     import tempfile
@@ -636,12 +648,18 @@ def native_sequence(cfg, cam, frames, warmup=4, acfg=None, passes=1, device=0):
             ids = visible.split(",") if visible else [str(i) for i in range(64)]
             env["CUDA_VISIBLE_DEVICES"] = ids[device]
         res = subprocess.run([_RUNNER["exe"], path, str(len(frames)), str(warmup)] + [repr(a) for a in args]
-                             + [str(passes)], capture_output=True, text=True, timeout=300, env=env)
+                             + [str(passes), str(int(fused))], capture_output=True, text=True, timeout=300, env=env)
         os.remove(path)
         if res.returncode != 0:
             return None
         r = json.loads(res.stdout.strip().splitlines()[-1])
         r["host"] = "C++14 (tools/sequence_runner.cpp)"
+        if fused:
+            r["what"] = ("vslam_fpg_frame_step: the frame as ONE graph launch and one synchronisation, points() of the "
+                         "previous frame resident on the device; results bit-identical to the stepwise calls")
+            for key in list(r):
+                if key.startswith("us_"):
+                    del r[key]
         return r
     except Exception:
         return None

@@ -237,6 +237,74 @@ int vslam_fpg_recover_points(vslam_fpg* h, const vslam_previous_point* lost, int
                              double maximum_depth_meters, double maximum_descriptor_distance_tracking,
                              vslam_recovered_point* recovered, int32_t capacity, int32_t* n_recovered);
 
+/* AlignerParameters (src/types/parameters.h:66-95) + BaseAligner thresholds (base_aligner.h:62-63) */
+typedef struct {
+  double error_delta_for_convergence;
+  double maximum_error_kernel;
+  double damping;
+  int32_t maximum_number_of_iterations;
+  int32_t minimum_number_of_inliers;
+} vslam_aligner_parameters;
+
+/* ---- One tracked frame as ONE device pass ------------------------------------------------------------------------
+ * PoseTracker3D::compute's per-frame order (src/position_tracking/pose_tracker_3d.cpp): :80 initialize, :239 track
+ * against points() of the previous frame, :124-126 / :355-357 StereoUVAligner::initialize + converge over the tracks,
+ * :437-472 _prunePoints, :210 compute.  The stepwise calls above return to the host between the stages because the
+ * reference's tracker owns that order; a host that owns its loop calls this instead: points() of the previous frame
+ * stay on the device (camera coordinates + both descriptors, 128 B each), the aligner's correspondences are packed on
+ * the device (stereouv_aligner.cpp:26-64, the branch without a landmark estimate: moving =
+ * previous->cameraCoordinatesLeft(), information = I), converge() runs as one thread-block cluster, the prune rule and
+ * the bin pre-load never leave the device, and the whole frame is one CUDA-graph launch and ONE synchronisation.
+ * Results are bit-identical to the stepwise calls in the same order (tests/test_gpu_frame_step.py).
+ * Limits: keypoint binning enabled; at most vslam_fpg_frame_step_capacity() points per frame (4096 on a B200: one
+ * 16-CTA cluster, one correspondence per thread) -- VSLAM_ERR_CAPACITY beyond, the stepwise calls have no such limit.
+ * index_left / index_right of the returned records count in the device's (row, col) order, which is the reference's
+ * keypoint order for one detector region; the descriptors travel inside frame_points. */
+typedef struct {
+  int32_t track_by_appearance;                       /* track(..., track_by_appearance_) */
+  int32_t projection_tracking_distance_pixels;       /* base_framepoint_generator.h:164 */
+  double maximum_descriptor_distance_tracking;       /* :165 */
+  vslam_aligner_parameters aligner;                  /* AlignerParameters of the pose optimiser */
+  int32_t enable_inverse_depth_as_information;       /* parameters.h:88 */
+  int32_t minimum_track_length_for_landmark_creation;/* parameters.h:259: has_landmark of the frame's points (track length >= this) */
+  double maximum_reliable_depth_meters;              /* slam_assembly.cpp:70 */
+  double minimum_reliable_depth_meters;              /* slam_assembly.cpp:69 */
+  int32_t publish_frame_points;                      /* != 0: frame_points below is filled (128 B per point) */
+  int32_t reserved;
+} vslam_frame_step_parameters;
+
+typedef struct {
+  int32_t n_left, n_right;                 /* descriptor-valid keypoints of the frame */
+  int32_t n_previous;                      /* points of the previous frame the frame was tracked against */
+  int32_t n_tracked, n_lost;               /* track(): tracks before the prune, lost points */
+  int32_t n_tracked_landmarks;             /* _number_of_tracked_landmarks */
+  int32_t n_tracks;                        /* tracks that survive _prunePoints */
+  int32_t n_new_points, n_matches;         /* compute(): framepoints appended, matches before binning */
+  int32_t aligner_rounds, aligner_converged, aligner_inliers, aligner_outliers;
+  int32_t inliers_only;                    /* the branch of pose_tracker_3d.cpp:441 */
+  double average_descriptor_distance;      /* setAverageDescriptorDistanceTracking (NaN without tracks) */
+  double aligner_total_error;
+  double previous_to_current[12];          /* the optimised motion (the prior when there was nothing to align) */
+  double information[36];                  /* _information_matrix (damped H of the last round) */
+  /* pinned memory owned by the handle, valid until the next call on it */
+  const vslam_track* tracks;               /* [n_tracks] surviving tracks, in order */
+  const uint8_t* kept;                     /* [n_tracked] 1 = track k survived */
+  const double* errors;                    /* [n_tracked] _errors of the last round */
+  const uint8_t* inliers;                  /* [n_tracked] _inliers */
+  const int32_t* lost;                     /* [n_lost] positions in the previous frame's points() */
+  const vslam_framepoint* points;          /* [n_new_points] */
+  const vslam_previous_point* frame_points;/* [n_tracks + n_new_points] points() of this frame (publish_frame_points) */
+} vslam_frame_step_result;
+
+int32_t vslam_fpg_frame_step_capacity(vslam_fpg* h);
+/* a new sequence: no previous points */
+int vslam_fpg_frame_step_reset(vslam_fpg* h);
+/* points() of the previous frame from the host (e.g. after the host re-estimated them from its landmarks) */
+int vslam_fpg_frame_step_set_previous(vslam_fpg* h, const vslam_previous_point* previous, int32_t n_previous);
+int vslam_fpg_frame_step(vslam_fpg* h, const uint8_t* left, const uint8_t* right, size_t stride_bytes, int localizing,
+                         const double previous_to_current_prior[12], const vslam_frame_step_parameters* parameters,
+                         vslam_frame_step_result* result);
+
 /* pass as n_tracked (tracked = NULL) to vslam_fpg_compute: the tracked points are those of the last
  * vslam_fpg_track, already resident on the device (no host round trip of the bin pre-load records) */
 #define VSLAM_TRACKED_FROM_LAST_TRACK (-1)
@@ -323,14 +391,7 @@ double vslam_threshold_proposal(double threshold, int32_t n_keypoints, double ta
 #define VSLAM_ALIGNER_STEREO_UV 0 /* src/aligners/stereouv_aligner.cpp */
 #define VSLAM_ALIGNER_UVD 1       /* src/aligners/uvd_aligner.cpp */
 
-/* AlignerParameters (src/types/parameters.h:66-95) + BaseAligner thresholds (base_aligner.h:62-63) */
-typedef struct {
-  double error_delta_for_convergence;
-  double maximum_error_kernel;
-  double damping;
-  int32_t maximum_number_of_iterations;
-  int32_t minimum_number_of_inliers;
-} vslam_aligner_parameters;
+/* (vslam_aligner_parameters is declared above, with vslam_fpg_frame_step) */
 
 int vslam_aligner_create(int kind, int32_t max_points, int device, vslam_aligner** out);
 int vslam_aligner_destroy(vslam_aligner* h);

@@ -144,6 +144,29 @@ class StereoFramePointGenerator {
     frame->tracks.resize(w);
   }
 
+  // PoseTracker3D::compute's per-frame order (pose_tracker_3d.cpp:80 initialize, :239 track, :355-357 StereoUVAligner
+  // initialize + converge, :437-472 _prunePoints, :210 compute) as ONE device pass with points() of the previous frame
+  // resident on the device (vslam_fpg_frame_step): frame->tracks, frame->points and frame->previous_points (= points() of
+  // this frame, when parameters.publish_frame_points) are filled from the handle's pinned result block.
+  vslam_frame_step_result trackFrame(Frame* frame, const std::array<double, 12>& previous_to_current_prior,
+                                     const vslam_frame_step_parameters& parameters) {
+    if (!frame) throw std::runtime_error("StereoFramePointGenerator::trackFrame|called with empty frame");
+    vslam_frame_step_result r;
+    check(vslam_fpg_frame_step(_handle, frame->intensity_image_left, frame->intensity_image_right, frame->image_step,
+                               frame->status == Frame::Localizing, previous_to_current_prior.data(), &parameters, &r),
+          "StereoFramePointGenerator::trackFrame");
+    frame->tracks.assign(r.tracks, r.tracks + r.n_tracks);
+    frame->points.assign(r.points, r.points + r.n_new_points);
+    if (r.frame_points) frame->previous_points.assign(r.frame_points, r.frame_points + r.n_tracks + r.n_new_points);
+    _number_of_detected_keypoints = r.n_left;
+    _number_of_tracked_landmarks = r.n_tracked_landmarks;
+    _number_of_new_points = r.n_matches;
+    _tracks_resident = false;
+    return r;
+  }
+  // a new sequence: the next trackFrame() has no previous points
+  void resetSequence() { check(vslam_fpg_frame_step_reset(_handle), "StereoFramePointGenerator::resetSequence"); }
+
   int numberOfTrackedLandmarks() const { return _number_of_tracked_landmarks; }
 
   int targetNumberOfKeypoints() const { return _target_number_of_keypoints; }

@@ -1,0 +1,176 @@
+"""vslam_fpg_frame_step -- one tracked frame as ONE device pass (graph launch + one synchronisation) -- against the
+stepwise calls in the tracker's order (initialize -> track -> StereoUVAligner initialize + converge -> _prunePoints ->
+compute -> points() of the frame for the next track()), which tests/test_gpu_track.py, test_gpu_aligner.py and
+test_gpu_fpg.py pin to the oracle stage by stage: every output of every frame must be bit-identical -- tracks, lost
+list, aligner errors / inliers / pose / round count, the prune decision, the new framepoints and the 128-byte points()
+records with their descriptors."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from vslam_b200 import api, configs, synth
+
+pytestmark = pytest.mark.gpu
+
+TRACK_FIELDS = ("index_previous", "xl", "yl", "xr", "yr", "distance", "epipolar_offset", "projection_left",
+                "projection_right", "projection_right_corrected", "camera")
+POINT_FIELDS = ("xl", "yl", "xr", "yr", "distance", "epipolar_offset", "camera")
+
+
+def _prior(cam, error=0.0):
+    T = np.hstack([np.eye(3), np.zeros((3, 1))])
+    T[0, 3] = -(-cam.bx / cam.fx) / 4 + error      # the band world moves a quarter baseline per frame along x
+    return T
+
+
+class Stepwise:
+    """the tracker's per-frame order through the stage-by-stage C ABI (what tools/sequence_runner.cpp does)"""
+
+    def __init__(self, cfg, acfg, cam, D, max_distance, min_track_length=1):
+        self.cfg, self.acfg, self.cam, self.D, self.max_distance = cfg, acfg, cam, D, max_distance
+        self.min_track_length = min_track_length
+        self.gen = api.StereoFramePointGenerator(cfg, cam)
+        self.aligner = api.StereoUVAligner(acfg, max_points=8192)
+        self.previous = np.zeros(0, api.PREVIOUS_POINT)
+
+    def step(self, left, right, localizing, T_prior):
+        gen, cam, acfg = self.gen, self.cam, self.acfg
+        out = {}
+        out["n_left"], out["n_right"] = gen.initialize(left, right, localizing)
+        prev = self.previous
+        tr = gen.track(prev, T_prior, False, self.D, self.max_distance)
+        tracks = tr["tracks"]
+        out.update(n_previous=len(prev), n_tracked=len(tracks), lost=tr["lost"], n_tracked_landmarks=tr["tracked_landmarks"],
+                   average_descriptor_distance=tr["average_descriptor_distance"])
+        T = np.array(T_prior, np.float64)
+        keep = np.zeros(0, bool)
+        out.update(aligner_rounds=0, aligner_converged=0, errors=np.zeros(0), inliers=np.zeros(0, bool))
+        if len(tracks):
+            moving = np.ascontiguousarray(prev["camera_left"][tracks["index_previous"]])
+            fixed = np.stack([tracks["xl"], tracks["yl"], tracks["xr"], tracks["yr"]], 1).astype(np.float64)
+            q = acfg.maximum_reliable_depth_meters / tracks["camera"][:, 2]
+            wt = np.where(1.0 < q, 1.0, q) if acfg.enable_inverse_depth_as_information else np.ones(len(tracks))
+            self.aligner.initialize(moving, fixed, np.ones(len(tracks)), wt, cam.K, cam.baseline, cam.rows, cam.cols, T)
+            self.aligner.converge(fused=True)
+            T = np.array(self.aligner.previousToCurrent(), np.float64)
+            keep = gen.prune_tracks(self.aligner, acfg.maximum_error_kernel)
+            out.update(aligner_rounds=self.aligner.number_of_rounds,
+                       aligner_converged=int(self.aligner.has_system_converged),
+                       errors=self.aligner.errors(), inliers=self.aligner.inliers())
+        out["previous_to_current"] = np.asarray(T).reshape(3, 4)
+        out["kept"] = keep
+        kept_tracks = tracks[keep] if len(tracks) else tracks
+        out["tracks"] = kept_tracks
+        points = gen.compute(api.TRACKED_FROM_LAST_TRACK)
+        out["points"] = points
+        out["n_matches"] = gen.number_of_matches
+        _, dl = gen.features(0)
+        _, dr = gen.features(1)
+        nxt = api.make_previous_points([kept_tracks, points], dl, dr)
+        length = np.concatenate([prev["reserved"][kept_tracks["index_previous"]] + 1, np.ones(len(points), np.int32)])
+        nxt["reserved"] = length
+        nxt["has_landmark"] = length >= self.min_track_length
+        out["frame_points"] = nxt
+        self.previous = nxt
+        return out
+
+    def close(self):
+        self.gen.close()
+        self.aligner.close()
+
+
+def _compare(k, got, want, gen_fused, single_region):
+    ctx = "frame %d" % k
+    for f in ("n_left", "n_right", "n_previous", "n_tracked", "n_tracked_landmarks", "n_matches", "aligner_rounds",
+              "aligner_converged"):
+        assert got[f] == want[f], (ctx, f, got[f], want[f])
+    assert np.array_equal(got["lost"], want["lost"]), ctx
+    if want["n_tracked"]:
+        assert got["average_descriptor_distance"] == want["average_descriptor_distance"], ctx
+    else:
+        assert np.isnan(got["average_descriptor_distance"]), ctx
+    assert np.array_equal(got["errors"], want["errors"]), ctx
+    assert np.array_equal(got["inliers"], want["inliers"]), ctx
+    assert np.array_equal(got["kept"], want["kept"]), ctx
+    assert np.array_equal(got["previous_to_current"], want["previous_to_current"]), ctx      # bit-identical pose
+    assert got["n_tracks"] == len(want["tracks"]) and got["n_new_points"] == len(want["points"]), ctx
+    for f in TRACK_FIELDS:
+        assert np.array_equal(got["tracks"][f], want["tracks"][f]), (ctx, f)
+    for f in POINT_FIELDS:
+        assert np.array_equal(got["points"][f], want["points"][f]), (ctx, f)
+    if single_region:   # the device's (row, col) order IS the reference's keypoint order
+        for f in ("index_left", "index_right"):
+            assert np.array_equal(got["tracks"][f], want["tracks"][f]), (ctx, f)
+            assert np.array_equal(got["points"][f], want["points"][f]), (ctx, f)
+    a, b = got["frame_points"], want["frame_points"]
+    assert len(a) == len(b), ctx
+    for f in ("camera_left", "world", "descriptor_left", "descriptor_right", "epipolar_offset", "has_landmark",
+              "keypoint_size", "reserved"):
+        assert np.array_equal(a[f], b[f]), (ctx, f)
+
+
+@pytest.mark.parametrize("cfg_name,frames,prior_error,min_track_length", [
+    ("kitti", 8, 0.0, 1), ("kitti", 5, 0.05, 3), ("euroc", 6, 0.0, 1), ("kitti_fast", 5, 0.02, 2), ("hd", 4, 0.0, 1)])
+def test_frame_step_equals_the_stepwise_calls(cfg_name, frames, prior_error, min_track_length):
+    cfg, acfg = configs.BY_NAME[cfg_name], configs.ALIGNER_BY_NAME[cfg_name]
+    cam = synth.camera(cfg.camera)
+    world = synth.BandWorld(cam.cols, cam.rows, 31 + frames, max_frames=frames)
+    D, max_distance = 25, 40.0
+    ref = Stepwise(cfg, acfg, cam, D, max_distance, min_track_length)
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    assert gen.frame_step_capacity() >= 2048
+    gen.frame_step_reset()
+    T = _prior(cam, prior_error)
+    total_tracks = total_pruned = 0
+    for k in range(frames):
+        left, right = world.pair(k)
+        want = ref.step(left, right, k == 0, T)
+        got = gen.frame_step(left, right, k == 0, T, acfg, False, D, max_distance, min_track_length)
+        _compare(k, got, want, gen, gen.number_of_detectors == 1)
+        assert np.array_equal(gen.thresholds, ref.gen.thresholds), k
+        total_tracks += got["n_tracks"]
+        total_pruned += got["n_tracked"] - got["n_tracks"]
+    assert total_tracks > 100 * (frames - 1)
+    if prior_error:
+        assert total_pruned > 0            # the prune rule was exercised
+    assert gen.graph_launch_count >= frames - 1
+    ref.close()
+    gen.close()
+
+
+def test_frame_step_with_previous_points_from_the_host_and_reset():
+    cfg, acfg = configs.KITTI, configs.KITTI_ALIGNER
+    cam = synth.camera(cfg.camera)
+    world = synth.BandWorld(cam.cols, cam.rows, 77, max_frames=3)
+    ref = Stepwise(cfg, acfg, cam, 25, 40.0)
+    T = _prior(cam)
+    ref.step(*world.pair(0), True, T)
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    # the generator's thresholds follow the same one-frame history; the previous points come from the host
+    gen.initialize(*world.pair(0), True)
+    gen.compute()
+    gen.frame_step_set_previous(ref.previous)
+    want = ref.step(*world.pair(1), False, T)
+    got = gen.frame_step(*world.pair(1), False, T, acfg, False, 25, 40.0)
+    _compare(1, got, want, gen, True)
+    assert got["n_tracks"] > 200
+    # a new sequence: nothing to track against, the frame is a first frame again
+    gen.frame_step_reset()
+    got = gen.frame_step(*world.pair(2), True, T, acfg, False, 25, 40.0)
+    assert got["n_previous"] == 0 and got["n_tracked"] == 0 and got["n_tracks"] == 0 and got["aligner_rounds"] == 0
+    assert np.array_equal(got["previous_to_current"], T)
+    assert got["n_new_points"] > 200 and len(got["frame_points"]) == got["n_new_points"]
+    ref.close()
+    gen.close()
+
+
+def test_frame_step_needs_binning():
+    cfg = dataclasses.replace(configs.KITTI, enable_keypoint_binning=False)
+    cam = synth.camera(cfg.camera)
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    assert gen.frame_step_capacity() == 0
+    left, right = synth.band_world_pair(cfg.camera, 3)
+    with pytest.raises(api.VslamError):
+        gen.frame_step(left, right, True, _prior(cam), configs.KITTI_ALIGNER, False, 25, 40.0)
+    gen.close()

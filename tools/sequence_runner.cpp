@@ -4,7 +4,9 @@
 // pre-loaded) driven from C++14 through include/vslam_b200.hpp, i.e. what the adapters do per frame minus the reference's
 // object graph.  bench.py builds and runs it to report the single-sequence latency without the Python harness in the loop.
 //
-//   sequence_runner <frames.u8> <n_frames> <warmup> <24 configuration numbers, see below> [passes]
+//   sequence_runner <frames.u8> <n_frames> <warmup> <24 configuration numbers, see below> [passes [fused]]
+// fused = 1: the same per-frame order as ONE device pass per frame (vslam_fpg_frame_step through
+// StereoFramePointGenerator::trackFrame: one graph launch and one synchronisation, points() resident on the device).
 // passes > 1 replays the sequence from its first frame (fresh tracker state) so that a short sequence gives a timed
 // region long enough to overlap with the other GPUs' runs (BASELINE configs[4]: one sequence per GPU).
 // frames.u8: [n_frames][2][rows][cols] u8.  Prints one JSON object.
@@ -18,7 +20,7 @@
 #include "vslam_b200.hpp"
 
 int main(int argc, char** argv) {
-  if (argc != 4 + 24 && argc != 4 + 25) {
+  if (argc != 4 + 24 && argc != 4 + 25 && argc != 4 + 26) {
     std::fprintf(stderr, "usage: sequence_runner frames.u8 n_frames warmup rows cols tolerance thr_min thr_max max_change "
                          "detectors_v detectors_h binning bin_size max_distance min_disparity max_offset fx fy cx cy bx "
                          "projection_tracking_distance error_delta_for_convergence maximum_error_kernel damping "
@@ -47,7 +49,18 @@ int main(int argc, char** argv) {
     ap.maximum_number_of_iterations = 1000;
     ap.minimum_number_of_inliers = std::atoi(a[22]);
     const double maximum_reliable_depth = std::atof(a[23]);
-    const int passes = argc == 4 + 25 ? std::atoi(a[24]) : 1;
+    const int passes = argc >= 4 + 25 ? std::atoi(a[24]) : 1;
+    const bool fused = argc == 4 + 26 && std::atoi(a[25]) != 0;
+    vslam_frame_step_parameters fsp = {};
+    fsp.track_by_appearance = 0;
+    fsp.projection_tracking_distance_pixels = tracking_distance;
+    fsp.maximum_descriptor_distance_tracking = descriptor_distance;
+    fsp.aligner = ap;
+    fsp.enable_inverse_depth_as_information = 1;
+    fsp.minimum_track_length_for_landmark_creation = 1;
+    fsp.maximum_reliable_depth_meters = maximum_reliable_depth;
+    fsp.minimum_reliable_depth_meters = 0.1;
+    fsp.publish_frame_points = 1;
     const size_t image_bytes = (size_t)c.rows * c.cols;
 
     // page-locked frame buffers (vslam_host_alloc): the H2D copy of initialize() is one asynchronous DMA
@@ -85,6 +98,7 @@ int main(int argc, char** argv) {
     std::vector<int32_t> lost;
     for (int pass = 0; pass < passes; ++pass) {
     have_previous = false;
+    if (fused) generator.resetSequence();
     for (int k = 0; k < n_frames; ++k) {
       const auto t0 = std::chrono::steady_clock::now();
       current.status = k == 0 ? vslam::Frame::Localizing : vslam::Frame::Tracking;
@@ -92,6 +106,22 @@ int main(int argc, char** argv) {
       current.intensity_image_right = frames + (size_t)(2 * k + 1) * image_bytes;
       current.image_step = (size_t)c.cols;
       current.tracks.clear();
+      if (fused) {
+        // the whole frame on the device; trackFrame copies tracks / points / points() of the frame out of the pinned block
+        const vslam_frame_step_result r = generator.trackFrame(&current, motion, fsp);
+        const auto t1 = std::chrono::steady_clock::now();
+        if (k >= warmup || pass > 0) {
+          seconds += std::chrono::duration<double>(t1 - t0).count();
+          n_rounds += r.aligner_rounds;
+          n_inliers += r.aligner_inliers;
+          n_previous += r.n_previous;
+          n_tracks += r.n_tracks;
+          n_new += r.n_new_points;
+          const double e = std::fabs(r.previous_to_current[3] - tx);
+          if (r.n_tracked && e > worst_translation_error) worst_translation_error = e;
+        }
+        continue;
+      }
       generator.initialize(&current);
       const double d_initialize = since(t0);
       const auto t_track = std::chrono::steady_clock::now();
@@ -165,11 +195,11 @@ int main(int argc, char** argv) {
     std::printf("{\"frames_per_s\": %.3f, \"ms_per_frame\": %.6f, \"mean_previous_points\": %.2f, \"mean_tracks\": %.2f, "
                 "\"mean_new_points\": %.2f, \"frames\": %d, \"us_initialize_with_feature_download\": %.1f, \"us_track\": %.1f, "
                 "\"us_align\": %.1f, \"us_compute\": %.1f, \"us_assemble_previous_points\": %.1f, \"mean_aligner_rounds\": %.2f, "
-                "\"mean_aligner_inliers\": %.1f, \"worst_translation_error_m\": %.3g}\n",
+                "\"mean_aligner_inliers\": %.1f, \"worst_translation_error_m\": %.3g, \"fused\": %d}\n",
                 timed / seconds, seconds / timed * 1e3, (double)n_previous / timed, (double)n_tracks / timed,
                 (double)n_new / timed, timed, s_initialize / timed * 1e6, s_track / timed * 1e6, s_align / timed * 1e6,
                 s_compute / timed * 1e6, s_assemble / timed * 1e6, (double)n_rounds / timed, (double)n_inliers / timed,
-                worst_translation_error);
+                worst_translation_error, (int)fused);
     vslam_host_free(frames);
   } catch (const std::exception& e) {
     std::fprintf(stderr, "FAILED: %s\n", e.what());

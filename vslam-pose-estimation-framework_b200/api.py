@@ -47,6 +47,7 @@ vslam_fpg_create vslam_fpg_destroy vslam_fpg_info vslam_fpg_get_thresholds vslam
 vslam_fpg_initialize vslam_fpg_get_features vslam_fpg_get_detection_stats vslam_fpg_set_remaining_features
 vslam_fpg_reset_features vslam_fpg_graph_launch_count
 vslam_fpg_compute vslam_fpg_get_matches vslam_fpg_track vslam_fpg_recover_points vslam_fpg_prune_tracks
+vslam_fpg_frame_step vslam_fpg_frame_step_capacity vslam_fpg_frame_step_reset vslam_fpg_frame_step_set_previous
 vslam_fpg_set_profiling vslam_fpg_get_time_consumption vslam_fpg_batch_upload vslam_fpg_batch_run
 vslam_fpg_batch_download vslam_fpg_batch_process vslam_fpg_batch_linearize vslam_fpg_batch_get_systems
 vslam_fpg_get_kernel_profile vslam_fpg_batch_get_features vslam_fpg_stream vslam_fpg_synchronize
@@ -79,6 +80,27 @@ class AlignerParameters(C.Structure):
     _fields_ = [("error_delta_for_convergence", C.c_double), ("maximum_error_kernel", C.c_double),
                 ("damping", C.c_double), ("maximum_number_of_iterations", C.c_int32),
                 ("minimum_number_of_inliers", C.c_int32)]
+
+
+class FrameStepParameters(C.Structure):
+    _fields_ = [("track_by_appearance", C.c_int32), ("projection_tracking_distance_pixels", C.c_int32),
+                ("maximum_descriptor_distance_tracking", C.c_double), ("aligner", AlignerParameters),
+                ("enable_inverse_depth_as_information", C.c_int32),
+                ("minimum_track_length_for_landmark_creation", C.c_int32),
+                ("maximum_reliable_depth_meters", C.c_double), ("minimum_reliable_depth_meters", C.c_double),
+                ("publish_frame_points", C.c_int32), ("reserved", C.c_int32)]
+
+
+class FrameStepResult(C.Structure):
+    _fields_ = [("n_left", C.c_int32), ("n_right", C.c_int32), ("n_previous", C.c_int32), ("n_tracked", C.c_int32),
+                ("n_lost", C.c_int32), ("n_tracked_landmarks", C.c_int32), ("n_tracks", C.c_int32),
+                ("n_new_points", C.c_int32), ("n_matches", C.c_int32), ("aligner_rounds", C.c_int32),
+                ("aligner_converged", C.c_int32), ("aligner_inliers", C.c_int32), ("aligner_outliers", C.c_int32),
+                ("inliers_only", C.c_int32), ("average_descriptor_distance", C.c_double),
+                ("aligner_total_error", C.c_double), ("previous_to_current", C.c_double * 12),
+                ("information", C.c_double * 36), ("tracks", C.c_void_p), ("kept", C.c_void_p),
+                ("errors", C.c_void_p), ("inliers", C.c_void_p), ("lost", C.c_void_p), ("points", C.c_void_p),
+                ("frame_points", C.c_void_p)]
 
 
 class LinearSystem(C.Structure):
@@ -127,6 +149,11 @@ def lib():
         L.vslam_fpg_get_matches.argtypes = [vp, vp, i32, vp]
         L.vslam_fpg_track.argtypes = [vp, vp, i32, vp, C.c_int, i32, C.c_double, vp, i32, vp, vp, vp, vp, vp]
         L.vslam_fpg_recover_points.argtypes = [vp, vp, i32, vp, C.c_double, C.c_double, C.c_double, vp, i32, vp]
+        L.vslam_fpg_frame_step.argtypes = [vp, vp, vp, sz, C.c_int, vp, vp, vp]
+        L.vslam_fpg_frame_step_capacity.argtypes = [vp]
+        L.vslam_fpg_frame_step_capacity.restype = i32
+        L.vslam_fpg_frame_step_reset.argtypes = [vp]
+        L.vslam_fpg_frame_step_set_previous.argtypes = [vp, vp, i32]
         L.vslam_fpg_set_profiling.argtypes = [vp, C.c_int]
         L.vslam_fpg_get_time_consumption.argtypes = [vp, vp, vp, vp]
         L.vslam_fpg_batch_upload.argtypes = [vp, i32, vp, vp, sz, sz]
@@ -326,6 +353,58 @@ class StereoFramePointGenerator:
                                               float(maximum_descriptor_distance_tracking), _p(out), len(out),
                                               C.byref(n)))
         return out[:n.value].copy()
+
+    # -- one tracked frame as one device pass (PoseTracker3D::compute's order: initialize, track, aligner, prune, compute)
+    def frame_step_capacity(self) -> int:
+        return int(lib().vslam_fpg_frame_step_capacity(self._h))
+
+    def frame_step_reset(self):
+        _check(lib().vslam_fpg_frame_step_reset(self._h))
+
+    def frame_step_set_previous(self, previous):
+        previous = np.ascontiguousarray(previous, PREVIOUS_POINT)
+        _check(lib().vslam_fpg_frame_step_set_previous(self._h, _p(previous) if len(previous) else None, len(previous)))
+
+    def frame_step(self, left, right, localizing, previous_to_current_prior, aligner_cfg, track_by_appearance,
+                   projection_tracking_distance_pixels, maximum_descriptor_distance_tracking,
+                   minimum_track_length_for_landmark_creation=1, publish_frame_points=True):
+        """-> dict with the counts, the optimised motion and copies of the result arrays (tracks, kept, errors, inliers,
+        lost, points, frame_points)"""
+        left, right = _image(left, self.cam), _image(right, self.cam)
+        T = np.ascontiguousarray(previous_to_current_prior, np.float64).reshape(12)
+        p = FrameStepParameters()
+        p.track_by_appearance = int(bool(track_by_appearance))
+        p.projection_tracking_distance_pixels = int(projection_tracking_distance_pixels)
+        p.maximum_descriptor_distance_tracking = float(maximum_descriptor_distance_tracking)
+        p.aligner = AlignerParameters(aligner_cfg.error_delta_for_convergence, aligner_cfg.maximum_error_kernel,
+                                      aligner_cfg.damping, aligner_cfg.maximum_number_of_iterations,
+                                      aligner_cfg.minimum_number_of_inliers)
+        p.enable_inverse_depth_as_information = int(aligner_cfg.enable_inverse_depth_as_information)
+        p.minimum_track_length_for_landmark_creation = int(minimum_track_length_for_landmark_creation)
+        p.maximum_reliable_depth_meters = float(aligner_cfg.maximum_reliable_depth_meters)
+        p.minimum_reliable_depth_meters = float(aligner_cfg.minimum_reliable_depth_meters)
+        p.publish_frame_points = int(bool(publish_frame_points))
+        r = FrameStepResult()
+        _check(lib().vslam_fpg_frame_step(self._h, _p(left), _p(right), left.strides[0], int(bool(localizing)), _p(T),
+                                          C.byref(p), C.byref(r)))
+
+        def view(ptr, n, dtype):
+            if n == 0 or not ptr:
+                return np.zeros(0, dtype)
+            buf = (C.c_uint8 * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype, n).copy()
+
+        out = {f: getattr(r, f) for f, _ in FrameStepResult._fields_[:16]}
+        out["previous_to_current"] = np.array(r.previous_to_current).reshape(3, 4)
+        out["information"] = np.array(r.information).reshape(6, 6)
+        out["tracks"] = view(r.tracks, r.n_tracks, TRACK)
+        out["kept"] = view(r.kept, r.n_tracked, np.uint8).astype(bool)
+        out["errors"] = view(r.errors, r.n_tracked, np.float64)
+        out["inliers"] = view(r.inliers, r.n_tracked, np.uint8).astype(bool)
+        out["lost"] = view(r.lost, r.n_lost, np.int32)
+        out["points"] = view(r.points, r.n_new_points, FRAMEPOINT)
+        out["frame_points"] = view(r.frame_points, r.n_tracks + r.n_new_points, PREVIOUS_POINT)
+        return out
 
     # -- StereoFramePointGenerator::compute(frame)
     def prune_tracks(self, aligner, maximum_error_kernel):

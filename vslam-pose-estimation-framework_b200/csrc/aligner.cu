@@ -471,9 +471,16 @@ __global__ void __launch_bounds__(kThreads) converge_kernel(int n, AlignerBuffer
 // correspondence in registers across the rounds.  Launched as a plain kernel with a cluster dimension.
 template <int KIND>
 __global__ void __launch_bounds__(kThreads, 1) converge_cluster_kernel(int n, AlignerBuffers b, AlignerCamera cam, GnParams p,
-                                                                    GnControl* __restrict__ ctl) {
+                                                                    GnControl* __restrict__ ctl,
+                                                                    const int32_t* __restrict__ n_device) {
   constexpr int D = KIND == 0 ? 4 : 3;
   constexpr int W = KIND == 0 ? 1 : 2;
+  // fused frame (captured graph): the correspondence count is what track() left in device memory; nothing to align
+  // without tracks (pose_tracker_3d.cpp:355: the tracker only optimises a frame that has points)
+  if (n_device) {
+    n = *n_device;
+    if (n <= 0 || n > (int)(gridDim.x * kThreads)) return;
+  }
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank(), n_blocks = (int)cluster.num_blocks();
   __shared__ double s_part[kThreads / 32][kAcc];
@@ -530,11 +537,12 @@ __global__ void __launch_bounds__(kThreads, 1) converge_cluster_kernel(int n, Al
     cluster.sync();                     // every block's partial is in its shared memory
 
     if (rank == 0) {
-      {  // the block partials in block order, 8 interleaved slices per value -- as in linearize_kernel (n_blocks <= 8:
-         // slice `part` holds block `part`)
+      {  // the block partials in block order, 8 interleaved slices per value -- as in linearize_kernel (blocks without a
+         // correspondence contribute +0.0, so a cluster larger than the grid of the stepwise path adds up to the same bits)
         const int j = threadIdx.x & 31, part = threadIdx.x >> 5;
         double v = 0;
-        if (j < kAcc && part < n_blocks) v += cluster.map_shared_rank(s_total, part)[j];
+        if (j < kAcc)
+          for (int blk = part; blk < n_blocks; blk += kThreads / 32) v += cluster.map_shared_rank(s_total, blk)[j];
         __syncthreads();
         if (j < kAcc) s_part[part][j] = v;
         __syncthreads();
@@ -676,13 +684,53 @@ cudaError_t launch_converge(int kind, int n, const AlignerBuffers& b, const Alig
     attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    const cudaError_t e = kind == 0 ? cudaLaunchKernelEx(&cfg, converge_cluster_kernel<0>, n_arg, b_arg, cam_arg, p_arg, ctl)
-                                    : cudaLaunchKernelEx(&cfg, converge_cluster_kernel<1>, n_arg, b_arg, cam_arg, p_arg, ctl);
+    const int32_t* no_device_count = nullptr;
+    const cudaError_t e =
+        kind == 0 ? cudaLaunchKernelEx(&cfg, converge_cluster_kernel<0>, n_arg, b_arg, cam_arg, p_arg, ctl, no_device_count)
+                  : cudaLaunchKernelEx(&cfg, converge_cluster_kernel<1>, n_arg, b_arg, cam_arg, p_arg, ctl, no_device_count);
     if (e == cudaSuccess) return e;
     cudaGetLastError();                 // e.g. a cluster size this device does not schedule: use the grid kernel
   }
   const void* fn = kind == 0 ? (const void*)converge_kernel<0> : (const void*)converge_kernel<1>;
   return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, stream);
+}
+
+namespace {
+void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int blocks, cudaStream_t stream) {
+  *cfg = cudaLaunchConfig_t{};
+  cfg->gridDim = dim3(blocks);
+  cfg->blockDim = dim3(kThreads);
+  cfg->stream = stream;
+  attr->id = cudaLaunchAttributeClusterDimension;
+  attr->val.clusterDim.x = blocks;
+  attr->val.clusterDim.y = 1;
+  attr->val.clusterDim.z = 1;
+  cfg->attrs = attr;
+  cfg->numAttrs = 1;
+}
+}  // namespace
+
+int frame_step_cluster_blocks() {
+  // 16 CTAs per cluster need the non-portable opt-in; the occupancy query says whether this device co-schedules them
+  const bool opt_in = cudaFuncSetAttribute(converge_cluster_kernel<0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+  for (int blocks : {16, 8}) {
+    if (blocks > 8 && !opt_in) continue;
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr;
+    cluster_config(&cfg, &attr, blocks, nullptr);
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, converge_cluster_kernel<0>, &cfg) == cudaSuccess && clusters > 0) return blocks;
+    cudaGetLastError();
+  }
+  return 0;
+}
+
+cudaError_t launch_converge_frame(const AlignerBuffers& b, const AlignerCamera& cam, const GnParams& p, GnControl* ctl,
+                                  const int32_t* n_device, int cluster_blocks, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr;
+  cluster_config(&cfg, &attr, cluster_blocks, stream);
+  return cudaLaunchKernelEx(&cfg, converge_cluster_kernel<0>, 0, b, cam, p, ctl, n_device);
 }
 
 void launch_linearize_pairs(const FramePointRecord* records, int record_stride, const int32_t* n_out, int n_pairs,

@@ -137,9 +137,41 @@ struct vslam_fpg {
   RecoveredRecord* d_recovered = nullptr;
   int32_t* d_recover_n = nullptr;        // {n_xy left, n_xy right, n_recovered}
   int8_t* d_brief_tests = nullptr;       // [256][4] when descriptor_type == VSLAM_DESCRIPTOR_BRIEF
+  // fused tracked frame (vslam_fpg_frame_step): device-resident counters, the StereoUV aligner's planes, the pinned and
+  // device-mapped result block, and one captured graph per frame status
+  int step_cap = 0;                      // points per frame = cluster blocks x 256; 0 = not set up, -1 = unavailable
+  int step_cluster_blocks = 0;
+  FrameStepState* d_step = nullptr;
+  GnControl* d_step_ctl = nullptr;
+  double* d_step_planes = nullptr;       // [3 + 4 + 1 + 1][step_cap] moving | fixed | omega | wt
+  double* d_step_errors = nullptr;       // [step_cap]
+  uint8_t* d_step_inliers = nullptr;     // [step_cap]
+  double* d_step_system = nullptr;       // [32]
+  int32_t* d_step_track_length = nullptr;
+  int32_t* d_step_kept_pos = nullptr;
+  uint8_t* h_step = nullptr;             // pinned + mapped result block
+  uint8_t* h_step_device = nullptr;      // its device address
+  double* h_step_T = nullptr;            // pinned [12]: the motion prior a copy node of the graph reads
+  size_t step_off_tracks = 0, step_off_kept = 0, step_off_errors = 0, step_off_inliers = 0, step_off_lost = 0,
+         step_off_points = 0, step_off_frame_points = 0;
+  cudaGraphExec_t step_graph[2] = {nullptr, nullptr};   // [localizing]
+  int step_graph_kernels[2] = {0, 0};
+  const uint8_t* step_graph_stage = nullptr;
+  size_t step_graph_stride = 0;
+  bool step_graph_profiling = false;
+  vslam_frame_step_parameters step_graph_parameters;
 };
 
 namespace {
+
+// the captured frame graphs bake buffer addresses: any reallocation of a buffer they touch drops them
+void invalidate_step_graphs(vslam_fpg* h) {
+  for (auto& gph : h->step_graph)
+    if (gph) {
+      cudaGraphExecDestroy(gph);
+      gph = nullptr;
+    }
+}
 
 void refresh_region_table(const vslam_fpg* h, RegionTable* rt) {
   for (int i = 0; i < h->g.n_regions; ++i) {
@@ -282,6 +314,7 @@ int ensure_stage(vslam_fpg* h, Lane& lane, size_t bytes, size_t pair_stride) {
     cudaGraphExecDestroy(h->init_graph);
     h->init_graph = nullptr;
   }
+  if (&lane == &h->lanes[0]) invalidate_step_graphs(h);
   const size_t want = (size_t)h->chunk * pair_stride;
   CUDA_TRY(cudaMalloc((void**)&lane.stage, 2 * want + 64));
   lane.stage_bytes = want;
@@ -664,6 +697,10 @@ int vslam_fpg_destroy(vslam_fpg* h) {
   cudaFree(h->d_brief_tests);
   cudaFreeHost(h->h_track_stats); cudaFreeHost(h->h_tracks); cudaFreeHost(h->h_lost);
   if (h->init_graph) cudaGraphExecDestroy(h->init_graph);
+  invalidate_step_graphs(h);
+  cudaFree(h->d_step); cudaFree(h->d_step_ctl); cudaFree(h->d_step_planes); cudaFree(h->d_step_errors);
+  cudaFree(h->d_step_inliers); cudaFree(h->d_step_system); cudaFree(h->d_step_track_length); cudaFree(h->d_step_kept_pos);
+  cudaFreeHost(h->h_step); cudaFreeHost(h->h_step_T);
   cudaFreeHost(h->h_thr);
   cudaFree(h->d_thr);
   cudaFreeHost(h->h_feat);
@@ -708,6 +745,26 @@ int vslam_fpg_set_thresholds(vslam_fpg* h, const double* t) {
   if (!h || !t) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
   for (int i = 0; i < h->g.n_regions; ++i) h->thresholds[i] = std::rint(t[i]);
   return VSLAM_OK;
+}
+
+// host side of a finished single-pair detection: adjustDetectorThresholds (base :440-459) over the two detections
+// (L, R) of this frame and the handle's frame state
+static void finish_detection(vslam_fpg* h, int localizing) {
+  const Geometry& g = h->g;
+  for (int i = 0; i < g.n_regions; ++i) {
+    double acc = 0;
+    for (int side = 0; side < 2; ++side)
+      acc += threshold_proposal(h->thresholds[i], h->h_counts[side * g.n_regions + i], h->target_per_detector,
+                                h->cfg.target_number_of_keypoints_tolerance, h->cfg.detector_threshold_maximum_change,
+                                h->cfg.detector_threshold_minimum, h->cfg.detector_threshold_maximum);
+    h->thresholds[i] = std::rint(acc / 2);
+  }
+  h->localizing = localizing != 0;
+  h->sp.localizing = h->localizing;
+  h->matching_distance = host_matching_distance(h, h->localizing, h->h_n_desc[0]);
+  h->initialized = true;
+  h->last_pairs = 1;
+  h->n_device_tracks = -1;
 }
 
 int vslam_fpg_initialize(vslam_fpg* h, const uint8_t* left, const uint8_t* right, size_t stride, int localizing,
@@ -786,21 +843,7 @@ int vslam_fpg_initialize(vslam_fpg* h, const uint8_t* left, const uint8_t* right
     cudaMemset(h->b.error_flag, 0, sizeof(int32_t));
     return rc;
   }
-  // adjustDetectorThresholds (base :440-459) over the two detections (L, R) of this frame
-  for (int i = 0; i < g.n_regions; ++i) {
-    double acc = 0;
-    for (int side = 0; side < 2; ++side)
-      acc += threshold_proposal(h->thresholds[i], h->h_counts[side * g.n_regions + i], h->target_per_detector,
-                                h->cfg.target_number_of_keypoints_tolerance, h->cfg.detector_threshold_maximum_change,
-                                h->cfg.detector_threshold_minimum, h->cfg.detector_threshold_maximum);
-    h->thresholds[i] = std::rint(acc / 2);
-  }
-  h->localizing = localizing != 0;
-  h->sp.localizing = h->localizing;
-  h->matching_distance = host_matching_distance(h, h->localizing, h->h_n_desc[0]);
-  h->initialized = true;
-  h->last_pairs = 1;
-  h->n_device_tracks = -1;
+  finish_detection(h, localizing);
   if (n_left) *n_left = h->h_n_desc[0];
   if (n_right) *n_right = h->h_n_desc[1];
   return prefetch_features(h);
@@ -847,6 +890,7 @@ int vslam_fpg_compute(vslam_fpg* h, const vslam_tracked_point* tracked, int32_t 
   Lane& lane = h->lanes[0];
   if (!device_tracks) h->n_device_tracks = -1;   // d_tracked is about to be overwritten
   if (!device_tracks && n_tracked > h->tracked_cap) {
+    invalidate_step_graphs(h);
     cudaFree(h->d_tracked);
     h->d_tracked = nullptr;
     h->tracked_cap = 0;
@@ -900,6 +944,7 @@ int vslam_fpg_compute(vslam_fpg* h, const vslam_tracked_point* tracked, int32_t 
 static int ensure_previous_capacity(vslam_fpg* h, int n) {
   if (n <= h->previous_cap) return VSLAM_OK;
   CUDA_TRY(cudaStreamSynchronize(h->lanes[0].stream));
+  invalidate_step_graphs(h);
   const int cap = std::max(2 * n, 1024);
   cudaFree(h->d_previous); cudaFree(h->track_scratch.tentative); cudaFree(h->d_tracks); cudaFree(h->d_lost);
   cudaFree(h->d_recover_xy); cudaFree(h->d_recover_desc); cudaFree(h->d_recovered);
@@ -1017,6 +1062,281 @@ int vslam_fpg_prune_tracks(vslam_fpg* h, vslam_aligner* aligner, double maximum_
   CUDA_TRY(cudaGetLastError());
   h->n_device_tracks = count;
   if (n_kept) *n_kept = count;
+  return VSLAM_OK;
+}
+
+// ---- fused tracked frame ------------------------------------------------------------------------------------------
+
+static int ensure_previous_capacity(vslam_fpg* h, int n);
+
+static int setup_frame_step(vslam_fpg* h) {
+  if (h->step_cap > 0) return VSLAM_OK;
+  if (h->step_cap < 0) return fail(VSLAM_ERR_STATE, "the fused frame is not available on this device (no thread-block cluster of 8 CTAs)");
+  if (!h->g.enable_binning) return fail(VSLAM_ERR_STATE, "vslam_fpg_frame_step needs enable_keypoint_binning");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int blocks = frame_step_cluster_blocks();
+  if (blocks < 8) {
+    h->step_cap = -1;
+    return fail(VSLAM_ERR_STATE, "the fused frame is not available on this device (no thread-block cluster of 8 CTAs)");
+  }
+  const int cap = blocks * 256;
+  int rc = ensure_previous_capacity(h, cap);
+  if (rc) return rc;
+  const size_t C = cap;
+  CUDA_TRY(cudaMalloc((void**)&h->d_step, sizeof(FrameStepState)));
+  CUDA_TRY(cudaMemset(h->d_step, 0, sizeof(FrameStepState)));
+  CUDA_TRY(cudaMalloc((void**)&h->d_step_ctl, sizeof(GnControl)));
+  CUDA_TRY(cudaMalloc((void**)&h->d_step_planes, sizeof(double) * 9 * C));
+  CUDA_TRY(cudaMalloc((void**)&h->d_step_errors, sizeof(double) * C));
+  CUDA_TRY(cudaMalloc((void**)&h->d_step_inliers, C));
+  CUDA_TRY(cudaMalloc((void**)&h->d_step_system, sizeof(double) * 32));
+  CUDA_TRY(cudaMalloc((void**)&h->d_step_track_length, sizeof(int32_t) * C));
+  CUDA_TRY(cudaMalloc((void**)&h->d_step_kept_pos, sizeof(int32_t) * C));
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  size_t off = up(sizeof(FrameStepHeader));
+  h->step_off_tracks = off;        off = up(off + sizeof(TrackRecord) * C);
+  h->step_off_kept = off;          off = up(off + C);
+  h->step_off_errors = off;        off = up(off + sizeof(double) * C);
+  h->step_off_inliers = off;       off = up(off + C);
+  h->step_off_lost = off;          off = up(off + sizeof(int32_t) * C);
+  h->step_off_points = off;        off = up(off + sizeof(FramePointRecord) * (size_t)h->out_cap);
+  h->step_off_frame_points = off;  off = up(off + sizeof(PreviousPoint) * C);
+  CUDA_TRY(cudaHostAlloc((void**)&h->h_step, off, cudaHostAllocMapped));
+  std::memset(h->h_step, 0, off);
+  CUDA_TRY(cudaHostGetDevicePointer((void**)&h->h_step_device, h->h_step, 0));
+  CUDA_TRY(cudaMallocHost((void**)&h->h_step_T, sizeof(double) * 12));
+  h->step_cluster_blocks = blocks;
+  h->step_cap = cap;
+  return VSLAM_OK;
+}
+
+static FrameStepBuffers frame_step_buffers(vslam_fpg* h) {
+  FrameStepBuffers f;
+  const size_t C = h->step_cap;
+  f.state = h->d_step;
+  f.previous = h->d_previous;
+  f.tracks = h->d_tracks;
+  f.lost = h->d_lost;
+  f.tracked = h->d_tracked;
+  f.stats = h->track_scratch.stats;
+  f.track_length = h->d_step_track_length;
+  f.kept_pos = h->d_step_kept_pos;
+  f.points = h->d_out;
+  f.n_out = h->b.n_out;
+  f.error_flag = h->b.error_flag;
+  f.desc = h->b.desc;
+  f.ctl = h->d_step_ctl;
+  f.aligner.moving = h->d_step_planes;
+  f.aligner.fixed = h->d_step_planes + 3 * C;
+  f.aligner.omega = h->d_step_planes + 7 * C;
+  f.aligner.wt = h->d_step_planes + 8 * C;
+  f.aligner.errors = h->d_step_errors;
+  f.aligner.inliers = h->d_step_inliers;
+  f.aligner.partials = nullptr;    // (the cluster kernel keeps its partials in shared memory)
+  f.aligner.system = h->d_step_system;
+  f.aligner.ticket = nullptr;
+  f.aligner.stride = h->step_cap;
+  f.cap = h->step_cap;
+  f.out_cap = h->out_cap;
+  uint8_t* d = h->h_step_device;
+  f.h_header = reinterpret_cast<FrameStepHeader*>(d);
+  f.h_tracks = reinterpret_cast<TrackRecord*>(d + h->step_off_tracks);
+  f.h_kept = d + h->step_off_kept;
+  f.h_errors = reinterpret_cast<double*>(d + h->step_off_errors);
+  f.h_inliers = d + h->step_off_inliers;
+  f.h_lost = reinterpret_cast<int32_t*>(d + h->step_off_lost);
+  f.h_points = reinterpret_cast<FramePointRecord*>(d + h->step_off_points);
+  f.h_frame_points = reinterpret_cast<PreviousPoint*>(d + h->step_off_frame_points);
+  return f;
+}
+
+// the device side of one tracked frame on lane 0's stream (captured once per frame status, or issued directly)
+static int issue_frame_step(vslam_fpg* h, Lane& lane, size_t stride, const vslam_frame_step_parameters& p) {
+  const Geometry& g = h->g;
+  CUDA_TRY(cudaMemcpyAsync(h->d_thr, h->h_thr, sizeof(int32_t) * g.n_regions, cudaMemcpyHostToDevice, lane.stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_step, h->h_step_T, sizeof(double) * 12, cudaMemcpyHostToDevice, lane.stream));
+  launch_repitch(g, lane.stage, lane.stage + lane.stage_bytes, (int)stride, h->b.image, 1, lane.stream);
+  ++h->launches;
+  run_detect_describe(h, lane, 0, 1, h->d_thr);                                  // pose_tracker_3d.cpp:80
+  const FrameStepBuffers f = frame_step_buffers(h);
+  FrameStepParams fp;
+  fp.max_reliable_depth = p.maximum_reliable_depth_meters;
+  fp.inverse_depth_weight = p.enable_inverse_depth_as_information != 0;
+  fp.error_kernel = p.aligner.maximum_error_kernel;
+  fp.min_track_length = p.minimum_track_length_for_landmark_creation;
+  fp.publish_frame_points = p.publish_frame_points != 0;
+  TrackParams tp;
+  for (int i = 0; i < 12; ++i) tp.T[i] = 0;                                      // (read from FrameStepState)
+  tp.by_appearance = p.track_by_appearance != 0;
+  tp.distance_pixels = p.projection_tracking_distance_pixels;
+  tp.max_distance_tracking = p.maximum_descriptor_distance_tracking;
+  mark(h, lane, kEvTrack0);
+  launch_track(g, h->sp, h->b, 0, h->d_previous, h->step_cap, tp, h->track_scratch, h->d_tracks, h->d_lost, h->d_tracked,
+               lane.stream, h->d_step);                                          // :239
+  mark(h, lane, kEvTrack1);
+  launch_frame_aligner_fill(f, fp, lane.stream);                                 // :124-126 / :355-356
+  AlignerCamera cam;
+  const double K[9] = {h->sp.fx, 0, h->sp.cx, 0, h->sp.fy, h->sp.cy, 0, 0, 1};
+  for (int i = 0; i < 9; ++i) cam.K[i] = K[i];
+  cam.baseline[0] = h->sp.bx; cam.baseline[1] = 0; cam.baseline[2] = 0;
+  cam.rows = g.rows; cam.cols = g.cols;
+  cam.min_depth = p.minimum_reliable_depth_meters;
+  GnParams gp;
+  gp.error_delta = p.aligner.error_delta_for_convergence;
+  gp.kernel = p.aligner.maximum_error_kernel;
+  gp.damping = p.aligner.damping;
+  gp.max_iterations = p.aligner.maximum_number_of_iterations;
+  gp.inlier_gate = p.aligner.minimum_number_of_inliers;                          // stereouv_aligner.cpp:224
+  CUDA_TRY(launch_converge_frame(f.aligner, cam, gp, h->d_step_ctl, h->track_scratch.stats, h->step_cluster_blocks,
+                                 lane.stream));                                  // :357
+  launch_frame_prune(f, fp, lane.stream);                                        // :437-472
+  mark(h, lane, kEvMatch0);
+  for (int pass = 0; pass < h->n_passes; ++pass) {                               // :210
+    const int offset = pass == 0 ? 0 : ((pass & 1) ? (pass + 1) / 2 : -(pass / 2));
+    launch_match(g, h->sp, h->b, 0, 1, pass, offset, lane.stream);
+    ++h->launches;
+  }
+  mark(h, lane, kEvMatch1);
+  launch_select(g, h->sp, h->b, 0, 1, h->n_passes, h->d_tracked, 0, h->d_out, h->out_cap, false, lane.stream,
+                &h->d_step->n_kept);
+  mark(h, lane, kEvSelect1);
+  launch_frame_assemble(g, f, fp, lane.stream);
+  h->launches += 2 + 4 + 1;   // track (2), fill / converge / prune / assemble, select
+  return status_download(h, lane);
+}
+
+int32_t vslam_fpg_frame_step_capacity(vslam_fpg* h) {
+  if (!h) return 0;
+  return setup_frame_step(h) == VSLAM_OK ? h->step_cap : 0;
+}
+
+int vslam_fpg_frame_step_reset(vslam_fpg* h) {
+  if (!h) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null handle");
+  int rc = setup_frame_step(h);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemsetAsync(h->d_step, 0, sizeof(FrameStepState), h->lanes[0].stream));
+  return VSLAM_OK;
+}
+
+int vslam_fpg_frame_step_set_previous(vslam_fpg* h, const vslam_previous_point* previous, int32_t n_previous) {
+  if (!h || n_previous < 0 || (n_previous > 0 && !previous)) return fail(VSLAM_ERR_INVALID_ARGUMENT, "bad previous points");
+  int rc = setup_frame_step(h);
+  if (rc) return rc;
+  if (n_previous > h->step_cap) return fail(VSLAM_ERR_CAPACITY, "%d previous points, the fused frame holds %d", n_previous, h->step_cap);
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->lanes[0].stream;
+  if (n_previous)
+    CUDA_TRY(cudaMemcpyAsync(h->d_previous, previous, sizeof(PreviousPoint) * (size_t)n_previous, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(&h->d_step->n_previous, &n_previous, sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));   // the caller's buffer and the stack variable may go away
+  return VSLAM_OK;
+}
+
+int vslam_fpg_frame_step(vslam_fpg* h, const uint8_t* left, const uint8_t* right, size_t stride, int localizing,
+                         const double T_prior[12], const vslam_frame_step_parameters* p, vslam_frame_step_result* out) {
+  VSLAM_NVTX("vslam_fpg_frame_step [PoseTracker3D::compute]");
+  if (!h || !left || !right || !T_prior || !p || !out) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  if (stride < (size_t)h->g.cols) return fail(VSLAM_ERR_INVALID_ARGUMENT, "stride smaller than the image width");
+  if (p->projection_tracking_distance_pixels < 0) return fail(VSLAM_ERR_INVALID_ARGUMENT, "negative tracking distance");
+  if (p->aligner.maximum_number_of_iterations < 1) return fail(VSLAM_ERR_INVALID_ARGUMENT, "maximum_number_of_iterations < 1");
+  int rc = setup_frame_step(h);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  Lane& lane = h->lanes[0];
+  const Geometry& g = h->g;
+  if (h->feat_valid) CUDA_TRY(cudaStreamWaitEvent(lane.stream, h->feat_ev, 0));
+  h->feat_valid = false;
+  const size_t image_bytes = stride * (size_t)g.rows;
+  if (!linear_upload(g, 1, stride, image_bytes)) return fail(VSLAM_ERR_INVALID_ARGUMENT, "the fused frame takes dense images (row stride close to the width)");
+  if ((rc = ensure_stage(h, lane, image_bytes, image_bytes))) return rc;
+  const int L = localizing != 0;
+  if (h->step_graph[0] || h->step_graph[1]) {
+    if (h->step_graph_stage != lane.stage || h->step_graph_stride != stride || h->step_graph_profiling != h->profiling ||
+        std::memcmp(&h->step_graph_parameters, p, sizeof(*p)) != 0)
+      invalidate_step_graphs(h);
+  }
+  for (int i = 0; i < g.n_regions; ++i) {   // FastDetector::setThreshold -> std::rint (:21); cv::FAST clamps
+    const int t = (int)std::rint(h->thresholds[i]);
+    h->h_thr[i] = std::min(std::max(t, 0), 255);
+  }
+  for (int i = 0; i < 12; ++i) h->h_step_T[i] = T_prior[i];
+  h->sp.localizing = L;
+  h->localizing = L;
+  static const bool use_graph = std::getenv("VSLAM_NO_FRAME_GRAPH") == nullptr;
+  if (use_graph && !h->step_graph[L]) {   // capture the device side of the frame once per frame status
+    const int64_t launches_before = h->launches;
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(lane.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      h->capturing = true;
+      const int issued = issue_frame_step(h, lane, stride, *p);
+      h->capturing = false;
+      ok = cudaStreamEndCapture(lane.stream, &graph) == cudaSuccess && graph != nullptr && issued == VSLAM_OK;
+    }
+    if (ok) ok = cudaGraphInstantiate(&h->step_graph[L], graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    h->step_graph_kernels[L] = (int)(h->launches - launches_before);
+    h->launches = launches_before;
+    if (!ok) {
+      const cudaError_t e = cudaGetLastError();
+      h->step_graph[L] = nullptr;
+      return fail(VSLAM_ERR_CUDA, "capturing the frame graph failed: %s", cudaGetErrorString(e));
+    }
+    h->step_graph_stage = lane.stage;
+    h->step_graph_stride = stride;
+    h->step_graph_profiling = h->profiling;
+    h->step_graph_parameters = *p;
+  }
+  CUDA_TRY(cudaMemcpyAsync(lane.stage, left, image_bytes, cudaMemcpyHostToDevice, lane.stream));
+  CUDA_TRY(cudaMemcpyAsync(lane.stage + lane.stage_bytes, right, image_bytes, cudaMemcpyHostToDevice, lane.stream));
+  if (use_graph) {
+    CUDA_TRY(cudaGraphLaunch(h->step_graph[L], lane.stream));
+    h->launches += h->step_graph_kernels[L];
+    ++h->graph_launches;
+  } else if ((rc = issue_frame_step(h, lane, stride, *p))) {
+    return rc;
+  }
+  CUDA_TRY(cudaStreamSynchronize(lane.stream));
+  CUDA_TRY(cudaGetLastError());
+  collect_clock(h, true, true);
+  if (h->profiling) add_interval(h, kKTrack, kEvTrack0, kEvTrack1, 2);
+  const FrameStepHeader* hd = reinterpret_cast<const FrameStepHeader*>(h->h_step);
+  if ((rc = check_flag(h)) || hd->overflow) {
+    cudaMemset(h->b.error_flag, 0, sizeof(int32_t));
+    cudaMemset(h->d_step, 0, sizeof(FrameStepState));   // the device-resident points are not usable: a new sequence
+    h->initialized = false;
+    if (rc) return rc;
+    return fail(VSLAM_ERR_CAPACITY, "more than %d points in a frame: use the stepwise calls", h->step_cap);
+  }
+  finish_detection(h, L);
+  h->n_device_tracks = hd->n_kept;
+  std::memset(out, 0, sizeof(*out));
+  out->n_left = h->h_n_desc[0];
+  out->n_right = h->h_n_desc[1];
+  out->n_previous = hd->n_previous;
+  out->n_tracked = hd->stats[0];
+  out->n_lost = hd->stats[1];
+  out->n_tracked_landmarks = hd->stats[2];
+  out->average_descriptor_distance = hd->stats[0] ? (double)hd->stats[3] / (double)hd->stats[0] : std::nan("");
+  out->n_tracks = hd->n_kept;
+  out->n_new_points = hd->n_out[0];
+  out->n_matches = hd->n_out[1];
+  out->aligner_rounds = hd->ctl.rounds;
+  out->aligner_converged = hd->ctl.converged;
+  out->aligner_inliers = (int32_t)std::llrint(hd->system[28]);
+  out->aligner_outliers = hd->stats[0] - out->aligner_inliers;
+  out->inliers_only = hd->inliers_only;
+  out->aligner_total_error = hd->system[27];
+  for (int i = 0; i < 12; ++i) out->previous_to_current[i] = hd->ctl.T[i];
+  if (hd->ctl.converged) std::memcpy(out->information, hd->ctl.H, sizeof(double) * 36);
+  out->tracks = reinterpret_cast<const vslam_track*>(h->h_step + h->step_off_tracks);
+  out->kept = h->h_step + h->step_off_kept;
+  out->errors = reinterpret_cast<const double*>(h->h_step + h->step_off_errors);
+  out->inliers = h->h_step + h->step_off_inliers;
+  out->lost = reinterpret_cast<const int32_t*>(h->h_step + h->step_off_lost);
+  out->points = reinterpret_cast<const vslam_framepoint*>(h->h_step + h->step_off_points);
+  out->frame_points = p->publish_frame_points ? reinterpret_cast<const vslam_previous_point*>(h->h_step + h->step_off_frame_points) : nullptr;
   return VSLAM_OK;
 }
 

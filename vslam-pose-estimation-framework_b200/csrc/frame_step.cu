@@ -1,0 +1,252 @@
+// frame_step.cu -- the glue kernels of the fused tracked frame (vslam_fpg_frame_step): what PoseTracker3D::compute does
+// on the host between the generator's and the aligner's calls (reference src/position_tracking/pose_tracker_3d.cpp:
+// 124-126 / 355-357 aligner initialize + converge, 437-472 _prunePoints, 210 compute, and the points() of the frame the
+// next track() reads), moved to the device so that a frame is ONE graph launch and one synchronisation.  Counts travel
+// through FrameStepState (device memory), never through kernel arguments.
+//
+//   frame_aligner_fill_kernel   StereoUVAligner::initialize over the tracks (reference src/aligners/stereouv_aligner.cpp:
+//                               26-64, the branch without a landmark estimate) + the control block of converge()
+//   frame_prune_kernel          _prunePoints on the bin pre-load records, the kept flags and their ordered positions
+//   frame_assemble_kernel       points() of the frame (surviving tracks, then the new framepoints, with their descriptors)
+//                               replace the previous points in place; everything the host reads is written into the
+//                               handle's pinned, device-mapped result block
+#include "kernels.cuh"
+
+namespace vslam {
+
+namespace {
+
+constexpr int kFillThreads = 256;
+
+__global__ void __launch_bounds__(kFillThreads) frame_aligner_fill_kernel(FrameStepBuffers f, FrameStepParams p) {
+  const int n = f.stats[0];
+  const int u = blockIdx.x * kFillThreads + threadIdx.x;
+  if (u == 0) {
+    GnControl* c = f.ctl;
+    for (int i = 0; i < 12; ++i) c->T[i] = f.state->T_prior[i];
+    for (int i = 0; i < 36; ++i) c->H[i] = 0.0;
+    c->total_error_previous = 0.0;
+    c->rounds = c->phase = c->iteration = c->ignore = c->converged = c->done = 0;
+    for (int i = 0; i < 32; ++i) f.aligner.system[i] = 0.0;
+    f.state->overflow = n > f.cap ? 1 : 0;
+    f.state->n_kept = 0;
+    f.state->inliers_only = 0;
+  }
+  if (u >= n || u >= f.cap) return;
+  const TrackRecord t = f.tracks[u];
+  const PreviousPoint* pp = f.previous + t.index_previous;
+  const int S = f.aligner.stride;
+  double* moving = const_cast<double*>(f.aligner.moving);
+  double* fixed = const_cast<double*>(f.aligner.fixed);
+  moving[u] = pp->camera[0];                                 // :52-55 previous->cameraCoordinatesLeft()
+  moving[S + u] = pp->camera[1];
+  moving[2 * S + u] = pp->camera[2];
+  fixed[u] = (double)t.xl;                                   // :36-39
+  fixed[S + u] = (double)t.yl;
+  fixed[2 * S + u] = (double)t.xr;
+  fixed[3 * S + u] = (double)t.yr;
+  const_cast<double*>(f.aligner.omega)[u] = 1.0;             // :28 setIdentity
+  double w = 1.0;
+  if (p.inverse_depth_weight) {                              // :59-63 std::min(max_depth / depth, 1.0)
+    const double q = p.max_reliable_depth / t.camera[2];
+    w = 1.0 < q ? 1.0 : q;
+  }
+  const_cast<double*>(f.aligner.wt)[u] = w;
+  f.track_length[u] = pp->reserved;                          // trackLength() of the previous point (frame_point.cpp:27)
+}
+
+// pose_tracker_3d.cpp:437-472.  One CTA, 8 consecutive tracks per thread (up to 8192); the kept bin pre-load records are
+// compacted in place, in order (every thread reads its share before anyone writes).
+constexpr int kPruneThreads = 1024;
+__global__ void __launch_bounds__(kPruneThreads) frame_prune_kernel(FrameStepBuffers f, FrameStepParams p) {
+  __shared__ int s_warp[kPruneThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = min(f.stats[0], f.cap);
+  // averageError() = total error / correspondences (base_aligner.h:46) of the last linearisation
+  const bool inliers_only = n > 0 && f.aligner.system[27] / n < p.error_kernel;
+  const double cap = 100 * p.error_kernel;
+  constexpr int kPer = 8;
+  const int begin = tid * kPer;
+  TrackedPoint mine[kPer];
+  int kept = 0;
+  unsigned keep_mask = 0;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int k = begin + j;
+    if (k < n) {
+      const bool keep = inliers_only ? f.aligner.inliers[k] != 0 : (f.aligner.errors[k] != -1.0 && f.aligner.errors[k] < cap);
+      if (keep) {
+        mine[kept++] = f.tracked[k];
+        keep_mask |= 1u << j;
+      }
+    }
+  }
+  int inc = kept;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();                              // (also: every record has been read)
+  int base = 0, total = 0;
+  for (int w = 0; w < kPruneThreads / 32; ++w) {
+    if (w < warp) base += s_warp[w];
+    total += s_warp[w];
+  }
+  const int first = base + inc - kept;
+  for (int j = 0; j < kept; ++j) f.tracked[first + j] = mine[j];
+  int pos = first;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int k = begin + j;
+    if (k < n) f.kept_pos[k] = (keep_mask >> j) & 1u ? pos++ : -1;
+  }
+  if (tid == 0) {
+    f.state->n_kept = total;
+    f.state->inliers_only = inliers_only;
+  }
+}
+
+// coalesced 16-byte copies of a contiguous range by one block
+__device__ __forceinline__ void copy16(void* dst, const void* src, size_t bytes, int tid, int threads) {
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  for (size_t i = tid; i < bytes / 16; i += threads) d[i] = s[i];
+}
+
+constexpr int kAssembleThreads = 256;
+constexpr int kAssemblePoints = 64;   // points() entries per block: 8 KB of shared memory, written out in 512-byte rows
+
+__global__ void __launch_bounds__(kAssembleThreads) frame_assemble_kernel(Geometry g, FrameStepBuffers f, FrameStepParams p) {
+  __shared__ __align__(16) PreviousPoint s_points[kAssemblePoints];
+  __shared__ __align__(16) TrackRecord s_tracks[kAssemblePoints];
+  __shared__ int s_pos[kAssemblePoints];
+  const int tid = threadIdx.x;
+  const int n_tracks = min(f.stats[0], f.cap);
+  const int n_kept = f.state->n_kept;
+  const int n_new = min(f.n_out[0], f.out_cap);
+  const bool overflow = f.state->overflow != 0 || n_kept + n_new > f.cap;
+  const int n_points = overflow ? 0 : n_kept + n_new;
+  const uint8_t* desc_l = f.desc;
+  const uint8_t* desc_r = f.desc + (size_t)g.cap * kDescBytes;
+  const int track_blocks = (f.cap + kAssemblePoints - 1) / kAssemblePoints;
+  const int new_blocks = (f.out_cap + kAssemblePoints - 1) / kAssemblePoints;
+
+  auto fill = [&](PreviousPoint* q, const double camera[3], int index_left, int index_right, int epipolar_offset, int length) {
+    for (int d = 0; d < 3; ++d) q->camera[d] = q->world[d] = camera[d];
+    const uint4* dl = reinterpret_cast<const uint4*>(desc_l + (size_t)index_left * kDescBytes);
+    const uint4* dr = reinterpret_cast<const uint4*>(desc_r + (size_t)index_right * kDescBytes);
+    uint4* ql = reinterpret_cast<uint4*>(q->descriptor_left);
+    uint4* qr = reinterpret_cast<uint4*>(q->descriptor_right);
+    ql[0] = dl[0]; ql[1] = dl[1];
+    qr[0] = dr[0]; qr[1] = dr[1];
+    q->epipolar_offset = epipolar_offset;
+    q->has_landmark = length >= p.min_track_length;
+    q->keypoint_size = 7.f;        // cv::FastFeatureDetector keypoints (fast.cpp: KeyPoint(x, y, 7.f, -1, score))
+    q->reserved = length;          // trackLength()
+  };
+
+  if ((int)blockIdx.x < track_blocks) {
+    // ---- tracks [k0, k0 + 64) of track(): the survivors go to their ordered position among points() and the host's tracks.
+    // A block's survivors are consecutive positions (the order is kept), so both outputs are contiguous ranges.
+    const int k0 = blockIdx.x * kAssemblePoints;
+    if (k0 >= n_tracks) return;
+    if (tid < kAssemblePoints) {
+      const int k = k0 + tid;
+      const int pos = k < n_tracks ? f.kept_pos[k] : -1;
+      s_pos[tid] = pos;
+    }
+    __syncthreads();
+    // first surviving position of the block and the count
+    int first = -1, count = 0;
+    for (int i = 0; i < kAssemblePoints; ++i)
+      if (s_pos[i] >= 0) {
+        if (first < 0) first = s_pos[i];
+        ++count;
+      }
+    if (tid < kAssemblePoints && s_pos[tid] >= 0) {
+      const TrackRecord t = f.tracks[k0 + tid];
+      const int slot = s_pos[tid] - first;
+      s_tracks[slot] = t;
+      fill(&s_points[slot], t.camera, t.index_left, t.index_right, t.epipolar_offset, f.track_length[k0 + tid] + 1);
+    }
+    __syncthreads();
+    if (count && !overflow) {
+      copy16(f.previous + first, s_points, sizeof(PreviousPoint) * (size_t)count, tid, kAssembleThreads);
+      if (p.publish_frame_points)
+        copy16(f.h_frame_points + first, s_points, sizeof(PreviousPoint) * (size_t)count, tid, kAssembleThreads);
+      // TrackRecord is 88 bytes: copy as 8-byte words (first * 88 is 8-byte aligned)
+      const uint2* s = reinterpret_cast<const uint2*>(s_tracks);
+      uint2* d = reinterpret_cast<uint2*>(f.h_tracks + first);
+      for (int i = tid; i < count * (int)(sizeof(TrackRecord) / 8); i += kAssembleThreads) d[i] = s[i];
+    }
+    // per-track results of the aligner and the prune, for the host's own bookkeeping
+    if (tid < kAssemblePoints && k0 + tid < n_tracks) {
+      const int k = k0 + tid;
+      f.h_kept[k] = s_pos[tid] >= 0;
+      f.h_errors[k] = f.aligner.errors[k];
+      f.h_inliers[k] = f.aligner.inliers[k];
+    }
+    return;
+  }
+  const int nb = blockIdx.x - track_blocks;
+  if (nb < new_blocks) {
+    // ---- new framepoints [k0, k0 + 64) of compute(): behind the surviving tracks
+    const int k0 = nb * kAssemblePoints;
+    if (k0 >= n_new) return;
+    const int count = min(kAssemblePoints, n_new - k0);
+    if (tid < count) {
+      const FramePointRecord r = f.points[k0 + tid];
+      fill(&s_points[tid], r.camera, r.index_left, r.index_right, r.epipolar_offset, 1);
+    }
+    __syncthreads();
+    if (!overflow) {
+      copy16(f.previous + n_kept + k0, s_points, sizeof(PreviousPoint) * (size_t)count, tid, kAssembleThreads);
+      if (p.publish_frame_points)
+        copy16(f.h_frame_points + n_kept + k0, s_points, sizeof(PreviousPoint) * (size_t)count, tid, kAssembleThreads);
+    }
+    // FramePointRecord is 56 bytes: 8-byte words
+    const uint2* s = reinterpret_cast<const uint2*>(f.points + k0);
+    uint2* d = reinterpret_cast<uint2*>(f.h_points + k0);
+    for (int i = tid; i < count * (int)(sizeof(FramePointRecord) / 8); i += kAssembleThreads) d[i] = s[i];
+    return;
+  }
+  // ---- last block: lost points, header, and the count the next frame's track() reads
+  const int n_lost = min(f.stats[1], f.cap);
+  for (int i = tid; i < n_lost; i += kAssembleThreads) f.h_lost[i] = f.lost[i];
+  if (tid < 4) f.h_header->stats[tid] = f.stats[tid];
+  if (tid < 2) f.h_header->n_out[tid] = f.n_out[tid];
+  if (tid < 32) f.h_header->system[tid] = f.aligner.system[tid];
+  {
+    const double* s = reinterpret_cast<const double*>(f.ctl);
+    double* d = reinterpret_cast<double*>(&f.h_header->ctl);
+    for (int i = tid; i < (int)(sizeof(GnControl) / 8); i += kAssembleThreads) d[i] = s[i];
+  }
+  if (tid == 0) {
+    f.h_header->n_kept = n_kept;
+    f.h_header->inliers_only = f.state->inliers_only;
+    f.h_header->overflow = overflow;
+    f.h_header->error_flag = *f.error_flag;
+    f.h_header->n_previous = f.state->n_previous;
+    f.h_header->n_points = n_points;
+    f.state->n_previous = n_points;   // (no other block reads it: track() of this frame is long done)
+  }
+}
+
+}  // namespace
+
+void launch_frame_aligner_fill(const FrameStepBuffers& f, const FrameStepParams& p, cudaStream_t stream) {
+  frame_aligner_fill_kernel<<<(f.cap + kFillThreads - 1) / kFillThreads, kFillThreads, 0, stream>>>(f, p);
+}
+
+void launch_frame_prune(const FrameStepBuffers& f, const FrameStepParams& p, cudaStream_t stream) {
+  frame_prune_kernel<<<1, kPruneThreads, 0, stream>>>(f, p);
+}
+
+void launch_frame_assemble(const Geometry& g, const FrameStepBuffers& f, const FrameStepParams& p, cudaStream_t stream) {
+  const int blocks = (f.cap + kAssemblePoints - 1) / kAssemblePoints + (f.out_cap + kAssemblePoints - 1) / kAssemblePoints + 1;
+  frame_assemble_kernel<<<blocks, kAssembleThreads, 0, stream>>>(g, f, p);
+}
+
+}  // namespace vslam

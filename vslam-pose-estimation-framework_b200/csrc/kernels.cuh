@@ -64,6 +64,17 @@ struct TrackParams {
   double max_distance_tracking;    // _maximum_descriptor_distance_tracking
 };
 
+// Device-resident inputs and counters of the fused tracked frame (vslam_fpg_frame_step).  A captured CUDA graph
+// re-launches every kernel of the frame with the same arguments, so everything that changes from frame to frame --
+// the motion prior and the point counts the stages hand to each other -- lives here instead of in kernel arguments.
+struct FrameStepState {
+  double T_prior[12];      // camera_left_previous_in_current of this frame (copy node of the graph, from pinned memory)
+  int32_t n_previous;      // points() of the previous frame held in `previous` (written by frame_assemble_kernel)
+  int32_t n_kept;          // tracks that survive _prunePoints (frame_prune_kernel)
+  int32_t inliers_only;    // the branch of pose_tracker_3d.cpp:441 taken by frame_prune_kernel
+  int32_t overflow;        // != 0: more points than the fused path holds (the stepwise calls have no such limit)
+};
+
 struct TrackScratch {
   int4* tentative;       // [n_previous] {sorted left feature | -1, sorted right feature | -1, distance, status}
   int32_t* claim_l;      // [cap] lowest previous-point index that consumes the left feature
@@ -110,7 +121,8 @@ void launch_match(const Geometry& g, const StereoParams& sp, const Buffers& b, i
                   int epipolar_offset, cudaStream_t stream);
 void launch_select(const Geometry& g, const StereoParams& sp, const Buffers& b, int first_pair, int n_pairs,
                    int n_passes, const TrackedPoint* tracked, int n_tracked, FramePointRecord* out,
-                   int out_capacity_per_pair, bool generic, cudaStream_t stream);
+                   int out_capacity_per_pair, bool generic, cudaStream_t stream,
+                   const int32_t* n_tracked_device = nullptr);
 void launch_emit_matches(const Geometry& g, const StereoParams& sp, const Buffers& b, int pair, int n_passes,
                          FramePointRecord* out, int out_capacity, int32_t* n_out, cudaStream_t stream);
 int kernels_per_match_pass();
@@ -128,7 +140,7 @@ void launch_describe_brief(const Geometry& g, const uint16_t* boxsum, const int8
 // consumed features in pruned_l / consumed_r, writes tracks / lost (ordered), the bin pre-load records and stats.
 void launch_track(const Geometry& g, const StereoParams& sp, const Buffers& b, int pair, const PreviousPoint* previous,
                   int n_previous, const TrackParams& tp, const TrackScratch& scratch, TrackRecord* tracks,
-                  int32_t* lost, TrackedPoint* tracked, cudaStream_t stream);
+                  int32_t* lost, TrackedPoint* tracked, cudaStream_t stream, const FrameStepState* step = nullptr);
 // StereoFramePointGenerator::recoverPoints for pair `pair` (blurred images at `blurred`): three launches
 void launch_recover(const Geometry& g, const StereoParams& sp, const Buffers& b, int pair, const uint8_t* blurred,
                     const PreviousPoint* lost, int n_lost, const RecoverParams& rp, uint32_t* xy, int32_t* n_xy,
@@ -177,6 +189,13 @@ cudaError_t launch_converge(int kind, int n, const AlignerBuffers& b, const Alig
                             GnControl* ctl, int grid, cudaStream_t stream);
 void launch_linearize(int kind, int n, const AlignerBuffers& b, const AlignerCamera& cam, const double T[12],
                       int ignore_outliers, double kernel, int grid, cudaStream_t stream);
+// StereoUV converge of the fused tracked frame: ONE thread-block cluster of `cluster_blocks` CTAs (the same blocks as
+// launch_converge's, so the pose sequence is bit-identical), the correspondence count read from *n_device (0: the
+// kernel leaves the control block as it is, rounds = 0).  frame_step_cluster_blocks(): the largest cluster this device
+// schedules for the kernel (16 with the non-portable opt-in, else 8, 0 when none); capacity = blocks x 256.
+int frame_step_cluster_blocks();
+cudaError_t launch_converge_frame(const AlignerBuffers& b, const AlignerCamera& cam, const GnParams& p, GnControl* ctl,
+                                  const int32_t* n_device, int cluster_blocks, cudaStream_t stream);
 // one CTA per stereo pair: StereoUV initialize + linearize of the pair's new framepoints against themselves
 void launch_linearize_pairs(const FramePointRecord* records, int record_stride, const int32_t* n_out, int n_pairs,
                             const AlignerCamera& cam, const double T[12], int ignore_outliers, double kernel,
@@ -193,6 +212,56 @@ struct LandmarkMeasurement {
 // PoseTracker3D::_prunePoints on the bin pre-load records of the last track() (at most 8192), ordered, in place
 void launch_prune_tracked(TrackedPoint* tracked, int n, const double* errors, const uint8_t* inliers, int inliers_only,
                           double error_cap, cudaStream_t stream);
+// ---- fused tracked frame (frame_step.cu) ----
+// what the frame publishes into the handle's pinned result block, written by the device through the mapped pointer
+struct FrameStepHeader {
+  int32_t stats[4];        // track(): {tracks, lost, tracked landmarks, accumulated descriptor distance}
+  int32_t n_kept, inliers_only, overflow, error_flag;
+  int32_t n_out[2];        // compute(): {new framepoints, matches}
+  int32_t n_previous;      // points the frame was tracked against
+  int32_t n_points;        // points() of this frame = n_kept + new framepoints
+  GnControl ctl;           // pose, damped H, rounds, converged
+  double system[32];       // last linearisation: H upper triangle, b, total error, inliers
+};
+struct FrameStepBuffers {
+  FrameStepState* state;
+  PreviousPoint* previous;          // [cap] points() of the previous frame, replaced in place at the end of the frame
+  const TrackRecord* tracks;        // [cap] track() output
+  const int32_t* lost;              // [cap]
+  TrackedPoint* tracked;            // [cap] bin pre-load records (pruned in place)
+  const int32_t* stats;             // track() stats
+  int32_t* track_length;            // [cap] per track: trackLength() of its previous point
+  int32_t* kept_pos;                // [cap] per track: position among the surviving tracks or -1
+  const FramePointRecord* points;   // [out_cap] compute() output
+  const int32_t* n_out;             // {new framepoints, matches}
+  const int32_t* error_flag;
+  const uint8_t* desc;              // descriptors of the frame [2][g.cap][32]
+  GnControl* ctl;
+  AlignerBuffers aligner;           // StereoUV planes with stride = cap
+  int cap, out_cap;
+  // pinned, device-mapped result block
+  FrameStepHeader* h_header;
+  TrackRecord* h_tracks;            // [cap] surviving tracks, in order
+  uint8_t* h_kept;                  // [cap] per track of track()
+  double* h_errors;                 // [cap]
+  uint8_t* h_inliers;               // [cap]
+  int32_t* h_lost;                  // [cap]
+  FramePointRecord* h_points;       // [out_cap]
+  PreviousPoint* h_frame_points;    // [cap] points() of this frame (the next frame's previous points)
+};
+struct FrameStepParams {
+  double max_reliable_depth;        // _maximum_reliable_depth_meters of the aligner (slam_assembly.cpp:70)
+  int inverse_depth_weight;         // enable_inverse_depth_as_information
+  double error_kernel;              // maximum_error_kernel (the prune rule)
+  int min_track_length;             // minimum_track_length_for_landmark_creation: has_landmark of the assembled points
+  int publish_frame_points;         // copy points() of the frame (128 B each) to the host as well
+};
+// StereoUVAligner::initialize over the tracks (stereouv_aligner.cpp:26-64, the branch without a landmark estimate) and the
+// control block of converge(); then, after the cluster kernel: _prunePoints; after select: points() of the frame
+void launch_frame_aligner_fill(const FrameStepBuffers& f, const FrameStepParams& p, cudaStream_t stream);
+void launch_frame_prune(const FrameStepBuffers& f, const FrameStepParams& p, cudaStream_t stream);
+void launch_frame_assemble(const Geometry& g, const FrameStepBuffers& f, const FrameStepParams& p, cudaStream_t stream);
+
 // device-resident landmark map (vslam_landmark_map): per landmark a chain of 32-measurement blocks, its world
 // coordinates and update count; per frame slot the two poses every measurement of that frame is evaluated with
 struct LandmarkMapBuffers {

@@ -175,8 +175,10 @@ __global__ void __launch_bounds__(256) select_kernel(Geometry g, StereoParams sp
                                                      const int2* __restrict__ match, int n_passes,
                                                      const TrackedPoint* __restrict__ tracked, int n_tracked,
                                                      FramePointRecord* __restrict__ out, int out_cap,
-                                                     int32_t* __restrict__ n_out, int32_t* __restrict__ error_flag) {
+                                                     int32_t* __restrict__ n_out, int32_t* __restrict__ error_flag,
+                                                     const int32_t* __restrict__ n_tracked_device) {
   __shared__ int s_warp[8];
+  if (n_tracked_device) n_tracked = *n_tracked_device;   // fused frame: the count of the device-side _prunePoints
   const int pair = blockIdx.x;
   const int il = 2 * pair, ir = 2 * pair + 1;
   const int32_t* rpl = row_ptr + (size_t)il * (g.rows + 1);
@@ -287,8 +289,9 @@ __global__ void __launch_bounds__(kSelectWarps * 32) select_strips_kernel(
     Geometry g, StereoParams sp, const int32_t* __restrict__ row_ptr, const uint32_t* __restrict__ kp_xy,
     const int32_t* __restrict__ n_desc, const int2* __restrict__ match, int n_passes,
     const TrackedPoint* __restrict__ tracked, int n_tracked, FramePointRecord* __restrict__ out, int out_cap,
-    int32_t* __restrict__ n_out, int32_t* __restrict__ error_flag) {
+    int32_t* __restrict__ n_out, int32_t* __restrict__ error_flag, const int32_t* __restrict__ n_tracked_device) {
   extern __shared__ __align__(16) unsigned char s_raw[];
+  if (n_tracked_device) n_tracked = *n_tracked_device;   // fused frame: the count of the device-side _prunePoints
   const int n_bins = g.rows_bin * g.cols_bin;
   int* s_win = reinterpret_cast<int*>(s_raw);
   float* s_disp = reinterpret_cast<float*>(s_win + n_bins);
@@ -533,7 +536,7 @@ void launch_match(const Geometry& g, const StereoParams& sp, const Buffers& b, i
 
 void launch_select(const Geometry& g, const StereoParams& sp, const Buffers& b, int first_pair, int n_pairs,
                    int n_passes, const TrackedPoint* tracked, int n_tracked, FramePointRecord* out,
-                   int out_capacity_per_pair, bool generic, cudaStream_t stream) {
+                   int out_capacity_per_pair, bool generic, cudaStream_t stream, const int32_t* n_tracked_device) {
   // shared state of the strip kernel: 12 B per bin + one counter per bin row
   const size_t smem = (size_t)g.rows_bin * g.cols_bin * 12 + (size_t)(g.rows_bin + 1) * 4;
   if (!generic && smem <= 160 * 1024) {
@@ -543,14 +546,15 @@ void launch_select(const Geometry& g, const StereoParams& sp, const Buffers& b, 
     select_strips_kernel<<<n_pairs, kSelectWarps * 32, smem, stream>>>(
         g, sp, b.row_ptr + (size_t)2 * first_pair * (g.rows + 1), b.kp_xy + (size_t)2 * first_pair * g.cap,
         b.n_desc + 2 * first_pair, b.match + (size_t)first_pair * g.cap, n_passes, tracked, n_tracked,
-        out + (size_t)first_pair * out_capacity_per_pair, out_capacity_per_pair, b.n_out + 2 * first_pair, b.error_flag);
+        out + (size_t)first_pair * out_capacity_per_pair, out_capacity_per_pair, b.n_out + 2 * first_pair, b.error_flag,
+        n_tracked_device);
     return;
   }
   select_kernel<<<n_pairs, 256, 0, stream>>>(g, sp, b.row_ptr + (size_t)2 * first_pair * (g.rows + 1),
                                              b.kp_xy + (size_t)2 * first_pair * g.cap, b.n_desc + 2 * first_pair,
                                              b.match + (size_t)first_pair * g.cap, n_passes, tracked, n_tracked,
                                              out + (size_t)first_pair * out_capacity_per_pair, out_capacity_per_pair,
-                                             b.n_out + 2 * first_pair, b.error_flag);
+                                             b.n_out + 2 * first_pair, b.error_flag, n_tracked_device);
 }
 
 void launch_emit_matches(const Geometry& g, const StereoParams& sp, const Buffers& b, int pair, int n_passes,

@@ -179,8 +179,15 @@ __global__ void __launch_bounds__(256) track_search_kernel(Geometry g, StereoPar
                                                            const uint8_t* desc, const int32_t* n_desc,
                                                            const uint8_t* gone_l, const uint8_t* gone_r,
                                                            const PreviousPoint* __restrict__ previous, int n_previous,
-                                                           int4* __restrict__ tentative) {
+                                                           int4* __restrict__ tentative,
+                                                           const FrameStepState* __restrict__ step) {
   const int u = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (step) {   // fused frame: the point count and the motion prior live in device memory (n_previous = capacity)
+    n_previous = min(n_previous, step->n_previous);
+    if (u >= n_previous) return;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) tp.T[i] = step->T_prior[i];
+  }
   if (u >= n_previous) return;
   const TrackView v = make_view(g, sp, row_ptr, kp_xy, desc, n_desc, gone_l, gone_r);
   Projection proj;
@@ -234,10 +241,16 @@ __global__ void __launch_bounds__(kResolveThreads) track_resolve_kernel(
     Geometry g, StereoParams sp, TrackParams tp, const int32_t* row_ptr, const uint32_t* kp_xy, const uint8_t* desc,
     const int32_t* n_desc, uint8_t* gone_l, uint8_t* gone_r, const PreviousPoint* __restrict__ previous,
     int n_previous, int4* tentative, int32_t* claim_l, int32_t* claim_r, TrackRecord* __restrict__ tracks,
-    int32_t* __restrict__ lost, TrackedPoint* __restrict__ tracked, int32_t* __restrict__ stats) {
+    int32_t* __restrict__ lost, TrackedPoint* __restrict__ tracked, int32_t* __restrict__ stats,
+    const FrameStepState* __restrict__ step) {
   __shared__ int s_red[32];
   __shared__ int s_acc[2];
   const int tid = threadIdx.x;
+  if (step) {   // fused frame: see track_search_kernel
+    n_previous = min(n_previous, step->n_previous);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) tp.T[i] = step->T_prior[i];
+  }
   const TrackView v = make_view(g, sp, row_ptr, kp_xy, desc, n_desc, gone_l, gone_r);
   const int n_l = n_desc[0], n_r = n_desc[1];
 
@@ -468,7 +481,7 @@ __global__ void __launch_bounds__(kResolveThreads) recover_finish_kernel(
 
 void launch_track(const Geometry& g, const StereoParams& sp, const Buffers& b, int pair, const PreviousPoint* previous,
                   int n_previous, const TrackParams& tp, const TrackScratch& s, TrackRecord* tracks, int32_t* lost,
-                  TrackedPoint* tracked, cudaStream_t stream) {
+                  TrackedPoint* tracked, cudaStream_t stream, const FrameStepState* step) {
   const int32_t* row_ptr = b.row_ptr + (size_t)2 * pair * (g.rows + 1);
   const uint32_t* kp_xy = b.kp_xy + (size_t)2 * pair * g.cap;
   const uint8_t* desc = b.desc + (size_t)2 * pair * g.cap * kDescBytes;
@@ -477,10 +490,10 @@ void launch_track(const Geometry& g, const StereoParams& sp, const Buffers& b, i
   uint8_t* gone_r = b.consumed_r + (size_t)pair * g.cap;
   if (n_previous > 0)
     track_search_kernel<<<(n_previous + 7) / 8, 256, 0, stream>>>(g, sp, tp, row_ptr, kp_xy, desc, n_desc, gone_l, gone_r,
-                                                                  previous, n_previous, s.tentative);
+                                                                  previous, n_previous, s.tentative, step);
   track_resolve_kernel<<<1, kResolveThreads, 0, stream>>>(g, sp, tp, row_ptr, kp_xy, desc, n_desc, gone_l, gone_r,
                                                           previous, n_previous, s.tentative, s.claim_l, s.claim_r, tracks,
-                                                          lost, tracked, s.stats);
+                                                          lost, tracked, s.stats, step);
 }
 
 void launch_recover(const Geometry& g, const StereoParams& sp, const Buffers& b, int pair, const uint8_t* blurred,
