@@ -10,6 +10,7 @@
 // ticket after which the last block adds the block partials in a fixed order -> run-to-run deterministic).
 #include <cooperative_groups.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "gn_math.h"
@@ -152,15 +153,35 @@ __device__ __forceinline__ void accumulate_point(const double m0, const double m
   }
 }
 
-// warp shuffle tree + cross-warp sum; the block's kAcc totals end up in threads 0..kAcc-1 (return value)
+// Warp stage of every reduction in this file: the xor-butterfly sum tree of each of the kAcc accumulators, evaluated
+// TRANSPOSED -- at the step with lane distance o a lane keeps the half of its values whose index bit o matches its own
+// lane bit and hands the other half to its partner, so a step moves o values instead of all of them: 31 shuffles of a
+// double instead of 29 x 5.  Every accumulator still sees the sums (l, l ^ 16), then (.., l ^ 8), ... of the plain
+// butterfly, and IEEE addition is commutative: the totals are bit-identical to `v += __shfl_xor_sync(v, o)`.
+// Lane i < kAcc returns the warp's total of accumulator i.
+__device__ __forceinline__ double warp_reduce(const double (&acc)[kAcc]) {
+  const int lane = threadIdx.x & 31;
+  double v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = i < kAcc ? acc[i] : 0.0;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < o; ++j) {
+      const double send = upper ? v[j] : v[j + o];
+      const double keep = upper ? v[j + o] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+// warp stage + cross-warp sum; the block's kAcc totals end up in threads 0..kAcc-1 (return value)
 __device__ __forceinline__ double block_reduce(const double (&acc)[kAcc], double (*s_part)[kAcc]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int i = 0; i < kAcc; ++i) {
-    double v = acc[i];
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) s_part[warp][i] = v;
-  }
+  const double mine = warp_reduce(acc);
+  if (lane < kAcc) s_part[warp][lane] = mine;
   __syncthreads();
   double v = 0;
   if (threadIdx.x < kAcc)
@@ -221,126 +242,137 @@ __global__ void __launch_bounds__(kThreads) linearize_kernel(int n, AlignerBuffe
   }
 }
 
-// solve6 of gn_math.h (Eigen::FullPivLU<Matrix6>::solve) by ONE WARP, bit-identical to the single-thread form: lane j < 6
-// holds column j of the matrix, lane 6 the right-hand side as a seventh column (row swaps and eliminations act on it
-// exactly as on the others).  The single-thread form indexes its arrays with the run-time pivot position, i.e. lives in
-// local memory, and costs ~8 us per Gauss-Newton round; here every index is a compile-time constant or a select.
-// Every lane of the warp must call; every lane receives x[6].
-__device__ __forceinline__ void solve6_warp(const double* H /* 36, row-major */, const double* rhs, double x[6]) {
-  const int lane = threadIdx.x & 31;
-  const unsigned full = 0xffffffffu;
-  double a[6];
+// solve6 of gn_math.h (Eigen::FullPivLU<Matrix6>::solve) with the 6 x 7 augmented matrix in REGISTERS, bit-identical to
+// the single-thread form.  That form indexes its arrays with the run-time pivot position, i.e. lives in local memory
+// (~8 us per Gauss-Newton round); a first register version spread the columns over the lanes of a warp and paid ~400
+// dependent shuffles (5.9 us per round, measured with clock64).  Here every step is unrolled with compile-time indices:
+// the complete-pivot search is a tournament over the candidates in row-major order (the earlier one wins ties, as the
+// scan's strict `>` does), the row / column swaps are selects on the run-time pivot position, no data leaves the
+// thread.  Every calling thread computes the same result (callers run it on one warp and let lane 0 write).
+struct PivotCandidate {
+  double v;
+  int idx;   // 6 i + j
+};
+
+// `a` precedes `b` in row-major order: b wins only with a strictly larger value
+__device__ __forceinline__ PivotCandidate first_max(const PivotCandidate& a, const PivotCandidate& b) {
+  return b.v > a.v ? b : a;
+}
+
+// ordered tournament over c[0..N): neighbours merge, an odd tail moves up (compile-time recursion: every index is a
+// constant, the candidates stay in registers)
+template <int N, int CAP>
+__device__ __forceinline__ void first_max_of(PivotCandidate (&c)[CAP]) {
+  if constexpr (N > 1) {
 #pragma unroll
-  for (int r = 0; r < 6; ++r) a[r] = lane < 6 ? H[r * 6 + lane] : (lane == 6 ? rhs[r] : 0.0);
-  int perm = lane;                 // lane j < 6: perm[j]
-  int rank = 6;
-  double maxpivot = 0;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    if (k < rank) {               // (uniform: after a zero pivot the remaining steps are skipped, as the break does)
-      // ---- complete pivoting: the first element in row-major order that attains the maximum of |A[i][j]|, i, j >= k
-      double best = -1;
-      int bi = k;
-      if (lane >= k && lane < 6) {
-#pragma unroll
-        for (int r = 0; r < 6; ++r)
-          if (r >= k && fabs(a[r]) > best) {
-            best = fabs(a[r]);
-            bi = r;
-          }
-      }
-      int bj = lane;
-#pragma unroll
-      for (int o = 4; o; o >>= 1) {
-        const double ov = __shfl_xor_sync(full, best, o);
-        const int oi = __shfl_xor_sync(full, bi, o), oj = __shfl_xor_sync(full, bj, o);
-        if (ov > best || (ov == best && (oi < bi || (oi == bi && oj < bj)))) {
-          best = ov;
-          bi = oi;
-          bj = oj;
-        }
-      }
-      // lanes 0..7 now agree; everyone takes lane 0's
-      const double biggest = __shfl_sync(full, best, 0);
-      const int pr = __shfl_sync(full, bi, 0), pc = __shfl_sync(full, bj, 0);
-      if (biggest == 0) {
-        rank = k;
-      } else {
-        if (biggest > maxpivot) maxpivot = biggest;
-        if (pr != k) {            // row swap (the right-hand side in lane 6 follows)
-          const double vk = a[k];
-          double vp = vk;
-#pragma unroll
-          for (int r = 0; r < 6; ++r)
-            if (r == pr) vp = a[r];
-#pragma unroll
-          for (int r = 0; r < 6; ++r)
-            if (r == pr) a[r] = vk;
-          a[k] = vp;
-        }
-        {                          // column swap: lanes k and pc exchange their columns and their perm entry
-          const int partner = pc != k ? (lane == k ? pc : (lane == pc ? k : lane)) : lane;
-#pragma unroll
-          for (int r = 0; r < 6; ++r) a[r] = __shfl_sync(full, a[r], partner);
-          perm = __shfl_sync(full, perm, partner);
-        }
-        // ---- elimination: f_i = A[i][k] / A[k][k] from column k (lane k), then A[i][j] -= f_i A[k][j] in every column
-        double f[6];
-        const double pivot = __shfl_sync(full, a[k], k);
-#pragma unroll
-        for (int r = 0; r < 6; ++r) f[r] = r > k ? __shfl_sync(full, a[r], k) / pivot : 0.0;
-        if (lane == k) {
-#pragma unroll
-          for (int r = 0; r < 6; ++r)
-            if (r > k) a[r] = f[r];
-        } else if (lane > k && lane <= 6) {
-#pragma unroll
-          for (int r = 0; r < 6; ++r)
-            if (r > k) a[r] = a[r] - f[r] * a[k];
-        }
-      }
-    }
+    for (int t = 0; t < N / 2; ++t) c[t] = first_max(c[2 * t], c[2 * t + 1]);
+    if (N & 1) c[N / 2] = c[N - 1];
+    first_max_of<(N + 1) / 2, CAP>(c);
   }
-  // Eigen::FullPivLU::rank(): only pivots above |largest pivot| * epsilon * size are used by solve()
-  {
-    double diag = 0;
+}
+
+template <int K>
+__device__ __forceinline__ void lu_step(double (&A)[6][7], int (&perm)[6], int& rank, double& maxpivot) {
+  if (rank < 6) return;                 // a zero pivot ended the elimination (the break of the scalar form)
+  constexpr int M = 6 - K;              // the trailing block is M x M
+  PivotCandidate c[M * M];
 #pragma unroll
-    for (int r = 0; r < 6; ++r)
-      if (r == lane) diag = a[r];
-    const bool used = lane < rank && fabs(diag) > maxpivot * (2.220446049250313e-16 * 6);
-    rank = __popc(__ballot_sync(full, used));
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) c[i * M + j] = PivotCandidate{fabs(A[K + i][K + j]), 6 * (K + i) + (K + j)};
+  first_max_of<M * M, M * M>(c);
+  const double biggest = c[0].v;
+  if (biggest == 0) {
+    rank = K;
+    return;
   }
-  // ---- back substitution, every lane redundantly on a gathered copy of U and the transformed right-hand side
-  double U[6][6], bb[6], y[6];
+  if (biggest > maxpivot) maxpivot = biggest;
+  const int pr = (c[0].idx * 43) >> 8;  // idx / 6 for idx < 36
+  const int pc = c[0].idx - 6 * pr;
+  // rows K and pr (columns >= K and the right-hand side: the multipliers left of K are never read again)
+#pragma unroll
+  for (int j = K; j < 7; ++j) {
+    const double vk = A[K][j];
+    double vp = vk;
+#pragma unroll
+    for (int r = K + 1; r < 6; ++r) vp = pr == r ? A[r][j] : vp;
+#pragma unroll
+    for (int r = K + 1; r < 6; ++r) A[r][j] = pr == r ? vk : A[r][j];
+    A[K][j] = vp;
+  }
+  // columns K and pc (every row: the finished rows of U above K follow the permutation)
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
-    bb[i] = __shfl_sync(full, a[i], 6);
+    const double vk = A[i][K];
+    double vp = vk;
 #pragma unroll
-    for (int j = 0; j < 6; ++j)
-      U[i][j] = j >= i ? __shfl_sync(full, a[i], j) : 0.0;
+    for (int q = K + 1; q < 6; ++q) vp = pc == q ? A[i][q] : vp;
+#pragma unroll
+    for (int q = K + 1; q < 6; ++q) A[i][q] = pc == q ? vk : A[i][q];
+    A[i][K] = vp;
   }
+  {
+    const int vk = perm[K];
+    int vp = vk;
+#pragma unroll
+    for (int q = K + 1; q < 6; ++q) vp = pc == q ? perm[q] : vp;
+#pragma unroll
+    for (int q = K + 1; q < 6; ++q) perm[q] = pc == q ? vk : perm[q];
+    perm[K] = vp;
+  }
+#pragma unroll
+  for (int i = K + 1; i < 6; ++i) {
+    const double f = A[i][K] / A[K][K];
+#pragma unroll
+    for (int j = K + 1; j < 7; ++j) A[i][j] = A[i][j] - f * A[K][j];
+  }
+}
+
+__device__ __forceinline__ void solve6_regs(const double* H /* 36, row-major */, const double* rhs, double x[6]) {
+  double A[6][7];
+  int perm[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) A[i][j] = H[i * 6 + j];
+    A[i][6] = rhs[i];
+    perm[i] = i;
+  }
+  int rank = 6;
+  double maxpivot = 0;
+  lu_step<0>(A, perm, rank, maxpivot);
+  lu_step<1>(A, perm, rank, maxpivot);
+  lu_step<2>(A, perm, rank, maxpivot);
+  lu_step<3>(A, perm, rank, maxpivot);
+  lu_step<4>(A, perm, rank, maxpivot);
+  lu_step<5>(A, perm, rank, maxpivot);
+  // Eigen::FullPivLU::rank(): only pivots above |largest pivot| * epsilon * size are used by solve()
+  {
+    int r = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r += (i < rank && fabs(A[i][i]) > maxpivot * (2.220446049250313e-16 * 6)) ? 1 : 0;
+    rank = r;
+  }
+  double y[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) y[i] = 0;
 #pragma unroll
   for (int i = 5; i >= 0; --i) {
     if (i < rank) {
-      double sum = bb[i];
+      double sum = A[i][6];
 #pragma unroll
       for (int j = 0; j < 6; ++j)
-        if (j > i && j < rank) sum = sum - U[i][j] * y[j];
-      y[i] = sum / U[i][i];
+        if (j > i && j < rank) sum = sum - A[i][j] * y[j];
+      y[i] = sum / A[i][i];
     }
   }
   // x[perm[i]] = y[i]
 #pragma unroll
   for (int t = 0; t < 6; ++t) x[t] = 0;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    const int pi = __shfl_sync(full, perm, i);
+  for (int i = 0; i < 6; ++i)
 #pragma unroll
-    for (int t = 0; t < 6; ++t)
-      if (t == pi) x[t] = y[i];
-  }
+    for (int t = 0; t < 6; ++t) x[t] = perm[i] == t ? y[i] : x[t];
 }
 
 // oneRound (:190-207 / :174-191) + the converge state machine (:213-247 / :197-233) for one finished linearisation:
@@ -351,17 +383,17 @@ __device__ __forceinline__ void gn_step(GnControl* ctl, const double* s_sys, con
                                         const GnParams& p) {
   const int lane = threadIdx.x & 31;
   {   // H as the single-thread form builds it: both triangles from the packed upper one, then the damping on the diagonal
-    int k = 0;
-    for (int i = 0; i < 6; ++i)
-      for (int j = i; j < 6; ++j, ++k)
-        if (lane == 0) s_H[i * 6 + j] = s_H[j * 6 + i] = s_sys[k];
-    __syncwarp();
-    if (lane < 6) s_H[lane * 6 + lane] += p.damping * n;
+    for (int idx = lane; idx < 36; idx += 32) {
+      const int i = idx / 6, j = idx - 6 * i;
+      double v = s_sys[tri(min(i, j), max(i, j))];
+      if (i == j) v += p.damping * n;
+      s_H[idx] = v;
+    }
     __syncwarp();
   }
   double nb[6], dx[6];
   for (int i = 0; i < 6; ++i) nb[i] = -s_sys[21 + i];
-  solve6_warp(s_H, nb, dx);
+  solve6_regs(s_H, nb, dx);
   if (lane != 0) return;
   double T[12];
   for (int i = 0; i < 12; ++i) T[i] = s_T[i];
@@ -463,12 +495,19 @@ __global__ void __launch_bounds__(kThreads) converge_kernel(int n, AlignerBuffer
   }
 }
 
-// The same loop for the problem sizes of a tracked frame (n <= 8 x 256 correspondences): ONE thread-block cluster
+// The same loop for the problem sizes of a tracked frame (one correspondence per thread): ONE thread-block cluster
 // instead of a cooperative grid.  The CTAs of the cluster are the blocks of the grid version -- same per-point code, same
-// per-block partials, same order of the final sum, so pose and round count stay bit-identical -- but the two barriers of
-// a round are cluster barriers (hardware, no round trip through global memory), the block partials and the control
-// block live in shared memory and are read through distributed shared memory, and every thread keeps its ONE
-// correspondence in registers across the rounds.  Launched as a plain kernel with a cluster dimension.
+// per-block partials, same order of the final sum, so pose and round count stay bit-identical -- but
+//  * every thread keeps its ONE correspondence in registers across the rounds;
+//  * a round has ONE barrier, a hardware cluster barrier: every block publishes its partial sums in its own shared
+//    memory (double-buffered by round parity, so a block that runs ahead cannot overwrite what a slower block still
+//    reads), then EVERY block gathers all partials through distributed shared memory in block order and runs the
+//    damped solve, the pose update and the convergence state machine itself on its own copy of the control block --
+//    redundant, deterministic and identical in every block, instead of block 0 solving while the others wait at a
+//    second barrier and then fetch the pose from it;
+//  * blocks without a correspondence exit at once (their partials would be +0.0: skipping them leaves every sum
+//    unchanged; a cluster barrier waits for the non-exited threads only).
+// Launched as a plain kernel with a cluster dimension.
 template <int KIND>
 __global__ void __launch_bounds__(kThreads, 1) converge_cluster_kernel(int n, AlignerBuffers b, AlignerCamera cam, GnParams p,
                                                                     GnControl* __restrict__ ctl,
@@ -482,26 +521,25 @@ __global__ void __launch_bounds__(kThreads, 1) converge_cluster_kernel(int n, Al
     if (n <= 0 || n > (int)(gridDim.x * kThreads)) return;
   }
   cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank(), n_blocks = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  const int n_active = (n + kThreads - 1) / kThreads;     // blocks that hold a correspondence
+  if (rank >= n_active) return;
   __shared__ double s_part[kThreads / 32][kAcc];
-  __shared__ double s_total[32];        // this block's partial sums, read by block 0
+  __shared__ double s_total[2][32];     // this block's partial sums of the even / odd rounds, read by every block
   __shared__ double s_T[12];
   __shared__ double s_sys[32];
   __shared__ double s_H[36];
-  __shared__ GnControl s_ctl;           // authoritative copy in block 0
-  GnControl* ctl0 = cluster.map_shared_rank(&s_ctl, 0);
+  __shared__ GnControl s_ctl;           // every block advances its own copy (identically)
 
-  if (rank == 0) {
-    if (threadIdx.x < 12) s_ctl.T[threadIdx.x] = ctl->T[threadIdx.x];
-    if (threadIdx.x == 0) {
-      s_ctl.total_error_previous = ctl->total_error_previous;
-      s_ctl.rounds = ctl->rounds;
-      s_ctl.phase = ctl->phase;
-      s_ctl.iteration = ctl->iteration;
-      s_ctl.ignore = ctl->ignore;
-      s_ctl.converged = ctl->converged;
-      s_ctl.done = ctl->done;
-    }
+  if (threadIdx.x < 12) s_ctl.T[threadIdx.x] = ctl->T[threadIdx.x];
+  if (threadIdx.x == 0) {
+    s_ctl.total_error_previous = ctl->total_error_previous;
+    s_ctl.rounds = ctl->rounds;
+    s_ctl.phase = ctl->phase;
+    s_ctl.iteration = ctl->iteration;
+    s_ctl.ignore = ctl->ignore;
+    s_ctl.converged = ctl->converged;
+    s_ctl.done = ctl->done;
   }
   // this thread's correspondence (the grid version's block `rank`, thread threadIdx.x, first and only iteration)
   const int u = rank * kThreads + threadIdx.x;
@@ -520,44 +558,58 @@ __global__ void __launch_bounds__(kThreads, 1) converge_cluster_kernel(int n, Al
     for (int d = 0; d < W; ++d) om[d] = b.omega[d * b.stride + u];
     wt = b.wt[u];
   }
-  cluster.sync();
+  __syncthreads();
 
   double err = -1.0;
   uint8_t inl = 0;
-  for (;;) {
-    if (threadIdx.x < 12) s_T[threadIdx.x] = ctl0->T[threadIdx.x];
-    const int ignore_outliers = ctl0->ignore;
+#ifdef VSLAM_GN_TIMING   // phase clocks of block 0 (development aid: make EXTRA_aligner="-fmad=false -DVSLAM_GN_TIMING")
+  long long t_phase[6] = {0, 0, 0, 0, 0, 0}, t_mark = clock64();
+#define GN_MARK(i) { const long long t_now = clock64(); t_phase[i] += t_now - t_mark; t_mark = t_now; }
+#else
+#define GN_MARK(i)
+#endif
+  for (int parity = 0;; parity ^= 1) {
+    if (threadIdx.x < 12) s_T[threadIdx.x] = s_ctl.T[threadIdx.x];
+    const int ignore_outliers = s_ctl.ignore;
     __syncthreads();
+    GN_MARK(0)
     double acc[kAcc];
 #pragma unroll
     for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
     if (mine) accumulate_point<KIND>(m[0], m[1], m[2], fx, om, wt, s_T, cam, ignore_outliers, p.kernel, acc, err, inl);
+    GN_MARK(1)
     const double total = block_reduce(acc, s_part);
-    if (threadIdx.x < kAcc) s_total[threadIdx.x] = total;
-    cluster.sync();                     // every block's partial is in its shared memory
+    if (threadIdx.x < kAcc) s_total[parity][threadIdx.x] = total;
+    GN_MARK(2)
+    cluster.sync();                     // every block's partial of this round is in its shared memory
+    GN_MARK(3)
 
-    if (rank == 0) {
-      {  // the block partials in block order, 8 interleaved slices per value -- as in linearize_kernel (blocks without a
-         // correspondence contribute +0.0, so a cluster larger than the grid of the stepwise path adds up to the same bits)
-        const int j = threadIdx.x & 31, part = threadIdx.x >> 5;
-        double v = 0;
-        if (j < kAcc)
-          for (int blk = part; blk < n_blocks; blk += kThreads / 32) v += cluster.map_shared_rank(s_total, blk)[j];
-        __syncthreads();
-        if (j < kAcc) s_part[part][j] = v;
-        __syncthreads();
-        if (threadIdx.x < kAcc) {
-          double s = 0;
-          for (int w = 0; w < kThreads / 32; ++w) s += s_part[w][threadIdx.x];
-          s_sys[threadIdx.x] = s;
-        }
-        __syncthreads();
+    {  // the block partials in block order, 8 interleaved slices per value -- as in linearize_kernel
+      const int j = threadIdx.x & 31, part = threadIdx.x >> 5;
+      double v = 0;
+      if (j < kAcc)
+        for (int blk = part; blk < n_active; blk += kThreads / 32) v += cluster.map_shared_rank(&s_total[parity][0], blk)[j];
+      __syncthreads();
+      if (j < kAcc) s_part[part][j] = v;
+      __syncthreads();
+      if (threadIdx.x < kAcc) {
+        double s = 0;
+        for (int w = 0; w < kThreads / 32; ++w) s += s_part[w][threadIdx.x];
+        s_sys[threadIdx.x] = s;
       }
-      if (threadIdx.x < 32) gn_step(&s_ctl, s_sys, s_T, s_H, n, p);
+      __syncthreads();
     }
-    cluster.sync();                     // block 0's control block is final for this round
-    if (ctl0->done) break;
+    GN_MARK(4)
+    if (threadIdx.x < 32) gn_step(&s_ctl, s_sys, s_T, s_H, n, p);
+    GN_MARK(5)
+    __syncthreads();
+    if (s_ctl.done) break;
   }
+#ifdef VSLAM_GN_TIMING
+  if (rank == 0 && threadIdx.x == 0)
+    printf("gn timing (cycles, %d rounds): load T %lld | accumulate %lld | block reduce %lld | cluster barrier %lld | gather %lld | "
+           "solve + update %lld\n", s_ctl.rounds, t_phase[0], t_phase[1], t_phase[2], t_phase[3], t_phase[4], t_phase[5]);
+#endif
   // errors[] / inliers[] hold the last round's values as in the reference; the system and the control block go to
   // global memory once
   if (mine) {
@@ -578,7 +630,7 @@ __global__ void __launch_bounds__(kThreads, 1) converge_cluster_kernel(int n, Al
       ctl->done = s_ctl.done;
     }
   }
-  cluster.sync();                       // no block may exit while block 0 still reads its shared memory
+  cluster.sync();                       // no block may exit while another still reads its partials of the last round
 }
 
 // Batched form for independent stereo pairs: one WARP per pair linearises the StereoUV problem that aligns the
@@ -621,13 +673,7 @@ __global__ void __launch_bounds__(kPairWarps * 32) linearize_pairs_kernel(const 
     errors[(size_t)pair * record_stride + u] = err;
     inliers[(size_t)pair * record_stride + u] = inl;
   }
-  double mine = 0.0;   // lane i ends up with the warp's total i
-#pragma unroll
-  for (int i = 0; i < kAcc; ++i) {
-    double v = acc[i];
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == i) mine = v;
-  }
+  const double mine = warp_reduce(acc);   // lane i ends up with the warp's total i
   s_part[warp][lane] = mine;
   __syncthreads();
   if (warp == 0 && lane < kAcc) {

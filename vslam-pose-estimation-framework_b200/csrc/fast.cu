@@ -472,6 +472,116 @@ __global__ void __launch_bounds__(256) compact_kernel(Geometry g, const uint32_t
   }
 }
 
+// K2 for a single frame: ONE 512-thread CTA per image instead of one thread per row.  The mask of an image is a
+// row-major list of uint4 (mask_words is a multiple of 4); thread t owns the Q consecutive uint4 from t * Q, loads them
+// all at once (independent loads: one memory round trip), counts its keypoints, ONE block scan gives its offset in the
+// (row, col)-sorted list, and it emits its own bits in order.  The thread that owns the first uint4 of a row writes that
+// row's CSR pointer.  Same outputs as compact_kernel, which every single-pair initialize() and every fused frame pays for
+// (ncu: profiles/r2s).
+constexpr int kCompactFrameThreads = 512;
+constexpr int kCompactFrameBatch = 8;    // uint4 loaded at once (32 registers)
+constexpr int kCompactFrameMaxQ = 64;    // uint4 per thread: images up to 512 x 64 x 128 = 4.2 M mask bits
+__global__ void __launch_bounds__(kCompactFrameThreads) compact_frame_kernel(
+    Geometry g, const uint32_t* __restrict__ mask, int32_t* __restrict__ row_ptr, uint32_t* __restrict__ kp_xy,
+    int32_t* __restrict__ n_desc, int32_t* __restrict__ error_flag, uint8_t* __restrict__ pruned_l,
+    uint8_t* __restrict__ consumed_r, int Q) {
+  __shared__ int s_warp[kCompactFrameThreads / 32];
+  const int img = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  {   // a new frame: no feature is pruned yet (see compact_kernel)
+    uint32_t* flags = reinterpret_cast<uint32_t*>(((img & 1) ? consumed_r : pruned_l) + (size_t)(img >> 1) * g.cap);
+    for (int i = tid; i < (g.cap + 3) / 4; i += kCompactFrameThreads) flags[i] = 0u;   // (cap bytes, allocations are 256-byte aligned)
+  }
+  const uint4* m = reinterpret_cast<const uint4*>(mask + (size_t)img * g.rows * g.mask_words);
+  const int per_row = g.mask_words >> 2, total = per_row * g.rows;
+  const int lo_x = g.border, hi_x = g.cols - g.border, lo_y = g.border, hi_y = g.rows - g.border;
+  const int w_lo = lo_x >> 5, w_hi = min(g.mask_words - 1, (hi_x - 1) >> 5);
+  const uint32_t m_lo = 0xffffffffu << (lo_x & 31);
+  const uint32_t m_hi = ((hi_x & 31) == 0) ? 0xffffffffu : (0xffffffffu >> (32 - (hi_x & 31)));
+  auto clip = [&](uint32_t w, int wd) -> uint32_t {
+    if (wd < w_lo || wd > w_hi) return 0u;
+    if (wd == w_lo) w &= m_lo;
+    if (wd == w_hi) w &= m_hi;
+    return w;
+  };
+  auto clip4 = [&](uint4 v, int y, int xq) -> uint4 {
+    if (!(y >= lo_y && y < hi_y && hi_x > lo_x)) return make_uint4(0, 0, 0, 0);
+    return make_uint4(clip(v.x, 4 * xq), clip(v.y, 4 * xq + 1), clip(v.z, 4 * xq + 2), clip(v.w, 4 * xq + 3));
+  };
+  const int q0 = tid * Q;
+  const int y0 = q0 / per_row, xq0 = q0 - y0 * per_row;   // row and uint4 column of the thread's first entry
+
+  // pass 1: count
+  int count = 0;
+  {
+    int y = y0, xq = xq0;
+    for (int c0 = 0; c0 < Q; c0 += kCompactFrameBatch) {
+      uint4 v[kCompactFrameBatch];
+#pragma unroll
+      for (int i = 0; i < kCompactFrameBatch; ++i)
+        v[i] = c0 + i < Q && q0 + c0 + i < total ? __ldg(m + q0 + c0 + i) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int i = 0; i < kCompactFrameBatch; ++i) {
+        const uint4 c = clip4(v[i], y, xq);
+        count += __popc(c.x) + __popc(c.y) + __popc(c.z) + __popc(c.w);
+        if (++xq == per_row) xq = 0, ++y;
+      }
+    }
+  }
+  // block-wide exclusive scan of the thread counts
+  int inc = count;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  int before = 0, all = 0;
+  for (int w = 0; w < kCompactFrameThreads / 32; ++w) {
+    const int c = s_warp[w];
+    if (w < warp) before += c;
+    all += c;
+  }
+  // pass 2: the same entries again (L1 / L2 hits), emitted in order
+  int idx = before + inc - count;
+  int32_t* rp = row_ptr + (size_t)img * (g.rows + 1);
+  uint32_t* xy = kp_xy + (size_t)img * g.cap;
+  {
+    int y = y0, xq = xq0;
+    for (int c0 = 0; c0 < Q; c0 += kCompactFrameBatch) {
+      uint4 v[kCompactFrameBatch];
+#pragma unroll
+      for (int i = 0; i < kCompactFrameBatch; ++i)
+        v[i] = c0 + i < Q && q0 + c0 + i < total ? __ldg(m + q0 + c0 + i) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int i = 0; i < kCompactFrameBatch; ++i) {
+        if (c0 + i < Q && q0 + c0 + i < total) {
+          if (xq == 0) rp[y] = min(idx, g.cap);
+          const uint4 c = clip4(v[i], y, xq);
+          const uint32_t w4[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t bits = w4[j];
+            while (bits) {
+              const int bpos = __ffs(bits) - 1;
+              bits &= bits - 1;
+              if (idx < g.cap) xy[idx] = (uint32_t)((4 * xq + j) * 32 + bpos) | ((uint32_t)y << 16);
+              ++idx;
+            }
+          }
+        }
+        if (++xq == per_row) xq = 0, ++y;
+      }
+    }
+  }
+  if (tid == 0) {
+    rp[g.rows] = min(all, g.cap);
+    n_desc[img] = min(all, g.cap);
+    if (all > g.cap) atomicExch(error_flag, 1);
+  }
+}
+
 // one thread per 4 output bytes: aligned 32-bit store, source assembled from two aligned words (rows of the dense
 // layout start at arbitrary byte offsets, e.g. stride 1241)
 __global__ void __launch_bounds__(256) repitch_kernel(Geometry g, const uint8_t* __restrict__ left,
@@ -522,6 +632,15 @@ void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, con
 }
 
 void launch_compact(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream) {
+  const int total = (g.mask_words >> 2) * g.rows;
+  const int Q = (total + kCompactFrameThreads - 1) / kCompactFrameThreads;
+  if (n_images <= 16 && Q <= kCompactFrameMaxQ) {   // single frames: one wide CTA per image (latency)
+    compact_frame_kernel<<<n_images, kCompactFrameThreads, 0, stream>>>(
+        g, b.mask + (size_t)first_image * g.rows * g.mask_words, b.row_ptr + (size_t)first_image * (g.rows + 1),
+        b.kp_xy + (size_t)first_image * g.cap, b.n_desc + first_image, b.error_flag,
+        b.pruned_l + (size_t)(first_image >> 1) * g.cap, b.consumed_r + (size_t)(first_image >> 1) * g.cap, Q);
+    return;
+  }
   const int strips = n_images <= 16 ? 8 : 1;   // single frames: split each image over 8 CTAs (latency)
   const size_t smem = sizeof(int) * ((g.rows + strips - 1) / strips + 2);
   compact_kernel<<<dim3(strips, n_images), 256, smem, stream>>>(

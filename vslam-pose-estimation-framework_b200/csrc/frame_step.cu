@@ -55,55 +55,61 @@ __global__ void __launch_bounds__(kFillThreads) frame_aligner_fill_kernel(FrameS
   f.track_length[u] = pp->reserved;                          // trackLength() of the previous point (frame_point.cpp:27)
 }
 
-// pose_tracker_3d.cpp:437-472.  One CTA, 8 consecutive tracks per thread (up to 8192); the kept bin pre-load records are
-// compacted in place, in order (every thread reads its share before anyone writes).
+// pose_tracker_3d.cpp:437-472.  One CTA; track k is handled by thread k mod 1024 in chunk k / 1024 (at most 4 chunks:
+// the fused frame holds 4096 tracks), every load of a thread is independent of the others (one memory round trip), and
+// the ordered positions come from one block scan per chunk.  The kept bin pre-load records are compacted in place: a
+// chunk writes to positions at or below its own indices, all of which have been read before its scan's barrier.
 constexpr int kPruneThreads = 1024;
+constexpr int kPruneChunks = 4;
 __global__ void __launch_bounds__(kPruneThreads) frame_prune_kernel(FrameStepBuffers f, FrameStepParams p) {
   __shared__ int s_warp[kPruneThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = min(f.stats[0], f.cap);
+  const int n = min(f.stats[0], min(f.cap, kPruneThreads * kPruneChunks));
   // averageError() = total error / correspondences (base_aligner.h:46) of the last linearisation
   const bool inliers_only = n > 0 && f.aligner.system[27] / n < p.error_kernel;
   const double cap = 100 * p.error_kernel;
-  constexpr int kPer = 8;
-  const int begin = tid * kPer;
-  TrackedPoint mine[kPer];
-  int kept = 0;
-  unsigned keep_mask = 0;
+  uint4 rec[kPruneChunks][2];
+  bool keep[kPruneChunks];
 #pragma unroll
-  for (int j = 0; j < kPer; ++j) {
-    const int k = begin + j;
+  for (int j = 0; j < kPruneChunks; ++j) {
+    const int k = j * kPruneThreads + tid;
+    keep[j] = false;
     if (k < n) {
-      const bool keep = inliers_only ? f.aligner.inliers[k] != 0 : (f.aligner.errors[k] != -1.0 && f.aligner.errors[k] < cap);
-      if (keep) {
-        mine[kept++] = f.tracked[k];
-        keep_mask |= 1u << j;
-      }
+      const double e = f.aligner.errors[k];
+      keep[j] = inliers_only ? f.aligner.inliers[k] != 0 : (e != -1.0 && e < cap);
+      const uint4* src = reinterpret_cast<const uint4*>(f.tracked + k);
+      rec[j][0] = src[0];
+      rec[j][1] = src[1];
     }
   }
-  int inc = kept;
+  int base = 0;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += v;
-  }
-  if (lane == 31) s_warp[warp] = inc;
-  __syncthreads();                              // (also: every record has been read)
-  int base = 0, total = 0;
-  for (int w = 0; w < kPruneThreads / 32; ++w) {
-    if (w < warp) base += s_warp[w];
-    total += s_warp[w];
-  }
-  const int first = base + inc - kept;
-  for (int j = 0; j < kept; ++j) f.tracked[first + j] = mine[j];
-  int pos = first;
-#pragma unroll
-  for (int j = 0; j < kPer; ++j) {
-    const int k = begin + j;
-    if (k < n) f.kept_pos[k] = (keep_mask >> j) & 1u ? pos++ : -1;
+  for (int j = 0; j < kPruneChunks; ++j) {
+    if (j * kPruneThreads >= n) break;             // (uniform)
+    const unsigned bal = __ballot_sync(0xffffffffu, keep[j]);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();                               // (also: every record of this chunk has been read)
+    int before = 0, total = 0;
+    for (int w = 0; w < kPruneThreads / 32; ++w) {
+      const int c = s_warp[w];
+      if (w < warp) before += c;
+      total += c;
+    }
+    const int k = j * kPruneThreads + tid;
+    if (k < n) {
+      const int pos = base + before + __popc(bal & ((1u << lane) - 1u));
+      f.kept_pos[k] = keep[j] ? pos : -1;
+      if (keep[j]) {
+        uint4* dst = reinterpret_cast<uint4*>(f.tracked + pos);
+        dst[0] = rec[j][0];
+        dst[1] = rec[j][1];
+      }
+    }
+    base += total;
+    __syncthreads();                               // s_warp is reused by the next chunk
   }
   if (tid == 0) {
-    f.state->n_kept = total;
+    f.state->n_kept = base;
     f.state->inliers_only = inliers_only;
   }
 }
