@@ -9,6 +9,8 @@
 // FAST-9/16 semantics (OpenCV, TYPE_9_16, nonmaxSuppression=true): SURVEY.md Appendix A.1.
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "kernels.cuh"
 
 namespace vslam {
@@ -472,25 +474,32 @@ __global__ void __launch_bounds__(256) compact_kernel(Geometry g, const uint32_t
   }
 }
 
-// K2 for a single frame: ONE 512-thread CTA per image instead of one thread per row.  The mask of an image is a
-// row-major list of uint4 (mask_words is a multiple of 4); thread t owns the Q consecutive uint4 from t * Q, loads them
-// all at once (independent loads: one memory round trip), counts its keypoints, ONE block scan gives its offset in the
-// (row, col)-sorted list, and it emits its own bits in order.  The thread that owns the first uint4 of a row writes that
-// row's CSR pointer.  Same outputs as compact_kernel, which every single-pair initialize() and every fused frame pays for
-// (ncu: profiles/r2s).
-constexpr int kCompactFrameThreads = 512;
+// K2 for a single frame: ONE CLUSTER of 8 CTAs per image instead of one thread per row (the batched kernel above keeps
+// 2 SMs busy with a frame and is bound by its own instruction latency there: 14 us per KITTI frame, 37 us per 1920 x 1080
+// frame, ncu profiles/r2u).  The mask of an image is a row-major list of uint4 (mask_words is a multiple of 4); thread t
+// of the cluster's 2048 owns the Q consecutive uint4 from t * Q, loads them all at once (independent loads: one memory
+// round trip), counts its keypoints; a block scan, the block totals exchanged through distributed shared memory and ONE
+// cluster barrier give its offset in the (row, col)-sorted list, and it emits its own bits in order.  The thread that
+// owns the first uint4 of a row writes that row's CSR pointer.  Same outputs as compact_kernel.
+constexpr int kCompactFrameThreads = 256;
+constexpr int kCompactFrameBlocks = 8;   // CTAs per cluster = per image (portable cluster size)
 constexpr int kCompactFrameBatch = 8;    // uint4 loaded at once (32 registers)
-constexpr int kCompactFrameMaxQ = 64;    // uint4 per thread: images up to 512 x 64 x 128 = 4.2 M mask bits
+constexpr int kCompactFrameMaxQ = 64;    // uint4 per thread: images up to 2048 x 64 x 128 = 16.7 M mask bits
 __global__ void __launch_bounds__(kCompactFrameThreads) compact_frame_kernel(
     Geometry g, const uint32_t* __restrict__ mask, int32_t* __restrict__ row_ptr, uint32_t* __restrict__ kp_xy,
     int32_t* __restrict__ n_desc, int32_t* __restrict__ error_flag, uint8_t* __restrict__ pruned_l,
     uint8_t* __restrict__ consumed_r, int Q) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ int s_warp[kCompactFrameThreads / 32];
-  const int img = blockIdx.x;
+  __shared__ int s_block_total;
+  const int img = blockIdx.x / kCompactFrameBlocks;
+  const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ct = rank * kCompactFrameThreads + tid;   // thread index within the image's cluster
   {   // a new frame: no feature is pruned yet (see compact_kernel)
     uint32_t* flags = reinterpret_cast<uint32_t*>(((img & 1) ? consumed_r : pruned_l) + (size_t)(img >> 1) * g.cap);
-    for (int i = tid; i < (g.cap + 3) / 4; i += kCompactFrameThreads) flags[i] = 0u;   // (cap bytes, allocations are 256-byte aligned)
+    for (int i = ct; i < (g.cap + 3) / 4; i += kCompactFrameThreads * kCompactFrameBlocks) flags[i] = 0u;   // (allocations are 256-byte aligned)
   }
   const uint4* m = reinterpret_cast<const uint4*>(mask + (size_t)img * g.rows * g.mask_words);
   const int per_row = g.mask_words >> 2, total = per_row * g.rows;
@@ -508,7 +517,7 @@ __global__ void __launch_bounds__(kCompactFrameThreads) compact_frame_kernel(
     if (!(y >= lo_y && y < hi_y && hi_x > lo_x)) return make_uint4(0, 0, 0, 0);
     return make_uint4(clip(v.x, 4 * xq), clip(v.y, 4 * xq + 1), clip(v.z, 4 * xq + 2), clip(v.w, 4 * xq + 3));
   };
-  const int q0 = tid * Q;
+  const int q0 = ct * Q;
   const int y0 = q0 / per_row, xq0 = q0 - y0 * per_row;   // row and uint4 column of the thread's first entry
 
   // pass 1: count
@@ -528,7 +537,7 @@ __global__ void __launch_bounds__(kCompactFrameThreads) compact_frame_kernel(
       }
     }
   }
-  // block-wide exclusive scan of the thread counts
+  // exclusive scan of the thread counts: within the warp, over the block's warps, over the cluster's blocks
   int inc = count;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -537,10 +546,20 @@ __global__ void __launch_bounds__(kCompactFrameThreads) compact_frame_kernel(
   }
   if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
-  int before = 0, all = 0;
+  int before = 0, block_total = 0;
+#pragma unroll
   for (int w = 0; w < kCompactFrameThreads / 32; ++w) {
     const int c = s_warp[w];
     if (w < warp) before += c;
+    block_total += c;
+  }
+  if (tid == 0) s_block_total = block_total;
+  cluster.sync();                           // every block's total is in its shared memory
+  int all = 0;
+#pragma unroll
+  for (int r = 0; r < kCompactFrameBlocks; ++r) {
+    const int c = *cluster.map_shared_rank(&s_block_total, r);
+    if (r < rank) before += c;
     all += c;
   }
   // pass 2: the same entries again (L1 / L2 hits), emitted in order
@@ -575,18 +594,23 @@ __global__ void __launch_bounds__(kCompactFrameThreads) compact_frame_kernel(
       }
     }
   }
-  if (tid == 0) {
+  if (ct == 0) {
     rp[g.rows] = min(all, g.cap);
     n_desc[img] = min(all, g.cap);
     if (all > g.cap) atomicExch(error_flag, 1);
   }
+  cluster.sync();                           // no block may exit while another still reads its total
 }
 
 // one thread per 4 output bytes: aligned 32-bit store, source assembled from two aligned words (rows of the dense
 // layout start at arbitrary byte offsets, e.g. stride 1241)
 __global__ void __launch_bounds__(256) repitch_kernel(Geometry g, const uint8_t* __restrict__ left,
                                                       const uint8_t* __restrict__ right, int stride,
-                                                      uint8_t* __restrict__ image) {
+                                                      uint8_t* __restrict__ image, int32_t* __restrict__ clear,
+                                                      int n_clear) {
+  // single frames: the raw FAST counters of the frame are zeroed here instead of by a memset node in front of FAST
+  if (clear && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+    for (int i = threadIdx.x; i < n_clear; i += 256) clear[i] = 0;
   const int words = g.pitch >> 2;
   const int row = blockIdx.y;
   const int img = blockIdx.z;   // 2 * pair + side
@@ -610,9 +634,9 @@ __global__ void __launch_bounds__(256) repitch_kernel(Geometry g, const uint8_t*
 }
 
 void launch_repitch(const Geometry& g, const uint8_t* left, const uint8_t* right, int stride, uint8_t* image,
-                    int n_pairs, cudaStream_t stream) {
+                    int n_pairs, cudaStream_t stream, int32_t* clear, int n_clear) {
   dim3 grid(((g.pitch >> 2) + 255) / 256, g.rows, 2 * n_pairs);
-  repitch_kernel<<<grid, 256, 0, stream>>>(g, left, right, stride, image);
+  repitch_kernel<<<grid, 256, 0, stream>>>(g, left, right, stride, image, clear, n_clear);
 }
 
 bool make_fast_tensor_map(const Geometry& g, const uint8_t* images, int n_images, CUtensorMap* out) {
@@ -620,11 +644,12 @@ bool make_fast_tensor_map(const Geometry& g, const uint8_t* images, int n_images
 }
 
 void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, const CUtensorMap& image_map, int first_image,
-                 int n_images, cudaStream_t stream, const int32_t* device_thresholds) {
+                 int n_images, cudaStream_t stream, const int32_t* device_thresholds, bool counts_cleared) {
   const int single = g.n_regions == 1;
   const size_t mask_bytes = (size_t)g.rows * g.mask_words * sizeof(uint32_t);
   if (!single) cudaMemsetAsync(b.mask + (size_t)first_image * g.rows * g.mask_words, 0, mask_bytes * n_images, stream);
-  cudaMemsetAsync(b.raw_count + (size_t)first_image * g.n_regions, 0, sizeof(int32_t) * g.n_regions * n_images, stream);
+  if (!counts_cleared)
+    cudaMemsetAsync(b.raw_count + (size_t)first_image * g.n_regions, 0, sizeof(int32_t) * g.n_regions * n_images, stream);
   dim3 grid((g.cols + TW - 1) / TW, (g.rows + TH - 1) / TH, n_images * g.n_regions);
   fast_nms_kernel<<<grid, 256, 0, stream>>>(image_map, g, rt, first_image,
                                             b.mask + (size_t)first_image * g.rows * g.mask_words,
@@ -633,13 +658,26 @@ void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, con
 
 void launch_compact(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream) {
   const int total = (g.mask_words >> 2) * g.rows;
-  const int Q = (total + kCompactFrameThreads - 1) / kCompactFrameThreads;
-  if (n_images <= 16 && Q <= kCompactFrameMaxQ) {   // single frames: one wide CTA per image (latency)
-    compact_frame_kernel<<<n_images, kCompactFrameThreads, 0, stream>>>(
-        g, b.mask + (size_t)first_image * g.rows * g.mask_words, b.row_ptr + (size_t)first_image * (g.rows + 1),
-        b.kp_xy + (size_t)first_image * g.cap, b.n_desc + first_image, b.error_flag,
-        b.pruned_l + (size_t)(first_image >> 1) * g.cap, b.consumed_r + (size_t)(first_image >> 1) * g.cap, Q);
-    return;
+  const int cluster_threads = kCompactFrameThreads * kCompactFrameBlocks;
+  const int Q = (total + cluster_threads - 1) / cluster_threads;
+  if (n_images <= 16 && Q <= kCompactFrameMaxQ) {   // single frames: one cluster of 8 CTAs per image (latency)
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr;
+    cfg.gridDim = dim3(n_images * kCompactFrameBlocks);
+    cfg.blockDim = dim3(kCompactFrameThreads);
+    cfg.stream = stream;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = kCompactFrameBlocks;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, compact_frame_kernel, g, (const uint32_t*)(b.mask + (size_t)first_image * g.rows * g.mask_words),
+                           b.row_ptr + (size_t)first_image * (g.rows + 1), b.kp_xy + (size_t)first_image * g.cap,
+                           b.n_desc + first_image, b.error_flag, b.pruned_l + (size_t)(first_image >> 1) * g.cap,
+                           b.consumed_r + (size_t)(first_image >> 1) * g.cap, Q) == cudaSuccess)
+      return;
+    cudaGetLastError();   // no cluster launch on this device: the strip kernel below
   }
   const int strips = n_images <= 16 ? 8 : 1;   // single frames: split each image over 8 CTAs (latency)
   const size_t smem = sizeof(int) * ((g.rows + strips - 1) / strips + 2);

@@ -84,6 +84,7 @@ struct vslam_fpg {
   int32_t* h_flag = nullptr;
   int32_t* d_status = nullptr;   // [error_flag, pad | n_desc 2B | raw_count 2B x regions]; b.error_flag / n_desc / raw_count point into it
   int32_t* h_status = nullptr;   // pinned mirror; h_flag / h_n_desc / h_counts point into it
+  int32_t* h_status_device = nullptr;   // the same words as the device addresses them (written by the fused frame)
   // state of the last single-pair initialize / last batch
   bool initialized = false;
   int last_pairs = 0;
@@ -117,6 +118,12 @@ struct vslam_fpg {
   int64_t k_n[kNumKernels] = {};
   cudaEvent_t fork_ev = nullptr;
   cudaEvent_t join_ev[kLanes] = {};
+  // single frames leave most of the 148 SMs idle: kernels that do not depend on each other (blur beside FAST + compact;
+  // the epipolar match beside the aligner; the tracks' share of points() beside the bin selection) run on a side stream,
+  // i.e. as parallel branches of the captured frame graph
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t branch_ev[4] = {};
+  bool branches = true;                        // VSLAM_NO_FRAME_BRANCHES=1: one chain (A/B measurements)
   // batched StereoUV linearize over the pairs' own framepoints
   double* d_systems = nullptr;        // [max_batch][32]
   double* d_pair_errors = nullptr;    // [max_batch][out_cap]
@@ -195,8 +202,20 @@ inline void mark(vslam_fpg* h, Lane& lane, int ev) {
   else cudaEventRecord(h->clock.ev[ev], lane.stream);
 }
 
+// `to` continues after everything issued on `from` so far (inside a stream capture: an edge of the graph)
+inline void order_after(vslam_fpg* h, cudaStream_t from, cudaStream_t to, int ev) {
+  cudaEventRecord(h->branch_ev[ev], from);
+  cudaStreamWaitEvent(to, h->branch_ev[ev], 0);
+}
+
+// single frames on lane 0 without the timing events (they bracket the kernels of ONE chain)
+inline bool use_branches(const vslam_fpg* h, const Lane& lane, int n) {
+  return h->branches && n == 1 && !h->profiling && &lane == &h->lanes[0];
+}
+
 // kernels of initialize() for images [2*p0, 2*(p0+n)) on one lane
-void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n, const int32_t* device_thresholds = nullptr) {
+void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n, const int32_t* device_thresholds = nullptr,
+                         bool counts_cleared = false) {
   Buffers b = h->b;
   // lane-local scratch is indexed from image 0 of the chunk: shift the base so that image index 2*p0 lands on it
   b.blurred = lane.blurred - (size_t)2 * p0 * h->g.rows * h->g.pitch;
@@ -204,12 +223,20 @@ void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n, const int32_t*
   RegionTable rt;
   refresh_region_table(h, &rt);
   // (the pruned / consumed flags of the new frame are cleared by compact_kernel)
+  const bool blur_beside_fast = use_branches(h, lane, n) && !h->d_brief_tests;
+  if (blur_beside_fast) {   // the blur reads the image only: it does not wait for FAST + compact
+    order_after(h, lane.stream, h->side_stream, 0);
+    launch_blur(h->g, b, h->blur_map, 2 * p0, 2, h->side_stream);
+  }
   mark(h, lane, kEvFast0);
-  launch_fast(h->g, rt, b, h->image_map, 2 * p0, 2 * n, lane.stream, device_thresholds);
+  launch_fast(h->g, rt, b, h->image_map, 2 * p0, 2 * n, lane.stream, device_thresholds, counts_cleared);
   mark(h, lane, kEvFast1);
   launch_compact(h->g, b, 2 * p0, 2 * n, lane.stream);
   mark(h, lane, kEvCompact1);
-  if (h->d_brief_tests) {   // BRIEF-32: 9x9 box sums (u16) take the place of the blurred image
+  if (blur_beside_fast) {
+    order_after(h, h->side_stream, lane.stream, 0);
+    launch_describe(h->g, b, lane.blurred_map, 2 * p0, 2, lane.stream, 0);
+  } else if (h->d_brief_tests) {   // BRIEF-32: 9x9 box sums (u16) take the place of the blurred image
     uint16_t* boxsum = reinterpret_cast<uint16_t*>(lane.blurred);
     launch_box9(h->g, h->b.image + (size_t)2 * p0 * h->g.rows * h->g.pitch, boxsum, 2 * n, lane.stream);
     mark(h, lane, kEvBlur1);
@@ -664,6 +691,10 @@ int vslam_fpg_create(const vslam_fpg_config* c, int device, vslam_fpg** out) {
   if (ok && cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming) != cudaSuccess) ok = false;
   for (auto& e : h->join_ev)
     if (ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) ok = false;
+  if (ok && cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking) != cudaSuccess) ok = false;
+  for (auto& e : h->branch_ev)
+    if (ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) ok = false;
+  h->branches = std::getenv("VSLAM_NO_FRAME_BRANCHES") == nullptr;
   if (ok && cudaMemset(b.error_flag, 0, sizeof(int32_t)) != cudaSuccess) ok = false;
   if (ok && cudaMemset(b.image, 0, I * img_bytes) != cudaSuccess) ok = false;   // row padding is never uninitialised
   if (!ok) {
@@ -714,6 +745,9 @@ int vslam_fpg_destroy(vslam_fpg* h) {
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
   for (auto& e : h->join_ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : h->branch_ev)
+    if (e) cudaEventDestroy(e);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   delete h;
   return VSLAM_OK;
 }
@@ -797,9 +831,10 @@ int vslam_fpg_initialize(vslam_fpg* h, const uint8_t* left, const uint8_t* right
       if (ok) {
         h->capturing = true;
         cudaMemcpyAsync(h->d_thr, h->h_thr, sizeof(int32_t) * g.n_regions, cudaMemcpyHostToDevice, lane.stream);
-        launch_repitch(g, lane.stage, lane.stage + lane.stage_bytes, (int)stride, h->b.image, 1, lane.stream);
+        launch_repitch(g, lane.stage, lane.stage + lane.stage_bytes, (int)stride, h->b.image, 1, lane.stream,
+                       h->b.raw_count, 2 * g.n_regions);
         ++h->launches;
-        run_detect_describe(h, lane, 0, 1, h->d_thr);
+        run_detect_describe(h, lane, 0, 1, h->d_thr, true);
         status_download(h, lane);
         h->capturing = false;
         ok = cudaStreamEndCapture(lane.stream, &graph) == cudaSuccess && graph != nullptr;
@@ -1105,6 +1140,7 @@ static int setup_frame_step(vslam_fpg* h) {
   std::memset(h->h_step, 0, off);
   CUDA_TRY(cudaHostGetDevicePointer((void**)&h->h_step_device, h->h_step, 0));
   CUDA_TRY(cudaMallocHost((void**)&h->h_step_T, sizeof(double) * 12));
+  CUDA_TRY(cudaHostGetDevicePointer((void**)&h->h_status_device, h->h_status, 0));
   h->step_cluster_blocks = blocks;
   h->step_cap = cap;
   return VSLAM_OK;
@@ -1147,17 +1183,29 @@ static FrameStepBuffers frame_step_buffers(vslam_fpg* h) {
   f.h_lost = reinterpret_cast<int32_t*>(d + h->step_off_lost);
   f.h_points = reinterpret_cast<FramePointRecord*>(d + h->step_off_points);
   f.h_frame_points = reinterpret_cast<PreviousPoint*>(d + h->step_off_frame_points);
+  f.d_status = h->d_status;
+  f.d_raw_count = h->b.raw_count;
+  f.h_status = h->h_status_device;
+  f.h_counts = h->h_status_device + (h->h_counts - h->h_status);
+  f.n_regions = h->g.n_regions;
   return f;
 }
 
 // the device side of one tracked frame on lane 0's stream (captured once per frame status, or issued directly)
 static int issue_frame_step(vslam_fpg* h, Lane& lane, size_t stride, const vslam_frame_step_parameters& p) {
   const Geometry& g = h->g;
-  CUDA_TRY(cudaMemcpyAsync(h->d_thr, h->h_thr, sizeof(int32_t) * g.n_regions, cudaMemcpyHostToDevice, lane.stream));
-  CUDA_TRY(cudaMemcpyAsync(h->d_step, h->h_step_T, sizeof(double) * 12, cudaMemcpyHostToDevice, lane.stream));
-  launch_repitch(g, lane.stage, lane.stage + lane.stage_bytes, (int)stride, h->b.image, 1, lane.stream);
-  ++h->launches;
-  run_detect_describe(h, lane, 0, 1, h->d_thr);                                  // pose_tracker_3d.cpp:80
+  {   // the thresholds and the motion prior travel beside the repitch (FAST is the first kernel that reads either)
+    const bool beside = use_branches(h, lane, 1);
+    cudaStream_t s = beside ? h->side_stream : lane.stream;
+    if (beside) order_after(h, lane.stream, s, 0);
+    CUDA_TRY(cudaMemcpyAsync(h->d_thr, h->h_thr, sizeof(int32_t) * g.n_regions, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->d_step, h->h_step_T, sizeof(double) * 12, cudaMemcpyHostToDevice, s));
+    launch_repitch(g, lane.stage, lane.stage + lane.stage_bytes, (int)stride, h->b.image, 1, lane.stream,
+                   h->b.raw_count, 2 * g.n_regions);
+    ++h->launches;
+    if (beside) order_after(h, s, lane.stream, 0);
+  }
+  run_detect_describe(h, lane, 0, 1, h->d_thr, true);                            // pose_tracker_3d.cpp:80
   const FrameStepBuffers f = frame_step_buffers(h);
   FrameStepParams fp;
   fp.max_reliable_depth = p.maximum_reliable_depth_meters;
@@ -1174,6 +1222,20 @@ static int issue_frame_step(vslam_fpg* h, Lane& lane, size_t stride, const vslam
   launch_track(g, h->sp, h->b, 0, h->d_previous, h->step_cap, tp, h->track_scratch, h->d_tracks, h->d_lost, h->d_tracked,
                lane.stream, h->d_step);                                          // :239
   mark(h, lane, kEvTrack1);
+  // After track() the frame splits into two chains that meet at the bin selection: the aligner (fill -> converge ->
+  // prune) and the epipolar match of the features track() left over (:210; it reads neither the tracks nor the pose).
+  // The tracks' share of points() needs the prune only and runs beside the selection.
+  const bool branches = use_branches(h, lane, 1);
+  cudaStream_t side = branches ? h->side_stream : lane.stream;
+  if (branches) order_after(h, lane.stream, side, 1);
+  auto match_passes = [&](cudaStream_t s) {
+    for (int pass = 0; pass < h->n_passes; ++pass) {                             // :210
+      const int offset = pass == 0 ? 0 : ((pass & 1) ? (pass + 1) / 2 : -(pass / 2));
+      launch_match(g, h->sp, h->b, 0, 1, pass, offset, s);
+      ++h->launches;
+    }
+  };
+  if (branches) match_passes(side);
   launch_frame_aligner_fill(f, fp, lane.stream);                                 // :124-126 / :355-356
   AlignerCamera cam;
   const double K[9] = {h->sp.fx, 0, h->sp.cx, 0, h->sp.fy, h->sp.cy, 0, 0, 1};
@@ -1190,19 +1252,26 @@ static int issue_frame_step(vslam_fpg* h, Lane& lane, size_t stride, const vslam
   CUDA_TRY(launch_converge_frame(f.aligner, cam, gp, h->d_step_ctl, h->track_scratch.stats, h->step_cluster_blocks,
                                  lane.stream));                                  // :357
   launch_frame_prune(f, fp, lane.stream);                                        // :437-472
-  mark(h, lane, kEvMatch0);
-  for (int pass = 0; pass < h->n_passes; ++pass) {                               // :210
-    const int offset = pass == 0 ? 0 : ((pass & 1) ? (pass + 1) / 2 : -(pass / 2));
-    launch_match(g, h->sp, h->b, 0, 1, pass, offset, lane.stream);
-    ++h->launches;
+  if (branches) {
+    order_after(h, side, lane.stream, 2);      // the selection needs the matches ...
+    order_after(h, lane.stream, side, 3);      // ... and the tracks' share of points() the prune
+    launch_frame_assemble(g, f, fp, kAssembleTracks, side);
   }
+  mark(h, lane, kEvMatch0);
+  if (!branches) match_passes(lane.stream);
   mark(h, lane, kEvMatch1);
   launch_select(g, h->sp, h->b, 0, 1, h->n_passes, h->d_tracked, 0, h->d_out, h->out_cap, false, lane.stream,
                 &h->d_step->n_kept);
   mark(h, lane, kEvSelect1);
-  launch_frame_assemble(g, f, fp, lane.stream);
+  if (branches) {
+    order_after(h, side, lane.stream, 1);
+    launch_frame_assemble(g, f, fp, kAssembleRest, lane.stream);
+    ++h->launches;
+  } else {
+    launch_frame_assemble(g, f, fp, kAssembleAll, lane.stream);
+  }
   h->launches += 2 + 4 + 1;   // track (2), fill / converge / prune / assemble, select
-  return status_download(h, lane);
+  return VSLAM_OK;                // (the detection status reaches the host through frame_assemble_kernel's last block)
 }
 
 int32_t vslam_fpg_frame_step_capacity(vslam_fpg* h) {

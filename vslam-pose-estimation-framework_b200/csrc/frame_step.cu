@@ -124,14 +124,18 @@ __device__ __forceinline__ void copy16(void* dst, const void* src, size_t bytes,
 constexpr int kAssembleThreads = 256;
 constexpr int kAssemblePoints = 64;   // points() entries per block: 8 KB of shared memory, written out in 512-byte rows
 
-__global__ void __launch_bounds__(kAssembleThreads) frame_assemble_kernel(Geometry g, FrameStepBuffers f, FrameStepParams p) {
+// `part` (kAssembleAll / kAssembleTracks / kAssembleRest) selects the blocks of this launch: the tracks' blocks need the
+// prune only and may run beside the bin selection; they do not read its counts (a frame that overflows is discarded by
+// the host together with the device-resident points, so what they wrote then is never used).
+__global__ void __launch_bounds__(kAssembleThreads) frame_assemble_kernel(Geometry g, FrameStepBuffers f, FrameStepParams p,
+                                                                         int part) {
   __shared__ __align__(16) PreviousPoint s_points[kAssemblePoints];
   __shared__ __align__(16) TrackRecord s_tracks[kAssemblePoints];
   __shared__ int s_pos[kAssemblePoints];
   const int tid = threadIdx.x;
   const int n_tracks = min(f.stats[0], f.cap);
   const int n_kept = f.state->n_kept;
-  const int n_new = min(f.n_out[0], f.out_cap);
+  const int n_new = part == kAssembleTracks ? 0 : min(f.n_out[0], f.out_cap);
   const bool overflow = f.state->overflow != 0 || n_kept + n_new > f.cap;
   const int n_points = overflow ? 0 : n_kept + n_new;
   const uint8_t* desc_l = f.desc;
@@ -153,10 +157,11 @@ __global__ void __launch_bounds__(kAssembleThreads) frame_assemble_kernel(Geomet
     q->reserved = length;          // trackLength()
   };
 
-  if ((int)blockIdx.x < track_blocks) {
+  const int block = part == kAssembleRest ? (int)blockIdx.x + track_blocks : (int)blockIdx.x;
+  if (block < track_blocks) {
     // ---- tracks [k0, k0 + 64) of track(): the survivors go to their ordered position among points() and the host's tracks.
     // A block's survivors are consecutive positions (the order is kept), so both outputs are contiguous ranges.
-    const int k0 = blockIdx.x * kAssemblePoints;
+    const int k0 = block * kAssemblePoints;
     if (k0 >= n_tracks) return;
     if (tid < kAssemblePoints) {
       const int k = k0 + tid;
@@ -196,7 +201,7 @@ __global__ void __launch_bounds__(kAssembleThreads) frame_assemble_kernel(Geomet
     }
     return;
   }
-  const int nb = blockIdx.x - track_blocks;
+  const int nb = block - track_blocks;
   if (nb < new_blocks) {
     // ---- new framepoints [k0, k0 + 64) of compute(): behind the surviving tracks
     const int k0 = nb * kAssemblePoints;
@@ -222,6 +227,8 @@ __global__ void __launch_bounds__(kAssembleThreads) frame_assemble_kernel(Geomet
   const int n_lost = min(f.stats[1], f.cap);
   for (int i = tid; i < n_lost; i += kAssembleThreads) f.h_lost[i] = f.lost[i];
   if (tid < 4) f.h_header->stats[tid] = f.stats[tid];
+  if (tid < 4) f.h_status[tid] = f.d_status[tid];
+  for (int i = tid; i < 2 * f.n_regions; i += kAssembleThreads) f.h_counts[i] = f.d_raw_count[i];
   if (tid < 2) f.h_header->n_out[tid] = f.n_out[tid];
   if (tid < 32) f.h_header->system[tid] = f.aligner.system[tid];
   {
@@ -250,9 +257,12 @@ void launch_frame_prune(const FrameStepBuffers& f, const FrameStepParams& p, cud
   frame_prune_kernel<<<1, kPruneThreads, 0, stream>>>(f, p);
 }
 
-void launch_frame_assemble(const Geometry& g, const FrameStepBuffers& f, const FrameStepParams& p, cudaStream_t stream) {
-  const int blocks = (f.cap + kAssemblePoints - 1) / kAssemblePoints + (f.out_cap + kAssemblePoints - 1) / kAssemblePoints + 1;
-  frame_assemble_kernel<<<blocks, kAssembleThreads, 0, stream>>>(g, f, p);
+void launch_frame_assemble(const Geometry& g, const FrameStepBuffers& f, const FrameStepParams& p, int part,
+                           cudaStream_t stream) {
+  const int track_blocks = (f.cap + kAssemblePoints - 1) / kAssemblePoints;
+  const int rest_blocks = (f.out_cap + kAssemblePoints - 1) / kAssemblePoints + 1;
+  const int blocks = part == kAssembleTracks ? track_blocks : (part == kAssembleRest ? rest_blocks : track_blocks + rest_blocks);
+  frame_assemble_kernel<<<blocks, kAssembleThreads, 0, stream>>>(g, f, p, part);
 }
 
 }  // namespace vslam

@@ -91,14 +91,16 @@ struct RecoverParams {
 
 // all launches are asynchronous on `stream`; image ranges are [first_image, first_image + n_images)
 // dense host-layout images (row stride `stride` bytes, any alignment) -> pitched device images [pair][side][row][pitch]
+// clear (optional): n_clear i32 zeroed by the kernel (the raw FAST counters of a single frame)
 void launch_repitch(const Geometry& g, const uint8_t* left, const uint8_t* right, int stride, uint8_t* image,
-                    int n_pairs, cudaStream_t stream);
+                    int n_pairs, cudaStream_t stream, int32_t* clear = nullptr, int n_clear = 0);
 // `image_map`: TMA descriptor of b.image (all images of the handle) with the FAST tile as box
 bool make_fast_tensor_map(const Geometry& g, const uint8_t* images, int n_images, CUtensorMap* out);
 bool make_image_tensor_map(const Geometry& g, const uint8_t* images, int n_images, int box_w, int box_h, CUtensorMap* out);
 // device_thresholds (optional): [n_regions] i32 in device memory, read instead of rt.threshold
 void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, const CUtensorMap& image_map, int first_image,
-                 int n_images, cudaStream_t stream, const int32_t* device_thresholds = nullptr);
+                 int n_images, cudaStream_t stream, const int32_t* device_thresholds = nullptr,
+                 bool counts_cleared = false);
 void launch_compact(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream);
 // layout of the packed features of pair 0 (pack_features_kernel): per side [n] u32 | [n] u8 padded to 16 | [n][32]
 __host__ __device__ inline size_t feature_pack_desc_offset(int n) { return (5 * (size_t)n + 15) / 16 * 16; }
@@ -248,6 +250,13 @@ struct FrameStepBuffers {
   int32_t* h_lost;                  // [cap]
   FramePointRecord* h_points;       // [out_cap]
   PreviousPoint* h_frame_points;    // [cap] points() of this frame (the next frame's previous points)
+  // detection status of the frame ({error flag, pad, n_desc[2]} and the raw FAST counts per region), mirrored into the
+  // handle's pinned status words by the last block of frame_assemble_kernel (no copy node at the end of the graph)
+  const int32_t* d_status;          // [4]
+  const int32_t* d_raw_count;       // [2 * n_regions]
+  int32_t* h_status;                // pinned, device-visible
+  int32_t* h_counts;                // pinned, device-visible
+  int n_regions;
 };
 struct FrameStepParams {
   double max_reliable_depth;        // _maximum_reliable_depth_meters of the aligner (slam_assembly.cpp:70)
@@ -260,7 +269,9 @@ struct FrameStepParams {
 // control block of converge(); then, after the cluster kernel: _prunePoints; after select: points() of the frame
 void launch_frame_aligner_fill(const FrameStepBuffers& f, const FrameStepParams& p, cudaStream_t stream);
 void launch_frame_prune(const FrameStepBuffers& f, const FrameStepParams& p, cudaStream_t stream);
-void launch_frame_assemble(const Geometry& g, const FrameStepBuffers& f, const FrameStepParams& p, cudaStream_t stream);
+enum { kAssembleAll = 0, kAssembleTracks = 1, kAssembleRest = 2 };   // blocks of one frame_assemble launch
+void launch_frame_assemble(const Geometry& g, const FrameStepBuffers& f, const FrameStepParams& p, int part,
+                           cudaStream_t stream);
 
 // device-resident landmark map (vslam_landmark_map): per landmark a chain of 32-measurement blocks, its world
 // coordinates and update count; per frame slot the two poses every measurement of that frame is evaluated with

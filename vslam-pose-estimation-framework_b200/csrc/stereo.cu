@@ -283,8 +283,12 @@ __device__ __forceinline__ int bin_of(int v, int bin) {
 // as float (exact: disparities are differences of integer pixel columns / float-valued inputs, distances Hamming
 // counts; the API routes anything else to the generic kernel); distance -1 marks "occupied by a point with
 // previous()": `dist_new <= dist_cur` (:385-386) can then never hold, which is the !current->previous() test (:383).
-constexpr int kSelectWarps = 16;
-
+// Replay: the rule is sequential PER BIN only, so the matched features of a chunk of 32 are grouped by bin
+// (__match_any_sync) and step j applies the j-th feature of every group at once -- the groups touch different bins, and
+// within a group the lane order is the emission order.  Keypoints that are neighbours in (row, col) order rarely share
+// a bin, so a chunk takes 1-3 steps instead of one per matched feature.
+// kSelectWarps: 16 for batches (one CTA per pair, several CTAs per SM), 32 for a single frame.
+template <int kSelectWarps>
 __global__ void __launch_bounds__(kSelectWarps * 32) select_strips_kernel(
     Geometry g, StereoParams sp, const int32_t* __restrict__ row_ptr, const uint32_t* __restrict__ kp_xy,
     const int32_t* __restrict__ n_desc, const int2* __restrict__ match, int n_passes,
@@ -385,20 +389,23 @@ __global__ void __launch_bounds__(kSelectWarps * 32) select_strips_kernel(
             const int cb = bin_of(col, bs);
             const float disp = (float)(col - (int)(qr[u] & 0xffffu));   // frame_point.cpp:19
             const float dist = (float)(mm[u].y & 0xffff);
-            unsigned todo = __ballot_sync(0xffffffffu, cand);
+            const unsigned todo = __ballot_sync(0xffffffffu, cand);
             my_matches += __popc(todo);   // cand holds this pass only: the passes sum to every match once
-            while (todo) {                       // replay in emission order (ascending i)
-              const int l = __ffs(todo) - 1;
-              todo &= todo - 1;
-              const int b = __shfl_sync(0xffffffffu, cb, l);
-              const float dp = __shfl_sync(0xffffffffu, disp, l), dt = __shfl_sync(0xffffffffu, dist, l);
-              if (lane == (b & 31)) {            // the owner of bin column b
-                const int cur = win[b];
-                if (cur == INT32_MIN || (dp > wdisp[b] && dt <= wdist[b])) {   // :390-393 / :378-389
-                  win[b] = f0 + l;
-                  wdisp[b] = dp;
-                  wdist[b] = dt;
+            if (todo) {                   // (uniform)
+              // lanes without a match get a key of their own: negative, no bin is
+              const unsigned group = __match_any_sync(0xffffffffu, cand ? cb : -1 - lane);
+              const int rank = __popc(group & ((1u << lane) - 1u));      // position among the bin's features, in order
+              const int steps = __reduce_max_sync(0xffffffffu, cand ? __popc(group) : 0);
+              for (int j = 0; j < steps; ++j) {
+                if (cand && rank == j) {
+                  const int cur = win[cb];
+                  if (cur == INT32_MIN || (disp > wdisp[cb] && dist <= wdist[cb])) {   // :390-393 / :378-389
+                    win[cb] = f0 + lane;
+                    wdisp[cb] = disp;
+                    wdist[cb] = dist;
+                  }
                 }
+                __syncwarp();
               }
             }
             __syncwarp();
@@ -542,8 +549,10 @@ void launch_select(const Geometry& g, const StereoParams& sp, const Buffers& b, 
   if (!generic && smem <= 160 * 1024) {
     // opt in to > 48 KB dynamic shared memory; the attribute is per device, so it is simply set whenever it is needed
     if (smem > 48 * 1024)
-      cudaFuncSetAttribute(select_strips_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    select_strips_kernel<<<n_pairs, kSelectWarps * 32, smem, stream>>>(
+      cudaFuncSetAttribute(n_pairs == 1 ? select_strips_kernel<32> : select_strips_kernel<16>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kernel = n_pairs == 1 ? select_strips_kernel<32> : select_strips_kernel<16>;
+    kernel<<<n_pairs, (n_pairs == 1 ? 32 : 16) * 32, smem, stream>>>(
         g, sp, b.row_ptr + (size_t)2 * first_pair * (g.rows + 1), b.kp_xy + (size_t)2 * first_pair * g.cap,
         b.n_desc + 2 * first_pair, b.match + (size_t)first_pair * g.cap, n_passes, tracked, n_tracked,
         out + (size_t)first_pair * out_capacity_per_pair, out_capacity_per_pair, b.n_out + 2 * first_pair, b.error_flag,

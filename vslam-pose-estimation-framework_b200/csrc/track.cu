@@ -25,6 +25,8 @@
 //
 // The lattice of the reference is replaced by the (row, col)-sorted feature arrays + CSR row pointers: a window's rows
 // are one contiguous index range, scanned in the reference's row-major order (ties resolve to the lowest index).
+#include <algorithm>
+
 #include "kernels.cuh"
 #include "stereo_device.cuh"
 
@@ -59,6 +61,16 @@ struct Projection {
   float right_x, right_y;
 };
 
+// The claims and the tentative results of track_resolve_kernel live in shared memory when they fit and in global memory
+// otherwise; both are written by other threads between two barriers (atomics at the L2 / plain stores), so every read
+// goes to the memory itself: volatile loads through the generic address (global: past the L1; shared: as they are).
+__device__ __forceinline__ int32_t load_claim(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
+__device__ __forceinline__ int4 load_result(const int4* p) {
+  int4 r;
+  asm volatile("ld.volatile.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
 // intensity_feature_matcher.cpp:81-148, warp-cooperative.  Returns the sorted index of the chosen feature or -1;
 // *distance = descriptor_distance_best_ of the chosen feature.
 __device__ int search_region(const int32_t* __restrict__ row_ptr, const uint32_t* __restrict__ xy,
@@ -74,7 +86,7 @@ __device__ int search_region(const int32_t* __restrict__ row_ptr, const uint32_t
     const uint32_t q = xy[f];
     const int col = (int)(q & 0xffffu);
     if (col < col_start || col >= col_end) continue;
-    if (claim ? __ldcg(claim + f) < self : gone[f] != 0) continue;  // feature_lattice[row][col] == nullptr
+    if (claim ? load_claim(claim + f) < self : gone[f] != 0) continue;  // feature_lattice[row][col] == nullptr
     const int d = popc256(q0, q1, desc[2 * f], desc[2 * f + 1]);
     if (!((double)d < maximum_distance)) continue;                   // :103 / :121 (strict, against the double limit)
     unsigned key;
@@ -236,13 +248,16 @@ __device__ __forceinline__ int block_scan_flag(bool flag, int* s_red, int* total
   return warp_offset + __popc(bal & ((1u << lane) - 1u));
 }
 
-// K10
+// K10.  Dynamic shared memory (layout chosen by launch_track, 0 = the global scratch is used): the two claim arrays
+// [2][smem_claims] and the tentative results + the worklist of the dirty points [smem_points] -- a round then runs out
+// of shared memory instead of paying an L2 round trip per phase (reset, atomicMin, dirty test, recompute).
 __global__ void __launch_bounds__(kResolveThreads) track_resolve_kernel(
     Geometry g, StereoParams sp, TrackParams tp, const int32_t* row_ptr, const uint32_t* kp_xy, const uint8_t* desc,
     const int32_t* n_desc, uint8_t* gone_l, uint8_t* gone_r, const PreviousPoint* __restrict__ previous,
     int n_previous, int4* tentative, int32_t* claim_l, int32_t* claim_r, TrackRecord* __restrict__ tracks,
     int32_t* __restrict__ lost, TrackedPoint* __restrict__ tracked, int32_t* __restrict__ stats,
-    const FrameStepState* __restrict__ step) {
+    const FrameStepState* __restrict__ step, int smem_claims, int smem_points) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ int s_red[32];
   __shared__ int s_acc[2];
   const int tid = threadIdx.x;
@@ -255,10 +270,20 @@ __global__ void __launch_bounds__(kResolveThreads) track_resolve_kernel(
   const int n_l = n_desc[0], n_r = n_desc[1];
 
   __shared__ int s_count, s_changed;
+  int32_t* worklist = lost;          // scratch until the ordered output below fills it
+  if (smem_claims) {
+    claim_l = reinterpret_cast<int32_t*>(s_dyn);
+    claim_r = claim_l + smem_claims;
+  }
+  if (smem_points) {                 // (n_previous <= smem_points: launch_track)
+    int4* s_tentative = reinterpret_cast<int4*>(s_dyn + sizeof(int32_t) * 2 * (size_t)smem_claims);
+    for (int u = tid; u < n_previous; u += kResolveThreads) s_tentative[u] = tentative[u];
+    tentative = s_tentative;
+    worklist = reinterpret_cast<int32_t*>(s_tentative + smem_points);
+  }
   TrackView vc = v;   // the lattice as point `self` sees it: claims of lower points
   vc.claim_l = claim_l;
   vc.claim_r = claim_r;
-  int32_t* worklist = lost;          // scratch until the ordered output below fills it
   uint8_t* ever_dirty = reinterpret_cast<uint8_t*>(tracked);   // [n_previous] bytes of the (later written) pre-load array
   for (int u = tid; u < n_previous; u += kResolveThreads) ever_dirty[u] = 0;
   if (tid < 2) s_acc[tid] = 0;
@@ -270,7 +295,7 @@ __global__ void __launch_bounds__(kResolveThreads) track_resolve_kernel(
     if (tid == 0) s_count = 0, s_changed = 0;
     __syncthreads();
     for (int u = tid; u < n_previous; u += kResolveThreads) {
-      const int4 t = __ldcg(tentative + u);
+      const int4 t = load_result(tentative + u);
       if (t.w != kStatusTracked) continue;
       atomicMin(&claim_l[t.x], u);
       for_each_consumed_right(v, t.x, t.y, [&](int s) { atomicMin(&claim_r[s], u); });
@@ -278,9 +303,9 @@ __global__ void __launch_bounds__(kResolveThreads) track_resolve_kernel(
     __syncthreads();
     // points whose result depends on a feature a lower point removes join the set that is recomputed every round
     for (int u = tid; u < n_previous; u += kResolveThreads) {
-      const int4 t = __ldcg(tentative + u);
+      const int4 t = load_result(tentative + u);
       bool d = ever_dirty[u] != 0;
-      if (!d && ((t.x >= 0 && __ldcg(claim_l + t.x) < u) || (t.y >= 0 && __ldcg(claim_r + t.y) < u))) {
+      if (!d && ((t.x >= 0 && load_claim(claim_l + t.x) < u) || (t.y >= 0 && load_claim(claim_r + t.y) < u))) {
         d = true;
         ever_dirty[u] = 1;
         s_changed = 1;
@@ -291,12 +316,12 @@ __global__ void __launch_bounds__(kResolveThreads) track_resolve_kernel(
     const int n_work = s_count;
     if (n_work == 0) break;
     for (int k = tid >> 5; k < n_work; k += kResolveThreads / 32) {
-      const int u = __ldcg(worklist + k);
+      const int u = *reinterpret_cast<volatile int32_t*>(worklist + k);
       vc.self = u;
       Projection proj;
       const int4 t = track_point(vc, tp, previous + u, &proj);
       if ((tid & 31) == 0) {
-        const int4 old = __ldcg(tentative + u);
+        const int4 old = load_result(tentative + u);
         if (old.x != t.x || old.y != t.y || old.z != t.z || old.w != t.w) {
           tentative[u] = t;
           s_changed = 1;
@@ -308,8 +333,8 @@ __global__ void __launch_bounds__(kResolveThreads) track_resolve_kernel(
     __syncthreads();
   }
   // the claims of the final results == matched_indices_left / _right of :646-651 (+ the parallax ranges :611-620)
-  for (int i = tid; i < n_l; i += kResolveThreads) gone_l[i] = claim_l[i] != INT32_MAX;
-  for (int i = tid; i < n_r; i += kResolveThreads) gone_r[i] = claim_r[i] != INT32_MAX;
+  for (int i = tid; i < n_l; i += kResolveThreads) gone_l[i] = load_claim(claim_l + i) != INT32_MAX;
+  for (int i = tid; i < n_r; i += kResolveThreads) gone_r[i] = load_claim(claim_r + i) != INT32_MAX;
   __syncthreads();
 
   // ordered output: tracks (:623-643), lost points (:660-663), the tracked points as compute() pre-loads them (:147-155)
@@ -317,7 +342,7 @@ __global__ void __launch_bounds__(kResolveThreads) track_resolve_kernel(
   for (int u0 = 0; u0 < n_previous; u0 += kResolveThreads) {
     const int u = u0 + tid;
     int4 t = make_int4(-1, -1, 0, kStatusSkipped);
-    if (u < n_previous) t = __ldcg(tentative + u);
+    if (u < n_previous) t = load_result(tentative + u);
     int total_t, total_l;
     const int pos_t = n_tracks + block_scan_flag(t.w == kStatusTracked, s_red, &total_t);
     const int pos_l = n_lost + block_scan_flag(t.w == kStatusLost, s_red, &total_l);
@@ -491,9 +516,33 @@ void launch_track(const Geometry& g, const StereoParams& sp, const Buffers& b, i
   if (n_previous > 0)
     track_search_kernel<<<(n_previous + 7) / 8, 256, 0, stream>>>(g, sp, tp, row_ptr, kp_xy, desc, n_desc, gone_l, gone_r,
                                                                   previous, n_previous, s.tentative, step);
-  track_resolve_kernel<<<1, kResolveThreads, 0, stream>>>(g, sp, tp, row_ptr, kp_xy, desc, n_desc, gone_l, gone_r,
-                                                          previous, n_previous, s.tentative, s.claim_l, s.claim_r, tracks,
-                                                          lost, tracked, s.stats, step);
+  // claims, tentative results and worklist in shared memory as far as they fit (claims first)
+  static const int smem_limit = [] {
+    int device = 0, optin = 0;
+    cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    const int limit = std::max(0, optin - 1024);   // (the kernel's static shared memory)
+    if (cudaFuncSetAttribute(track_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, limit) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    return limit;
+  }();
+  size_t smem = 0;
+  int smem_claims = 0, smem_points = 0;
+  if (sizeof(int32_t) * 2 * (size_t)g.cap <= (size_t)smem_limit) {
+    smem_claims = g.cap;
+    smem = sizeof(int32_t) * 2 * (size_t)g.cap;
+    const size_t points = (sizeof(int4) + sizeof(int32_t)) * (size_t)n_previous;
+    if (n_previous > 0 && smem + points <= (size_t)smem_limit) {
+      smem_points = n_previous;
+      smem += points;
+    }
+  }
+  track_resolve_kernel<<<1, kResolveThreads, smem, stream>>>(g, sp, tp, row_ptr, kp_xy, desc, n_desc, gone_l, gone_r,
+                                                             previous, n_previous, s.tentative, s.claim_l, s.claim_r,
+                                                             tracks, lost, tracked, s.stats, step, smem_claims,
+                                                             smem_points);
 }
 
 void launch_recover(const Geometry& g, const StereoParams& sp, const Buffers& b, int pair, const uint8_t* blurred,
