@@ -242,128 +242,148 @@ __global__ void __launch_bounds__(kThreads) linearize_kernel(int n, AlignerBuffe
   }
 }
 
-// solve6 of gn_math.h (Eigen::FullPivLU<Matrix6>::solve) with the 6 x 7 augmented matrix in REGISTERS, bit-identical to
-// the single-thread form.  That form indexes its arrays with the run-time pivot position, i.e. lives in local memory
-// (~8 us per Gauss-Newton round); a first register version spread the columns over the lanes of a warp and paid ~400
-// dependent shuffles (5.9 us per round, measured with clock64).  Here every step is unrolled with compile-time indices:
-// the complete-pivot search is a tournament over the candidates in row-major order (the earlier one wins ties, as the
-// scan's strict `>` does), the row / column swaps are selects on the run-time pivot position, no data leaves the
-// thread.  Every calling thread computes the same result (callers run it on one warp and let lane 0 write).
-struct PivotCandidate {
-  double v;
-  int idx;   // 6 i + j
-};
-
-// `a` precedes `b` in row-major order: b wins only with a strictly larger value
-__device__ __forceinline__ PivotCandidate first_max(const PivotCandidate& a, const PivotCandidate& b) {
-  return b.v > a.v ? b : a;
+#ifdef VSLAM_GN_TIMING   // development aid: clocks of the phases of gn_step, lane 0 of warp 0 (make EXTRA_aligner="-fmad=false -DVSLAM_GN_TIMING")
+__device__ __forceinline__ long long* gn_clk() {
+  __shared__ long long s[16];
+  return s;
 }
+#define GN_CLK_START() do { if ((threadIdx.x & 31) == 0) gn_clk()[15] = clock64(); } while (0)
+#define GN_CLK(i) do { if ((threadIdx.x & 31) == 0) { long long* c_ = gn_clk(); const long long t_ = clock64(); c_[i] += t_ - c_[15]; c_[15] = t_; } } while (0)
+// the values pass through an empty asm: what is computed from them cannot start before it, what produced them is done
+#define GN_PIN6(v) asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]), "+d"(v[4]), "+d"(v[5]))
+#define GN_PIN1(v) asm volatile("" : "+d"(v))
+#else
+#define GN_CLK_START()
+#define GN_CLK(i)
+#define GN_PIN6(v)
+#define GN_PIN1(v)
+#endif
 
-// ordered tournament over c[0..N): neighbours merge, an odd tail moves up (compile-time recursion: every index is a
-// constant, the candidates stay in registers)
-template <int N, int CAP>
-__device__ __forceinline__ void first_max_of(PivotCandidate (&c)[CAP]) {
-  if constexpr (N > 1) {
-#pragma unroll
-    for (int t = 0; t < N / 2; ++t) c[t] = first_max(c[2 * t], c[2 * t + 1]);
-    if (N & 1) c[N / 2] = c[N - 1];
-    first_max_of<(N + 1) / 2, CAP>(c);
-  }
-}
-
-template <int K>
-__device__ __forceinline__ void lu_step(double (&A)[6][7], int (&perm)[6], int& rank, double& maxpivot) {
-  if (rank < 6) return;                 // a zero pivot ended the elimination (the break of the scalar form)
-  constexpr int M = 6 - K;              // the trailing block is M x M
-  PivotCandidate c[M * M];
-#pragma unroll
-  for (int i = 0; i < M; ++i)
-#pragma unroll
-    for (int j = 0; j < M; ++j) c[i * M + j] = PivotCandidate{fabs(A[K + i][K + j]), 6 * (K + i) + (K + j)};
-  first_max_of<M * M, M * M>(c);
-  const double biggest = c[0].v;
-  if (biggest == 0) {
-    rank = K;
-    return;
-  }
-  if (biggest > maxpivot) maxpivot = biggest;
-  const int pr = (c[0].idx * 43) >> 8;  // idx / 6 for idx < 36
-  const int pc = c[0].idx - 6 * pr;
-  // rows K and pr (columns >= K and the right-hand side: the multipliers left of K are never read again)
-#pragma unroll
-  for (int j = K; j < 7; ++j) {
-    const double vk = A[K][j];
-    double vp = vk;
-#pragma unroll
-    for (int r = K + 1; r < 6; ++r) vp = pr == r ? A[r][j] : vp;
-#pragma unroll
-    for (int r = K + 1; r < 6; ++r) A[r][j] = pr == r ? vk : A[r][j];
-    A[K][j] = vp;
-  }
-  // columns K and pc (every row: the finished rows of U above K follow the permutation)
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    const double vk = A[i][K];
-    double vp = vk;
-#pragma unroll
-    for (int q = K + 1; q < 6; ++q) vp = pc == q ? A[i][q] : vp;
-#pragma unroll
-    for (int q = K + 1; q < 6; ++q) A[i][q] = pc == q ? vk : A[i][q];
-    A[i][K] = vp;
-  }
-  {
-    const int vk = perm[K];
-    int vp = vk;
-#pragma unroll
-    for (int q = K + 1; q < 6; ++q) vp = pc == q ? perm[q] : vp;
-#pragma unroll
-    for (int q = K + 1; q < 6; ++q) perm[q] = pc == q ? vk : perm[q];
-    perm[K] = vp;
-  }
-#pragma unroll
-  for (int i = K + 1; i < 6; ++i) {
-    const double f = A[i][K] / A[K][K];
-#pragma unroll
-    for (int j = K + 1; j < 7; ++j) A[i][j] = A[i][j] - f * A[K][j];
-  }
-}
-
-__device__ __forceinline__ void solve6_regs(const double* H /* 36, row-major */, const double* rhs, double x[6]) {
-  double A[6][7];
-  int perm[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-#pragma unroll
-    for (int j = 0; j < 6; ++j) A[i][j] = H[i * 6 + j];
-    A[i][6] = rhs[i];
-    perm[i] = i;
-  }
+// solve6 of gn_math.h (Eigen::FullPivLU<Matrix6>::solve) by ONE WARP on the 6 x 7 augmented matrix in SHARED memory,
+// bit-identical to the single-thread form.  That form indexes its arrays with the run-time pivot position, i.e. lives in
+// local memory (~8 us per Gauss-Newton round).  Two register forms were measured with clock64 at 7800 cycles per round
+// each: columns spread over the lanes (~400 dependent shuffles), and everything in one thread's registers with
+// compile-time indices (no memory, but ~1100 selects for the run-time row / column swaps: a single warp issues them one
+// after the other).  Here a step of the elimination is a handful of instructions per lane:
+//   * pivot search: lane t holds |A| of candidate t of the trailing block in row-major order (two for lanes 0..3 of the
+//     first step); the maximum is three warp reductions on the bit pattern (high word, low word among the lanes that
+//     hold the maximal high word, lowest candidate index among the lanes that hold the maximum: the FIRST maximum in
+//     scan order, as the scalar strict `>` keeps it);
+//   * row / column swap: lane c swaps its column entry of the two rows, lane r its row entry of the two columns --
+//     run-time indices are free in shared memory;
+//   * elimination: lane (r, c) updates A[k+1+r][k+1+c] (30 lanes in the first step), every lane dividing for itself.
+// A NaN is never the maximum of the scalar scan (`fabs(a) > biggest` is false): its key is 0, below every number's.
+// Every lane of the warp must call; every lane receives x[6].  A: [6][8], column 6 = right-hand side, written by the
+// caller and made visible (__syncwarp) before the call.
+__device__ __forceinline__ void solve6_warp(double (*A)[8], double x[6]) {
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  unsigned perm = 0x543210u;   // nibble i = perm[i]
   int rank = 6;
   double maxpivot = 0;
-  lu_step<0>(A, perm, rank, maxpivot);
-  lu_step<1>(A, perm, rank, maxpivot);
-  lu_step<2>(A, perm, rank, maxpivot);
-  lu_step<3>(A, perm, rank, maxpivot);
-  lu_step<4>(A, perm, rank, maxpivot);
-  lu_step<5>(A, perm, rank, maxpivot);
+  // (Written without divergent branches -- clamped indices, selects, predicated stores: on this machine a divergent
+  // region costs ~100 cycles of a single warp's time, measured with clock64.)
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    if (k < rank) {              // (uniform: a zero pivot ended the elimination, the break of the scalar form)
+      constexpr int kSix = 6;
+      const int M = kSix - k;    // the trailing block is M x M (compile-time: the loop is unrolled)
+      int t = lane;
+      unsigned hk, lk;
+      {
+        const int tc = min(lane, M * M - 1);
+        const double v = fabs(A[k + tc / M][k + tc % M]);
+        const bool valid = lane < M * M && v == v;
+        hk = valid ? (unsigned)__double2hiint(v) + 1u : 0u;
+        lk = valid ? (unsigned)__double2loint(v) : 0u;
+      }
+      if (M * M > 32) {          // candidates 32..35 of the first step: later in scan order, they win when larger
+        const int t2 = min(lane + 32, M * M - 1);
+        const double v = fabs(A[k + t2 / M][k + t2 % M]);
+        const bool valid = lane + 32 < M * M && v == v;
+        const unsigned h2 = valid ? (unsigned)__double2hiint(v) + 1u : 0u, l2 = valid ? (unsigned)__double2loint(v) : 0u;
+        const bool take = h2 > hk || (h2 == hk && l2 > lk);
+        hk = take ? h2 : hk;
+        lk = take ? l2 : lk;
+        t = take ? t2 : t;
+      }
+      GN_CLK(0);
+      const unsigned mh = __reduce_max_sync(full, hk);
+      const unsigned ml = __reduce_max_sync(full, hk == mh ? lk : 0u);
+      const int tw = (int)__reduce_min_sync(full, (hk == mh && lk == ml) ? (unsigned)t : 64u);
+      // (mh == 0: every candidate is a NaN: the scalar scan keeps -1 and (k, k))
+      const double biggest = mh != 0 ? __hiloint2double((int)(mh - 1u), (int)ml) : -1.0;
+      const int pr = mh != 0 ? k + tw / M : k;
+      const int pc = mh != 0 ? k + tw % M : k;
+      GN_CLK(1);
+      if (biggest == 0) {        // (uniform)
+        rank = k;
+      } else {
+        maxpivot = biggest > maxpivot ? biggest : maxpivot;
+        {                        // rows k and pr (the right-hand side in column 6 follows); pr == k rewrites the row
+          const int c = min(lane, 6);
+          const double a = A[k][c], b = A[pr][c];
+          __syncwarp();
+          A[k][c] = b;
+          A[pr][c] = a;
+        }
+        __syncwarp();
+        {                        // columns k and pc (every row: the finished rows of U follow the permutation)
+          const int r = min(lane, 5);
+          const double a = A[r][k], b = A[r][pc];
+          __syncwarp();
+          A[r][k] = b;
+          A[r][pc] = a;
+          const unsigned pk = (perm >> (4 * k)) & 15u, pp = (perm >> (4 * pc)) & 15u;
+          perm = (perm & ~((15u << (4 * k)) | (15u << (4 * pc)))) | (pp << (4 * k)) | (pk << (4 * pc));
+        }
+        __syncwarp();
+        GN_CLK(2);
+        {
+          const int r = lane / 6, c = lane - 6 * r;
+          const bool mine = k + 1 + r < 6 && k + 1 + c < 7;
+          const int i = min(k + 1 + r, 5), j = min(k + 1 + c, 6);
+          const double f = A[i][k] / A[k][k];
+          const double v = A[i][j] - f * A[k][j];
+          __syncwarp();
+          if (mine) A[i][j] = v;
+        }
+        __syncwarp();
+        GN_CLK(3);
+      }
+    }
+  }
   // Eigen::FullPivLU::rank(): only pivots above |largest pivot| * epsilon * size are used by solve()
+  GN_PIN1(maxpivot);
+  GN_CLK(7);
   {
     int r = 0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) r += (i < rank && fabs(A[i][i]) > maxpivot * (2.220446049250313e-16 * 6)) ? 1 : 0;
     rank = r;
   }
+  // back substitution, every lane for itself (broadcast reads); full rank -- the regular case -- as straight-line code
   double y[6];
+  if (rank == 6) {
 #pragma unroll
-  for (int i = 0; i < 6; ++i) y[i] = 0;
-#pragma unroll
-  for (int i = 5; i >= 0; --i) {
-    if (i < rank) {
+    for (int i = 5; i >= 0; --i) {
       double sum = A[i][6];
 #pragma unroll
-      for (int j = 0; j < 6; ++j)
-        if (j > i && j < rank) sum = sum - A[i][j] * y[j];
+      for (int j = i + 1; j < 6; ++j) sum = sum - A[i][j] * y[j];
       y[i] = sum / A[i][i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] = 0;
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+      if (i < rank) {
+        double sum = A[i][6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+          if (j > i && j < rank) sum = sum - A[i][j] * y[j];
+        y[i] = sum / A[i][i];
+      }
     }
   }
   // x[perm[i]] = y[i]
@@ -372,34 +392,53 @@ __device__ __forceinline__ void solve6_regs(const double* H /* 36, row-major */,
 #pragma unroll
   for (int i = 0; i < 6; ++i)
 #pragma unroll
-    for (int t = 0; t < 6; ++t) x[t] = perm[i] == t ? y[i] : x[t];
+    for (int t = 0; t < 6; ++t) x[t] = (int)((perm >> (4 * i)) & 15u) == t ? y[i] : x[t];
+  GN_PIN6(x);
+  GN_CLK(4);
 }
 
 // oneRound (:190-207 / :174-191) + the converge state machine (:213-247 / :197-233) for one finished linearisation:
 // damped system, full-pivot solve, pose update, bookkeeping in *ctl (global memory in the grid kernel, shared memory in
-// the cluster kernel).  Called by the WHOLE first warp of the block (the solve is warp-cooperative); lane 0 writes.
-// `s_H` is a 36-double scratch in shared memory.
-__device__ __forceinline__ void gn_step(GnControl* ctl, const double* s_sys, const double* s_T, double* s_H, int n,
+// the cluster kernel).  Called by the WHOLE first warp of the block (the solve is warp-cooperative).
+// `s_A` is the solver's [6][8] scratch in shared memory.
+__device__ __forceinline__ void gn_step(GnControl* ctl, const double* s_sys, const double* s_T, double (*s_A)[8], int n,
                                         const GnParams& p) {
   const int lane = threadIdx.x & 31;
-  {   // H as the single-thread form builds it: both triangles from the packed upper one, then the damping on the diagonal
+  GN_CLK_START();
+  {   // H as the single-thread form builds it: both triangles from the packed upper one, then the damping on the
+      // diagonal; the solver's working copy carries -b as a seventh column
     for (int idx = lane; idx < 36; idx += 32) {
       const int i = idx / 6, j = idx - 6 * i;
       double v = s_sys[tri(min(i, j), max(i, j))];
       if (i == j) v += p.damping * n;
-      s_H[idx] = v;
+      ctl->H[idx] = v;
+      s_A[i][j] = v;
     }
+    if (lane < 6) s_A[lane][6] = -s_sys[21 + lane];
     __syncwarp();
   }
-  double nb[6], dx[6];
-  for (int i = 0; i < 6; ++i) nb[i] = -s_sys[21 + i];
-  solve6_regs(s_H, nb, dx);
-  if (lane != 0) return;
-  double T[12];
+  double dx[6];
+  solve6_warp(s_A, dx);
+  double T[12];   // (every lane: the update is a few dozen operations, the pose is written by 12 lanes at once)
+#pragma unroll
   for (int i = 0; i < 12; ++i) T[i] = s_T[i];
+  GN_PIN6(T);
+  GN_CLK(8);
   apply_update(dx, T);
-  for (int i = 0; i < 12; ++i) ctl->T[i] = T[i];
-  for (int i = 0; i < 36; ++i) ctl->H[i] = s_H[i];
+  GN_PIN6(T);
+  {
+    double* T6 = T + 6;
+    GN_PIN6(T6);
+  }
+  GN_CLK(9);
+  {   // lane i < 12 stores T[i] (a select chain: twelve divergent one-lane stores cost 2000 cycles)
+    double mine = T[0];
+#pragma unroll
+    for (int i = 1; i < 12; ++i) mine = lane == i ? T[i] : mine;
+    if (lane < 12) ctl->T[lane] = mine;
+  }
+  GN_CLK(5);
+  if (lane != 0) return;
   const double total_error = s_sys[27];
   const int inliers = (int)llrint(s_sys[28]);
   const int outliers = n - inliers;
@@ -427,6 +466,7 @@ __device__ __forceinline__ void gn_step(GnControl* ctl, const double* s_sys, con
   ctl->converged = converged;
   __threadfence();
   ctl->done = done;
+  GN_CLK(6);
 }
 
 // Fused Gauss-Newton: BaseAligner::converge (reference stereouv_aligner.cpp:210-264, uvd_aligner.cpp:194-248) as ONE
@@ -443,7 +483,7 @@ __global__ void __launch_bounds__(kThreads) converge_kernel(int n, AlignerBuffer
   __shared__ double s_part[kThreads / 32][kAcc];
   __shared__ double s_T[12];
   __shared__ double s_sys[32];
-  __shared__ double s_H[36];
+  __shared__ double s_A[6][8];          // working copy of the damped system, column 6 = -b
   __shared__ int s_ignore;
 
   for (;;) {
@@ -488,7 +528,7 @@ __global__ void __launch_bounds__(kThreads) converge_kernel(int n, AlignerBuffer
         }
         __syncthreads();
       }
-      if (threadIdx.x < 32) gn_step(ctl, s_sys, s_T, s_H, n, p);
+      if (threadIdx.x < 32) gn_step(ctl, s_sys, s_T, s_A, n, p);
     }
     grid.sync();
     if (__ldcg(&ctl->done)) break;
@@ -528,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, 1) converge_cluster_kernel(int n, Al
   __shared__ double s_total[2][32];     // this block's partial sums of the even / odd rounds, read by every block
   __shared__ double s_T[12];
   __shared__ double s_sys[32];
-  __shared__ double s_H[36];
+  __shared__ double s_A[6][8];          // working copy of the damped system, column 6 = -b
   __shared__ GnControl s_ctl;           // every block advances its own copy (identically)
 
   if (threadIdx.x < 12) s_ctl.T[threadIdx.x] = ctl->T[threadIdx.x];
@@ -563,6 +603,7 @@ __global__ void __launch_bounds__(kThreads, 1) converge_cluster_kernel(int n, Al
   double err = -1.0;
   uint8_t inl = 0;
 #ifdef VSLAM_GN_TIMING   // phase clocks of block 0 (development aid: make EXTRA_aligner="-fmad=false -DVSLAM_GN_TIMING")
+  if (threadIdx.x < 16) gn_clk()[threadIdx.x] = 0;
   long long t_phase[6] = {0, 0, 0, 0, 0, 0}, t_mark = clock64();
 #define GN_MARK(i) { const long long t_now = clock64(); t_phase[i] += t_now - t_mark; t_mark = t_now; }
 #else
@@ -600,12 +641,16 @@ __global__ void __launch_bounds__(kThreads, 1) converge_cluster_kernel(int n, Al
       __syncthreads();
     }
     GN_MARK(4)
-    if (threadIdx.x < 32) gn_step(&s_ctl, s_sys, s_T, s_H, n, p);
+    if (threadIdx.x < 32) gn_step(&s_ctl, s_sys, s_T, s_A, n, p);
     GN_MARK(5)
     __syncthreads();
     if (s_ctl.done) break;
   }
 #ifdef VSLAM_GN_TIMING
+  if (rank == 0 && threadIdx.x == 0)
+    printf("gn_step clocks: build + candidates %lld | pivot reductions %lld | swaps %lld | elimination %lld | (pin) %lld | rank + back "
+           "substitution %lld | load T %lld | apply_update %lld | store T %lld | state machine %lld\n", gn_clk()[0], gn_clk()[1],
+           gn_clk()[2], gn_clk()[3], gn_clk()[7], gn_clk()[4], gn_clk()[8], gn_clk()[9], gn_clk()[5], gn_clk()[6]);
   if (rank == 0 && threadIdx.x == 0)
     printf("gn timing (cycles, %d rounds): load T %lld | accumulate %lld | block reduce %lld | cluster barrier %lld | gather %lld | "
            "solve + update %lld\n", s_ctl.rounds, t_phase[0], t_phase[1], t_phase[2], t_phase[3], t_phase[4], t_phase[5]);
