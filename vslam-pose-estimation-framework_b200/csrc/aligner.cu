@@ -551,17 +551,31 @@ __global__ void __launch_bounds__(kThreads) converge_kernel(int n, AlignerBuffer
 template <int KIND>
 __global__ void __launch_bounds__(kThreads, 1) converge_cluster_kernel(int n, AlignerBuffers b, AlignerCamera cam, GnParams p,
                                                                     GnControl* __restrict__ ctl,
-                                                                    const int32_t* __restrict__ n_device) {
+                                                                    const int32_t* __restrict__ n_device, FrameFill fill,
+                                                                    FramePrune prune) {
   constexpr int D = KIND == 0 ? 4 : 3;
   constexpr int W = KIND == 0 ? 1 : 2;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
   // fused frame (captured graph): the correspondence count is what track() left in device memory; nothing to align
   // without tracks (pose_tracker_3d.cpp:355: the tracker only optimises a frame that has points)
   if (n_device) {
     n = *n_device;
-    if (n <= 0 || n > (int)(gridDim.x * kThreads)) return;
+    const bool run = n > 0 && n <= (int)(gridDim.x * kThreads);
+    if (fill.tracks && rank == 0 && !run) {   // the frame still publishes a control block: the prior, no rounds
+      if (threadIdx.x < 12) ctl->T[threadIdx.x] = fill.state->T_prior[threadIdx.x];
+      if (threadIdx.x < 36) ctl->H[threadIdx.x] = 0.0;
+      if (threadIdx.x < kAcc) b.system[threadIdx.x] = 0.0;
+      if (threadIdx.x == 0) {
+        ctl->total_error_previous = 0.0;
+        ctl->rounds = ctl->phase = ctl->iteration = ctl->ignore = ctl->converged = ctl->done = 0;
+        fill.state->overflow = n > (int)(gridDim.x * kThreads) ? 1 : 0;
+        fill.state->n_kept = 0;
+        fill.state->inliers_only = 0;
+      }
+    }
+    if (!run) return;
   }
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank();
   const int n_active = (n + kThreads - 1) / kThreads;     // blocks that hold a correspondence
   if (rank >= n_active) return;
   __shared__ double s_part[kThreads / 32][kAcc];
@@ -571,15 +585,28 @@ __global__ void __launch_bounds__(kThreads, 1) converge_cluster_kernel(int n, Al
   __shared__ double s_A[6][8];          // working copy of the damped system, column 6 = -b
   __shared__ GnControl s_ctl;           // every block advances its own copy (identically)
 
-  if (threadIdx.x < 12) s_ctl.T[threadIdx.x] = ctl->T[threadIdx.x];
-  if (threadIdx.x == 0) {
-    s_ctl.total_error_previous = ctl->total_error_previous;
-    s_ctl.rounds = ctl->rounds;
-    s_ctl.phase = ctl->phase;
-    s_ctl.iteration = ctl->iteration;
-    s_ctl.ignore = ctl->ignore;
-    s_ctl.converged = ctl->converged;
-    s_ctl.done = ctl->done;
+  if (fill.tracks) {                   // converge() of a fused frame starts from the motion prior (stereouv_aligner.cpp:213-216)
+    if (threadIdx.x < 12) s_ctl.T[threadIdx.x] = fill.state->T_prior[threadIdx.x];
+    if (threadIdx.x == 0) {
+      s_ctl.total_error_previous = 0.0;
+      s_ctl.rounds = s_ctl.phase = s_ctl.iteration = s_ctl.ignore = s_ctl.converged = s_ctl.done = 0;
+      if (rank == 0) {
+        fill.state->overflow = 0;
+        fill.state->n_kept = 0;
+        fill.state->inliers_only = 0;
+      }
+    }
+  } else {
+    if (threadIdx.x < 12) s_ctl.T[threadIdx.x] = ctl->T[threadIdx.x];
+    if (threadIdx.x == 0) {
+      s_ctl.total_error_previous = ctl->total_error_previous;
+      s_ctl.rounds = ctl->rounds;
+      s_ctl.phase = ctl->phase;
+      s_ctl.iteration = ctl->iteration;
+      s_ctl.ignore = ctl->ignore;
+      s_ctl.converged = ctl->converged;
+      s_ctl.done = ctl->done;
+    }
   }
   // this thread's correspondence (the grid version's block `rank`, thread threadIdx.x, first and only iteration)
   const int u = rank * kThreads + threadIdx.x;
@@ -589,7 +616,26 @@ __global__ void __launch_bounds__(kThreads, 1) converge_cluster_kernel(int n, Al
   for (int d = 0; d < D; ++d) fx[d] = 0;
 #pragma unroll
   for (int d = 0; d < W; ++d) om[d] = 0;
-  if (mine) {
+  if (KIND == 0 && fill.tracks) {
+    if (mine) {                        // StereoUVAligner::initialize for correspondence u (stereouv_aligner.cpp:26-64)
+      const TrackRecord* t = fill.tracks + u;
+      const PreviousPoint* pp = fill.previous + t->index_previous;
+      m[0] = pp->camera[0];            // :52-55 previous->cameraCoordinatesLeft()
+      m[1] = pp->camera[1];
+      m[2] = pp->camera[2];
+      fx[0] = (double)t->xl;           // :36-39
+      fx[1] = (double)t->yl;
+      fx[2] = (double)t->xr;
+      fx[D - 1] = (double)t->yr;
+      om[0] = 1.0;                     // :28 setIdentity
+      wt = 1.0;
+      if (fill.inverse_depth_weight) { // :59-63 std::min(max_depth / depth, 1.0)
+        const double ratio = fill.max_reliable_depth / t->camera[2];
+        wt = 1.0 < ratio ? 1.0 : ratio;
+      }
+      fill.track_length[u] = pp->reserved;   // trackLength() of the previous point (frame_point.cpp:27)
+    }
+  } else if (mine) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) m[d] = b.moving[d * b.stride + u];
 #pragma unroll
@@ -675,7 +721,57 @@ __global__ void __launch_bounds__(kThreads, 1) converge_cluster_kernel(int n, Al
       ctl->done = s_ctl.done;
     }
   }
-  cluster.sync();                       // no block may exit while another still reads its partials of the last round
+  if (!prune.tracked) {
+    cluster.sync();                     // no block may exit while another still reads its partials of the last round
+    return;
+  }
+  // ---- _prunePoints (pose_tracker_3d.cpp:437-472) over the cluster: keep = inlier when the average error
+  // (total error / correspondences, base_aligner.h:46) is below the kernel, else error != -1 && error < 100 kernel; the
+  // kept records keep their order: block scan, block totals through distributed shared memory, one cluster barrier
+  // (every record is read before it, every write comes after it: the compaction is in place)
+  __shared__ int s_keep_warp[kThreads / 32];
+  __shared__ int s_keep_total;
+  const bool inliers_only = s_sys[27] / n < prune.error_kernel;     // (n > 0 here)
+  const bool keep = mine && (inliers_only ? inl != 0 : (err != -1.0 && err < 100 * prune.error_kernel));
+  uint4 rec0 = make_uint4(0, 0, 0, 0), rec1 = rec0;
+  if (keep) {
+    const uint4* src = reinterpret_cast<const uint4*>(prune.tracked + u);
+    rec0 = src[0];
+    rec1 = src[1];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) s_keep_warp[warp] = __popc(bal);
+  __syncthreads();
+  int before = 0, block_total = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const int c = s_keep_warp[w];
+    if (w < warp) before += c;
+    block_total += c;
+  }
+  if (threadIdx.x == 0) s_keep_total = block_total;
+  cluster.sync();                       // totals published, records read, partials of the last round no longer needed
+  int all = 0;
+  for (int r = 0; r < n_active; ++r) {
+    const int c = *cluster.map_shared_rank(&s_keep_total, r);
+    if (r < rank) before += c;
+    all += c;
+  }
+  if (mine) {
+    const int pos = before + __popc(bal & ((1u << lane) - 1u));
+    prune.kept_pos[u] = keep ? pos : -1;
+    if (keep) {
+      uint4* dst = reinterpret_cast<uint4*>(prune.tracked + pos);
+      dst[0] = rec0;
+      dst[1] = rec1;
+    }
+  }
+  if (rank == 0 && threadIdx.x == 0) {
+    prune.state->n_kept = all;
+    prune.state->inliers_only = inliers_only;
+  }
+  cluster.sync();                       // no block may exit while another still reads its total
 }
 
 // Batched form for independent stereo pairs: one WARP per pair linearises the StereoUV problem that aligns the
@@ -776,9 +872,11 @@ cudaError_t launch_converge(int kind, int n, const AlignerBuffers& b, const Alig
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     const int32_t* no_device_count = nullptr;
+    const FrameFill no_fill = {nullptr, nullptr, nullptr, nullptr, 0.0, 0};
+    const FramePrune no_prune = {nullptr, nullptr, nullptr, 0.0};
     const cudaError_t e =
-        kind == 0 ? cudaLaunchKernelEx(&cfg, converge_cluster_kernel<0>, n_arg, b_arg, cam_arg, p_arg, ctl, no_device_count)
-                  : cudaLaunchKernelEx(&cfg, converge_cluster_kernel<1>, n_arg, b_arg, cam_arg, p_arg, ctl, no_device_count);
+        kind == 0 ? cudaLaunchKernelEx(&cfg, converge_cluster_kernel<0>, n_arg, b_arg, cam_arg, p_arg, ctl, no_device_count, no_fill, no_prune)
+                  : cudaLaunchKernelEx(&cfg, converge_cluster_kernel<1>, n_arg, b_arg, cam_arg, p_arg, ctl, no_device_count, no_fill, no_prune);
     if (e == cudaSuccess) return e;
     cudaGetLastError();                 // e.g. a cluster size this device does not schedule: use the grid kernel
   }
@@ -817,11 +915,12 @@ int frame_step_cluster_blocks() {
 }
 
 cudaError_t launch_converge_frame(const AlignerBuffers& b, const AlignerCamera& cam, const GnParams& p, GnControl* ctl,
-                                  const int32_t* n_device, int cluster_blocks, cudaStream_t stream) {
+                                  const int32_t* n_device, int cluster_blocks, const FrameFill& fill, const FramePrune& prune,
+                                  cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr;
   cluster_config(&cfg, &attr, cluster_blocks, stream);
-  return cudaLaunchKernelEx(&cfg, converge_cluster_kernel<0>, 0, b, cam, p, ctl, n_device);
+  return cudaLaunchKernelEx(&cfg, converge_cluster_kernel<0>, 0, b, cam, p, ctl, n_device, fill, prune);
 }
 
 void launch_linearize_pairs(const FramePointRecord* records, int record_stride, const int32_t* n_out, int n_pairs,

@@ -1222,8 +1222,8 @@ static int issue_frame_step(vslam_fpg* h, Lane& lane, size_t stride, const vslam
   launch_track(g, h->sp, h->b, 0, h->d_previous, h->step_cap, tp, h->track_scratch, h->d_tracks, h->d_lost, h->d_tracked,
                lane.stream, h->d_step);                                          // :239
   mark(h, lane, kEvTrack1);
-  // After track() the frame splits into two chains that meet at the bin selection: the aligner (fill -> converge ->
-  // prune) and the epipolar match of the features track() left over (:210; it reads neither the tracks nor the pose).
+  // After track() the frame splits into two chains that meet at the bin selection: the aligner (converge, with
+  // _prunePoints as its tail) and the epipolar match of the features track() left over (:210; it reads neither the tracks nor the pose).
   // The tracks' share of points() needs the prune only and runs beside the selection.
   const bool branches = use_branches(h, lane, 1);
   cudaStream_t side = branches ? h->side_stream : lane.stream;
@@ -1236,7 +1236,6 @@ static int issue_frame_step(vslam_fpg* h, Lane& lane, size_t stride, const vslam
     }
   };
   if (branches) match_passes(side);
-  launch_frame_aligner_fill(f, fp, lane.stream);                                 // :124-126 / :355-356
   AlignerCamera cam;
   const double K[9] = {h->sp.fx, 0, h->sp.cx, 0, h->sp.fy, h->sp.cy, 0, 0, 1};
   for (int i = 0; i < 9; ++i) cam.K[i] = K[i];
@@ -1249,9 +1248,12 @@ static int issue_frame_step(vslam_fpg* h, Lane& lane, size_t stride, const vslam
   gp.damping = p.aligner.damping;
   gp.max_iterations = p.aligner.maximum_number_of_iterations;
   gp.inlier_gate = p.aligner.minimum_number_of_inliers;                          // stereouv_aligner.cpp:224
-  CUDA_TRY(launch_converge_frame(f.aligner, cam, gp, h->d_step_ctl, h->track_scratch.stats, h->step_cluster_blocks,
-                                 lane.stream));                                  // :357
-  launch_frame_prune(f, fp, lane.stream);                                        // :437-472
+  // StereoUVAligner::initialize (:124-126 / :355-356) is the head of the kernel, _prunePoints (:437-472) its tail
+  const FrameFill fill = {h->d_tracks, h->d_previous, h->d_step_track_length, h->d_step, fp.max_reliable_depth,
+                          fp.inverse_depth_weight};
+  const FramePrune prune = {h->d_tracked, h->d_step_kept_pos, h->d_step, fp.error_kernel};
+  CUDA_TRY(launch_converge_frame(f.aligner, cam, gp, h->d_step_ctl, h->track_scratch.stats, h->step_cluster_blocks, fill,
+                                 prune, lane.stream));                           // :357
   if (branches) {
     order_after(h, side, lane.stream, 2);      // the selection needs the matches ...
     order_after(h, lane.stream, side, 3);      // ... and the tracks' share of points() the prune
@@ -1270,7 +1272,7 @@ static int issue_frame_step(vslam_fpg* h, Lane& lane, size_t stride, const vslam
   } else {
     launch_frame_assemble(g, f, fp, kAssembleAll, lane.stream);
   }
-  h->launches += 2 + 4 + 1;   // track (2), fill / converge / prune / assemble, select
+  h->launches += 2 + 2 + 1;   // track (2), converge + prune / assemble, select
   return VSLAM_OK;                // (the detection status reaches the host through frame_assemble_kernel's last block)
 }
 

@@ -4,9 +4,8 @@
 // next track() reads), moved to the device so that a frame is ONE graph launch and one synchronisation.  Counts travel
 // through FrameStepState (device memory), never through kernel arguments.
 //
-//   frame_aligner_fill_kernel   StereoUVAligner::initialize over the tracks (reference src/aligners/stereouv_aligner.cpp:
-//                               26-64, the branch without a landmark estimate) + the control block of converge()
-//   frame_prune_kernel          _prunePoints on the bin pre-load records, the kept flags and their ordered positions
+//   (StereoUVAligner::initialize over the tracks is written by track_resolve_kernel's ordered output, track.cu;
+//    _prunePoints on the bin pre-load records runs as the tail of converge_cluster_kernel, aligner.cu)
 //   frame_assemble_kernel       points() of the frame (surviving tracks, then the new framepoints, with their descriptors)
 //                               replace the previous points in place; everything the host reads is written into the
 //                               handle's pinned, device-mapped result block
@@ -15,104 +14,6 @@
 namespace vslam {
 
 namespace {
-
-constexpr int kFillThreads = 256;
-
-__global__ void __launch_bounds__(kFillThreads) frame_aligner_fill_kernel(FrameStepBuffers f, FrameStepParams p) {
-  const int n = f.stats[0];
-  const int u = blockIdx.x * kFillThreads + threadIdx.x;
-  if (u == 0) {
-    GnControl* c = f.ctl;
-    for (int i = 0; i < 12; ++i) c->T[i] = f.state->T_prior[i];
-    for (int i = 0; i < 36; ++i) c->H[i] = 0.0;
-    c->total_error_previous = 0.0;
-    c->rounds = c->phase = c->iteration = c->ignore = c->converged = c->done = 0;
-    for (int i = 0; i < 32; ++i) f.aligner.system[i] = 0.0;
-    f.state->overflow = n > f.cap ? 1 : 0;
-    f.state->n_kept = 0;
-    f.state->inliers_only = 0;
-  }
-  if (u >= n || u >= f.cap) return;
-  const TrackRecord t = f.tracks[u];
-  const PreviousPoint* pp = f.previous + t.index_previous;
-  const int S = f.aligner.stride;
-  double* moving = const_cast<double*>(f.aligner.moving);
-  double* fixed = const_cast<double*>(f.aligner.fixed);
-  moving[u] = pp->camera[0];                                 // :52-55 previous->cameraCoordinatesLeft()
-  moving[S + u] = pp->camera[1];
-  moving[2 * S + u] = pp->camera[2];
-  fixed[u] = (double)t.xl;                                   // :36-39
-  fixed[S + u] = (double)t.yl;
-  fixed[2 * S + u] = (double)t.xr;
-  fixed[3 * S + u] = (double)t.yr;
-  const_cast<double*>(f.aligner.omega)[u] = 1.0;             // :28 setIdentity
-  double w = 1.0;
-  if (p.inverse_depth_weight) {                              // :59-63 std::min(max_depth / depth, 1.0)
-    const double q = p.max_reliable_depth / t.camera[2];
-    w = 1.0 < q ? 1.0 : q;
-  }
-  const_cast<double*>(f.aligner.wt)[u] = w;
-  f.track_length[u] = pp->reserved;                          // trackLength() of the previous point (frame_point.cpp:27)
-}
-
-// pose_tracker_3d.cpp:437-472.  One CTA; track k is handled by thread k mod 1024 in chunk k / 1024 (at most 4 chunks:
-// the fused frame holds 4096 tracks), every load of a thread is independent of the others (one memory round trip), and
-// the ordered positions come from one block scan per chunk.  The kept bin pre-load records are compacted in place: a
-// chunk writes to positions at or below its own indices, all of which have been read before its scan's barrier.
-constexpr int kPruneThreads = 1024;
-constexpr int kPruneChunks = 4;
-__global__ void __launch_bounds__(kPruneThreads) frame_prune_kernel(FrameStepBuffers f, FrameStepParams p) {
-  __shared__ int s_warp[kPruneThreads / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = min(f.stats[0], min(f.cap, kPruneThreads * kPruneChunks));
-  // averageError() = total error / correspondences (base_aligner.h:46) of the last linearisation
-  const bool inliers_only = n > 0 && f.aligner.system[27] / n < p.error_kernel;
-  const double cap = 100 * p.error_kernel;
-  uint4 rec[kPruneChunks][2];
-  bool keep[kPruneChunks];
-#pragma unroll
-  for (int j = 0; j < kPruneChunks; ++j) {
-    const int k = j * kPruneThreads + tid;
-    keep[j] = false;
-    if (k < n) {
-      const double e = f.aligner.errors[k];
-      keep[j] = inliers_only ? f.aligner.inliers[k] != 0 : (e != -1.0 && e < cap);
-      const uint4* src = reinterpret_cast<const uint4*>(f.tracked + k);
-      rec[j][0] = src[0];
-      rec[j][1] = src[1];
-    }
-  }
-  int base = 0;
-#pragma unroll
-  for (int j = 0; j < kPruneChunks; ++j) {
-    if (j * kPruneThreads >= n) break;             // (uniform)
-    const unsigned bal = __ballot_sync(0xffffffffu, keep[j]);
-    if (lane == 0) s_warp[warp] = __popc(bal);
-    __syncthreads();                               // (also: every record of this chunk has been read)
-    int before = 0, total = 0;
-    for (int w = 0; w < kPruneThreads / 32; ++w) {
-      const int c = s_warp[w];
-      if (w < warp) before += c;
-      total += c;
-    }
-    const int k = j * kPruneThreads + tid;
-    if (k < n) {
-      const int pos = base + before + __popc(bal & ((1u << lane) - 1u));
-      f.kept_pos[k] = keep[j] ? pos : -1;
-      if (keep[j]) {
-        uint4* dst = reinterpret_cast<uint4*>(f.tracked + pos);
-        dst[0] = rec[j][0];
-        dst[1] = rec[j][1];
-      }
-    }
-    base += total;
-    __syncthreads();                               // s_warp is reused by the next chunk
-  }
-  if (tid == 0) {
-    f.state->n_kept = base;
-    f.state->inliers_only = inliers_only;
-  }
-}
 
 // coalesced 16-byte copies of a contiguous range by one block
 __device__ __forceinline__ void copy16(void* dst, const void* src, size_t bytes, int tid, int threads) {
@@ -248,14 +149,6 @@ __global__ void __launch_bounds__(kAssembleThreads) frame_assemble_kernel(Geomet
 }
 
 }  // namespace
-
-void launch_frame_aligner_fill(const FrameStepBuffers& f, const FrameStepParams& p, cudaStream_t stream) {
-  frame_aligner_fill_kernel<<<(f.cap + kFillThreads - 1) / kFillThreads, kFillThreads, 0, stream>>>(f, p);
-}
-
-void launch_frame_prune(const FrameStepBuffers& f, const FrameStepParams& p, cudaStream_t stream) {
-  frame_prune_kernel<<<1, kPruneThreads, 0, stream>>>(f, p);
-}
 
 void launch_frame_assemble(const Geometry& g, const FrameStepBuffers& f, const FrameStepParams& p, int part,
                            cudaStream_t stream) {

@@ -185,6 +185,28 @@ struct GnControl {
   int rounds, phase, iteration, ignore, converged, done;
 };
 
+// fused frame: StereoUVAligner::initialize (reference src/aligners/stereouv_aligner.cpp:26-64, the branch without a
+// landmark estimate) as the head of the cluster Gauss-Newton kernel -- thread k reads track k and its previous point
+// instead of planes another kernel would have to write; the control block of converge() starts from the motion prior.
+struct FrameFill {
+  const TrackRecord* tracks;       // [cap] track() output; nullptr: the correspondences come from AlignerBuffers
+  const PreviousPoint* previous;   // points() of the previous frame
+  int32_t* track_length;           // [cap] per track: trackLength() of its previous point (for the frame's points())
+  FrameStepState* state;           // T_prior in; overflow, n_kept, inliers_only out
+  double max_reliable_depth;       // _maximum_reliable_depth_meters (slam_assembly.cpp:70)
+  int inverse_depth_weight;        // enable_inverse_depth_as_information
+};
+
+// fused frame: PoseTracker3D::_prunePoints (reference src/position_tracking/pose_tracker_3d.cpp:437-472) as the tail of the
+// cluster Gauss-Newton kernel -- the errors / inliers of the last round are still in the threads' registers.  Record k of
+// the bin pre-load belongs to correspondence k; the kept records are compacted in place, in order.
+struct FramePrune {
+  TrackedPoint* tracked;   // [cap] bin pre-load records of track(); nullptr: no prune
+  int32_t* kept_pos;       // [cap] per track: position among the surviving tracks or -1
+  FrameStepState* state;   // n_kept, inliers_only
+  double error_kernel;     // maximum_error_kernel
+};
+
 int aligner_grid(int n, int resident_blocks);
 int converge_max_blocks_per_sm(int kind);
 cudaError_t launch_converge(int kind, int n, const AlignerBuffers& b, const AlignerCamera& cam, const GnParams& p,
@@ -197,7 +219,8 @@ void launch_linearize(int kind, int n, const AlignerBuffers& b, const AlignerCam
 // schedules for the kernel (16 with the non-portable opt-in, else 8, 0 when none); capacity = blocks x 256.
 int frame_step_cluster_blocks();
 cudaError_t launch_converge_frame(const AlignerBuffers& b, const AlignerCamera& cam, const GnParams& p, GnControl* ctl,
-                                  const int32_t* n_device, int cluster_blocks, cudaStream_t stream);
+                                  const int32_t* n_device, int cluster_blocks, const FrameFill& fill, const FramePrune& prune,
+                                  cudaStream_t stream);
 // one CTA per stereo pair: StereoUV initialize + linearize of the pair's new framepoints against themselves
 void launch_linearize_pairs(const FramePointRecord* records, int record_stride, const int32_t* n_out, int n_pairs,
                             const AlignerCamera& cam, const double T[12], int ignore_outliers, double kernel,
@@ -267,8 +290,6 @@ struct FrameStepParams {
 };
 // StereoUVAligner::initialize over the tracks (stereouv_aligner.cpp:26-64, the branch without a landmark estimate) and the
 // control block of converge(); then, after the cluster kernel: _prunePoints; after select: points() of the frame
-void launch_frame_aligner_fill(const FrameStepBuffers& f, const FrameStepParams& p, cudaStream_t stream);
-void launch_frame_prune(const FrameStepBuffers& f, const FrameStepParams& p, cudaStream_t stream);
 enum { kAssembleAll = 0, kAssembleTracks = 1, kAssembleRest = 2 };   // blocks of one frame_assemble launch
 void launch_frame_assemble(const Geometry& g, const FrameStepBuffers& f, const FrameStepParams& p, int part,
                            cudaStream_t stream);
