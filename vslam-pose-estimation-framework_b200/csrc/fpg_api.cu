@@ -722,7 +722,7 @@ int vslam_fpg_destroy(vslam_fpg* h) {
     if (l.stream) cudaStreamDestroy(l.stream);
   }
   cudaFree(h->d_systems); cudaFree(h->d_pair_errors); cudaFree(h->d_pair_inliers);
-  cudaFree(h->d_previous); cudaFree(h->track_scratch.tentative); cudaFree(h->track_scratch.claim_l);
+  cudaFree(h->d_previous); cudaFree(h->track_scratch.tentative); cudaFree(h->track_scratch.final); cudaFree(h->track_scratch.claim_l);
   cudaFree(h->track_scratch.claim_r); cudaFree(h->track_scratch.stats); cudaFree(h->d_tracks); cudaFree(h->d_lost);
   cudaFree(h->d_recover_xy); cudaFree(h->d_recover_desc); cudaFree(h->d_recovered); cudaFree(h->d_recover_n);
   cudaFree(h->d_brief_tests);
@@ -981,15 +981,16 @@ static int ensure_previous_capacity(vslam_fpg* h, int n) {
   CUDA_TRY(cudaStreamSynchronize(h->lanes[0].stream));
   invalidate_step_graphs(h);
   const int cap = std::max(2 * n, 1024);
-  cudaFree(h->d_previous); cudaFree(h->track_scratch.tentative); cudaFree(h->d_tracks); cudaFree(h->d_lost);
+  cudaFree(h->d_previous); cudaFree(h->track_scratch.tentative); cudaFree(h->track_scratch.final); cudaFree(h->d_tracks); cudaFree(h->d_lost);
   cudaFree(h->d_recover_xy); cudaFree(h->d_recover_desc); cudaFree(h->d_recovered);
-  h->d_previous = nullptr; h->track_scratch.tentative = nullptr; h->d_tracks = nullptr; h->d_lost = nullptr;
+  h->d_previous = nullptr; h->track_scratch.tentative = nullptr; h->track_scratch.final = nullptr; h->d_tracks = nullptr; h->d_lost = nullptr;
   h->d_recover_xy = nullptr; h->d_recover_desc = nullptr; h->d_recovered = nullptr;
   cudaFreeHost(h->h_tracks); cudaFreeHost(h->h_lost);
   h->h_tracks = nullptr; h->h_lost = nullptr;
   h->previous_cap = 0;
   CUDA_TRY(cudaMalloc((void**)&h->d_previous, sizeof(PreviousPoint) * (size_t)cap));
   CUDA_TRY(cudaMalloc((void**)&h->track_scratch.tentative, sizeof(int4) * (size_t)cap));
+  CUDA_TRY(cudaMalloc((void**)&h->track_scratch.final, sizeof(int4) * (size_t)cap));
   CUDA_TRY(cudaMalloc((void**)&h->d_tracks, sizeof(TrackRecord) * (size_t)cap));
   CUDA_TRY(cudaMalloc((void**)&h->d_lost, sizeof(int32_t) * (size_t)cap));
   CUDA_TRY(cudaMalloc((void**)&h->d_recover_xy, sizeof(uint32_t) * 2 * (size_t)cap));
@@ -1033,7 +1034,7 @@ int vslam_fpg_track(vslam_fpg* h, const vslam_previous_point* previous, int32_t 
   launch_track(h->g, h->sp, h->b, 0, h->d_previous, n_previous, tp, h->track_scratch, h->d_tracks, h->d_lost,
                h->d_tracked, lane.stream);
   mark(h, lane, kEvTrack1);
-  h->launches += n_previous > 0 ? 2 : 1;
+  h->launches += n_previous > 0 ? 3 : 1;
   // results travel with the counts in ONE round trip: at most n_previous records each (ordered, valid prefix)
   CUDA_TRY(cudaMemcpyAsync(h->h_track_stats, h->track_scratch.stats, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, lane.stream));
   if (n_previous) {
@@ -1272,7 +1273,7 @@ static int issue_frame_step(vslam_fpg* h, Lane& lane, size_t stride, const vslam
   } else {
     launch_frame_assemble(g, f, fp, kAssembleAll, lane.stream);
   }
-  h->launches += 2 + 2 + 1;   // track (2), converge + prune / assemble, select
+  h->launches += 3 + 2 + 1;   // track (search, resolve, emit), converge (+ initialize, prune) / assemble, select
   return VSLAM_OK;                // (the detection status reaches the host through frame_assemble_kernel's last block)
 }
 

@@ -77,6 +77,7 @@ struct FrameStepState {
 
 struct TrackScratch {
   int4* tentative;       // [n_previous] {sorted left feature | -1, sorted right feature | -1, distance, status}
+  int4* final;           // [n_previous] per track, in order: {previous point, left feature, right feature, distance}
   int32_t* claim_l;      // [cap] lowest previous-point index that consumes the left feature
   int32_t* claim_r;      // [cap]
   int32_t* stats;        // [4] {tracks, lost, tracked landmarks, accumulated distance}

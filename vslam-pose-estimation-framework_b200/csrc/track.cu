@@ -26,6 +26,7 @@
 // The lattice of the reference is replaced by the (row, col)-sorted feature arrays + CSR row pointers: a window's rows
 // are one contiguous index range, scanned in the reference's row-major order (ties resolve to the lowest index).
 #include <algorithm>
+#include <cstdio>
 
 #include "kernels.cuh"
 #include "stereo_device.cuh"
@@ -248,14 +249,20 @@ __device__ __forceinline__ int block_scan_flag(bool flag, int* s_red, int* total
   return warp_offset + __popc(bal & ((1u << lane) - 1u));
 }
 
+#ifdef VSLAM_TRACK_TIMING   // development aid: phase clocks of track_resolve_kernel (make EXTRA_track="-fmad=false -DVSLAM_TRACK_TIMING")
+#define TR_MARK(i) { if (threadIdx.x == 0) { const long long t_now = clock64(); t_phase[i] += t_now - t_mark; t_mark = t_now; } }
+#else
+#define TR_MARK(i)
+#endif
+
 // K10.  Dynamic shared memory (layout chosen by launch_track, 0 = the global scratch is used): the two claim arrays
 // [2][smem_claims] and the tentative results + the worklist of the dirty points [smem_points] -- a round then runs out
 // of shared memory instead of paying an L2 round trip per phase (reset, atomicMin, dirty test, recompute).
 __global__ void __launch_bounds__(kResolveThreads) track_resolve_kernel(
     Geometry g, StereoParams sp, TrackParams tp, const int32_t* row_ptr, const uint32_t* kp_xy, const uint8_t* desc,
     const int32_t* n_desc, uint8_t* gone_l, uint8_t* gone_r, const PreviousPoint* __restrict__ previous,
-    int n_previous, int4* tentative, int32_t* claim_l, int32_t* claim_r, TrackRecord* __restrict__ tracks,
-    int32_t* __restrict__ lost, TrackedPoint* __restrict__ tracked, int32_t* __restrict__ stats,
+    int n_previous, int4* tentative, int32_t* claim_l, int32_t* claim_r, int4* __restrict__ final,
+    int32_t* __restrict__ lost, uint8_t* __restrict__ ever_dirty, int32_t* __restrict__ stats,
     const FrameStepState* __restrict__ step, int smem_claims, int smem_points) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ int s_red[32];
@@ -284,16 +291,23 @@ __global__ void __launch_bounds__(kResolveThreads) track_resolve_kernel(
   TrackView vc = v;   // the lattice as point `self` sees it: claims of lower points
   vc.claim_l = claim_l;
   vc.claim_r = claim_r;
-  uint8_t* ever_dirty = reinterpret_cast<uint8_t*>(tracked);   // [n_previous] bytes of the (later written) pre-load array
   for (int u = tid; u < n_previous; u += kResolveThreads) ever_dirty[u] = 0;
   if (tid < 2) s_acc[tid] = 0;
 
+#ifdef VSLAM_TRACK_TIMING
+  long long t_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_mark = clock64();
+  int n_rounds = 0, work_total = 0;
+#endif
   for (int round = 0; round <= n_previous; ++round) {
+#ifdef VSLAM_TRACK_TIMING
+    ++n_rounds;
+#endif
     // claims of the current results; a feature that was gone at entry is gone for everybody (claim -1)
     for (int i = tid; i < n_l; i += kResolveThreads) claim_l[i] = gone_l[i] ? -1 : INT32_MAX;
     for (int i = tid; i < n_r; i += kResolveThreads) claim_r[i] = gone_r[i] ? -1 : INT32_MAX;
     if (tid == 0) s_count = 0, s_changed = 0;
     __syncthreads();
+    TR_MARK(0)
     for (int u = tid; u < n_previous; u += kResolveThreads) {
       const int4 t = load_result(tentative + u);
       if (t.w != kStatusTracked) continue;
@@ -301,6 +315,7 @@ __global__ void __launch_bounds__(kResolveThreads) track_resolve_kernel(
       for_each_consumed_right(v, t.x, t.y, [&](int s) { atomicMin(&claim_r[s], u); });
     }
     __syncthreads();
+    TR_MARK(1)
     // points whose result depends on a feature a lower point removes join the set that is recomputed every round
     for (int u = tid; u < n_previous; u += kResolveThreads) {
       const int4 t = load_result(tentative + u);
@@ -313,7 +328,11 @@ __global__ void __launch_bounds__(kResolveThreads) track_resolve_kernel(
       if (d) worklist[atomicAdd(&s_count, 1)] = u;
     }
     __syncthreads();
+    TR_MARK(2)
     const int n_work = s_count;
+#ifdef VSLAM_TRACK_TIMING
+    work_total += n_work;
+#endif
     if (n_work == 0) break;
     for (int k = tid >> 5; k < n_work; k += kResolveThreads / 32) {
       const int u = *reinterpret_cast<volatile int32_t*>(worklist + k);
@@ -329,15 +348,20 @@ __global__ void __launch_bounds__(kResolveThreads) track_resolve_kernel(
       }
     }
     __syncthreads();
+    TR_MARK(3)
     if (!s_changed) break;   // every point satisfies its own equation: the sequential result
     __syncthreads();
   }
+  TR_MARK(4)
   // the claims of the final results == matched_indices_left / _right of :646-651 (+ the parallax ranges :611-620)
   for (int i = tid; i < n_l; i += kResolveThreads) gone_l[i] = load_claim(claim_l + i) != INT32_MAX;
   for (int i = tid; i < n_r; i += kResolveThreads) gone_r[i] = load_claim(claim_r + i) != INT32_MAX;
   __syncthreads();
 
-  // ordered output: tracks (:623-643), lost points (:660-663), the tracked points as compute() pre-loads them (:147-155)
+  // ordered positions: tracks (:623-643) and lost points (:660-663) keep the order of the previous points.  This CTA
+  // only compacts {previous point, left feature, right feature, distance} of every track into `final` (and the indices of
+  // the lost points); the records themselves -- projections, triangulation, 120 bytes per track -- are written by
+  // track_emit_kernel on the whole device (in this single CTA they cost 10 us per 1000 tracks, measured with clock64).
   int n_tracks = 0, n_lost = 0, landmarks = 0, accumulated = 0;
   for (int u0 = 0; u0 < n_previous; u0 += kResolveThreads) {
     const int u = u0 + tid;
@@ -348,55 +372,21 @@ __global__ void __launch_bounds__(kResolveThreads) track_resolve_kernel(
     const int pos_l = n_lost + block_scan_flag(t.w == kStatusLost, s_red, &total_l);
     if (t.w == kStatusLost) lost[pos_l] = u;
     if (t.w == kStatusTracked) {
-      const PreviousPoint* pp = previous + u;
-      // the projections of this point (visualisation fields :620-626): same arithmetic as track_point
-      double pc[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-        pc[i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(tp.T[4 * i], pp->camera[0]), __dmul_rn(tp.T[4 * i + 1], pp->camera[1])),
-                                    __dmul_rn(tp.T[4 * i + 2], pp->camera[2])), tp.T[4 * i + 3]);
-      const double il0 = __dadd_rn(__dmul_rn(v.fx, pc[0]), __dmul_rn(v.cx, pc[2]));
-      const double il1 = __dadd_rn(__dmul_rn(v.fy, pc[1]), __dmul_rn(v.cy, pc[2]));
-      const int32_t col_l = to_i32(__ddiv_rn(il0, pc[2])), row_l = to_i32(__ddiv_rn(il1, pc[2]));
-      const uint32_t pl = v.xyl[t.x], pr = v.xyr[t.y];
-      const float error_x = __fsub_rn((float)col_l, (float)(pl & 0xffffu));
-      const float error_y = __fsub_rn((float)row_l, (float)(pl >> 16));
-      const double rx = __ddiv_rn(__dadd_rn(il0, v.bx), __dadd_rn(pc[2], 0.0));
-      const double ry = __ddiv_rn(__dadd_rn(il1, 0.0), __dadd_rn(pc[2], 0.0));
-      TrackRecord r;
-      r.index_previous = u;
-      r.index_left = t.x;
-      r.index_right = t.y;
-      r.xl = (float)(pl & 0xffffu);
-      r.yl = (float)(pl >> 16);
-      r.xr = (float)(pr & 0xffffu);
-      r.yr = (float)(pr >> 16);
-      r.distance = t.z;
-      r.epipolar_offset = (int)(pr >> 16) - (int)(pl >> 16);                                     // :616
-      r.projection_left[0] = (float)col_l;
-      r.projection_left[1] = (float)row_l;
-      r.projection_right[0] = (float)rx;
-      r.projection_right[1] = (float)ry;
-      r.projection_right_corrected[0] = (float)to_i32(__dsub_rn(rx, (double)error_x));
-      r.projection_right_corrected[1] = (float)to_i32(__dsub_rn(ry, (double)error_y));
-      r.reserved = 0;
-      triangulate(sp, r.xl, r.yl, r.xr, r.yr, r.camera);
-      tracks[pos_t] = r;
-      TrackedPoint q;
-      q.row = (int)(pl >> 16);
-      q.col = (int)(pl & 0xffffu);
-      q.has_previous = 1;
-      q.reserved = 0;
-      q.disparity = (double)__fsub_rn(r.xl, r.xr);                                               // frame_point.cpp:19
-      q.distance = (double)t.z;
-      tracked[pos_t] = q;
-      atomicAdd(&s_acc[0], pp->has_landmark != 0);                                               // :653-655
+      final[pos_t] = make_int4(u, t.x, t.y, t.z);
+      atomicAdd(&s_acc[0], previous[u].has_landmark != 0);                                       // :653-655
       atomicAdd(&s_acc[1], t.z);                                                                 // :627
     }
     n_tracks += total_t;
     n_lost += total_l;
   }
   __syncthreads();
+  TR_MARK(5)
+#ifdef VSLAM_TRACK_TIMING
+  if (tid == 0)
+    printf("resolve clocks (%d previous, %d + %d features, %d rounds, %d recomputed): reset claims %lld | claim %lld | dirty test %lld | "
+           "recompute %lld | exit %lld | gone flags + ordered output %lld\n", n_previous, n_l, n_r, n_rounds, work_total, t_phase[0],
+           t_phase[1], t_phase[2], t_phase[3], t_phase[4], t_phase[5]);
+#endif
   landmarks = s_acc[0];
   accumulated = s_acc[1];
   if (tid == 0) {
@@ -405,6 +395,68 @@ __global__ void __launch_bounds__(kResolveThreads) track_resolve_kernel(
     stats[2] = landmarks;
     stats[3] = accumulated;
   }
+}
+
+// K10b: the records of the tracks, one thread per track in its final position (`final` of track_resolve_kernel):
+// TrackRecord (:623-643: features, descriptor distance, projections, triangulated camera coordinates) and the bin
+// pre-load record compute() reads (:147-155).
+__global__ void __launch_bounds__(128) track_emit_kernel(Geometry g, StereoParams sp, TrackParams tp, const int32_t* row_ptr,
+                                                         const uint32_t* kp_xy, const uint8_t* desc, const int32_t* n_desc,
+                                                         const PreviousPoint* __restrict__ previous,
+                                                         const int4* __restrict__ final, const int32_t* __restrict__ stats,
+                                                         TrackRecord* __restrict__ tracks, TrackedPoint* __restrict__ tracked,
+                                                         const FrameStepState* __restrict__ step) {
+  const int k = blockIdx.x * 128 + threadIdx.x;
+  if (k >= stats[0]) return;
+  if (step) {   // fused frame: see track_search_kernel
+#pragma unroll
+    for (int i = 0; i < 12; ++i) tp.T[i] = step->T_prior[i];
+  }
+  const TrackView v = make_view(g, sp, row_ptr, kp_xy, desc, n_desc, nullptr, nullptr);
+  const int4 f = final[k];
+  const int u = f.x;
+  const PreviousPoint* pp = previous + u;
+  // the projections of this point (visualisation fields :620-626): same arithmetic as track_point
+  double pc[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    pc[i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(tp.T[4 * i], pp->camera[0]), __dmul_rn(tp.T[4 * i + 1], pp->camera[1])),
+                                __dmul_rn(tp.T[4 * i + 2], pp->camera[2])), tp.T[4 * i + 3]);
+  const double il0 = __dadd_rn(__dmul_rn(v.fx, pc[0]), __dmul_rn(v.cx, pc[2]));
+  const double il1 = __dadd_rn(__dmul_rn(v.fy, pc[1]), __dmul_rn(v.cy, pc[2]));
+  const int32_t col_l = to_i32(__ddiv_rn(il0, pc[2])), row_l = to_i32(__ddiv_rn(il1, pc[2]));
+  const uint32_t pl = v.xyl[f.y], pr = v.xyr[f.z];
+  const float error_x = __fsub_rn((float)col_l, (float)(pl & 0xffffu));
+  const float error_y = __fsub_rn((float)row_l, (float)(pl >> 16));
+  const double rx = __ddiv_rn(__dadd_rn(il0, v.bx), __dadd_rn(pc[2], 0.0));
+  const double ry = __ddiv_rn(__dadd_rn(il1, 0.0), __dadd_rn(pc[2], 0.0));
+  TrackRecord r;
+  r.index_previous = u;
+  r.index_left = f.y;
+  r.index_right = f.z;
+  r.xl = (float)(pl & 0xffffu);
+  r.yl = (float)(pl >> 16);
+  r.xr = (float)(pr & 0xffffu);
+  r.yr = (float)(pr >> 16);
+  r.distance = f.w;
+  r.epipolar_offset = (int)(pr >> 16) - (int)(pl >> 16);                                     // :616
+  r.projection_left[0] = (float)col_l;
+  r.projection_left[1] = (float)row_l;
+  r.projection_right[0] = (float)rx;
+  r.projection_right[1] = (float)ry;
+  r.projection_right_corrected[0] = (float)to_i32(__dsub_rn(rx, (double)error_x));
+  r.projection_right_corrected[1] = (float)to_i32(__dsub_rn(ry, (double)error_y));
+  r.reserved = 0;
+  triangulate(sp, r.xl, r.yl, r.xr, r.yr, r.camera);
+  tracks[k] = r;
+  TrackedPoint q;
+  q.row = (int)(pl >> 16);
+  q.col = (int)(pl & 0xffffu);
+  q.has_previous = 1;
+  q.reserved = 0;
+  q.disparity = (double)__fsub_rn(r.xl, r.xr);                                               // frame_point.cpp:19
+  q.distance = (double)f.w;
+  tracked[k] = q;
 }
 
 // ---- recoverPoints ---------------------------------------------------------------------------------------------
@@ -541,8 +593,12 @@ void launch_track(const Geometry& g, const StereoParams& sp, const Buffers& b, i
   }
   track_resolve_kernel<<<1, kResolveThreads, smem, stream>>>(g, sp, tp, row_ptr, kp_xy, desc, n_desc, gone_l, gone_r,
                                                              previous, n_previous, s.tentative, s.claim_l, s.claim_r,
-                                                             tracks, lost, tracked, s.stats, step, smem_claims,
-                                                             smem_points);
+                                                             s.final, lost, reinterpret_cast<uint8_t*>(tracked), s.stats,
+                                                             step, smem_claims, smem_points);
+  // (`tracked` doubles as the resolve kernel's per-point dirty flags: one byte per previous point of a 32-byte record)
+  if (n_previous > 0)
+    track_emit_kernel<<<(n_previous + 127) / 128, 128, 0, stream>>>(g, sp, tp, row_ptr, kp_xy, desc, n_desc, previous, s.final,
+                                                                    s.stats, tracks, tracked, step);
 }
 
 void launch_recover(const Geometry& g, const StereoParams& sp, const Buffers& b, int pair, const uint8_t* blurred,
