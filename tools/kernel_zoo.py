@@ -65,6 +65,24 @@ def fpg_sequence(cfg_name, frames, seed=5):
     gen.close()
 
 
+def frame_steps(cfg_name, frames, seed=7):
+    """vslam_fpg_frame_step: the tracked frame as one graph (compact_frame / track_search / track_resolve / track_emit /
+    converge_cluster with initialize + prune / match / select_strips<32> / frame_assemble)"""
+    cfg, acfg = configs.BY_NAME[cfg_name], configs.ALIGNER_BY_NAME[cfg_name]
+    cam = synth.camera(cfg.camera)
+    world = synth.BandWorld(cam.cols, cam.rows, seed, max_frames=frames + 1)
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    gen.frame_step_reset()
+    T = np.hstack([np.eye(3), np.zeros((3, 1))])
+    T[0, 3] = -(-cam.bx / cam.fx) / 4
+    for k in range(frames):
+        left, right = world.pair(k)
+        r = gen.frame_step(left, right, k == 0, T, acfg, False, 15, 25.6, publish_frame_points=True)
+        print("%s fused frame %d: previous %d tracks %d new %d rounds %d" % (cfg_name, k, r["n_previous"], r["n_tracks"],
+                                                                           r["n_new_points"], r["aligner_rounds"]), flush=True)
+    gen.close()
+
+
 def fpg_batch(cfg_name, n, rounds=2):
     cfg = configs.BY_NAME[cfg_name]
     cam = synth.camera(cfg.camera)
@@ -116,11 +134,13 @@ def main():
     if a.profile:
         fpg_batch("kitti_fast", 64, rounds=2)
         fpg_sequence("kitti", 3)
+        frame_steps("kitti", 4)
         aligner("stereouv", 4_000_000)
         aligner("uvd", 4_000_000)
         landmarks(20000, 100)
     else:
         fpg_sequence("euroc", 3)
+        frame_steps("euroc", 3)
         fpg_batch("kitti_fast", 2)
         aligner("stereouv", 3000)
         aligner("uvd", 3000)
