@@ -158,7 +158,9 @@ struct vslam_fpg {
   int32_t* d_step_kept_pos = nullptr;
   uint8_t* h_step = nullptr;             // pinned + mapped result block
   uint8_t* h_step_device = nullptr;      // its device address
-  double* h_step_T = nullptr;            // pinned [12]: the motion prior a copy node of the graph reads
+  double* h_step_T = nullptr;            // pinned [13]: the motion prior + {frame number, 0} a copy node of the graph reads
+  int32_t step_frame_id = 0;
+  bool step_poll = true;                 // VSLAM_FRAME_STEP_SYNC=1: wait with cudaStreamSynchronize instead of polling
   size_t step_off_tracks = 0, step_off_kept = 0, step_off_errors = 0, step_off_inliers = 0, step_off_lost = 0,
          step_off_points = 0, step_off_frame_points = 0;
   cudaGraphExec_t step_graph[2] = {nullptr, nullptr};   // [localizing]
@@ -1140,7 +1142,8 @@ static int setup_frame_step(vslam_fpg* h) {
   CUDA_TRY(cudaHostAlloc((void**)&h->h_step, off, cudaHostAllocMapped));
   std::memset(h->h_step, 0, off);
   CUDA_TRY(cudaHostGetDevicePointer((void**)&h->h_step_device, h->h_step, 0));
-  CUDA_TRY(cudaMallocHost((void**)&h->h_step_T, sizeof(double) * 12));
+  CUDA_TRY(cudaMallocHost((void**)&h->h_step_T, sizeof(double) * 13));
+  h->step_poll = std::getenv("VSLAM_FRAME_STEP_SYNC") == nullptr;
   CUDA_TRY(cudaHostGetDevicePointer((void**)&h->h_status_device, h->h_status, 0));
   h->step_cluster_blocks = blocks;
   h->step_cap = cap;
@@ -1200,7 +1203,7 @@ static int issue_frame_step(vslam_fpg* h, Lane& lane, size_t stride, const vslam
     cudaStream_t s = beside ? h->side_stream : lane.stream;
     if (beside) order_after(h, lane.stream, s, 0);
     CUDA_TRY(cudaMemcpyAsync(h->d_thr, h->h_thr, sizeof(int32_t) * g.n_regions, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(h->d_step, h->h_step_T, sizeof(double) * 12, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->d_step, h->h_step_T, sizeof(double) * 13, cudaMemcpyHostToDevice, s));   // T_prior, frame_id, ticket = 0
     launch_repitch(g, lane.stage, lane.stage + lane.stage_bytes, (int)stride, h->b.image, 1, lane.stream,
                    h->b.raw_count, 2 * g.n_regions);
     ++h->launches;
@@ -1333,6 +1336,12 @@ int vslam_fpg_frame_step(vslam_fpg* h, const uint8_t* left, const uint8_t* right
     h->h_thr[i] = std::min(std::max(t, 0), 255);
   }
   for (int i = 0; i < 12; ++i) h->h_step_T[i] = T_prior[i];
+  const int32_t frame_id = h->step_frame_id = (h->step_frame_id % 0x3fffffff) + 1;   // never 0
+  {
+    int32_t* tail = reinterpret_cast<int32_t*>(h->h_step_T + 12);
+    tail[0] = frame_id;
+    tail[1] = 0;
+  }
   h->sp.localizing = L;
   h->localizing = L;
   static const bool use_graph = std::getenv("VSLAM_NO_FRAME_GRAPH") == nullptr;
@@ -1369,11 +1378,22 @@ int vslam_fpg_frame_step(vslam_fpg* h, const uint8_t* left, const uint8_t* right
   } else if ((rc = issue_frame_step(h, lane, stride, *p))) {
     return rc;
   }
-  CUDA_TRY(cudaStreamSynchronize(lane.stream));
+  const FrameStepHeader* hd = reinterpret_cast<const FrameStepHeader*>(h->h_step);
+  // The last kernel echoes the frame number into the pinned header once every block has published its share
+  // (frame_assemble_kernel): polling that word returns a few microseconds before the stream reports idle.  The stream is
+  // asked now and then, so an error or a device that never answers still ends in cudaStreamSynchronize.
+  bool complete = false;
+  if (h->step_poll && !h->profiling) {
+    const volatile int32_t* done = &hd->done_frame;
+    for (uint32_t spins = 1; !complete; ++spins) {
+      complete = *done == frame_id;
+      if (!complete && (spins & 0x3ffu) == 0 && cudaStreamQuery(lane.stream) != cudaErrorNotReady) break;
+    }
+  }
+  if (!complete) CUDA_TRY(cudaStreamSynchronize(lane.stream));
   CUDA_TRY(cudaGetLastError());
   collect_clock(h, true, true);
   if (h->profiling) add_interval(h, kKTrack, kEvTrack0, kEvTrack1, 2);
-  const FrameStepHeader* hd = reinterpret_cast<const FrameStepHeader*>(h->h_step);
   if ((rc = check_flag(h)) || hd->overflow) {
     cudaMemset(h->b.error_flag, 0, sizeof(int32_t));
     cudaMemset(h->d_step, 0, sizeof(FrameStepState));   // the device-resident points are not usable: a new sequence

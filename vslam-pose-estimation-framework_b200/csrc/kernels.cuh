@@ -69,6 +69,8 @@ struct TrackParams {
 // the motion prior and the point counts the stages hand to each other -- lives here instead of in kernel arguments.
 struct FrameStepState {
   double T_prior[12];      // camera_left_previous_in_current of this frame (copy node of the graph, from pinned memory)
+  int32_t frame_id;        // (same copy) the host's number of this frame, echoed into the result header when it is complete
+  int32_t ticket;          // (same copy: 0) blocks of the last kernel that have published their share
   int32_t n_previous;      // points() of the previous frame held in `previous` (written by frame_assemble_kernel)
   int32_t n_kept;          // tracks that survive _prunePoints (frame_prune_kernel)
   int32_t inliers_only;    // the branch of pose_tracker_3d.cpp:441 taken by frame_prune_kernel
@@ -248,6 +250,8 @@ struct FrameStepHeader {
   int32_t n_points;        // points() of this frame = n_kept + new framepoints
   GnControl ctl;           // pose, damped H, rounds, converged
   double system[32];       // last linearisation: H upper triangle, b, total error, inliers
+  int32_t done_frame;      // == the frame_id of the call once EVERYTHING of the frame is in this block (written last)
+  int32_t reserved;
 };
 struct FrameStepBuffers {
   FrameStepState* state;
