@@ -84,6 +84,7 @@ struct vslam_fpg {
   int32_t* h_flag = nullptr;
   int32_t* d_status = nullptr;   // [error_flag, pad | n_desc 2B | raw_count 2B x regions]; b.error_flag / n_desc / raw_count point into it
   int32_t* h_status = nullptr;   // pinned mirror; h_flag / h_n_desc / h_counts point into it
+  int32_t* d_step_bins = nullptr;       // [rows_bin * cols_bin + 1] winners of the match replay (fused frame)
   int32_t* h_status_device = nullptr;   // the same words as the device addresses them (written by the fused frame)
   // state of the last single-pair initialize / last batch
   bool initialized = false;
@@ -733,6 +734,7 @@ int vslam_fpg_destroy(vslam_fpg* h) {
   invalidate_step_graphs(h);
   cudaFree(h->d_step); cudaFree(h->d_step_ctl); cudaFree(h->d_step_planes); cudaFree(h->d_step_errors);
   cudaFree(h->d_step_inliers); cudaFree(h->d_step_system); cudaFree(h->d_step_track_length); cudaFree(h->d_step_kept_pos);
+  cudaFree(h->d_step_bins);
   cudaFreeHost(h->h_step); cudaFreeHost(h->h_step_T);
   cudaFreeHost(h->h_thr);
   cudaFree(h->d_thr);
@@ -1130,6 +1132,7 @@ static int setup_frame_step(vslam_fpg* h) {
   CUDA_TRY(cudaMalloc((void**)&h->d_step_system, sizeof(double) * 32));
   CUDA_TRY(cudaMalloc((void**)&h->d_step_track_length, sizeof(int32_t) * C));
   CUDA_TRY(cudaMalloc((void**)&h->d_step_kept_pos, sizeof(int32_t) * C));
+  CUDA_TRY(cudaMalloc((void**)&h->d_step_bins, sizeof(int32_t) * ((size_t)h->g.rows_bin * h->g.cols_bin + 1)));
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   size_t off = up(sizeof(FrameStepHeader));
   h->step_off_tracks = off;        off = up(off + sizeof(TrackRecord) * C);
@@ -1239,7 +1242,15 @@ static int issue_frame_step(vslam_fpg* h, Lane& lane, size_t stride, const vslam
       ++h->launches;
     }
   };
+  // ... and so does the replay of the matches over the bins: every pre-loaded point of a fused frame has previous(), so
+  // a surviving track simply empties its bin afterwards (select_strips_kernel, kSelectMerge)
+  const bool split_select = branches && select_strips_available(g);
   if (branches) match_passes(side);
+  if (split_select) {
+    launch_select(g, h->sp, h->b, 0, 1, h->n_passes, nullptr, 0, h->d_out, h->out_cap, false, side, nullptr, kSelectReplay,
+                  h->d_step_bins);
+    ++h->launches;
+  }
   AlignerCamera cam;
   const double K[9] = {h->sp.fx, 0, h->sp.cx, 0, h->sp.fy, h->sp.cy, 0, 0, 1};
   for (int i = 0; i < 9; ++i) cam.K[i] = K[i];
@@ -1267,7 +1278,7 @@ static int issue_frame_step(vslam_fpg* h, Lane& lane, size_t stride, const vslam
   if (!branches) match_passes(lane.stream);
   mark(h, lane, kEvMatch1);
   launch_select(g, h->sp, h->b, 0, 1, h->n_passes, h->d_tracked, 0, h->d_out, h->out_cap, false, lane.stream,
-                &h->d_step->n_kept);
+                &h->d_step->n_kept, split_select ? kSelectMerge : kSelectAll, h->d_step_bins);
   mark(h, lane, kEvSelect1);
   if (branches) {
     order_after(h, side, lane.stream, 1);

@@ -127,7 +127,11 @@ void launch_match(const Geometry& g, const StereoParams& sp, const Buffers& b, i
 void launch_select(const Geometry& g, const StereoParams& sp, const Buffers& b, int first_pair, int n_pairs,
                    int n_passes, const TrackedPoint* tracked, int n_tracked, FramePointRecord* out,
                    int out_capacity_per_pair, bool generic, cudaStream_t stream,
-                   const int32_t* n_tracked_device = nullptr);
+                   const int32_t* n_tracked_device = nullptr, int mode = 0, int32_t* bins = nullptr);
+// fused frame: the strip kernel in two halves (kSelectReplay beside the aligner -> bins[rows_bin * cols_bin + 1],
+// kSelectMerge after the prune); only where the strip kernel serves the bin grid
+enum { kSelectAll = 0, kSelectReplay = 1, kSelectMerge = 2 };
+bool select_strips_available(const Geometry& g);
 void launch_emit_matches(const Geometry& g, const StereoParams& sp, const Buffers& b, int pair, int n_passes,
                          FramePointRecord* out, int out_capacity, int32_t* n_out, cudaStream_t stream);
 int kernels_per_match_pass();

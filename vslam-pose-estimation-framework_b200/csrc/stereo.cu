@@ -293,9 +293,15 @@ __global__ void __launch_bounds__(kSelectWarps * 32) select_strips_kernel(
     Geometry g, StereoParams sp, const int32_t* __restrict__ row_ptr, const uint32_t* __restrict__ kp_xy,
     const int32_t* __restrict__ n_desc, const int2* __restrict__ match, int n_passes,
     const TrackedPoint* __restrict__ tracked, int n_tracked, FramePointRecord* __restrict__ out, int out_cap,
-    int32_t* __restrict__ n_out, int32_t* __restrict__ error_flag, const int32_t* __restrict__ n_tracked_device) {
+    int32_t* __restrict__ n_out, int32_t* __restrict__ error_flag, const int32_t* __restrict__ n_tracked_device,
+    int mode, int32_t* __restrict__ bins) {
+  // mode (fused frame, one pair): kSelectAll = everything; kSelectReplay = the replay of the matches over EMPTY bins, the
+  // winners go to bins[] (+ the match count in bins[n_bins]) -- it needs neither the aligner nor the prune and runs beside
+  // them; kSelectMerge = bins[] minus the bins a surviving track occupies, then the ordered output.  Every pre-loaded point
+  // of a fused frame has previous(): no match can take its bin (:383), and it is not appended itself (:443) -- its bin is
+  // simply empty in the output, whatever the replay put there.
   extern __shared__ __align__(16) unsigned char s_raw[];
-  if (n_tracked_device) n_tracked = *n_tracked_device;   // fused frame: the count of the device-side _prunePoints
+  if (n_tracked_device && mode != kSelectReplay) n_tracked = *n_tracked_device;   // fused frame: the count of the device-side _prunePoints
   const int n_bins = g.rows_bin * g.cols_bin;
   int* s_win = reinterpret_cast<int*>(s_raw);
   float* s_disp = reinterpret_cast<float*>(s_win + n_bins);
@@ -313,9 +319,21 @@ __global__ void __launch_bounds__(kSelectWarps * 32) select_strips_kernel(
   FramePointRecord* o = out + (size_t)pair * out_cap;
   const int bs = g.bin_size;
 
+  if (mode == kSelectMerge) {
+    for (int i = tid; i < n_bins; i += kSelectWarps * 32) s_win[i] = bins[i];
+    if (tid == 0) s_matches = bins[n_bins];
+    __syncthreads();
+    for (int k = tid; k < n_tracked; k += kSelectWarps * 32) {
+      const TrackedPoint t = tracked[k];
+      const int trb = bin_of(t.row, bs), tcb = bin_of(t.col, bs);
+      if (trb < g.rows_bin && tcb < g.cols_bin) s_win[trb * g.cols_bin + tcb] = INT32_MIN;
+    }
+    __syncthreads();
+  } else {
   for (int i = tid; i < n_bins; i += kSelectWarps * 32) s_win[i] = INT32_MIN;
   if (tid == 0) s_matches = 0;
   __syncthreads();
+  if (mode == kSelectReplay) n_tracked = 0;
   // :147-155 pre-load, in order: a later tracked point overwrites an earlier one in the same bin, i.e. the LAST point
   // of a bin wins.  Two parallel passes: atomicMax of the point index per bin (indices are stored as -(k+1) < 0, so the
   // last point is the MINIMUM of the stored values; INT32_MIN = empty is kept apart by the first pass writing through
@@ -346,6 +364,7 @@ __global__ void __launch_bounds__(kSelectWarps * 32) select_strips_kernel(
     if (v != 0x80000000u) s_win[i] = -(int)(v & 0x7fffffffu);
   }
   __syncthreads();
+  }
 
   int my_matches = 0;
   for (int rb = warp; rb < g.rows_bin; rb += kSelectWarps) {
@@ -354,11 +373,11 @@ __global__ void __launch_bounds__(kSelectWarps * 32) select_strips_kernel(
     while (r_lo <= r_hi && bin_of(r_lo, bs) != rb) ++r_lo;
     while (r_hi >= r_lo && bin_of(r_hi, bs) != rb) --r_hi;
     int winners = 0;
-    if (r_lo <= r_hi) {
+    int* win = s_win + rb * g.cols_bin;
+    float* wdist = s_dist + rb * g.cols_bin;
+    if (mode != kSelectMerge && r_lo <= r_hi) {
       const int f_lo = rpl[r_lo], f_hi = rpl[r_hi + 1];
-      int* win = s_win + rb * g.cols_bin;
       float* wdisp = s_disp + rb * g.cols_bin;
-      float* wdist = s_dist + rb * g.cols_bin;
       for (int pass = 0; pass < n_passes; ++pass) {
         // four chunks of 32 features per trip: their (independent) loads are issued together, so a strip pays the
         // global-memory latency of m -> xy_right once per 128 features instead of once per 32
@@ -412,22 +431,27 @@ __global__ void __launch_bounds__(kSelectWarps * 32) select_strips_kernel(
           }
         }
       }
-      // :443 only points without previous() are appended; tracked survivors without previous() are reported
-      for (int c0 = 0; c0 < g.cols_bin; c0 += 32) {
-        const int c = c0 + lane;
-        bool on = false;
-        if (c < g.cols_bin) {
-          const int w = win[c];
-          on = w != INT32_MIN && !(w < 0 && wdist[c] < 0.0f);
-          if (!on) win[c] = INT32_MIN;
-        }
-        winners += __popc(__ballot_sync(0xffffffffu, on));
+    }
+    // :443 only points without previous() are appended; tracked survivors without previous() are reported
+    for (int c0 = 0; c0 < g.cols_bin; c0 += 32) {
+      const int c = c0 + lane;
+      bool on = false;
+      if (c < g.cols_bin) {
+        const int w = win[c];
+        on = w != INT32_MIN && (mode == kSelectMerge || !(w < 0 && wdist[c] < 0.0f));
+        if (!on) win[c] = INT32_MIN;
+        if (mode == kSelectReplay) bins[rb * g.cols_bin + c] = on ? w : INT32_MIN;
       }
+      winners += __popc(__ballot_sync(0xffffffffu, on));
     }
     if (lane == 0) s_cnt[rb] = winners;
   }
   if (lane == 0 && my_matches) atomicAdd(&s_matches, my_matches);
   __syncthreads();
+  if (mode == kSelectReplay) {
+    if (tid == 0) bins[n_bins] = s_matches;
+    return;
+  }
   if (warp == 0) {   // exclusive scan of the strip counts
     int carry = 0;
     for (int r0 = 0; r0 < g.rows_bin; r0 += 32) {
@@ -541,9 +565,14 @@ void launch_match(const Geometry& g, const StereoParams& sp, const Buffers& b, i
                                          b.consumed_r + (size_t)first_pair * g.cap, pass, epipolar_offset);
 }
 
+bool select_strips_available(const Geometry& g) {
+  return (size_t)g.rows_bin * g.cols_bin * 12 + (size_t)(g.rows_bin + 1) * 4 <= 160 * 1024;
+}
+
 void launch_select(const Geometry& g, const StereoParams& sp, const Buffers& b, int first_pair, int n_pairs,
                    int n_passes, const TrackedPoint* tracked, int n_tracked, FramePointRecord* out,
-                   int out_capacity_per_pair, bool generic, cudaStream_t stream, const int32_t* n_tracked_device) {
+                   int out_capacity_per_pair, bool generic, cudaStream_t stream, const int32_t* n_tracked_device,
+                   int mode, int32_t* bins) {
   // shared state of the strip kernel: 12 B per bin + one counter per bin row
   const size_t smem = (size_t)g.rows_bin * g.cols_bin * 12 + (size_t)(g.rows_bin + 1) * 4;
   if (!generic && smem <= 160 * 1024) {
@@ -556,7 +585,7 @@ void launch_select(const Geometry& g, const StereoParams& sp, const Buffers& b, 
         g, sp, b.row_ptr + (size_t)2 * first_pair * (g.rows + 1), b.kp_xy + (size_t)2 * first_pair * g.cap,
         b.n_desc + 2 * first_pair, b.match + (size_t)first_pair * g.cap, n_passes, tracked, n_tracked,
         out + (size_t)first_pair * out_capacity_per_pair, out_capacity_per_pair, b.n_out + 2 * first_pair, b.error_flag,
-        n_tracked_device);
+        n_tracked_device, mode, bins);
     return;
   }
   select_kernel<<<n_pairs, 256, 0, stream>>>(g, sp, b.row_ptr + (size_t)2 * first_pair * (g.rows + 1),
