@@ -66,7 +66,7 @@ def launches(path):
     # the kernels of ONE bench step (the other launches belong to bench.py's aligner_stress / sequence sections and to
     # the e2e repitch): their shares are what roofline.kernel_share_of_step must agree with
     step = ("fast_nms_kernel", "compact_kernel", "blur_kernel", "describe_tile_kernel", "match_kernel",
-            "select_strips_kernel", "linearize_pairs_kernel")
+            "select_strips_kernel", "select_strips_kernel<16>", "linearize_pairs_kernel")
     stot = sum(agg[k][1] for k in step if k in agg)
     if stot:
         print()

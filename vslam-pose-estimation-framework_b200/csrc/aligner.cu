@@ -401,6 +401,7 @@ __device__ __forceinline__ void solve6_warp(double (*A)[8], double x[6]) {
 // damped system, full-pivot solve, pose update, bookkeeping in *ctl (global memory in the grid kernel, shared memory in
 // the cluster kernel).  Called by the WHOLE first warp of the block (the solve is warp-cooperative).
 // `s_A` is the solver's [6][8] scratch in shared memory.
+template <bool kControlInGlobalMemory>
 __device__ __forceinline__ void gn_step(GnControl* ctl, const double* s_sys, const double* s_T, double (*s_A)[8], int n,
                                         const GnParams& p) {
   const int lane = threadIdx.x & 31;
@@ -464,7 +465,7 @@ __device__ __forceinline__ void gn_step(GnControl* ctl, const double* s_sys, con
   ctl->iteration = it;
   ctl->ignore = phase;
   ctl->converged = converged;
-  __threadfence();
+  if (kControlInGlobalMemory) __threadfence();   // (other blocks read it after the grid barrier)
   ctl->done = done;
   GN_CLK(6);
 }
@@ -528,7 +529,7 @@ __global__ void __launch_bounds__(kThreads) converge_kernel(int n, AlignerBuffer
         }
         __syncthreads();
       }
-      if (threadIdx.x < 32) gn_step(ctl, s_sys, s_T, s_A, n, p);
+      if (threadIdx.x < 32) gn_step<true>(ctl, s_sys, s_T, s_A, n, p);
     }
     grid.sync();
     if (__ldcg(&ctl->done)) break;
@@ -687,7 +688,7 @@ __global__ void __launch_bounds__(kThreads, 1) converge_cluster_kernel(int n, Al
       __syncthreads();
     }
     GN_MARK(4)
-    if (threadIdx.x < 32) gn_step(&s_ctl, s_sys, s_T, s_A, n, p);
+    if (threadIdx.x < 32) gn_step<false>(&s_ctl, s_sys, s_T, s_A, n, p);
     GN_MARK(5)
     __syncthreads();
     if (s_ctl.done) break;
