@@ -563,6 +563,8 @@ def sequence_latency(api, configs, synth, device):
         out[name]["tracked_native"] = native_sequence(cfg, cam, frames)
         # ... and the frame as one device pass (vslam_fpg_frame_step)
         out[name]["tracked_fused"] = native_sequence(cfg, cam, frames, fused=True)
+        # ... with the next frame's images uploaded while the current frame runs (vslam_fpg_frame_step_prefetch)
+        out[name]["tracked_fused_prefetch"] = native_sequence(cfg, cam, frames, fused=2)
     return out
 
 
@@ -582,17 +584,24 @@ def sequence_multi(configs, synth, rank, world, device, barrier, dist, torch, de
     barrier()
     mine_fused = native_sequence(cfg, cam, frames, passes=passes, device=device, fused=True)
     barrier()
+    alone_prefetch = native_sequence(cfg, cam, frames, passes=passes, device=device, fused=2) if rank == 0 else None
+    barrier()
+    mine_prefetch = native_sequence(cfg, cam, frames, passes=passes, device=device, fused=2)
+    barrier()
     fps = float(mine["frames_per_s"]) if mine else 0.0
     fps_fused = float(mine_fused["frames_per_s"]) if mine_fused else 0.0
+    fps_prefetch = float(mine_prefetch["frames_per_s"]) if mine_prefetch else 0.0
     if dist is not None:
-        t = torch.zeros(2 * world, dtype=torch.float64, device=dev)
+        t = torch.zeros(3 * world, dtype=torch.float64, device=dev)
         t[rank] = fps
         t[world + rank] = fps_fused
+        t[2 * world + rank] = fps_prefetch
         dist.all_reduce(t)
         per_rank = [float(x) for x in t.tolist()[:world]]
-        per_rank_fused = [float(x) for x in t.tolist()[world:]]
+        per_rank_fused = [float(x) for x in t.tolist()[world:2 * world]]
+        per_rank_prefetch = [float(x) for x in t.tolist()[2 * world:]]
     else:
-        per_rank, per_rank_fused = [fps], [fps_fused]
+        per_rank, per_rank_fused, per_rank_prefetch = [fps], [fps_fused], [fps_prefetch]
     if rank != 0:
         return None
     out = {"workload": "%d-frame 1920x1080 band-world sequence per GPU (seeds 8000 + rank), bin 23, FAST thr 20..100; "
@@ -604,7 +613,14 @@ def sequence_multi(configs, synth, rank, world, device, barrier, dist, torch, de
            "fused": {"per_rank_frames_per_s": per_rank_fused, "aggregate_frames_per_s": sum(per_rank_fused),
                      "rank0_alone": alone_fused, "rank0_concurrent": mine_fused,
                      "efficiency": (sum(per_rank_fused) / len(per_rank_fused)) / alone_fused["frames_per_s"]
-                     if alone_fused else None}}
+                     if alone_fused else None},
+           "fused_prefetch": {"what": "fused frames, the images of frame k + 1 uploaded while frame k runs "
+                                      "(vslam_fpg_frame_step_prefetch)",
+                              "per_rank_frames_per_s": per_rank_prefetch,
+                              "aggregate_frames_per_s": sum(per_rank_prefetch),
+                              "rank0_alone": alone_prefetch, "rank0_concurrent": mine_prefetch,
+                              "efficiency": (sum(per_rank_prefetch) / len(per_rank_prefetch))
+                              / alone_prefetch["frames_per_s"] if alone_prefetch else None}}
     return out
 
 

@@ -304,6 +304,13 @@ int vslam_fpg_frame_step_set_previous(vslam_fpg* h, const vslam_previous_point* 
 int vslam_fpg_frame_step(vslam_fpg* h, const uint8_t* left, const uint8_t* right, size_t stride_bytes, int localizing,
                          const double previous_to_current_prior[12], const vslam_frame_step_parameters* parameters,
                          vslam_frame_step_result* result);
+/* Upload of the NEXT frame's images while the current frame runs (a host that replays a sequence knows them: the reference's
+ * playback, executables/app.cpp, reads them from disk).  Asynchronous on a copy stream of the handle; the images must stay
+ * valid (and should be page-locked, vslam_host_alloc) until the vslam_fpg_frame_step that consumes them returns.  Staged
+ * pairs are consumed oldest first by vslam_fpg_frame_step with left == right == NULL (stride_bytes is then ignored); at most
+ * two pairs are staged (VSLAM_ERR_STATE beyond), and a call WITH images while a pair is staged is VSLAM_ERR_STATE too.
+ * vslam_fpg_frame_step_reset drops staged pairs.  Results do not depend on how the images arrived. */
+int vslam_fpg_frame_step_prefetch(vslam_fpg* h, const uint8_t* left, const uint8_t* right, size_t stride_bytes);
 
 /* pass as n_tracked (tracked = NULL) to vslam_fpg_compute: the tracked points are those of the last
  * vslam_fpg_track, already resident on the device (no host round trip of the bin pre-load records) */

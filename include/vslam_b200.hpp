@@ -164,6 +164,11 @@ class StereoFramePointGenerator {
     _tracks_resident = false;
     return r;
   }
+  // the images of the NEXT frame, uploaded while the current one runs (vslam_fpg_frame_step_prefetch); the trackFrame()
+  // that consumes them is called with frame->intensity_image_left == frame->intensity_image_right == nullptr
+  void prefetchFrame(const uint8_t* left, const uint8_t* right, size_t image_step) {
+    check(vslam_fpg_frame_step_prefetch(_handle, left, right, image_step), "StereoFramePointGenerator::prefetchFrame");
+  }
   // a new sequence: the next trackFrame() has no previous points
   void resetSequence() { check(vslam_fpg_frame_step_reset(_handle), "StereoFramePointGenerator::resetSequence"); }
 

@@ -174,3 +174,46 @@ def test_frame_step_needs_binning():
     with pytest.raises(api.VslamError):
         gen.frame_step(left, right, True, _prior(cam), configs.KITTI_ALIGNER, False, 25, 40.0)
     gen.close()
+
+
+def test_prefetched_frames_give_the_same_results_and_the_inbox_rules_hold():
+    """vslam_fpg_frame_step_prefetch: the images of frame k + 1 travel while frame k runs (two inbox buffers, a copy
+    stream); the results equal the stepwise calls frame by frame, mixed with frames that bring their own images"""
+    cfg, acfg = configs.KITTI, configs.KITTI_ALIGNER
+    cam = synth.camera(cfg.camera)
+    frames = 7
+    world = synth.BandWorld(cam.cols, cam.rows, 91, max_frames=frames)
+    pairs = [world.pair(k) for k in range(frames)]
+    D, max_distance = 25, 40.0
+    ref = Stepwise(cfg, acfg, cam, D, max_distance)
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    gen.frame_step_reset()
+    T = _prior(cam)
+    with pytest.raises(api.VslamError):          # nothing staged
+        gen.frame_step(None, None, True, T, acfg, False, D, max_distance)
+    own_images = 4                               # this frame is not prefetched: it brings its own images
+    gen.frame_step_prefetch(*pairs[0])
+    for k in range(frames):
+        ahead = k + 1 < frames and k + 1 != own_images and k != own_images
+        if ahead:                                # frame k + 1 travels while frame k runs
+            gen.frame_step_prefetch(*pairs[k + 1])
+        want = ref.step(*pairs[k], k == 0, T)
+        if k == own_images:
+            got = gen.frame_step(*pairs[k], False, T, acfg, False, D, max_distance)
+            gen.frame_step_prefetch(*pairs[k + 1])
+        else:
+            got = gen.frame_step(None, None, k == 0, T, acfg, False, D, max_distance)
+        _compare(k, got, want, gen, True)
+        assert np.array_equal(gen.thresholds, ref.gen.thresholds), k
+    # two staged pairs at most; a frame with images while a pair is staged is refused; reset drops staged pairs
+    gen.frame_step_prefetch(*pairs[0])
+    gen.frame_step_prefetch(*pairs[1])
+    with pytest.raises(api.VslamError):
+        gen.frame_step_prefetch(*pairs[2])
+    with pytest.raises(api.VslamError):
+        gen.frame_step(*pairs[2], False, T, acfg, False, D, max_distance)
+    gen.frame_step_reset()
+    with pytest.raises(api.VslamError):
+        gen.frame_step(None, None, True, T, acfg, False, D, max_distance)
+    ref.close()
+    gen.close()

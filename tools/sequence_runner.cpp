@@ -7,6 +7,8 @@
 //   sequence_runner <frames.u8> <n_frames> <warmup> <24 configuration numbers, see below> [passes [fused]]
 // fused = 1: the same per-frame order as ONE device pass per frame (vslam_fpg_frame_step through
 // StereoFramePointGenerator::trackFrame: one graph launch and one synchronisation, points() resident on the device).
+// fused = 2: the same, and the images of frame k + 1 are uploaded while frame k runs (prefetchFrame: a replayed sequence
+// knows its next frame, as the reference's playback from disk does).
 // passes > 1 replays the sequence from its first frame (fresh tracker state) so that a short sequence gives a timed
 // region long enough to overlap with the other GPUs' runs (BASELINE configs[4]: one sequence per GPU).
 // frames.u8: [n_frames][2][rows][cols] u8.  Prints one JSON object.
@@ -50,7 +52,8 @@ int main(int argc, char** argv) {
     ap.minimum_number_of_inliers = std::atoi(a[22]);
     const double maximum_reliable_depth = std::atof(a[23]);
     const int passes = argc >= 4 + 25 ? std::atoi(a[24]) : 1;
-    const bool fused = argc == 4 + 26 && std::atoi(a[25]) != 0;
+    const int fused_mode = argc == 4 + 26 ? std::atoi(a[25]) : 0;
+    const bool fused = fused_mode != 0, prefetch = fused_mode == 2;
     vslam_frame_step_parameters fsp = {};
     fsp.track_by_appearance = 0;
     fsp.projection_tracking_distance_pixels = tracking_distance;
@@ -99,6 +102,7 @@ int main(int argc, char** argv) {
     for (int pass = 0; pass < passes; ++pass) {
     have_previous = false;
     if (fused) generator.resetSequence();
+    if (prefetch) generator.prefetchFrame(frames, frames + image_bytes, (size_t)c.cols);
     for (int k = 0; k < n_frames; ++k) {
       const auto t0 = std::chrono::steady_clock::now();
       current.status = k == 0 ? vslam::Frame::Localizing : vslam::Frame::Tracking;
@@ -107,6 +111,12 @@ int main(int argc, char** argv) {
       current.image_step = (size_t)c.cols;
       current.tracks.clear();
       if (fused) {
+        if (prefetch) {   // frame k was staged by the previous iteration; frame k + 1 travels while k runs
+          if (k + 1 < n_frames)
+            generator.prefetchFrame(frames + (size_t)(2 * k + 2) * image_bytes, frames + (size_t)(2 * k + 3) * image_bytes,
+                                    (size_t)c.cols);
+          current.intensity_image_left = current.intensity_image_right = nullptr;
+        }
         // the whole frame on the device; trackFrame copies tracks / points / points() of the frame out of the pinned block
         const vslam_frame_step_result r = generator.trackFrame(&current, motion, fsp);
         const auto t1 = std::chrono::steady_clock::now();
@@ -199,7 +209,7 @@ int main(int argc, char** argv) {
                 timed / seconds, seconds / timed * 1e3, (double)n_previous / timed, (double)n_tracks / timed,
                 (double)n_new / timed, timed, s_initialize / timed * 1e6, s_track / timed * 1e6, s_align / timed * 1e6,
                 s_compute / timed * 1e6, s_assemble / timed * 1e6, (double)n_rounds / timed, (double)n_inliers / timed,
-                worst_translation_error, (int)fused);
+                worst_translation_error, fused_mode);
     vslam_host_free(frames);
   } catch (const std::exception& e) {
     std::fprintf(stderr, "FAILED: %s\n", e.what());

@@ -48,6 +48,7 @@ vslam_fpg_initialize vslam_fpg_get_features vslam_fpg_get_detection_stats vslam_
 vslam_fpg_reset_features vslam_fpg_graph_launch_count
 vslam_fpg_compute vslam_fpg_get_matches vslam_fpg_track vslam_fpg_recover_points vslam_fpg_prune_tracks
 vslam_fpg_frame_step vslam_fpg_frame_step_capacity vslam_fpg_frame_step_reset vslam_fpg_frame_step_set_previous
+vslam_fpg_frame_step_prefetch
 vslam_fpg_set_profiling vslam_fpg_get_time_consumption vslam_fpg_batch_upload vslam_fpg_batch_run
 vslam_fpg_batch_download vslam_fpg_batch_process vslam_fpg_batch_linearize vslam_fpg_batch_get_systems
 vslam_fpg_get_kernel_profile vslam_fpg_batch_get_features vslam_fpg_stream vslam_fpg_synchronize
@@ -150,6 +151,7 @@ def lib():
         L.vslam_fpg_track.argtypes = [vp, vp, i32, vp, C.c_int, i32, C.c_double, vp, i32, vp, vp, vp, vp, vp]
         L.vslam_fpg_recover_points.argtypes = [vp, vp, i32, vp, C.c_double, C.c_double, C.c_double, vp, i32, vp]
         L.vslam_fpg_frame_step.argtypes = [vp, vp, vp, sz, C.c_int, vp, vp, vp]
+        L.vslam_fpg_frame_step_prefetch.argtypes = [vp, vp, vp, sz]
         L.vslam_fpg_frame_step_capacity.argtypes = [vp]
         L.vslam_fpg_frame_step_capacity.restype = i32
         L.vslam_fpg_frame_step_reset.argtypes = [vp]
@@ -365,12 +367,22 @@ class StereoFramePointGenerator:
         previous = np.ascontiguousarray(previous, PREVIOUS_POINT)
         _check(lib().vslam_fpg_frame_step_set_previous(self._h, _p(previous) if len(previous) else None, len(previous)))
 
+    def frame_step_prefetch(self, left, right):
+        """upload of the NEXT frame's images while the current frame runs; consumed by frame_step(None, None, ...)"""
+        left, right = _image(left, self.cam), _image(right, self.cam)
+        _check(lib().vslam_fpg_frame_step_prefetch(self._h, _p(left), _p(right), left.strides[0]))
+        if not hasattr(self, "_staged"):
+            self._staged = []
+        self._staged.append((left, right))   # the copy is asynchronous: keep the arrays alive until they are consumed
+
     def frame_step(self, left, right, localizing, previous_to_current_prior, aligner_cfg, track_by_appearance,
                    projection_tracking_distance_pixels, maximum_descriptor_distance_tracking,
                    minimum_track_length_for_landmark_creation=1, publish_frame_points=True):
         """-> dict with the counts, the optimised motion and copies of the result arrays (tracks, kept, errors, inliers,
         lost, points, frame_points)"""
-        left, right = _image(left, self.cam), _image(right, self.cam)
+        staged = left is None and right is None   # the oldest pair of frame_step_prefetch()
+        if not staged:
+            left, right = _image(left, self.cam), _image(right, self.cam)
         T = np.ascontiguousarray(previous_to_current_prior, np.float64).reshape(12)
         p = FrameStepParameters()
         p.track_by_appearance = int(bool(track_by_appearance))
@@ -385,8 +397,11 @@ class StereoFramePointGenerator:
         p.minimum_reliable_depth_meters = float(aligner_cfg.minimum_reliable_depth_meters)
         p.publish_frame_points = int(bool(publish_frame_points))
         r = FrameStepResult()
-        _check(lib().vslam_fpg_frame_step(self._h, _p(left), _p(right), left.strides[0], int(bool(localizing)), _p(T),
+        _check(lib().vslam_fpg_frame_step(self._h, None if staged else _p(left), None if staged else _p(right),
+                                          0 if staged else left.strides[0], int(bool(localizing)), _p(T),
                                           C.byref(p), C.byref(r)))
+        if staged:
+            self._staged.pop(0)
 
         def view(ptr, n, dtype):
             if n == 0 or not ptr:

@@ -164,8 +164,17 @@ struct vslam_fpg {
   bool step_poll = true;                 // VSLAM_FRAME_STEP_SYNC=1: wait with cudaStreamSynchronize instead of polling
   size_t step_off_tracks = 0, step_off_kept = 0, step_off_errors = 0, step_off_inliers = 0, step_off_lost = 0,
          step_off_points = 0, step_off_frame_points = 0;
-  cudaGraphExec_t step_graph[2] = {nullptr, nullptr};   // [localizing]
-  int step_graph_kernels[2] = {0, 0};
+  cudaGraphExec_t step_graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [localizing][inbox buffer]
+  int step_graph_kernels[2][2] = {{0, 0}, {0, 0}};
+  // The images of a fused frame land in one of TWO inbox buffers (left at [0], right at [inbox_bytes]); the graph of a
+  // frame reads the buffer its images are in.  vslam_fpg_frame_step_prefetch uploads the NEXT frame into the other one on
+  // a copy stream of its own, i.e. while the current frame runs.
+  uint8_t* step_inbox[2] = {nullptr, nullptr};
+  size_t step_inbox_bytes = 0;           // per image
+  size_t step_inbox_stride[2] = {0, 0};  // row stride of the staged pair
+  int step_inbox_head = 0, step_inbox_count = 0;   // staged pairs: buffers head, head + 1 (mod 2)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t step_inbox_ev[2] = {nullptr, nullptr};
   const uint8_t* step_graph_stage = nullptr;
   size_t step_graph_stride = 0;
   bool step_graph_profiling = false;
@@ -176,7 +185,8 @@ namespace {
 
 // the captured frame graphs bake buffer addresses: any reallocation of a buffer they touch drops them
 void invalidate_step_graphs(vslam_fpg* h) {
-  for (auto& gph : h->step_graph)
+  for (auto& row : h->step_graph)
+  for (auto& gph : row)
     if (gph) {
       cudaGraphExecDestroy(gph);
       gph = nullptr;
@@ -735,6 +745,10 @@ int vslam_fpg_destroy(vslam_fpg* h) {
   cudaFree(h->d_step); cudaFree(h->d_step_ctl); cudaFree(h->d_step_planes); cudaFree(h->d_step_errors);
   cudaFree(h->d_step_inliers); cudaFree(h->d_step_system); cudaFree(h->d_step_track_length); cudaFree(h->d_step_kept_pos);
   cudaFree(h->d_step_bins);
+  for (auto& b : h->step_inbox) cudaFree(b);
+  for (auto& e : h->step_inbox_ev)
+    if (e) cudaEventDestroy(e);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   cudaFreeHost(h->h_step); cudaFreeHost(h->h_step_T);
   cudaFreeHost(h->h_thr);
   cudaFree(h->d_thr);
@@ -1199,7 +1213,8 @@ static FrameStepBuffers frame_step_buffers(vslam_fpg* h) {
 }
 
 // the device side of one tracked frame on lane 0's stream (captured once per frame status, or issued directly)
-static int issue_frame_step(vslam_fpg* h, Lane& lane, size_t stride, const vslam_frame_step_parameters& p) {
+static int issue_frame_step(vslam_fpg* h, Lane& lane, size_t stride, const vslam_frame_step_parameters& p,
+                            const uint8_t* image_left, const uint8_t* image_right) {
   const Geometry& g = h->g;
   {   // the thresholds and the motion prior travel beside the repitch (FAST is the first kernel that reads either)
     const bool beside = use_branches(h, lane, 1);
@@ -1207,8 +1222,7 @@ static int issue_frame_step(vslam_fpg* h, Lane& lane, size_t stride, const vslam
     if (beside) order_after(h, lane.stream, s, 0);
     CUDA_TRY(cudaMemcpyAsync(h->d_thr, h->h_thr, sizeof(int32_t) * g.n_regions, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(h->d_step, h->h_step_T, sizeof(double) * 13, cudaMemcpyHostToDevice, s));   // T_prior, frame_id, ticket = 0
-    launch_repitch(g, lane.stage, lane.stage + lane.stage_bytes, (int)stride, h->b.image, 1, lane.stream,
-                   h->b.raw_count, 2 * g.n_regions);
+    launch_repitch(g, image_left, image_right, (int)stride, h->b.image, 1, lane.stream, h->b.raw_count, 2 * g.n_regions);
     ++h->launches;
     if (beside) order_after(h, s, lane.stream, 0);
   }
@@ -1302,6 +1316,8 @@ int vslam_fpg_frame_step_reset(vslam_fpg* h) {
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaMemsetAsync(h->d_step, 0, sizeof(FrameStepState), h->lanes[0].stream));
+  if (h->copy_stream) CUDA_TRY(cudaStreamSynchronize(h->copy_stream));   // a new sequence: staged frames are dropped
+  h->step_inbox_count = 0;
   return VSLAM_OK;
 }
 
@@ -1319,10 +1335,55 @@ int vslam_fpg_frame_step_set_previous(vslam_fpg* h, const vslam_previous_point* 
   return VSLAM_OK;
 }
 
+// the two inbox buffers of the fused frame, sized for `image_bytes` per image
+static int ensure_inbox(vslam_fpg* h, size_t image_bytes) {
+  if (h->step_inbox_bytes >= image_bytes) return VSLAM_OK;
+  if (h->step_inbox_count) return fail(VSLAM_ERR_STATE, "a larger frame than the prefetched one: consume the staged pair first");
+  CUDA_TRY(cudaStreamSynchronize(h->lanes[0].stream));
+  if (h->copy_stream) CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+  invalidate_step_graphs(h);
+  for (auto& b : h->step_inbox) {
+    cudaFree(b);
+    b = nullptr;
+  }
+  h->step_inbox_bytes = 0;
+  if (!h->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (auto& e : h->step_inbox_ev)
+    if (!e) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& b : h->step_inbox) CUDA_TRY(cudaMalloc((void**)&b, 2 * image_bytes + 64));   // (+ the repitch kernel's read slack)
+  h->step_inbox_bytes = image_bytes;
+  return VSLAM_OK;
+}
+
+int vslam_fpg_frame_step_prefetch(vslam_fpg* h, const uint8_t* left, const uint8_t* right, size_t stride) {
+  VSLAM_NVTX("vslam_fpg_frame_step_prefetch");
+  if (!h || !left || !right) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  if (stride < (size_t)h->g.cols) return fail(VSLAM_ERR_INVALID_ARGUMENT, "stride smaller than the image width");
+  int rc = setup_frame_step(h);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t image_bytes = stride * (size_t)h->g.rows;
+  if (!linear_upload(h->g, 1, stride, image_bytes)) return fail(VSLAM_ERR_INVALID_ARGUMENT, "the fused frame takes dense images (row stride close to the width)");
+  if (h->step_inbox_count >= 2) return fail(VSLAM_ERR_STATE, "two frames are staged already: call vslam_fpg_frame_step");
+  if ((rc = ensure_inbox(h, image_bytes))) return rc;
+  // the buffer behind the staged ones: its last reader is a frame that has returned (the call is synchronous)
+  const int buf = (h->step_inbox_head + h->step_inbox_count) & 1;
+  CUDA_TRY(cudaMemcpyAsync(h->step_inbox[buf], left, image_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+  CUDA_TRY(cudaMemcpyAsync(h->step_inbox[buf] + h->step_inbox_bytes, right, image_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+  CUDA_TRY(cudaEventRecord(h->step_inbox_ev[buf], h->copy_stream));
+  h->step_inbox_stride[buf] = stride;
+  ++h->step_inbox_count;
+  return VSLAM_OK;
+}
+
 int vslam_fpg_frame_step(vslam_fpg* h, const uint8_t* left, const uint8_t* right, size_t stride, int localizing,
                          const double T_prior[12], const vslam_frame_step_parameters* p, vslam_frame_step_result* out) {
   VSLAM_NVTX("vslam_fpg_frame_step [PoseTracker3D::compute]");
-  if (!h || !left || !right || !T_prior || !p || !out) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  if (!h || !T_prior || !p || !out || (left == nullptr) != (right == nullptr)) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
+  const bool staged = left == nullptr;   // the oldest pair of vslam_fpg_frame_step_prefetch
+  if (staged && h->step_inbox_count == 0) return fail(VSLAM_ERR_STATE, "no images and no prefetched frame");
+  if (!staged && h->step_inbox_count) return fail(VSLAM_ERR_STATE, "a prefetched frame is waiting: pass null images to consume it");
+  if (staged) stride = h->step_inbox_stride[h->step_inbox_head];
   if (stride < (size_t)h->g.cols) return fail(VSLAM_ERR_INVALID_ARGUMENT, "stride smaller than the image width");
   if (p->projection_tracking_distance_pixels < 0) return fail(VSLAM_ERR_INVALID_ARGUMENT, "negative tracking distance");
   if (p->aligner.maximum_number_of_iterations < 1) return fail(VSLAM_ERR_INVALID_ARGUMENT, "maximum_number_of_iterations < 1");
@@ -1335,10 +1396,13 @@ int vslam_fpg_frame_step(vslam_fpg* h, const uint8_t* left, const uint8_t* right
   h->feat_valid = false;
   const size_t image_bytes = stride * (size_t)g.rows;
   if (!linear_upload(g, 1, stride, image_bytes)) return fail(VSLAM_ERR_INVALID_ARGUMENT, "the fused frame takes dense images (row stride close to the width)");
-  if ((rc = ensure_stage(h, lane, image_bytes, image_bytes))) return rc;
+  if ((rc = ensure_inbox(h, image_bytes))) return rc;
+  const int buf = h->step_inbox_head;
+  const uint8_t* image_left = h->step_inbox[buf];
+  const uint8_t* image_right = h->step_inbox[buf] + h->step_inbox_bytes;
   const int L = localizing != 0;
-  if (h->step_graph[0] || h->step_graph[1]) {
-    if (h->step_graph_stage != lane.stage || h->step_graph_stride != stride || h->step_graph_profiling != h->profiling ||
+  if (h->step_graph[0][0] || h->step_graph[0][1] || h->step_graph[1][0] || h->step_graph[1][1]) {
+    if (h->step_graph_stage != h->step_inbox[0] || h->step_graph_stride != stride || h->step_graph_profiling != h->profiling ||
         std::memcmp(&h->step_graph_parameters, p, sizeof(*p)) != 0)
       invalidate_step_graphs(h);
   }
@@ -1356,37 +1420,43 @@ int vslam_fpg_frame_step(vslam_fpg* h, const uint8_t* left, const uint8_t* right
   h->sp.localizing = L;
   h->localizing = L;
   static const bool use_graph = std::getenv("VSLAM_NO_FRAME_GRAPH") == nullptr;
-  if (use_graph && !h->step_graph[L]) {   // capture the device side of the frame once per frame status
+  if (use_graph && !h->step_graph[L][buf]) {   // capture the device side of the frame once per frame status and buffer
     const int64_t launches_before = h->launches;
     cudaGraph_t graph = nullptr;
     bool ok = cudaStreamBeginCapture(lane.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     if (ok) {
       h->capturing = true;
-      const int issued = issue_frame_step(h, lane, stride, *p);
+      const int issued = issue_frame_step(h, lane, stride, *p, image_left, image_right);
       h->capturing = false;
       ok = cudaStreamEndCapture(lane.stream, &graph) == cudaSuccess && graph != nullptr && issued == VSLAM_OK;
     }
-    if (ok) ok = cudaGraphInstantiate(&h->step_graph[L], graph, 0) == cudaSuccess;
+    if (ok) ok = cudaGraphInstantiate(&h->step_graph[L][buf], graph, 0) == cudaSuccess;
     if (graph) cudaGraphDestroy(graph);
-    h->step_graph_kernels[L] = (int)(h->launches - launches_before);
+    h->step_graph_kernels[L][buf] = (int)(h->launches - launches_before);
     h->launches = launches_before;
     if (!ok) {
       const cudaError_t e = cudaGetLastError();
-      h->step_graph[L] = nullptr;
+      h->step_graph[L][buf] = nullptr;
       return fail(VSLAM_ERR_CUDA, "capturing the frame graph failed: %s", cudaGetErrorString(e));
     }
-    h->step_graph_stage = lane.stage;
+    h->step_graph_stage = h->step_inbox[0];
     h->step_graph_stride = stride;
     h->step_graph_profiling = h->profiling;
     h->step_graph_parameters = *p;
   }
-  CUDA_TRY(cudaMemcpyAsync(lane.stage, left, image_bytes, cudaMemcpyHostToDevice, lane.stream));
-  CUDA_TRY(cudaMemcpyAsync(lane.stage + lane.stage_bytes, right, image_bytes, cudaMemcpyHostToDevice, lane.stream));
+  if (staged) {   // uploaded by vslam_fpg_frame_step_prefetch on the copy stream
+    CUDA_TRY(cudaStreamWaitEvent(lane.stream, h->step_inbox_ev[buf], 0));
+    --h->step_inbox_count;
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(h->step_inbox[buf], left, image_bytes, cudaMemcpyHostToDevice, lane.stream));
+    CUDA_TRY(cudaMemcpyAsync(h->step_inbox[buf] + h->step_inbox_bytes, right, image_bytes, cudaMemcpyHostToDevice, lane.stream));
+  }
+  h->step_inbox_head = buf ^ 1;   // the next frame's images go to the other buffer
   if (use_graph) {
-    CUDA_TRY(cudaGraphLaunch(h->step_graph[L], lane.stream));
-    h->launches += h->step_graph_kernels[L];
+    CUDA_TRY(cudaGraphLaunch(h->step_graph[L][buf], lane.stream));
+    h->launches += h->step_graph_kernels[L][buf];
     ++h->graph_launches;
-  } else if ((rc = issue_frame_step(h, lane, stride, *p))) {
+  } else if ((rc = issue_frame_step(h, lane, stride, *p, image_left, image_right))) {
     return rc;
   }
   const FrameStepHeader* hd = reinterpret_cast<const FrameStepHeader*>(h->h_step);
