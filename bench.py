@@ -643,11 +643,20 @@ def native_sequence(cfg, cam, frames, warmup=4, acfg=None, passes=1, device=0, f
                                    os.path.join(ROOT, "tools", "sequence_runner.cpp"), "-o", exe, "-L", pkg, "-lvslam_b200",
                                    "-Wl,-rpath," + pkg], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             _RUNNER["exe"], _RUNNER["dir"] = exe, d
-        path = os.path.join(_RUNNER["dir"], "frames_%s.u8" % cfg.name)
-        with open(path, "wb") as f:
-            for l, r in frames:
-                f.write(np.ascontiguousarray(l).tobytes())
-                f.write(np.ascontiguousarray(r).tobytes())
+        # the frames file is written once per sequence and reused by the stepwise / fused / prefetch runs of it
+        key = (cfg.name, len(frames), id(frames))
+        path = _RUNNER.setdefault("frames", {}).get(key)
+        if path is None:
+            for old in _RUNNER["frames"].values():
+                if os.path.exists(old):
+                    os.remove(old)
+            _RUNNER["frames"].clear()
+            path = os.path.join(_RUNNER["dir"], "frames_%s_%d.u8" % (cfg.name, len(_RUNNER["frames"])))
+            with open(path, "wb") as f:
+                for l, r in frames:
+                    f.write(np.ascontiguousarray(l).tobytes())
+                    f.write(np.ascontiguousarray(r).tobytes())
+            _RUNNER["frames"][key] = path
         args = [cam.rows, cam.cols, cfg.target_number_of_keypoints_tolerance, cfg.detector_threshold_minimum,
                 cfg.detector_threshold_maximum, cfg.detector_threshold_maximum_change, cfg.number_of_detectors_vertical,
                 cfg.number_of_detectors_horizontal, int(cfg.enable_keypoint_binning), cfg.bin_size_pixels,
@@ -665,7 +674,6 @@ def native_sequence(cfg, cam, frames, warmup=4, acfg=None, passes=1, device=0, f
             env["CUDA_VISIBLE_DEVICES"] = ids[device]
         res = subprocess.run([_RUNNER["exe"], path, str(len(frames)), str(warmup)] + [repr(a) for a in args]
                              + [str(passes), str(int(fused))], capture_output=True, text=True, timeout=300, env=env)
-        os.remove(path)
         if res.returncode != 0:
             return None
         r = json.loads(res.stdout.strip().splitlines()[-1])

@@ -569,17 +569,23 @@ void launch_track(const Geometry& g, const StereoParams& sp, const Buffers& b, i
     track_search_kernel<<<(n_previous + 7) / 8, 256, 0, stream>>>(g, sp, tp, row_ptr, kp_xy, desc, n_desc, gone_l, gone_r,
                                                                   previous, n_previous, s.tentative, step);
   // claims, tentative results and worklist in shared memory as far as they fit (claims first)
-  static const int smem_limit = [] {
-    int device = 0, optin = 0;
-    cudaGetDevice(&device);
+  // (the opt-in to more than 48 KB of dynamic shared memory is a per-device attribute of the kernel)
+  static int limit_of_device[64] = {};   // 0 = not asked yet, -1 = refused
+  int device = 0;
+  cudaGetDevice(&device);
+  int& cached = limit_of_device[device & 63];
+  if (cached == 0) {
+    int optin = 0;
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     const int limit = std::max(0, optin - 1024);   // (the kernel's static shared memory)
-    if (cudaFuncSetAttribute(track_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, limit) != cudaSuccess) {
+    if (limit > 0 && cudaFuncSetAttribute(track_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, limit) == cudaSuccess) {
+      cached = limit;
+    } else {
       cudaGetLastError();
-      return 0;
+      cached = -1;
     }
-    return limit;
-  }();
+  }
+  const int smem_limit = std::max(cached, 0);
   size_t smem = 0;
   int smem_claims = 0, smem_points = 0;
   if (sizeof(int32_t) * 2 * (size_t)g.cap <= (size_t)smem_limit) {
