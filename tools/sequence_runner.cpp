@@ -63,7 +63,8 @@ int main(int argc, char** argv) {
     fsp.minimum_track_length_for_landmark_creation = 1;
     fsp.maximum_reliable_depth_meters = maximum_reliable_depth;
     fsp.minimum_reliable_depth_meters = 0.1;
-    fsp.publish_frame_points = 1;
+    // points() of the frame as 128-byte records for a host that mirrors them (the device keeps its own copy either way)
+    fsp.publish_frame_points = std::getenv("VSLAM_RUNNER_NO_FRAME_POINTS") ? 0 : 1;
     const size_t image_bytes = (size_t)c.rows * c.cols;
 
     // page-locked frame buffers (vslam_host_alloc): the H2D copy of initialize() is one asynchronous DMA
