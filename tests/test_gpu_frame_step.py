@@ -217,3 +217,26 @@ def test_prefetched_frames_give_the_same_results_and_the_inbox_rules_hold():
         gen.frame_step(None, None, True, T, acfg, False, D, max_distance)
     ref.close()
     gen.close()
+
+
+@pytest.mark.parametrize("switch", ["VSLAM_NO_FRAME_BRANCHES", "VSLAM_FRAME_STEP_SYNC"])
+def test_frame_step_variants_one_chain_and_stream_synchronize(switch, monkeypatch):
+    """the A/B switches of the fused frame -- one chain of kernels instead of parallel branches (which also runs the bin
+    selection as ONE kernel), cudaStreamSynchronize instead of the polled completion word -- give the same frames"""
+    monkeypatch.setenv(switch, "1")     # read when the handle (the fused frame's state) is created
+    cfg, acfg = configs.KITTI, configs.KITTI_ALIGNER
+    cam = synth.camera(cfg.camera)
+    frames = 5
+    world = synth.BandWorld(cam.cols, cam.rows, 57, max_frames=frames)
+    D, max_distance = 25, 40.0
+    ref = Stepwise(cfg, acfg, cam, D, max_distance)
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    gen.frame_step_reset()
+    T = _prior(cam, 0.03)
+    for k in range(frames):
+        left, right = world.pair(k)
+        want = ref.step(left, right, k == 0, T)
+        got = gen.frame_step(left, right, k == 0, T, acfg, False, D, max_distance)
+        _compare(k, got, want, gen, True)
+    ref.close()
+    gen.close()
