@@ -44,89 +44,113 @@ __device__ __forceinline__ void ordered_add(double (*s)[33], const double* terms
 }
 
 // solve3 of gn_math.h (Eigen::FullPivLU<Matrix3>::solve, landmark.cpp:136) with every index a compile-time constant:
-// the run-time pivot position only drives predicated swaps, so the 3 x 3 system stays in registers (the generic form
-// indexes its arrays with the pivot position and lives in local memory: 160 bytes of stack per thread).  Same
-// operations in the same order: bit-identical.
+// the 3 x 4 augmented system stays in registers (the generic form indexes its arrays with the run-time pivot position
+// and lives in local memory: 160 bytes of stack per thread), the pivot search is a chain of selects in the scalar scan's
+// order (strict `>`: the first maximum wins, a NaN never does), the row / column swaps are selects on the pivot position
+// and the back substitution is straight-line code at full rank -- a branch region costs a warp ~100 cycles of latency on
+// this machine, and an iteration of Landmark::update is one long dependency chain.  Same operations in
+// the same order: bit-identical.
+template <int K>
+__device__ __forceinline__ void lu3_step(double (&a)[3][4], int (&perm)[3], int& rank, double& maxpivot) {
+  if (K >= rank) return;                 // a zero pivot ended the elimination (the break of the scalar form)
+  double biggest = -1;
+  int pr = K, pc = K;
+#pragma unroll
+  for (int i = K; i < 3; ++i)
+#pragma unroll
+    for (int j = K; j < 3; ++j) {
+      const double v = fabs(a[i][j]);
+      const bool g = v > biggest;
+      biggest = g ? v : biggest;
+      pr = g ? i : pr;
+      pc = g ? j : pc;
+    }
+  if (biggest == 0) {
+    rank = K;
+    return;
+  }
+  maxpivot = biggest > maxpivot ? biggest : maxpivot;
+  // rows K and pr (all four columns: what lies left of K is never read again, the right-hand side follows)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double vk = a[K][j];
+    double vp = vk;
+#pragma unroll
+    for (int r = K + 1; r < 3; ++r) vp = pr == r ? a[r][j] : vp;
+#pragma unroll
+    for (int r = K + 1; r < 3; ++r) a[r][j] = pr == r ? vk : a[r][j];
+    a[K][j] = vp;
+  }
+  // columns K and pc (every row: the finished rows of U follow the permutation)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double vk = a[i][K];
+    double vp = vk;
+#pragma unroll
+    for (int c = K + 1; c < 3; ++c) vp = pc == c ? a[i][c] : vp;
+#pragma unroll
+    for (int c = K + 1; c < 3; ++c) a[i][c] = pc == c ? vk : a[i][c];
+    a[i][K] = vp;
+  }
+  {
+    const int vk = perm[K];
+    int vp = vk;
+#pragma unroll
+    for (int c = K + 1; c < 3; ++c) vp = pc == c ? perm[c] : vp;
+#pragma unroll
+    for (int c = K + 1; c < 3; ++c) perm[c] = pc == c ? vk : perm[c];
+    perm[K] = vp;
+  }
+#pragma unroll
+  for (int i = K + 1; i < 3; ++i) {
+    const double f = a[i][K] / a[K][K];
+#pragma unroll
+    for (int j = K + 1; j < 4; ++j) a[i][j] = a[i][j] - f * a[K][j];
+  }
+}
+
 __device__ __forceinline__ void solve3_registers(const double* H, const double* rhs, double* x) {
-  double a[3][3], b[3];
+  double a[3][4];
   int perm[3] = {0, 1, 2};
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    b[i] = rhs[i];
 #pragma unroll
     for (int j = 0; j < 3; ++j) a[i][j] = H[i * 3 + j];
+    a[i][3] = rhs[i];
   }
   int rank = 3;
   double maxpivot = 0;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    if (k < rank) {
-      int pr = k, pc = k;
-      double biggest = -1;
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-          if (i >= k && j >= k && fabs(a[i][j]) > biggest) {
-            biggest = fabs(a[i][j]);
-            pr = i;
-            pc = j;
-          }
-      if (biggest == 0) {
-        rank = k;
-      } else {
-        if (biggest > maxpivot) maxpivot = biggest;
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-          if (r > k && r == pr) {
-#pragma unroll
-            for (int j = 0; j < 3; ++j) swap_values(a[k][j], a[r][j]);
-            swap_values(b[k], b[r]);
-          }
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          if (c > k && c == pc) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i) swap_values(a[i][k], a[i][c]);
-            swap_values(perm[k], perm[c]);
-          }
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-          if (i > k) {
-            const double f = a[i][k] / a[k][k];
-            a[i][k] = f;
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-              if (j > k) a[i][j] -= f * a[k][j];
-            b[i] -= f * b[k];
-          }
-      }
-    }
-  }
+  lu3_step<0>(a, perm, rank, maxpivot);
+  lu3_step<1>(a, perm, rank, maxpivot);
+  lu3_step<2>(a, perm, rank, maxpivot);
   {
     int r = 0;
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-      if (i < rank) r += fabs(a[i][i]) > maxpivot * (2.220446049250313e-16 * 3);
+    for (int i = 0; i < 3; ++i) r += (i < rank && fabs(a[i][i]) > maxpivot * (2.220446049250313e-16 * 3)) ? 1 : 0;
     rank = r;
   }
   double y[3] = {0, 0, 0};
+  if (rank == 3) {
+    y[2] = a[2][3] / a[2][2];
+    y[1] = (a[1][3] - a[1][2] * y[2]) / a[1][1];
+    y[0] = ((a[0][3] - a[0][1] * y[1]) - a[0][2] * y[2]) / a[0][0];
+  } else {
 #pragma unroll
-  for (int i = 2; i >= 0; --i)
-    if (i < rank) {
-      double sum = b[i];
+    for (int i = 2; i >= 0; --i)
+      if (i < rank) {
+        double sum = a[i][3];
 #pragma unroll
-      for (int j = 0; j < 3; ++j)
-        if (j > i && j < rank) sum -= a[i][j] * y[j];
-      y[i] = sum / a[i][i];
-    }
+        for (int j = 0; j < 3; ++j)
+          if (j > i && j < rank) sum -= a[i][j] * y[j];
+        y[i] = sum / a[i][i];
+      }
+  }
 #pragma unroll
   for (int t = 0; t < 3; ++t) x[t] = 0;
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int t = 0; t < 3; ++t)
-      if (t == perm[i]) x[t] = y[i];
+    for (int t = 0; t < 3; ++t) x[t] = perm[i] == t ? y[i] : x[t];
 }
 
 // where the measurement history of a landmark lives: one CSR segment of a caller-provided array (vslam_landmark_optimizer)
@@ -157,6 +181,18 @@ __device__ __forceinline__ void landmark_update_warp(const History ms, int n, in
   double total_previous = 0;                                                                      // :88
   int result = 0;
   uint32_t it = 0;
+  // the measurement and the pose of this lane in the FIRST chunk stay in registers across the iterations (most histories
+  // are one chunk; an iteration otherwise starts with two dependent trips to memory: measurement -> its frame's pose)
+  LandmarkMeasurement q_first = {};
+  double w_first[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) w_first[i] = 0.0;
+  if (lane < n) {
+    q_first = ms.at(lane);
+    const double* W = world_to_camera + 12 * (size_t)q_first.frame;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) w_first[i] = __ldg(W + i);
+  }
   for (; it < max_iterations; ++it) {                                                             // :91
     double running = 0;                                 // lane c: H[c] (c < 9), b[c - 9] (c < 12), total (c == 12)
     uint32_t outliers = 0;
@@ -167,11 +203,16 @@ __device__ __forceinline__ void landmark_update_warp(const History ms, int n, in
       for (int c = 0; c < kLmTerms; ++c) terms[c] = 0.0;   // +0.0 is neutral for sums that start at +0.0
       bool outlier = false;
       if (m < n) {
-        const LandmarkMeasurement q = ms.at(m);
-        const double* W = world_to_camera + 12 * (size_t)q.frame;
+        LandmarkMeasurement q = q_first;
         double w_[12];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) w_[i] = __ldg(W + i);
+        for (int i = 0; i < 12; ++i) w_[i] = w_first[i];
+        if (c0 > 0) {
+          q = ms.at(m);
+          const double* W = world_to_camera + 12 * (size_t)q.frame;
+#pragma unroll
+          for (int i = 0; i < 12; ++i) w_[i] = __ldg(W + i);
+        }
         double p[3], e[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r)                                                               // :102
