@@ -84,10 +84,11 @@ __device__ int search_region(const int32_t* __restrict__ row_ptr, const uint32_t
   const int f0 = row_ptr[row_start], f1 = row_ptr[row_end];
   unsigned best = 0xffffffffu;
   for (int f = f0 + lane; f < f1; f += 32) {
+    // (the position and the removed flag are fetched together: one trip to memory instead of two in a row)
     const uint32_t q = xy[f];
+    const bool removed = claim ? load_claim(claim + f) < self : gone[f] != 0;   // feature_lattice[row][col] == nullptr
     const int col = (int)(q & 0xffffu);
-    if (col < col_start || col >= col_end) continue;
-    if (claim ? load_claim(claim + f) < self : gone[f] != 0) continue;  // feature_lattice[row][col] == nullptr
+    if (col < col_start || col >= col_end || removed) continue;
     const int d = popc256(q0, q1, desc[2 * f], desc[2 * f + 1]);
     if (!((double)d < maximum_distance)) continue;                   // :103 / :121 (strict, against the double limit)
     unsigned key;
