@@ -240,3 +240,31 @@ def test_frame_step_variants_one_chain_and_stream_synchronize(switch, monkeypatc
         _compare(k, got, want, gen, True)
     ref.close()
     gen.close()
+
+
+def test_frame_step_when_every_previous_point_is_lost():
+    """a motion prior that is far off: previous points exist, none is tracked -- the aligner has nothing to align (the
+    control block still carries the prior, zero rounds), nothing survives, the frame consists of new points only, and the
+    sequence carries on from there"""
+    cfg, acfg = configs.KITTI, configs.KITTI_ALIGNER
+    cam = synth.camera(cfg.camera)
+    world = synth.BandWorld(cam.cols, cam.rows, 63, max_frames=4)
+    D, max_distance = 25, 40.0
+    ref = Stepwise(cfg, acfg, cam, D, max_distance)
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    gen.frame_step_reset()
+    good = _prior(cam)
+    off = good.copy()
+    off[1, 3] = 40.0                    # 40 m sideways: every projection leaves the image or finds nothing nearby
+    for k, T in enumerate([good, off, good, good]):
+        want = ref.step(*world.pair(k), k == 0, T)
+        got = gen.frame_step(*world.pair(k), k == 0, T, acfg, False, D, max_distance)
+        _compare(k, got, want, gen, True)
+        if k == 1:
+            assert got["n_previous"] > 300 and got["n_tracked"] == 0 and got["n_tracks"] == 0
+            assert got["aligner_rounds"] == 0 and np.array_equal(got["previous_to_current"], off)
+            assert got["n_new_points"] > 300
+        if k >= 2:
+            assert got["n_tracks"] > 200
+    ref.close()
+    gen.close()
