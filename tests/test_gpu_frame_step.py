@@ -268,3 +268,39 @@ def test_frame_step_when_every_previous_point_is_lost():
             assert got["n_tracks"] > 200
     ref.close()
     gen.close()
+
+
+ERR_CAPACITY = -3   # VSLAM_ERR_CAPACITY (include/vslam_b200.h)
+
+
+def test_frame_step_capacity():
+    """more points than the fused path holds: VSLAM_ERR_CAPACITY (the stepwise calls have no such limit), the device-
+    resident points are dropped, and the next frame starts a new sequence"""
+    cfg = dataclasses.replace(configs.HD, name="hd_dense", bin_size_pixels=6, detector_threshold_minimum=5,
+                              detector_threshold_maximum=20)
+    acfg = configs.KITTI_ALIGNER
+    cam = synth.camera(cfg.camera)
+    world = synth.BandWorld(cam.cols, cam.rows, 17, max_frames=3)
+    gen = api.StereoFramePointGenerator(cfg, cam, max_keypoints=32768)
+    cap = gen.frame_step_capacity()
+    T = _prior(cam)
+    # from the host: more previous points than the capacity
+    with pytest.raises(api.VslamError) as e:
+        gen.frame_step_set_previous(np.zeros(cap + 1, api.PREVIOUS_POINT))
+    assert e.value.code == ERR_CAPACITY
+    # from a frame: 6-pixel bins on a 1920 x 1080 pair hold far more new points than the capacity
+    gen.frame_step_reset()
+    gen.thresholds = np.full(gen.number_of_detectors, 5.0)
+    with pytest.raises(api.VslamError) as e:
+        gen.frame_step(*world.pair(0), True, T, acfg, False, 25, 40.0)
+    assert e.value.code == ERR_CAPACITY
+    # the same pair through the stepwise calls is fine, and shows that the limit was the reason
+    gen.initialize(*world.pair(0), True)
+    assert len(gen.compute()) > cap
+    gen.close()
+    # a handle with room: the frame after a refused one is a first frame again
+    gen = api.StereoFramePointGenerator(configs.HD, cam)
+    gen.frame_step_reset()
+    got = gen.frame_step(*world.pair(1), True, T, acfg, False, 25, 40.0)
+    assert got["n_previous"] == 0 and 0 < got["n_new_points"] <= cap
+    gen.close()
