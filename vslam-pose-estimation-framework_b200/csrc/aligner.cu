@@ -672,7 +672,23 @@ __global__ void __launch_bounds__(kThreads, 1) converge_cluster_kernel(int n, Al
     cluster.sync();                     // every block's partial of this round is in its shared memory
     GN_MARK(3)
 
-    {  // the block partials in block order, 8 interleaved slices per value -- as in linearize_kernel
+    if (n_active <= kThreads / 32) {
+      // At most one block per slice: the two-level sum of linearize_kernel (slices of every 8th block, then the 8 slices)
+      // degenerates to the chain 0 + t_0 + t_1 + ... over the blocks -- the empty slices add +0.0, which changes nothing --
+      // so the first kAcc threads (all in warp 0, which goes on to solve) add the blocks' partials directly: no block
+      // barrier, no trip through s_part.  Everybody else meets them at the barrier behind gn_step.
+      if (threadIdx.x < kAcc) {
+        double t[kThreads / 32];
+#pragma unroll
+        for (int blk = 0; blk < kThreads / 32; ++blk)
+          t[blk] = blk < n_active ? cluster.map_shared_rank(&s_total[parity][0], blk)[threadIdx.x] : 0.0;
+        double s = 0;
+#pragma unroll
+        for (int blk = 0; blk < kThreads / 32; ++blk) s += t[blk];
+        s_sys[threadIdx.x] = s;
+      }
+      if (threadIdx.x < 32) __syncwarp();
+    } else {  // the block partials in block order, 8 interleaved slices per value -- as in linearize_kernel
       const int j = threadIdx.x & 31, part = threadIdx.x >> 5;
       double v = 0;
       if (j < kAcc)
