@@ -221,17 +221,6 @@ __device__ __forceinline__ void for_each_consumed_right(const TrackView& v, int 
 
 constexpr int kResolveThreads = 1024;
 
-__device__ __forceinline__ int block_min(int v, int* s_red) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  v = __reduce_min_sync(0xffffffffu, v);
-  if (lane == 0) s_red[warp] = v;
-  __syncthreads();
-  v = s_red[lane];
-  v = __reduce_min_sync(0xffffffffu, v);
-  __syncthreads();
-  return v;
-}
-
 // exclusive scan of a 0/1 flag over the block; total in *total
 __device__ __forceinline__ int block_scan_flag(bool flag, int* s_red, int* total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
