@@ -254,7 +254,9 @@ typedef struct {
  * stay on the device (camera coordinates + both descriptors, 128 B each), the aligner's correspondences are packed on
  * the device (stereouv_aligner.cpp:26-64, the branch without a landmark estimate: moving =
  * previous->cameraCoordinatesLeft(), information = I), converge() runs as one thread-block cluster, the prune rule and
- * the bin pre-load never leave the device, and the whole frame is one CUDA-graph launch and ONE synchronisation.
+ * the bin pre-load never leave the device, and the whole frame is one CUDA-graph launch (kernels that do not depend on
+ * each other run as parallel branches of the graph) and ONE wait: the call returns when the frame's last kernel has
+ * echoed the frame number into the pinned result block, which the host polls.
  * Results are bit-identical to the stepwise calls in the same order (tests/test_gpu_frame_step.py).
  * Limits: keypoint binning enabled; at most vslam_fpg_frame_step_capacity() points per frame (4096 on a B200: one
  * 16-CTA cluster, one correspondence per thread) -- VSLAM_ERR_CAPACITY beyond, the stepwise calls have no such limit.
