@@ -304,3 +304,33 @@ def test_frame_step_capacity():
     got = gen.frame_step(*world.pair(1), True, T, acfg, False, 25, 40.0)
     assert got["n_previous"] == 0 and 0 < got["n_new_points"] <= cap
     gen.close()
+
+
+def test_frame_step_is_deterministic_under_repetition():
+    """compute-sanitizer is closed on this GPU pool; a race in the cluster kernels, the shared-memory claims of the track
+    resolver or the parallel branches of the frame graph would show up as run-to-run differences: the same four frames,
+    40 times over (fresh sequence each time), must give the same bytes"""
+    import hashlib
+    cfg, acfg = configs.KITTI, configs.KITTI_ALIGNER
+    cam = synth.camera(cfg.camera)
+    world = synth.BandWorld(cam.cols, cam.rows, 29, max_frames=4)
+    pairs = [world.pair(k) for k in range(4)]
+    T = _prior(cam, 0.02)
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    first = None
+    for rep in range(40):
+        gen.frame_step_reset()
+        gen.thresholds = np.full(gen.number_of_detectors, 50.0)
+        h = hashlib.sha256()
+        for k, (left, right) in enumerate(pairs):
+            got = gen.frame_step(left, right, k == 0, T, acfg, False, 25, 40.0)
+            for key in ("tracks", "kept", "errors", "inliers", "lost", "points", "frame_points", "previous_to_current",
+                        "information"):
+                h.update(np.ascontiguousarray(got[key]).tobytes())
+            h.update(np.array([got[f] for f in ("n_left", "n_right", "n_tracked", "n_tracks", "n_new_points", "n_matches",
+                                                "aligner_rounds", "aligner_inliers")], np.int64).tobytes())
+        if first is None:
+            first = h.hexdigest()
+            assert got["n_tracks"] > 200
+        assert h.hexdigest() == first, rep
+    gen.close()
