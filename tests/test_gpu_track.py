@@ -42,11 +42,11 @@ def _same_points(got, want):
     assert np.array_equal(got["camera"], want["cam"])
 
 
-def _setup(cfg, seed, k0=0, k1=1):
+def _setup(cfg, seed, k0=0, k1=1, max_keypoints=0):
     cam = synth.camera(cfg.camera)
     world = synth.BandWorld(cam.cols, cam.rows, seed, max_frames=8)
     ora = pipeline.StereoFramePointGeneratorOracle(cfg, cam, "a")
-    gen = api.StereoFramePointGenerator(cfg, cam)
+    gen = api.StereoFramePointGenerator(cfg, cam, max_keypoints=max_keypoints)
     l0, r0 = world.pair(k0)
     ora.initialize(l0, r0, True)
     ora.compute()
@@ -94,11 +94,14 @@ def test_track_and_following_compute_match_oracle(cfg_name, by_appearance, D, no
     gen.close()
 
 
-def test_track_heavy_conflicts():
+@pytest.mark.parametrize("max_keypoints", [0, 40000])
+def test_track_heavy_conflicts(max_keypoints):
     """every previous point three times, in shuffled order, with a loose appearance gate and the widest window: hundreds
-    of points pick a feature a lower-indexed point already consumed"""
+    of points pick a feature a lower-indexed point already consumed.  With the default capacity the resolver keeps its
+    claims, tentative results and worklist in shared memory; a handle created for 40 000 keypoints per image does not fit
+    (320 KB of claims) and runs the same rounds on the global scratch."""
     cfg = configs.KITTI_FAST
-    cam, world, ora, gen, prev = _setup(cfg, seed=3)
+    cam, world, ora, gen, prev = _setup(cfg, seed=3, max_keypoints=max_keypoints)
     rng = np.random.default_rng(0)
     prev = np.concatenate([prev, prev, prev])[rng.permutation(3 * len(prev))]
     T = _motion(cam, 1, 0.03, seed=1)
