@@ -1355,6 +1355,19 @@ static int ensure_inbox(vslam_fpg* h, size_t image_bytes) {
   return VSLAM_OK;
 }
 
+// the two images of a frame into inbox buffer `buf`: ONE copy when the host keeps the pair back to back (left, then
+// right) and the inbox is sized for exactly this image, else one per side
+static int upload_pair(vslam_fpg* h, int buf, const uint8_t* left, const uint8_t* right, size_t image_bytes,
+                       cudaStream_t stream) {
+  if (right == left + image_bytes && h->step_inbox_bytes == image_bytes) {
+    CUDA_TRY(cudaMemcpyAsync(h->step_inbox[buf], left, 2 * image_bytes, cudaMemcpyHostToDevice, stream));
+    return VSLAM_OK;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->step_inbox[buf], left, image_bytes, cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(h->step_inbox[buf] + h->step_inbox_bytes, right, image_bytes, cudaMemcpyHostToDevice, stream));
+  return VSLAM_OK;
+}
+
 int vslam_fpg_frame_step_prefetch(vslam_fpg* h, const uint8_t* left, const uint8_t* right, size_t stride) {
   VSLAM_NVTX("vslam_fpg_frame_step_prefetch");
   if (!h || !left || !right) return fail(VSLAM_ERR_INVALID_ARGUMENT, "null argument");
@@ -1368,8 +1381,7 @@ int vslam_fpg_frame_step_prefetch(vslam_fpg* h, const uint8_t* left, const uint8
   if ((rc = ensure_inbox(h, image_bytes))) return rc;
   // the buffer behind the staged ones: its last reader is a frame that has returned (the call is synchronous)
   const int buf = (h->step_inbox_head + h->step_inbox_count) & 1;
-  CUDA_TRY(cudaMemcpyAsync(h->step_inbox[buf], left, image_bytes, cudaMemcpyHostToDevice, h->copy_stream));
-  CUDA_TRY(cudaMemcpyAsync(h->step_inbox[buf] + h->step_inbox_bytes, right, image_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+  if ((rc = upload_pair(h, buf, left, right, image_bytes, h->copy_stream))) return rc;
   CUDA_TRY(cudaEventRecord(h->step_inbox_ev[buf], h->copy_stream));
   h->step_inbox_stride[buf] = stride;
   ++h->step_inbox_count;
@@ -1448,8 +1460,7 @@ int vslam_fpg_frame_step(vslam_fpg* h, const uint8_t* left, const uint8_t* right
     CUDA_TRY(cudaStreamWaitEvent(lane.stream, h->step_inbox_ev[buf], 0));
     --h->step_inbox_count;
   } else {
-    CUDA_TRY(cudaMemcpyAsync(h->step_inbox[buf], left, image_bytes, cudaMemcpyHostToDevice, lane.stream));
-    CUDA_TRY(cudaMemcpyAsync(h->step_inbox[buf] + h->step_inbox_bytes, right, image_bytes, cudaMemcpyHostToDevice, lane.stream));
+    if ((rc = upload_pair(h, buf, left, right, image_bytes, lane.stream))) return rc;
   }
   h->step_inbox_head = buf ^ 1;   // the next frame's images go to the other buffer
   if (use_graph) {
