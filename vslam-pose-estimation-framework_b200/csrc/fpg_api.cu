@@ -159,7 +159,8 @@ struct vslam_fpg {
   int32_t* d_step_kept_pos = nullptr;
   uint8_t* h_step = nullptr;             // pinned + mapped result block
   uint8_t* h_step_device = nullptr;      // its device address
-  double* h_step_T = nullptr;            // pinned [13]: the motion prior + {frame number, 0} a copy node of the graph reads
+  double* h_step_T = nullptr;            // pinned: the copied prefix of FrameStepState (motion prior, frame number, ticket = 0,
+                                         // thresholds) that ONE copy node of the graph reads
   int32_t step_frame_id = 0;
   bool step_poll = true;                 // VSLAM_FRAME_STEP_SYNC=1: wait with cudaStreamSynchronize instead of polling
   size_t step_off_tracks = 0, step_off_kept = 0, step_off_errors = 0, step_off_inliers = 0, step_off_lost = 0,
@@ -1159,7 +1160,8 @@ static int setup_frame_step(vslam_fpg* h) {
   CUDA_TRY(cudaHostAlloc((void**)&h->h_step, off, cudaHostAllocMapped));
   std::memset(h->h_step, 0, off);
   CUDA_TRY(cudaHostGetDevicePointer((void**)&h->h_step_device, h->h_step, 0));
-  CUDA_TRY(cudaMallocHost((void**)&h->h_step_T, sizeof(double) * 13));
+  CUDA_TRY(cudaMallocHost((void**)&h->h_step_T, offsetof(FrameStepState, n_previous)));   // the copied prefix of FrameStepState
+  std::memset(h->h_step_T, 0, offsetof(FrameStepState, n_previous));
   h->step_poll = std::getenv("VSLAM_FRAME_STEP_SYNC") == nullptr;
   CUDA_TRY(cudaHostGetDevicePointer((void**)&h->h_status_device, h->h_status, 0));
   h->step_cluster_blocks = blocks;
@@ -1220,13 +1222,14 @@ static int issue_frame_step(vslam_fpg* h, Lane& lane, size_t stride, const vslam
     const bool beside = use_branches(h, lane, 1);
     cudaStream_t s = beside ? h->side_stream : lane.stream;
     if (beside) order_after(h, lane.stream, s, 0);
-    CUDA_TRY(cudaMemcpyAsync(h->d_thr, h->h_thr, sizeof(int32_t) * g.n_regions, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(h->d_step, h->h_step_T, sizeof(double) * 13, cudaMemcpyHostToDevice, s));   // T_prior, frame_id, ticket = 0
+    // ONE copy node: T_prior, frame_id, ticket = 0 and the thresholds are the leading members of FrameStepState
+    CUDA_TRY(cudaMemcpyAsync(h->d_step, h->h_step_T, offsetof(FrameStepState, thresholds) + sizeof(int32_t) * g.n_regions,
+                             cudaMemcpyHostToDevice, s));
     launch_repitch(g, image_left, image_right, (int)stride, h->b.image, 1, lane.stream, h->b.raw_count, 2 * g.n_regions);
     ++h->launches;
     if (beside) order_after(h, s, lane.stream, 0);
   }
-  run_detect_describe(h, lane, 0, 1, h->d_thr, true);                            // pose_tracker_3d.cpp:80
+  run_detect_describe(h, lane, 0, 1, h->d_step->thresholds, true);               // pose_tracker_3d.cpp:80
   const FrameStepBuffers f = frame_step_buffers(h);
   FrameStepParams fp;
   fp.max_reliable_depth = p.maximum_reliable_depth_meters;
@@ -1425,9 +1428,10 @@ int vslam_fpg_frame_step(vslam_fpg* h, const uint8_t* left, const uint8_t* right
   for (int i = 0; i < 12; ++i) h->h_step_T[i] = T_prior[i];
   const int32_t frame_id = h->step_frame_id = (h->step_frame_id % 0x3fffffff) + 1;   // never 0
   {
-    int32_t* tail = reinterpret_cast<int32_t*>(h->h_step_T + 12);
-    tail[0] = frame_id;
-    tail[1] = 0;
+    FrameStepState* staged_state = reinterpret_cast<FrameStepState*>(h->h_step_T);   // (its copied prefix)
+    staged_state->frame_id = frame_id;
+    staged_state->ticket = 0;
+    for (int i = 0; i < g.n_regions; ++i) staged_state->thresholds[i] = h->h_thr[i];
   }
   h->sp.localizing = L;
   h->localizing = L;

@@ -71,6 +71,7 @@ struct FrameStepState {
   double T_prior[12];      // camera_left_previous_in_current of this frame (copy node of the graph, from pinned memory)
   int32_t frame_id;        // (same copy) the host's number of this frame, echoed into the result header when it is complete
   int32_t ticket;          // (same copy: 0) blocks of the last kernel that have published their share
+  int32_t thresholds[kMaxRegions];   // (same copy) the FAST thresholds of this frame, per detector region
   int32_t n_previous;      // points() of the previous frame held in `previous` (written by frame_assemble_kernel)
   int32_t n_kept;          // tracks that survive _prunePoints (frame_prune_kernel)
   int32_t inliers_only;    // the branch of pose_tracker_3d.cpp:441 taken by frame_prune_kernel
