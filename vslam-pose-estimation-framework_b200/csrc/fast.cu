@@ -644,10 +644,12 @@ bool make_fast_tensor_map(const Geometry& g, const uint8_t* images, int n_images
 }
 
 void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, const CUtensorMap& image_map, int first_image,
-                 int n_images, cudaStream_t stream, const int32_t* device_thresholds, bool counts_cleared) {
+                 int n_images, cudaStream_t stream, const int32_t* device_thresholds, bool counts_cleared,
+                 bool mask_cleared) {
   const int single = g.n_regions == 1;
   const size_t mask_bytes = (size_t)g.rows * g.mask_words * sizeof(uint32_t);
-  if (!single) cudaMemsetAsync(b.mask + (size_t)first_image * g.rows * g.mask_words, 0, mask_bytes * n_images, stream);
+  if (!single && !mask_cleared)
+    cudaMemsetAsync(b.mask + (size_t)first_image * g.rows * g.mask_words, 0, mask_bytes * n_images, stream);
   if (!counts_cleared)
     cudaMemsetAsync(b.raw_count + (size_t)first_image * g.n_regions, 0, sizeof(int32_t) * g.n_regions * n_images, stream);
   dim3 grid((g.cols + TW - 1) / TW, (g.rows + TH - 1) / TH, n_images * g.n_regions);

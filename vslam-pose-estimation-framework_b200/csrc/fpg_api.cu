@@ -229,7 +229,7 @@ inline bool use_branches(const vslam_fpg* h, const Lane& lane, int n) {
 
 // kernels of initialize() for images [2*p0, 2*(p0+n)) on one lane
 void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n, const int32_t* device_thresholds = nullptr,
-                         bool counts_cleared = false) {
+                         bool counts_cleared = false, bool mask_cleared = false) {
   Buffers b = h->b;
   // lane-local scratch is indexed from image 0 of the chunk: shift the base so that image index 2*p0 lands on it
   b.blurred = lane.blurred - (size_t)2 * p0 * h->g.rows * h->g.pitch;
@@ -243,7 +243,7 @@ void run_detect_describe(vslam_fpg* h, Lane& lane, int p0, int n, const int32_t*
     launch_blur(h->g, b, h->blur_map, 2 * p0, 2, h->side_stream);
   }
   mark(h, lane, kEvFast0);
-  launch_fast(h->g, rt, b, h->image_map, 2 * p0, 2 * n, lane.stream, device_thresholds, counts_cleared);
+  launch_fast(h->g, rt, b, h->image_map, 2 * p0, 2 * n, lane.stream, device_thresholds, counts_cleared, mask_cleared);
   mark(h, lane, kEvFast1);
   launch_compact(h->g, b, 2 * p0, 2 * n, lane.stream);
   mark(h, lane, kEvCompact1);
@@ -1225,11 +1225,14 @@ static int issue_frame_step(vslam_fpg* h, Lane& lane, size_t stride, const vslam
     // ONE copy node: T_prior, frame_id, ticket = 0 and the thresholds are the leading members of FrameStepState
     CUDA_TRY(cudaMemcpyAsync(h->d_step, h->h_step_T, offsetof(FrameStepState, thresholds) + sizeof(int32_t) * g.n_regions,
                              cudaMemcpyHostToDevice, s));
+    // several detector regions OR their keypoints into the mask: it is cleared here, beside the repitch, not in front of FAST
+    if (g.n_regions > 1)
+      CUDA_TRY(cudaMemsetAsync(lane.mask, 0, (size_t)2 * g.rows * g.mask_words * sizeof(uint32_t), s));
     launch_repitch(g, image_left, image_right, (int)stride, h->b.image, 1, lane.stream, h->b.raw_count, 2 * g.n_regions);
     ++h->launches;
     if (beside) order_after(h, s, lane.stream, 0);
   }
-  run_detect_describe(h, lane, 0, 1, h->d_step->thresholds, true);               // pose_tracker_3d.cpp:80
+  run_detect_describe(h, lane, 0, 1, h->d_step->thresholds, true, true);         // pose_tracker_3d.cpp:80
   const FrameStepBuffers f = frame_step_buffers(h);
   FrameStepParams fp;
   fp.max_reliable_depth = p.maximum_reliable_depth_meters;

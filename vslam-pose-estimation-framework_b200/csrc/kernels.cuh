@@ -104,7 +104,7 @@ bool make_image_tensor_map(const Geometry& g, const uint8_t* images, int n_image
 // device_thresholds (optional): [n_regions] i32 in device memory, read instead of rt.threshold
 void launch_fast(const Geometry& g, const RegionTable& rt, const Buffers& b, const CUtensorMap& image_map, int first_image,
                  int n_images, cudaStream_t stream, const int32_t* device_thresholds = nullptr,
-                 bool counts_cleared = false);
+                 bool counts_cleared = false, bool mask_cleared = false);
 void launch_compact(const Geometry& g, const Buffers& b, int first_image, int n_images, cudaStream_t stream);
 // layout of the packed features of pair 0 (pack_features_kernel): per side [n] u32 | [n] u8 padded to 16 | [n][32]
 __host__ __device__ inline size_t feature_pack_desc_offset(int n) { return (5 * (size_t)n + 15) / 16 * 16; }
