@@ -849,11 +849,19 @@ int vslam_fpg_initialize(vslam_fpg* h, const uint8_t* left, const uint8_t* right
       bool ok = cudaStreamBeginCapture(lane.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
       if (ok) {
         h->capturing = true;
-        cudaMemcpyAsync(h->d_thr, h->h_thr, sizeof(int32_t) * g.n_regions, cudaMemcpyHostToDevice, lane.stream);
-        launch_repitch(g, lane.stage, lane.stage + lane.stage_bytes, (int)stride, h->b.image, 1, lane.stream,
-                       h->b.raw_count, 2 * g.n_regions);
-        ++h->launches;
-        run_detect_describe(h, lane, 0, 1, h->d_thr, true);
+        {   // the thresholds (and the mask clear of a multi-region grid) travel beside the repitch: FAST is the first
+            // kernel that needs either (a copy node in front of the chain costs ~3 us of a single frame)
+            const bool beside = use_branches(h, lane, 1);
+            cudaStream_t s = beside ? h->side_stream : lane.stream;
+            if (beside) order_after(h, lane.stream, s, 0);
+            cudaMemcpyAsync(h->d_thr, h->h_thr, sizeof(int32_t) * g.n_regions, cudaMemcpyHostToDevice, s);
+            if (g.n_regions > 1) cudaMemsetAsync(lane.mask, 0, (size_t)2 * g.rows * g.mask_words * sizeof(uint32_t), s);
+            launch_repitch(g, lane.stage, lane.stage + lane.stage_bytes, (int)stride, h->b.image, 1, lane.stream,
+                           h->b.raw_count, 2 * g.n_regions);
+            ++h->launches;
+            if (beside) order_after(h, s, lane.stream, 0);
+        }
+        run_detect_describe(h, lane, 0, 1, h->d_thr, true, true);
         status_download(h, lane);
         h->capturing = false;
         ok = cudaStreamEndCapture(lane.stream, &graph) == cudaSuccess && graph != nullptr;
