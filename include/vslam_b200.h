@@ -306,6 +306,18 @@ int vslam_fpg_frame_step_set_previous(vslam_fpg* h, const vslam_previous_point* 
 int vslam_fpg_frame_step(vslam_fpg* h, const uint8_t* left, const uint8_t* right, size_t stride_bytes, int localizing,
                          const double previous_to_current_prior[12], const vslam_frame_step_parameters* parameters,
                          vslam_frame_step_result* result);
+/* Landmark estimates for the points() the device holds (the frame that just returned), read by the NEXT frame's pose
+ * optimisation as StereoUVAligner::initialize does (stereouv_aligner.cpp:43-51): a point whose entry has
+ * information_scale != 0 is moved as `camera` (previous->cameraCoordinatesLeftLandmark()) with its information scaled by
+ * information_scale (the caller's 1 + log(landmark->numberOfUpdates())); 0 = no landmark, the point's own camera
+ * coordinates and identity information.  One entry per point, in the order of frame_points (n_tracks survivors, then the
+ * new points); entries are forgotten when the next frame replaces points().  Landmark refinement itself stays with the
+ * host or with the device-resident landmark map below. */
+typedef struct {
+  double camera[3];
+  double information_scale;
+} vslam_landmark_estimate;
+int vslam_fpg_frame_step_set_landmark_estimates(vslam_fpg* h, const vslam_landmark_estimate* estimates, int32_t n_points);
 /* Upload of the NEXT frame's images while the current frame runs (a host that replays a sequence knows them: the reference's
  * playback, executables/app.cpp, reads them from disk).  Asynchronous on a copy stream of the handle; the images must stay
  * valid (and should be page-locked, vslam_host_alloc) until the vslam_fpg_frame_step that consumes them returns.  Staged

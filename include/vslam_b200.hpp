@@ -169,6 +169,12 @@ class StereoFramePointGenerator {
   void prefetchFrame(const uint8_t* left, const uint8_t* right, size_t image_step) {
     check(vslam_fpg_frame_step_prefetch(_handle, left, right, image_step), "StereoFramePointGenerator::prefetchFrame");
   }
+  // landmark estimates of the points() the device holds (stereouv_aligner.cpp:43-51), one entry per point of the frame
+  // that just returned; read by the next trackFrame()
+  void setLandmarkEstimates(const std::vector<vslam_landmark_estimate>& estimates) {
+    check(vslam_fpg_frame_step_set_landmark_estimates(_handle, estimates.data(), (int32_t)estimates.size()),
+          "StereoFramePointGenerator::setLandmarkEstimates");
+  }
   // a new sequence: the next trackFrame() has no previous points
   void resetSequence() { check(vslam_fpg_frame_step_reset(_handle), "StereoFramePointGenerator::resetSequence"); }
 

@@ -33,6 +33,7 @@ class Stepwise:
         self.gen = api.StereoFramePointGenerator(cfg, cam)
         self.aligner = api.StereoUVAligner(acfg, max_points=8192)
         self.previous = np.zeros(0, api.PREVIOUS_POINT)
+        self.estimates = None          # LANDMARK_ESTIMATE per previous point (stereouv_aligner.cpp:43-51) or None
 
     def step(self, left, right, localizing, T_prior):
         gen, cam, acfg = self.gen, self.cam, self.acfg
@@ -48,10 +49,16 @@ class Stepwise:
         out.update(aligner_rounds=0, aligner_converged=0, errors=np.zeros(0), inliers=np.zeros(0, bool))
         if len(tracks):
             moving = np.ascontiguousarray(prev["camera_left"][tracks["index_previous"]])
+            omega = np.ones(len(tracks))
+            if self.estimates is not None:     # a landmark estimate is preferred, its information scaled (:43-51)
+                est = self.estimates[tracks["index_previous"]]
+                has = est["information_scale"] != 0
+                moving[has] = est["camera"][has]
+                omega[has] = est["information_scale"][has]
             fixed = np.stack([tracks["xl"], tracks["yl"], tracks["xr"], tracks["yr"]], 1).astype(np.float64)
             q = acfg.maximum_reliable_depth_meters / tracks["camera"][:, 2]
             wt = np.where(1.0 < q, 1.0, q) if acfg.enable_inverse_depth_as_information else np.ones(len(tracks))
-            self.aligner.initialize(moving, fixed, np.ones(len(tracks)), wt, cam.K, cam.baseline, cam.rows, cam.cols, T)
+            self.aligner.initialize(moving, fixed, omega, wt, cam.K, cam.baseline, cam.rows, cam.cols, T)
             self.aligner.converge(fused=True)
             T = np.array(self.aligner.previousToCurrent(), np.float64)
             keep = gen.prune_tracks(self.aligner, acfg.maximum_error_kernel)
@@ -73,6 +80,7 @@ class Stepwise:
         nxt["has_landmark"] = length >= self.min_track_length
         out["frame_points"] = nxt
         self.previous = nxt
+        self.estimates = None          # estimates belong to the points they were given for
         return out
 
     def close(self):
@@ -333,4 +341,42 @@ def test_frame_step_is_deterministic_under_repetition():
             first = h.hexdigest()
             assert got["n_tracks"] > 200
         assert h.hexdigest() == first, rep
+    gen.close()
+
+
+def test_frame_step_with_landmark_estimates():
+    """StereoUVAligner::initialize prefers a landmark estimate and scales its information with the landmark's updates
+    (stereouv_aligner.cpp:43-51): the host pushes the estimates for the points() the device holds, the next fused frame
+    aligns with them -- bit-identical to the stepwise calls fed the same moving points and information"""
+    cfg, acfg = configs.KITTI, configs.KITTI_ALIGNER
+    cam = synth.camera(cfg.camera)
+    frames = 6
+    world = synth.BandWorld(cam.cols, cam.rows, 83, max_frames=frames)
+    D, max_distance = 25, 40.0
+    ref = Stepwise(cfg, acfg, cam, D, max_distance)
+    gen = api.StereoFramePointGenerator(cfg, cam)
+    gen.frame_step_reset()
+    T = _prior(cam, 0.02)
+    rng = np.random.default_rng(4)
+    with_estimates = 0
+    for k in range(frames):
+        want = ref.step(*world.pair(k), k == 0, T)
+        got = gen.frame_step(*world.pair(k), k == 0, T, acfg, False, D, max_distance)
+        _compare(k, got, want, gen, True)
+        points = got["frame_points"]
+        # "landmarks": points tracked for at least two frames get an estimate close to their camera coordinates and the
+        # reference's information scale 1 + log(number of updates); frame 3 deliberately gives none
+        est = np.zeros(len(points), api.LANDMARK_ESTIMATE)
+        has = (points["reserved"] >= 2) & (rng.random(len(points)) < 0.8)
+        est["camera"][has] = points["camera_left"][has] + rng.normal(0, 0.01, (int(has.sum()), 3))
+        est["information_scale"][has] = 1.0 + np.log(points["reserved"][has].astype(np.float64))
+        if k != 3:
+            gen.frame_step_set_landmark_estimates(est)
+            ref.estimates = est
+            with_estimates += int(has.sum())
+    assert with_estimates > 500
+    # one entry per point, or the call is refused
+    with pytest.raises(api.VslamError):
+        gen.frame_step_set_landmark_estimates(est[:-1])
+    ref.close()
     gen.close()

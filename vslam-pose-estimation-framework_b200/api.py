@@ -28,6 +28,7 @@ TRACKED = np.dtype([("row", "<i4"), ("col", "<i4"), ("has_previous", "<i4"), ("r
 PREVIOUS_POINT = np.dtype([("camera_left", "<f8", (3,)), ("world", "<f8", (3,)), ("descriptor_left", "u1", (32,)),
                            ("descriptor_right", "u1", (32,)), ("epipolar_offset", "<i4"), ("has_landmark", "<i4"),
                            ("keypoint_size", "<f4"), ("reserved", "<i4")])
+LANDMARK_ESTIMATE = np.dtype([("camera", "<f8", (3,)), ("information_scale", "<f8")])
 TRACK = np.dtype([("index_previous", "<i4"), ("index_left", "<i4"), ("index_right", "<i4"), ("xl", "<f4"),
                   ("yl", "<f4"), ("xr", "<f4"), ("yr", "<f4"), ("distance", "<i4"), ("epipolar_offset", "<i4"),
                   ("projection_left", "<f4", (2,)), ("projection_right", "<f4", (2,)),
@@ -48,7 +49,7 @@ vslam_fpg_initialize vslam_fpg_get_features vslam_fpg_get_detection_stats vslam_
 vslam_fpg_reset_features vslam_fpg_graph_launch_count
 vslam_fpg_compute vslam_fpg_get_matches vslam_fpg_track vslam_fpg_recover_points vslam_fpg_prune_tracks
 vslam_fpg_frame_step vslam_fpg_frame_step_capacity vslam_fpg_frame_step_reset vslam_fpg_frame_step_set_previous
-vslam_fpg_frame_step_prefetch
+vslam_fpg_frame_step_prefetch vslam_fpg_frame_step_set_landmark_estimates
 vslam_fpg_set_profiling vslam_fpg_get_time_consumption vslam_fpg_batch_upload vslam_fpg_batch_run
 vslam_fpg_batch_download vslam_fpg_batch_process vslam_fpg_batch_linearize vslam_fpg_batch_get_systems
 vslam_fpg_get_kernel_profile vslam_fpg_batch_get_features vslam_fpg_stream vslam_fpg_synchronize
@@ -152,6 +153,7 @@ def lib():
         L.vslam_fpg_recover_points.argtypes = [vp, vp, i32, vp, C.c_double, C.c_double, C.c_double, vp, i32, vp]
         L.vslam_fpg_frame_step.argtypes = [vp, vp, vp, sz, C.c_int, vp, vp, vp]
         L.vslam_fpg_frame_step_prefetch.argtypes = [vp, vp, vp, sz]
+        L.vslam_fpg_frame_step_set_landmark_estimates.argtypes = [vp, vp, i32]
         L.vslam_fpg_frame_step_capacity.argtypes = [vp]
         L.vslam_fpg_frame_step_capacity.restype = i32
         L.vslam_fpg_frame_step_reset.argtypes = [vp]
@@ -366,6 +368,13 @@ class StereoFramePointGenerator:
     def frame_step_set_previous(self, previous):
         previous = np.ascontiguousarray(previous, PREVIOUS_POINT)
         _check(lib().vslam_fpg_frame_step_set_previous(self._h, _p(previous) if len(previous) else None, len(previous)))
+
+    def frame_step_set_landmark_estimates(self, estimates):
+        """one LANDMARK_ESTIMATE per point of the last frame's points(): information_scale != 0 -> the next frame's pose
+        optimisation moves `camera` (the landmark estimate in the previous camera frame) with that information scale"""
+        estimates = np.ascontiguousarray(estimates, LANDMARK_ESTIMATE)
+        _check(lib().vslam_fpg_frame_step_set_landmark_estimates(self._h, _p(estimates) if len(estimates) else None,
+                                                                 len(estimates)))
 
     def frame_step_prefetch(self, left, right):
         """upload of the NEXT frame's images while the current frame runs; consumed by frame_step(None, None, ...)"""

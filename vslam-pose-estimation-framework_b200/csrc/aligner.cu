@@ -629,6 +629,15 @@ __global__ void __launch_bounds__(kThreads, 1) converge_cluster_kernel(int n, Al
       fx[2] = (double)t->xr;
       fx[D - 1] = (double)t->yr;
       om[0] = 1.0;                     // :28 setIdentity
+      {                                // :43-51 a landmark estimate is preferred, its information grows with the updates
+        const LandmarkEstimate le = fill.estimates[t->index_previous];
+        if (le.information_scale != 0.0) {
+          m[0] = le.camera[0];
+          m[1] = le.camera[1];
+          m[2] = le.camera[2];
+          om[0] = le.information_scale;   // identity * (1 + log(numberOfUpdates)), evaluated by the host
+        }
+      }
       wt = 1.0;
       if (fill.inverse_depth_weight) { // :59-63 std::min(max_depth / depth, 1.0)
         const double ratio = fill.max_reliable_depth / t->camera[2];
@@ -889,7 +898,7 @@ cudaError_t launch_converge(int kind, int n, const AlignerBuffers& b, const Alig
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     const int32_t* no_device_count = nullptr;
-    const FrameFill no_fill = {nullptr, nullptr, nullptr, nullptr, 0.0, 0};
+    const FrameFill no_fill = {nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0};
     const FramePrune no_prune = {nullptr, nullptr, nullptr, 0.0};
     const cudaError_t e =
         kind == 0 ? cudaLaunchKernelEx(&cfg, converge_cluster_kernel<0>, n_arg, b_arg, cam_arg, p_arg, ctl, no_device_count, no_fill, no_prune)

@@ -85,6 +85,8 @@ struct vslam_fpg {
   int32_t* d_status = nullptr;   // [error_flag, pad | n_desc 2B | raw_count 2B x regions]; b.error_flag / n_desc / raw_count point into it
   int32_t* h_status = nullptr;   // pinned mirror; h_flag / h_n_desc / h_counts point into it
   int32_t* d_step_bins = nullptr;       // [rows_bin * cols_bin + 1] winners of the match replay (fused frame)
+  LandmarkEstimate* d_step_estimates = nullptr;   // [step_cap] landmark estimates of the device-resident points()
+  int32_t step_points = 0;              // points() the device holds for the next fused frame
   int32_t* h_status_device = nullptr;   // the same words as the device addresses them (written by the fused frame)
   // state of the last single-pair initialize / last batch
   bool initialized = false;
@@ -745,7 +747,7 @@ int vslam_fpg_destroy(vslam_fpg* h) {
   invalidate_step_graphs(h);
   cudaFree(h->d_step); cudaFree(h->d_step_ctl); cudaFree(h->d_step_planes); cudaFree(h->d_step_errors);
   cudaFree(h->d_step_inliers); cudaFree(h->d_step_system); cudaFree(h->d_step_track_length); cudaFree(h->d_step_kept_pos);
-  cudaFree(h->d_step_bins);
+  cudaFree(h->d_step_bins); cudaFree(h->d_step_estimates);
   for (auto& b : h->step_inbox) cudaFree(b);
   for (auto& e : h->step_inbox_ev)
     if (e) cudaEventDestroy(e);
@@ -1156,6 +1158,8 @@ static int setup_frame_step(vslam_fpg* h) {
   CUDA_TRY(cudaMalloc((void**)&h->d_step_track_length, sizeof(int32_t) * C));
   CUDA_TRY(cudaMalloc((void**)&h->d_step_kept_pos, sizeof(int32_t) * C));
   CUDA_TRY(cudaMalloc((void**)&h->d_step_bins, sizeof(int32_t) * ((size_t)h->g.rows_bin * h->g.cols_bin + 1)));
+  CUDA_TRY(cudaMalloc((void**)&h->d_step_estimates, sizeof(LandmarkEstimate) * C));
+  CUDA_TRY(cudaMemset(h->d_step_estimates, 0, sizeof(LandmarkEstimate) * C));
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   size_t off = up(sizeof(FrameStepHeader));
   h->step_off_tracks = off;        off = up(off + sizeof(TrackRecord) * C);
@@ -1214,6 +1218,7 @@ static FrameStepBuffers frame_step_buffers(vslam_fpg* h) {
   f.h_lost = reinterpret_cast<int32_t*>(d + h->step_off_lost);
   f.h_points = reinterpret_cast<FramePointRecord*>(d + h->step_off_points);
   f.h_frame_points = reinterpret_cast<PreviousPoint*>(d + h->step_off_frame_points);
+  f.estimates = h->d_step_estimates;
   f.d_status = h->d_status;
   f.d_raw_count = h->b.raw_count;
   f.h_status = h->h_status_device;
@@ -1292,8 +1297,8 @@ static int issue_frame_step(vslam_fpg* h, Lane& lane, size_t stride, const vslam
   gp.max_iterations = p.aligner.maximum_number_of_iterations;
   gp.inlier_gate = p.aligner.minimum_number_of_inliers;                          // stereouv_aligner.cpp:224
   // StereoUVAligner::initialize (:124-126 / :355-356) is the head of the kernel, _prunePoints (:437-472) its tail
-  const FrameFill fill = {h->d_tracks, h->d_previous, h->d_step_track_length, h->d_step, fp.max_reliable_depth,
-                          fp.inverse_depth_weight};
+  const FrameFill fill = {h->d_tracks, h->d_previous, h->d_step_estimates, h->d_step_track_length, h->d_step,
+                          fp.max_reliable_depth, fp.inverse_depth_weight};
   const FramePrune prune = {h->d_tracked, h->d_step_kept_pos, h->d_step, fp.error_kernel};
   CUDA_TRY(launch_converge_frame(f.aligner, cam, gp, h->d_step_ctl, h->track_scratch.stats, h->step_cluster_blocks, fill,
                                  prune, lane.stream));                           // :357
@@ -1332,6 +1337,7 @@ int vslam_fpg_frame_step_reset(vslam_fpg* h) {
   CUDA_TRY(cudaMemsetAsync(h->d_step, 0, sizeof(FrameStepState), h->lanes[0].stream));
   if (h->copy_stream) CUDA_TRY(cudaStreamSynchronize(h->copy_stream));   // a new sequence: staged frames are dropped
   h->step_inbox_count = 0;
+  h->step_points = 0;
   return VSLAM_OK;
 }
 
@@ -1345,7 +1351,25 @@ int vslam_fpg_frame_step_set_previous(vslam_fpg* h, const vslam_previous_point* 
   if (n_previous)
     CUDA_TRY(cudaMemcpyAsync(h->d_previous, previous, sizeof(PreviousPoint) * (size_t)n_previous, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(&h->d_step->n_previous, &n_previous, sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  if (n_previous) CUDA_TRY(cudaMemsetAsync(h->d_step_estimates, 0, sizeof(LandmarkEstimate) * (size_t)n_previous, s));
   CUDA_TRY(cudaStreamSynchronize(s));   // the caller's buffer and the stack variable may go away
+  h->step_points = n_previous;
+  return VSLAM_OK;
+}
+
+int vslam_fpg_frame_step_set_landmark_estimates(vslam_fpg* h, const vslam_landmark_estimate* estimates, int32_t n_points) {
+  if (!h || n_points < 0 || (n_points > 0 && !estimates)) return fail(VSLAM_ERR_INVALID_ARGUMENT, "bad landmark estimates");
+  int rc = setup_frame_step(h);
+  if (rc) return rc;
+  if (n_points != h->step_points)
+    return fail(VSLAM_ERR_STATE, "%d landmark estimates for the %d points the device holds (one entry per point of the last frame's points())",
+                n_points, h->step_points);
+  if (n_points == 0) return VSLAM_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->lanes[0].stream;
+  static_assert(sizeof(vslam_landmark_estimate) == sizeof(LandmarkEstimate), "vslam_landmark_estimate layout");
+  CUDA_TRY(cudaMemcpyAsync(h->d_step_estimates, estimates, sizeof(LandmarkEstimate) * (size_t)n_points, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));   // the caller's buffer may go away
   return VSLAM_OK;
 }
 
@@ -1504,12 +1528,14 @@ int vslam_fpg_frame_step(vslam_fpg* h, const uint8_t* left, const uint8_t* right
   if ((rc = check_flag(h)) || hd->overflow) {
     cudaMemset(h->b.error_flag, 0, sizeof(int32_t));
     cudaMemset(h->d_step, 0, sizeof(FrameStepState));   // the device-resident points are not usable: a new sequence
+    h->step_points = 0;
     h->initialized = false;
     if (rc) return rc;
     return fail(VSLAM_ERR_CAPACITY, "more than %d points in a frame: use the stepwise calls", h->step_cap);
   }
   finish_detection(h, L);
   h->n_device_tracks = hd->n_kept;
+  h->step_points = hd->n_points;
   std::memset(out, 0, sizeof(*out));
   out->n_left = h->h_n_desc[0];
   out->n_right = h->h_n_desc[1];

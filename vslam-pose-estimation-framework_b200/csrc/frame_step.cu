@@ -85,6 +85,7 @@ __device__ __forceinline__ void frame_assemble_block(const Geometry& g, const Fr
     }
     __syncthreads();
     if (count && !overflow) {
+      if (tid < count) f.estimates[first + tid].information_scale = 0.0;   // points() of the new frame: no estimate yet
       copy16(f.previous + first, s_points, sizeof(PreviousPoint) * (size_t)count, tid, kAssembleThreads);
       if (p.publish_frame_points)
         copy16(f.h_frame_points + first, s_points, sizeof(PreviousPoint) * (size_t)count, tid, kAssembleThreads);
@@ -114,6 +115,7 @@ __device__ __forceinline__ void frame_assemble_block(const Geometry& g, const Fr
     }
     __syncthreads();
     if (!overflow) {
+      if (tid < count) f.estimates[n_kept + k0 + tid].information_scale = 0.0;
       copy16(f.previous + n_kept + k0, s_points, sizeof(PreviousPoint) * (size_t)count, tid, kAssembleThreads);
       if (p.publish_frame_points)
         copy16(f.h_frame_points + n_kept + k0, s_points, sizeof(PreviousPoint) * (size_t)count, tid, kAssembleThreads);

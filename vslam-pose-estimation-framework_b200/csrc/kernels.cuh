@@ -196,9 +196,18 @@ struct GnControl {
 // fused frame: StereoUVAligner::initialize (reference src/aligners/stereouv_aligner.cpp:26-64, the branch without a
 // landmark estimate) as the head of the cluster Gauss-Newton kernel -- thread k reads track k and its previous point
 // instead of planes another kernel would have to write; the control block of converge() starts from the motion prior.
+// the landmark estimate of a point of the previous frame (stereouv_aligner.cpp:43-51): when information_scale != 0 the
+// aligner moves `camera` (previous->cameraCoordinatesLeftLandmark()) instead of the point's own camera coordinates and
+// scales its information by information_scale (the host's 1 + log(landmark->numberOfUpdates())).  == vslam_landmark_estimate
+struct LandmarkEstimate {
+  double camera[3];
+  double information_scale;
+};
+
 struct FrameFill {
   const TrackRecord* tracks;       // [cap] track() output; nullptr: the correspondences come from AlignerBuffers
   const PreviousPoint* previous;   // points() of the previous frame
+  const LandmarkEstimate* estimates;   // [cap] per point of the previous frame (vslam_fpg_frame_step_set_landmark_estimates)
   int32_t* track_length;           // [cap] per track: trackLength() of its previous point (for the frame's points())
   FrameStepState* state;           // T_prior in; overflow, n_kept, inliers_only out
   double max_reliable_depth;       // _maximum_reliable_depth_meters (slam_assembly.cpp:70)
@@ -283,6 +292,7 @@ struct FrameStepBuffers {
   int32_t* h_lost;                  // [cap]
   FramePointRecord* h_points;       // [out_cap]
   PreviousPoint* h_frame_points;    // [cap] points() of this frame (the next frame's previous points)
+  LandmarkEstimate* estimates;      // [cap] landmark estimates of points(): a new frame's points have none until the host says so
   // detection status of the frame ({error flag, pad, n_desc[2]} and the raw FAST counts per region), mirrored into the
   // handle's pinned status words by the last block of frame_assemble_kernel (no copy node at the end of the graph)
   const int32_t* d_status;          // [4]
