@@ -54,3 +54,14 @@ def test_struct_layouts_match_the_header(tmp_path):
         if last:
             assert seen[name][1] == offset, (name, last, seen[name][1], offset)
 
+
+
+def test_cpp_hosts_compile_and_link_without_a_gpu(tmp_path):
+    """the C++14 layer over the C ABI (include/vslam_b200.hpp) and its two hosts -- the consumer check and the sequence
+    runner bench.py times -- build and link against the in-tree library on a CPU-only box (they run in the GPU tests)"""
+    pkg = os.path.join(ROOT, "vslam-pose-estimation-framework_b200")
+    for source in ("tests/cpp/host_api_check.cpp", "tools/sequence_runner.cpp"):
+        exe = tmp_path / os.path.basename(source).replace(".cpp", "")
+        subprocess.check_call(["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-O1", "-I", os.path.join(ROOT, "include"),
+                               os.path.join(ROOT, source), "-o", str(exe), "-L", pkg, "-lvslam_b200", "-Wl,-rpath," + pkg])
+        assert exe.exists()
