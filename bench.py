@@ -677,6 +677,9 @@ def native_sequence(cfg, cam, frames, warmup=4, acfg=None, passes=1, device=0, f
         if res.returncode != 0:
             return None
         r = json.loads(res.stdout.strip().splitlines()[-1])
+        for line in res.stderr.splitlines():      # VSLAM_RUNNER_PROFILE=1: device us per stage of the fused frame
+            if line.startswith("device us per frame"):
+                r["stage_profile"] = line
         r["host"] = "C++14 (tools/sequence_runner.cpp)"
         if fused:
             r["what"] = ("vslam_fpg_frame_step: the frame as ONE graph launch and one synchronisation, points() of the "

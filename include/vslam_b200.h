@@ -347,8 +347,10 @@ int vslam_fpg_get_matches(vslam_fpg* h, vslam_framepoint* matches, int32_t capac
 /* enabled > 0: on (batched calls then run serialised on one stream); 0: off; < 0: off and reset accumulators */
 int vslam_fpg_set_profiling(vslam_fpg* h, int enabled);
 /* accumulated device milliseconds and launch counts per kernel while profiling was on, in this order:
- * fast_nms, compact, blur, describe, match, select, linearize_pairs, track (search + resolve) */
-#define VSLAM_FPG_KERNELS 8
+ * fast_nms, compact, blur, describe, match, select, linearize_pairs, track (search + resolve + emit),
+ * frame aligner (StereoUVAligner initialize + converge + _prunePoints inside vslam_fpg_frame_step).  With profiling on,
+ * vslam_fpg_frame_step runs its kernels as ONE chain (no parallel branches) with the timing events between them. */
+#define VSLAM_FPG_KERNELS 9
 int vslam_fpg_get_kernel_profile(vslam_fpg* h, double* milliseconds, int64_t* launches);
 int vslam_fpg_get_time_consumption(vslam_fpg* h, double* keypoint_detection, double* descriptor_extraction,
                                    double* point_triangulation);

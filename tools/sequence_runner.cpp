@@ -100,6 +100,10 @@ int main(int argc, char** argv) {
       return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count();
     };
     std::vector<int32_t> lost;
+    // VSLAM_RUNNER_PROFILE=1: device time per stage of the fused frame (CUDA events between the kernels; the frame then
+    // runs as ONE chain without parallel branches, so its total is not the number to quote)
+    const bool stage_profile = fused && std::getenv("VSLAM_RUNNER_PROFILE") != nullptr;
+    if (stage_profile) vslam_fpg_set_profiling(generator.handle(), 1);
     for (int pass = 0; pass < passes; ++pass) {
     have_previous = false;
     if (fused) generator.resetSequence();
@@ -203,6 +207,18 @@ int main(int argc, char** argv) {
     }
     }
     const int timed = n_frames * passes - warmup;
+    if (stage_profile) {
+      double ms[VSLAM_FPG_KERNELS];
+      int64_t launches[VSLAM_FPG_KERNELS];
+      vslam_fpg_get_kernel_profile(generator.handle(), ms, launches);
+      const char* names[VSLAM_FPG_KERNELS] = {"fast_nms", "compact", "blur", "describe", "match", "select", "linearize_pairs",
+                                              "track", "frame_aligner"};
+      const long frames_total = (long)passes * n_frames;
+      std::fprintf(stderr, "device us per frame (%ld frames, one chain):", frames_total);
+      for (int i = 0; i < VSLAM_FPG_KERNELS; ++i)
+        if (launches[i]) std::fprintf(stderr, " %s %.1f", names[i], ms[i] * 1000.0 / frames_total);
+      std::fprintf(stderr, "\n");
+    }
     std::printf("{\"frames_per_s\": %.3f, \"ms_per_frame\": %.6f, \"mean_previous_points\": %.2f, \"mean_tracks\": %.2f, "
                 "\"mean_new_points\": %.2f, \"frames\": %d, \"us_initialize_with_feature_download\": %.1f, \"us_track\": %.1f, "
                 "\"us_align\": %.1f, \"us_compute\": %.1f, \"us_assemble_previous_points\": %.1f, \"mean_aligner_rounds\": %.2f, "

@@ -506,7 +506,7 @@ class StereoFramePointGenerator:
                                              int(bool(localizing)), _p(out), out.shape[1], _p(counts)))
         return out, counts
 
-    KERNELS = ("fast_nms", "compact", "blur", "describe", "match", "select", "linearize_pairs", "track")
+    KERNELS = ("fast_nms", "compact", "blur", "describe", "match", "select", "linearize_pairs", "track", "frame_aligner")
 
     def kernel_profile(self):
         """{kernel: (accumulated device ms, launches)} while profiling was on"""

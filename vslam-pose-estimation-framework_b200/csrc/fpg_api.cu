@@ -43,7 +43,7 @@ struct Lane {
 
 // profiling: events at the kernel boundaries of one chunk (single lane, serialised)
 enum { kEvFast0, kEvFast1, kEvCompact1, kEvBlur1, kEvDescribe1, kEvMatch0, kEvMatch1, kEvSelect1, kEvLin0, kEvLin1, kEvTrack0, kEvTrack1, kNumEv };
-enum { kKFast, kKCompact, kKBlur, kKDescribe, kKMatch, kKSelect, kKLinearize, kKTrack, kNumKernels };
+enum { kKFast, kKCompact, kKBlur, kKDescribe, kKMatch, kKSelect, kKLinearize, kKTrack, kKFrameAligner, kNumKernels };
 static_assert(kNumKernels == VSLAM_FPG_KERNELS, "kernel profile size");
 
 struct StageClock {
@@ -1072,7 +1072,7 @@ int vslam_fpg_track(vslam_fpg* h, const vslam_previous_point* previous, int32_t 
   }
   CUDA_TRY(cudaStreamSynchronize(lane.stream));
   CUDA_TRY(cudaGetLastError());
-  if (h->profiling) add_interval(h, kKTrack, kEvTrack0, kEvTrack1, n_previous > 0 ? 2 : 1);
+  if (h->profiling) add_interval(h, kKTrack, kEvTrack0, kEvTrack1, n_previous > 0 ? 3 : 1);
   const int nt = h->h_track_stats[0], nl = h->h_track_stats[1];
   h->n_device_tracks = nt;
   if (n_tracks) *n_tracks = nt;
@@ -1524,7 +1524,10 @@ int vslam_fpg_frame_step(vslam_fpg* h, const uint8_t* left, const uint8_t* right
   if (!complete) CUDA_TRY(cudaStreamSynchronize(lane.stream));
   CUDA_TRY(cudaGetLastError());
   collect_clock(h, true, true);
-  if (h->profiling) add_interval(h, kKTrack, kEvTrack0, kEvTrack1, 2);
+  if (h->profiling) {
+    add_interval(h, kKTrack, kEvTrack0, kEvTrack1, 3);
+    add_interval(h, kKFrameAligner, kEvTrack1, kEvMatch0, 1);   // (one chain: the aligner sits between track() and the match)
+  }
   if ((rc = check_flag(h)) || hd->overflow) {
     cudaMemset(h->b.error_flag, 0, sizeof(int32_t));
     cudaMemset(h->d_step, 0, sizeof(FrameStepState));   // the device-resident points are not usable: a new sequence
