@@ -4,8 +4,8 @@
 // next track() reads), moved to the device so that a frame is ONE graph launch and one synchronisation.  Counts travel
 // through FrameStepState (device memory), never through kernel arguments.
 //
-//   (StereoUVAligner::initialize over the tracks is written by track_resolve_kernel's ordered output, track.cu;
-//    _prunePoints on the bin pre-load records runs as the tail of converge_cluster_kernel, aligner.cu)
+//   (StereoUVAligner::initialize over the tracks is the head of converge_cluster_kernel, _prunePoints on the bin
+//    pre-load records its tail: aligner.cu, FrameFill / FramePrune)
 //   frame_assemble_kernel       points() of the frame (surviving tracks, then the new framepoints, with their descriptors)
 //                               replace the previous points in place; everything the host reads is written into the
 //                               handle's pinned, device-mapped result block
