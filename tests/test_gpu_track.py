@@ -94,12 +94,12 @@ def test_track_and_following_compute_match_oracle(cfg_name, by_appearance, D, no
     gen.close()
 
 
-@pytest.mark.parametrize("max_keypoints", [0, 40000])
+@pytest.mark.parametrize("max_keypoints", [0, 4097, 40000])
 def test_track_heavy_conflicts(max_keypoints):
     """every previous point three times, in shuffled order, with a loose appearance gate and the widest window: hundreds
     of points pick a feature a lower-indexed point already consumed.  With the default capacity the resolver keeps its
-    claims, tentative results and worklist in shared memory; a handle created for 40 000 keypoints per image does not fit
-    (320 KB of claims) and runs the same rounds on the global scratch."""
+    claims, tentative results and worklist in shared memory (also with an odd capacity, which shifts the layout); a handle
+    created for 40 000 keypoints per image does not fit (320 KB of claims) and runs the same rounds on the global scratch."""
     cfg = configs.KITTI_FAST
     cam, world, ora, gen, prev = _setup(cfg, seed=3, max_keypoints=max_keypoints)
     rng = np.random.default_rng(0)

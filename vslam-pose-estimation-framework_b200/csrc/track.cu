@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(kResolveThreads) track_resolve_kernel(
     claim_r = claim_l + smem_claims;
   }
   if (smem_points) {                 // (n_previous <= smem_points: launch_track)
-    int4* s_tentative = reinterpret_cast<int4*>(s_dyn + sizeof(int32_t) * 2 * (size_t)smem_claims);
+    int4* s_tentative = reinterpret_cast<int4*>(s_dyn + ((sizeof(int32_t) * 2 * (size_t)smem_claims + 15) & ~(size_t)15));
     for (int u = tid; u < n_previous; u += kResolveThreads) s_tentative[u] = tentative[u];
     tentative = s_tentative;
     worklist = reinterpret_cast<int32_t*>(s_tentative + smem_points);
@@ -578,9 +578,11 @@ void launch_track(const Geometry& g, const StereoParams& sp, const Buffers& b, i
   const int smem_limit = std::max(cached, 0);
   size_t smem = 0;
   int smem_claims = 0, smem_points = 0;
-  if (sizeof(int32_t) * 2 * (size_t)g.cap <= (size_t)smem_limit) {
+  const size_t claims_bytes = (sizeof(int32_t) * 2 * (size_t)g.cap + 15) & ~(size_t)15;   // (the int4 results behind the
+                                                                                         // claims stay 16-byte aligned)
+  if (claims_bytes <= (size_t)smem_limit) {
     smem_claims = g.cap;
-    smem = sizeof(int32_t) * 2 * (size_t)g.cap;
+    smem = claims_bytes;
     const size_t points = (sizeof(int4) + sizeof(int32_t)) * (size_t)n_previous;
     if (n_previous > 0 && smem + points <= (size_t)smem_limit) {
       smem_points = n_previous;
