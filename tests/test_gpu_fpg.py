@@ -201,7 +201,8 @@ def test_batched_pairs_with_epipolar_offsets_count_every_pass():
     left, right = synth.band_world_batch(cfg.camera, range(60, 60 + n))
     right = np.roll(right, 1, axis=1).copy()       # true matches sit one row lower in the right images
     right[:, :2] = 96
-    gen = api.StereoFramePointGenerator(cfg, cam, max_batch=n)
+    # (a keypoint capacity that is not a multiple of 4: the per-pair shares of the byte-flag arrays are then unaligned)
+    gen = api.StereoFramePointGenerator(cfg, cam, max_batch=n, max_keypoints=4099)
     out, counts = gen.batch_process(left, right, True)
     _, nf, nm, _, _ = gen.batch_download(n)
     later = 0

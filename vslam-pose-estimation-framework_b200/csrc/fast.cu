@@ -498,8 +498,13 @@ __global__ void __launch_bounds__(kCompactFrameThreads) compact_frame_kernel(
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ct = rank * kCompactFrameThreads + tid;   // thread index within the image's cluster
   {   // a new frame: no feature is pruned yet (see compact_kernel)
-    uint32_t* flags = reinterpret_cast<uint32_t*>(((img & 1) ? consumed_r : pruned_l) + (size_t)(img >> 1) * g.cap);
-    for (int i = ct; i < (g.cap + 3) / 4; i += kCompactFrameThreads * kCompactFrameBlocks) flags[i] = 0u;   // (allocations are 256-byte aligned)
+    uint8_t* flags = ((img & 1) ? consumed_r : pruned_l) + (size_t)(img >> 1) * g.cap;
+    if ((g.cap & 3) == 0) {   // (the allocations are 256-byte aligned: with a capacity that is a multiple of 4 so is every pair's share)
+      uint32_t* words = reinterpret_cast<uint32_t*>(flags);
+      for (int i = ct; i < g.cap / 4; i += kCompactFrameThreads * kCompactFrameBlocks) words[i] = 0u;
+    } else {
+      for (int i = ct; i < g.cap; i += kCompactFrameThreads * kCompactFrameBlocks) flags[i] = 0;
+    }
   }
   const uint4* m = reinterpret_cast<const uint4*>(mask + (size_t)img * g.rows * g.mask_words);
   const int per_row = g.mask_words >> 2, total = per_row * g.rows;
