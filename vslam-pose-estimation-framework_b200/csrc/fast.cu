@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(256) compact_kernel(Geometry g, const uint32_t
 
 // K2 for a single frame: ONE CLUSTER of 8 CTAs per image instead of one thread per row (the batched kernel above keeps
 // 2 SMs busy with a frame and is bound by its own instruction latency there: 14 us per KITTI frame, 37 us per 1920 x 1080
-// frame, ncu profiles/r2u).  The mask of an image is a row-major list of uint4 (mask_words is a multiple of 4); thread t
+// frame, profiles/r2_frame/r2u_prof_frame_step_summary.txt).  The mask of an image is a row-major list of uint4 (mask_words is a multiple of 4); thread t
 // of the cluster's 2048 owns the Q consecutive uint4 from t * Q, loads them all at once (independent loads: one memory
 // round trip), counts its keypoints; a block scan, the block totals exchanged through distributed shared memory and ONE
 // cluster barrier give its offset in the (row, col)-sorted list, and it emits its own bits in order.  The thread that
